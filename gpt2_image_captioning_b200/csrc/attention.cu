@@ -1,0 +1,289 @@
+// Attention kernels of the caption path (head_dim 64 for GPT-2; 64..160 for the transformer mapper).
+//
+//  attn_decode  : one new query per (row, head) against the KV cache -- the HBM-bound half of a decode step.
+//                 Replaces GPT2Attention.forward's cache `torch.cat` + SDPA for T_q = 1
+//                 (HF:models/gpt2/modeling_gpt2.py:185-220, HF:cache_utils.py:102-121).  One warp per (row, head);
+//                 K/V rows are 128 B (bf16) / 256 B (fp32): 8 / 16 lanes take one key with 128-bit loads, so a warp
+//                 iteration reads 4 / 2 consecutive keys = 512 contiguous bytes.  fp32 scores, warp-shuffle softmax.
+//                 The new token's K/V are appended to the cache in the same kernel (no separate cat/copy).
+//  attn_prefill : causal attention over the P prefix tokens of a row, writing K/V into the cache (prefill).
+//  attn_encoder : bidirectional attention of nn.TransformerEncoderLayer's MHA (torch:nn/modules/transformer.py:946-950)
+//                 for the transformer mapping network (src/models.py:129-139), head_dim = d/8.
+//  kv_reorder   : beam-search cache gather, index_select(0, beam_idx) per layer (HF:cache_utils.py:81-85).
+//
+// KV cache layout (one layer): K [rows][H][T_max][64], V the same; element type T (bf16 or fp32).
+#include "kernels.cuh"
+
+namespace gic {
+
+constexpr int HD = 64;  // GPT-2 head_dim (small/medium/large: n_embd / n_head = 64)
+
+template <typename T>
+__global__ void __launch_bounds__(128) attn_decode_kernel(const T* __restrict__ qkv, T* kcache, T* vcache, ActOut out,
+                                                          const int* __restrict__ d_pos, int rows, int H, int t_max) {
+  constexpr int VEC = 16 / sizeof(T);   // elements per 128-bit load
+  constexpr int LPK = HD / VEC;         // lanes per key: 8 (bf16) / 16 (fp32)
+  constexpr int KPI = 32 / LPK;         // keys per warp iteration
+  extern __shared__ float smem_scores[];  // [warps][t_max]
+  const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+  if (wid >= rows * H) return;
+  const int row = wid / H, h = wid % H;
+  const int d = H * HD;
+  const int pos = *d_pos;  // tokens already cached == position of the new token
+  const int ctx = pos + 1;
+  const int g = lane / LPK, sub = lane % LPK;
+  float* sc = smem_scores + (size_t)warp_in_block * t_max;
+
+  const T* qrow = qkv + (size_t)row * 3 * d + h * HD;
+  T* kbase = kcache + ((size_t)row * H + h) * t_max * HD;
+  T* vbase = vcache + ((size_t)row * H + h) * t_max * HD;
+
+  // append the new token's K,V (one 16-byte vector per lane of group 0)
+  if (g == 0) {
+    Vec16<T> kv;
+    kv.load(qrow + d + sub * VEC);
+    kv.store(kbase + (size_t)pos * HD + sub * VEC);
+    kv.load(qrow + 2 * d + sub * VEC);
+    kv.store(vbase + (size_t)pos * HD + sub * VEC);
+  }
+  float qf[VEC];
+  {
+    Vec16<T> qv;
+    qv.load(qrow + sub * VEC);
+    qv.unpack(qf);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) qf[i] *= 0.125f;  // 1/sqrt(64), HF :211-220 (sdpa default scale)
+  }
+  __syncwarp();  // orders the append before the cache reads below (same warp)
+
+  // ---- scores ----
+  float mx = -INFINITY;
+  constexpr int UNR = 4;
+  for (int j0 = 0; j0 < ctx; j0 += KPI * UNR) {
+    Vec16<T> kv[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + u * KPI + g;
+      if (j < ctx) kv[u].load(kbase + (size_t)j * HD + sub * VEC);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + u * KPI + g;
+      float s = 0.f;
+      if (j < ctx) {
+        float kf[VEC];
+        kv[u].unpack(kf);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) s = fmaf(qf[i], kf[i], s);
+      }
+#pragma unroll
+      for (int o = LPK / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (j < ctx) {
+        if (sub == 0) sc[j] = s;
+        mx = fmaxf(mx, s);
+      }
+    }
+  }
+  mx = warp_max(mx);
+  __syncwarp();
+  float sum = 0.f;
+  for (int j = lane; j < ctx; j += 32) {
+    const float p = expf(sc[j] - mx);
+    sc[j] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+
+  // ---- P.V ----
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  for (int j0 = 0; j0 < ctx; j0 += KPI * UNR) {
+    Vec16<T> vv[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + u * KPI + g;
+      if (j < ctx) vv[u].load(vbase + (size_t)j * HD + sub * VEC);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + u * KPI + g;
+      if (j < ctx) {
+        float vf[VEC];
+        vv[u].unpack(vf);
+        const float p = sc[j];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = LPK; o < 32; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  if (g == 0) {
+    const float inv = 1.0f / sum;
+    const size_t o0 = (size_t)row * d + h * HD + sub * VEC;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) out.write(o0 + i, acc[i] * inv);
+  }
+}
+
+template <typename T>
+int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows, int H, int t_max, cudaStream_t st) {
+  const int warps = rows * H;
+  const int blocks = ceil_div(warps, 4);
+  const size_t smem = (size_t)4 * t_max * sizeof(float);
+  GIC_REQUIRE(smem <= 48 * 1024, "attn_decode: t_max %d too large", t_max);
+  attn_decode_kernel<T><<<blocks, 128, smem, st>>>(qkv, kcache, vcache, out, d_pos, rows, H, t_max);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  return GIC_OK;
+}
+template int launch_attn_decode<float>(const float*, float*, float*, ActOut, const int*, int, int, int, cudaStream_t);
+template int launch_attn_decode<bf16>(const bf16*, bf16*, bf16*, ActOut, const int*, int, int, int, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sequence attention: one block per (row, head), K/V of the row staged in shared memory as fp32, one warp per query.
+//   CAUSAL + cache write  -> GPT-2 prefill over the prefix tokens
+//   bidirectional          -> transformer-mapper encoder layers
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int HDIM, bool CAUSAL>
+__global__ void __launch_bounds__(128) attn_seq_kernel(const T* __restrict__ qkv, T* kcache, T* vcache, ActOut out, int S, int H,
+                                                       int t_max, float scale) {
+  constexpr int DPL = HDIM / 32;  // dims per lane
+  extern __shared__ float sm[];
+  float* Ks = sm;                       // [S][HDIM]
+  float* Vs = Ks + (size_t)S * HDIM;    // [S][HDIM]
+  float* Sc = Vs + (size_t)S * HDIM;    // [4 warps][S]
+  const int row = blockIdx.x / H, h = blockIdx.x % H;
+  const int d = H * HDIM;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* base = qkv + (size_t)row * S * 3 * d + h * HDIM;
+
+  for (int i = threadIdx.x; i < S * HDIM; i += blockDim.x) {
+    const int t = i / HDIM, c = i % HDIM;
+    const T kv = base[(size_t)t * 3 * d + d + c];
+    const T vv = base[(size_t)t * 3 * d + 2 * d + c];
+    Ks[i] = to_f32(kv);
+    Vs[i] = to_f32(vv);
+    if (kcache) {
+      const size_t ci = (((size_t)row * H + h) * t_max + t) * HDIM + c;
+      kcache[ci] = kv;
+      vcache[ci] = vv;
+    }
+  }
+  __syncthreads();
+
+  float* sc = Sc + (size_t)warp * S;
+  for (int t = warp; t < S; t += 4) {
+    float q[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) q[i] = to_f32(base[(size_t)t * 3 * d + lane + 32 * i]) * scale;
+    const int n = CAUSAL ? t + 1 : S;
+    float mx = -INFINITY;
+    for (int j = 0; j < n; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) s = fmaf(q[i], Ks[j * HDIM + lane + 32 * i], s);
+      s = warp_sum(s);
+      if (lane == 0) sc[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    __syncwarp();
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) {
+      const float p = expf(sc[j] - mx);
+      sc[j] = p;
+      sum += p;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    float o[DPL];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) o[i] = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const float p = sc[j];
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) o[i] = fmaf(p, Vs[j * HDIM + lane + 32 * i], o[i]);
+    }
+    const float inv = 1.0f / sum;
+    const size_t o0 = ((size_t)row * S + t) * d + h * HDIM;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) out.write(o0 + lane + 32 * i, o[i] * inv);
+    __syncwarp();
+  }
+}
+
+template <typename T, int HDIM, bool CAUSAL>
+static int launch_attn_seq(const T* qkv, T* kcache, T* vcache, ActOut out, int B, int S, int H, int t_max, cudaStream_t st) {
+  const size_t smem = ((size_t)2 * S * HDIM + 4 * S) * sizeof(float);
+  GIC_REQUIRE(smem <= 200 * 1024, "attention: sequence %d x head_dim %d does not fit in shared memory", S, HDIM);
+  auto kern = attn_seq_kernel<T, HDIM, CAUSAL>;
+  if (smem > 48 * 1024) GIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<B * H, 128, smem, st>>>(qkv, kcache, vcache, out, S, H, t_max, 1.0f / sqrtf((float)HDIM));
+  GIC_CHECK_CUDA(cudaGetLastError());
+  return GIC_OK;
+}
+
+template <typename T>
+int launch_attn_prefill(const T* qkv, T* kcache, T* vcache, ActOut out, int B, int P, int H, int t_max, cudaStream_t st) {
+  GIC_REQUIRE(P <= t_max, "attn_prefill: P %d > t_max %d", P, t_max);
+  return launch_attn_seq<T, 64, true>(qkv, kcache, vcache, out, B, P, H, t_max, st);
+}
+template int launch_attn_prefill<float>(const float*, float*, float*, ActOut, int, int, int, int, cudaStream_t);
+template int launch_attn_prefill<bf16>(const bf16*, bf16*, bf16*, ActOut, int, int, int, int, cudaStream_t);
+
+template <typename T>
+int launch_attn_encoder(const T* qkv, ActOut out, int B, int S, int H, int hd, cudaStream_t st) {
+  switch (hd) {
+    case 32: return launch_attn_seq<T, 32, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
+    case 64: return launch_attn_seq<T, 64, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
+    case 96: return launch_attn_seq<T, 96, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
+    case 128: return launch_attn_seq<T, 128, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
+    case 160: return launch_attn_seq<T, 160, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
+    default: set_error("attn_encoder: unsupported head_dim %d (32/64/96/128/160)", hd); return GIC_ERR_UNSUPPORTED;
+  }
+}
+template int launch_attn_encoder<float>(const float*, ActOut, int, int, int, int, cudaStream_t);
+template int launch_attn_encoder<bf16>(const bf16*, ActOut, int, int, int, int, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Beam reorder: dst[l][kv][r][h][0:ctx] = src[l][kv][beam_idx[r]][h][0:ctx].  One warp per (l, kv, r, h) segment,
+// 128-bit loads/stores, only the live ctx_len positions are moved.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) kv_reorder_kernel(const T* __restrict__ src, T* __restrict__ dst, const int* __restrict__ beam_idx,
+                                                         int L2, int rows, int H, int ctx_len, int t_max) {
+  constexpr int VEC = 16 / sizeof(T);
+  const long seg = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long nseg = (long)L2 * rows * H;
+  if (seg >= nseg) return;
+  const int lane = threadIdx.x & 31;
+  const int h = (int)(seg % H);
+  const int r = (int)((seg / H) % rows);
+  const long l = seg / ((long)H * rows);
+  const int sr = beam_idx[r];
+  const T* s = src + (((size_t)l * rows + sr) * H + h) * t_max * HD;
+  T* dd = dst + (((size_t)l * rows + r) * H + h) * t_max * HD;
+  const int nvec = ctx_len * HD / VEC;
+  for (int i = lane; i < nvec; i += 32) {
+    Vec16<T> v;
+    v.load(s + (size_t)i * VEC);
+    v.store(dd + (size_t)i * VEC);
+  }
+}
+
+template <typename T>
+int launch_kv_reorder(const T* src, T* dst, const int* beam_idx, int L, int rows, int H, int ctx_len, int t_max, cudaStream_t st) {
+  const long nseg = (long)L * 2 * rows * H;
+  const int blocks = (int)((nseg + 7) / 8);
+  kv_reorder_kernel<T><<<blocks, 256, 0, st>>>(src, dst, beam_idx, L * 2, rows, H, ctx_len, t_max);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  return GIC_OK;
+}
+template int launch_kv_reorder<float>(const float*, float*, const int*, int, int, int, int, int, cudaStream_t);
+template int launch_kv_reorder<bf16>(const bf16*, bf16*, const int*, int, int, int, int, int, cudaStream_t);
+
+}  // namespace gic

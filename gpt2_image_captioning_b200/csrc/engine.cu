@@ -1,0 +1,646 @@
+// Host side of libgic_b200.so: the opaque engine (packed weights), workspace carving, the generate drivers
+// (mapper -> prefill -> KV-cached decode loop, captured in a CUDA graph) and the extern "C" entry points.
+// See include/gic_b200.h for the contract and the reference lines each entry point replaces.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace gic {
+
+// ---------------------------------------------------------------------------------------------------------------
+// error state
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// packed weights
+// ---------------------------------------------------------------------------------------------------------------
+static const int kBlockNs[3] = {32, 64, 128};
+
+struct Linear {  // y = x . W^T + b with W packed as [N,K] K-major
+  int N = 0, K = 0;
+  float* w_f32 = nullptr;
+  bf16* w_hi = nullptr;
+  bf16* w_lo = nullptr;
+  float* bias = nullptr;
+  TmaDesc tm_hi[3], tm_lo[3];  // per block_n in kBlockNs
+};
+struct Norm { float* w = nullptr; float* b = nullptr; };
+struct GptLayer { Norm ln1, ln2; Linear attn, proj, fc, fc2; };
+struct TfmLayer { Norm n1, n2; Linear in_proj, out_proj, lin1, lin2; };
+
+// activation buffer in the engine's arithmetic mode (F32: f32; BF16: hi; BF16X2: hi + lo)
+struct Act {
+  float* f32 = nullptr;
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+  ActOut out() const { ActOut o; o.f32 = f32; o.hi = hi; o.lo = lo; return o; }
+};
+
+struct Workspace {
+  int B = 0, rows = 0, max_new = 0, beams = 1, P = 0, t_max = 0, m_max = 0;
+  Act x_in, map_hidden, a, o, f;   // GEMM A operands
+  float* map_lin = nullptr;        // transformer mapper: Linear output [B, Hl*d] fp32
+  float* prefix = nullptr;         // mapper output [B, P_img, d] fp32
+  float* h = nullptr;              // residual stream [m_max, d] fp32
+  float* h_dec = nullptr;          // decode residual [rows, d] fp32
+  float* qkv_f32 = nullptr;        // [m_max, 3d]  (F32 / BF16X2)
+  bf16* qkv_bf16 = nullptr;        //              (BF16)
+  void* kv = nullptr;              // [L][2][rows][H][t_max][64]
+  size_t kv_layer_elems = 0;       // elements of one K (or V) plane of one layer
+  float* logits = nullptr;         // [rows, V] fp32 (F32 mode)
+  float* part_val = nullptr; int* part_idx = nullptr; int n_parts_max = 0;
+  int64_t* ids = nullptr;          // [rows, max_new]
+  unsigned char* finished = nullptr; int* first_eos = nullptr;
+  int *d_step = nullptr, *d_pos = nullptr, *done_counter = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace gic
+
+using namespace gic;
+
+struct gic_engine {
+  gic_config cfg;
+  int d = 0, L = 0, H = 0, V = 0, P_img = 0, P_task = 0, E = 0;
+  bool split = false;  // BF16X2
+  bool tc = false;     // tensor-core modes (BF16 / BF16X2)
+  std::vector<void*> allocs;
+  size_t weight_bytes = 0;
+  bool gpt_loaded = false, mapper_loaded = false;
+  // GPT-2
+  Linear lm_head;       // wte as [V,d]
+  float* wte_f32 = nullptr;  // embedding table (F32 / BF16X2); BF16 gathers from lm_head.w_hi
+  float* wpe = nullptr;
+  Norm lnf;
+  std::vector<GptLayer> layers;
+  float* task_prefix = nullptr;  // [P_task, d]
+  // mappers
+  Linear map1, map2;             // MLP
+  Linear tfm_linear; float* tfm_prefix_const = nullptr; std::vector<TfmLayer> tfm_layers;
+  // decode-step CUDA graph cache (one entry)
+  cudaGraphExec_t graph_exec = nullptr;
+  void* graph_ws = nullptr; int graph_B = 0, graph_max_new = 0;
+  bool use_graph = true;
+};
+
+namespace gic {
+
+static int dev_alloc(gic_engine* e, void** p, size_t bytes) {
+  GIC_CHECK_CUDA(cudaMalloc(p, bytes));
+  e->allocs.push_back(*p);
+  e->weight_bytes += bytes;
+  return GIC_OK;
+}
+
+static int copy_vec(gic_engine* e, float** dst, const float* src, size_t n, cudaStream_t st) {
+  GIC_REQUIRE(src != nullptr, "null weight pointer");
+  GIC_TRY(dev_alloc(e, (void**)dst, n * sizeof(float)));
+  GIC_CHECK_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return GIC_OK;
+}
+
+// in: fp32 [N,K] (transpose = false, nn.Linear / wte) or [K,N] (transpose = true, HF Conv1D)
+static int pack_linear(gic_engine* e, Linear* lin, const float* w, const float* bias, int N, int K, bool transpose, cudaStream_t st) {
+  GIC_REQUIRE(w != nullptr, "null weight pointer");
+  lin->N = N;
+  lin->K = K;
+  const size_t n = (size_t)N * K;
+  ActOut out;
+  if (!e->tc) {
+    GIC_TRY(dev_alloc(e, (void**)&lin->w_f32, n * sizeof(float)));
+    out.f32 = lin->w_f32;
+  } else {
+    GIC_TRY(dev_alloc(e, (void**)&lin->w_hi, n * sizeof(bf16)));
+    out.hi = lin->w_hi;
+    if (e->split) {
+      GIC_TRY(dev_alloc(e, (void**)&lin->w_lo, n * sizeof(bf16)));
+      out.lo = lin->w_lo;
+    }
+  }
+  // source is [R,C]: transpose -> [C,R] = [N,K]
+  const int R = transpose ? K : N, C = transpose ? N : K;
+  GIC_TRY(launch_pack_weight(w, R, C, transpose, out, st));
+  if (bias) GIC_TRY(copy_vec(e, &lin->bias, bias, N, st));
+  if (e->tc) {
+    GIC_REQUIRE(K % 8 == 0, "tensor-core modes need K (%d) to be a multiple of 8", K);
+    for (int i = 0; i < 3; ++i) {
+      GIC_TRY(make_tma_2d_bf16(&lin->tm_hi[i], lin->w_hi, N, K, K, kBlockNs[i]));
+      if (e->split) GIC_TRY(make_tma_2d_bf16(&lin->tm_lo[i], lin->w_lo, N, K, K, kBlockNs[i]));
+    }
+  }
+  return GIC_OK;
+}
+
+static int copy_norm(gic_engine* e, Norm* n, const float* w, const float* b, int d, cudaStream_t st) {
+  GIC_TRY(copy_vec(e, &n->w, w, d, st));
+  GIC_TRY(copy_vec(e, &n->b, b, d, st));
+  return GIC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------------------------------
+struct Carver {
+  unsigned char* base; size_t off = 0;
+  explicit Carver(void* b) : base((unsigned char*)b) {}
+  template <typename T> T* take(size_t n) {
+    off = align_up(off, 1024);  // TMA-friendly alignment for every buffer
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+static void carve_act(const gic_engine* e, Carver& c, Act* a, size_t n) {
+  if (!e->tc) a->f32 = c.take<float>(n);
+  else {
+    a->hi = c.take<bf16>(n);
+    if (e->split) a->lo = c.take<bf16>(n);
+  }
+}
+
+static void carve(const gic_engine* e, void* base, int B, int max_new, int beams, Workspace* w) {
+  const int d = e->d;
+  w->B = B; w->beams = beams < 1 ? 1 : beams; w->rows = B * w->beams; w->max_new = max_new;
+  w->P = e->P_img + e->P_task;
+  w->t_max = w->P + max_new;
+  const int S_map = e->cfg.mapper_kind == GIC_MAPPER_TRANSFORMER ? e->cfg.hidden_length + e->P_img : 0;
+  int m = B * w->P;
+  if (B * S_map > m) m = B * S_map;
+  if (w->rows > m) m = w->rows;
+  w->m_max = m;
+  Carver c(base);
+  carve_act(e, c, &w->x_in, (size_t)B * e->E);
+  if (e->cfg.mapper_kind == GIC_MAPPER_MLP) carve_act(e, c, &w->map_hidden, (size_t)B * (e->P_img * d / 2));
+  else w->map_lin = c.take<float>((size_t)B * e->cfg.hidden_length * d);
+  w->prefix = c.take<float>((size_t)B * e->P_img * d);
+  w->h = c.take<float>((size_t)m * d);
+  w->h_dec = c.take<float>((size_t)w->rows * d);
+  carve_act(e, c, &w->a, (size_t)m * d);
+  carve_act(e, c, &w->o, (size_t)m * d);
+  carve_act(e, c, &w->f, (size_t)m * 4 * d);
+  if (e->cfg.dtype == GIC_DTYPE_BF16) w->qkv_bf16 = c.take<bf16>((size_t)m * 3 * d);
+  else w->qkv_f32 = c.take<float>((size_t)m * 3 * d);
+  w->kv_layer_elems = (size_t)w->rows * e->H * w->t_max * 64;
+  const size_t kv_elems = (size_t)e->L * 2 * w->kv_layer_elems;
+  if (e->cfg.dtype == GIC_DTYPE_BF16) w->kv = c.take<bf16>(kv_elems);
+  else w->kv = c.take<float>(kv_elems);
+  if (!e->tc) {
+    w->logits = c.take<float>((size_t)w->rows * e->V);
+    w->n_parts_max = LMHEAD_F32_PARTS;
+  } else {
+    w->n_parts_max = ceil_div(e->V, 32);
+  }
+  w->part_val = c.take<float>((size_t)w->n_parts_max * w->rows);
+  w->part_idx = c.take<int>((size_t)w->n_parts_max * w->rows);
+  w->ids = c.take<int64_t>((size_t)w->rows * (max_new > 0 ? max_new : 1));
+  w->finished = c.take<unsigned char>(w->rows);
+  w->first_eos = c.take<int>(w->rows);
+  w->d_step = c.take<int>(1);
+  w->d_pos = c.take<int>(1);
+  w->done_counter = c.take<int>(1);
+  w->bytes = align_up(c.off, 1024) + 1024;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// building blocks
+// ---------------------------------------------------------------------------------------------------------------
+// out = epi(A . W^T + b).  A: Act with M rows of K (dense).  Outputs follow `out` (row stride ld_out).
+static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, int epilogue, ActOut out, int ld_out, cudaStream_t st,
+                  float* part_val = nullptr, int* part_idx = nullptr, int* n_parts = nullptr) {
+  if (!e->tc) {
+    GIC_REQUIRE(out.f32 != nullptr, "fp32 linear needs an fp32 output");
+    return launch_sgemm_nt(A.f32, lin.K, lin.w_f32, lin.bias, out.f32, ld_out, M, lin.N, lin.K, epilogue, st);
+  }
+  GemmBf16Args g;
+  const int bn = gemm_bf16_pick_block_n(M, lin.N);
+  const int bi = bn == 32 ? 0 : (bn == 64 ? 1 : 2);
+  GIC_TRY(make_tma_2d_bf16(&g.a_hi, A.hi, M, lin.K, lin.K, 128));
+  g.w_hi = lin.tm_hi[bi];
+  if (e->split) {
+    GIC_TRY(make_tma_2d_bf16(&g.a_lo, A.lo, M, lin.K, lin.K, 128));
+    g.w_lo = lin.tm_lo[bi];
+  }
+  g.M = M; g.N = lin.N; g.K = lin.K; g.block_n = bn; g.split = e->split ? 1 : 0; g.epilogue = epilogue; g.bias = lin.bias;
+  g.out = out; g.ld_out = ld_out; g.part_val = part_val; g.part_idx = part_idx;
+  if (n_parts) *n_parts = ceil_div(lin.N, bn);
+  return launch_gemm_bf16(g, st);
+}
+
+static ActOut qkv_out(const Workspace& w) {
+  ActOut o;
+  o.f32 = w.qkv_f32;
+  o.hi = w.qkv_bf16;
+  return o;
+}
+
+// one GPT-2 block over M rows of the residual stream `h` (HF GPT2Block.forward :262-309)
+static int gpt_layer(const gic_engine* e, const Workspace& w, int l, float* h, int M, bool prefill, cudaStream_t st) {
+  const GptLayer& Lw = e->layers[l];
+  const int d = e->d;
+  GIC_TRY(launch_layernorm(h, d, Lw.ln1.w, Lw.ln1.b, w.a.out(), M, d, st));
+  GIC_TRY(linear(e, Lw.attn, w.a, M, EPI_NONE, qkv_out(w), 3 * d, st));
+  if (e->cfg.dtype == GIC_DTYPE_BF16) {
+    bf16* kc = (bf16*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
+    bf16* vc = kc + w.kv_layer_elems;
+    if (prefill) GIC_TRY(launch_attn_prefill<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, st));
+    else GIC_TRY(launch_attn_decode<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st));
+  } else {
+    float* kc = (float*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
+    float* vc = kc + w.kv_layer_elems;
+    if (prefill) GIC_TRY(launch_attn_prefill<float>(w.qkv_f32, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, st));
+    else GIC_TRY(launch_attn_decode<float>(w.qkv_f32, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st));
+  }
+  ActOut hres; hres.f32 = h;
+  GIC_TRY(linear(e, Lw.proj, w.o, M, EPI_RESIDUAL, hres, d, st));
+  GIC_TRY(launch_layernorm(h, d, Lw.ln2.w, Lw.ln2.b, w.a.out(), M, d, st));
+  GIC_TRY(linear(e, Lw.fc, w.a, M, EPI_GELU, w.f.out(), 4 * d, st));
+  GIC_TRY(linear(e, Lw.fc2, w.f, M, EPI_RESIDUAL, hres, d, st));
+  return GIC_OK;
+}
+
+// ln_f on `rows` rows (row r at h + r*stride) -> LM head -> (val, idx) partials -> finalize (token, EOS rules, next input)
+static int lm_head_and_token(const gic_engine* e, const Workspace& w, const float* h, long row_stride, int rows, float* logits_tap,
+                             cudaStream_t st) {
+  const int d = e->d;
+  GIC_TRY(launch_layernorm(h, row_stride, e->lnf.w, e->lnf.b, w.a.out(), rows, d, st));
+  int n_parts = 0;
+  if (!e->tc) {
+    float* lg = logits_tap ? logits_tap : w.logits;
+    ActOut o; o.f32 = lg;
+    GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st));
+    GIC_TRY(launch_argmax_partials(lg, rows, e->V, w.part_val, w.part_idx, st));
+    n_parts = LMHEAD_F32_PARTS;
+  } else {
+    ActOut o; o.f32 = logits_tap;  // null on the product path: logits never reach HBM
+    GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st, w.part_val, w.part_idx, &n_parts));
+  }
+  FinalizeArgs fa;
+  fa.part_val = w.part_val; fa.part_idx = w.part_idx; fa.n_parts = n_parts;
+  fa.B = rows; fa.d = d; fa.eos = e->cfg.eos_token_id; fa.max_new = w.max_new; fa.P = w.P; fa.n_pos = e->cfg.n_positions;
+  fa.d_step = w.d_step; fa.d_pos = w.d_pos; fa.done_counter = w.done_counter;
+  fa.finished = w.finished; fa.first_eos = w.first_eos; fa.ids_out = w.ids;
+  fa.wte_f32 = e->wte_f32; fa.wte_bf16 = e->wte_f32 ? nullptr : e->lm_head.w_hi;
+  fa.wpe = e->wpe; fa.h_next = w.h_dec;
+  return launch_finalize_token(fa, st);
+}
+
+static int decode_step(const gic_engine* e, const Workspace& w, float* logits_tap, cudaStream_t st) {
+  for (int l = 0; l < e->L; ++l) GIC_TRY(gpt_layer(e, w, l, w.h_dec, w.rows, false, st));
+  return lm_head_and_token(e, w, w.h_dec, e->d, w.rows, logits_tap, st);
+}
+
+// mapping network: image embeddings [B,E] -> prefix tokens fp32 [B,P_img,d] in w.prefix
+static int mapper_forward(const gic_engine* e, const Workspace& w, const float* x, cudaStream_t st) {
+  const int B = w.B, d = e->d;
+  Act xin;
+  if (!e->tc) xin.f32 = const_cast<float*>(x);
+  else {
+    GIC_TRY(launch_convert(x, w.x_in.out(), (size_t)B * e->E, st));
+    xin = w.x_in;
+  }
+  if (e->cfg.mapper_kind == GIC_MAPPER_MLP) {
+    // Linear -> Tanh -> Linear -> view [B,P,d]  (src/models.py:52-56,71-74)
+    GIC_TRY(linear(e, e->map1, xin, B, EPI_TANH, w.map_hidden.out(), e->map1.N, st));
+    ActOut o; o.f32 = w.prefix;
+    GIC_TRY(linear(e, e->map2, w.map_hidden, B, EPI_NONE, o, e->map2.N, st));
+    return GIC_OK;
+  }
+  // transformer mapper (src/models.py:141-174)
+  const int Hl = e->cfg.hidden_length, P = e->P_img, S = Hl + P, M = B * S, heads = e->cfg.mapper_heads;
+  ActOut lo; lo.f32 = w.map_lin;
+  GIC_TRY(linear(e, e->tfm_linear, xin, B, EPI_NONE, lo, e->tfm_linear.N, st));
+  GIC_TRY(launch_build_mapper_seq(w.map_lin, e->tfm_prefix_const, w.h, B, Hl, P, d, st));
+  ActOut hres; hres.f32 = w.h;
+  for (size_t l = 0; l < e->tfm_layers.size(); ++l) {
+    const TfmLayer& T = e->tfm_layers[l];
+    GIC_TRY(launch_layernorm(w.h, d, T.n1.w, T.n1.b, w.a.out(), M, d, st));
+    GIC_TRY(linear(e, T.in_proj, w.a, M, EPI_NONE, qkv_out(w), 3 * d, st));
+    if (e->cfg.dtype == GIC_DTYPE_BF16) GIC_TRY(launch_attn_encoder<bf16>(w.qkv_bf16, w.o.out(), B, S, heads, d / heads, st));
+    else GIC_TRY(launch_attn_encoder<float>(w.qkv_f32, w.o.out(), B, S, heads, d / heads, st));
+    GIC_TRY(linear(e, T.out_proj, w.o, M, EPI_RESIDUAL, hres, d, st));
+    GIC_TRY(launch_layernorm(w.h, d, T.n2.w, T.n2.b, w.a.out(), M, d, st));
+    GIC_TRY(linear(e, T.lin1, w.a, M, EPI_RELU, w.f.out(), 4 * d, st));
+    GIC_TRY(linear(e, T.lin2, w.f, M, EPI_RESIDUAL, hres, d, st));
+  }
+  return launch_slice_tokens(w.h, S, Hl, P, w.prefix, B, d, st);
+}
+
+static int check_ready(const gic_engine* e) {
+  GIC_REQUIRE(e != nullptr, "null engine");
+  GIC_REQUIRE(e->gpt_loaded, "GPT-2 weights not loaded (gic_engine_load_gpt2)");
+  GIC_REQUIRE(e->mapper_loaded, "mapping-network weights not loaded");
+  GIC_REQUIRE(e->P_task == 0 || e->task_prefix != nullptr, "task prefix declared in the config but not loaded");
+  return GIC_OK;
+}
+
+}  // namespace gic
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+extern "C" {
+
+const char* gic_last_error(void) { return gic::get_error(); }
+int gic_abi_version(void) { return GIC_ABI_VERSION; }
+
+int gic_device_check(void) {
+  int dev = 0;
+  GIC_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  GIC_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    gic::set_error("device %d (%s) is sm_%d%d; this library contains sm_100a code only", dev, prop.name, prop.major, prop.minor);
+    return GIC_ERR_UNSUPPORTED;
+  }
+  return GIC_OK;
+}
+
+int gic_engine_create(const gic_config* cfg, gic_engine** out) {
+  GIC_REQUIRE(cfg != nullptr && out != nullptr, "null argument");
+  GIC_REQUIRE(cfg->abi_version == GIC_ABI_VERSION, "ABI version mismatch: caller %d, library %d", cfg->abi_version, GIC_ABI_VERSION);
+  GIC_REQUIRE(cfg->dtype >= GIC_DTYPE_F32 && cfg->dtype <= GIC_DTYPE_BF16X2, "unknown dtype %d", cfg->dtype);
+  GIC_REQUIRE(cfg->n_embd > 0 && cfg->n_head > 0 && cfg->n_embd == cfg->n_head * 64,
+              "GPT-2 head_dim must be 64 (n_embd %d, n_head %d)", cfg->n_embd, cfg->n_head);
+  GIC_REQUIRE(cfg->n_embd % 64 == 0 && cfg->n_embd <= 1280, "n_embd %d unsupported (multiple of 64, <= 1280)", cfg->n_embd);
+  GIC_REQUIRE(cfg->n_layer > 0 && cfg->vocab_size > 0 && cfg->n_positions > 0, "bad GPT-2 dimensions");
+  GIC_REQUIRE(cfg->embed_dim > 0 && cfg->embed_dim % 8 == 0, "embed_dim %d must be a positive multiple of 8", cfg->embed_dim);
+  GIC_REQUIRE(cfg->prefix_length > 0 && cfg->task_prefix_length >= 0, "bad prefix lengths");
+  GIC_REQUIRE(cfg->mapper_kind == GIC_MAPPER_MLP || cfg->mapper_kind == GIC_MAPPER_TRANSFORMER, "unknown mapper kind %d", cfg->mapper_kind);
+  if (cfg->mapper_kind == GIC_MAPPER_TRANSFORMER) {
+    GIC_REQUIRE(cfg->hidden_length > 0 && cfg->mapper_layers > 0 && cfg->mapper_heads > 0, "bad transformer-mapper dimensions");
+    GIC_REQUIRE(cfg->n_embd % cfg->mapper_heads == 0 && (cfg->n_embd / cfg->mapper_heads) % 32 == 0,
+                "transformer mapper head_dim %d unsupported", cfg->n_embd / cfg->mapper_heads);
+  } else {
+    GIC_REQUIRE((cfg->prefix_length * cfg->n_embd) % 16 == 0, "MLP mapper hidden size must be a multiple of 8");
+  }
+  GIC_TRY(gic_device_check());
+  gic_engine* e = new gic_engine();
+  e->cfg = *cfg;
+  e->d = cfg->n_embd; e->L = cfg->n_layer; e->H = cfg->n_head; e->V = cfg->vocab_size;
+  e->P_img = cfg->prefix_length; e->P_task = cfg->task_prefix_length; e->E = cfg->embed_dim;
+  e->tc = cfg->dtype != GIC_DTYPE_F32;
+  e->split = cfg->dtype == GIC_DTYPE_BF16X2;
+  const char* ng = getenv("GIC_NO_GRAPH");
+  e->use_graph = !(ng && ng[0] == '1');
+  if (e->tc) {
+    int r = gic::tma_init();
+    if (r == GIC_OK) r = gic::gemm_bf16_configure();
+    if (r != GIC_OK) { delete e; return r; }
+  }
+  *out = e;
+  return GIC_OK;
+}
+
+int gic_engine_destroy(gic_engine* e) {
+  if (!e) return GIC_OK;
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  for (void* p : e->allocs) cudaFree(p);
+  delete e;
+  return GIC_OK;
+}
+
+size_t gic_engine_weight_bytes(const gic_engine* e) { return e ? e->weight_bytes : 0; }
+
+int gic_engine_load_gpt2(gic_engine* e, const gic_gpt2_weights* w, void* stream) {
+  GIC_REQUIRE(e && w && w->layers, "null argument");
+  GIC_REQUIRE(!e->gpt_loaded, "GPT-2 weights already loaded; create a new engine to reload");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = e->d;
+  GIC_TRY(pack_linear(e, &e->lm_head, w->wte, nullptr, e->V, d, false, st));
+  if (e->cfg.dtype == GIC_DTYPE_F32) e->wte_f32 = e->lm_head.w_f32;
+  else if (e->cfg.dtype == GIC_DTYPE_BF16X2) GIC_TRY(copy_vec(e, &e->wte_f32, w->wte, (size_t)e->V * d, st));
+  GIC_TRY(copy_vec(e, &e->wpe, w->wpe, (size_t)e->cfg.n_positions * d, st));
+  GIC_TRY(copy_norm(e, &e->lnf, w->lnf_w, w->lnf_b, d, st));
+  e->layers.resize(e->L);
+  for (int l = 0; l < e->L; ++l) {
+    const gic_gpt2_layer_weights& s = w->layers[l];
+    GptLayer& D = e->layers[l];
+    GIC_TRY(copy_norm(e, &D.ln1, s.ln1_w, s.ln1_b, d, st));
+    GIC_TRY(copy_norm(e, &D.ln2, s.ln2_w, s.ln2_b, d, st));
+    GIC_TRY(pack_linear(e, &D.attn, s.attn_w, s.attn_b, 3 * d, d, true, st));   // Conv1D [d,3d] -> [3d,d]
+    GIC_TRY(pack_linear(e, &D.proj, s.proj_w, s.proj_b, d, d, true, st));
+    GIC_TRY(pack_linear(e, &D.fc, s.fc_w, s.fc_b, 4 * d, d, true, st));
+    GIC_TRY(pack_linear(e, &D.fc2, s.fc2_w, s.fc2_b, d, 4 * d, true, st));
+  }
+  e->gpt_loaded = true;
+  return GIC_OK;
+}
+
+int gic_engine_load_mlp_mapper(gic_engine* e, const gic_mlp_mapper_weights* w, void* stream) {
+  GIC_REQUIRE(e && w, "null argument");
+  GIC_REQUIRE(e->cfg.mapper_kind == GIC_MAPPER_MLP, "engine was not configured for the MLP mapper");
+  GIC_REQUIRE(!e->mapper_loaded, "mapper weights already loaded");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int out = e->P_img * e->d, hid = out / 2;
+  GIC_TRY(pack_linear(e, &e->map1, w->w1, w->b1, hid, e->E, false, st));
+  GIC_TRY(pack_linear(e, &e->map2, w->w2, w->b2, out, hid, false, st));
+  e->mapper_loaded = true;
+  return GIC_OK;
+}
+
+int gic_engine_load_tfm_mapper(gic_engine* e, const gic_tfm_mapper_weights* w, void* stream) {
+  GIC_REQUIRE(e && w && w->layers, "null argument");
+  GIC_REQUIRE(e->cfg.mapper_kind == GIC_MAPPER_TRANSFORMER, "engine was not configured for the transformer mapper");
+  GIC_REQUIRE(!e->mapper_loaded, "mapper weights already loaded");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = e->d;
+  GIC_TRY(pack_linear(e, &e->tfm_linear, w->linear_w, w->linear_b, e->cfg.hidden_length * d, e->E, false, st));
+  GIC_TRY(copy_vec(e, &e->tfm_prefix_const, w->prefix_const, (size_t)e->P_img * d, st));
+  e->tfm_layers.resize(e->cfg.mapper_layers);
+  for (int l = 0; l < e->cfg.mapper_layers; ++l) {
+    const gic_tfm_layer_weights& s = w->layers[l];
+    TfmLayer& D = e->tfm_layers[l];
+    GIC_TRY(copy_norm(e, &D.n1, s.norm1_w, s.norm1_b, d, st));
+    GIC_TRY(copy_norm(e, &D.n2, s.norm2_w, s.norm2_b, d, st));
+    GIC_TRY(pack_linear(e, &D.in_proj, s.in_proj_w, s.in_proj_b, 3 * d, d, false, st));
+    GIC_TRY(pack_linear(e, &D.out_proj, s.out_proj_w, s.out_proj_b, d, d, false, st));
+    GIC_TRY(pack_linear(e, &D.lin1, s.lin1_w, s.lin1_b, 4 * d, d, false, st));
+    GIC_TRY(pack_linear(e, &D.lin2, s.lin2_w, s.lin2_b, d, 4 * d, false, st));
+  }
+  e->mapper_loaded = true;
+  return GIC_OK;
+}
+
+int gic_engine_load_task_prefix(gic_engine* e, const float* task, void* stream) {
+  GIC_REQUIRE(e && task, "null argument");
+  GIC_REQUIRE(e->P_task > 0, "engine was configured without a task prefix");
+  GIC_REQUIRE(e->task_prefix == nullptr, "task prefix already loaded");
+  return copy_vec(e, &e->task_prefix, task, (size_t)e->P_task * e->d, (cudaStream_t)stream);
+}
+
+size_t gic_workspace_bytes(const gic_engine* e, int batch, int max_new_tokens, int num_beams) {
+  if (!e || batch <= 0 || max_new_tokens < 0) return 0;
+  Workspace w;
+  carve(e, nullptr, batch, max_new_tokens, num_beams, &w);
+  return w.bytes;
+}
+
+static int prepare_ws(const gic_engine* e, void* workspace, size_t workspace_bytes, int batch, int max_new, int beams, Workspace* w) {
+  GIC_REQUIRE(batch > 0, "batch must be positive (got %d)", batch);
+  GIC_REQUIRE(max_new >= 0, "max_new_tokens must be >= 0");
+  GIC_REQUIRE(workspace != nullptr, "null workspace");
+  GIC_REQUIRE(e->P_img + e->P_task + max_new <= e->cfg.n_positions, "prefix + max_new_tokens (%d) exceeds n_positions (%d)",
+              e->P_img + e->P_task + max_new, e->cfg.n_positions);
+  void* aligned = (void*)align_up((size_t)workspace, 1024);
+  const size_t lost = (size_t)((unsigned char*)aligned - (unsigned char*)workspace);
+  carve(e, aligned, batch, max_new, beams, w);
+  if (w->bytes - 1024 + lost > workspace_bytes) {  // gic_workspace_bytes includes 1024 bytes of alignment slack
+    set_error("workspace too small: need %zu bytes, got %zu", w->bytes, workspace_bytes);
+    return GIC_ERR_WORKSPACE;
+  }
+  return GIC_OK;
+}
+
+int gic_mapper_forward(gic_engine* e, const float* x, int batch, float* prefix_out, void* workspace, size_t workspace_bytes, void* stream) {
+  GIC_TRY(check_ready(e));
+  GIC_REQUIRE(x && prefix_out, "null argument");
+  Workspace w;
+  GIC_TRY(prepare_ws(e, workspace, workspace_bytes, batch, 0, 1, &w));
+  cudaStream_t st = (cudaStream_t)stream;
+  GIC_TRY(mapper_forward(e, w, x, st));
+  // [B, P_img + P_task, d]: image prefix then the task rows (src/models.py:364-375)
+  return launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, nullptr, nullptr, prefix_out, batch, e->d, st);
+}
+
+int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, int64_t* ids_out, int32_t* gen_len_out, float* logits_out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  GIC_TRY(check_ready(e));
+  GIC_REQUIRE(x && ids_out, "null argument");
+  GIC_REQUIRE(max_new >= 1, "max_new_tokens must be >= 1 (the caller handles 0, src/models.py:471-473)");
+  Workspace w;
+  GIC_TRY(prepare_ws(e, workspace, workspace_bytes, batch, max_new, 1, &w));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = e->d, B = batch, P = w.P;
+
+  GIC_TRY(launch_init_decode_state(w.finished, w.first_eos, B, max_new, w.d_step, w.d_pos, w.done_counter, P, st));
+  GIC_TRY(mapper_forward(e, w, x, st));
+  GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));
+  // ---- prefill over the P prefix tokens of every row ----
+  for (int l = 0; l < e->L; ++l) GIC_TRY(gpt_layer(e, w, l, w.h, B * P, true, st));
+  // only the last position feeds the LM head (the reference computes all positions and keeps [:, -1, :], src/models.py:398)
+  GIC_TRY(lm_head_and_token(e, w, w.h + (size_t)(P - 1) * d, (long)P * d, B, logits_out, st));
+
+  // ---- decode: max_new-1 identical steps; positions / step index live on the device ----
+  const int steps = max_new - 1;
+  const bool graph_ok = e->use_graph && logits_out == nullptr && steps >= 2;
+  if (!graph_ok) {
+    for (int s = 1; s <= steps; ++s)
+      GIC_TRY(decode_step(e, w, logits_out ? logits_out + (size_t)s * B * e->V : nullptr, st));
+  } else {
+    if (!(e->graph_exec && e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new)) {
+      if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      GIC_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int r = decode_step(e, w, nullptr, st);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (r != GIC_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+      GIC_CHECK_CUDA(ce);
+      ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      GIC_CHECK_CUDA(ce);
+      e->graph_ws = workspace; e->graph_B = B; e->graph_max_new = max_new;
+    }
+    for (int s = 1; s <= steps; ++s) GIC_CHECK_CUDA(cudaGraphLaunch(e->graph_exec, st));
+  }
+  GIC_CHECK_CUDA(cudaMemcpyAsync(ids_out, w.ids, (size_t)B * max_new * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+  if (gen_len_out) GIC_TRY(launch_gen_len(w.first_eos, B, max_new, gen_len_out, st));
+  return GIC_OK;
+}
+
+int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int num_beams, float length_penalty, int64_t* ids_out,
+                      float* scores_out, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)e; (void)x; (void)batch; (void)max_new; (void)num_beams; (void)length_penalty; (void)ids_out; (void)scores_out;
+  (void)workspace; (void)workspace_bytes; (void)stream;
+  gic::set_error("gic_generate_beam: not implemented yet");
+  return GIC_ERR_UNSUPPORTED;
+}
+
+int gic_kv_reorder(gic_engine* e, const void* kv_src, void* kv_dst, const int32_t* beam_idx, int rows, int ctx_len, int t_max, void* stream) {
+  GIC_REQUIRE(e && kv_src && kv_dst && beam_idx, "null argument");
+  GIC_REQUIRE(rows > 0 && ctx_len >= 0 && ctx_len <= t_max, "bad sizes rows=%d ctx_len=%d t_max=%d", rows, ctx_len, t_max);
+  if (e->cfg.dtype == GIC_DTYPE_BF16)
+    return launch_kv_reorder<bf16>((const bf16*)kv_src, (bf16*)kv_dst, beam_idx, e->L, rows, e->H, ctx_len, t_max, (cudaStream_t)stream);
+  return launch_kv_reorder<float>((const float*)kv_src, (float*)kv_dst, beam_idx, e->L, rows, e->H, ctx_len, t_max, (cudaStream_t)stream);
+}
+
+size_t gic_topk_workspace_bytes(int batch, int n_rows, int dim, int k) { return gic::topk_workspace_bytes(batch, n_rows, dim, k); }
+
+int gic_topk_ip(const float* q, const float* db, int batch, int n_rows, int dim, int k, float* scores_out, int64_t* idx_out, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  GIC_REQUIRE(q && db && scores_out && idx_out && workspace, "null argument");
+  return launch_topk_ip(q, db, batch, n_rows, dim, k, scores_out, idx_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gic_select_caption_rows(const float* scores, const int64_t* idx, int batch, int k_searched, const int64_t* cap_row_start,
+                            const int64_t* cap_row_ids, int top_i, int top_k, int64_t* rows_out, void* stream) {
+  GIC_REQUIRE(scores && idx && cap_row_start && rows_out, "null argument");
+  return launch_select_caption_rows(scores, idx, batch, k_searched, cap_row_start, cap_row_ids, top_i, top_k, rows_out,
+                                    (cudaStream_t)stream);
+}
+
+int gic_gather_aggregate_add(const float* q, const float* cap_db, const int64_t* rows, int batch, int top_k, int dim, int aggregation,
+                             float* out, void* stream) {
+  GIC_REQUIRE(q && cap_db && rows && out, "null argument");
+  GIC_REQUIRE(batch > 0, "batch must be positive");
+  return launch_gather_aggregate_add(q, cap_db, rows, batch, top_k, dim, aggregation, out, (cudaStream_t)stream);
+}
+
+// ---- kernel-level test entry points ---------------------------------------------------------------------------------
+int gic_test_gemm(int dtype, const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int epilogue, void* stream) {
+  GIC_REQUIRE(A && W && C, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == GIC_DTYPE_F32) return launch_sgemm_nt(A, K, W, bias, C, N, M, N, K, epilogue, st);
+  GIC_REQUIRE(dtype == GIC_DTYPE_BF16 || dtype == GIC_DTYPE_BF16X2, "unknown dtype %d", dtype);
+  GIC_TRY(gic_device_check());
+  GIC_TRY(gic::tma_init());
+  GIC_TRY(gic::gemm_bf16_configure());
+  const bool split = dtype == GIC_DTYPE_BF16X2;
+  bf16 *a_hi = nullptr, *a_lo = nullptr, *w_hi = nullptr, *w_lo = nullptr;
+  const size_t na = (size_t)M * K, nw = (size_t)N * K;
+  GIC_CHECK_CUDA(cudaMalloc(&a_hi, na * 2));
+  GIC_CHECK_CUDA(cudaMalloc(&w_hi, nw * 2));
+  if (split) {
+    GIC_CHECK_CUDA(cudaMalloc(&a_lo, na * 2));
+    GIC_CHECK_CUDA(cudaMalloc(&w_lo, nw * 2));
+  }
+  ActOut ao; ao.hi = a_hi; ao.lo = a_lo;
+  ActOut wo; wo.hi = w_hi; wo.lo = w_lo;
+  int r = launch_convert(A, ao, na, st);
+  if (r == GIC_OK) r = launch_convert(W, wo, nw, st);
+  GemmBf16Args g;
+  const int bn = gemm_bf16_pick_block_n(M, N);
+  if (r == GIC_OK) r = make_tma_2d_bf16(&g.a_hi, a_hi, M, K, K, 128);
+  if (r == GIC_OK) r = make_tma_2d_bf16(&g.w_hi, w_hi, N, K, K, bn);
+  if (r == GIC_OK && split) r = make_tma_2d_bf16(&g.a_lo, a_lo, M, K, K, 128);
+  if (r == GIC_OK && split) r = make_tma_2d_bf16(&g.w_lo, w_lo, N, K, K, bn);
+  g.M = M; g.N = N; g.K = K; g.block_n = bn; g.split = split; g.epilogue = epilogue; g.bias = bias;
+  g.out.f32 = C; g.ld_out = N;
+  if (r == GIC_OK) r = launch_gemm_bf16(g, st);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  cudaFree(a_hi); cudaFree(w_hi); cudaFree(a_lo); cudaFree(w_lo);
+  if (r != GIC_OK) return r;
+  GIC_CHECK_CUDA(ce);
+  return GIC_OK;
+}
+
+int gic_test_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int d, void* stream) {
+  GIC_REQUIRE(x && w && b && y, "null argument");
+  ActOut o; o.f32 = y;
+  return launch_layernorm(x, d, w, b, o, rows, d, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,102 @@
+// Launch-function declarations for every kernel of the caption path (definitions in the .cu files).
+#pragma once
+#include "common.cuh"
+
+namespace gic {
+
+enum Epilogue { EPI_NONE = 0, EPI_TANH = 1, EPI_GELU = 2, EPI_RELU = 3, EPI_RESIDUAL = 4 };
+
+// Where a producer kernel writes an activation: fp32 and/or bf16 (hi) and/or the bf16 remainder (lo = bf16(v - hi),
+// the second half of a BF16X2 GEMM operand).  Any pointer may be null.
+struct ActOut {
+  float* f32 = nullptr;
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+  __device__ __forceinline__ void write(size_t i, float v) const {
+    if (f32) f32[i] = v;
+    if (hi) {
+      const bf16 h = __float2bfloat16_rn(v);
+      hi[i] = h;
+      if (lo) lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+};
+
+// ---- sgemm_fp32.cu : CUDA-core fp32 GEMM, C[M,N] = epi(A[M,K] . W[N,K]^T + bias) ----------------------
+// A rows have stride lda (elements); W is [N,K] K-major; C row stride ldc.  EPI_RESIDUAL: C += result (in place).
+int launch_sgemm_nt(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N, int K, int epilogue,
+                    cudaStream_t st);
+
+// ---- gemm_tcgen05.cu : bf16 tcgen05/TMEM GEMM fed by TMA ----------------------------------------------------
+struct alignas(64) TmaDesc { unsigned char bytes[128]; };  // CUtensorMap
+int tma_init();  // resolves cuTensorMapEncodeTiled through the runtime
+// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128B swizzle, out-of-bounds -> zero
+int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows);
+
+struct GemmBf16Args {
+  TmaDesc a_hi, w_hi, a_lo, w_lo;  // lo maps used only when split (BF16X2); A box rows = 128, W box rows = block_n
+  int M = 0, N = 0, K = 0;
+  int block_n = 128;               // 32 | 64 | 128
+  int split = 0;                   // 0: one MMA per k-step; 1: hi.hi + hi.lo + lo.hi
+  int epilogue = EPI_NONE;
+  const float* bias = nullptr;     // [N] or null
+  ActOut out;                      // fp32 (EPI_RESIDUAL: in-place +=) and/or bf16 hi/lo, row stride ld_out
+  int ld_out = 0;
+  float* part_val = nullptr;       // fused LM-head argmax: [n_tiles][M] best value ...
+  int* part_idx = nullptr;         // ... and its lowest column index (cols >= N masked)
+};
+int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st);
+int gemm_bf16_pick_block_n(int M, int N);
+int gemm_bf16_configure();  // cudaFuncSetAttribute for every instantiation (call once, outside stream capture)
+
+// ---- elementwise.cu -----------------------------------------------------------------------------------------------
+int launch_layernorm(const float* x, long x_row_stride, const float* w, const float* b, ActOut y, int rows, int d, cudaStream_t st);
+int launch_pack_weight(const float* in, int R, int C, bool transpose, ActOut out, cudaStream_t st);
+int launch_convert(const float* in, ActOut out, size_t n, cudaStream_t st);
+int launch_embed_prefix(const float* prefix, int P_img, const float* task, int P_task, const float* wpe, float* h, float* prefix_out,
+                        int B, int d, cudaStream_t st);
+int launch_slice_tokens(const float* in, int S, int tok0, int n_tok, float* out, int B, int d, cudaStream_t st);
+int launch_build_mapper_seq(const float* lin, const float* prefix_const, float* seq, int B, int Hl, int P, int d, cudaStream_t st);
+
+// ---- attention.cu -------------------------------------------------------------------------------------------------
+// KV cache layout: [L][2][rows][H][T_max][64], element T.  qkv rows are [.., 3d] (q | k | v), head h at h*64.
+template <typename T>
+int launch_attn_prefill(const T* qkv, T* kcache, T* vcache, ActOut out, int B, int P, int H, int t_max, cudaStream_t st);
+template <typename T>
+int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows, int H, int t_max, cudaStream_t st);
+template <typename T>
+int launch_attn_encoder(const T* qkv, ActOut out, int B, int S, int H, int hd, cudaStream_t st);
+template <typename T>
+int launch_kv_reorder(const T* src, T* dst, const int* beam_idx, int L, int rows, int H, int ctx_len, int t_max, cudaStream_t st);
+
+// ---- lmhead.cu ----------------------------------------------------------------------------------------------------
+constexpr int LMHEAD_F32_PARTS = 8;
+int launch_argmax_partials(const float* logits, int B, int V, float* part_val, int* part_idx, cudaStream_t st);
+struct FinalizeArgs {
+  const float* part_val; const int* part_idx; int n_parts;  // [n_parts][B]
+  int B, d, eos, max_new, P, n_pos;
+  int* d_step;              // device scalar: index of the token being produced; advanced by the kernel
+  int* d_pos;               // device scalar: KV position of the token fed to the next decode step
+  int* done_counter;        // device scalar used to elect the last block
+  unsigned char* finished;  // [B]
+  int* first_eos;           // [B]; max_new = never
+  int64_t* ids_out;         // [B, max_new]
+  const float* wte_f32; const bf16* wte_bf16;  // exactly one: embedding table [V,d]
+  const float* wpe;         // [n_pos, d]
+  float* h_next;            // [B, d] fp32: next-step input = wte[tok] + wpe[P + step]
+};
+int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st);
+int launch_init_decode_state(unsigned char* finished, int* first_eos, int B, int max_new, int* d_step, int* d_pos, int* done_counter,
+                             int P, cudaStream_t st);
+int launch_gen_len(const int* first_eos, int B, int max_new, int* gen_len_out, cudaStream_t st);
+
+// ---- retrieval.cu -------------------------------------------------------------------------------------------------
+size_t topk_workspace_bytes(int B, int N, int D, int k);
+int launch_topk_ip(const float* q, const float* db, int B, int N, int D, int k, float* scores, int64_t* idx, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
+int launch_select_caption_rows(const float* scores, const int64_t* idx, int B, int k_searched, const int64_t* cap_row_start,
+                               const int64_t* cap_row_ids, int top_i, int top_k, int64_t* rows_out, cudaStream_t st);
+int launch_gather_aggregate_add(const float* q, const float* cap_db, const int64_t* rows, int B, int top_k, int D, int aggregation,
+                                float* out, cudaStream_t st);
+
+}  // namespace gic

@@ -1,0 +1,171 @@
+// Token selection: argmax over the LM-head logits and the per-step bookkeeping of the greedy loop.
+// Replaces src/models.py:398-469 per step: logits[:, -1, :] -> argmax (ties -> LOWEST index, as torch.argmax) ->
+// finished |= (tok == eos); tok[finished] = eos -> append -> wte(tok) as the next input (+ wpe of its position,
+// HF:models/gpt2/modeling_gpt2.py:579-585).  Everything stays on the device: no per-step host sync
+// (the reference does `is_finished.all()` on the host every step, src/models.py:390).
+#include "kernels.cuh"
+
+namespace gic {
+
+__device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
+
+__device__ __forceinline__ void block_argmax(float& v, int& idx, float* sv, int* si) {
+  // warp reduce, then across warps; keeps the lowest index among equal maxima
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (better(ov, oi, v, idx)) { v = ov; idx = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) { sv[warp] = v; si[warp] = idx; }
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < nw ? sv[lane] : -INFINITY;
+    idx = lane < nw ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (better(ov, oi, v, idx)) { v = ov; idx = oi; }
+    }
+    if (lane == 0) { sv[0] = v; si[0] = idx; }
+  }
+  __syncthreads();
+  v = sv[0];
+  idx = si[0];
+}
+
+// fp32 mode: logits [B,V] were materialised by the CUDA-core GEMM; scan them in LMHEAD_F32_PARTS column slabs per row.
+__global__ void __launch_bounds__(256) argmax_partials_kernel(const float* __restrict__ logits, int B, int V, float* __restrict__ part_val,
+                                                              int* __restrict__ part_idx) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const int b = blockIdx.x, part = blockIdx.y;
+  const int chunk = (V + LMHEAD_F32_PARTS - 1) / LMHEAD_F32_PARTS;
+  const int c0 = part * chunk, c1 = min(V, c0 + chunk);
+  float v = -INFINITY;
+  int idx = 0x7fffffff;
+  const float* row = logits + (size_t)b * V;
+  for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
+    const float x = row[c];
+    if (better(x, c, v, idx)) { v = x; idx = c; }
+  }
+  block_argmax(v, idx, sv, si);
+  if (threadIdx.x == 0) {
+    part_val[(size_t)part * B + b] = v;
+    part_idx[(size_t)part * B + b] = idx;
+  }
+}
+
+int launch_argmax_partials(const float* logits, int B, int V, float* part_val, int* part_idx, cudaStream_t st) {
+  dim3 grid(B, LMHEAD_F32_PARTS);
+  argmax_partials_kernel<<<grid, 256, 0, st>>>(logits, B, V, part_val, part_idx);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  return GIC_OK;
+}
+
+// One block per row: reduce the partial maxima, apply the EOS rules, record the token and build the next input.
+__global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
+  __shared__ float sv[4];
+  __shared__ int si[4];
+  __shared__ int s_tok;
+  const int b = blockIdx.x;
+  const int step = *a.d_step;
+  float v = -INFINITY;
+  int idx = 0x7fffffff;
+  for (int p = threadIdx.x; p < a.n_parts; p += blockDim.x) {
+    const float pv = a.part_val[(size_t)p * a.B + b];
+    const int pi = a.part_idx[(size_t)p * a.B + b];
+    if (better(pv, pi, v, idx)) { v = pv; idx = pi; }
+  }
+  block_argmax(v, idx, sv, si);
+  if (threadIdx.x == 0) {
+    int tok = idx;
+    unsigned char fin = a.finished[b];
+    if (tok == a.eos && !fin) {  // src/models.py:453-455
+      fin = 1;
+      a.finished[b] = 1;
+      a.first_eos[b] = step;
+    }
+    if (fin) tok = a.eos;  // :458-460
+    a.ids_out[(size_t)b * a.max_new + step] = (int64_t)tok;
+    s_tok = tok;
+  }
+  __syncthreads();
+  const int tok = s_tok;
+  const int pos = a.P + step;  // position of this token when it is fed back
+  if (pos < a.n_pos) {
+    const float* pe = a.wpe + (size_t)pos * a.d;
+    float* hn = a.h_next + (size_t)b * a.d;
+    if (a.wte_f32) {
+      const float* te = a.wte_f32 + (size_t)tok * a.d;
+      for (int c = threadIdx.x; c < a.d; c += blockDim.x) hn[c] = te[c] + pe[c];
+    } else {
+      const bf16* te = a.wte_bf16 + (size_t)tok * a.d;
+      for (int c = threadIdx.x; c < a.d; c += blockDim.x) hn[c] = __bfloat162float(te[c]) + pe[c];
+    }
+  }
+  // the last block to finish advances the device-side step / position counters (all blocks have read them by then)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(a.done_counter, 1);
+    if (t == (int)gridDim.x - 1) {
+      *a.done_counter = 0;
+      *a.d_pos = pos;
+      *a.d_step = step + 1;
+    }
+  }
+}
+
+int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st) {
+  finalize_token_kernel<<<a.B, 128, 0, st>>>(a);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  return GIC_OK;
+}
+
+__global__ void init_decode_state_kernel(unsigned char* finished, int* first_eos, int B, int max_new, int* d_step, int* d_pos,
+                                         int* done_counter, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) {
+    finished[i] = 0;
+    first_eos[i] = max_new;
+  }
+  if (i == 0) {
+    *d_step = 0;
+    *d_pos = P - 1;
+    *done_counter = 0;
+  }
+}
+
+int launch_init_decode_state(unsigned char* finished, int* first_eos, int B, int max_new, int* d_step, int* d_pos, int* done_counter,
+                             int P, cudaStream_t st) {
+  init_decode_state_kernel<<<ceil_div(B, 256), 256, 0, st>>>(finished, first_eos, B, max_new, d_step, d_pos, done_counter, P);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  return GIC_OK;
+}
+
+// L_gen of src/models.py:389-391: the reference loop stops BEFORE a step once every row has emitted EOS, so
+// L_gen = max_new if some row never finished, else max_b(first_eos[b]) + 1.
+__global__ void gen_len_kernel(const int* __restrict__ first_eos, int B, int max_new, int* gen_len_out) {
+  __shared__ int smax[32];
+  int m = 0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) m = max(m, first_eos[i] >= max_new ? max_new : first_eos[i] + 1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = max(m, smax[w]);
+    *gen_len_out = min(m, max_new);
+  }
+}
+
+int launch_gen_len(const int* first_eos, int B, int max_new, int* gen_len_out, cudaStream_t st) {
+  gen_len_kernel<<<1, 256, 0, st>>>(first_eos, B, max_new, gen_len_out);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  return GIC_OK;
+}
+
+}  // namespace gic

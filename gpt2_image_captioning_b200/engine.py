@@ -1,0 +1,173 @@
+"""CaptionEngine: Python owner of one `gic_engine` handle (packed weights) and its workspace.
+
+PyTorch owns the parameters (`model.gpt`, `model.mapping_network`); the engine holds packed copies derived from them
+and is rebuilt when they change (checkpoints are loaded into ordinary nn.Parameters).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _capi, ops
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class CaptionEngine:
+    def __init__(self, gpt, mapping_network, eos_token_id: int, task_prefix_embeds: torch.Tensor | None = None,
+                 dtype: str = "bf16", device: torch.device | str | None = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("CaptionEngine needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _capi.lib()
+        self.device = torch.device(device) if device is not None else next(gpt.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError(f"model parameters live on {self.device}; move the model to a CUDA device first (model.to('cuda'))")
+        if dtype not in _capi.DTYPES:
+            raise ValueError(f"unknown engine dtype {dtype!r}; choose from {sorted(_capi.DTYPES)}")
+        self.dtype = dtype
+        self._handle = C.c_void_p()
+        self._ws: torch.Tensor | None = None
+        gcfg = gpt.config
+        sd = {k: v for k, v in gpt.state_dict().items()}
+        msd = {k: v for k, v in mapping_network.state_dict().items()}
+        is_tfm = "prefix_const" in msd
+        d = int(gcfg.n_embd)
+        cfg = _capi.Config()
+        cfg.abi_version = _capi.ABI_VERSION
+        cfg.dtype = _capi.DTYPES[dtype]
+        cfg.n_embd, cfg.n_layer, cfg.n_head = d, int(gcfg.n_layer), int(gcfg.n_head)
+        cfg.vocab_size, cfg.n_positions = int(sd["transformer.wte.weight"].shape[0]), int(sd["transformer.wpe.weight"].shape[0])
+        cfg.mapper_kind = _capi.MAPPER_TRANSFORMER if is_tfm else _capi.MAPPER_MLP
+        cfg.prefix_length = int(mapping_network.prefix_length)
+        cfg.task_prefix_length = 0 if task_prefix_embeds is None else int(task_prefix_embeds.shape[0])
+        cfg.eos_token_id = int(eos_token_id)
+        if is_tfm:
+            cfg.embed_dim = int(msd["linear.weight"].shape[1])
+            cfg.hidden_length = int(mapping_network.hidden_length)
+            cfg.mapper_layers = len(mapping_network.transformer.layers)
+            cfg.mapper_heads = int(mapping_network.transformer.layers[0].self_attn.num_heads)
+        else:
+            cfg.embed_dim = int(msd["model.0.weight"].shape[1])
+            if "model.0.bias" not in msd:
+                raise NotImplementedError("MLP mapper without bias is not supported by the engine")
+        self.cfg = cfg
+        self.embed_dim, self.gpt_dim, self.vocab = cfg.embed_dim, d, cfg.vocab_size
+        self.prefix_total = cfg.prefix_length + cfg.task_prefix_length
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.gic_engine_create(C.byref(cfg), C.byref(self._handle)))
+            keep = []  # fp32 staging tensors must outlive the asynchronous pack kernels
+            stream = torch.cuda.current_stream().cuda_stream
+
+            def p(t):
+                t = _f32(t, self.device)
+                keep.append(t)
+                return t.data_ptr()
+
+            layers = (_capi.Gpt2LayerWeights * cfg.n_layer)()
+            for i in range(cfg.n_layer):
+                pre = f"transformer.h.{i}."
+                lw = layers[i]
+                lw.ln1_w, lw.ln1_b = p(sd[pre + "ln_1.weight"]), p(sd[pre + "ln_1.bias"])
+                lw.attn_w, lw.attn_b = p(sd[pre + "attn.c_attn.weight"]), p(sd[pre + "attn.c_attn.bias"])
+                lw.proj_w, lw.proj_b = p(sd[pre + "attn.c_proj.weight"]), p(sd[pre + "attn.c_proj.bias"])
+                lw.ln2_w, lw.ln2_b = p(sd[pre + "ln_2.weight"]), p(sd[pre + "ln_2.bias"])
+                lw.fc_w, lw.fc_b = p(sd[pre + "mlp.c_fc.weight"]), p(sd[pre + "mlp.c_fc.bias"])
+                lw.fc2_w, lw.fc2_b = p(sd[pre + "mlp.c_proj.weight"]), p(sd[pre + "mlp.c_proj.bias"])
+            gw = _capi.Gpt2Weights()
+            gw.wte, gw.wpe = p(sd["transformer.wte.weight"]), p(sd["transformer.wpe.weight"])
+            gw.lnf_w, gw.lnf_b = p(sd["transformer.ln_f.weight"]), p(sd["transformer.ln_f.bias"])
+            gw.layers = layers
+            _capi.check(self.lib.gic_engine_load_gpt2(self._handle, C.byref(gw), stream))
+            if is_tfm:
+                tl = (_capi.TfmLayerWeights * cfg.mapper_layers)()
+                for i in range(cfg.mapper_layers):
+                    pre = f"transformer.layers.{i}."
+                    t = tl[i]
+                    t.norm1_w, t.norm1_b = p(msd[pre + "norm1.weight"]), p(msd[pre + "norm1.bias"])
+                    t.norm2_w, t.norm2_b = p(msd[pre + "norm2.weight"]), p(msd[pre + "norm2.bias"])
+                    t.in_proj_w, t.in_proj_b = p(msd[pre + "self_attn.in_proj_weight"]), p(msd[pre + "self_attn.in_proj_bias"])
+                    t.out_proj_w, t.out_proj_b = p(msd[pre + "self_attn.out_proj.weight"]), p(msd[pre + "self_attn.out_proj.bias"])
+                    t.lin1_w, t.lin1_b = p(msd[pre + "linear1.weight"]), p(msd[pre + "linear1.bias"])
+                    t.lin2_w, t.lin2_b = p(msd[pre + "linear2.weight"]), p(msd[pre + "linear2.bias"])
+                tw = _capi.TfmMapperWeights()
+                tw.linear_w, tw.linear_b = p(msd["linear.weight"]), p(msd["linear.bias"])
+                tw.prefix_const = p(msd["prefix_const"])
+                tw.layers = tl
+                _capi.check(self.lib.gic_engine_load_tfm_mapper(self._handle, C.byref(tw), stream))
+            else:
+                mw = _capi.MlpMapperWeights()
+                mw.w1, mw.b1 = p(msd["model.0.weight"]), p(msd["model.0.bias"])
+                mw.w2, mw.b2 = p(msd["model.2.weight"]), p(msd["model.2.bias"])
+                _capi.check(self.lib.gic_engine_load_mlp_mapper(self._handle, C.byref(mw), stream))
+            if task_prefix_embeds is not None:
+                _capi.check(self.lib.gic_engine_load_task_prefix(self._handle, p(task_prefix_embeds), stream))
+            torch.cuda.current_stream().synchronize()
+            del keep
+
+    # ------------------------------------------------------------------------------------------------------------
+    @property
+    def handle(self) -> int:
+        return self._handle.value
+
+    def weight_bytes(self) -> int:
+        return int(self.lib.gic_engine_weight_bytes(self._handle))
+
+    def workspace(self, batch: int, max_new: int, beams: int = 1) -> torch.Tensor:
+        need = int(self.lib.gic_workspace_bytes(self._handle, batch, max_new, beams))
+        if need == 0:
+            raise ValueError(f"bad workspace request batch={batch} max_new={max_new} beams={beams}")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def close(self) -> None:
+        if self._handle:
+            self.lib.gic_engine_destroy(self._handle)
+            self._handle = C.c_void_p()
+        self._ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _check_x(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != 2 or x.shape[1] != self.embed_dim:
+            raise ValueError(f"image_embeddings must be [batch, {self.embed_dim}], got {tuple(x.shape)}")
+        return x.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+
+    def mapper_forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self._check_x(x)
+        B = x.shape[0]
+        out = torch.empty(B, self.prefix_total, self.gpt_dim, dtype=torch.float32, device=self.device)
+        if B == 0:
+            return out
+        ops.mapper_forward(self.handle, x, out, self.workspace(B, 0))
+        return out
+
+    def generate_greedy(self, x: torch.Tensor, max_new_tokens: int, return_logits: bool = False):
+        """ids int64 [B, max_new_tokens] (full length), gen_len int32 [1] (device) [, logits fp32 [max_new, B, V]]."""
+        x = self._check_x(x)
+        B = x.shape[0]
+        ids = torch.empty(B, max_new_tokens, dtype=torch.int64, device=self.device)
+        gen_len = torch.zeros(1, dtype=torch.int32, device=self.device)
+        logits = torch.empty(max_new_tokens, B, self.vocab, dtype=torch.float32, device=self.device) if return_logits else None
+        if B > 0 and max_new_tokens > 0:
+            ops.generate_greedy(self.handle, x, max_new_tokens, ids, gen_len, logits, self.workspace(B, max_new_tokens))
+        return (ids, gen_len, logits) if return_logits else (ids, gen_len)
+
+    def generate_beam(self, x: torch.Tensor, max_new_tokens: int, num_beams: int = 5, length_penalty: float = 1.0):
+        x = self._check_x(x)
+        B = x.shape[0]
+        ids = torch.empty(B, max_new_tokens, dtype=torch.int64, device=self.device)
+        scores = torch.empty(B, dtype=torch.float32, device=self.device)
+        if B > 0 and max_new_tokens > 0:
+            ops.generate_beam(self.handle, x, max_new_tokens, num_beams, length_penalty, ids, scores,
+                              self.workspace(B, max_new_tokens, num_beams))
+        return ids, scores

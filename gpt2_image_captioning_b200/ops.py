@@ -1,0 +1,95 @@
+"""torch custom ops (namespace `gic::`) over the C ABI: each op passes `tensor.data_ptr()` + the current CUDA stream
+to libgic_b200.so.  PyTorch is plumbing here (device memory, streams); the arithmetic is in the CUDA library."""
+from __future__ import annotations
+
+import torch
+
+from . import _capi
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*tensors: torch.Tensor) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("gic ops need CUDA tensors: libgic_b200 has no CPU path")
+
+
+@torch.library.custom_op("gic::mapper_forward", mutates_args=("prefix_out", "workspace"))
+def mapper_forward(engine: int, image_embeddings: torch.Tensor, prefix_out: torch.Tensor, workspace: torch.Tensor) -> None:
+    _need_cuda(image_embeddings, prefix_out, workspace)
+    L = _capi.lib()
+    _capi.check(L.gic_mapper_forward(engine, _ptr(image_embeddings), image_embeddings.shape[0], _ptr(prefix_out), _ptr(workspace),
+                                     workspace.numel(), _stream()))
+
+
+@torch.library.custom_op("gic::generate_greedy", mutates_args=("ids_out", "gen_len_out", "logits_out", "workspace"))
+def generate_greedy(engine: int, image_embeddings: torch.Tensor, max_new_tokens: int, ids_out: torch.Tensor,
+                    gen_len_out: torch.Tensor, logits_out: torch.Tensor | None, workspace: torch.Tensor) -> None:
+    _need_cuda(image_embeddings, ids_out, gen_len_out, logits_out, workspace)
+    L = _capi.lib()
+    _capi.check(L.gic_generate_greedy(engine, _ptr(image_embeddings), image_embeddings.shape[0], max_new_tokens, _ptr(ids_out),
+                                      _ptr(gen_len_out), _ptr(logits_out), _ptr(workspace), workspace.numel(), _stream()))
+
+
+@torch.library.custom_op("gic::generate_beam", mutates_args=("ids_out", "scores_out", "workspace"))
+def generate_beam(engine: int, image_embeddings: torch.Tensor, max_new_tokens: int, num_beams: int, length_penalty: float,
+                  ids_out: torch.Tensor, scores_out: torch.Tensor, workspace: torch.Tensor) -> None:
+    _need_cuda(image_embeddings, ids_out, scores_out, workspace)
+    L = _capi.lib()
+    _capi.check(L.gic_generate_beam(engine, _ptr(image_embeddings), image_embeddings.shape[0], max_new_tokens, num_beams,
+                                    float(length_penalty), _ptr(ids_out), _ptr(scores_out), _ptr(workspace), workspace.numel(),
+                                    _stream()))
+
+
+@torch.library.custom_op("gic::kv_reorder", mutates_args=("kv_dst",))
+def kv_reorder(engine: int, kv_src: torch.Tensor, kv_dst: torch.Tensor, beam_idx: torch.Tensor, ctx_len: int, t_max: int) -> None:
+    _need_cuda(kv_src, kv_dst, beam_idx)
+    L = _capi.lib()
+    _capi.check(L.gic_kv_reorder(engine, _ptr(kv_src), _ptr(kv_dst), _ptr(beam_idx), beam_idx.numel(), ctx_len, t_max, _stream()))
+
+
+@torch.library.custom_op("gic::topk_ip", mutates_args=("scores_out", "idx_out", "workspace"))
+def topk_ip(queries: torch.Tensor, db: torch.Tensor, k: int, scores_out: torch.Tensor, idx_out: torch.Tensor,
+            workspace: torch.Tensor) -> None:
+    _need_cuda(queries, db, scores_out, idx_out, workspace)
+    L = _capi.lib()
+    _capi.check(L.gic_topk_ip(_ptr(queries), _ptr(db), queries.shape[0], db.shape[0], db.shape[1], k, _ptr(scores_out), _ptr(idx_out),
+                              _ptr(workspace), workspace.numel(), _stream()))
+
+
+@torch.library.custom_op("gic::select_caption_rows", mutates_args=("rows_out",))
+def select_caption_rows(scores: torch.Tensor, idx: torch.Tensor, cap_row_start: torch.Tensor, cap_row_ids: torch.Tensor | None,
+                        top_i: int, top_k: int, rows_out: torch.Tensor) -> None:
+    _need_cuda(scores, idx, cap_row_start, cap_row_ids, rows_out)
+    L = _capi.lib()
+    _capi.check(L.gic_select_caption_rows(_ptr(scores), _ptr(idx), scores.shape[0], scores.shape[1], _ptr(cap_row_start),
+                                          _ptr(cap_row_ids), top_i, top_k, _ptr(rows_out), _stream()))
+
+
+@torch.library.custom_op("gic::gather_aggregate_add", mutates_args=("out",))
+def gather_aggregate_add(queries: torch.Tensor, cap_db: torch.Tensor, rows: torch.Tensor, aggregation: int, out: torch.Tensor) -> None:
+    _need_cuda(queries, cap_db, rows, out)
+    L = _capi.lib()
+    _capi.check(L.gic_gather_aggregate_add(_ptr(queries), _ptr(cap_db), _ptr(rows), queries.shape[0], rows.shape[1], queries.shape[1],
+                                           aggregation, _ptr(out), _stream()))
+
+
+@torch.library.custom_op("gic::test_gemm", mutates_args=("C",))
+def test_gemm(dtype: int, A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor | None, C: torch.Tensor, epilogue: int) -> None:
+    _need_cuda(A, W, bias, C)
+    L = _capi.lib()
+    _capi.check(L.gic_test_gemm(dtype, _ptr(A), _ptr(W), _ptr(bias), _ptr(C), A.shape[0], W.shape[0], A.shape[1], epilogue, _stream()))
+
+
+@torch.library.custom_op("gic::test_layernorm", mutates_args=("y",))
+def test_layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, y: torch.Tensor) -> None:
+    _need_cuda(x, w, b, y)
+    L = _capi.lib()
+    _capi.check(L.gic_test_layernorm(_ptr(x), _ptr(w), _ptr(b), _ptr(y), x.shape[0], x.shape[1], _stream()))

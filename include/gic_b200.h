@@ -1,0 +1,178 @@
+/* gic_b200.h -- C ABI of libgic_b200.so: the B200 (sm_100a) caption-generation hot path.
+ *
+ * The reference (thenoobychocobo/gpt2-image-captioning) has no FFI of its own: the path is a Python
+ * class API (`ImageCaptioningModel.generate`, src/models.py:327-477; `RetrievalAugmentedTransformer
+ * .generate`, src/models.py:748-771).  This header is the boundary a maintainer binds with ctypes
+ * (INTEGRATION.md shows the stub); each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked `dev` is a DEVICE pointer owned by the caller
+ *   - no ownership transfer: the caller allocates outputs and one workspace (size from
+ *     gic_workspace_bytes); the opaque engine handle owns only its packed weight copies
+ *   - every function returns GIC_OK (0) or a negative error code and never throws;
+ *     gic_last_error() returns the message of the last failure on the calling thread
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are asynchronous
+ *     on that stream unless stated otherwise; one host thread per engine handle
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with GIC_ERR_CUDA
+ */
+#ifndef GIC_B200_H_
+#define GIC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GIC_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GIC_API __attribute__((visibility("default")))
+#else
+#define GIC_API
+#endif
+
+enum { GIC_OK = 0, GIC_ERR_INVALID = -1, GIC_ERR_CUDA = -2, GIC_ERR_UNSUPPORTED = -3, GIC_ERR_WORKSPACE = -4 };
+
+/* arithmetic modes.  F32: CUDA-core FFMA GEMMs, fp32 everywhere (token-exact parity mode).
+ * BF16: bf16 weights/activations/KV cache, tcgen05 MMA with fp32 TMEM accumulators, fp32 residual stream,
+ * LayerNorm statistics, softmax and logits.  BF16X2: every GEMM operand split hi+lo (two bf16), three
+ * tcgen05 MMAs per product -- ~16 mantissa bits on the tensor cores. */
+enum { GIC_DTYPE_F32 = 0, GIC_DTYPE_BF16 = 1, GIC_DTYPE_BF16X2 = 2 };
+enum { GIC_MAPPER_MLP = 0, GIC_MAPPER_TRANSFORMER = 1 };
+enum { GIC_AGG_MEAN = 0, GIC_AGG_MAX = 1, GIC_AGG_SUM_NORM = 2 };
+
+typedef struct gic_engine gic_engine; /* opaque */
+
+typedef struct gic_config {
+  int32_t abi_version;     /* GIC_ABI_VERSION */
+  int32_t dtype;           /* GIC_DTYPE_* */
+  /* GPT-2 (HF GPT2Config): small 768/12/12, medium 1024/24/16, large 1280/36/20; head_dim must be 64 */
+  int32_t n_embd, n_layer, n_head, vocab_size, n_positions;
+  /* mapping network (src/models.py:14-174) */
+  int32_t mapper_kind;     /* GIC_MAPPER_* */
+  int32_t embed_dim;       /* E: 512 CLIP ViT-B/32, 1024 DINOv3 / ViT-L */
+  int32_t prefix_length;   /* image prefix tokens P */
+  int32_t hidden_length;   /* transformer mapper: image tokens Hl (src/models.py:119) */
+  int32_t mapper_layers;   /* transformer mapper: encoder layers (8) */
+  int32_t mapper_heads;    /* transformer mapper: nhead (8, src/models.py:131) */
+  int32_t task_prefix_length; /* rows of task_prefix_embeds appended AFTER the image prefix (src/models.py:364-375); 0 = none */
+  int32_t eos_token_id;    /* tokenizer.eos_token_id (src/models.py:348); 50256 for GPT-2 */
+} gic_config;
+
+/* fp32 parameter tables in the reference's NATIVE layouts (HF Conv1D weights are [in,out]; nn.Linear and
+ * wte are [out,in]).  The engine makes its own packed copies; the caller's tensors are not referenced
+ * after the load call's stream work completes. */
+typedef struct gic_gpt2_layer_weights {
+  const float *ln1_w, *ln1_b;     /* [d] */
+  const float *attn_w, *attn_b;   /* c_attn  [d,3d], [3d]   (HF modeling_gpt2.py:185) */
+  const float *proj_w, *proj_b;   /* c_proj  [d,d],  [d]    (:223) */
+  const float *ln2_w, *ln2_b;     /* [d] */
+  const float *fc_w, *fc_b;       /* mlp.c_fc   [d,4d], [4d] (:238-243) */
+  const float *fc2_w, *fc2_b;     /* mlp.c_proj [4d,d], [d] */
+} gic_gpt2_layer_weights;
+
+typedef struct gic_gpt2_weights {
+  const float *wte;               /* [V,d], tied LM head (HF :646,651) */
+  const float *wpe;               /* [n_positions,d] */
+  const float *lnf_w, *lnf_b;     /* [d] */
+  const gic_gpt2_layer_weights* layers; /* host array of n_layer entries (device pointers inside) */
+} gic_gpt2_weights;
+
+typedef struct gic_mlp_mapper_weights { /* MLPMappingNetwork.model.{0,2} (src/models.py:52-56) */
+  const float *w1, *b1;           /* [P*d/2, E], [P*d/2] */
+  const float *w2, *b2;           /* [P*d, P*d/2], [P*d] */
+} gic_mlp_mapper_weights;
+
+typedef struct gic_tfm_layer_weights { /* nn.TransformerEncoderLayer, norm_first, relu (src/models.py:129-136) */
+  const float *norm1_w, *norm1_b, *norm2_w, *norm2_b;   /* [d] */
+  const float *in_proj_w, *in_proj_b;                   /* [3d,d], [3d]  (q,k,v order) */
+  const float *out_proj_w, *out_proj_b;                 /* [d,d], [d] */
+  const float *lin1_w, *lin1_b;                         /* [4d,d], [4d] */
+  const float *lin2_w, *lin2_b;                         /* [d,4d], [d] */
+} gic_tfm_layer_weights;
+
+typedef struct gic_tfm_mapper_weights { /* TransformerMappingNetwork (src/models.py:119-139) */
+  const float *linear_w, *linear_b;                     /* [Hl*d, E], [Hl*d] */
+  const float *prefix_const;                            /* [P, d] */
+  const gic_tfm_layer_weights* layers;                  /* host array of mapper_layers entries */
+} gic_tfm_mapper_weights;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------ */
+GIC_API const char* gic_last_error(void);
+GIC_API int gic_abi_version(void);
+GIC_API int gic_device_check(void); /* GIC_OK iff device 0.. current device is sm_100 (compute capability 10.x) */
+
+/* replaces: model construction + `.to(device)` (src/eval.py:189-190) for the engine's packed weights */
+GIC_API int gic_engine_create(const gic_config* cfg, gic_engine** out);
+GIC_API int gic_engine_destroy(gic_engine* e);
+GIC_API int gic_engine_load_gpt2(gic_engine* e, const gic_gpt2_weights* w, void* stream);
+GIC_API int gic_engine_load_mlp_mapper(gic_engine* e, const gic_mlp_mapper_weights* w, void* stream);
+GIC_API int gic_engine_load_tfm_mapper(gic_engine* e, const gic_tfm_mapper_weights* w, void* stream);
+GIC_API int gic_engine_load_task_prefix(gic_engine* e, const float* task_prefix_embeds /* dev [Tp,d] */, void* stream);
+GIC_API size_t gic_engine_weight_bytes(const gic_engine* e); /* bytes of packed weights held by the handle */
+
+/* workspace for one generate call: activations + KV cache [L][2][rows][H][T_max][64] + LM-head partials.
+ * rows = batch * max(1, num_beams); T_max = prefix_length + task_prefix_length + max_new_tokens. */
+GIC_API size_t gic_workspace_bytes(const gic_engine* e, int batch, int max_new_tokens, int num_beams);
+
+/* ---- the hot path ---------------------------------------------------------------------------------- */
+/* replaces MLPMappingNetwork.forward / TransformerMappingNetwork.forward (src/models.py:58-74,141-174)
+ * plus the task-prefix concat (:364-375).  prefix_out: dev fp32 [B, P_total, d]. */
+GIC_API int gic_mapper_forward(gic_engine* e, const float* image_embeddings /* dev [B,E] */, int batch,
+                       float* prefix_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces the greedy branch of ImageCaptioningModel.generate (src/models.py:327-477, temperature == 0):
+ * mapper -> prefill -> (max_new_tokens-1) KV-cached decode steps with the LM head fused with argmax
+ * (ties -> lowest index), EOS rows keep emitting EOS (:453-460).  Always writes the full
+ * ids_out dev int64 [B, max_new_tokens]; *gen_len_out (dev int32, may be NULL) receives L_gen of
+ * :390-391 (the caller slices [:, :L_gen]).  logits_out (dev fp32 [max_new_tokens, B, V], may be NULL)
+ * receives every step's last-position logits -- a parity/debug tap, not used by the product path. */
+GIC_API int gic_generate_greedy(gic_engine* e, const float* image_embeddings /* dev [B,E] */, int batch, int max_new_tokens,
+                        int64_t* ids_out, int32_t* gen_len_out, float* logits_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Beam search (not in the reference; semantics of HF GenerationMixin._beam_search, generation/utils.py:3076-3385,
+ * early_stopping=False, length_penalty given, num_return_sequences=1): ids_out dev int64 [B, max_new_tokens]
+ * padded with eos; scores_out dev fp32 [B] (may be NULL). */
+GIC_API int gic_generate_beam(gic_engine* e, const float* image_embeddings, int batch, int max_new_tokens, int num_beams,
+                      float length_penalty, int64_t* ids_out, float* scores_out,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces DynamicCache.reorder_cache / index_select(0, beam_idx) per layer (HF cache_utils.py:81-85):
+ * dst[l][kv][r] = src[l][kv][beam_idx[r]] for the first `ctx_len` positions.  Element type follows the engine dtype. */
+GIC_API int gic_kv_reorder(gic_engine* e, const void* kv_src, void* kv_dst, const int32_t* beam_idx /* dev [rows] */,
+                   int rows, int ctx_len, int t_max, void* stream);
+
+/* replaces faiss IndexFlatIP.search as called by retrieve_images_by_vector_similarity
+ * (src/database/faiss_store.py:153-155): exact inner product of q [B,D] against db [N,D] (fp32, row-major),
+ * k best per row, descending, ties -> lowest index; scores_out dev fp32 [B,k], idx_out dev int64 [B,k]
+ * (-1 / -inf when k > N).  workspace from gic_topk_workspace_bytes. */
+GIC_API size_t gic_topk_workspace_bytes(int batch, int n_rows, int dim, int k);
+GIC_API int gic_topk_ip(const float* queries, const float* db, int batch, int n_rows, int dim, int k,
+                float* scores_out, int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* replaces the Python hit filter + caption-row selection (faiss_store.py:160-183,208-229) on integer ids:
+ * image hits -> first top_i with idx != -1 and score <= 0.9999 -> their caption rows via a CSR table
+ * (cap_row_start dev int64 [N_img+1]; the caption rows of image i are cap_row_ids[start[i] .. start[i+1]), or the
+ * range itself when cap_row_ids is NULL) in hit order, first top_k; rows_out dev int64 [B, top_k], -1 = zero padding row. */
+GIC_API int gic_select_caption_rows(const float* scores, const int64_t* idx, int batch, int k_searched,
+                            const int64_t* cap_row_start, const int64_t* cap_row_ids, int top_i, int top_k,
+                            int64_t* rows_out, void* stream);
+
+/* replaces get_caption_embeddings' reconstruct loop + RetrievalAggregator.forward (faiss_store.py:229-251,
+ * src/models.py:589-625): out[b] = q[b] + agg_k(cap_db[rows[b,k]]) with zero rows for -1 (padding counts in the mean). */
+GIC_API int gic_gather_aggregate_add(const float* queries, const float* cap_db, const int64_t* rows, int batch, int top_k, int dim,
+                             int aggregation, float* out, void* stream);
+
+/* ---- kernel-level entry points (unit tests / profiling; same kernels the path uses) --------------------- */
+/* C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias[N]) ; epilogue: 0 none, 1 tanh, 2 gelu_tanh, 3 relu, 4 += residual(fp32 C in place).
+ * dtype F32: A,W,C fp32 (CUDA cores).  BF16 / BF16X2: A,W fp32 inputs are packed internally, C fp32. */
+GIC_API int gic_test_gemm(int dtype, const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int epilogue, void* stream);
+GIC_API int gic_test_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIC_B200_H_ */

@@ -1,0 +1,178 @@
+"""Kernel-level parity (run with -m gpu on a B200): each kernel, called through the C ABI (torch custom ops ->
+libgic_b200.so), against a plain fp32 PyTorch / numpy expression of the same op."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import captioner as oc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ops():
+    from gpt2_image_captioning_b200 import ops, _capi
+    return ops, _capi
+
+
+def _epi_ref(y, epi, res=None):
+    if epi == 1:
+        return torch.tanh(y)
+    if epi == 2:
+        return oc.gelu_new(y)
+    if epi == 3:
+        return torch.relu(y)
+    if epi == 4:
+        return y + res
+    return y
+
+
+SHAPES = [(64, 2304, 768), (1, 768, 768), (130, 1000, 512), (300, 3072, 768), (77, 50257, 128), (1024, 768, 3072), (8, 256, 64)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("epi", [0, 1, 2, 3, 4])
+def test_sgemm_fp32(M, N, K, epi):
+    ops, capi = _ops()
+    if epi and N > 4000:
+        pytest.skip("epilogues covered on the smaller shapes")
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N + K + epi)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    C = res.clone() if epi == 4 else torch.empty(M, N, device=DEV)
+    ops.test_gemm(capi.DTYPE_F32, A, W, b, C, epi)
+    ref = _epi_ref(A.double() @ W.double().t() + b.double(), epi, res.double())
+    err = (C.double() - ref).abs().max().item()
+    assert err <= 2e-5 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES + [(1024, 2304, 768), (10240, 768, 768), (129, 40, 3840)])
+@pytest.mark.parametrize("mode", ["bf16", "bf16x2"])
+def test_gemm_tcgen05(M, N, K, mode):
+    """bf16: against the same product with both operands rounded to bf16 (fp64 accumulate) -> only accumulation
+    order differs.  bf16x2 (hi+lo split, 3 MMAs): against the exact fp64 product, ~2^-16 relative per term."""
+    ops, capi = _ops()
+    g = torch.Generator(device="cpu").manual_seed(M + 3 * N + 5 * K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    C = torch.empty(M, N, device=DEV)
+    dt = capi.DTYPE_BF16 if mode == "bf16" else capi.DTYPE_BF16X2
+    ops.test_gemm(dt, A, W, b, C, 0)
+    torch.cuda.synchronize()
+    if mode == "bf16":
+        ref = A.bfloat16().double() @ W.bfloat16().double().t() + b.double()
+        tol = 2e-5
+    else:
+        ref = A.double() @ W.double().t() + b.double()
+        tol = 6e-5
+    scale = (A.double().abs() @ W.double().abs().t()).max().item()  # error scales with sum |a||w|
+    err = (C.double() - ref).abs().max().item()
+    assert err <= tol * scale, f"{mode} M={M} N={N} K={K}: max abs err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("epi", [1, 2, 3, 4])
+def test_gemm_tcgen05_epilogues(epi):
+    ops, capi = _ops()
+    M, N, K = 200, 384, 256
+    g = torch.Generator(device="cpu").manual_seed(epi)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    res = torch.randn(M, N, generator=g).to(DEV)
+    C = res.clone() if epi == 4 else torch.empty(M, N, device=DEV)
+    ops.test_gemm(capi.DTYPE_BF16X2, A, W, b, C, epi)
+    ref = _epi_ref(A.double() @ W.double().t() + b.double(), epi, res.double())
+    assert (C.double() - ref).abs().max().item() <= 2e-4
+
+
+@pytest.mark.parametrize("rows,d", [(1, 768), (1000, 768), (33, 1024), (7, 1280), (5, 128)])
+def test_layernorm(rows, d):
+    ops, _ = _ops()
+    g = torch.Generator(device="cpu").manual_seed(rows + d)
+    x = (torch.randn(rows, d, generator=g) * 3 + 1).to(DEV)
+    w = torch.randn(d, generator=g).to(DEV)
+    b = torch.randn(d, generator=g).to(DEV)
+    y = torch.empty_like(x)
+    ops.test_layernorm(x, w, b, y)
+    ref = torch.nn.functional.layer_norm(x, (d,), w, b, 1e-5)
+    assert (y - ref).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("B,N,k", [(37, 5000, 14), (1, 100, 5), (5, 70000, 16), (3, 7, 12), (64, 40000, 5), (2, 33000, 30)])
+def test_topk_ip_exact_indices(B, N, k):
+    """Indices bit-exact against exact IndexFlatIP semantics (descending, ties -> lowest index), incl. k > N padding,
+    duplicate database rows (exact ties) and more than one 32768-row chunk."""
+    from gpt2_image_captioning_b200.database import _GpuFlatIndex
+    rng = np.random.default_rng(B * 31 + N + k)
+    D = 64
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    if N > 50:
+        db[N // 2] = db[3]  # exact duplicate -> tie
+        db[N - 1] = db[3]
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    q[0] = db[3]
+    idx = _GpuFlatIndex(torch.from_numpy(db).to(DEV))
+    s, i = idx.search(q, k)
+    # integer-valued inputs would make scores exact; with real data compare to the fp64 ordering and allow a swap only
+    # where the exact scores are closer than fp32 rounding
+    exact = q.astype(np.float64) @ db.astype(np.float64).T
+    ws, wi = oc.flat_ip_search(db, q, k)
+    for b in range(B):
+        for j in range(k):
+            if i[b, j] != wi[b, j]:
+                assert i[b, j] >= 0 and wi[b, j] >= 0
+                assert abs(exact[b, i[b, j]] - exact[b, wi[b, j]]) < 1e-6, (b, j, i[b], wi[b])
+    valid = wi >= 0
+    np.testing.assert_allclose(s[valid], ws[valid], atol=2e-6)
+    assert np.all(i[~valid] == -1) and np.all(np.isneginf(s[~valid]))
+    if N > 50:  # the three identical rows must come out in index order
+        pos = [int(np.where(i[0] == r)[0][0]) for r in (3, N // 2, N - 1) if r in i[0]]
+        assert pos == sorted(pos)
+
+
+def test_topk_ip_integer_scores_bit_exact():
+    """Integer-valued vectors make every inner product exact in fp32, so scores AND indices must be bit-identical."""
+    from gpt2_image_captioning_b200.database import _GpuFlatIndex
+    rng = np.random.default_rng(5)
+    db = rng.integers(-3, 4, (9000, 32)).astype(np.float32)
+    q = rng.integers(-3, 4, (20, 32)).astype(np.float32)
+    s, i = _GpuFlatIndex(torch.from_numpy(db).to(DEV)).search(q, 15)
+    ws, wi = oc.flat_ip_search(db, q, 15)
+    assert np.array_equal(i, wi) and np.array_equal(s, ws)
+
+
+def test_retrieval_against_reference_fixture():
+    """GpuFlatStore vs what the reference's own faiss_store functions + RetrievalAggregator produced (rat_retrieval.npz)."""
+    from gpt2_image_captioning_b200 import GpuFlatStore
+    g = gu.load("rat_retrieval")
+    rng = np.random.default_rng(int(g["db_seed"]))
+    n_img, D = int(g["n_img"]), 512
+    img = rng.standard_normal((n_img, D)).astype(np.float32)
+    img /= np.linalg.norm(img, axis=1, keepdims=True)
+    counts = rng.integers(0, 7, n_img)
+    owner = np.repeat(np.arange(n_img), counts)
+    cap = rng.standard_normal((len(owner), D)).astype(np.float32)
+    names = [f"img_{i:06d}.jpg" for i in range(n_img)]
+    store = GpuFlatStore(img, cap, names, [{"filename": names[o], "caption_id": j} for j, o in enumerate(owner)], device=DEV)
+    q = torch.from_numpy(g["q"])
+    for (k, i) in [(10, 4), (20, 6), (5, 1)]:
+        ret = store.retrieve_caption_embeddings(q.to(DEV), top_i=i, top_k=k).cpu().numpy()
+        assert np.array_equal(ret, g[f"ret_k{k}_i{i}"]), (k, i)
+        aug = store.retrieve_and_aggregate(q, top_i=i, top_k=k, aggregation="mean")
+        assert aug.device.type == "cpu"
+        np.testing.assert_allclose(aug.numpy(), g[f"aug_k{k}_i{i}"], atol=1e-6)
+    # other pooling modes against the PyTorch expression of RetrievalAggregator (src/models.py:593-606)
+    ret = torch.from_numpy(g["ret_k10_i4"])
+    want_max = q + ret.max(dim=1)[0]
+    want_sn = q + torch.nn.functional.normalize(torch.nn.functional.normalize(ret, p=2, dim=2).sum(dim=1), p=2, dim=1)
+    np.testing.assert_allclose(store.retrieve_and_aggregate(q, 4, 10, "max").numpy(), want_max.numpy(), atol=1e-6)
+    np.testing.assert_allclose(store.retrieve_and_aggregate(q, 4, 10, "sum_norm").numpy(), want_sn.numpy(), atol=2e-6)
+    # duck-typed faiss surface
+    s, ix = store.image_index.search(g["q"][:3], 14)
+    assert s.shape == (3, 14) and ix.dtype == np.int64
+    assert np.array_equal(store.caption_index.reconstruct(7), cap[7])

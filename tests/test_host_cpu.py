@@ -1,0 +1,203 @@
+"""CPU-only checks (-m "not gpu"): the C-ABI library loads and exports every symbol the header declares, the host-side
+mirror keeps the reference's API surface, the product path fails loudly without CUDA, and the N>1 sharding logic works
+over gloo with world_size 2."""
+import inspect
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import captioner as oc
+from oracle import ref_harness
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="session", autouse=True)
+def built_library():
+    lib = os.path.join(ROOT, "gpt2_image_captioning_b200", "libgic_b200.so")
+    if not os.path.isfile(lib):
+        import __graft_entry__
+        __graft_entry__.build()
+    return lib
+
+
+def test_library_exports_every_declared_symbol(built_library):
+    from gpt2_image_captioning_b200 import _capi
+    header = open(os.path.join(ROOT, "include", "gic_b200.h")).read()
+    declared = set(re.findall(r"GIC_API\s+[\w\s\*]+?\b(gic_\w+)\s*\(", header))
+    assert len(declared) >= 20
+    assert declared == set(_capi.SIGNATURES), declared ^ set(_capi.SIGNATURES)
+    L = _capi.lib()  # dlopen; raises if a symbol is missing
+    for name in declared:
+        assert hasattr(L, name)
+    assert L.gic_abi_version() == _capi.ABI_VERSION
+    nm = subprocess.run(["nm", "-D", "--defined-only", built_library], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (gic_\w+)", nm))
+    assert declared <= exported
+
+
+def test_library_is_sm100a_tensor_core_code(built_library):
+    sass = subprocess.run(["cuobjdump", "-sass", built_library], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):  # tcgen05.mma / TMA / tcgen05.ld (B200_PROFILING.md)
+        assert mnemonic in sass, mnemonic
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_product_path_fails_loudly_without_cuda():
+    from gpt2_image_captioning_b200 import ImageCaptioningModel, MLPMappingNetwork, GpuFlatStore, _capi
+    spec = oc.ModelSpec(gpt="tiny", embed_dim=64, prefix_length=4)
+    gpt, mref = oc.build_modules(spec)
+    mapper = MLPMappingNetwork(4, 64, 128)
+    model = ImageCaptioningModel(mapper, tokenizer=ref_harness.StubTokenizer(), gpt=gpt)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        model.generate(image_embeddings=torch.zeros(2, 64), max_length=3, temperature=0.0)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        GpuFlatStore(np.zeros((4, 8), np.float32), np.zeros((4, 8), np.float32), ["a"] * 4, [{"filename": "a"}] * 4)
+    assert _capi.lib().gic_device_check() != 0  # no device -> error code, not a crash
+    assert b"" != _capi.lib().gic_last_error()
+
+
+def test_no_product_import_of_the_oracle():
+    pkg = os.path.join(ROOT, "gpt2_image_captioning_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+
+
+def test_mirror_classes_keep_reference_surface():
+    import gpt2_image_captioning_b200 as pkg
+    spec = oc.ModelSpec(gpt="tiny", embed_dim=64, prefix_length=4)
+    gpt, mref = oc.build_modules(spec)
+    mapper = pkg.MLPMappingNetwork(prefix_length=4, embed_dim=64, gpt_dim=128)
+    assert set(mapper.state_dict()) == set(mref.state_dict())
+    tfm = pkg.TransformerMappingNetwork(embed_dim=64, gpt_dim=128, prefix_length=5, hidden_length=3, num_layers=2)
+    assert tfm(torch.zeros(2, 64)).shape == (2, 5, 128)
+    model = pkg.RetrievalAugmentedTransformer(64, 4, "attention", mapper, tokenizer=ref_harness.StubTokenizer(), gpt=gpt)
+    keys = set(model.state_dict())
+    assert any(k.startswith("mapping_network.model.0.") for k in keys) and any(k.startswith("gpt.transformer.h.0.") for k in keys)
+    assert {"aggregator.attention_proj.weight", "aggregator.attention_proj.bias"} <= keys
+    sig = inspect.signature(pkg.ImageCaptioningModel.generate)
+    assert list(sig.parameters)[:5] == ["self", "image_embeddings", "max_length", "temperature", "top_p"]
+    assert (sig.parameters["max_length"].default, sig.parameters["temperature"].default, sig.parameters["top_p"].default) == (50, 1.0, 0.9)
+    rsig = inspect.signature(pkg.RetrievalAugmentedTransformer.generate)
+    assert list(rsig.parameters)[:5] == ["self", "db_store", "top_k", "top_i", "image_embeddings"]
+    # training forward stays plain PyTorch and works on the CPU
+    out = pkg.ImageCaptioningModel(mapper, tokenizer=ref_harness.StubTokenizer(), gpt=gpt).forward(
+        caption_token_ids=torch.randint(0, 100, (2, 6)), image_embeddings=torch.randn(2, 64),
+        attention_mask=torch.ones(2, 6, dtype=torch.long), labels=torch.randint(0, 100, (2, 6)))
+    assert out.logits.shape == (2, 4 + 6, 50257) and out.loss is not None
+
+
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="/root/reference not present")
+def test_mirror_matches_live_reference_signatures_and_keys():
+    import gpt2_image_captioning_b200 as pkg
+    ref, _ = ref_harness.import_reference()
+    for cls in ("MLPMappingNetwork", "TransformerMappingNetwork", "ImageCaptioningModel", "RetrievalAggregator",
+                "RetrievalAugmentedTransformer"):
+        r, m = getattr(ref, cls), getattr(pkg, cls)
+        rp = [p for p in inspect.signature(r.__init__).parameters.values()]
+        mp = [p for p in inspect.signature(m.__init__).parameters.values() if p.kind != p.KEYWORD_ONLY]
+        assert [p.name for p in rp] == [p.name for p in mp], cls
+        for meth in ("generate", "forward", "generate_captions", "save_parameters", "load_saved_parameters", "_retrieve_batch"):
+            if hasattr(r, meth):
+                assert list(inspect.signature(getattr(r, meth)).parameters) == list(inspect.signature(getattr(m, meth)).parameters), (cls, meth)
+    spec = oc.ModelSpec(gpt="tiny", embed_dim=64, prefix_length=4)
+    gpt, _ = oc.build_modules(spec)
+    a = ref.ImageCaptioningModel(ref.MLPMappingNetwork(4, 64, 128), tokenizer=ref_harness.StubTokenizer(), gpt=gpt)
+    b = pkg.ImageCaptioningModel(pkg.MLPMappingNetwork(4, 64, 128), tokenizer=ref_harness.StubTokenizer(), gpt=gpt)
+    assert list(a.state_dict()) == list(b.state_dict())
+    b.load_state_dict(a.state_dict())  # a reference checkpoint loads into the mirror
+    x = torch.randn(3, 64)
+    ids = torch.randint(0, 1000, (3, 5))
+    assert torch.allclose(a.forward(ids, x).logits, b.forward(ids, x).logits)
+
+
+def test_save_and_load_parameters_roundtrip(tmp_path):
+    import gpt2_image_captioning_b200 as pkg
+    spec = oc.ModelSpec(gpt="tiny", embed_dim=64, prefix_length=4)
+    gpt, _ = oc.build_modules(spec)
+    m1 = pkg.ImageCaptioningModel(pkg.MLPMappingNetwork(4, 64, 128), tokenizer=ref_harness.StubTokenizer(), gpt=gpt)
+    path = str(tmp_path / "ckpt.pt")
+    m1.save_parameters(path)
+    saved = torch.load(path)
+    assert saved and all(not k.startswith("gpt.") for k in saved)  # frozen GPT-2 is not saved (src/models.py:489-519)
+    m2 = pkg.ImageCaptioningModel(pkg.MLPMappingNetwork(4, 64, 128), tokenizer=ref_harness.StubTokenizer(), gpt=gpt)
+    m2.load_saved_parameters(path)
+    assert torch.equal(m1.mapping_network.model[0].weight, m2.mapping_network.model[0].weight)
+    torch.save({"bogus": torch.zeros(1)}, path)
+    with pytest.raises(ValueError):
+        m2.load_saved_parameters(path)
+
+
+# ---- sharding ---------------------------------------------------------------------------------------------------------
+def test_shard_range_covers_everything_in_order():
+    from gpt2_image_captioning_b200 import shard_range
+    for n in (0, 1, 7, 5000, 118287):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    assert shard_range(118287, 0, 8) == (0, 14786) and shard_range(118287, 7, 8)[1] == 118287
+    with pytest.raises(ValueError):
+        shard_range(10, 2, 2)
+
+
+def test_generate_batches_pads_with_eos():
+    from gpt2_image_captioning_b200.sharding import generate_batches
+    calls = []
+
+    def fake(xb):  # a "model.generate" whose L_gen varies per call
+        calls.append(xb.shape[0])
+        L = 2 if len(calls) == 1 else 4
+        return torch.arange(xb.shape[0] * L).view(xb.shape[0], L)
+
+    out = generate_batches(fake, torch.zeros(5, 8), max_length=4, batch_size=3, eos_token_id=9)
+    assert calls == [3, 2] and out.shape == (5, 4)
+    assert out[0].tolist() == [0, 1, 9, 9] and out[4].tolist() == [4, 5, 6, 7]
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from gpt2_image_captioning_b200.sharding import generate_sharded
+from oracle import captioner as oc
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+spec = oc.ModelSpec(gpt="tiny", embed_dim=64, prefix_length=4)
+o = oc.CaptionOracle(spec)
+x = oc.synthetic_embeddings(11, 64, 1)
+out = generate_sharded(lambda xb: o.generate(xb, 5, kv_cache=True), x, max_length=5, batch_size=4)
+if dist.get_rank() == 0:
+    want = o.generate(x, 5, kv_cache=True)
+    assert out.shape == (11, 5) and torch.equal(out, want), (out, want)
+    print("SHARDED_OK")
+else:
+    assert out is None
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_generate_world_size_2_gloo(tmp_path):
+    """Two CPU processes over gloo, each captioning its contiguous shard (the oracle stands in for the per-rank GPU
+    worker -- this tests the host-side split / gather / ordering only): the gathered result equals the single-process one."""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "SHARDED_OK" in outs[0]
