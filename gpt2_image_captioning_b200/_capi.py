@@ -56,6 +56,10 @@ class TfmMapperWeights(C.Structure):
     _fields_ = [("linear_w", _fp), ("linear_b", _fp), ("prefix_const", _fp), ("layers", C.POINTER(TfmLayerWeights))]
 
 
+class ProfileEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int32), ("total_ms", C.c_float)]
+
+
 # name -> (restype, argtypes); every symbol include/gic_b200.h declares
 SIGNATURES = {
     "gic_last_error": (C.c_char_p, []),
@@ -77,6 +81,9 @@ SIGNATURES = {
     "gic_topk_ip": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),
     "gic_select_caption_rows": (C.c_int, [_fp, _fp, C.c_int, C.c_int, _fp, _fp, C.c_int, C.c_int, _fp, C.c_void_p]),
     "gic_gather_aggregate_add": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_void_p]),
+    "gic_launch_count": (C.c_ulonglong, []),
+    "gic_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "gic_profile_read": (C.c_int, [C.c_void_p, C.POINTER(ProfileEntry), C.c_int, C.POINTER(C.c_int)]),
     "gic_test_gemm": (C.c_int, [C.c_int, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gic_test_layernorm": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_void_p]),
 }

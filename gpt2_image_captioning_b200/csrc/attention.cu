@@ -139,6 +139,7 @@ int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int
   GIC_REQUIRE(smem <= 48 * 1024, "attn_decode: t_max %d too large", t_max);
   attn_decode_kernel<T><<<blocks, 128, smem, st>>>(qkv, kcache, vcache, out, d_pos, rows, H, t_max);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 template int launch_attn_decode<float>(const float*, float*, float*, ActOut, const int*, int, int, int, cudaStream_t);
@@ -152,7 +153,7 @@ template int launch_attn_decode<bf16>(const bf16*, bf16*, bf16*, ActOut, const i
 template <typename T, int HDIM, bool CAUSAL>
 __global__ void __launch_bounds__(128) attn_seq_kernel(const T* __restrict__ qkv, T* kcache, T* vcache, ActOut out, int S, int H,
                                                        int t_max, float scale) {
-  constexpr int DPL = HDIM / 32;  // dims per lane
+  constexpr int DPL = (HDIM + 31) / 32;  // dims per lane (lanes >= HDIM idle when HDIM < 32)
   extern __shared__ float sm[];
   float* Ks = sm;                       // [S][HDIM]
   float* Vs = Ks + (size_t)S * HDIM;    // [S][HDIM]
@@ -180,13 +181,14 @@ __global__ void __launch_bounds__(128) attn_seq_kernel(const T* __restrict__ qkv
   for (int t = warp; t < S; t += 4) {
     float q[DPL];
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) q[i] = to_f32(base[(size_t)t * 3 * d + lane + 32 * i]) * scale;
+    for (int i = 0; i < DPL; ++i) q[i] = (lane + 32 * i < HDIM) ? to_f32(base[(size_t)t * 3 * d + lane + 32 * i]) * scale : 0.f;
     const int n = CAUSAL ? t + 1 : S;
     float mx = -INFINITY;
     for (int j = 0; j < n; ++j) {
       float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) s = fmaf(q[i], Ks[j * HDIM + lane + 32 * i], s);
+      for (int i = 0; i < DPL; ++i)
+        if (lane + 32 * i < HDIM) s = fmaf(q[i], Ks[j * HDIM + lane + 32 * i], s);
       s = warp_sum(s);
       if (lane == 0) sc[j] = s;
       mx = fmaxf(mx, s);
@@ -206,12 +208,14 @@ __global__ void __launch_bounds__(128) attn_seq_kernel(const T* __restrict__ qkv
     for (int j = 0; j < n; ++j) {
       const float p = sc[j];
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) o[i] = fmaf(p, Vs[j * HDIM + lane + 32 * i], o[i]);
+      for (int i = 0; i < DPL; ++i)
+        if (lane + 32 * i < HDIM) o[i] = fmaf(p, Vs[j * HDIM + lane + 32 * i], o[i]);
     }
     const float inv = 1.0f / sum;
     const size_t o0 = ((size_t)row * S + t) * d + h * HDIM;
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) out.write(o0 + lane + 32 * i, o[i] * inv);
+    for (int i = 0; i < DPL; ++i)
+      if (lane + 32 * i < HDIM) out.write(o0 + lane + 32 * i, o[i] * inv);
     __syncwarp();
   }
 }
@@ -224,6 +228,7 @@ static int launch_attn_seq(const T* qkv, T* kcache, T* vcache, ActOut out, int B
   if (smem > 48 * 1024) GIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<B * H, 128, smem, st>>>(qkv, kcache, vcache, out, S, H, t_max, 1.0f / sqrtf((float)HDIM));
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 
@@ -238,12 +243,13 @@ template int launch_attn_prefill<bf16>(const bf16*, bf16*, bf16*, ActOut, int, i
 template <typename T>
 int launch_attn_encoder(const T* qkv, ActOut out, int B, int S, int H, int hd, cudaStream_t st) {
   switch (hd) {
+    case 16: return launch_attn_seq<T, 16, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
     case 32: return launch_attn_seq<T, 32, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
     case 64: return launch_attn_seq<T, 64, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
     case 96: return launch_attn_seq<T, 96, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
     case 128: return launch_attn_seq<T, 128, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
     case 160: return launch_attn_seq<T, 160, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
-    default: set_error("attn_encoder: unsupported head_dim %d (32/64/96/128/160)", hd); return GIC_ERR_UNSUPPORTED;
+    default: set_error("attn_encoder: unsupported head_dim %d (16/32/64/96/128/160)", hd); return GIC_ERR_UNSUPPORTED;
   }
 }
 template int launch_attn_encoder<float>(const float*, ActOut, int, int, int, int, cudaStream_t);
@@ -281,6 +287,7 @@ int launch_kv_reorder(const T* src, T* dst, const int* beam_idx, int L, int rows
   const int blocks = (int)((nseg + 7) / 8);
   kv_reorder_kernel<T><<<blocks, 256, 0, st>>>(src, dst, beam_idx, L * 2, rows, H, ctx_len, t_max);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 template int launch_kv_reorder<float>(const float*, float*, const int*, int, int, int, int, int, cudaStream_t);

@@ -12,6 +12,7 @@ namespace gic {
 // ---- error plumbing: never throw across the C ABI; record a message, return a code --------------
 void set_error(const char* fmt, ...);
 const char* get_error();
+void note_launch();  // every kernel launch of the library reports here (gic_launch_count)
 
 #define GIC_CHECK_CUDA(expr)                                                                  \
   do {                                                                                        \

@@ -48,6 +48,7 @@ int launch_layernorm(const float* x, long x_row_stride, const float* w, const fl
   else if (d <= 32 * 32) layernorm_kernel<32><<<blocks, 128, 0, st>>>(x, x_row_stride, w, b, y, rows, d);
   else layernorm_kernel<40><<<blocks, 128, 0, st>>>(x, x_row_stride, w, b, y, rows, d);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 
@@ -82,6 +83,7 @@ int launch_pack_weight(const float* in, int R, int C, bool transpose, ActOut out
   GIC_REQUIRE(grid.y <= 65535, "pack_weight: too many rows (%d)", R);
   pack_weight_kernel<<<grid, block, 0, st>>>(in, R, C, transpose, out);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 
@@ -97,6 +99,7 @@ int launch_convert(const float* in, ActOut out, size_t n, cudaStream_t st) {
   if (blocks < 1) blocks = 1;
   convert_kernel<<<blocks, 256, 0, st>>>(in, out, n);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 
@@ -135,6 +138,7 @@ int launch_embed_prefix(const float* prefix, int P_img, const float* task, int P
   if (blocks > 148 * 16) blocks = 148 * 16;
   embed_prefix_kernel<<<blocks, 256, 0, st>>>(prefix, P_img, task, P_task, wpe, h, prefix_out, B, d);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 
@@ -157,6 +161,7 @@ int launch_slice_tokens(const float* in, int S, int tok0, int n_tok, float* out,
   if (blocks > 148 * 16) blocks = 148 * 16;
   slice_tokens_kernel<<<blocks, 256, 0, st>>>(in, S, tok0, n_tok, out, B, d);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 
@@ -181,6 +186,7 @@ int launch_build_mapper_seq(const float* lin, const float* prefix_const, float* 
   if (blocks > 148 * 16) blocks = 148 * 16;
   build_mapper_seq_kernel<<<blocks, 256, 0, st>>>(lin, prefix_const, seq, B, Hl, P, d);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 

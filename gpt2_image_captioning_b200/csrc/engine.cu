@@ -94,9 +94,34 @@ struct gic_engine {
   cudaGraphExec_t graph_exec = nullptr;
   void* graph_ws = nullptr; int graph_B = 0, graph_max_new = 0;
   bool use_graph = true;
+  int graph_nodes = 0;
+  // all generate work runs on this private stream (the caller's stream may be the legacy default stream, which cannot
+  // be captured into a graph); it is forked from / joined to the caller's stream with events
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // per-kernel-class CUDA-event profiling (bench.py roofline leg); generate runs eagerly while enabled
+  bool profiling = false;
+  struct ProfRec { const char* cat; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof;
 };
 
 namespace gic {
+
+// kernels launched by this library (graph replays count their kernel nodes) -- bench.py's `gpu_launches`
+static unsigned long long g_launches = 0;
+void note_launch() { ++g_launches; }
+
+struct ProfScope {
+  gic_engine* e; cudaStream_t st; bool on;
+  ProfScope(const gic_engine* ce, const char* cat, cudaStream_t s) : e(const_cast<gic_engine*>(ce)), st(s), on(ce->profiling) {
+    if (!on) return;
+    gic_engine::ProfRec r; r.cat = cat;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    e->prof.push_back(r);
+  }
+  ~ProfScope() { if (on) cudaEventRecord(e->prof.back().b, st); }
+};
 
 static int dev_alloc(gic_engine* e, void** p, size_t bytes) {
   GIC_CHECK_CUDA(cudaMalloc(p, bytes));
@@ -251,24 +276,26 @@ static ActOut qkv_out(const Workspace& w) {
 static int gpt_layer(const gic_engine* e, const Workspace& w, int l, float* h, int M, bool prefill, cudaStream_t st) {
   const GptLayer& Lw = e->layers[l];
   const int d = e->d;
-  GIC_TRY(launch_layernorm(h, d, Lw.ln1.w, Lw.ln1.b, w.a.out(), M, d, st));
-  GIC_TRY(linear(e, Lw.attn, w.a, M, EPI_NONE, qkv_out(w), 3 * d, st));
+  { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, d, Lw.ln1.w, Lw.ln1.b, w.a.out(), M, d, st)); }
+  { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_qkv", st); GIC_TRY(linear(e, Lw.attn, w.a, M, EPI_NONE, qkv_out(w), 3 * d, st)); }
   if (e->cfg.dtype == GIC_DTYPE_BF16) {
+    ProfScope ps(e, prefill ? "attn_prefill" : "attn_decode", st);
     bf16* kc = (bf16*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
     bf16* vc = kc + w.kv_layer_elems;
     if (prefill) GIC_TRY(launch_attn_prefill<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, st));
     else GIC_TRY(launch_attn_decode<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st));
   } else {
+    ProfScope ps(e, prefill ? "attn_prefill" : "attn_decode", st);
     float* kc = (float*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
     float* vc = kc + w.kv_layer_elems;
     if (prefill) GIC_TRY(launch_attn_prefill<float>(w.qkv_f32, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, st));
     else GIC_TRY(launch_attn_decode<float>(w.qkv_f32, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st));
   }
   ActOut hres; hres.f32 = h;
-  GIC_TRY(linear(e, Lw.proj, w.o, M, EPI_RESIDUAL, hres, d, st));
-  GIC_TRY(launch_layernorm(h, d, Lw.ln2.w, Lw.ln2.b, w.a.out(), M, d, st));
-  GIC_TRY(linear(e, Lw.fc, w.a, M, EPI_GELU, w.f.out(), 4 * d, st));
-  GIC_TRY(linear(e, Lw.fc2, w.f, M, EPI_RESIDUAL, hres, d, st));
+  { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_proj", st); GIC_TRY(linear(e, Lw.proj, w.o, M, EPI_RESIDUAL, hres, d, st)); }
+  { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, d, Lw.ln2.w, Lw.ln2.b, w.a.out(), M, d, st)); }
+  { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_fc", st); GIC_TRY(linear(e, Lw.fc, w.a, M, EPI_GELU, w.f.out(), 4 * d, st)); }
+  { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_fc2", st); GIC_TRY(linear(e, Lw.fc2, w.f, M, EPI_RESIDUAL, hres, d, st)); }
   return GIC_OK;
 }
 
@@ -276,18 +303,20 @@ static int gpt_layer(const gic_engine* e, const Workspace& w, int l, float* h, i
 static int lm_head_and_token(const gic_engine* e, const Workspace& w, const float* h, long row_stride, int rows, float* logits_tap,
                              cudaStream_t st) {
   const int d = e->d;
-  GIC_TRY(launch_layernorm(h, row_stride, e->lnf.w, e->lnf.b, w.a.out(), rows, d, st));
+  { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, row_stride, e->lnf.w, e->lnf.b, w.a.out(), rows, d, st)); }
   int n_parts = 0;
   if (!e->tc) {
     float* lg = logits_tap ? logits_tap : w.logits;
     ActOut o; o.f32 = lg;
-    GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st));
-    GIC_TRY(launch_argmax_partials(lg, rows, e->V, w.part_val, w.part_idx, st));
+    { ProfScope ps(e, "lm_head", st); GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st)); }
+    { ProfScope ps(e, "argmax", st); GIC_TRY(launch_argmax_partials(lg, rows, e->V, w.part_val, w.part_idx, st)); }
     n_parts = LMHEAD_F32_PARTS;
   } else {
     ActOut o; o.f32 = logits_tap;  // null on the product path: logits never reach HBM
+    ProfScope ps(e, "lm_head", st);
     GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st, w.part_val, w.part_idx, &n_parts));
   }
+  ProfScope psf(e, "finalize", st);
   FinalizeArgs fa;
   fa.part_val = w.part_val; fa.part_idx = w.part_idx; fa.n_parts = n_parts;
   fa.B = rows; fa.d = d; fa.eos = e->cfg.eos_token_id; fa.max_new = w.max_new; fa.P = w.P; fa.n_pos = e->cfg.n_positions;
@@ -339,6 +368,19 @@ static int mapper_forward(const gic_engine* e, const Workspace& w, const float* 
   return launch_slice_tokens(w.h, S, Hl, P, w.prefix, B, d, st);
 }
 
+// run on the engine's private stream, ordered after everything already queued on the caller's stream ...
+static int fork_stream(gic_engine* e, cudaStream_t user) {
+  GIC_CHECK_CUDA(cudaEventRecord(e->ev_in, user));
+  GIC_CHECK_CUDA(cudaStreamWaitEvent(e->stream, e->ev_in, 0));
+  return GIC_OK;
+}
+// ... and make the caller's stream wait for it
+static int join_stream(gic_engine* e, cudaStream_t user) {
+  GIC_CHECK_CUDA(cudaEventRecord(e->ev_out, e->stream));
+  GIC_CHECK_CUDA(cudaStreamWaitEvent(user, e->ev_out, 0));
+  return GIC_OK;
+}
+
 static int check_ready(const gic_engine* e) {
   GIC_REQUIRE(e != nullptr, "null engine");
   GIC_REQUIRE(e->gpt_loaded, "GPT-2 weights not loaded (gic_engine_load_gpt2)");
@@ -382,8 +424,8 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
   GIC_REQUIRE(cfg->mapper_kind == GIC_MAPPER_MLP || cfg->mapper_kind == GIC_MAPPER_TRANSFORMER, "unknown mapper kind %d", cfg->mapper_kind);
   if (cfg->mapper_kind == GIC_MAPPER_TRANSFORMER) {
     GIC_REQUIRE(cfg->hidden_length > 0 && cfg->mapper_layers > 0 && cfg->mapper_heads > 0, "bad transformer-mapper dimensions");
-    GIC_REQUIRE(cfg->n_embd % cfg->mapper_heads == 0 && (cfg->n_embd / cfg->mapper_heads) % 32 == 0,
-                "transformer mapper head_dim %d unsupported", cfg->n_embd / cfg->mapper_heads);
+    GIC_REQUIRE(cfg->n_embd % cfg->mapper_heads == 0, "transformer mapper: n_embd %d not divisible by %d heads", cfg->n_embd,
+                cfg->mapper_heads);
   } else {
     GIC_REQUIRE((cfg->prefix_length * cfg->n_embd) % 16 == 0, "MLP mapper hidden size must be a multiple of 8");
   }
@@ -401,13 +443,25 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
     if (r == GIC_OK) r = gic::gemm_bf16_configure();
     if (r != GIC_OK) { delete e; return r; }
   }
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+    gic::set_error("could not create the engine stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+    delete e;
+    return GIC_ERR_CUDA;
+  }
   *out = e;
   return GIC_OK;
 }
 
 int gic_engine_destroy(gic_engine* e) {
   if (!e) return GIC_OK;
+  if (e->stream) cudaStreamSynchronize(e->stream);
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
+  if (e->stream) cudaStreamDestroy(e->stream);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
   return GIC_OK;
@@ -510,10 +564,12 @@ int gic_mapper_forward(gic_engine* e, const float* x, int batch, float* prefix_o
   GIC_REQUIRE(x && prefix_out, "null argument");
   Workspace w;
   GIC_TRY(prepare_ws(e, workspace, workspace_bytes, batch, 0, 1, &w));
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t user = (cudaStream_t)stream, st = e->stream;
+  GIC_TRY(fork_stream(e, user));
   GIC_TRY(mapper_forward(e, w, x, st));
   // [B, P_img + P_task, d]: image prefix then the task rows (src/models.py:364-375)
-  return launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, nullptr, nullptr, prefix_out, batch, e->d, st);
+  GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, nullptr, nullptr, prefix_out, batch, e->d, st));
+  return join_stream(e, user);
 }
 
 int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, int64_t* ids_out, int32_t* gen_len_out, float* logits_out,
@@ -523,11 +579,12 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   GIC_REQUIRE(max_new >= 1, "max_new_tokens must be >= 1 (the caller handles 0, src/models.py:471-473)");
   Workspace w;
   GIC_TRY(prepare_ws(e, workspace, workspace_bytes, batch, max_new, 1, &w));
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t user = (cudaStream_t)stream, st = e->stream;
   const int d = e->d, B = batch, P = w.P;
+  GIC_TRY(fork_stream(e, user));
 
   GIC_TRY(launch_init_decode_state(w.finished, w.first_eos, B, max_new, w.d_step, w.d_pos, w.done_counter, P, st));
-  GIC_TRY(mapper_forward(e, w, x, st));
+  { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
   GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));
   // ---- prefill over the P prefix tokens of every row ----
   for (int l = 0; l < e->L; ++l) GIC_TRY(gpt_layer(e, w, l, w.h, B * P, true, st));
@@ -536,7 +593,7 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
 
   // ---- decode: max_new-1 identical steps; positions / step index live on the device ----
   const int steps = max_new - 1;
-  const bool graph_ok = e->use_graph && logits_out == nullptr && steps >= 2;
+  const bool graph_ok = e->use_graph && !e->profiling && logits_out == nullptr && steps >= 2;
   if (!graph_ok) {
     for (int s = 1; s <= steps; ++s)
       GIC_TRY(decode_step(e, w, logits_out ? logits_out + (size_t)s * B * e->V : nullptr, st));
@@ -544,9 +601,12 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
     if (!(e->graph_exec && e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new)) {
       if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
       cudaGraph_t graph = nullptr;
+      const unsigned long long before = g_launches;
       GIC_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       int r = decode_step(e, w, nullptr, st);
       cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      e->graph_nodes = (int)(g_launches - before);  // captured, not executed
+      g_launches = before;
       if (r != GIC_OK) { if (graph) cudaGraphDestroy(graph); return r; }
       GIC_CHECK_CUDA(ce);
       ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
@@ -555,10 +615,11 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
       e->graph_ws = workspace; e->graph_B = B; e->graph_max_new = max_new;
     }
     for (int s = 1; s <= steps; ++s) GIC_CHECK_CUDA(cudaGraphLaunch(e->graph_exec, st));
+    g_launches += (unsigned long long)e->graph_nodes * steps;
   }
   GIC_CHECK_CUDA(cudaMemcpyAsync(ids_out, w.ids, (size_t)B * max_new * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   if (gen_len_out) GIC_TRY(launch_gen_len(w.first_eos, B, max_new, gen_len_out, st));
-  return GIC_OK;
+  return join_stream(e, user);
 }
 
 int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int num_beams, float length_penalty, int64_t* ids_out,
@@ -597,6 +658,38 @@ int gic_gather_aggregate_add(const float* q, const float* cap_db, const int64_t*
   GIC_REQUIRE(q && cap_db && rows && out, "null argument");
   GIC_REQUIRE(batch > 0, "batch must be positive");
   return launch_gather_aggregate_add(q, cap_db, rows, batch, top_k, dim, aggregation, out, (cudaStream_t)stream);
+}
+
+unsigned long long gic_launch_count(void) { return gic::g_launches; }
+
+int gic_profile_enable(gic_engine* e, int on) {
+  GIC_REQUIRE(e != nullptr, "null engine");
+  for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  e->prof.clear();
+  e->profiling = on != 0;
+  return GIC_OK;
+}
+
+int gic_profile_read(gic_engine* e, gic_profile_entry* out, int max_entries, int* n_out) {
+  GIC_REQUIRE(e && out && n_out && max_entries > 0, "bad argument");
+  GIC_CHECK_CUDA(cudaDeviceSynchronize());
+  int n = 0;
+  for (auto& r : e->prof) {
+    float ms = 0.f;
+    GIC_CHECK_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    int j = 0;
+    for (; j < n; ++j) if (strncmp(out[j].name, r.cat, sizeof(out[j].name)) == 0) break;
+    if (j == n) {
+      if (n == max_entries) continue;
+      memset(&out[n], 0, sizeof(out[n]));
+      strncpy(out[n].name, r.cat, sizeof(out[n].name) - 1);
+      ++n;
+    }
+    out[j].launches += 1;
+    out[j].total_ms += ms;
+  }
+  *n_out = n;
+  return GIC_OK;
 }
 
 // ---- kernel-level test entry points ---------------------------------------------------------------------------------

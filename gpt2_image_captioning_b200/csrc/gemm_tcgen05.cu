@@ -410,6 +410,7 @@ static int launch_cfg(const GemmKernelParams& kp, cudaStream_t st) {
   dim3 grid(ceil_div(kp.M, GEMM_BLOCK_M), ceil_div(kp.N, BLOCK_N));
   kern<<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(kp);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 

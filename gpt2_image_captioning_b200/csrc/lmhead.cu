@@ -62,6 +62,7 @@ int launch_argmax_partials(const float* logits, int B, int V, float* part_val, i
   dim3 grid(B, LMHEAD_F32_PARTS);
   argmax_partials_kernel<<<grid, 256, 0, st>>>(logits, B, V, part_val, part_idx);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
 int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st) {
   finalize_token_kernel<<<a.B, 128, 0, st>>>(a);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 
@@ -143,6 +145,7 @@ int launch_init_decode_state(unsigned char* finished, int* first_eos, int B, int
                              int P, cudaStream_t st) {
   init_decode_state_kernel<<<ceil_div(B, 256), 256, 0, st>>>(finished, first_eos, B, max_new, d_step, d_pos, done_counter, P);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 
@@ -165,6 +168,7 @@ __global__ void gen_len_kernel(const int* __restrict__ first_eos, int B, int max
 int launch_gen_len(const int* first_eos, int B, int max_new, int* gen_len_out, cudaStream_t st) {
   gen_len_kernel<<<1, 256, 0, st>>>(first_eos, B, max_new, gen_len_out);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 

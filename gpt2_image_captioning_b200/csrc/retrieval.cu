@@ -112,7 +112,8 @@ int launch_topk_ip(const float* q, const float* db, int B, int N, int D, int k, 
   const size_t n = (size_t)B * k;
   topk_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(scores, idx, n);
   GIC_CHECK_CUDA(cudaGetLastError());
-  const int nthreads = k <= 16 ? 256 : 128;
+  note_launch();
+  const int nthreads = k <= 8 ? 256 : (k <= 16 ? 128 : 64);  // candidate lists must fit 48 KB of shared memory
   const size_t smem = (size_t)nthreads * k * (sizeof(float) + sizeof(long));
   for (long base = 0; base < N; base += TOPK_CHUNK) {
     const int rows = (int)((N - base) < TOPK_CHUNK ? (N - base) : TOPK_CHUNK);
@@ -121,6 +122,7 @@ int launch_topk_ip(const float* q, const float* db, int B, int N, int D, int k, 
     else if (k <= 16) topk_merge_kernel<16><<<B, nthreads, smem, st>>>(chunk_scores, rows, base, k, scores, idx);
     else topk_merge_kernel<32><<<B, nthreads, smem, st>>>(chunk_scores, rows, base, k, scores, idx);
     GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   }
   return GIC_OK;
 }
@@ -149,6 +151,7 @@ int launch_select_caption_rows(const float* scores, const int64_t* idx, int B, i
   GIC_REQUIRE(B > 0 && top_k > 0 && top_i > 0, "select_caption_rows: bad sizes");
   select_caption_rows_kernel<<<ceil_div(B, 128), 128, 0, st>>>(scores, idx, B, k_searched, cap_row_start, cap_row_ids, top_i, top_k, rows_out);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 
@@ -212,6 +215,7 @@ int launch_gather_aggregate_add(const float* q, const float* cap_db, const int64
   GIC_REQUIRE(aggregation >= GIC_AGG_MEAN && aggregation <= GIC_AGG_SUM_NORM, "gather_aggregate_add: unknown aggregation %d", aggregation);
   gather_aggregate_add_kernel<<<B, 256, 0, st>>>(q, cap_db, rows, top_k, D, aggregation, out);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 

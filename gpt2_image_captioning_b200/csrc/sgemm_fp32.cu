@@ -128,6 +128,7 @@ int launch_sgemm_nt(const float* A, int lda, const float* W, const float* bias, 
     sgemm_nt_kernel<128, 128, 8, 8><<<grid, 256, 0, st>>>(A, lda, W, bias, C, ldc, M, N, K, epilogue);
   }
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
   return GIC_OK;
 }
 

@@ -124,6 +124,21 @@ class CaptionEngine:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws
 
+    # ---- measurement hooks (bench.py) ----------------------------------------------------------------------------------
+    def profile(self, on: bool) -> None:
+        """While on, generate runs without the CUDA graph with CUDA events around every kernel class."""
+        _capi.check(self.lib.gic_profile_enable(self._handle, 1 if on else 0))
+
+    def profile_read(self) -> dict[str, dict]:
+        buf = (_capi.ProfileEntry * 64)()
+        n = C.c_int(0)
+        _capi.check(self.lib.gic_profile_read(self._handle, buf, 64, C.byref(n)))
+        return {buf[i].name.decode(): {"launches": int(buf[i].launches), "total_ms": float(buf[i].total_ms)} for i in range(n.value)}
+
+    @staticmethod
+    def launch_count() -> int:
+        return int(_capi.lib().gic_launch_count())
+
     def close(self) -> None:
         if self._handle:
             self.lib.gic_engine_destroy(self._handle)

@@ -166,6 +166,16 @@ GIC_API int gic_select_caption_rows(const float* scores, const int64_t* idx, int
 GIC_API int gic_gather_aggregate_add(const float* queries, const float* cap_db, const int64_t* rows, int batch, int top_k, int dim,
                              int aggregation, float* out, void* stream);
 
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------------------------ */
+/* kernels launched by this library in this process so far (CUDA-graph replays count their kernel nodes) */
+GIC_API unsigned long long gic_launch_count(void);
+/* while enabled, generate calls run without the CUDA graph and bracket every kernel class with CUDA events on the
+ * launch stream; gic_profile_read synchronises and returns per-class launch counts and summed device time.
+ * A "class" spans one logical op (e.g. "attn_decode", "gemm_qkv", "lm_head", "layernorm", "prefill_gemm"). */
+typedef struct gic_profile_entry { char name[32]; int32_t launches; float total_ms; } gic_profile_entry;
+GIC_API int gic_profile_enable(gic_engine* e, int on);
+GIC_API int gic_profile_read(gic_engine* e, gic_profile_entry* out, int max_entries, int* n_out);
+
 /* ---- kernel-level entry points (unit tests / profiling; same kernels the path uses) --------------------- */
 /* C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias[N]) ; epilogue: 0 none, 1 tanh, 2 gelu_tanh, 3 relu, 4 += residual(fp32 C in place).
  * dtype F32: A,W,C fp32 (CUDA cores).  BF16 / BF16X2: A,W fp32 inputs are packed internally, C fp32. */

@@ -161,6 +161,16 @@ def test_retrieval_against_reference_fixture():
     store = GpuFlatStore(img, cap, names, [{"filename": names[o], "caption_id": j} for j, o in enumerate(owner)], device=DEV)
     q = torch.from_numpy(g["q"])
     for (k, i) in [(10, 4), (20, 6), (5, 1)]:
+        rows = store.retrieve_rows(q.to(DEV), top_i=i, top_k=k).cpu().numpy()
+        starts = np.concatenate([[0], np.cumsum(counts)])
+        _, want_rows = oc.retrieve_and_aggregate(img, cap, lambda im: list(range(starts[im], starts[im + 1])), g["q"], top_i=i, top_k=k)
+        if not np.array_equal(rows, want_rows):
+            bad = np.nonzero((rows != want_rows).any(axis=1))[0]
+            s_gpu, i_gpu = store.image_index.search(g["q"][bad[:2]], i + 10)
+            s_ref, i_ref = oc.flat_ip_search(img, g["q"][bad[:2]], i + 10)
+            raise AssertionError(f"caption rows differ for queries {bad.tolist()} (k={k}, i={i}):\n gpu rows {rows[bad[:2]].tolist()}\n"
+                                 f" ref rows {want_rows[bad[:2]].tolist()}\n gpu idx {i_gpu.tolist()}\n ref idx {i_ref.tolist()}\n"
+                                 f" gpu scores {s_gpu.tolist()}\n ref scores {s_ref.tolist()}")
         ret = store.retrieve_caption_embeddings(q.to(DEV), top_i=i, top_k=k).cpu().numpy()
         assert np.array_equal(ret, g[f"ret_k{k}_i{i}"]), (k, i)
         aug = store.retrieve_and_aggregate(q, top_i=i, top_k=k, aggregation="mean")
