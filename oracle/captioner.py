@@ -164,7 +164,16 @@ def gpt2_weights(gpt) -> dict:
     return w
 
 
-def gpt2_forward(w: dict, inputs_embeds: torch.Tensor, kv: list | None = None, last_only: bool = False):
+def _identity(t: torch.Tensor) -> torch.Tensor:
+    return t
+
+
+def round_bf16(t: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest-even to bfloat16 and back: the storage rounding of GIC_DTYPE_BF16 operands."""
+    return t.bfloat16().float()
+
+
+def gpt2_forward(w: dict, inputs_embeds: torch.Tensor, kv: list | None = None, last_only: bool = False, rnd=_identity):
     """GPT2LMHeadModel.forward(inputs_embeds=) restated (HF:models/gpt2/modeling_gpt2.py:658-726,
     GPT2Model.forward :522-636, GPT2Block :262-309, GPT2Attention :144-226, GPT2MLP :238-243).
 
@@ -172,6 +181,10 @@ def gpt2_forward(w: dict, inputs_embeds: torch.Tensor, kv: list | None = None, l
     h += attn.Wo + b; m = LN2(h); h += gelu_new(m.Wfc + b).Wproj + b; logits = LNf(h).wte^T (tied, no bias).
     `kv` (list of per-layer [k, v]) turns on the incremental form: positions continue after the cache
     (the reference itself never passes past_key_values; used only to extend parity sets).
+    `rnd` (identity by default) is applied wherever the CUDA engine's bf16 mode stores a GEMM operand or the KV
+    cache in bfloat16 (LayerNorm outputs, q/k/v, attention output, GELU output, every weight matrix): with
+    rnd=round_bf16 this is a CPU emulation of that mode (fp32 accumulation, residual stream and logits), used to
+    separate "bf16 rounding" from "kernel bug" in the parity tests.
     Returns fp32 logits [B, T, V] (or [B, 1, V] if last_only)."""
     B, T, d = inputs_embeds.shape
     H = w["n_head"]
@@ -180,8 +193,8 @@ def gpt2_forward(w: dict, inputs_embeds: torch.Tensor, kv: list | None = None, l
     pos = torch.arange(past, past + T)
     h = inputs_embeds + w["wpe"][pos]  # HF :579-585 -- prefix tokens also get wpe
     for li, lw in enumerate(w["layers"]):
-        a = layer_norm(h, lw["ln1_w"], lw["ln1_b"])
-        qkv = a @ lw["attn_w"] + lw["attn_b"]  # Conv1D = addmm(bias, x, W[in,out])
+        a = rnd(layer_norm(h, lw["ln1_w"], lw["ln1_b"]))
+        qkv = rnd(a @ rnd(lw["attn_w"]) + lw["attn_b"])  # Conv1D = addmm(bias, x, W[in,out])
         q, k, v = qkv.split(d, dim=-1)
         q = q.view(B, T, H, hd).transpose(1, 2)
         k = k.view(B, T, H, hd).transpose(1, 2)
@@ -195,20 +208,20 @@ def gpt2_forward(w: dict, inputs_embeds: torch.Tensor, kv: list | None = None, l
         att = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
         causal = torch.ones(S, S, dtype=torch.bool).tril()[S - T:, :]
         att = att.masked_fill(~causal, float("-inf")).softmax(-1)
-        o = (att @ v).transpose(1, 2).reshape(B, T, d)
-        h = h + (o @ lw["proj_w"] + lw["proj_b"])
-        m = layer_norm(h, lw["ln2_w"], lw["ln2_b"])
-        h = h + (gelu_new(m @ lw["fc_w"] + lw["fc_b"]) @ lw["fc2_w"] + lw["fc2_b"])
+        o = rnd((att @ v).transpose(1, 2).reshape(B, T, d))
+        h = h + (o @ rnd(lw["proj_w"]) + lw["proj_b"])
+        m = rnd(layer_norm(h, lw["ln2_w"], lw["ln2_b"]))
+        h = h + (rnd(gelu_new(m @ rnd(lw["fc_w"]) + lw["fc_b"])) @ rnd(lw["fc2_w"]) + lw["fc2_b"])
     if last_only:
         h = h[:, -1:, :]
-    h = layer_norm(h, w["lnf_w"], w["lnf_b"])
-    return h @ w["wte"].t()
+    h = rnd(layer_norm(h, w["lnf_w"], w["lnf_b"]))
+    return h @ rnd(w["wte"]).t()
 
 
-def mlp_mapper(mw: dict, x: torch.Tensor, prefix_length: int) -> torch.Tensor:
+def mlp_mapper(mw: dict, x: torch.Tensor, prefix_length: int, rnd=_identity) -> torch.Tensor:
     """MLPMappingNetwork.forward (src/models.py:58-74): view(tanh(x W1^T + b1) W2^T + b2, [B,P,d])."""
-    h = torch.tanh(x @ mw["model.0.weight"].t() + mw["model.0.bias"])
-    y = h @ mw["model.2.weight"].t() + mw["model.2.bias"]
+    h = rnd(torch.tanh(rnd(x) @ rnd(mw["model.0.weight"]).t() + mw["model.0.bias"]))
+    y = h @ rnd(mw["model.2.weight"]).t() + mw["model.2.bias"]
     return y.view(x.shape[0], prefix_length, -1)
 
 
@@ -270,11 +283,11 @@ class CaptionOracle:
 
     # -- mapper ---------------------------------------------------------------------------
     @torch.no_grad()
-    def prefix(self, x: torch.Tensor, backend: str = "restated") -> torch.Tensor:
+    def prefix(self, x: torch.Tensor, backend: str = "restated", rnd=_identity) -> torch.Tensor:
         if backend == "hf":
             p = self.mapper(x)
         elif self.spec.mapper == "mlp":
-            p = mlp_mapper(self.mw, x, self.spec.prefix_length)
+            p = mlp_mapper(self.mw, x, self.spec.prefix_length, rnd)
         else:
             p = transformer_mapper(self.mw, x, self.spec.prefix_length, self.spec.hidden_length, self.spec.mapper_layers)
         if self.task_prefix_embeds is not None:
@@ -284,13 +297,17 @@ class CaptionOracle:
     # -- greedy generate (src/models.py:327-477, temperature == 0 branch) -----------------------
     @torch.no_grad()
     def generate(self, x: torch.Tensor, max_length: int = 30, backend: str = "restated", kv_cache: bool = False,
-                 return_logits: bool = False):
+                 return_logits: bool = False, emulate_bf16: bool = False):
         """Token ids int64 [B, L_gen].  `kv_cache=False` is the reference's algorithm verbatim: re-forward the
         whole growing sequence every step (src/models.py:395,466-469), logits of ALL positions computed
         (HF :705-706) and only the last used (:398); argmax ties -> lowest index; rows that have emitted EOS
         keep emitting EOS (:453-460); stop before a step once all rows are finished (:390-391)."""
         B = x.shape[0]
-        cur = self.prefix(x, backend)
+        rnd = round_bf16 if emulate_bf16 else _identity
+        if emulate_bf16 and (backend != "restated" or self.spec.mapper != "mlp"):
+            raise ValueError("bf16 emulation is implemented for the restated backend with the MLP mapper")
+        wte_in = rnd(self.w["wte"])  # the bf16 engine gathers next-token embeddings from its bf16 table
+        cur = self.prefix(x, backend, rnd)
         finished = torch.zeros(B, dtype=torch.bool)
         toks, logits_log = [], []
         kv = [None] * self.w["n_layer"] if kv_cache else None
@@ -303,16 +320,16 @@ class CaptionOracle:
                     raise ValueError("the reference never uses past_key_values; hf backend is cache-less")
                 logits = self.gpt(inputs_embeds=cur).logits[:, -1, :]
             elif kv_cache:
-                logits = gpt2_forward(self.w, step_in, kv=kv, last_only=True)[:, -1, :]
+                logits = gpt2_forward(self.w, step_in, kv=kv, last_only=True, rnd=rnd)[:, -1, :]
             else:
-                logits = gpt2_forward(self.w, cur)[:, -1, :]
+                logits = gpt2_forward(self.w, cur, rnd=rnd)[:, -1, :]
             if return_logits:
                 logits_log.append(logits.clone())
             nxt = torch.argmax(logits / 1.0, dim=-1)  # :401-403 divides by 1.0 when temperature == 0
             finished = finished | nxt.eq(EOS_TOKEN_ID)
             nxt = torch.where(finished, torch.full_like(nxt, EOS_TOKEN_ID), nxt)
             toks.append(nxt.unsqueeze(-1))
-            step_in = self.w["wte"][nxt].unsqueeze(1)  # :466 wte lookup of the new token
+            step_in = wte_in[nxt].unsqueeze(1)  # :466 wte lookup of the new token
             cur = torch.cat((cur, step_in), dim=1)
         ids = torch.cat(toks, dim=1) if toks else torch.empty((B, 0), dtype=torch.long)
         return (ids, logits_log) if return_logits else ids

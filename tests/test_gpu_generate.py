@@ -102,6 +102,24 @@ def test_c2_first1024_caption_match(dtype, min_match):
             assert a["gap"] < 1e-4, f"fp32 mismatch is not a near-tie: {a}"
 
 
+def test_bf16_engine_matches_cpu_emulation_of_the_same_roundings():
+    """Separates "bf16 rounding" from "kernel bug": the bf16 engine against the oracle run with the SAME bf16 storage
+    roundings emulated on the CPU (oracle.generate(emulate_bf16=True)); what remains is accumulation order (which can
+    still flip a bf16 rounding of an intermediate, hence not 100 %)."""
+    g = gu.load("c2_small_mlp_first1024")
+    model, oracle, x = gpu_util.product_model(g, "bf16")
+    n = 256
+    ids = model.generate(image_embeddings=x[:n].to(DEV), max_length=30, temperature=0.0).cpu()
+    emu = oracle.generate(x[:n], 30, kv_cache=True, emulate_bf16=True)
+    ref = torch.from_numpy(g["ids"][:n].astype(np.int64))
+    m_emu = float((ids == emu).all(dim=1).float().mean())
+    m_ref = float((ids == ref).all(dim=1).float().mean())
+    m_emu_ref = float((emu == ref).all(dim=1).float().mean())
+    _report(test="bf16_vs_emulation", rows=n, gpu_vs_emulation=m_emu, gpu_vs_fp32_reference=m_ref, emulation_vs_fp32_reference=m_emu_ref)
+    assert m_emu >= 0.9, f"bf16 engine agrees with its own CPU emulation on only {m_emu:.3f} of captions"
+    assert m_emu > m_ref
+
+
 @pytest.mark.parametrize("name,dtype", [("c4_large_mlp", "fp32"), ("c3_medium_tfm", "fp32"), ("c4_large_mlp", "bf16x2"),
                                         ("c3_medium_tfm", "bf16x2")])
 def test_larger_models_token_exact(name, dtype):
@@ -182,8 +200,9 @@ def test_engine_rebuilds_after_parameter_update():
     g = gu.load("tiny_mlp_eos")
     model, _, x = gpu_util.product_model(g, "fp32")
     a = model.generate(image_embeddings=x[:8].to(DEV), max_length=6, temperature=0.0)
-    with torch.no_grad():
-        model.mapping_network.model[2].bias.add_(0.5)
+    with torch.no_grad():  # (a uniform shift would be invisible: LayerNorm removes a constant added to every channel)
+        bias = model.mapping_network.model[2].bias
+        bias.add_(torch.randn(bias.shape, generator=torch.Generator().manual_seed(3)).to(bias.device))
     b = model.generate(image_embeddings=x[:8].to(DEV), max_length=6, temperature=0.0)
     assert not torch.equal(a, b), "engine kept stale packed weights after an in-place parameter update"
 
@@ -198,7 +217,7 @@ def test_full_size_bf16_properties():
     b = model.generate(image_embeddings=x, max_length=30, temperature=0.0)
     assert a.shape == (1024, 30) and torch.equal(a, b)
     c = model.generate(image_embeddings=x[512:900], max_length=30, temperature=0.0)
-    row_same = (c == a[512:900]).all(dim=1).float().mean().item()
-    _report(test="full_size_bf16_split_invariance", frac_rows_identical=row_same)
-    assert row_same == 1.0
+    rows_same = (c == a[512:900]).all(dim=1)
+    _report(test="full_size_bf16_split_invariance", rows=int(rows_same.numel()), rows_identical=int(rows_same.sum()))
+    assert bool(rows_same.all())
     assert int(a.min()) >= 0 and int(a.max()) < 50257

@@ -83,6 +83,22 @@ def test_c4_large_tokens():
     assert np.array_equal(ids.numpy(), g["ids"].astype(np.int64))
 
 
+@pytest.mark.skipif(not gu.have("c1_small_mlp_b64"), reason="fixture not generated")
+def test_bf16_emulation_documents_the_random_init_margin_problem():
+    """With RANDOM-INIT weights the greedy margins are small (median top-2 gap 0.24, min 3e-3): merely
+    storing GEMM operands in bfloat16 (fp32 accumulation, emulated here on the CPU) changes a large share of 30-token
+    captions while the logits stay within 1e-2.  This is why the bf16 mode's caption agreement with the fp32 reference is
+    reported rather than asserted at 99 %, and why the BF16X2 mode exists (precision modes)."""
+    g = gu.load("c1_small_mlp_b64")
+    o, x = _oracle(g)
+    ref = torch.from_numpy(g["ids"].astype(np.int64))
+    emu, logs = o.generate(x, 30, kv_cache=True, emulate_bf16=True, return_logits=True)
+    match = float((emu == ref).all(dim=1).float().mean())
+    assert 0.5 < match < 0.99, match
+    rel = (logs[0][:2] - torch.from_numpy(g["logits0"])).abs().max() / torch.from_numpy(g["logits0"]).abs().max()
+    assert rel < 1e-2
+
+
 def test_beam_fixture_reproduces():
     """Beam search is not in the reference; its oracle is HF GenerationMixin on the same pinned weights."""
     g = gu.load("tiny_mlp_beam5")
