@@ -75,7 +75,7 @@ SIGNATURES = {
     "gic_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "gic_mapper_forward": (C.c_int, [C.c_void_p, _fp, C.c_int, _fp, _fp, C.c_size_t, C.c_void_p]),
     "gic_generate_greedy": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),
-    "gic_generate_beam": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),
+    "gic_generate_beam": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),
     "gic_kv_reorder": (C.c_int, [C.c_void_p, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gic_topk_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "gic_topk_ip": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),

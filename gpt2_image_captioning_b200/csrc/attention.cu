@@ -152,7 +152,7 @@ template int launch_attn_decode<bf16>(const bf16*, bf16*, bf16*, ActOut, const i
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int HDIM, bool CAUSAL>
 __global__ void __launch_bounds__(128) attn_seq_kernel(const T* __restrict__ qkv, T* kcache, T* vcache, ActOut out, int S, int H,
-                                                       int t_max, float scale) {
+                                                       int t_max, int cache_row_mult, float scale) {
   constexpr int DPL = (HDIM + 31) / 32;  // dims per lane (lanes >= HDIM idle when HDIM < 32)
   extern __shared__ float sm[];
   float* Ks = sm;                       // [S][HDIM]
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(128) attn_seq_kernel(const T* __restrict__ qkv
     Ks[i] = to_f32(kv);
     Vs[i] = to_f32(vv);
     if (kcache) {
-      const size_t ci = (((size_t)row * H + h) * t_max + t) * HDIM + c;
+      const size_t ci = (((size_t)row * cache_row_mult * H + h) * t_max + t) * HDIM + c;
       kcache[ci] = kv;
       vcache[ci] = vv;
     }
@@ -221,34 +221,36 @@ __global__ void __launch_bounds__(128) attn_seq_kernel(const T* __restrict__ qkv
 }
 
 template <typename T, int HDIM, bool CAUSAL>
-static int launch_attn_seq(const T* qkv, T* kcache, T* vcache, ActOut out, int B, int S, int H, int t_max, cudaStream_t st) {
+static int launch_attn_seq(const T* qkv, T* kcache, T* vcache, ActOut out, int B, int S, int H, int t_max, int cache_row_mult,
+                           cudaStream_t st) {
   const size_t smem = ((size_t)2 * S * HDIM + 4 * S) * sizeof(float);
   GIC_REQUIRE(smem <= 200 * 1024, "attention: sequence %d x head_dim %d does not fit in shared memory", S, HDIM);
   auto kern = attn_seq_kernel<T, HDIM, CAUSAL>;
   if (smem > 48 * 1024) GIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<B * H, 128, smem, st>>>(qkv, kcache, vcache, out, S, H, t_max, 1.0f / sqrtf((float)HDIM));
+  kern<<<B * H, 128, smem, st>>>(qkv, kcache, vcache, out, S, H, t_max, cache_row_mult, 1.0f / sqrtf((float)HDIM));
   GIC_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return GIC_OK;
 }
 
 template <typename T>
-int launch_attn_prefill(const T* qkv, T* kcache, T* vcache, ActOut out, int B, int P, int H, int t_max, cudaStream_t st) {
+int launch_attn_prefill(const T* qkv, T* kcache, T* vcache, ActOut out, int B, int P, int H, int t_max, int cache_row_mult,
+                        cudaStream_t st) {
   GIC_REQUIRE(P <= t_max, "attn_prefill: P %d > t_max %d", P, t_max);
-  return launch_attn_seq<T, 64, true>(qkv, kcache, vcache, out, B, P, H, t_max, st);
+  return launch_attn_seq<T, 64, true>(qkv, kcache, vcache, out, B, P, H, t_max, cache_row_mult, st);
 }
-template int launch_attn_prefill<float>(const float*, float*, float*, ActOut, int, int, int, int, cudaStream_t);
-template int launch_attn_prefill<bf16>(const bf16*, bf16*, bf16*, ActOut, int, int, int, int, cudaStream_t);
+template int launch_attn_prefill<float>(const float*, float*, float*, ActOut, int, int, int, int, int, cudaStream_t);
+template int launch_attn_prefill<bf16>(const bf16*, bf16*, bf16*, ActOut, int, int, int, int, int, cudaStream_t);
 
 template <typename T>
 int launch_attn_encoder(const T* qkv, ActOut out, int B, int S, int H, int hd, cudaStream_t st) {
   switch (hd) {
-    case 16: return launch_attn_seq<T, 16, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
-    case 32: return launch_attn_seq<T, 32, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
-    case 64: return launch_attn_seq<T, 64, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
-    case 96: return launch_attn_seq<T, 96, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
-    case 128: return launch_attn_seq<T, 128, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
-    case 160: return launch_attn_seq<T, 160, false>(qkv, nullptr, nullptr, out, B, S, H, 0, st);
+    case 16: return launch_attn_seq<T, 16, false>(qkv, nullptr, nullptr, out, B, S, H, 0, 1, st);
+    case 32: return launch_attn_seq<T, 32, false>(qkv, nullptr, nullptr, out, B, S, H, 0, 1, st);
+    case 64: return launch_attn_seq<T, 64, false>(qkv, nullptr, nullptr, out, B, S, H, 0, 1, st);
+    case 96: return launch_attn_seq<T, 96, false>(qkv, nullptr, nullptr, out, B, S, H, 0, 1, st);
+    case 128: return launch_attn_seq<T, 128, false>(qkv, nullptr, nullptr, out, B, S, H, 0, 1, st);
+    case 160: return launch_attn_seq<T, 160, false>(qkv, nullptr, nullptr, out, B, S, H, 0, 1, st);
     default: set_error("attn_encoder: unsupported head_dim %d (16/32/64/96/128/160)", hd); return GIC_ERR_UNSUPPORTED;
   }
 }

@@ -65,6 +65,9 @@ struct Workspace {
   int64_t* ids = nullptr;          // [rows, max_new]
   unsigned char* finished = nullptr; int* first_eos = nullptr;
   int *d_step = nullptr, *d_pos = nullptr, *done_counter = nullptr;
+  // beam search only
+  void* kv2 = nullptr;             // second KV cache (reorder target; the two swap every step)
+  BeamState beam;
   size_t bytes = 0;
 };
 
@@ -228,6 +231,20 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
     w->n_parts_max = LMHEAD_F32_PARTS;
   } else {
     w->n_parts_max = ceil_div(e->V, 32);
+    if (w->beams > 1) w->logits = c.take<float>((size_t)w->rows * e->V);  // beam search needs full rows for log-softmax + top-2K
+  }
+  if (w->beams > 1) {
+    if (e->cfg.dtype == GIC_DTYPE_BF16) w->kv2 = c.take<bf16>(kv_elems);
+    else w->kv2 = c.take<float>(kv_elems);
+    BeamState& bs = w->beam;
+    const size_t nseq = (size_t)w->rows * (max_new > 0 ? max_new : 1);
+    bs.B = B; bs.beams = w->beams; bs.max_new = max_new; bs.V = e->V; bs.eos = e->cfg.eos_token_id;
+    for (int i = 0; i < 2; ++i) { bs.run_seq[i] = c.take<int>(nseq); bs.fin_seq[i] = c.take<int>(nseq); }
+    bs.run_score = c.take<float>(w->rows); bs.fin_score = c.take<float>(w->rows);
+    bs.fin_flag = c.take<unsigned char>(w->rows); bs.fin_len = c.take<int>(w->rows);
+    bs.unsat = c.take<unsigned char>(B);
+    bs.beam_idx = c.take<int>(w->rows); bs.next_tok = c.take<int>(w->rows);
+    bs.cand_score = c.take<float>((size_t)2 * w->rows); bs.cand_idx = c.take<int>((size_t)2 * w->rows);
   }
   w->part_val = c.take<float>((size_t)w->n_parts_max * w->rows);
   w->part_idx = c.take<int>((size_t)w->n_parts_max * w->rows);
@@ -282,13 +299,13 @@ static int gpt_layer(const gic_engine* e, const Workspace& w, int l, float* h, i
     ProfScope ps(e, prefill ? "attn_prefill" : "attn_decode", st);
     bf16* kc = (bf16*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
     bf16* vc = kc + w.kv_layer_elems;
-    if (prefill) GIC_TRY(launch_attn_prefill<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, st));
+    if (prefill) GIC_TRY(launch_attn_prefill<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, w.beams, st));
     else GIC_TRY(launch_attn_decode<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st));
   } else {
     ProfScope ps(e, prefill ? "attn_prefill" : "attn_decode", st);
     float* kc = (float*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
     float* vc = kc + w.kv_layer_elems;
-    if (prefill) GIC_TRY(launch_attn_prefill<float>(w.qkv_f32, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, st));
+    if (prefill) GIC_TRY(launch_attn_prefill<float>(w.qkv_f32, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, w.beams, st));
     else GIC_TRY(launch_attn_decode<float>(w.qkv_f32, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st));
   }
   ActOut hres; hres.f32 = h;
@@ -584,6 +601,7 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   GIC_TRY(fork_stream(e, user));
 
   GIC_TRY(launch_init_decode_state(w.finished, w.first_eos, B, max_new, w.d_step, w.d_pos, w.done_counter, P, st));
+  if (e->profiling) GIC_TRY(launch_spin(150000000LL, st));  // ~75 ms: lets the host queue ahead so events time the device only
   { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
   GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));
   // ---- prefill over the P prefix tokens of every row ----
@@ -622,12 +640,54 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   return join_stream(e, user);
 }
 
+// ln_f -> LM head with the full fp32 logit rows materialised (beam search needs log-softmax + top-2K over beams x V)
+static int lm_head_logits(const gic_engine* e, const Workspace& w, const float* h, long row_stride, int rows, cudaStream_t st) {
+  { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, row_stride, e->lnf.w, e->lnf.b, w.a.out(), rows, e->d, st)); }
+  ActOut o; o.f32 = w.logits;
+  ProfScope ps(e, "lm_head", st);
+  return linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st);
+}
+
 int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int num_beams, float length_penalty, int64_t* ids_out,
-                      float* scores_out, void* workspace, size_t workspace_bytes, void* stream) {
-  (void)e; (void)x; (void)batch; (void)max_new; (void)num_beams; (void)length_penalty; (void)ids_out; (void)scores_out;
-  (void)workspace; (void)workspace_bytes; (void)stream;
-  gic::set_error("gic_generate_beam: not implemented yet");
-  return GIC_ERR_UNSUPPORTED;
+                      float* scores_out, int32_t* gen_len_out, void* workspace, size_t workspace_bytes, void* stream) {
+  GIC_TRY(check_ready(e));
+  GIC_REQUIRE(x && ids_out, "null argument");
+  GIC_REQUIRE(max_new >= 1, "max_new_tokens must be >= 1");
+  GIC_REQUIRE(num_beams >= 2 && num_beams <= 8, "num_beams must be in [2, 8] (got %d); use gic_generate_greedy for 1", num_beams);
+  Workspace w;
+  GIC_TRY(prepare_ws(e, workspace, workspace_bytes, batch, max_new, num_beams, &w));
+  cudaStream_t user = (cudaStream_t)stream, st = e->stream;
+  const int d = e->d, B = batch, P = w.P, nb = num_beams, rows = w.rows, K = 2 * nb;
+  GIC_TRY(fork_stream(e, user));
+  GIC_TRY(launch_beam_init(w.beam, st));
+  { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
+  GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));
+  // prefill once per image; its K/V land in cache row b*beams and the first reorder fans them out to every beam
+  for (int l = 0; l < e->L; ++l) GIC_TRY(gpt_layer(e, w, l, w.h, B * P, true, st));
+  GIC_TRY(lm_head_logits(e, w, w.h + (size_t)(P - 1) * d, (long)P * d, B, st));
+  const size_t esz = e->cfg.dtype == GIC_DTYPE_BF16 ? sizeof(bf16) : sizeof(float);
+  (void)esz;
+  for (int t = 0; t < max_new; ++t) {
+    const int live = t == 0 ? 1 : nb;  // only beam 0 is live at the first step (running scores 0, -1e9, ...)
+    { ProfScope ps(e, "beam_topk", st);
+      GIC_TRY(launch_beam_topk(w.logits, B, live, live, w.beam.run_score, nb, e->V, K, w.beam.cand_score, w.beam.cand_idx, st)); }
+    const float denom = (float)pow((double)(t + 1), (double)length_penalty);
+    { ProfScope ps(e, "beam_update", st); GIC_TRY(launch_beam_update(w.beam, t, denom, st)); }
+    if (t + 1 == max_new) break;
+    // reorder_cache: dst[row] = src[beam_idx[row]] over the P + t cached positions, then swap the two caches
+    { ProfScope ps(e, "kv_reorder", st);
+      if (e->cfg.dtype == GIC_DTYPE_BF16)
+        GIC_TRY(launch_kv_reorder<bf16>((const bf16*)w.kv, (bf16*)w.kv2, w.beam.beam_idx, e->L, rows, e->H, P + t, w.t_max, st));
+      else
+        GIC_TRY(launch_kv_reorder<float>((const float*)w.kv, (float*)w.kv2, w.beam.beam_idx, e->L, rows, e->H, P + t, w.t_max, st)); }
+    { void* tmp = w.kv; w.kv = w.kv2; w.kv2 = tmp; }
+    GIC_TRY(launch_beam_embed(w.beam.next_tok, e->wte_f32, e->wte_f32 ? nullptr : e->lm_head.w_hi, e->wpe, P + t, d, w.h_dec, rows, st));
+    GIC_TRY(launch_set_int(w.d_pos, P + t, st));
+    for (int l = 0; l < e->L; ++l) GIC_TRY(gpt_layer(e, w, l, w.h_dec, rows, false, st));
+    GIC_TRY(lm_head_logits(e, w, w.h_dec, d, rows, st));
+  }
+  GIC_TRY(launch_beam_finalize(w.beam, max_new & 1, ids_out, scores_out, gen_len_out, st));
+  return join_stream(e, user);
 }
 
 int gic_kv_reorder(gic_engine* e, const void* kv_src, void* kv_dst, const int32_t* beam_idx, int rows, int ctx_len, int t_max, void* stream) {

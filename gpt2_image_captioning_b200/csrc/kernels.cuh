@@ -60,8 +60,11 @@ int launch_build_mapper_seq(const float* lin, const float* prefix_const, float* 
 
 // ---- attention.cu -------------------------------------------------------------------------------------------------
 // KV cache layout: [L][2][rows][H][T_max][64], element T.  qkv rows are [.., 3d] (q | k | v), head h at h*64.
+// cache_row_mult: sequence b writes its K/V into cache row b * cache_row_mult (beam search prefills B rows into a
+// cache laid out for B * beams rows)
 template <typename T>
-int launch_attn_prefill(const T* qkv, T* kcache, T* vcache, ActOut out, int B, int P, int H, int t_max, cudaStream_t st);
+int launch_attn_prefill(const T* qkv, T* kcache, T* vcache, ActOut out, int B, int P, int H, int t_max, int cache_row_mult,
+                        cudaStream_t st);
 template <typename T>
 int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows, int H, int t_max, cudaStream_t st);
 template <typename T>
@@ -89,6 +92,26 @@ int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st);
 int launch_init_decode_state(unsigned char* finished, int* first_eos, int B, int max_new, int* d_step, int* d_pos, int* done_counter,
                              int P, cudaStream_t st);
 int launch_gen_len(const int* first_eos, int B, int max_new, int* gen_len_out, cudaStream_t st);
+int launch_spin(long long cycles, cudaStream_t st);  // profiling aid (see lmhead.cu)
+
+// ---- beam.cu ------------------------------------------------------------------------------------------------------
+struct BeamState {
+  int B, beams, max_new, V, eos;
+  int* run_seq[2]; int* fin_seq[2];       // [B, beams, max_new] token ids, double-buffered across steps
+  float* run_score; float* fin_score;     // [B, beams]
+  unsigned char* fin_flag; int* fin_len;  // [B, beams]
+  unsigned char* unsat;                   // [B] early-stop heuristic still unsatisfied
+  int* beam_idx; int* next_tok;           // [B * beams] parent cache row / token of every surviving beam
+  float* cand_score; int* cand_idx;       // [B, 2 * beams]
+};
+int launch_beam_init(const BeamState& s, cudaStream_t st);
+int launch_beam_topk(const float* logits, int B, int rows_per_image, int n_live, const float* run_score, int beams, int V, int K,
+                     float* cand_score, int* cand_idx, cudaStream_t st);
+int launch_beam_update(const BeamState& s, int step, float len_denom, cudaStream_t st);
+int launch_beam_embed(const int* next_tok, const float* wte_f32, const bf16* wte_bf16, const float* wpe, int pos, int d, float* h, int rows,
+                      cudaStream_t st);
+int launch_set_int(int* p, int v, cudaStream_t st);
+int launch_beam_finalize(const BeamState& s, int final_buf, int64_t* ids_out, float* scores_out, int* gen_len_out, cudaStream_t st);
 
 // ---- retrieval.cu -------------------------------------------------------------------------------------------------
 size_t topk_workspace_bytes(int B, int N, int D, int k);

@@ -149,6 +149,19 @@ int launch_init_decode_state(unsigned char* finished, int* first_eos, int B, int
   return GIC_OK;
 }
 
+// Profiling aid: occupies the stream for `cycles` SM clocks so the host can queue the whole step behind it; the queued
+// kernels then run back to back and the CUDA events between them measure device time, not host launch latency.
+__global__ void spin_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {
+  }
+}
+int launch_spin(long long cycles, cudaStream_t st) {
+  spin_kernel<<<1, 1, 0, st>>>(cycles);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  return GIC_OK;
+}
+
 // L_gen of src/models.py:389-391: the reference loop stops BEFORE a step once every row has emitted EOS, so
 // L_gen = max_new if some row never finished, else max_b(first_eos[b]) + 1.
 __global__ void gen_len_kernel(const int* __restrict__ first_eos, int B, int max_new, int* gen_len_out) {

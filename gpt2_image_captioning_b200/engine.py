@@ -178,11 +178,13 @@ class CaptionEngine:
         return (ids, gen_len, logits) if return_logits else (ids, gen_len)
 
     def generate_beam(self, x: torch.Tensor, max_new_tokens: int, num_beams: int = 5, length_penalty: float = 1.0):
+        """ids int64 [B, max_new_tokens] (eos padded), scores fp32 [B], gen_len int32 [1] = longest selected hypothesis."""
         x = self._check_x(x)
         B = x.shape[0]
         ids = torch.empty(B, max_new_tokens, dtype=torch.int64, device=self.device)
         scores = torch.empty(B, dtype=torch.float32, device=self.device)
+        gen_len = torch.zeros(1, dtype=torch.int32, device=self.device)
         if B > 0 and max_new_tokens > 0:
-            ops.generate_beam(self.handle, x, max_new_tokens, num_beams, length_penalty, ids, scores,
+            ops.generate_beam(self.handle, x, max_new_tokens, num_beams, length_penalty, ids, scores, gen_len,
                               self.workspace(B, max_new_tokens, num_beams))
-        return ids, scores
+        return ids, scores, gen_len

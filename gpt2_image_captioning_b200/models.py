@@ -106,8 +106,8 @@ class _EngineMixin:
         beams = int(getattr(self, "num_beams", 1) or 1)
         with torch.cuda.device(eng.device):
             if beams > 1:
-                ids, _ = eng.generate_beam(image_embeddings, max_length, beams, float(getattr(self, "length_penalty", 1.0)))
-                return ids.to(device)
+                ids, _, gen_len = eng.generate_beam(image_embeddings, max_length, beams, float(getattr(self, "length_penalty", 1.0)))
+                return ids[:, : int(gen_len.item())].to(device)  # HF crops to the longest selected hypothesis
             ids, gen_len = eng.generate_greedy(image_embeddings, max_length)
             # one D2H read at the end of the loop (the reference syncs every step, src/models.py:390)
             n = int(gen_len.item())

@@ -38,14 +38,14 @@ def generate_greedy(engine: int, image_embeddings: torch.Tensor, max_new_tokens:
                                       _ptr(gen_len_out), _ptr(logits_out), _ptr(workspace), workspace.numel(), _stream()))
 
 
-@torch.library.custom_op("gic::generate_beam", mutates_args=("ids_out", "scores_out", "workspace"))
+@torch.library.custom_op("gic::generate_beam", mutates_args=("ids_out", "scores_out", "gen_len_out", "workspace"))
 def generate_beam(engine: int, image_embeddings: torch.Tensor, max_new_tokens: int, num_beams: int, length_penalty: float,
-                  ids_out: torch.Tensor, scores_out: torch.Tensor, workspace: torch.Tensor) -> None:
-    _need_cuda(image_embeddings, ids_out, scores_out, workspace)
+                  ids_out: torch.Tensor, scores_out: torch.Tensor, gen_len_out: torch.Tensor, workspace: torch.Tensor) -> None:
+    _need_cuda(image_embeddings, ids_out, scores_out, gen_len_out, workspace)
     L = _capi.lib()
     _capi.check(L.gic_generate_beam(engine, _ptr(image_embeddings), image_embeddings.shape[0], max_new_tokens, num_beams,
-                                    float(length_penalty), _ptr(ids_out), _ptr(scores_out), _ptr(workspace), workspace.numel(),
-                                    _stream()))
+                                    float(length_penalty), _ptr(ids_out), _ptr(scores_out), _ptr(gen_len_out), _ptr(workspace),
+                                    workspace.numel(), _stream()))
 
 
 @torch.library.custom_op("gic::kv_reorder", mutates_args=("kv_dst",))

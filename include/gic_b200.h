@@ -134,10 +134,12 @@ GIC_API int gic_generate_greedy(gic_engine* e, const float* image_embeddings /* 
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* Beam search (not in the reference; semantics of HF GenerationMixin._beam_search, generation/utils.py:3076-3385,
- * early_stopping=False, length_penalty given, num_return_sequences=1): ids_out dev int64 [B, max_new_tokens]
- * padded with eos; scores_out dev fp32 [B] (may be NULL). */
+ * do_sample=False, early_stopping=False, length_penalty given, num_return_sequences=1, eos = pad): ids_out dev int64
+ * [B, max_new_tokens] = best finished hypothesis per image padded with eos; scores_out dev fp32 [B] (may be NULL) its
+ * length-normalised score; *gen_len_out dev int32 (may be NULL) the longest selected hypothesis (HF crops to it).
+ * 2 <= num_beams <= 8.  The KV cache is reordered every step with the gic_kv_reorder gather. */
 GIC_API int gic_generate_beam(gic_engine* e, const float* image_embeddings, int batch, int max_new_tokens, int num_beams,
-                      float length_penalty, int64_t* ids_out, float* scores_out,
+                      float length_penalty, int64_t* ids_out, float* scores_out, int32_t* gen_len_out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* replaces DynamicCache.reorder_cache / index_select(0, beam_idx) per layer (HF cache_utils.py:81-85):

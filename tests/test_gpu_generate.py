@@ -138,6 +138,40 @@ def test_larger_models_token_exact(name, dtype):
             assert a["gap"] < (1e-4 if dtype == "fp32" else 2e-3), f"{name}/{dtype}: mismatch is not a near-tie: {a}"
 
 
+@pytest.mark.parametrize("name,dtype,emb_total", [("tiny_mlp_beam5", "fp32", 8), ("tiny_mlp_beam5", "bf16x2", 8),
+                                                   ("c3_medium_tfm_beam5", "fp32", 8), ("c3_medium_tfm_beam5", "bf16x2", 8)])
+def test_beam_search_matches_hf_generation(name, dtype, emb_total):
+    """Beam search (width 5, KV-cache beam reorder) is not in the reference; the fixture is HF GenerationMixin on
+    `model.gpt` with the same pinned weights.  Config 3: GPT-2 medium + 8-layer transformer mapper, P=40."""
+    g = gu.load(name)
+    g = dict(g, emb_total=np.array(emb_total))
+    model, oracle, x = gpu_util.product_model(g, dtype)
+    model.num_beams = int(g["num_beams"])
+    ids = model.generate(image_embeddings=x.to(DEV), max_length=int(g["max_length"]), temperature=0.0).cpu().numpy()
+    ref = g["ids"].astype(np.int64)
+    rows_same = [(ids.shape[1] == ref.shape[1]) and np.array_equal(ids[b], ref[b]) for b in range(ref.shape[0])]
+    _report(test="beam", case=name, dtype=dtype, shape=list(ids.shape), ref_shape=list(ref.shape), rows_identical=int(sum(rows_same)),
+            rows=len(rows_same))
+    assert ids.shape == ref.shape, (ids.shape, ref.shape)
+    assert all(rows_same), (ids, ref)
+
+
+def test_kv_reorder_gathers_rows():
+    from gpt2_image_captioning_b200 import ops
+    g = gu.load("tiny_mlp_eos")
+    for dtype, tdt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+        model, _, _ = gpu_util.product_model(g, dtype)
+        eng = model._get_engine()
+        L, H, rows, t_max, ctx = 2, 2, 10, 20, 13
+        src = torch.randn(L, 2, rows, H, t_max, 64, device=DEV).to(tdt)
+        dst = torch.zeros_like(src)
+        idx = torch.tensor([3, 3, 0, 9, 1, 1, 1, 7, 2, 5], dtype=torch.int32, device=DEV)
+        ops.kv_reorder(eng.handle, src, dst, idx, ctx, t_max)
+        want = src[:, :, idx.long()]
+        assert torch.equal(dst[..., :ctx, :], want[..., :ctx, :])
+        assert torch.count_nonzero(dst[..., ctx:, :]) == 0  # only the live positions are moved
+
+
 def test_mapper_forward_matches_oracle():
     for name in ("tiny_tfm", "tiny_mlp_task", "c1_small_mlp_b64"):
         g = gu.load(name)
