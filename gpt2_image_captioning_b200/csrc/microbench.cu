@@ -1,0 +1,161 @@
+// Stand-alone kernel microbenchmarks (not part of the library): `make microbench && build/microbench`.
+// Times the decode-step kernels of the headline workload in isolation with CUDA events, rotating over 12 weight /
+// cache sets so the working set exceeds L2 like a real step, plus a few hardware probes (launch floor, SM clock,
+// dependent-load latency).
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace gic;
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } \
+  } while (0)
+#define OK(x)                                                              \
+  do {                                                                     \
+    if ((x) != GIC_OK) { printf("gic error: %s (%s:%d)\n", get_error(), __FILE__, __LINE__); exit(1); } \
+  } while (0)
+
+namespace gic {
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap); }
+const char* get_error() { return g_err; }
+void note_launch() {}
+}  // namespace gic
+
+__global__ void empty_kernel() {}
+__global__ void clock_probe(long long* out) {
+  long long c0 = clock64();
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < 200000);  // 200 us
+  out[0] = clock64() - c0;
+  out[1] = (long long)(t1 - t0);
+}
+__global__ void chase_kernel(const int* __restrict__ next, int start, int n, long long* out) {
+  int p = start;
+  long long c0 = clock64();
+  for (int i = 0; i < n; ++i) p = next[p];
+  out[0] = clock64() - c0;
+  out[1] = p;
+}
+
+template <typename F>
+static float time_loop(cudaStream_t st, int iters, F f) {
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  for (int i = 0; i < 3; ++i) f(i);
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventRecord(a, st));
+  for (int i = 0; i < iters; ++i) f(i);
+  CK(cudaEventRecord(b, st));
+  CK(cudaEventSynchronize(b));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  return ms * 1000.f / iters;  // us per iteration
+}
+
+int main(int argc, char** argv) {
+  const int B = argc > 1 ? atoi(argv[1]) : 1024;
+  const int d = 768, H = 12, L = 12, V = 50257;
+  cudaStream_t st;
+  CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device %s, %d SMs, clockRate %d kHz, memClock %d kHz, L2 %d MB\n", prop.name, prop.multiProcessorCount, prop.clockRate,
+         prop.memoryClockRate, prop.l2CacheSize >> 20);
+
+  // ---- probes ----
+  printf("empty kernel back-to-back: %.2f us/launch\n", time_loop(st, 2000, [&](int) { empty_kernel<<<1, 32, 0, st>>>(); }));
+  long long* dout; CK(cudaMalloc(&dout, 16));
+  clock_probe<<<1, 1, 0, st>>>(dout);
+  long long hout[2]; CK(cudaMemcpyAsync(hout, dout, 16, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+  printf("SM clock under a 1-thread spin: %.0f MHz\n", (double)hout[0] / ((double)hout[1] / 1000.0));
+  {
+    const int n = 1 << 24;  // 64 MB of ints: mostly L2-resident after warm-up? (126 MB L2) -> use stride to defeat
+    std::vector<int> h(n);
+    const int stride = 4099 * 32;
+    for (int i = 0; i < n; ++i) h[i] = (int)(((long long)i + stride) % n);
+    int* dn; CK(cudaMalloc(&dn, (size_t)n * 4));
+    CK(cudaMemcpy(dn, h.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+    chase_kernel<<<1, 1, 0, st>>>(dn, 0, 2000, dout);
+    CK(cudaMemcpyAsync(hout, dout, 16, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    printf("dependent global load latency (first touch): %.0f cycles\n", (double)hout[0] / 2000);
+    chase_kernel<<<1, 1, 0, st>>>(dn, 0, 2000, dout);
+    CK(cudaMemcpyAsync(hout, dout, 16, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+    printf("dependent global load latency (second pass, L2): %.0f cycles\n", (double)hout[0] / 2000);
+    cudaFree(dn);
+  }
+
+  // ---- buffers: 12 rotating sets ----
+  const int SETS = 12;
+  auto dmalloc = [&](size_t bytes) { void* p; CK(cudaMalloc(&p, bytes)); CK(cudaMemset(p, 0, bytes)); return p; };
+  float* h = (float*)dmalloc((size_t)B * d * 4);
+  float* lnw = (float*)dmalloc(d * 4); float* lnb = (float*)dmalloc(d * 4);
+  bf16* a = (bf16*)dmalloc((size_t)B * 4 * d * 2);
+  bf16* qkv = (bf16*)dmalloc((size_t)B * 3 * d * 2);
+  bf16* o = (bf16*)dmalloc((size_t)B * 4 * d * 2);
+  float* bias = (float*)dmalloc(4 * d * 4);
+  int* dpos = (int*)dmalloc(4);
+  const int t_max = 40;
+  std::vector<bf16*> w_qkv(SETS), w_proj(SETS), w_fc(SETS), w_fc2(SETS), kc(SETS), vc(SETS);
+  for (int s = 0; s < SETS; ++s) {
+    w_qkv[s] = (bf16*)dmalloc((size_t)3 * d * d * 2); w_proj[s] = (bf16*)dmalloc((size_t)d * d * 2);
+    w_fc[s] = (bf16*)dmalloc((size_t)4 * d * d * 2); w_fc2[s] = (bf16*)dmalloc((size_t)4 * d * d * 2);
+    kc[s] = (bf16*)dmalloc((size_t)B * H * t_max * 64 * 2); vc[s] = (bf16*)dmalloc((size_t)B * H * t_max * 64 * 2);
+  }
+  bf16* wte = (bf16*)dmalloc((size_t)V * d * 2);
+  float* pv = (float*)dmalloc((size_t)2048 * B * 4); int* pi = (int*)dmalloc((size_t)2048 * B * 4);
+  OK(tma_init()); OK(gemm_bf16_configure());
+
+  // ---- layernorm ----
+  for (int rows : {32, 256, B, 4 * B}) {
+    float* hh = (float*)dmalloc((size_t)rows * d * 4);
+    bf16* aa = (bf16*)dmalloc((size_t)rows * d * 2);
+    ActOut y; y.hi = aa;
+    printf("layernorm rows=%5d d=%d: %.2f us\n", rows, d, time_loop(st, 200, [&](int) { OK(launch_layernorm(hh, d, lnw, lnb, y, rows, d, st)); }));
+    cudaFree(hh); cudaFree(aa);
+  }
+  // ---- GEMMs (decode shapes), weights rotate over 12 sets ----
+  struct Shape { const char* name; int N, K; std::vector<bf16*>* w; int epi; bool res; };
+  Shape shapes[] = {{"qkv", 3 * d, d, &w_qkv, EPI_NONE, false}, {"proj", d, d, &w_proj, EPI_RESIDUAL, true},
+                    {"fc", 4 * d, d, &w_fc, EPI_GELU, false}, {"fc2", d, 4 * d, &w_fc2, EPI_RESIDUAL, true}};
+  for (auto& s : shapes) {
+    for (int bn : {32, 64, 128}) {
+      std::vector<GemmBf16Args> args(SETS);
+      for (int i = 0; i < SETS; ++i) {
+        GemmBf16Args& g = args[i];
+        OK(make_tma_2d_bf16(&g.a_hi, a, B, s.K, s.K, 128));
+        OK(make_tma_2d_bf16(&g.w_hi, (*s.w)[i], s.N, s.K, s.K, bn));
+        g.M = B; g.N = s.N; g.K = s.K; g.block_n = bn; g.epilogue = s.epi; g.bias = bias; g.ld_out = s.N;
+        if (s.res) g.out.f32 = h; else g.out.hi = (s.N == 3 * d ? qkv : o);
+      }
+      float us = time_loop(st, 240, [&](int i) { OK(launch_gemm_bf16(args[i % SETS], st)); });
+      printf("gemm %-4s M=%d N=%d K=%d block_n=%3d: %7.2f us  %6.1f TFLOP/s  (picked %d)\n", s.name, B, s.N, s.K, bn, us,
+             2.0 * B * s.N * s.K / us * 1e-6, gemm_bf16_pick_block_n(B, s.N));
+    }
+  }
+  {
+    GemmBf16Args g;
+    OK(make_tma_2d_bf16(&g.a_hi, a, B, d, d, 128));
+    OK(make_tma_2d_bf16(&g.w_hi, wte, V, d, d, 128));
+    g.M = B; g.N = V; g.K = d; g.block_n = 128; g.part_val = pv; g.part_idx = pi;
+    float us = time_loop(st, 50, [&](int) { OK(launch_gemm_bf16(g, st)); });
+    printf("lm_head M=%d N=%d K=%d: %.2f us  %.1f TFLOP/s\n", B, V, d, us, 2.0 * B * V * d / us * 1e-6);
+  }
+  // ---- decode attention ----
+  for (int ctx : {11, 25, 39}) {
+    int pos = ctx - 1;
+    CK(cudaMemcpy(dpos, &pos, 4, cudaMemcpyHostToDevice));
+    ActOut y; y.hi = o;
+    float us = time_loop(st, 240, [&](int i) { OK(launch_attn_decode<bf16>(qkv, kc[i % SETS], vc[i % SETS], y, dpos, B, H, t_max, st)); });
+    const double bytes = 2.0 * B * d * (2.0 * ctx + 2 + 3 + 1);
+    printf("attn_decode rows=%d ctx=%d: %.2f us  %.0f GB/s\n", B, ctx, us, bytes / us * 1e-3);
+  }
+  return 0;
+}
