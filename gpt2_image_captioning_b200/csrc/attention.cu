@@ -27,7 +27,9 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const T* __restrict__ 
   extern __shared__ float smem_scores[];  // [warps][t_max]
   const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wid = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+  pdl_launch_dependents();
   if (wid >= rows * H) return;
+  pdl_wait();
   const int row = wid / H, h = wid % H;
   const int d = H * HD;
   const int pos = *d_pos;  // tokens already cached == position of the new token
@@ -137,8 +139,7 @@ int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int
   const int blocks = ceil_div(warps, 4);
   const size_t smem = (size_t)4 * t_max * sizeof(float);
   GIC_REQUIRE(smem <= 48 * 1024, "attn_decode: t_max %d too large", t_max);
-  attn_decode_kernel<T><<<blocks, 128, smem, st>>>(qkv, kcache, vcache, out, d_pos, rows, H, t_max);
-  GIC_CHECK_CUDA(cudaGetLastError());
+  GIC_CHECK_CUDA(launch_kernel(attn_decode_kernel<T>, dim3(blocks), dim3(128), smem, st, qkv, kcache, vcache, out, d_pos, rows, H, t_max));
   note_launch();
   return GIC_OK;
 }
@@ -162,6 +163,8 @@ __global__ void __launch_bounds__(128) attn_seq_kernel(const T* __restrict__ qkv
   const int d = H * HDIM;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const T* base = qkv + (size_t)row * S * 3 * d + h * HDIM;
+  pdl_launch_dependents();
+  pdl_wait();
 
   for (int i = threadIdx.x; i < S * HDIM; i += blockDim.x) {
     const int t = i / HDIM, c = i % HDIM;
@@ -227,8 +230,8 @@ static int launch_attn_seq(const T* qkv, T* kcache, T* vcache, ActOut out, int B
   GIC_REQUIRE(smem <= 200 * 1024, "attention: sequence %d x head_dim %d does not fit in shared memory", S, HDIM);
   auto kern = attn_seq_kernel<T, HDIM, CAUSAL>;
   if (smem > 48 * 1024) GIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<B * H, 128, smem, st>>>(qkv, kcache, vcache, out, S, H, t_max, cache_row_mult, 1.0f / sqrtf((float)HDIM));
-  GIC_CHECK_CUDA(cudaGetLastError());
+  GIC_CHECK_CUDA(launch_kernel(kern, dim3(B * H), dim3(128), smem, st, qkv, kcache, vcache, out, S, H, t_max, cache_row_mult,
+                               1.0f / sqrtf((float)HDIM)));
   note_launch();
   return GIC_OK;
 }

@@ -110,6 +110,12 @@ struct gic_engine {
 
 namespace gic {
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* v = getenv("GIC_NO_PDL"); on = (v && v[0] == '1') ? 0 : 1; }
+  return on == 1;
+}
+
 // kernels launched by this library (graph replays count their kernel nodes) -- bench.py's `gpu_launches`
 static unsigned long long g_launches = 0;
 void note_launch() { ++g_launches; }

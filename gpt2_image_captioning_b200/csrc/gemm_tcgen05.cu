@@ -150,7 +150,7 @@ struct GemmTile {
   static constexpr int BUDGET = SPLIT ? 196 * 1024 : 100 * 1024;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + BLOCK_N * 4 /* bias */;
   static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
 };
 
@@ -165,10 +165,12 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(const _
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * Tile::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * GEMM_BLOCK_M, n0 = blockIdx.y * BLOCK_N;
   const int nk = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  pdl_launch_dependents();  // let the next kernel's CTAs be scheduled behind this grid (see common.cuh)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.a_hi);
@@ -190,6 +192,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(const _
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_acc = *tmem_base_slot;
+  pdl_wait();  // prologue above overlapped the previous kernel; its outputs are visible from here on
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -238,27 +241,47 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(const _
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
+    // Everything that does not depend on the accumulator is fetched BEFORE waiting for it (bias tile -> smem, first
+    // residual chunk -> registers), and inside the loop the next chunk's residual is loaded before the current chunk is
+    // stored: output and residual alias (in-place +=), so loads placed after stores would serialise one L2 round trip per
+    // float4 (ncu source page, round 1).
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const int et = (warp - 2) * 32 + lane;  // 0..127 over the four epilogue warps
+    for (int c = et; c < BLOCK_N; c += 128) s_bias[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+    const bool resid = p.epilogue == EPI_RESIDUAL;
+    const bool vec_f32 = (p.ld_f32 % 4 == 0);
+    float4 res_next[8];
+    auto load_res = [&](int c0) {
+      const float* src = p.out_f32 + (size_t)row * p.ld_f32 + n0 + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(src + 4 * j);
+    };
+    const bool res_vec_ok = resid && row_ok && vec_f32;
+    if (res_vec_ok && n0 + 32 <= p.N) load_res(0);
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
     float best = -INFINITY;
     int best_idx = 0x7fffffff;
-    const bool row_ok = row < p.M;
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t r[32];
       ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       const int col0 = n0 + c0;
       if (col0 >= p.N) continue;  // warp-uniform
+      const bool full = (col0 + 32 <= p.N);
+      float4 res_cur[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) res_cur[j] = res_next[j];
+      if (res_vec_ok && c0 + 32 < BLOCK_N && col0 + 64 <= p.N) load_res(c0 + 32);
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int col = col0 + j;
-        float x = __uint_as_float(r[j]);
-        if (p.bias && col < p.N) x += __ldg(p.bias + col);
+        float x = __uint_as_float(r[j]) + s_bias[c0 + j];
         if (p.epilogue == EPI_TANH) x = tanhf(x);
-        else if (p.epilogue == EPI_GELU) x = gelu_tanh(x);
+        else if (p.epilogue == EPI_GELU) x = SPLIT ? gelu_tanh(x) : gelu_tanh_fast(x);
         else if (p.epilogue == EPI_RELU) x = fmaxf(x, 0.f);
         v[j] = x;
       }
@@ -273,23 +296,22 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(const _
         }
       }
       if (!row_ok) continue;
-      const bool full = (col0 + 32 <= p.N);
       if (p.out_f32) {
         float* dst = p.out_f32 + (size_t)row * p.ld_f32 + col0;
-        if (full && (p.ld_f32 % 4 == 0)) {
+        if (full && vec_f32) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (p.epilogue == EPI_RESIDUAL) {
-              const float4 old = *reinterpret_cast<const float4*>(dst + j);
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            *reinterpret_cast<float4*>(dst + j) = o;
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (resid) { o.x += res_cur[j].x; o.y += res_cur[j].y; o.z += res_cur[j].z; o.w += res_cur[j].w; }
+            *reinterpret_cast<float4*>(dst + 4 * j) = o;
           }
         } else {
+          float old[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) old[j] = (resid && col0 + j < p.N) ? dst[j] : 0.f;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) dst[j] = (p.epilogue == EPI_RESIDUAL) ? dst[j] + v[j] : v[j];
+            if (col0 + j < p.N) dst[j] = old[j] + v[j];
         }
       }
       if (p.out_hi) {
@@ -370,15 +392,13 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t col
   return GIC_OK;
 }
 
-// Tile width: the widest BLOCK_N whose grid still covers the 148 SMs about once; the small-N GEMMs of a decode
-// step (N = 768 .. 3072 at M <= 1024) otherwise leave most of the chip idle.
+// Tile width.  Measured on B200 (csrc/microbench.cu, M = 1024): the single-wave body GEMMs of a decode step run fastest
+// with 64-wide tiles (qkv 18 us vs 26 us at 128; fc2 29 vs 43), 128-wide tiles win once the grid covers the chip twice
+// (LM head, prefill), 32-wide tiles only help when even 64-wide tiles leave most SMs idle (M <= 128).
 int gemm_bf16_pick_block_n(int M, int N) {
-  const int m_tiles = ceil_div(M, GEMM_BLOCK_M);
-  const int candidates[3] = {128, 64, 32};
-  for (int i = 0; i < 3; ++i) {
-    const int bn = candidates[i];
-    if ((long)m_tiles * ceil_div(N, bn) >= 140) return bn;
-  }
+  const long m_tiles = ceil_div(M, GEMM_BLOCK_M);
+  if (m_tiles * ceil_div(N, 128) >= 2 * 148) return 128;
+  if (m_tiles * ceil_div(N, 64) >= 74) return 64;
   return 32;
 }
 
@@ -408,8 +428,7 @@ static int launch_cfg(const GemmKernelParams& kp, cudaStream_t st) {
   using Tile = GemmTile<BLOCK_N, SPLIT>;
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT>;
   dim3 grid(ceil_div(kp.M, GEMM_BLOCK_M), ceil_div(kp.N, BLOCK_N));
-  kern<<<grid, GEMM_THREADS, Tile::SMEM_BYTES, st>>>(kp);
-  GIC_CHECK_CUDA(cudaGetLastError());
+  GIC_CHECK_CUDA(launch_kernel(kern, grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st, kp));
   note_launch();
   return GIC_OK;
 }

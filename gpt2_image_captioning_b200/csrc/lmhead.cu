@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(256) argmax_partials_kernel(const float* __res
   __shared__ float sv[8];
   __shared__ int si[8];
   const int b = blockIdx.x, part = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
   const int chunk = (V + LMHEAD_F32_PARTS - 1) / LMHEAD_F32_PARTS;
   const int c0 = part * chunk, c1 = min(V, c0 + chunk);
   float v = -INFINITY;
@@ -60,8 +62,7 @@ __global__ void __launch_bounds__(256) argmax_partials_kernel(const float* __res
 
 int launch_argmax_partials(const float* logits, int B, int V, float* part_val, int* part_idx, cudaStream_t st) {
   dim3 grid(B, LMHEAD_F32_PARTS);
-  argmax_partials_kernel<<<grid, 256, 0, st>>>(logits, B, V, part_val, part_idx);
-  GIC_CHECK_CUDA(cudaGetLastError());
+  GIC_CHECK_CUDA(launch_kernel(argmax_partials_kernel, grid, dim3(256), 0, st, logits, B, V, part_val, part_idx));
   note_launch();
   return GIC_OK;
 }
@@ -72,6 +73,8 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
   __shared__ int si[4];
   __shared__ int s_tok;
   const int b = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   const int step = *a.d_step;
   float v = -INFINITY;
   int idx = 0x7fffffff;
@@ -121,8 +124,7 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
 }
 
 int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st) {
-  finalize_token_kernel<<<a.B, 128, 0, st>>>(a);
-  GIC_CHECK_CUDA(cudaGetLastError());
+  GIC_CHECK_CUDA(launch_kernel(finalize_token_kernel, dim3(a.B), dim3(128), 0, st, a));
   note_launch();
   return GIC_OK;
 }

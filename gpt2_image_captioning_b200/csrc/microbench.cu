@@ -26,6 +26,7 @@ static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap); }
 const char* get_error() { return g_err; }
 void note_launch() {}
+bool pdl_enabled() { static int on = -1; if (on < 0) { const char* v = getenv("GIC_NO_PDL"); on = (v && v[0] == '1') ? 0 : 1; } return on == 1; }
 }  // namespace gic
 
 __global__ void empty_kernel() {}

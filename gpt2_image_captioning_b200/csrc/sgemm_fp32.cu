@@ -24,6 +24,8 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int ty = tid / (BN / TN), tx = tid % (BN / TN);
+  pdl_launch_dependents();
+  pdl_wait();
 
   float acc[TM][TN];
 #pragma unroll
@@ -122,12 +124,11 @@ int launch_sgemm_nt(const float* A, int lda, const float* W, const float* bias, 
   const long tiles128 = (long)ceil_div(M, 128) * ceil_div(N, 128);
   if (M <= 64 || tiles128 < 2 * 148) {
     dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
-    sgemm_nt_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(A, lda, W, bias, C, ldc, M, N, K, epilogue);
+    GIC_CHECK_CUDA(launch_kernel(sgemm_nt_kernel<64, 64, 4, 4>, grid, dim3(256), 0, st, A, lda, W, bias, C, ldc, M, N, K, epilogue));
   } else {
     dim3 grid(ceil_div(N, 128), ceil_div(M, 128));
-    sgemm_nt_kernel<128, 128, 8, 8><<<grid, 256, 0, st>>>(A, lda, W, bias, C, ldc, M, N, K, epilogue);
+    GIC_CHECK_CUDA(launch_kernel(sgemm_nt_kernel<128, 128, 8, 8>, grid, dim3(256), 0, st, A, lda, W, bias, C, ldc, M, N, K, epilogue));
   }
-  GIC_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return GIC_OK;
 }
