@@ -19,8 +19,8 @@ namespace gic {
 constexpr int HD = 64;  // GPT-2 head_dim (small/medium/large: n_embd / n_head = 64)
 
 template <typename T>
-__global__ void __launch_bounds__(128) attn_decode_kernel(const T* __restrict__ qkv, T* kcache, T* vcache, ActOut out,
-                                                          const int* __restrict__ d_pos, int rows, int H, int t_max) {
+__global__ void __launch_bounds__(128) attn_decode_kernel(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows,
+                                                          int H, int t_max) {
   constexpr int VEC = 16 / sizeof(T);   // elements per 128-bit load
   constexpr int LPK = HD / VEC;         // lanes per key: 8 (bf16) / 16 (fp32)
   constexpr int KPI = 32 / LPK;         // keys per warp iteration
@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const T* __restrict__ 
   pdl_wait();
   const int row = wid / H, h = wid % H;
   const int d = H * HD;
-  const int pos = *d_pos;  // tokens already cached == position of the new token
+  // (qkv / d_pos are written by the previous kernels: no __restrict__, so their loads are not invariant and stay below pdl_wait)
+  const int pos = __ldcg(d_pos);  // tokens already cached == position of the new token
   const int ctx = pos + 1;
   const int g = lane / LPK, sub = lane % LPK;
   float* sc = smem_scores + (size_t)warp_in_block * t_max;
@@ -152,7 +153,7 @@ template int launch_attn_decode<bf16>(const bf16*, bf16*, bf16*, ActOut, const i
 //   bidirectional          -> transformer-mapper encoder layers
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int HDIM, bool CAUSAL>
-__global__ void __launch_bounds__(128) attn_seq_kernel(const T* __restrict__ qkv, T* kcache, T* vcache, ActOut out, int S, int H,
+__global__ void __launch_bounds__(128) attn_seq_kernel(const T* qkv, T* kcache, T* vcache, ActOut out, int S, int H,
                                                        int t_max, int cache_row_mult, float scale) {
   constexpr int DPL = (HDIM + 31) / 32;  // dims per lane (lanes >= HDIM idle when HDIM < 32)
   extern __shared__ float sm[];

@@ -10,7 +10,7 @@ namespace gic {
 // One warp per row, the row held in registers (d <= 32*MAXV), two-pass mean / variance in fp32.
 // ---------------------------------------------------------------------------------------------------------------
 template <int MAXV>
-__global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict__ x, long x_row_stride, const float* __restrict__ w,
+__global__ void __launch_bounds__(128) layernorm_kernel(const float* x, long x_row_stride, const float* __restrict__ w,
                                                         const float* __restrict__ b, ActOut y, int rows, int d) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* __restrict_
   for (int i = 0; i < MAXV; ++i) {
     const int c = lane + i * 32;
     const bool ok = c < d;
-    v[i] = ok ? __ldg(xr + c) : 0.f;
+    v[i] = ok ? __ldcg(xr + c) : 0.f;  // activation written by the previous kernel: NOT an invariant load (must stay below pdl_wait)
     wv[i] = ok ? __ldg(w + c) : 0.f;
     bv[i] = ok ? __ldg(b + c) : 0.f;
   }

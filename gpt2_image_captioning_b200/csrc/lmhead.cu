@@ -37,8 +37,7 @@ __device__ __forceinline__ void block_argmax(float& v, int& idx, float* sv, int*
 }
 
 // fp32 mode: logits [B,V] were materialised by the CUDA-core GEMM; scan them in LMHEAD_F32_PARTS column slabs per row.
-__global__ void __launch_bounds__(256) argmax_partials_kernel(const float* __restrict__ logits, int B, int V, float* __restrict__ part_val,
-                                                              int* __restrict__ part_idx) {
+__global__ void __launch_bounds__(256) argmax_partials_kernel(const float* logits, int B, int V, float* part_val, int* part_idx) {
   __shared__ float sv[8];
   __shared__ int si[8];
   const int b = blockIdx.x, part = blockIdx.y;
@@ -50,7 +49,7 @@ __global__ void __launch_bounds__(256) argmax_partials_kernel(const float* __res
   int idx = 0x7fffffff;
   const float* row = logits + (size_t)b * V;
   for (int c = c0 + threadIdx.x; c < c1; c += blockDim.x) {
-    const float x = row[c];
+    const float x = __ldcg(row + c);  // produced by the previous kernel (not an invariant load)
     if (better(x, c, v, idx)) { v = x; idx = c; }
   }
   block_argmax(v, idx, sv, si);
@@ -75,12 +74,12 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
   const int b = blockIdx.x;
   pdl_launch_dependents();
   pdl_wait();
-  const int step = *a.d_step;
+  const int step = __ldcg(a.d_step);
   float v = -INFINITY;
   int idx = 0x7fffffff;
   for (int p = threadIdx.x; p < a.n_parts; p += blockDim.x) {
-    const float pv = a.part_val[(size_t)p * a.B + b];
-    const int pi = a.part_idx[(size_t)p * a.B + b];
+    const float pv = __ldcg(a.part_val + (size_t)p * a.B + b);
+    const int pi = __ldcg(a.part_idx + (size_t)p * a.B + b);
     if (better(pv, pi, v, idx)) { v = pv; idx = pi; }
   }
   block_argmax(v, idx, sv, si);

@@ -11,7 +11,7 @@ namespace gic {
 
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
-sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, const float* __restrict__ bias,
+sgemm_nt_kernel(const float* A, int lda, const float* __restrict__ W, const float* __restrict__ bias,
                 float* C, int ldc, int M, int N, int K, int epilogue) {
   constexpr int BK = 16;
   constexpr int NT = (BM / TM) * (BN / TN);
@@ -40,7 +40,8 @@ sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ 
       int i = tid + l * NT;
       int r = i / 4, kq = (i % 4) * 4;
       int gr = m0 + r, gk = k0 + kq;
-      ra[l] = (gr < M && gk < K) ? *reinterpret_cast<const float4*>(A + (size_t)gr * lda + gk) : make_float4(0, 0, 0, 0);
+      // A is an activation produced by the previous kernel: coherent (non-invariant) load, must not be hoisted above pdl_wait
+      ra[l] = (gr < M && gk < K) ? __ldcg(reinterpret_cast<const float4*>(A + (size_t)gr * lda + gk)) : make_float4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int l = 0; l < B_LD; ++l) {
