@@ -9,11 +9,11 @@
 // 129-139) and the tied LM head (HF :705-706) whose epilogue is fused with the greedy argmax (src/models.py:398-443):
 // each CTA reduces its 128 x BLOCK_N logit tile to one (max, lowest index) pair per row, so logits never reach HBM.
 //
-// Kernel shape: one 128 x BLOCK_N output tile per CTA, BLOCK_K = 64 (one 128-byte swizzle atom), STAGES-deep
-// TMA->MMA mbarrier ring.  6 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-// (TMEM lane quarter = warp_id % 4).  Two CTAs fit per SM (<= ~100 KB smem, <= 256 TMEM columns each) so one CTA's
-// epilogue overlaps the other's main loop.  blockIdx.x walks M tiles fastest: CTAs that share a W tile run together and
-// the weight tile is fetched from HBM once and served from L2 to the others.
+// Kernel shape: PERSISTENT, one CTA per SM walking 128 x BLOCK_N output tiles; BLOCK_K = 64 (one 128-byte swizzle atom),
+// a 6..10-stage TMA->MMA mbarrier ring that keeps streaming across tile boundaries, and two TMEM accumulators so the
+// epilogue of tile i overlaps the main loop of tile i+1.  6 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer, warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Tiles are numbered M-fastest: the ~148 tiles in
+// flight share a handful of W tiles, each fetched from HBM once and served from L2 to the other M tiles.
 // BF16X2 ("split") mode: A = A_hi + A_lo, W = W_hi + W_lo (each bf16); three MMAs per k-step
 // (hi.hi + hi.lo + lo.hi) into the same accumulator give ~16 mantissa bits.
 #include <cuda.h>
@@ -33,6 +33,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -146,16 +149,20 @@ struct GemmTile {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int W_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES) * (SPLIT ? 2 : 1);
-  // budget ~100 KB so two CTAs share an SM (non-split); split tiles take one SM each
-  static constexpr int BUDGET = SPLIT ? 196 * 1024 : 100 * 1024;
+  // one persistent CTA per SM: spend (almost) all of its shared memory on the TMA ring.  Measured round 1: with 3-4
+  // stages the main loop ran at ~0.35 us per k-block = (TMA round trip ~1.4 us) / stages, i.e. latency-bound.
+  static constexpr int BUDGET = 200 * 1024;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */ + BLOCK_N * 4 /* bias */;
-  static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int STAGES = STAGES_RAW > 10 ? 10 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 512 /* barriers */ + 2 * BLOCK_N * 4 /* bias */;
+  static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // one accumulator buffer
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;                 // double-buffered: epilogue(i) overlaps main loop(i+1)
 };
 
+// Persistent kernel: grid = min(#tiles, #SMs); CTA c walks tiles c, c + grid, ...  (tile t -> m_tile = t % m_tiles,
+// n_tile = t / m_tiles, so the ~148 tiles in flight share few W tiles and each is fetched from HBM once).
 template <int BLOCK_N, bool SPLIT>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKernelParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKernelParams p) {
   using Tile = GemmTile<BLOCK_N, SPLIT>;
   constexpr int STAGES = Tile::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -163,12 +170,15 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(const _
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Tile::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_bias = reinterpret_cast<float*>(smem + STAGES * Tile::STAGE_BYTES + 256);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * Tile::STAGE_BYTES + 512);  // [2][BLOCK_N]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * GEMM_BLOCK_M, n0 = blockIdx.y * BLOCK_N;
+  const int m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int total_tiles = m_tiles * n_tiles;
   const int nk = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   pdl_launch_dependents();  // let the next kernel's CTAs be scheduled behind this grid (see common.cuh)
 
@@ -183,7 +193,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(const _
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], 4);  // one arrival per epilogue warp
+    }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
   }
@@ -191,53 +204,64 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(const _
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_acc = *tmem_base_slot;
+  const uint32_t tmem_base = *tmem_base_slot;
   pdl_wait();  // prologue above overlapped the previous kernel; its outputs are visible from here on
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: streams k-blocks of successive tiles through the ring without pausing at tile boundaries =====
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* st = smem + s * Tile::STAGE_BYTES;
-        ptx::mbar_expect_tx(&full_bar[s], Tile::STAGE_BYTES);
-        const int k0 = kb * GEMM_BLOCK_K;
-        ptx::tma_load_2d(st, &p.a_hi, &full_bar[s], k0, m0);
-        ptx::tma_load_2d(st + Tile::A_BYTES, &p.w_hi, &full_bar[s], k0, n0);
-        if (SPLIT) {
-          ptx::tma_load_2d(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, &full_bar[s], k0, m0);
-          ptx::tma_load_2d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, &full_bar[s], k0, n0);
+      uint32_t it = 0;  // k-block counter across all tiles of this CTA
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* st = smem + s * Tile::STAGE_BYTES;
+          ptx::mbar_expect_tx(&full_bar[s], Tile::STAGE_BYTES);
+          const int k0 = kb * GEMM_BLOCK_K;
+          ptx::tma_load_2d(st, &p.a_hi, &full_bar[s], k0, m0);
+          ptx::tma_load_2d(st + Tile::A_BYTES, &p.w_hi, &full_bar[s], k0, n0);
+          if (SPLIT) {
+            ptx::tma_load_2d(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, &full_bar[s], k0, m0);
+            ptx::tma_load_2d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, &full_bar[s], k0, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
+    // ===== MMA issuer (single thread), alternating between the two TMEM accumulators =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const uint32_t acc = local & 1, use = local >> 1;
+        ptx::mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);  // epilogue has drained this accumulator (passes at first use)
         ptx::tc_fence_after();
-        const uint32_t sa = ptx::smem_u32(smem + s * Tile::STAGE_BYTES);
-        const uint64_t a_hi = make_smem_desc_sw128(sa);
-        const uint64_t w_hi = make_smem_desc_sw128(sa + Tile::A_BYTES);
-        const uint64_t a_lo = make_smem_desc_sw128(sa + Tile::A_BYTES + Tile::W_BYTES);
-        const uint64_t w_lo = make_smem_desc_sw128(sa + 2 * Tile::A_BYTES + Tile::W_BYTES);
+        const uint32_t tmem_acc = tmem_base + acc * Tile::ACC_COLS;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          ptx::mbar_wait(&full_bar[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t sa = ptx::smem_u32(smem + s * Tile::STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc_sw128(sa);
+          const uint64_t w_hi = make_smem_desc_sw128(sa + Tile::A_BYTES);
+          const uint64_t a_lo = make_smem_desc_sw128(sa + Tile::A_BYTES + Tile::W_BYTES);
+          const uint64_t w_lo = make_smem_desc_sw128(sa + 2 * Tile::A_BYTES + Tile::W_BYTES);
 #pragma unroll
-        for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-          const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);  // advance 32 bytes inside the swizzle atom
-          ptx::umma_bf16(tmem_acc, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
-          if (SPLIT) {
-            ptx::umma_bf16(tmem_acc, a_hi + koff, w_lo + koff, idesc, 1);
-            ptx::umma_bf16(tmem_acc, a_lo + koff, w_hi + koff, idesc, 1);
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);  // advance 32 bytes inside the swizzle atom
+            ptx::umma_bf16(tmem_acc, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
+            if (SPLIT) {
+              ptx::umma_bf16(tmem_acc, a_hi + koff, w_lo + koff, idesc, 1);
+              ptx::umma_bf16(tmem_acc, a_lo + koff, w_hi + koff, idesc, 1);
+            }
           }
+          ptx::umma_commit(&empty_bar[s]);  // smem slot is free once these MMAs have read it
         }
-        ptx::umma_commit(&empty_bar[s]);  // smem slot is free once these MMAs have read it
+        ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
-      ptx::umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
@@ -246,113 +270,127 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(const _
     // stored: output and residual alias (in-place +=), so loads placed after stores would serialise one L2 round trip per
     // float4 (ncu source page, round 1).
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
     const int et = (warp - 2) * 32 + lane;  // 0..127 over the four epilogue warps
-    for (int c = et; c < BLOCK_N; c += 128) s_bias[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
     const bool resid = p.epilogue == EPI_RESIDUAL;
     const bool vec_f32 = (p.ld_f32 % 4 == 0);
-    float4 res_next[8];
-    auto load_res = [&](int c0) {
-      const float* src = p.out_f32 + (size_t)row * p.ld_f32 + n0 + c0;
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const uint32_t acc = local & 1, use = local >> 1;
+      const int n_tile = tile / m_tiles;
+      const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      float* bias_s = s_bias + acc * BLOCK_N;
+      for (int c = et; c < BLOCK_N; c += 128) bias_s[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+      float4 res_next[8];
+      auto load_res = [&](int c0) {
+        const float* src = p.out_f32 + (size_t)row * p.ld_f32 + n0 + c0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(src + 4 * j);
-    };
-    const bool res_vec_ok = resid && row_ok && vec_f32;
-    if (res_vec_ok && n0 + 32 <= p.N) load_res(0);
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
-    float best = -INFINITY;
-    int best_idx = 0x7fffffff;
+        for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(src + 4 * j);
+      };
+      const bool res_vec_ok = resid && row_ok && vec_f32;
+      if (res_vec_ok && n0 + 32 <= p.N) load_res(0);
+      ptx::mbar_wait(&tmem_full_bar[acc], use & 1);
+      ptx::tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * Tile::ACC_COLS;
+      float best = -INFINITY;
+      int best_idx = 0x7fffffff;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      const int col0 = n0 + c0;
-      if (col0 >= p.N) continue;  // warp-uniform
-      const bool full = (col0 + 32 <= p.N);
-      float4 res_cur[8];
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        if (c0 + 32 >= BLOCK_N) {
+          // last TMEM read of this tile: hand the accumulator back to the MMA warp before doing the math / stores
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        const int col0 = n0 + c0;
+        if (col0 >= p.N) continue;  // warp-uniform
+        const bool full = (col0 + 32 <= p.N);
+        float4 res_cur[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) res_cur[j] = res_next[j];
-      if (res_vec_ok && c0 + 32 < BLOCK_N && col0 + 64 <= p.N) load_res(c0 + 32);
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]) + s_bias[c0 + j];
-        if (p.epilogue == EPI_TANH) x = tanhf(x);
-        else if (p.epilogue == EPI_GELU) x = SPLIT ? gelu_tanh(x) : gelu_tanh_fast(x);
-        else if (p.epilogue == EPI_RELU) x = fmaxf(x, 0.f);
-        v[j] = x;
-      }
-      if (p.part_val) {
+        for (int j = 0; j < 8; ++j) res_cur[j] = res_next[j];
+        if (res_vec_ok && c0 + 32 < BLOCK_N && col0 + 64 <= p.N) load_res(c0 + 32);
+        float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col < p.N && v[j] > best) {  // strict > keeps the lowest index among equal maxima
-            best = v[j];
-            best_idx = col;
-          }
+          float x = __uint_as_float(r[j]) + bias_s[c0 + j];
+          if (p.epilogue == EPI_TANH) x = tanhf(x);
+          else if (p.epilogue == EPI_GELU) x = SPLIT ? gelu_tanh(x) : gelu_tanh_fast(x);
+          else if (p.epilogue == EPI_RELU) x = fmaxf(x, 0.f);
+          v[j] = x;
         }
-      }
-      if (!row_ok) continue;
-      if (p.out_f32) {
-        float* dst = p.out_f32 + (size_t)row * p.ld_f32 + col0;
-        if (full && vec_f32) {
+        if (p.part_val) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (resid) { o.x += res_cur[j].x; o.y += res_cur[j].y; o.z += res_cur[j].z; o.w += res_cur[j].w; }
-            *reinterpret_cast<float4*>(dst + 4 * j) = o;
-          }
-        } else {
-          float old[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) old[j] = (resid && col0 + j < p.N) ? dst[j] : 0.f;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) dst[j] = old[j] + v[j];
-        }
-      }
-      if (p.out_hi) {
-        bf16* dh = p.out_hi + (size_t)row * p.ld_bf16 + col0;
-        bf16* dl = p.out_lo ? p.out_lo + (size_t)row * p.ld_bf16 + col0 : nullptr;
-        if (full && (p.ld_bf16 % 8 == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            Vec16<bf16> hv;
-            hv.pack(v + j);
-            hv.store(dh + j);
-            if (dl) {
-              float hf[8], lf[8];
-              hv.unpack(hf);
-#pragma unroll
-              for (int t = 0; t < 8; ++t) lf[t] = v[j + t] - hf[t];
-              Vec16<bf16> lv;
-              lv.pack(lf);
-              lv.store(dl + j);
+          for (int j = 0; j < 32; ++j) {
+            const int col = col0 + j;
+            if (col < p.N && v[j] > best) {  // strict > keeps the lowest index among equal maxima
+              best = v[j];
+              best_idx = col;
             }
           }
-        } else {
+        }
+        if (!row_ok) continue;
+        if (p.out_f32) {
+          float* dst = p.out_f32 + (size_t)row * p.ld_f32 + col0;
+          if (full && vec_f32) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) {
-              const bf16 hb = __float2bfloat16_rn(v[j]);
-              dh[j] = hb;
-              if (dl) dl[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hb));
+            for (int j = 0; j < 8; ++j) {
+              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (resid) { o.x += res_cur[j].x; o.y += res_cur[j].y; o.z += res_cur[j].z; o.w += res_cur[j].w; }
+              *reinterpret_cast<float4*>(dst + 4 * j) = o;
             }
+          } else {
+            float old[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) old[j] = (resid && col0 + j < p.N) ? dst[j] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) dst[j] = old[j] + v[j];
+          }
+        }
+        if (p.out_hi) {
+          bf16* dh = p.out_hi + (size_t)row * p.ld_bf16 + col0;
+          bf16* dl = p.out_lo ? p.out_lo + (size_t)row * p.ld_bf16 + col0 : nullptr;
+          if (full && (p.ld_bf16 % 8 == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              Vec16<bf16> hv;
+              hv.pack(v + j);
+              hv.store(dh + j);
+              if (dl) {
+                float hf[8], lf[8];
+                hv.unpack(hf);
+#pragma unroll
+                for (int t = 0; t < 8; ++t) lf[t] = v[j + t] - hf[t];
+                Vec16<bf16> lv;
+                lv.pack(lf);
+                lv.store(dl + j);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) {
+                const bf16 hb = __float2bfloat16_rn(v[j]);
+                dh[j] = hb;
+                if (dl) dl[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hb));
+              }
+          }
         }
       }
-    }
-    if (p.part_val && row_ok) {
-      p.part_val[(size_t)blockIdx.y * p.M + row] = best;
-      p.part_idx[(size_t)blockIdx.y * p.M + row] = best_idx;
+      if (p.part_val && row_ok) {
+        p.part_val[(size_t)n_tile * p.M + row] = best;
+        p.part_idx[(size_t)n_tile * p.M + row] = best_idx;
+      }
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_acc, Tile::TMEM_COLS);
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Tile::TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -402,6 +440,16 @@ int gemm_bf16_pick_block_n(int M, int N) {
   return 32;
 }
 
+static int gemm_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
 template <int BLOCK_N, bool SPLIT>
 static int configure_cfg() {
   GIC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -427,7 +475,9 @@ template <int BLOCK_N, bool SPLIT>
 static int launch_cfg(const GemmKernelParams& kp, cudaStream_t st) {
   using Tile = GemmTile<BLOCK_N, SPLIT>;
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT>;
-  dim3 grid(ceil_div(kp.M, GEMM_BLOCK_M), ceil_div(kp.N, BLOCK_N));
+  const long tiles = (long)ceil_div(kp.M, GEMM_BLOCK_M) * ceil_div(kp.N, BLOCK_N);
+  const int sms = gemm_num_sms();
+  dim3 grid((unsigned)(tiles < sms ? tiles : sms));  // persistent: one CTA per SM
   GIC_CHECK_CUDA(launch_kernel(kern, grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st, kp));
   note_launch();
   return GIC_OK;
