@@ -23,8 +23,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const T* qkv, T* kcach
                                                           int H, int t_max) {
   constexpr int VEC = 16 / sizeof(T);   // elements per 128-bit load
   constexpr int LPK = HD / VEC;         // lanes per key: 8 (bf16) / 16 (fp32)
-  constexpr int KPI = 32 / LPK;         // keys per warp iteration
-  extern __shared__ float smem_scores[];  // [warps][t_max]
+  constexpr int KPI = 32 / LPK;         // lane groups = keys per warp load instruction
+  constexpr int UNR = 4;                // keys per group per batch -> KPI*UNR keys (K and V) in flight per warp, twice (prefetch)
   const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wid = blockIdx.x * (blockDim.x >> 5) + warp_in_block;
   pdl_launch_dependents();
@@ -34,100 +34,118 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const T* qkv, T* kcach
   const int d = H * HD;
   // (qkv / d_pos are written by the previous kernels: no __restrict__, so their loads are not invariant and stay below pdl_wait)
   const int pos = __ldcg(d_pos);  // tokens already cached == position of the new token
-  const int ctx = pos + 1;
   const int g = lane / LPK, sub = lane % LPK;
-  float* sc = smem_scores + (size_t)warp_in_block * t_max;
+  (void)t_max;
 
   const T* qrow = qkv + (size_t)row * 3 * d + h * HD;
   T* kbase = kcache + ((size_t)row * H + h) * t_max * HD;
   T* vbase = vcache + ((size_t)row * H + h) * t_max * HD;
 
-  // append the new token's K,V (one 16-byte vector per lane of group 0)
+  // Single pass with an online softmax per lane group (flash-decoding style): K and V of a batch of keys are loaded
+  // together and the next batch is requested before the current one is consumed, so a warp keeps 2 x KPI x UNR rows of K
+  // and of V in flight; the KPI groups' partial (max, sum, acc) are merged with shuffles at the end.  The new token's
+  // K/V come straight from the qkv row (and are appended to the cache by group 0) instead of being read back.
+  Vec16<T> qv, knew, vnew;
+  qv.load(qrow + sub * VEC);
+  knew.load(qrow + d + sub * VEC);
+  vnew.load(qrow + 2 * d + sub * VEC);
+  Vec16<T> kn[UNR], vn[UNR];
+  auto request = [&](int j0) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const int j = j0 + u * KPI + g;
+      if (j < pos) {
+        kn[u].load(kbase + (size_t)j * HD + sub * VEC);
+        vn[u].load(vbase + (size_t)j * HD + sub * VEC);
+      }
+    }
+  };
+  request(0);
   if (g == 0) {
-    Vec16<T> kv;
-    kv.load(qrow + d + sub * VEC);
-    kv.store(kbase + (size_t)pos * HD + sub * VEC);
-    kv.load(qrow + 2 * d + sub * VEC);
-    kv.store(vbase + (size_t)pos * HD + sub * VEC);
+    knew.store(kbase + (size_t)pos * HD + sub * VEC);
+    vnew.store(vbase + (size_t)pos * HD + sub * VEC);
   }
   float qf[VEC];
-  {
-    Vec16<T> qv;
-    qv.load(qrow + sub * VEC);
-    qv.unpack(qf);
+  qv.unpack(qf);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) qf[i] *= 0.125f;  // 1/sqrt(64), HF :211-220 (sdpa default scale)
-  }
-  __syncwarp();  // orders the append before the cache reads below (same warp)
+  for (int i = 0; i < VEC; ++i) qf[i] *= 0.125f;  // 1/sqrt(64), HF :211-220 (sdpa default scale)
 
-  // ---- scores ----
-  float mx = -INFINITY;
-  constexpr int UNR = 4;
-  for (int j0 = 0; j0 < ctx; j0 += KPI * UNR) {
-    Vec16<T> kv[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int j = j0 + u * KPI + g;
-      if (j < ctx) kv[u].load(kbase + (size_t)j * HD + sub * VEC);
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int j = j0 + u * KPI + g;
-      float s = 0.f;
-      if (j < ctx) {
-        float kf[VEC];
-        kv[u].unpack(kf);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) s = fmaf(qf[i], kf[i], s);
-      }
-#pragma unroll
-      for (int o = LPK / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (j < ctx) {
-        if (sub == 0) sc[j] = s;
-        mx = fmaxf(mx, s);
-      }
-    }
-  }
-  mx = warp_max(mx);
-  __syncwarp();
-  float sum = 0.f;
-  for (int j = lane; j < ctx; j += 32) {
-    const float p = expf(sc[j] - mx);
-    sc[j] = p;
-    sum += p;
-  }
-  sum = warp_sum(sum);
-  __syncwarp();
-
-  // ---- P.V ----
-  float acc[VEC];
+  float m = -INFINITY, l = 0.f, acc[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-  for (int j0 = 0; j0 < ctx; j0 += KPI * UNR) {
-    Vec16<T> vv[UNR];
+  auto dot_q = [&](const Vec16<T>& kv) {
+    float kf[VEC];
+    kv.unpack(kf);
+    float s = 0.f;
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int j = j0 + u * KPI + g;
-      if (j < ctx) vv[u].load(vbase + (size_t)j * HD + sub * VEC);
-    }
+    for (int i = 0; i < VEC; ++i) s = fmaf(qf[i], kf[i], s);
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const int j = j0 + u * KPI + g;
-      if (j < ctx) {
-        float vf[VEC];
-        vv[u].unpack(vf);
-        const float p = sc[j];
+    for (int o = LPK / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+  };
+  // the new token (position pos) is handled by group 0
+  {
+    const float s = dot_q(knew);  // all lanes participate in the shuffles
+    if (g == 0) {
+      m = s;
+      l = 1.f;
+      float vf[VEC];
+      vnew.unpack(vf);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
-      }
+      for (int i = 0; i < VEC; ++i) acc[i] = vf[i];
     }
   }
+  for (int j0 = 0; j0 < pos; j0 += KPI * UNR) {
+    Vec16<T> kc[UNR], vc[UNR];
 #pragma unroll
-  for (int o = LPK; o < 32; o <<= 1)
+    for (int u = 0; u < UNR; ++u) { kc[u] = kn[u]; vc[u] = vn[u]; }
+    if (j0 + KPI * UNR < pos) request(j0 + KPI * UNR);
+    float sc[UNR];
+    float bm = m;
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    for (int u = 0; u < UNR; ++u) {
+      const bool ok = (j0 + u * KPI + g) < pos;
+      const float s = dot_q(kc[u]);  // shuffles executed by every lane; result ignored where !ok
+      sc[u] = ok ? s : -INFINITY;
+      bm = fmaxf(bm, sc[u]);
+    }
+    if (bm > -INFINITY) {
+      const float scale = (m == -INFINITY) ? 0.f : expf(m - bm);
+      l *= scale;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[i] *= scale;
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (sc[u] > -INFINITY) {
+          const float pr = expf(sc[u] - bm);
+          l += pr;
+          float vf[VEC];
+          vc[u].unpack(vf);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(pr, vf[i], acc[i]);
+        }
+      }
+      m = bm;
+    }
+  }
+  // merge the KPI lane groups
+#pragma unroll
+  for (int o = LPK; o < 32; o <<= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const float ol = __shfl_xor_sync(0xffffffffu, l, o);
+    const float nm = fmaxf(m, om);
+    const float sa = (m == -INFINITY) ? 0.f : expf(m - nm);
+    const float sb = (om == -INFINITY) ? 0.f : expf(om - nm);
+    l = l * sa + ol * sb;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float oa = __shfl_xor_sync(0xffffffffu, acc[i], o);
+      acc[i] = acc[i] * sa + oa * sb;
+    }
+    m = nm;
+  }
   if (g == 0) {
-    const float inv = 1.0f / sum;
+    const float inv = 1.0f / l;
     const size_t o0 = (size_t)row * d + h * HD + sub * VEC;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) out.write(o0 + i, acc[i] * inv);
@@ -138,8 +156,7 @@ template <typename T>
 int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows, int H, int t_max, cudaStream_t st) {
   const int warps = rows * H;
   const int blocks = ceil_div(warps, 4);
-  const size_t smem = (size_t)4 * t_max * sizeof(float);
-  GIC_REQUIRE(smem <= 48 * 1024, "attn_decode: t_max %d too large", t_max);
+  const size_t smem = 0;
   GIC_CHECK_CUDA(launch_kernel(attn_decode_kernel<T>, dim3(blocks), dim3(128), smem, st, qkv, kcache, vcache, out, d_pos, rows, H, t_max));
   note_launch();
   return GIC_OK;

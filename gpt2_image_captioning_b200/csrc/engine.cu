@@ -27,7 +27,8 @@ const char* get_error() { return g_err; }
 // ---------------------------------------------------------------------------------------------------------------
 // packed weights
 // ---------------------------------------------------------------------------------------------------------------
-static const int kBlockNs[3] = {32, 64, 128};
+static const int kBlockNs[5] = {32, 64, 128, 192, 256};
+static int block_n_index(int bn) { for (int i = 0; i < 5; ++i) if (kBlockNs[i] == bn) return i; return 0; }
 
 struct Linear {  // y = x . W^T + b with W packed as [N,K] K-major
   int N = 0, K = 0;
@@ -35,7 +36,7 @@ struct Linear {  // y = x . W^T + b with W packed as [N,K] K-major
   bf16* w_hi = nullptr;
   bf16* w_lo = nullptr;
   float* bias = nullptr;
-  TmaDesc tm_hi[3], tm_lo[3];  // per block_n in kBlockNs
+  TmaDesc tm_hi[5], tm_lo[5];  // per block_n in kBlockNs
 };
 struct Norm { float* w = nullptr; float* b = nullptr; };
 struct GptLayer { Norm ln1, ln2; Linear attn, proj, fc, fc2; };
@@ -170,7 +171,7 @@ static int pack_linear(gic_engine* e, Linear* lin, const float* w, const float* 
   if (bias) GIC_TRY(copy_vec(e, &lin->bias, bias, N, st));
   if (e->tc) {
     GIC_REQUIRE(K % 8 == 0, "tensor-core modes need K (%d) to be a multiple of 8", K);
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 5; ++i) {
       GIC_TRY(make_tma_2d_bf16(&lin->tm_hi[i], lin->w_hi, N, K, K, kBlockNs[i]));
       if (e->split) GIC_TRY(make_tma_2d_bf16(&lin->tm_lo[i], lin->w_lo, N, K, K, kBlockNs[i]));
     }
@@ -274,8 +275,8 @@ static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, i
     return launch_sgemm_nt(A.f32, lin.K, lin.w_f32, lin.bias, out.f32, ld_out, M, lin.N, lin.K, epilogue, st);
   }
   GemmBf16Args g;
-  const int bn = gemm_bf16_pick_block_n(M, lin.N);
-  const int bi = bn == 32 ? 0 : (bn == 64 ? 1 : 2);
+  const int bn = gemm_bf16_pick_block_n(M, lin.N, e->split ? 1 : 0);
+  const int bi = block_n_index(bn);
   GIC_TRY(make_tma_2d_bf16(&g.a_hi, A.hi, M, lin.K, lin.K, 128));
   g.w_hi = lin.tm_hi[bi];
   if (e->split) {
@@ -781,7 +782,7 @@ int gic_test_gemm(int dtype, const float* A, const float* W, const float* bias, 
   int r = launch_convert(A, ao, na, st);
   if (r == GIC_OK) r = launch_convert(W, wo, nw, st);
   GemmBf16Args g;
-  const int bn = gemm_bf16_pick_block_n(M, N);
+  const int bn = gemm_bf16_pick_block_n(M, N, split ? 1 : 0);
   if (r == GIC_OK) r = make_tma_2d_bf16(&g.a_hi, a_hi, M, K, K, 128);
   if (r == GIC_OK) r = make_tma_2d_bf16(&g.w_hi, w_hi, N, K, K, bn);
   if (r == GIC_OK && split) r = make_tma_2d_bf16(&g.a_lo, a_lo, M, K, K, 128);

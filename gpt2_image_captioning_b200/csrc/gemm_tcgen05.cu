@@ -156,7 +156,8 @@ struct GemmTile {
   static constexpr int STAGES = STAGES_RAW > 10 ? 10 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 512 /* barriers */ + 2 * BLOCK_N * 4 /* bias */;
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // one accumulator buffer
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;                 // double-buffered: epilogue(i) overlaps main loop(i+1)
+  static constexpr int TMEM_NEED = 2 * ACC_COLS;                 // double-buffered: epilogue(i) overlaps main loop(i+1)
+  static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;  // power of two
 };
 
 // Persistent kernel: grid = min(#tiles, #SMs); CTA c walks tiles c, c + grid, ...  (tile t -> m_tile = t % m_tiles,
@@ -430,14 +431,26 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t col
   return GIC_OK;
 }
 
-// Tile width.  Measured on B200 (csrc/microbench.cu, M = 1024): the single-wave body GEMMs of a decode step run fastest
-// with 64-wide tiles (qkv 18 us vs 26 us at 128; fc2 29 vs 43), 128-wide tiles win once the grid covers the chip twice
-// (LM head, prefill), 32-wide tiles only help when even 64-wide tiles leave most SMs idle (M <= 128).
-int gemm_bf16_pick_block_n(int M, int N) {
+// Tile width.  Measured on B200 (csrc/microbench.cu): the kernel is bound by how fast one SM can pull operand bytes
+// through its TMA ring (~70 GB/s per SM, ~8 TB/s chip-wide from L2), so the best tile minimises
+// rounds x bytes-per-tile-per-k-block = ceil(tiles / #SMs) x (A 16 KB + W 128 B x BLOCK_N): wide tiles re-read the
+// activation slab less often, narrow ones keep all SMs busy when M is small.
+int gemm_bf16_pick_block_n(int M, int N, int split) {
+  static const int wide[] = {256, 192, 128, 64, 32};
+  static const int narrow[] = {128, 64, 32};  // split (bf16x2) stages carry four operand tiles: keep them <= 128 wide
+  const int* cand = split ? narrow : wide;
+  const int n_cand = split ? 3 : 5;
   const long m_tiles = ceil_div(M, GEMM_BLOCK_M);
-  if (m_tiles * ceil_div(N, 128) >= 2 * 148) return 128;
-  if (m_tiles * ceil_div(N, 64) >= 74) return 64;
-  return 32;
+  const int sms = 148;
+  int best = cand[0];
+  long best_cost = -1;
+  for (int i = 0; i < n_cand; ++i) {
+    const int bn = cand[i];
+    const long tiles = m_tiles * ceil_div(N, bn);
+    const long cost = ((tiles + sms - 1) / sms) * (16384 + 128L * bn);
+    if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
 }
 
 static int gemm_num_sms() {
@@ -464,6 +477,8 @@ int gemm_bf16_configure() {
   GIC_TRY((configure_cfg<32, false>()));
   GIC_TRY((configure_cfg<64, false>()));
   GIC_TRY((configure_cfg<128, false>()));
+  GIC_TRY((configure_cfg<192, false>()));
+  GIC_TRY((configure_cfg<256, false>()));
   GIC_TRY((configure_cfg<32, true>()));
   GIC_TRY((configure_cfg<64, true>()));
   GIC_TRY((configure_cfg<128, true>()));
@@ -503,6 +518,8 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
       case 32: return launch_cfg<32, false>(kp, st);
       case 64: return launch_cfg<64, false>(kp, st);
       case 128: return launch_cfg<128, false>(kp, st);
+      case 192: return launch_cfg<192, false>(kp, st);
+      case 256: return launch_cfg<256, false>(kp, st);
     }
   }
   set_error("gemm_bf16: unsupported block_n %d", a.block_n);

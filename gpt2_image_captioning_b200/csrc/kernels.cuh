@@ -36,7 +36,7 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t col
 struct GemmBf16Args {
   TmaDesc a_hi, w_hi, a_lo, w_lo;  // lo maps used only when split (BF16X2); A box rows = 128, W box rows = block_n
   int M = 0, N = 0, K = 0;
-  int block_n = 128;               // 32 | 64 | 128
+  int block_n = 128;               // 32 | 64 | 128 | 192 | 256 (split: <= 128)
   int split = 0;                   // 0: one MMA per k-step; 1: hi.hi + hi.lo + lo.hi
   int epilogue = EPI_NONE;
   const float* bias = nullptr;     // [N] or null
@@ -46,7 +46,7 @@ struct GemmBf16Args {
   int* part_idx = nullptr;         // ... and its lowest column index (cols >= N masked)
 };
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st);
-int gemm_bf16_pick_block_n(int M, int N);
+int gemm_bf16_pick_block_n(int M, int N, int split);
 int gemm_bf16_configure();  // cudaFuncSetAttribute for every instantiation (call once, outside stream capture)
 
 // ---- elementwise.cu -----------------------------------------------------------------------------------------------
