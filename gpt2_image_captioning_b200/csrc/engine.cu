@@ -103,6 +103,11 @@ struct gic_engine {
   // be captured into a graph); it is forked from / joined to the caller's stream with events
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // decode runs as two half-batches on two streams (captured as two branches of one graph): the HBM-bound attention of
+  // one half overlaps the operand-delivery-bound GEMMs of the other and each fills the other's launch gaps
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int sub_batches = 2;
   // per-kernel-class CUDA-event profiling (bench.py roofline leg); generate runs eagerly while enabled
   bool profiling = false;
   struct ProfRec { const char* cat; cudaEvent_t a, b; };
@@ -258,9 +263,9 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
   w->ids = c.take<int64_t>((size_t)w->rows * (max_new > 0 ? max_new : 1));
   w->finished = c.take<unsigned char>(w->rows);
   w->first_eos = c.take<int>(w->rows);
-  w->d_step = c.take<int>(1);
-  w->d_pos = c.take<int>(1);
-  w->done_counter = c.take<int>(1);
+  w->d_step = c.take<int>(2);  // [sub-batch]
+  w->d_pos = c.take<int>(2);
+  w->done_counter = c.take<int>(2);
   w->bytes = align_up(c.off, 1024) + 1024;
 }
 
@@ -354,6 +359,46 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
 static int decode_step(const gic_engine* e, const Workspace& w, float* logits_tap, cudaStream_t st) {
   for (int l = 0; l < e->L; ++l) GIC_TRY(gpt_layer(e, w, l, w.h_dec, w.rows, false, st));
   return lm_head_and_token(e, w, w.h_dec, e->d, w.rows, logits_tap, st);
+}
+
+// view of rows [row0, row0 + nrows) of a workspace, with its own device-side step / position counters (`sub`)
+static Workspace slice_rows(const gic_engine* e, const Workspace& w, int row0, int nrows, int sub) {
+  Workspace s = w;
+  const size_t d = e->d;
+  auto shift = [&](Act& a, size_t width) {
+    if (a.f32) a.f32 += (size_t)row0 * width;
+    if (a.hi) a.hi += (size_t)row0 * width;
+    if (a.lo) a.lo += (size_t)row0 * width;
+  };
+  s.rows = nrows; s.B = nrows;
+  shift(s.a, d); shift(s.o, d); shift(s.f, 4 * d);
+  if (s.qkv_f32) s.qkv_f32 += (size_t)row0 * 3 * d;
+  if (s.qkv_bf16) s.qkv_bf16 += (size_t)row0 * 3 * d;
+  s.h_dec += (size_t)row0 * d;
+  const size_t kv_row = (size_t)e->H * w.t_max * 64;  // the per-layer plane stride (kv_layer_elems) keeps the full row count
+  if (e->cfg.dtype == GIC_DTYPE_BF16) s.kv = (bf16*)w.kv + (size_t)row0 * kv_row;
+  else s.kv = (float*)w.kv + (size_t)row0 * kv_row;
+  if (s.logits) s.logits += (size_t)row0 * e->V;
+  s.part_val += (size_t)w.n_parts_max * row0;
+  s.part_idx += (size_t)w.n_parts_max * row0;
+  s.ids += (size_t)row0 * w.max_new;
+  s.finished += row0; s.first_eos += row0;
+  s.d_step += sub; s.d_pos += sub; s.done_counter += sub;
+  return s;
+}
+
+// one decode step for every row: two half-batches on two streams when the batch is large enough (see gic_engine)
+static int decode_step_all(gic_engine* e, const Workspace& w, float* logits_tap, cudaStream_t st) {
+  if (e->sub_batches < 2 || w.rows < 512 || logits_tap) return decode_step(e, w, logits_tap, st);
+  const int r0 = ((w.rows / 2 + 127) / 128) * 128;  // first half rounded up to whole 128-row GEMM tiles
+  const Workspace a = slice_rows(e, w, 0, r0, 0), b = slice_rows(e, w, r0, w.rows - r0, 1);
+  GIC_CHECK_CUDA(cudaEventRecord(e->ev_fork, st));
+  GIC_CHECK_CUDA(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+  GIC_TRY(decode_step(e, a, nullptr, st));
+  GIC_TRY(decode_step(e, b, nullptr, e->stream2));
+  GIC_CHECK_CUDA(cudaEventRecord(e->ev_join, e->stream2));
+  GIC_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
+  return GIC_OK;
 }
 
 // mapping network: image embeddings [B,E] -> prefix tokens fp32 [B,P_img,d] in w.prefix
@@ -467,9 +512,14 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
     if (r == GIC_OK) r = gic::gemm_bf16_configure();
     if (r != GIC_OK) { delete e; return r; }
   }
+  const char* sb = getenv("GIC_SUBBATCH");
+  if (sb && sb[0] == '1') e->sub_batches = 1;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     gic::set_error("could not create the engine stream / events: %s", cudaGetErrorString(cudaGetLastError()));
     delete e;
     return GIC_ERR_CUDA;
@@ -485,6 +535,9 @@ int gic_engine_destroy(gic_engine* e) {
   for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->stream2) cudaStreamDestroy(e->stream2);
   if (e->stream) cudaStreamDestroy(e->stream);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
@@ -621,14 +674,14 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   const bool graph_ok = e->use_graph && !e->profiling && logits_out == nullptr && steps >= 2;
   if (!graph_ok) {
     for (int s = 1; s <= steps; ++s)
-      GIC_TRY(decode_step(e, w, logits_out ? logits_out + (size_t)s * B * e->V : nullptr, st));
+      GIC_TRY(decode_step_all(e, w, logits_out ? logits_out + (size_t)s * B * e->V : nullptr, st));
   } else {
     if (!(e->graph_exec && e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new)) {
       if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
       cudaGraph_t graph = nullptr;
       const unsigned long long before = g_launches;
       GIC_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      int r = decode_step(e, w, nullptr, st);
+      int r = decode_step_all(e, w, nullptr, st);
       cudaError_t ce = cudaStreamEndCapture(st, &graph);
       e->graph_nodes = (int)(g_launches - before);  // captured, not executed
       g_launches = before;
