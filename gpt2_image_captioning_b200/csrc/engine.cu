@@ -27,8 +27,9 @@ const char* get_error() { return g_err; }
 // ---------------------------------------------------------------------------------------------------------------
 // packed weights
 // ---------------------------------------------------------------------------------------------------------------
-static const int kBlockNs[5] = {32, 64, 128, 192, 256};
-static int block_n_index(int bn) { for (int i = 0; i < 5; ++i) if (kBlockNs[i] == bn) return i; return 0; }
+// W tensor maps are keyed by their box height = block_n / cluster_m (rows of the W tile one CTA fetches per k-block)
+static const int kBoxRows[10] = {8, 16, 24, 32, 48, 64, 96, 128, 192, 256};
+static int box_rows_index(int rows) { for (int i = 0; i < 10; ++i) if (kBoxRows[i] == rows) return i; return -1; }
 
 struct Linear {  // y = x . W^T + b with W packed as [N,K] K-major
   int N = 0, K = 0;
@@ -36,7 +37,7 @@ struct Linear {  // y = x . W^T + b with W packed as [N,K] K-major
   bf16* w_hi = nullptr;
   bf16* w_lo = nullptr;
   float* bias = nullptr;
-  TmaDesc tm_hi[5], tm_lo[5];  // per block_n in kBlockNs
+  TmaDesc tm_hi[10], tm_lo[10];  // per box height in kBoxRows
 };
 struct Norm { float* w = nullptr; float* b = nullptr; };
 struct GptLayer { Norm ln1, ln2; Linear attn, proj, fc, fc2; };
@@ -107,7 +108,7 @@ struct gic_engine {
   // one half overlaps the operand-delivery-bound GEMMs of the other and each fills the other's launch gaps
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int sub_batches = 2;
+  int sub_batches = 1;  // measured round 1: 2 is ~5 % slower (persistent GEMM CTAs own their SMs); GIC_SUBBATCH=2 enables
   // per-kernel-class CUDA-event profiling (bench.py roofline leg); generate runs eagerly while enabled
   bool profiling = false;
   struct ProfRec { const char* cat; cudaEvent_t a, b; };
@@ -176,9 +177,9 @@ static int pack_linear(gic_engine* e, Linear* lin, const float* w, const float* 
   if (bias) GIC_TRY(copy_vec(e, &lin->bias, bias, N, st));
   if (e->tc) {
     GIC_REQUIRE(K % 8 == 0, "tensor-core modes need K (%d) to be a multiple of 8", K);
-    for (int i = 0; i < 5; ++i) {
-      GIC_TRY(make_tma_2d_bf16(&lin->tm_hi[i], lin->w_hi, N, K, K, kBlockNs[i]));
-      if (e->split) GIC_TRY(make_tma_2d_bf16(&lin->tm_lo[i], lin->w_lo, N, K, K, kBlockNs[i]));
+    for (int i = 0; i < 10; ++i) {
+      GIC_TRY(make_tma_2d_bf16(&lin->tm_hi[i], lin->w_hi, N, K, K, kBoxRows[i]));
+      if (e->split) GIC_TRY(make_tma_2d_bf16(&lin->tm_lo[i], lin->w_lo, N, K, K, kBoxRows[i]));
     }
   }
   return GIC_OK;
@@ -281,7 +282,10 @@ static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, i
   }
   GemmBf16Args g;
   const int bn = gemm_bf16_pick_block_n(M, lin.N, e->split ? 1 : 0);
-  const int bi = block_n_index(bn);
+  const int cs = gemm_bf16_pick_cluster(M, bn);
+  const int bi = box_rows_index(bn / cs);
+  GIC_REQUIRE(bi >= 0, "no W tensor map for box height %d", bn / cs);
+  g.cluster_m = cs;
   GIC_TRY(make_tma_2d_bf16(&g.a_hi, A.hi, M, lin.K, lin.K, 128));
   g.w_hi = lin.tm_hi[bi];
   if (e->split) {
@@ -513,7 +517,7 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
     if (r != GIC_OK) { delete e; return r; }
   }
   const char* sb = getenv("GIC_SUBBATCH");
-  if (sb && sb[0] == '1') e->sub_batches = 1;
+  if (sb && sb[0] == '2') e->sub_batches = 2;
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
@@ -836,10 +840,12 @@ int gic_test_gemm(int dtype, const float* A, const float* W, const float* bias, 
   if (r == GIC_OK) r = launch_convert(W, wo, nw, st);
   GemmBf16Args g;
   const int bn = gemm_bf16_pick_block_n(M, N, split ? 1 : 0);
+  const int cs = gemm_bf16_pick_cluster(M, bn);
+  g.cluster_m = cs;
   if (r == GIC_OK) r = make_tma_2d_bf16(&g.a_hi, a_hi, M, K, K, 128);
-  if (r == GIC_OK) r = make_tma_2d_bf16(&g.w_hi, w_hi, N, K, K, bn);
+  if (r == GIC_OK) r = make_tma_2d_bf16(&g.w_hi, w_hi, N, K, K, bn / cs);
   if (r == GIC_OK && split) r = make_tma_2d_bf16(&g.a_lo, a_lo, M, K, K, 128);
-  if (r == GIC_OK && split) r = make_tma_2d_bf16(&g.w_lo, w_lo, N, K, K, bn);
+  if (r == GIC_OK && split) r = make_tma_2d_bf16(&g.w_lo, w_lo, N, K, K, bn / cs);
   g.M = M; g.N = N; g.K = K; g.block_n = bn; g.split = split; g.epilogue = epilogue; g.bias = bias;
   g.out.f32 = C; g.ld_out = N;
   if (r == GIC_OK) r = launch_gemm_bf16(g, st);

@@ -63,6 +63,23 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// same load, delivered to the same smem offset (and signalling the same mbarrier offset) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
@@ -91,6 +108,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 // arrive on an mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// the same arrive delivered to the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets row (lane base + i)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
@@ -134,6 +157,7 @@ struct alignas(64) GemmKernelParams {
   TmaDesc a_hi, w_hi, a_lo, w_lo;
   int M, N, K;
   int epilogue;
+  int cluster_m;  // CTAs per cluster (1, 2, 4, 8): consecutive M tiles of one N tile; the W tile is TMA-multicast among them
   const float* bias;
   float* out_f32; int ld_f32;
   bf16* out_hi; bf16* out_lo; int ld_bf16;
@@ -179,8 +203,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int total_tiles = m_tiles * n_tiles;
   const int nk = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  // Work item = (group of CS consecutive M tiles, one N tile), numbered M-group-fastest; cluster c walks items c, c + #clusters, ..
+  // and the CTA of rank r takes M tile group*CS + r.  All CS CTAs need the same W tile: each fetches 1/CS of its rows and
+  // TMA-multicasts them to the whole cluster, so a weight byte crosses the L2 fabric once per cluster instead of once per
+  // M tile (round 1: the decode GEMMs were bound by delivering the weight tile 8x, once to each of the 8 M tiles).
+  const int CS = p.cluster_m;
+  const uint32_t rank = CS > 1 ? ptx::cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << CS) - 1);
+  const int m_groups = (m_tiles + CS - 1) / CS;
+  const int total_items = m_groups * n_tiles;
+  const int item0 = blockIdx.x / CS, item_stride = gridDim.x / CS;
+  constexpr int W_ROW_BYTES = GEMM_BLOCK_K * 2;
+  const int w_slice_rows = BLOCK_N / CS;
   pdl_launch_dependents();  // let the next kernel's CTAs be scheduled behind this grid (see common.cuh)
 
   if (warp == 0 && lane == 0) {
@@ -192,7 +227,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     }
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], CS);  // a slot is reusable once every CTA of the cluster has consumed it (peers write into it)
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
@@ -204,6 +239,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   if (warp == 1) ptx::tmem_alloc(tmem_base_slot, Tile::TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
+  if (CS > 1) ptx::cluster_sync_all();  // every CTA's barriers exist before a peer multicasts into / arrives on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
   pdl_wait();  // prologue above overlapped the previous kernel; its outputs are visible from here on
@@ -212,20 +248,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     // ===== TMA producer: streams k-blocks of successive tiles through the ring without pausing at tile boundaries =====
     if (lane == 0) {
       uint32_t it = 0;  // k-block counter across all tiles of this CTA
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
+      for (int item = item0; item < total_items; item += item_stride) {
+        const int m0 = ((item % m_groups) * CS + (int)rank) * GEMM_BLOCK_M, n0 = (item / m_groups) * BLOCK_N;
+        const int wn0 = n0 + (int)rank * w_slice_rows;                       // my slice of the W tile's rows
+        const int w_off = (int)rank * w_slice_rows * W_ROW_BYTES;
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = smem + s * Tile::STAGE_BYTES;
-          ptx::mbar_expect_tx(&full_bar[s], Tile::STAGE_BYTES);
+          ptx::mbar_expect_tx(&full_bar[s], Tile::STAGE_BYTES);  // own A + the whole W tile (arriving from CS sources)
           const int k0 = kb * GEMM_BLOCK_K;
           ptx::tma_load_2d(st, &p.a_hi, &full_bar[s], k0, m0);
-          ptx::tma_load_2d(st + Tile::A_BYTES, &p.w_hi, &full_bar[s], k0, n0);
+          if (CS == 1) ptx::tma_load_2d(st + Tile::A_BYTES, &p.w_hi, &full_bar[s], k0, n0);
+          else ptx::tma_load_2d_multicast(st + Tile::A_BYTES + w_off, &p.w_hi, &full_bar[s], k0, wn0, cmask);
           if (SPLIT) {
             ptx::tma_load_2d(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, &full_bar[s], k0, m0);
-            ptx::tma_load_2d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, &full_bar[s], k0, n0);
+            if (CS == 1) ptx::tma_load_2d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, &full_bar[s], k0, n0);
+            else ptx::tma_load_2d_multicast(st + 2 * Tile::A_BYTES + Tile::W_BYTES + w_off, &p.w_lo, &full_bar[s], k0, wn0, cmask);
           }
         }
       }
@@ -235,7 +275,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
       uint32_t it = 0, local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      for (int item = item0; item < total_items; item += item_stride, ++local) {
         const uint32_t acc = local & 1, use = local >> 1;
         ptx::mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);  // epilogue has drained this accumulator (passes at first use)
         ptx::tc_fence_after();
@@ -259,7 +299,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
               ptx::umma_bf16(tmem_acc, a_lo + koff, w_hi + koff, idesc, 1);
             }
           }
-          ptx::umma_commit(&empty_bar[s]);  // smem slot is free once these MMAs have read it
+          // the smem slot is free once these MMAs have read it -- tell every CTA that multicasts into it
+          if (CS == 1) ptx::umma_commit(&empty_bar[s]);
+          else ptx::umma_commit_multicast(&empty_bar[s], cmask);
         }
         ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
@@ -275,10 +317,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     const bool resid = p.epilogue == EPI_RESIDUAL;
     const bool vec_f32 = (p.ld_f32 % 4 == 0);
     uint32_t local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int item = item0; item < total_items; item += item_stride, ++local) {
       const uint32_t acc = local & 1, use = local >> 1;
-      const int n_tile = tile / m_tiles;
-      const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
+      const int n_tile = item / m_groups;
+      const int m0 = ((item % m_groups) * CS + (int)rank) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       float* bias_s = s_bias + acc * BLOCK_N;
@@ -391,6 +433,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CS > 1) ptx::cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or signal its barriers
   if (warp == 1) ptx::tmem_dealloc(tmem_base, Tile::TMEM_COLS);
 }
 
@@ -490,12 +533,55 @@ template <int BLOCK_N, bool SPLIT>
 static int launch_cfg(const GemmKernelParams& kp, cudaStream_t st) {
   using Tile = GemmTile<BLOCK_N, SPLIT>;
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT>;
-  const long tiles = (long)ceil_div(kp.M, GEMM_BLOCK_M) * ceil_div(kp.N, BLOCK_N);
-  const int sms = gemm_num_sms();
-  dim3 grid((unsigned)(tiles < sms ? tiles : sms));  // persistent: one CTA per SM
-  GIC_CHECK_CUDA(launch_kernel(kern, grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st, kp));
+  const int CS = kp.cluster_m;
+  const int m_tiles = ceil_div(kp.M, GEMM_BLOCK_M), n_tiles = ceil_div(kp.N, BLOCK_N);
+  const long items = (long)ceil_div(m_tiles, CS) * n_tiles;
+  // persistent: as many clusters as can be co-resident (a cluster of CS CTAs needs CS free SMs inside one GPC)
+  static int max_clusters[9] = {0};
+  if (max_clusters[CS] == 0) {
+    int n = 0;
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(CS * 64); q.blockDim = dim3(GEMM_THREADS); q.dynamicSmemBytes = Tile::SMEM_BYTES;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = CS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    q.attrs = qa; q.numAttrs = 1;
+    if (CS == 1 || cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) { cudaGetLastError(); n = gemm_num_sms() / CS; }
+    max_clusters[CS] = n;
+  }
+  const long clusters = items < max_clusters[CS] ? items : max_clusters[CS];
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CS));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Tile::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (CS > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CS; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  GIC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
   note_launch();
   return GIC_OK;
+}
+
+// CTAs per cluster for an M x N problem: the largest power of two <= min(GIC_CLUSTER (default 4), #M tiles) whose W
+// slice is still a whole number of 8-row swizzle atoms
+int gemm_bf16_pick_cluster(int M, int block_n) {
+  static int limit = 0;
+  if (limit == 0) { const char* v = getenv("GIC_CLUSTER"); limit = v ? atoi(v) : 4; if (limit < 1) limit = 1; if (limit > 8) limit = 8; }
+  const int m_tiles = ceil_div(M, GEMM_BLOCK_M);
+  int cs = 1;
+  while (cs * 2 <= limit && cs * 2 <= m_tiles && (block_n / (cs * 2)) % 8 == 0 && block_n % (cs * 2) == 0) cs *= 2;
+  return cs;
 }
 
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
@@ -504,6 +590,10 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   GemmKernelParams kp;
   kp.a_hi = a.a_hi; kp.w_hi = a.w_hi; kp.a_lo = a.a_lo; kp.w_lo = a.w_lo;
   kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.epilogue = a.epilogue; kp.bias = a.bias;
+  kp.cluster_m = a.cluster_m < 1 ? 1 : a.cluster_m;
+  GIC_REQUIRE(kp.cluster_m == 1 || kp.cluster_m == 2 || kp.cluster_m == 4 || kp.cluster_m == 8, "gemm_bf16: cluster_m %d", kp.cluster_m);
+  GIC_REQUIRE(a.block_n % kp.cluster_m == 0 && (a.block_n / kp.cluster_m) % 8 == 0, "gemm_bf16: block_n %d not divisible into %d 8-row slices",
+              a.block_n, kp.cluster_m);
   kp.out_f32 = a.out.f32; kp.ld_f32 = a.ld_out; kp.out_hi = a.out.hi; kp.out_lo = a.out.lo; kp.ld_bf16 = a.ld_out;
   kp.part_val = a.part_val; kp.part_idx = a.part_idx;
   GIC_REQUIRE(!(a.epilogue == EPI_RESIDUAL && !a.out.f32), "gemm_bf16: residual epilogue needs the fp32 output");

@@ -38,6 +38,7 @@ struct GemmBf16Args {
   int M = 0, N = 0, K = 0;
   int block_n = 128;               // 32 | 64 | 128 | 192 | 256 (split: <= 128)
   int split = 0;                   // 0: one MMA per k-step; 1: hi.hi + hi.lo + lo.hi
+  int cluster_m = 1;               // CTAs per cluster sharing one W tile by TMA multicast; the W maps' box rows = block_n / cluster_m
   int epilogue = EPI_NONE;
   const float* bias = nullptr;     // [N] or null
   ActOut out;                      // fp32 (EPI_RESIDUAL: in-place +=) and/or bf16 hi/lo, row stride ld_out
@@ -47,6 +48,7 @@ struct GemmBf16Args {
 };
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st);
 int gemm_bf16_pick_block_n(int M, int N, int split);
+int gemm_bf16_pick_cluster(int M, int block_n);
 int gemm_bf16_configure();  // cudaFuncSetAttribute for every instantiation (call once, outside stream capture)
 
 // ---- elementwise.cu -----------------------------------------------------------------------------------------------
