@@ -27,9 +27,9 @@ const char* get_error() { return g_err; }
 // ---------------------------------------------------------------------------------------------------------------
 // packed weights
 // ---------------------------------------------------------------------------------------------------------------
-// W tensor maps are keyed by their box height = block_n / cluster_m (rows of the W tile one CTA fetches per k-block)
-static const int kBoxRows[10] = {8, 16, 24, 32, 48, 64, 96, 128, 192, 256};
-static int box_rows_index(int rows) { for (int i = 0; i < 10; ++i) if (kBoxRows[i] == rows) return i; return -1; }
+// W tensor maps are keyed by their box height = block_n
+static const int kBoxRows[5] = {32, 64, 128, 192, 256};
+static int box_rows_index(int rows) { for (int i = 0; i < 5; ++i) if (kBoxRows[i] == rows) return i; return -1; }
 
 struct Linear {  // y = x . W^T + b with W packed as [N,K] K-major
   int N = 0, K = 0;
@@ -37,7 +37,7 @@ struct Linear {  // y = x . W^T + b with W packed as [N,K] K-major
   bf16* w_hi = nullptr;
   bf16* w_lo = nullptr;
   float* bias = nullptr;
-  TmaDesc tm_hi[10], tm_lo[10];  // per box height in kBoxRows
+  TmaDesc tm_hi[5], tm_lo[5];  // per box height in kBoxRows
 };
 struct Norm { float* w = nullptr; float* b = nullptr; };
 struct GptLayer { Norm ln1, ln2; Linear attn, proj, fc, fc2; };
@@ -176,8 +176,8 @@ static int pack_linear(gic_engine* e, Linear* lin, const float* w, const float* 
   GIC_TRY(launch_pack_weight(w, R, C, transpose, out, st));
   if (bias) GIC_TRY(copy_vec(e, &lin->bias, bias, N, st));
   if (e->tc) {
-    GIC_REQUIRE(K % 8 == 0, "tensor-core modes need K (%d) to be a multiple of 8", K);
-    for (int i = 0; i < 10; ++i) {
+    GIC_REQUIRE(K % 64 == 0, "tensor-core modes need K (%d) to be a multiple of 64", K);
+    for (int i = 0; i < 5; ++i) {
       GIC_TRY(make_tma_2d_bf16(&lin->tm_hi[i], lin->w_hi, N, K, K, kBoxRows[i]));
       if (e->split) GIC_TRY(make_tma_2d_bf16(&lin->tm_lo[i], lin->w_lo, N, K, K, kBoxRows[i]));
     }
@@ -282,10 +282,8 @@ static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, i
   }
   GemmBf16Args g;
   const int bn = gemm_bf16_pick_block_n(M, lin.N, e->split ? 1 : 0);
-  const int cs = gemm_bf16_pick_cluster(M, bn);
-  const int bi = box_rows_index(bn / cs);
-  GIC_REQUIRE(bi >= 0, "no W tensor map for box height %d", bn / cs);
-  g.cluster_m = cs;
+  const int bi = box_rows_index(bn);
+  GIC_REQUIRE(bi >= 0, "no W tensor map for box height %d", bn);
   GIC_TRY(make_tma_2d_bf16(&g.a_hi, A.hi, M, lin.K, lin.K, 128));
   g.w_hi = lin.tm_hi[bi];
   if (e->split) {
@@ -840,12 +838,10 @@ int gic_test_gemm(int dtype, const float* A, const float* W, const float* bias, 
   if (r == GIC_OK) r = launch_convert(W, wo, nw, st);
   GemmBf16Args g;
   const int bn = gemm_bf16_pick_block_n(M, N, split ? 1 : 0);
-  const int cs = gemm_bf16_pick_cluster(M, bn);
-  g.cluster_m = cs;
   if (r == GIC_OK) r = make_tma_2d_bf16(&g.a_hi, a_hi, M, K, K, 128);
-  if (r == GIC_OK) r = make_tma_2d_bf16(&g.w_hi, w_hi, N, K, K, bn / cs);
+  if (r == GIC_OK) r = make_tma_2d_bf16(&g.w_hi, w_hi, N, K, K, bn);
   if (r == GIC_OK && split) r = make_tma_2d_bf16(&g.a_lo, a_lo, M, K, K, 128);
-  if (r == GIC_OK && split) r = make_tma_2d_bf16(&g.w_lo, w_lo, N, K, K, bn / cs);
+  if (r == GIC_OK && split) r = make_tma_2d_bf16(&g.w_lo, w_lo, N, K, K, bn);
   g.M = M; g.N = N; g.K = K; g.block_n = bn; g.split = split; g.epilogue = epilogue; g.bias = bias;
   g.out.f32 = C; g.ld_out = N;
   if (r == GIC_OK) r = launch_gemm_bf16(g, st);

@@ -63,22 +63,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// same load, delivered to the same smem offset (and signalling the same mbarrier offset) in every CTA of `mask`
-__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, uint16_t mask) {
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
@@ -108,12 +97,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 // arrive on an mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// the same arrive delivered to the mbarrier at this offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"(mask)
-               : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets row (lane base + i)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
@@ -157,7 +140,6 @@ struct alignas(64) GemmKernelParams {
   TmaDesc a_hi, w_hi, a_lo, w_lo;
   int M, N, K;
   int epilogue;
-  int cluster_m;  // CTAs per cluster (1, 2, 4, 8): consecutive M tiles of one N tile; the W tile is TMA-multicast among them
   const float* bias;
   float* out_f32; int ld_f32;
   bf16* out_hi; bf16* out_lo; int ld_bf16;
@@ -165,19 +147,23 @@ struct alignas(64) GemmKernelParams {
 };
 
 constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_BLOCK_K = 64;
+constexpr int GEMM_BLOCK_K = 128;  // two 128-byte swizzle atoms per stage, each operand fetched by ONE 3-D TMA
+constexpr int GEMM_ATOM_K = 64;    // elements per swizzle atom row
 constexpr int GEMM_THREADS = 192;
 
 template <int BLOCK_N, bool SPLIT>
 struct GemmTile {
-  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
-  static constexpr int W_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // [2 atoms][128 rows][128 B]
+  static constexpr int W_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;       // [2 atoms][BLOCK_N rows][128 B]
   static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES) * (SPLIT ? 2 : 1);
-  // one persistent CTA per SM: spend (almost) all of its shared memory on the TMA ring.  Measured round 1: with 3-4
-  // stages the main loop ran at ~0.35 us per k-block = (TMA round trip ~1.4 us) / stages, i.e. latency-bound.
+  // one persistent CTA per SM: spend (almost) all of its shared memory on the TMA ring.  Measured round 1
+  // (microbench tma_probe): the single-thread producer loop costs ~520 cycles per stage (mbarrier wait + expect_tx + two
+  // TMA issues) whatever the stage size -- a 64-wide k-block capped the feed at 123 GB/s per SM and the GEMMs ran at ~1050
+  // cycles per k-block, 4x the MMA time; 128-wide k-blocks fetched by one 3-D TMA per operand halve the per-byte overhead.
   static constexpr int BUDGET = 200 * 1024;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 10 ? 10 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static_assert(STAGES * STAGE_BYTES + 4096 <= 227 * 1024, "tile does not fit in shared memory");
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 512 /* barriers */ + 2 * BLOCK_N * 4 /* bias */;
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // one accumulator buffer
   static constexpr int TMEM_NEED = 2 * ACC_COLS;                 // double-buffered: epilogue(i) overlaps main loop(i+1)
@@ -203,19 +189,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int total_tiles = m_tiles * n_tiles;
   const int nk = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
-  // Work item = (group of CS consecutive M tiles, one N tile), numbered M-group-fastest; cluster c walks items c, c + #clusters, ..
-  // and the CTA of rank r takes M tile group*CS + r.  All CS CTAs need the same W tile: each fetches 1/CS of its rows and
-  // TMA-multicasts them to the whole cluster, so a weight byte crosses the L2 fabric once per cluster instead of once per
-  // M tile (round 1: the decode GEMMs were bound by delivering the weight tile 8x, once to each of the 8 M tiles).
-  const int CS = p.cluster_m;
-  const uint32_t rank = CS > 1 ? ptx::cluster_ctarank() : 0;
-  const uint16_t cmask = (uint16_t)((1u << CS) - 1);
-  const int m_groups = (m_tiles + CS - 1) / CS;
-  const int total_items = m_groups * n_tiles;
-  const int item0 = blockIdx.x / CS, item_stride = gridDim.x / CS;
-  constexpr int W_ROW_BYTES = GEMM_BLOCK_K * 2;
-  const int w_slice_rows = BLOCK_N / CS;
   pdl_launch_dependents();  // let the next kernel's CTAs be scheduled behind this grid (see common.cuh)
 
   if (warp == 0 && lane == 0) {
@@ -227,7 +202,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     }
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], CS);  // a slot is reusable once every CTA of the cluster has consumed it (peers write into it)
+      ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
@@ -239,7 +214,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   if (warp == 1) ptx::tmem_alloc(tmem_base_slot, Tile::TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
-  if (CS > 1) ptx::cluster_sync_all();  // every CTA's barriers exist before a peer multicasts into / arrives on them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
   pdl_wait();  // prologue above overlapped the previous kernel; its outputs are visible from here on
@@ -248,24 +222,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     // ===== TMA producer: streams k-blocks of successive tiles through the ring without pausing at tile boundaries =====
     if (lane == 0) {
       uint32_t it = 0;  // k-block counter across all tiles of this CTA
-      for (int item = item0; item < total_items; item += item_stride) {
-        const int m0 = ((item % m_groups) * CS + (int)rank) * GEMM_BLOCK_M, n0 = (item / m_groups) * BLOCK_N;
-        const int wn0 = n0 + (int)rank * w_slice_rows;                       // my slice of the W tile's rows
-        const int w_off = (int)rank * w_slice_rows * W_ROW_BYTES;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* st = smem + s * Tile::STAGE_BYTES;
-          ptx::mbar_expect_tx(&full_bar[s], Tile::STAGE_BYTES);  // own A + the whole W tile (arriving from CS sources)
-          const int k0 = kb * GEMM_BLOCK_K;
-          ptx::tma_load_2d(st, &p.a_hi, &full_bar[s], k0, m0);
-          if (CS == 1) ptx::tma_load_2d(st + Tile::A_BYTES, &p.w_hi, &full_bar[s], k0, n0);
-          else ptx::tma_load_2d_multicast(st + Tile::A_BYTES + w_off, &p.w_hi, &full_bar[s], k0, wn0, cmask);
+          ptx::mbar_expect_tx(&full_bar[s], Tile::STAGE_BYTES);
+          const int ka = kb * (GEMM_BLOCK_K / GEMM_ATOM_K);  // first swizzle atom of this k-block (3rd tensor-map coordinate)
+          ptx::tma_load_3d(st, &p.a_hi, &full_bar[s], 0, m0, ka);
+          ptx::tma_load_3d(st + Tile::A_BYTES, &p.w_hi, &full_bar[s], 0, n0, ka);
           if (SPLIT) {
-            ptx::tma_load_2d(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, &full_bar[s], k0, m0);
-            if (CS == 1) ptx::tma_load_2d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, &full_bar[s], k0, n0);
-            else ptx::tma_load_2d_multicast(st + 2 * Tile::A_BYTES + Tile::W_BYTES + w_off, &p.w_lo, &full_bar[s], k0, wn0, cmask);
+            ptx::tma_load_3d(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, &full_bar[s], 0, m0, ka);
+            ptx::tma_load_3d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, &full_bar[s], 0, n0, ka);
           }
         }
       }
@@ -275,7 +245,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
       uint32_t it = 0, local = 0;
-      for (int item = item0; item < total_items; item += item_stride, ++local) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
         const uint32_t acc = local & 1, use = local >> 1;
         ptx::mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);  // epilogue has drained this accumulator (passes at first use)
         ptx::tc_fence_after();
@@ -292,16 +262,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           const uint64_t w_lo = make_smem_desc_sw128(sa + 2 * Tile::A_BYTES + Tile::W_BYTES);
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-            const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);  // advance 32 bytes inside the swizzle atom
-            ptx::umma_bf16(tmem_acc, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
+            // k-step inside the stage: atom (k / 4) is a whole [rows][128 B] tile further on, then 32 bytes per step inside it
+            constexpr uint64_t A_ATOM = (uint64_t)(GEMM_BLOCK_M * 128) >> 4, W_ATOM = (uint64_t)(BLOCK_N * 128) >> 4;
+            const uint64_t ka = (uint64_t)(k / 4), ki = (uint64_t)(((k % 4) * 16 * 2) >> 4);
+            const uint64_t aoff = ka * A_ATOM + ki, woff = ka * W_ATOM + ki;
+            ptx::umma_bf16(tmem_acc, a_hi + aoff, w_hi + woff, idesc, (kb | k) != 0);
             if (SPLIT) {
-              ptx::umma_bf16(tmem_acc, a_hi + koff, w_lo + koff, idesc, 1);
-              ptx::umma_bf16(tmem_acc, a_lo + koff, w_hi + koff, idesc, 1);
+              ptx::umma_bf16(tmem_acc, a_hi + aoff, w_lo + woff, idesc, 1);
+              ptx::umma_bf16(tmem_acc, a_lo + aoff, w_hi + woff, idesc, 1);
             }
           }
-          // the smem slot is free once these MMAs have read it -- tell every CTA that multicasts into it
-          if (CS == 1) ptx::umma_commit(&empty_bar[s]);
-          else ptx::umma_commit_multicast(&empty_bar[s], cmask);
+          ptx::umma_commit(&empty_bar[s]);  // smem slot is free once these MMAs have read it
         }
         ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
@@ -317,10 +288,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     const bool resid = p.epilogue == EPI_RESIDUAL;
     const bool vec_f32 = (p.ld_f32 % 4 == 0);
     uint32_t local = 0;
-    for (int item = item0; item < total_items; item += item_stride, ++local) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const uint32_t acc = local & 1, use = local >> 1;
-      const int n_tile = item / m_groups;
-      const int m0 = ((item % m_groups) * CS + (int)rank) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
+      const int n_tile = tile / m_tiles;
+      const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       float* bias_s = s_bias + acc * BLOCK_N;
@@ -433,7 +404,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (CS > 1) ptx::cluster_sync_all();  // no CTA leaves while a peer may still multicast into it or signal its barriers
   if (warp == 1) ptx::tmem_dealloc(tmem_base, Tile::TMEM_COLS);
 }
 
@@ -455,6 +425,9 @@ int tma_init() {
   return GIC_OK;
 }
 
+// bf16 row-major [rows, cols] viewed as [cols/64 atoms][rows][64] so that ONE box of (64 x box_rows x 2 atoms) lands in
+// shared memory as two consecutive 128B-swizzled K-major tiles -- exactly the layout the UMMA descriptors walk.
+// Out-of-bounds rows / atoms are zero-filled.  Requires cols % 8 == 0; a partial last atom is zero-filled by the box bounds.
 int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows) {
   GIC_TRY(tma_init());
   static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap size");
@@ -462,11 +435,12 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t col
               "TMA: base must be 16-byte aligned and the row stride a multiple of 8 elements (stride %llu)",
               (unsigned long long)row_stride_elems);
   GIC_REQUIRE(box_rows >= 1 && box_rows <= 256, "TMA: box rows %u out of range", box_rows);
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {row_stride_elems * 2};
-  cuuint32_t box[2] = {(cuuint32_t)GEMM_BLOCK_K, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+  GIC_REQUIRE(cols % GEMM_ATOM_K == 0, "tensor-core GEMM operands need K (%llu) to be a multiple of %d", (unsigned long long)cols, GEMM_ATOM_K);
+  cuuint64_t gdim[3] = {(cuuint64_t)GEMM_ATOM_K, rows, cols / GEMM_ATOM_K};
+  cuuint64_t gstride[2] = {row_stride_elems * 2, (cuuint64_t)GEMM_ATOM_K * 2};
+  cuuint32_t box[3] = {(cuuint32_t)GEMM_ATOM_K, box_rows, (cuuint32_t)(GEMM_BLOCK_K / GEMM_ATOM_K)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GIC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box_rows=%u)", (int)r,
@@ -480,9 +454,9 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t col
 // activation slab less often, narrow ones keep all SMs busy when M is small.
 int gemm_bf16_pick_block_n(int M, int N, int split) {
   static const int wide[] = {256, 192, 128, 64, 32};
-  static const int narrow[] = {128, 64, 32};  // split (bf16x2) stages carry four operand tiles: keep them <= 128 wide
+  static const int narrow[] = {64, 32};  // split (bf16x2) stages carry four operand tiles: two 96 KB stages at 64 wide
   const int* cand = split ? narrow : wide;
-  const int n_cand = split ? 3 : 5;
+  const int n_cand = split ? 2 : 5;
   const long m_tiles = ceil_div(M, GEMM_BLOCK_M);
   const int sms = 148;
   int best = cand[0];
@@ -490,7 +464,7 @@ int gemm_bf16_pick_block_n(int M, int N, int split) {
   for (int i = 0; i < n_cand; ++i) {
     const int bn = cand[i];
     const long tiles = m_tiles * ceil_div(N, bn);
-    const long cost = ((tiles + sms - 1) / sms) * (16384 + 128L * bn);
+    const long cost = ((tiles + sms - 1) / sms) * (16384 + 128L * bn);  // relative operand bytes per k-block
     if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
   }
   return best;
@@ -524,7 +498,6 @@ int gemm_bf16_configure() {
   GIC_TRY((configure_cfg<256, false>()));
   GIC_TRY((configure_cfg<32, true>()));
   GIC_TRY((configure_cfg<64, true>()));
-  GIC_TRY((configure_cfg<128, true>()));
   done = true;
   return GIC_OK;
 }
@@ -533,67 +506,20 @@ template <int BLOCK_N, bool SPLIT>
 static int launch_cfg(const GemmKernelParams& kp, cudaStream_t st) {
   using Tile = GemmTile<BLOCK_N, SPLIT>;
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT>;
-  const int CS = kp.cluster_m;
-  const int m_tiles = ceil_div(kp.M, GEMM_BLOCK_M), n_tiles = ceil_div(kp.N, BLOCK_N);
-  const long items = (long)ceil_div(m_tiles, CS) * n_tiles;
-  // persistent: as many clusters as can be co-resident (a cluster of CS CTAs needs CS free SMs inside one GPC)
-  static int max_clusters[9] = {0};
-  if (max_clusters[CS] == 0) {
-    int n = 0;
-    cudaLaunchConfig_t q = {};
-    q.gridDim = dim3(CS * 64); q.blockDim = dim3(GEMM_THREADS); q.dynamicSmemBytes = Tile::SMEM_BYTES;
-    cudaLaunchAttribute qa[1];
-    qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = CS; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-    q.attrs = qa; q.numAttrs = 1;
-    if (CS == 1 || cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) { cudaGetLastError(); n = gemm_num_sms() / CS; }
-    max_clusters[CS] = n;
-  }
-  const long clusters = items < max_clusters[CS] ? items : max_clusters[CS];
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)(clusters * CS));
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = Tile::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  int na = 0;
-  if (pdl_enabled()) {
-    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
-  if (CS > 1) {
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = CS; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
-    ++na;
-  }
-  cfg.attrs = attr;
-  cfg.numAttrs = na;
-  GIC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
+  const long tiles = (long)ceil_div(kp.M, GEMM_BLOCK_M) * ceil_div(kp.N, BLOCK_N);
+  const int sms = gemm_num_sms();
+  dim3 grid((unsigned)(tiles < sms ? tiles : sms));  // persistent: one CTA per SM
+  GIC_CHECK_CUDA(launch_kernel(kern, grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st, kp));
   note_launch();
   return GIC_OK;
 }
 
-// CTAs per cluster for an M x N problem: the largest power of two <= min(GIC_CLUSTER (default 4), #M tiles) whose W
-// slice is still a whole number of 8-row swizzle atoms
-int gemm_bf16_pick_cluster(int M, int block_n) {
-  static int limit = 0;
-  if (limit == 0) { const char* v = getenv("GIC_CLUSTER"); limit = v ? atoi(v) : 4; if (limit < 1) limit = 1; if (limit > 8) limit = 8; }
-  const int m_tiles = ceil_div(M, GEMM_BLOCK_M);
-  int cs = 1;
-  while (cs * 2 <= limit && cs * 2 <= m_tiles && (block_n / (cs * 2)) % 8 == 0 && block_n % (cs * 2) == 0) cs *= 2;
-  return cs;
-}
-
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   GIC_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm_bf16: empty problem");
-  GIC_REQUIRE(a.K % 8 == 0, "gemm_bf16: K (%d) must be a multiple of 8", a.K);
+  GIC_REQUIRE(a.K % GEMM_ATOM_K == 0, "gemm_bf16: K (%d) must be a multiple of %d", a.K, GEMM_ATOM_K);
   GemmKernelParams kp;
   kp.a_hi = a.a_hi; kp.w_hi = a.w_hi; kp.a_lo = a.a_lo; kp.w_lo = a.w_lo;
   kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.epilogue = a.epilogue; kp.bias = a.bias;
-  kp.cluster_m = a.cluster_m < 1 ? 1 : a.cluster_m;
-  GIC_REQUIRE(kp.cluster_m == 1 || kp.cluster_m == 2 || kp.cluster_m == 4 || kp.cluster_m == 8, "gemm_bf16: cluster_m %d", kp.cluster_m);
-  GIC_REQUIRE(a.block_n % kp.cluster_m == 0 && (a.block_n / kp.cluster_m) % 8 == 0, "gemm_bf16: block_n %d not divisible into %d 8-row slices",
-              a.block_n, kp.cluster_m);
   kp.out_f32 = a.out.f32; kp.ld_f32 = a.ld_out; kp.out_hi = a.out.hi; kp.out_lo = a.out.lo; kp.ld_bf16 = a.ld_out;
   kp.part_val = a.part_val; kp.part_idx = a.part_idx;
   GIC_REQUIRE(!(a.epilogue == EPI_RESIDUAL && !a.out.f32), "gemm_bf16: residual epilogue needs the fp32 output");
@@ -601,7 +527,6 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
     switch (a.block_n) {
       case 32: return launch_cfg<32, true>(kp, st);
       case 64: return launch_cfg<64, true>(kp, st);
-      case 128: return launch_cfg<128, true>(kp, st);
     }
   } else {
     switch (a.block_n) {

@@ -30,7 +30,7 @@ int launch_sgemm_nt(const float* A, int lda, const float* W, const float* bias, 
 // ---- gemm_tcgen05.cu : bf16 tcgen05/TMEM GEMM fed by TMA ----------------------------------------------------
 struct alignas(64) TmaDesc { unsigned char bytes[128]; };  // CUtensorMap
 int tma_init();  // resolves cuTensorMapEncodeTiled through the runtime
-// 2-D bf16 row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128B swizzle, out-of-bounds -> zero
+// bf16 row-major [rows, cols] operand map: one box = [2 swizzle atoms][box_rows][64 cols], 128B swizzle, out-of-bounds -> zero
 int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows);
 
 struct GemmBf16Args {
@@ -38,7 +38,6 @@ struct GemmBf16Args {
   int M = 0, N = 0, K = 0;
   int block_n = 128;               // 32 | 64 | 128 | 192 | 256 (split: <= 128)
   int split = 0;                   // 0: one MMA per k-step; 1: hi.hi + hi.lo + lo.hi
-  int cluster_m = 1;               // CTAs per cluster sharing one W tile by TMA multicast; the W maps' box rows = block_n / cluster_m
   int epilogue = EPI_NONE;
   const float* bias = nullptr;     // [N] or null
   ActOut out;                      // fp32 (EPI_RESIDUAL: in-place +=) and/or bf16 hi/lo, row stride ld_out
@@ -48,7 +47,7 @@ struct GemmBf16Args {
 };
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st);
 int gemm_bf16_pick_block_n(int M, int N, int split);
-int gemm_bf16_pick_cluster(int M, int block_n);
+
 int gemm_bf16_configure();  // cudaFuncSetAttribute for every instantiation (call once, outside stream capture)
 
 // ---- elementwise.cu -----------------------------------------------------------------------------------------------

@@ -127,28 +127,27 @@ int main(int argc, char** argv) {
   Shape shapes[] = {{"qkv", 3 * d, d, &w_qkv, EPI_NONE, false}, {"proj", d, d, &w_proj, EPI_RESIDUAL, true},
                     {"fc", 4 * d, d, &w_fc, EPI_GELU, false}, {"fc2", d, 4 * d, &w_fc2, EPI_RESIDUAL, true}};
   for (auto& s : shapes) {
-    for (int bn : {64, 128, 192, 256}) for (int cs : {1, 2, 4, 8}) {
-      if ((bn / cs) % 8 != 0 || cs > (B + 127) / 128) continue;
+    for (int bn : {64, 128, 192, 256}) {
       std::vector<GemmBf16Args> args(SETS);
       for (int i = 0; i < SETS; ++i) {
         GemmBf16Args& g = args[i];
         OK(make_tma_2d_bf16(&g.a_hi, a, B, s.K, s.K, 128));
-        OK(make_tma_2d_bf16(&g.w_hi, (*s.w)[i], s.N, s.K, s.K, bn / cs));
-        g.M = B; g.N = s.N; g.K = s.K; g.block_n = bn; g.cluster_m = cs; g.epilogue = s.epi; g.bias = bias; g.ld_out = s.N;
+        OK(make_tma_2d_bf16(&g.w_hi, (*s.w)[i], s.N, s.K, s.K, bn));
+        g.M = B; g.N = s.N; g.K = s.K; g.block_n = bn; g.epilogue = s.epi; g.bias = bias; g.ld_out = s.N;
         if (s.res) g.out.f32 = h; else g.out.hi = (s.N == 3 * d ? qkv : o);
       }
       float us = time_loop(st, 240, [&](int i) { OK(launch_gemm_bf16(args[i % SETS], st)); });
-      printf("gemm %-4s M=%d N=%d K=%d block_n=%3d cluster=%d: %7.2f us  %6.1f TFLOP/s  (picked %d/%d)\n", s.name, B, s.N, s.K, bn, cs, us,
-             2.0 * B * s.N * s.K / us * 1e-6, gemm_bf16_pick_block_n(B, s.N, 0), gemm_bf16_pick_cluster(B, gemm_bf16_pick_block_n(B, s.N, 0)));
+      printf("gemm %-4s M=%d N=%d K=%d block_n=%3d: %7.2f us  %6.1f TFLOP/s  (picked %d)\n", s.name, B, s.N, s.K, bn, us,
+             2.0 * B * s.N * s.K / us * 1e-6, gemm_bf16_pick_block_n(B, s.N, 0));
     }
   }
-  for (int bn : {128, 256}) for (int cs : {1, 2, 4, 8}) {
+  for (int bn : {128, 192, 256}) {
     GemmBf16Args g;
     OK(make_tma_2d_bf16(&g.a_hi, a, B, d, d, 128));
-    OK(make_tma_2d_bf16(&g.w_hi, wte, V, d, d, bn / cs));
-    g.M = B; g.N = V; g.K = d; g.block_n = bn; g.cluster_m = cs; g.part_val = pv; g.part_idx = pi;
+    OK(make_tma_2d_bf16(&g.w_hi, wte, V, d, d, bn));
+    g.M = B; g.N = V; g.K = d; g.block_n = bn; g.part_val = pv; g.part_idx = pi;
     float us = time_loop(st, 50, [&](int) { OK(launch_gemm_bf16(g, st)); });
-    printf("lm_head M=%d N=%d K=%d block_n=%d cluster=%d: %.2f us  %.1f TFLOP/s\n", B, V, d, bn, cs, us, 2.0 * B * V * d / us * 1e-6);
+    printf("lm_head M=%d N=%d K=%d block_n=%d: %.2f us  %.1f TFLOP/s\n", B, V, d, bn, us, 2.0 * B * V * d / us * 1e-6);
   }
   // ---- decode attention ----
   for (int ctx : {11, 25, 39}) {
