@@ -140,6 +140,7 @@ struct alignas(64) GemmKernelParams {
   TmaDesc a_hi, w_hi, a_lo, w_lo;
   int M, N, K;
   int epilogue;
+  int mma_repeat;  // 1; > 1 only in the microbenchmark probe: re-issue each k-block's MMAs to measure the tensor-pipe rate
   const float* bias;
   float* out_f32; int ld_f32;
   bf16* out_hi; bf16* out_lo; int ld_bf16;
@@ -260,13 +261,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           const uint64_t w_hi = make_smem_desc_sw128(sa + Tile::A_BYTES);
           const uint64_t a_lo = make_smem_desc_sw128(sa + Tile::A_BYTES + Tile::W_BYTES);
           const uint64_t w_lo = make_smem_desc_sw128(sa + 2 * Tile::A_BYTES + Tile::W_BYTES);
+          for (int rep = 0; rep < p.mma_repeat; ++rep)
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             // k-step inside the stage: atom (k / 4) is a whole [rows][128 B] tile further on, then 32 bytes per step inside it
             constexpr uint64_t A_ATOM = (uint64_t)(GEMM_BLOCK_M * 128) >> 4, W_ATOM = (uint64_t)(BLOCK_N * 128) >> 4;
             const uint64_t ka = (uint64_t)(k / 4), ki = (uint64_t)(((k % 4) * 16 * 2) >> 4);
             const uint64_t aoff = ka * A_ATOM + ki, woff = ka * W_ATOM + ki;
-            ptx::umma_bf16(tmem_acc, a_hi + aoff, w_hi + woff, idesc, (kb | k) != 0);
+            ptx::umma_bf16(tmem_acc, a_hi + aoff, w_hi + woff, idesc, (kb | k | rep) != 0);
             if (SPLIT) {
               ptx::umma_bf16(tmem_acc, a_hi + aoff, w_lo + woff, idesc, 1);
               ptx::umma_bf16(tmem_acc, a_lo + aoff, w_hi + woff, idesc, 1);
@@ -520,6 +522,7 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   GemmKernelParams kp;
   kp.a_hi = a.a_hi; kp.w_hi = a.w_hi; kp.a_lo = a.a_lo; kp.w_lo = a.w_lo;
   kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.epilogue = a.epilogue; kp.bias = a.bias;
+  kp.mma_repeat = a.mma_repeat < 1 ? 1 : a.mma_repeat;
   kp.out_f32 = a.out.f32; kp.ld_f32 = a.ld_out; kp.out_hi = a.out.hi; kp.out_lo = a.out.lo; kp.ld_bf16 = a.ld_out;
   kp.part_val = a.part_val; kp.part_idx = a.part_idx;
   GIC_REQUIRE(!(a.epilogue == EPI_RESIDUAL && !a.out.f32), "gemm_bf16: residual epilogue needs the fp32 output");

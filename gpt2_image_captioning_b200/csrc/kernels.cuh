@@ -39,6 +39,7 @@ struct GemmBf16Args {
   int block_n = 128;               // 32 | 64 | 128 | 192 | 256 (split: <= 128)
   int split = 0;                   // 0: one MMA per k-step; 1: hi.hi + hi.lo + lo.hi
   int epilogue = EPI_NONE;
+  int mma_repeat = 1;              // microbenchmark probe only (re-issues every MMA this many times)
   const float* bias = nullptr;     // [N] or null
   ActOut out;                      // fp32 (EPI_RESIDUAL: in-place +=) and/or bf16 hi/lo, row stride ld_out
   int ld_out = 0;

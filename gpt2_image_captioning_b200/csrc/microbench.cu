@@ -114,6 +114,44 @@ int main(int argc, char** argv) {
   float* pv = (float*)dmalloc((size_t)2048 * B * 4); int* pi = (int*)dmalloc((size_t)2048 * B * 4);
   OK(tma_init()); OK(gemm_bf16_configure());
 
+  // ---- tensor-pipe probe: the LM-head GEMM with every MMA re-issued R times (no extra operand traffic) ----
+  if (argc > 2 && atoi(argv[2]) == 2) {
+    for (int bn : {64, 128, 256}) {
+      float base = 0;
+      for (int rep : {1, 3, 5}) {
+        GemmBf16Args g;
+        OK(make_tma_2d_bf16(&g.a_hi, a, B, d, d, 128));
+        OK(make_tma_2d_bf16(&g.w_hi, wte, V, d, d, bn));
+        g.M = B; g.N = V; g.K = d; g.block_n = bn; g.part_val = pv; g.part_idx = pi; g.mma_repeat = rep;
+        float us = time_loop(st, 20, [&](int) { OK(launch_gemm_bf16(g, st)); });
+        if (rep == 1) base = us;
+        const double tiles_per_cta = (double)((B + 127) / 128) * ((V + bn - 1) / bn) / 148.0;
+        const double mmas_per_cta = tiles_per_cta * (d / 16);
+        printf("mma_probe block_n=%3d repeat=%d: %8.2f us", bn, rep, us);
+        if (rep > 1) printf("   -> %.0f cycles per extra 128x%dx16 MMA (floor %d)", (us - base) * 1965.0 / ((rep - 1) * mmas_per_cta), bn, bn / 2);
+        printf("\n");
+      }
+    }
+    return 0;
+  }
+
+  // ---- epilogue elimination: LM-head shape with (a) no outputs at all, (b) argmax partials, (c) bf16 logits stored ----
+  if (argc > 2 && atoi(argv[2]) == 3) {
+    bf16* big = (bf16*)dmalloc((size_t)B * V * 2 + 1024);
+    for (int bn : {128, 256}) for (int mode = 0; mode < 3; ++mode) {
+      GemmBf16Args g;
+      OK(make_tma_2d_bf16(&g.a_hi, a, B, d, d, 128));
+      OK(make_tma_2d_bf16(&g.w_hi, wte, V, d, d, bn));
+      g.M = B; g.N = V; g.K = d; g.block_n = bn;
+      if (mode == 1) { g.part_val = pv; g.part_idx = pi; }
+      if (mode == 2) { g.out.hi = big; g.ld_out = V; }
+      float us = time_loop(st, 20, [&](int) { OK(launch_gemm_bf16(g, st)); });
+      printf("epi_probe block_n=%3d %-14s: %8.2f us  %.1f TFLOP/s\n", bn, mode == 0 ? "no output" : mode == 1 ? "argmax" : "bf16 stores", us,
+             2.0 * B * V * d / us * 1e-6);
+    }
+    return 0;
+  }
+
   // ---- layernorm ----
   for (int rows : {32, 256, B, 4 * B}) {
     float* hh = (float*)dmalloc((size_t)rows * d * 4);
