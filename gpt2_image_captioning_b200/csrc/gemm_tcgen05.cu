@@ -145,6 +145,7 @@ struct alignas(64) GemmKernelParams {
   float* out_f32; int ld_f32;
   bf16* out_hi; bf16* out_lo; int ld_bf16;
   float* part_val; int* part_idx;
+  long long* trace;  // null; microbenchmark only: clock64 timeline of CTA 0's producer / MMA / epilogue threads
 };
 
 constexpr int GEMM_BLOCK_M = 128;
@@ -193,6 +194,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   const int total_tiles = m_tiles * n_tiles;
   const int nk = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   pdl_launch_dependents();  // let the next kernel's CTAs be scheduled behind this grid (see common.cuh)
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  const long long t_start = tracing ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.a_hi);
@@ -217,6 +220,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (tracing && threadIdx.x == 0) p.trace[600] = clock64() - t_start;  // prologue done
   pdl_wait();  // prologue above overlapped the previous kernel; its outputs are visible from here on
 
   if (warp == 0) {
@@ -228,7 +232,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
+          if (tracing && it < 60) p.trace[it * 4 + 0] = clock64() - t_start;
           ptx::mbar_wait(&empty_bar[s], ph ^ 1);
+          if (tracing && it < 60) p.trace[it * 4 + 1] = clock64() - t_start;
           uint8_t* st = smem + s * Tile::STAGE_BYTES;
           ptx::mbar_expect_tx(&full_bar[s], Tile::STAGE_BYTES);
           const int ka = kb * (GEMM_BLOCK_K / GEMM_ATOM_K);  // first swizzle atom of this k-block (3rd tensor-map coordinate)
@@ -238,6 +244,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             ptx::tma_load_3d(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, &full_bar[s], 0, m0, ka);
             ptx::tma_load_3d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, &full_bar[s], 0, n0, ka);
           }
+          if (tracing && it < 60) p.trace[it * 4 + 2] = clock64() - t_start;
         }
       }
     }
@@ -254,7 +261,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         for (int kb = 0; kb < nk; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
+          if (tracing && it < 60) p.trace[256 + it * 4 + 0] = clock64() - t_start;
           ptx::mbar_wait(&full_bar[s], ph);
+          if (tracing && it < 60) p.trace[256 + it * 4 + 1] = clock64() - t_start;
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + s * Tile::STAGE_BYTES);
           const uint64_t a_hi = make_smem_desc_sw128(sa);
@@ -275,6 +284,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             }
           }
           ptx::umma_commit(&empty_bar[s]);  // smem slot is free once these MMAs have read it
+          if (tracing && it < 60) p.trace[256 + it * 4 + 2] = clock64() - t_start;
         }
         ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
@@ -307,7 +317,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
       };
       const bool res_vec_ok = resid && row_ok && vec_f32;
       if (res_vec_ok && n0 + 32 <= p.N) load_res(0);
+      if (tracing && et == 0 && local < 8) p.trace[512 + local * 4 + 0] = clock64() - t_start;
       ptx::mbar_wait(&tmem_full_bar[acc], use & 1);
+      if (tracing && et == 0 && local < 8) p.trace[512 + local * 4 + 1] = clock64() - t_start;
       ptx::tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * Tile::ACC_COLS;
       float best = -INFINITY;
@@ -401,6 +413,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         p.part_val[(size_t)n_tile * p.M + row] = best;
         p.part_idx[(size_t)n_tile * p.M + row] = best_idx;
       }
+      if (tracing && et == 0 && local < 8) p.trace[512 + local * 4 + 2] = clock64() - t_start;
     }
   }
 
@@ -524,7 +537,7 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.epilogue = a.epilogue; kp.bias = a.bias;
   kp.mma_repeat = a.mma_repeat < 1 ? 1 : a.mma_repeat;
   kp.out_f32 = a.out.f32; kp.ld_f32 = a.ld_out; kp.out_hi = a.out.hi; kp.out_lo = a.out.lo; kp.ld_bf16 = a.ld_out;
-  kp.part_val = a.part_val; kp.part_idx = a.part_idx;
+  kp.part_val = a.part_val; kp.part_idx = a.part_idx; kp.trace = a.trace;
   GIC_REQUIRE(!(a.epilogue == EPI_RESIDUAL && !a.out.f32), "gemm_bf16: residual epilogue needs the fp32 output");
   if (a.split) {
     switch (a.block_n) {

@@ -45,6 +45,7 @@ struct GemmBf16Args {
   int ld_out = 0;
   float* part_val = nullptr;       // fused LM-head argmax: [n_tiles][M] best value ...
   int* part_idx = nullptr;         // ... and its lowest column index (cols >= N masked)
+  long long* trace = nullptr;      // microbenchmark only: device buffer of >= 640 int64 for CTA 0's clock64 timeline
 };
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st);
 int gemm_bf16_pick_block_n(int M, int N, int split);

@@ -152,6 +152,35 @@ int main(int argc, char** argv) {
     return 0;
   }
 
+  // ---- main-loop timeline of CTA 0 (clock64 deltas from kernel entry) ----
+  if (argc > 2 && atoi(argv[2]) == 4) {
+    long long* tr = (long long*)dmalloc(640 * 8);
+    struct Shape { const char* name; bf16* A; bf16* W; int N, K, bn; bool lm; };
+    Shape shapes[] = {{"qkv", a, w_qkv[0], 3 * d, d, 128, false}, {"fc2", a, w_fc2[0], d, 4 * d, 64, false}, {"lm_head", a, wte, V, d, 128, true}};
+    for (const Shape& sh : shapes) {
+      GemmBf16Args g;
+      OK(make_tma_2d_bf16(&g.a_hi, sh.A, B, sh.K, sh.K, 128));
+      OK(make_tma_2d_bf16(&g.w_hi, sh.W, sh.N, sh.K, sh.K, sh.bn));
+      g.M = B; g.N = sh.N; g.K = sh.K; g.block_n = sh.bn; g.bias = bias;
+      if (sh.lm) { g.part_val = pv; g.part_idx = pi; g.bias = nullptr; } else { g.out.hi = o; g.ld_out = sh.N; }
+      for (int i = 0; i < 3; ++i) OK(launch_gemm_bf16(g, st));
+      CK(cudaMemsetAsync(tr, 0, 640 * 8, st));
+      g.trace = tr;
+      OK(launch_gemm_bf16(g, st));
+      long long h_tr[640];
+      CK(cudaMemcpyAsync(h_tr, tr, sizeof(h_tr), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+      printf("timeline %s (N=%d K=%d block_n=%d): prologue done at %lld cycles\n", sh.name, sh.N, sh.K, sh.bn, h_tr[600]);
+      printf("  kb | producer: wait_begin empty_seen issued | mma: wait_begin full_seen committed\n");
+      const int nkb = sh.K / 128 * (sh.lm ? 3 : 1);
+      for (int kb = 0; kb < nkb && kb < 60; ++kb)
+        printf("  %2d | %8lld %8lld %8lld | %8lld %8lld %8lld\n", kb, h_tr[kb * 4], h_tr[kb * 4 + 1], h_tr[kb * 4 + 2], h_tr[256 + kb * 4],
+               h_tr[256 + kb * 4 + 1], h_tr[256 + kb * 4 + 2]);
+      for (int t = 0; t < (sh.lm ? 3 : 1); ++t)
+        printf("  epilogue tile %d: wait_begin %lld  accumulator_seen %lld  done %lld\n", t, h_tr[512 + t * 4], h_tr[512 + t * 4 + 1], h_tr[512 + t * 4 + 2]);
+    }
+    return 0;
+  }
+
   // ---- layernorm ----
   for (int rows : {32, 256, B, 4 * B}) {
     float* hh = (float*)dmalloc((size_t)rows * d * 4);

@@ -78,25 +78,26 @@ __global__ void __launch_bounds__(64, 1) tma_stream_probe(const __grid_constant_
   __syncthreads();
   const int row_blocks = p.rows_total / p.box_rows;  // boxes along the row axis
   if (warp == 0 && lane == 0) {
-    // box index walks (row block, k-block) like a GEMM operand stream: 6 k-blocks per row block
-    long box = p.shared_source ? (long)blockIdx.x * 131 : (long)blockIdx.x * p.iters * p.tmas_per_stage;  // shared: staggered start over the same L2-resident rows
+    // box index walks (row block, k-block) like a GEMM operand stream: 6 k-blocks per row block.  All indices advance
+    // incrementally: an integer division in this loop would cost more than the TMA issue it is trying to measure.
+    int kb = 0, rb = p.shared_source ? (int)((blockIdx.x * 7) % row_blocks) : (int)(((long)blockIdx.x * p.iters * p.tmas_per_stage / 6) % row_blocks);
+    int s = 0; uint32_t ph = 0;
     for (int it = 0; it < p.iters; ++it) {
-      const int s = it % p.stages;
-      const uint32_t ph = (it / p.stages) & 1;
       mbar_wait(&empty_bar[s], ph ^ 1);
       mbar_expect_tx(&full_bar[s], stage_bytes);
-      for (int t = 0; t < p.tmas_per_stage; ++t, ++box) {
-        const int kb = (int)(box % 6), rb = (int)((box / 6) % row_blocks);
+      for (int t = 0; t < p.tmas_per_stage; ++t) {
         tma_load_3d(smem + (size_t)s * stage_bytes + (size_t)t * p.box_rows * 256, &p.map, &full_bar[s], 0, rb * p.box_rows, kb * 2);
+        if (++kb == 6) { kb = 0; if (++rb == row_blocks) rb = 0; }
       }
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1 && lane == 0) {
     const long long c0 = clock64();
+    int s = 0; uint32_t ph = 0;
     for (int it = 0; it < p.iters; ++it) {
-      const int s = it % p.stages;
-      const uint32_t ph = (it / p.stages) & 1;
       mbar_wait(&full_bar[s], ph);
       mbar_arrive(&empty_bar[s]);
+      if (++s == p.stages) { s = 0; ph ^= 1; }
     }
     p.cycles[blockIdx.x] = clock64() - c0;
   }

@@ -31,9 +31,9 @@ if has full; then
   # 11 layers, then capture the last layer (7 launches) + ln_f + LM head + finalize of that step
   SKIP=${NCU_SKIP:-}
   if [ -z "$SKIP" ]; then SKIP=$(python - <<'PY'
-# matching launches before the last layer of decode step 1: prefill (12 layers x 6 matching [ln,gemm,gemm,ln,gemm,gemm] + ln_f,
+# matching launches before the last layer of decode step 1: mapper (2 GEMMs) + prefill (12 layers x 6 matching [ln,gemm,gemm,ln,gemm,gemm] + ln_f,
 # lm head, finalize = 75) + 11 decode layers x 7
-print(75 + 11 * 7)
+print(2 + 75 + 11 * 7)
 PY
 ); fi
   timeout 300 python tools/profile_step.py --max-length 6 > $OUT/${TAG}_plain2.log 2>&1 &&

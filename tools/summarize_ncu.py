@@ -78,7 +78,7 @@ WANT = collections.OrderedDict([
     ("gpu__time_duration.sum", "dur_us"),
     ("dram__bytes_read.sum", "dram_rd_MB"),
     ("dram__bytes_write.sum", "dram_wr_MB"),
-    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
+    ("dram__bytes.sum.per_second", "dram_GBps"),
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
     ("l1tex__m_xbar2l1tex_read_bytes.sum", "l2_to_sm_MB"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor_pct"),
@@ -88,7 +88,7 @@ WANT = collections.OrderedDict([
     ("launch__grid_size", "grid"),
     ("launch__block_size", "block"),
 ])
-SCALE = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}
+SCALE = {"Gbyte/s": 1.0, "Tbyte/s": 1e3, "Mbyte/s": 1e-3, "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}
 
 
 def step_metrics(tag: str) -> None:
@@ -136,7 +136,7 @@ def step_metrics(tag: str) -> None:
     out = [f"# {tag}: ncu --set full --clock-control none over one decode step (B=1024, GPT-2 small, bf16); means per kernel class.",
            "# dur = gpu__time_duration (cold-cache, serialised under the profiler: compare shares); dram = dram__bytes_read+write per launch;",
            "# l2_to_sm = l1tex__m_xbar2l1tex_read_bytes; pct columns are % of peak sustained over the kernel's elapsed time.",
-           f"{'class':12s} {'n':>3s} {'dur_us':>8s} {'share':>6s} {'dram_MB':>9s} {'l2_to_sm_MB':>11s} {'dram%':>6s} {'l2%':>6s} {'tensor%':>7s} {'sm%':>6s} {'regs':>5s} {'grid':>6s}"]
+           f"{'class':12s} {'n':>3s} {'dur_us':>8s} {'share':>6s} {'dram_MB':>9s} {'l2_to_sm_MB':>11s} {'dramGB/s':>8s} {'l2%':>6s} {'tensor%':>7s} {'sm%':>6s} {'regs':>5s} {'grid':>6s}"]
     traffic = {}
 
     def mean(rs, k):
@@ -148,7 +148,7 @@ def step_metrics(tag: str) -> None:
         traffic[cls] = dram * 1e6
         share = sum(r["dur_us"] for r in rs if isinstance(r["dur_us"], float)) / tot
         out.append(f"{cls:12s} {len(rs):3d} {mean(rs, 'dur_us'):8.2f} {100 * share:5.1f}% {dram:9.2f} {mean(rs, 'l2_to_sm_MB'):11.2f} "
-                   f"{mean(rs, 'dram_pct'):6.1f} {mean(rs, 'l2_pct'):6.1f} {mean(rs, 'tensor_pct'):7.1f} {mean(rs, 'sm_pct'):6.1f} "
+                   f"{mean(rs, 'dram_GBps'):8.0f} {mean(rs, 'l2_pct'):6.1f} {mean(rs, 'tensor_pct'):7.1f} {mean(rs, 'sm_pct'):6.1f} "
                    f"{mean(rs, 'regs'):5.0f} {mean(rs, 'grid'):6.0f}")
     out.append(f"# sum of profiled launch durations: {tot:.1f} us over {len(recs)} launches")
     dst = os.path.join(ROOT, "profiles", f"{tag}_step_metrics.txt")
