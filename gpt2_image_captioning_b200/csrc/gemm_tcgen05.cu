@@ -10,10 +10,18 @@
 // each CTA reduces its 128 x BLOCK_N logit tile to one (max, lowest index) pair per row, so logits never reach HBM.
 //
 // Kernel shape: PERSISTENT, one CTA per SM walking 128 x BLOCK_N output tiles; BLOCK_K = 64 (one 128-byte swizzle atom),
-// a 6..10-stage TMA->MMA mbarrier ring that keeps streaming across tile boundaries, and two TMEM accumulators so the
+// a 4..8-stage TMA->MMA mbarrier ring that keeps streaming across tile boundaries, and two TMEM accumulators so the
 // epilogue of tile i overlaps the main loop of tile i+1.  6 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
-// issuer, warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Tiles are numbered M-fastest: the ~148 tiles in
-// flight share a handful of W tiles, each fetched from HBM once and served from L2 to the other M tiles.
+// issuer, warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+//
+// Code-generation rules this file follows (measured round 1, profiles/r1b_gemm_timeline.txt):
+//  * the producer and MMA loops run with the WHOLE warp converged and issue through elect.sync.  Under `if (lane == 0)` the
+//    compiler cannot prove the TMA / MMA operands warp-uniform and wraps every UTMALDG / UTCHMMA in an
+//    ELECT + 5 x R2UR + BRA.U.ANY waterfall: 217 cycles per TMA and 88 per MMA issue (the MMA itself runs 64).
+//  * the epilogue kind is a template parameter: a run-time switch inside the per-element loop compiled to real branches
+//    (~90 cycles per element with one warp per scheduler; 12 k cycles per 128 x 128 tile against 3 k for its main loop).
+//  * epilogue stores go through a per-warp swizzled staging tile so that a warp writes whole 128-byte row segments
+//    (lane = row in the TMEM layout would scatter every store instruction over 32 rows).
 // BF16X2 ("split") mode: A = A_hi + A_lo, W = W_hi + W_lo (each bf16); three MMAs per k-step
 // (hi.hi + hi.lo + lo.hi) into the same accumulator give ~16 mantissa bits.
 #include <cuda.h>
@@ -28,16 +36,31 @@ namespace gic {
 namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// one lane of the (fully active) warp; the compiler keeps the guarded uniform-datapath instructions un-looped
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}\n"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n"
@@ -46,35 +69,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
 
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
@@ -95,8 +112,8 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 // arrive on an mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets row (lane base + i)
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
@@ -110,8 +127,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 }  // namespace ptx
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -139,56 +156,68 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 struct alignas(64) GemmKernelParams {
   TmaDesc a_hi, w_hi, a_lo, w_lo;
   int M, N, K;
-  int epilogue;
   int mma_repeat;  // 1; > 1 only in the microbenchmark probe: re-issue each k-block's MMAs to measure the tensor-pipe rate
   const float* bias;
   float* out_f32; int ld_f32;
   bf16* out_hi; bf16* out_lo; int ld_bf16;
   float* part_val; int* part_idx;
-  long long* trace;  // null; microbenchmark only: clock64 timeline of CTA 0's producer / MMA / epilogue threads
+  long long* trace;  // null; microbenchmark only: clock64 timeline of CTA 0's producer / MMA / epilogue warps
 };
 
 constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_BLOCK_K = 128;  // two 128-byte swizzle atoms per stage, each operand fetched by ONE 3-D TMA
-constexpr int GEMM_ATOM_K = 64;    // elements per swizzle atom row
+constexpr int GEMM_BLOCK_K = 64;   // one 128-byte swizzle atom per row
 constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 4;
+constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 32 * 128;  // per epilogue warp: 32 rows x 128 B, 16-byte chunks XOR-swizzled
 
 template <int BLOCK_N, bool SPLIT>
 struct GemmTile {
-  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // [2 atoms][128 rows][128 B]
-  static constexpr int W_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;       // [2 atoms][BLOCK_N rows][128 B]
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // [128 rows][128 B]
+  static constexpr int W_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;       // [BLOCK_N rows][128 B]
   static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES) * (SPLIT ? 2 : 1);
-  // one persistent CTA per SM: spend (almost) all of its shared memory on the TMA ring.  Measured round 1
-  // (microbench tma_probe): the single-thread producer loop costs ~520 cycles per stage (mbarrier wait + expect_tx + two
-  // TMA issues) whatever the stage size -- a 64-wide k-block capped the feed at 123 GB/s per SM and the GEMMs ran at ~1050
-  // cycles per k-block, 4x the MMA time; 128-wide k-blocks fetched by one 3-D TMA per operand halve the per-byte overhead.
-  static constexpr int BUDGET = 200 * 1024;
+  // one persistent CTA per SM: spend (almost) all of its shared memory on the TMA ring
+  static constexpr int BUDGET = 227 * 1024 - 1024 /* alignment slack */ - 1024 /* barriers */ - 2 * BLOCK_N * 4 /* bias */ - GEMM_STAGING_BYTES;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 10 ? 10 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
-  static_assert(STAGES * STAGE_BYTES + 4096 <= 227 * 1024, "tile does not fit in shared memory");
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 512 /* barriers */ + 2 * BLOCK_N * 4 /* bias */;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static_assert(STAGES >= 3, "tile does not leave room for a 3-stage ring");
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024 + 2 * BLOCK_N * 4 + GEMM_STAGING_BYTES;
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // one accumulator buffer
   static constexpr int TMEM_NEED = 2 * ACC_COLS;                 // double-buffered: epilogue(i) overlaps main loop(i+1)
   static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;  // power of two
 };
 
+template <int EPI>
+__device__ __forceinline__ float epi_act(float x, bool precise) {
+  if (EPI == EPI_TANH) return tanhf(x);
+  if (EPI == EPI_GELU) return precise ? gelu_tanh(x) : gelu_tanh_fast(x);
+  if (EPI == EPI_RELU) return fmaxf(x, 0.f);
+  return x;
+}
+
 // Persistent kernel: grid = min(#tiles, #SMs); CTA c walks tiles c, c + grid, ...  (tile t -> m_tile = t % m_tiles,
 // n_tile = t / m_tiles, so the ~148 tiles in flight share few W tiles and each is fetched from HBM once).
-template <int BLOCK_N, bool SPLIT>
+// EPI: EPI_NONE / TANH / GELU / RELU (bias + activation), EPI_RESIDUAL (out_f32 += result), EPI_ARGMAX (per-tile row argmax
+// partials; optional fp32 logits tap).
+template <int BLOCK_N, bool SPLIT, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKernelParams p) {
   using Tile = GemmTile<BLOCK_N, SPLIT>;
   constexpr int STAGES = Tile::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Tile::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* s_bias = reinterpret_cast<float*>(smem + STAGES * Tile::STAGE_BYTES + 512);  // [2][BLOCK_N]
+  // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment; everything below is addressed through 32-bit shared-window
+  // addresses derived from this one base so the compiler keeps them in uniform registers
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  constexpr uint32_t OFF_BAR = STAGES * Tile::STAGE_BYTES;
+  const uint32_t full_bar = smem_base + OFF_BAR;             // [STAGES]
+  const uint32_t empty_bar = full_bar + 8 * STAGES;          // [STAGES]
+  const uint32_t tmem_full_bar = empty_bar + 8 * STAGES;     // [2]
+  const uint32_t tmem_empty_bar = tmem_full_bar + 16;        // [2]
+  const uint32_t tmem_slot = tmem_empty_bar + 16;
+  float* s_bias = reinterpret_cast<float*>(smem_gen + OFF_BAR + 1024);                        // [2][BLOCK_N]
+  float4* s_stage = reinterpret_cast<float4*>(smem_gen + OFF_BAR + 1024 + 2 * BLOCK_N * 4);   // [4 warps][32 rows][8 chunks]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
+  const int lane = threadIdx.x & 31;
   const int m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int total_tiles = m_tiles * n_tiles;
@@ -197,7 +226,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
   const long long t_start = tracing ? clock64() : 0;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&p.a_hi);
     ptx::prefetch_tmap(&p.w_hi);
     if (SPLIT) {
@@ -205,213 +234,221 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
       ptx::prefetch_tmap(&p.w_lo);
     }
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(full_bar + 8 * s, 1);
+      ptx::mbar_init(empty_bar + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], 4);  // one arrival per epilogue warp
+      ptx::mbar_init(tmem_full_bar + 8 * a, 1);
+      ptx::mbar_init(tmem_empty_bar + 8 * a, GEMM_EPI_WARPS);  // one arrival per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_base_slot, Tile::TMEM_COLS);
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, Tile::TMEM_COLS);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_base_slot;
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (tracing && threadIdx.x == 0) p.trace[600] = clock64() - t_start;  // prologue done
   pdl_wait();  // prologue above overlapped the previous kernel; its outputs are visible from here on
 
   if (warp == 0) {
     // ===== TMA producer: streams k-blocks of successive tiles through the ring without pausing at tile boundaries =====
-    if (lane == 0) {
-      uint32_t it = 0;  // k-block counter across all tiles of this CTA
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
-        for (int kb = 0; kb < nk; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          if (tracing && it < 60) p.trace[it * 4 + 0] = clock64() - t_start;
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-          if (tracing && it < 60) p.trace[it * 4 + 1] = clock64() - t_start;
-          uint8_t* st = smem + s * Tile::STAGE_BYTES;
-          ptx::mbar_expect_tx(&full_bar[s], Tile::STAGE_BYTES);
-          const int ka = kb * (GEMM_BLOCK_K / GEMM_ATOM_K);  // first swizzle atom of this k-block (3rd tensor-map coordinate)
-          ptx::tma_load_3d(st, &p.a_hi, &full_bar[s], 0, m0, ka);
-          ptx::tma_load_3d(st + Tile::A_BYTES, &p.w_hi, &full_bar[s], 0, n0, ka);
+    uint32_t s = 0, ph = 0, it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        if (ptx::elect_one()) {
+          const uint32_t st = smem_base + s * Tile::STAGE_BYTES;
+          const uint32_t fb = full_bar + 8 * s;
+          ptx::mbar_expect_tx(fb, Tile::STAGE_BYTES);
+          ptx::tma_load_2d(st, &p.a_hi, fb, kb * GEMM_BLOCK_K, m0);
+          ptx::tma_load_2d(st + Tile::A_BYTES, &p.w_hi, fb, kb * GEMM_BLOCK_K, n0);
           if (SPLIT) {
-            ptx::tma_load_3d(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, &full_bar[s], 0, m0, ka);
-            ptx::tma_load_3d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, &full_bar[s], 0, n0, ka);
+            ptx::tma_load_2d(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, fb, kb * GEMM_BLOCK_K, m0);
+            ptx::tma_load_2d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, fb, kb * GEMM_BLOCK_K, n0);
           }
           if (tracing && it < 60) p.trace[it * 4 + 2] = clock64() - t_start;
         }
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread), alternating between the two TMEM accumulators =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
-      uint32_t it = 0, local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        const uint32_t acc = local & 1, use = local >> 1;
-        ptx::mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);  // epilogue has drained this accumulator (passes at first use)
+    // ===== MMA issuer (one elected lane, whole warp converged), alternating between the two TMEM accumulators =====
+    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+    uint32_t s = 0, ph = 0, it = 0, local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const uint32_t acc = local & 1, use = local >> 1;
+      ptx::mbar_wait(tmem_empty_bar + 8 * acc, (use & 1) ^ 1);  // epilogue has drained this accumulator (passes at first use)
+      ptx::tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * Tile::ACC_COLS;
+      for (int kb = 0; kb < nk; ++kb, ++it) {
+        ptx::mbar_wait(full_bar + 8 * s, ph);
         ptx::tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + acc * Tile::ACC_COLS;
-        for (int kb = 0; kb < nk; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          if (tracing && it < 60) p.trace[256 + it * 4 + 0] = clock64() - t_start;
-          ptx::mbar_wait(&full_bar[s], ph);
+        if (ptx::elect_one()) {
           if (tracing && it < 60) p.trace[256 + it * 4 + 1] = clock64() - t_start;
-          ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + s * Tile::STAGE_BYTES);
+          const uint32_t sa = smem_base + s * Tile::STAGE_BYTES;
           const uint64_t a_hi = make_smem_desc_sw128(sa);
           const uint64_t w_hi = make_smem_desc_sw128(sa + Tile::A_BYTES);
           const uint64_t a_lo = make_smem_desc_sw128(sa + Tile::A_BYTES + Tile::W_BYTES);
           const uint64_t w_lo = make_smem_desc_sw128(sa + 2 * Tile::A_BYTES + Tile::W_BYTES);
-          for (int rep = 0; rep < p.mma_repeat; ++rep)
+          for (int rep = 0; rep < p.mma_repeat; ++rep) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
-            // k-step inside the stage: atom (k / 4) is a whole [rows][128 B] tile further on, then 32 bytes per step inside it
-            constexpr uint64_t A_ATOM = (uint64_t)(GEMM_BLOCK_M * 128) >> 4, W_ATOM = (uint64_t)(BLOCK_N * 128) >> 4;
-            const uint64_t ka = (uint64_t)(k / 4), ki = (uint64_t)(((k % 4) * 16 * 2) >> 4);
-            const uint64_t aoff = ka * A_ATOM + ki, woff = ka * W_ATOM + ki;
-            ptx::umma_bf16(tmem_acc, a_hi + aoff, w_hi + woff, idesc, (kb | k | rep) != 0);
-            if (SPLIT) {
-              ptx::umma_bf16(tmem_acc, a_hi + aoff, w_lo + woff, idesc, 1);
-              ptx::umma_bf16(tmem_acc, a_lo + aoff, w_hi + woff, idesc, 1);
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+              const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per k-step inside the 128-byte swizzle row
+              ptx::umma_bf16(tmem_acc, a_hi + koff, w_hi + koff, idesc, (kb | k | rep) != 0);
+              if (SPLIT) {
+                ptx::umma_bf16(tmem_acc, a_hi + koff, w_lo + koff, idesc, 1);
+                ptx::umma_bf16(tmem_acc, a_lo + koff, w_hi + koff, idesc, 1);
+              }
             }
           }
-          ptx::umma_commit(&empty_bar[s]);  // smem slot is free once these MMAs have read it
+          ptx::umma_commit(empty_bar + 8 * s);                          // smem slot is free once these MMAs have read it
+          if (kb == nk - 1) ptx::umma_commit(tmem_full_bar + 8 * acc);  // accumulator complete
           if (tracing && it < 60) p.trace[256 + it * 4 + 2] = clock64() - t_start;
         }
-        ptx::umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
-    // Everything that does not depend on the accumulator is fetched BEFORE waiting for it (bias tile -> smem, first
-    // residual chunk -> registers), and inside the loop the next chunk's residual is loaded before the current chunk is
-    // stored: output and residual alias (in-place +=), so loads placed after stores would serialise one L2 round trip per
-    // float4 (ncu source page, round 1).
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ===== epilogue: TMEM -> registers (lane = row) -> swizzled staging tile -> coalesced global stores =====
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int et = (warp - 2) * 32 + lane;  // 0..127 over the four epilogue warps
-    const bool resid = p.epilogue == EPI_RESIDUAL;
-    const bool vec_f32 = (p.ld_f32 % 4 == 0);
+    float4* stage = s_stage + (warp - 2) * 256;  // this warp's [32 rows][8 x 16 B]
+    const bool vec_f32 = (p.ld_f32 % 4 == 0), vec_bf16 = (p.ld_bf16 % 4 == 0);
+    // coalesced domain: lane handles 16-byte chunk (lane & 7) of rows (lane >> 3) + 4 * i
+    const int cchunk = lane & 7, crow0 = lane >> 3;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const uint32_t acc = local & 1, use = local >> 1;
       const int n_tile = tile / m_tiles;
       const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
-      const int row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int wrow0 = m0 + q * 32;  // first row of this warp's 32-row band
       float* bias_s = s_bias + acc * BLOCK_N;
       for (int c = et; c < BLOCK_N; c += 128) bias_s[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-      float4 res_next[8];
-      auto load_res = [&](int c0) {
-        const float* src = p.out_f32 + (size_t)row * p.ld_f32 + n0 + c0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) res_next[j] = *reinterpret_cast<const float4*>(src + 4 * j);
-      };
-      const bool res_vec_ok = resid && row_ok && vec_f32;
-      if (res_vec_ok && n0 + 32 <= p.N) load_res(0);
-      if (tracing && et == 0 && local < 8) p.trace[512 + local * 4 + 0] = clock64() - t_start;
-      ptx::mbar_wait(&tmem_full_bar[acc], use & 1);
-      if (tracing && et == 0 && local < 8) p.trace[512 + local * 4 + 1] = clock64() - t_start;
+      ptx::mbar_wait(tmem_full_bar + 8 * acc, use & 1);
       ptx::tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + acc * Tile::ACC_COLS;
+      if (tracing && et == 0 && local < 8) p.trace[512 + local * 4 + 1] = clock64() - t_start;
+      const uint32_t tmem_acc = tmem_base + acc * Tile::ACC_COLS + ((uint32_t)(q * 32) << 16);
       float best = -INFINITY;
       int best_idx = 0x7fffffff;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        const int col0 = n0 + c0;
+        // residual values of this chunk, fetched in the coalesced layout before the accumulator is touched
+        float4 res[8];
+        if (EPI == EPI_RESIDUAL && col0 < p.N) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = wrow0 + crow0 + 4 * i, col = col0 + cchunk * 4;
+            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < p.M) {
+              const float* src = p.out_f32 + (size_t)row * p.ld_f32 + col;
+              if (vec_f32 && col + 3 < p.N) res[i] = __ldcg(reinterpret_cast<const float4*>(src));
+              else {
+                if (col < p.N) res[i].x = __ldcg(src);
+                if (col + 1 < p.N) res[i].y = __ldcg(src + 1);
+                if (col + 2 < p.N) res[i].z = __ldcg(src + 2);
+                if (col + 3 < p.N) res[i].w = __ldcg(src + 3);
+              }
+            }
+          }
+        }
         uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        ptx::tmem_ld_32x32(tmem_acc + (uint32_t)c0, r);
+        ptx::tmem_ld_wait();
         if (c0 + 32 >= BLOCK_N) {
           // last TMEM read of this tile: hand the accumulator back to the MMA warp before doing the math / stores
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
         }
-        const int col0 = n0 + c0;
         if (col0 >= p.N) continue;  // warp-uniform
-        const bool full = (col0 + 32 <= p.N);
-        float4 res_cur[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) res_cur[j] = res_next[j];
-        if (res_vec_ok && c0 + 32 < BLOCK_N && col0 + 64 <= p.N) load_res(c0 + 32);
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]) + bias_s[c0 + j];
-          if (p.epilogue == EPI_TANH) x = tanhf(x);
-          else if (p.epilogue == EPI_GELU) x = SPLIT ? gelu_tanh(x) : gelu_tanh_fast(x);
-          else if (p.epilogue == EPI_RELU) x = fmaxf(x, 0.f);
-          v[j] = x;
-        }
-        if (p.part_val) {
+        for (int j = 0; j < 32; ++j) v[j] = epi_act<EPI>(__uint_as_float(r[j]) + bias_s[c0 + j], SPLIT);
+        if (EPI == EPI_ARGMAX) {
+          if (col0 + 32 <= p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = col0 + j;
-            if (col < p.N && v[j] > best) {  // strict > keeps the lowest index among equal maxima
-              best = v[j];
-              best_idx = col;
-            }
-          }
-        }
-        if (!row_ok) continue;
-        if (p.out_f32) {
-          float* dst = p.out_f32 + (size_t)row * p.ld_f32 + col0;
-          if (full && vec_f32) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              if (resid) { o.x += res_cur[j].x; o.y += res_cur[j].y; o.z += res_cur[j].z; o.w += res_cur[j].w; }
-              *reinterpret_cast<float4*>(dst + 4 * j) = o;
+            for (int j = 0; j < 32; ++j) {
+              const bool gt = v[j] > best;  // strict > keeps the lowest index among equal maxima
+              best = gt ? v[j] : best;
+              best_idx = gt ? col0 + j : best_idx;
             }
           } else {
-            float old[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) old[j] = (resid && col0 + j < p.N) ? dst[j] : 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) dst[j] = old[j] + v[j];
+            for (int j = 0; j < 32; ++j) {
+              const bool gt = (col0 + j < p.N) && v[j] > best;
+              best = gt ? v[j] : best;
+              best_idx = gt ? col0 + j : best_idx;
+            }
           }
+          if (p.out_f32 == nullptr) continue;  // product path: logits never reach HBM
         }
-        if (p.out_hi) {
-          bf16* dh = p.out_hi + (size_t)row * p.ld_bf16 + col0;
-          bf16* dl = p.out_lo ? p.out_lo + (size_t)row * p.ld_bf16 + col0 : nullptr;
-          if (full && (p.ld_bf16 % 8 == 0)) {
+        // lane = row  ->  staging tile (chunk position XOR row keeps both directions bank-conflict free)
+        __syncwarp();  // previous chunk's readers are done with the staging tile
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              Vec16<bf16> hv;
-              hv.pack(v + j);
-              hv.store(dh + j);
+        for (int c = 0; c < 8; ++c) stage[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int lr = crow0 + 4 * i, row = wrow0 + lr, col = col0 + cchunk * 4;
+          float4 o = stage[lr * 8 + (cchunk ^ (lr & 7))];
+          if (row >= p.M || col >= p.N) continue;
+          if (EPI == EPI_RESIDUAL) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
+          const bool full4 = col + 3 < p.N;
+          if (p.out_f32) {
+            float* dst = p.out_f32 + (size_t)row * p.ld_f32 + col;
+            if (vec_f32 && full4) *reinterpret_cast<float4*>(dst) = o;
+            else {
+              dst[0] = o.x;
+              if (col + 1 < p.N) dst[1] = o.y;
+              if (col + 2 < p.N) dst[2] = o.z;
+              if (col + 3 < p.N) dst[3] = o.w;
+            }
+          }
+          if (p.out_hi) {
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(o.x, o.y), h23 = __floats2bfloat162_rn(o.z, o.w);
+            bf16* dh = p.out_hi + (size_t)row * p.ld_bf16 + col;
+            __nv_bfloat162 l01 = h01, l23 = h23;
+            if (p.out_lo) {
+              const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+              l01 = __floats2bfloat162_rn(o.x - f01.x, o.y - f01.y);
+              l23 = __floats2bfloat162_rn(o.z - f23.x, o.w - f23.y);
+            }
+            bf16* dl = p.out_lo ? p.out_lo + (size_t)row * p.ld_bf16 + col : nullptr;
+            if (vec_bf16 && full4) {
+              uint2 pk;
+              pk.x = *reinterpret_cast<const uint32_t*>(&h01);
+              pk.y = *reinterpret_cast<const uint32_t*>(&h23);
+              *reinterpret_cast<uint2*>(dh) = pk;
               if (dl) {
-                float hf[8], lf[8];
-                hv.unpack(hf);
-#pragma unroll
-                for (int t = 0; t < 8; ++t) lf[t] = v[j + t] - hf[t];
-                Vec16<bf16> lv;
-                lv.pack(lf);
-                lv.store(dl + j);
+                pk.x = *reinterpret_cast<const uint32_t*>(&l01);
+                pk.y = *reinterpret_cast<const uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(dl) = pk;
               }
+            } else {
+              const bf16 hv[4] = {h01.x, h01.y, h23.x, h23.y};
+              const bf16 lv[4] = {l01.x, l01.y, l23.x, l23.y};
+              for (int t = 0; t < 4; ++t)
+                if (col + t < p.N) {
+                  dh[t] = hv[t];
+                  if (dl) dl[t] = lv[t];
+                }
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) {
-                const bf16 hb = __float2bfloat16_rn(v[j]);
-                dh[j] = hb;
-                if (dl) dl[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hb));
-              }
           }
         }
       }
-      if (p.part_val && row_ok) {
-        p.part_val[(size_t)n_tile * p.M + row] = best;
-        p.part_idx[(size_t)n_tile * p.M + row] = best_idx;
+      if (EPI == EPI_ARGMAX) {
+        const int row = wrow0 + lane;
+        if (row < p.M) {
+          p.part_val[(size_t)n_tile * p.M + row] = best;
+          p.part_idx[(size_t)n_tile * p.M + row] = best_idx;
+        }
       }
       if (tracing && et == 0 && local < 8) p.trace[512 + local * 4 + 2] = clock64() - t_start;
     }
@@ -440,9 +477,8 @@ int tma_init() {
   return GIC_OK;
 }
 
-// bf16 row-major [rows, cols] viewed as [cols/64 atoms][rows][64] so that ONE box of (64 x box_rows x 2 atoms) lands in
-// shared memory as two consecutive 128B-swizzled K-major tiles -- exactly the layout the UMMA descriptors walk.
-// Out-of-bounds rows / atoms are zero-filled.  Requires cols % 8 == 0; a partial last atom is zero-filled by the box bounds.
+// bf16 row-major [rows, cols]: one box = [box_rows][64 cols] lands in shared memory as a 128B-swizzled K-major tile --
+// exactly the layout the UMMA descriptors walk.  Out-of-bounds rows / columns are zero-filled.
 int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows) {
   GIC_TRY(tma_init());
   static_assert(sizeof(CUtensorMap) == sizeof(TmaDesc), "CUtensorMap size");
@@ -450,12 +486,11 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t col
               "TMA: base must be 16-byte aligned and the row stride a multiple of 8 elements (stride %llu)",
               (unsigned long long)row_stride_elems);
   GIC_REQUIRE(box_rows >= 1 && box_rows <= 256, "TMA: box rows %u out of range", box_rows);
-  GIC_REQUIRE(cols % GEMM_ATOM_K == 0, "tensor-core GEMM operands need K (%llu) to be a multiple of %d", (unsigned long long)cols, GEMM_ATOM_K);
-  cuuint64_t gdim[3] = {(cuuint64_t)GEMM_ATOM_K, rows, cols / GEMM_ATOM_K};
-  cuuint64_t gstride[2] = {row_stride_elems * 2, (cuuint64_t)GEMM_ATOM_K * 2};
-  cuuint32_t box[3] = {(cuuint32_t)GEMM_ATOM_K, box_rows, (cuuint32_t)(GEMM_BLOCK_K / GEMM_ATOM_K)};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride,
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)GEMM_BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GIC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu box_rows=%u)", (int)r,
@@ -463,13 +498,11 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t col
   return GIC_OK;
 }
 
-// Tile width.  Measured on B200 (csrc/microbench.cu): the kernel is bound by how fast one SM can pull operand bytes
-// through its TMA ring (~70 GB/s per SM, ~8 TB/s chip-wide from L2), so the best tile minimises
-// rounds x bytes-per-tile-per-k-block = ceil(tiles / #SMs) x (A 16 KB + W 128 B x BLOCK_N): wide tiles re-read the
-// activation slab less often, narrow ones keep all SMs busy when M is small.
+// Tile width: minimise rounds x operand bytes per k-block, rounds = ceil(tiles / #SMs): wide tiles re-read the activation
+// slab less often, narrow ones keep all SMs busy when M is small.
 int gemm_bf16_pick_block_n(int M, int N, int split) {
   static const int wide[] = {256, 192, 128, 64, 32};
-  static const int narrow[] = {64, 32};  // split (bf16x2) stages carry four operand tiles: two 96 KB stages at 64 wide
+  static const int narrow[] = {64, 32};  // split (bf16x2) stages carry four operand tiles
   const int* cand = split ? narrow : wide;
   const int n_cand = split ? 2 : 5;
   const long m_tiles = ceil_div(M, GEMM_BLOCK_M);
@@ -495,10 +528,20 @@ static int gemm_num_sms() {
   return sms;
 }
 
+template <int BLOCK_N, bool SPLIT, int EPI>
+static int configure_one() {
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      GemmTile<BLOCK_N, SPLIT>::SMEM_BYTES));
+  return GIC_OK;
+}
 template <int BLOCK_N, bool SPLIT>
 static int configure_cfg() {
-  GIC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      GemmTile<BLOCK_N, SPLIT>::SMEM_BYTES));
+  GIC_TRY((configure_one<BLOCK_N, SPLIT, EPI_NONE>()));
+  GIC_TRY((configure_one<BLOCK_N, SPLIT, EPI_TANH>()));
+  GIC_TRY((configure_one<BLOCK_N, SPLIT, EPI_GELU>()));
+  GIC_TRY((configure_one<BLOCK_N, SPLIT, EPI_RELU>()));
+  GIC_TRY((configure_one<BLOCK_N, SPLIT, EPI_RESIDUAL>()));
+  GIC_TRY((configure_one<BLOCK_N, SPLIT, EPI_ARGMAX>()));
   return GIC_OK;
 }
 
@@ -517,10 +560,10 @@ int gemm_bf16_configure() {
   return GIC_OK;
 }
 
-template <int BLOCK_N, bool SPLIT>
-static int launch_cfg(const GemmKernelParams& kp, cudaStream_t st) {
+template <int BLOCK_N, bool SPLIT, int EPI>
+static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
   using Tile = GemmTile<BLOCK_N, SPLIT>;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, EPI>;
   const long tiles = (long)ceil_div(kp.M, GEMM_BLOCK_M) * ceil_div(kp.N, BLOCK_N);
   const int sms = gemm_num_sms();
   dim3 grid((unsigned)(tiles < sms ? tiles : sms));  // persistent: one CTA per SM
@@ -529,28 +572,47 @@ static int launch_cfg(const GemmKernelParams& kp, cudaStream_t st) {
   return GIC_OK;
 }
 
+template <int BLOCK_N, bool SPLIT>
+static int launch_cfg(const GemmKernelParams& kp, int epi, cudaStream_t st) {
+  switch (epi) {
+    case EPI_NONE: return launch_one<BLOCK_N, SPLIT, EPI_NONE>(kp, st);
+    case EPI_TANH: return launch_one<BLOCK_N, SPLIT, EPI_TANH>(kp, st);
+    case EPI_GELU: return launch_one<BLOCK_N, SPLIT, EPI_GELU>(kp, st);
+    case EPI_RELU: return launch_one<BLOCK_N, SPLIT, EPI_RELU>(kp, st);
+    case EPI_RESIDUAL: return launch_one<BLOCK_N, SPLIT, EPI_RESIDUAL>(kp, st);
+    case EPI_ARGMAX: return launch_one<BLOCK_N, SPLIT, EPI_ARGMAX>(kp, st);
+  }
+  set_error("gemm_bf16: unknown epilogue %d", epi);
+  return GIC_ERR_INVALID;
+}
+
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   GIC_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm_bf16: empty problem");
-  GIC_REQUIRE(a.K % GEMM_ATOM_K == 0, "gemm_bf16: K (%d) must be a multiple of %d", a.K, GEMM_ATOM_K);
+  GIC_REQUIRE(a.K % 8 == 0, "gemm_bf16: K (%d) must be a multiple of 8", a.K);
   GemmKernelParams kp;
   kp.a_hi = a.a_hi; kp.w_hi = a.w_hi; kp.a_lo = a.a_lo; kp.w_lo = a.w_lo;
-  kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.epilogue = a.epilogue; kp.bias = a.bias;
+  kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.bias = a.bias;
   kp.mma_repeat = a.mma_repeat < 1 ? 1 : a.mma_repeat;
   kp.out_f32 = a.out.f32; kp.ld_f32 = a.ld_out; kp.out_hi = a.out.hi; kp.out_lo = a.out.lo; kp.ld_bf16 = a.ld_out;
   kp.part_val = a.part_val; kp.part_idx = a.part_idx; kp.trace = a.trace;
-  GIC_REQUIRE(!(a.epilogue == EPI_RESIDUAL && !a.out.f32), "gemm_bf16: residual epilogue needs the fp32 output");
+  int epi = a.epilogue;
+  if (a.part_val) {
+    GIC_REQUIRE(a.epilogue == EPI_NONE && a.part_idx, "gemm_bf16: the fused argmax takes no activation and needs both partial buffers");
+    epi = EPI_ARGMAX;
+  }
+  GIC_REQUIRE(!(epi == EPI_RESIDUAL && !a.out.f32), "gemm_bf16: residual epilogue needs the fp32 output");
   if (a.split) {
     switch (a.block_n) {
-      case 32: return launch_cfg<32, true>(kp, st);
-      case 64: return launch_cfg<64, true>(kp, st);
+      case 32: return launch_cfg<32, true>(kp, epi, st);
+      case 64: return launch_cfg<64, true>(kp, epi, st);
     }
   } else {
     switch (a.block_n) {
-      case 32: return launch_cfg<32, false>(kp, st);
-      case 64: return launch_cfg<64, false>(kp, st);
-      case 128: return launch_cfg<128, false>(kp, st);
-      case 192: return launch_cfg<192, false>(kp, st);
-      case 256: return launch_cfg<256, false>(kp, st);
+      case 32: return launch_cfg<32, false>(kp, epi, st);
+      case 64: return launch_cfg<64, false>(kp, epi, st);
+      case 128: return launch_cfg<128, false>(kp, epi, st);
+      case 192: return launch_cfg<192, false>(kp, epi, st);
+      case 256: return launch_cfg<256, false>(kp, epi, st);
     }
   }
   set_error("gemm_bf16: unsupported block_n %d", a.block_n);

@@ -4,7 +4,7 @@
 
 namespace gic {
 
-enum Epilogue { EPI_NONE = 0, EPI_TANH = 1, EPI_GELU = 2, EPI_RELU = 3, EPI_RESIDUAL = 4 };
+enum Epilogue { EPI_NONE = 0, EPI_TANH = 1, EPI_GELU = 2, EPI_RELU = 3, EPI_RESIDUAL = 4, EPI_ARGMAX = 5 /* internal: set by part_val */ };
 
 // Where a producer kernel writes an activation: fp32 and/or bf16 (hi) and/or the bf16 remainder (lo = bf16(v - hi),
 // the second half of a BF16X2 GEMM operand).  Any pointer may be null.
@@ -30,7 +30,7 @@ int launch_sgemm_nt(const float* A, int lda, const float* W, const float* bias, 
 // ---- gemm_tcgen05.cu : bf16 tcgen05/TMEM GEMM fed by TMA ----------------------------------------------------
 struct alignas(64) TmaDesc { unsigned char bytes[128]; };  // CUtensorMap
 int tma_init();  // resolves cuTensorMapEncodeTiled through the runtime
-// bf16 row-major [rows, cols] operand map: one box = [2 swizzle atoms][box_rows][64 cols], 128B swizzle, out-of-bounds -> zero
+// bf16 row-major [rows, cols] operand map: one box = [box_rows][64 cols], 128B swizzle, out-of-bounds -> zero
 int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows);
 
 struct GemmBf16Args {

@@ -171,7 +171,7 @@ int main(int argc, char** argv) {
       CK(cudaMemcpyAsync(h_tr, tr, sizeof(h_tr), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
       printf("timeline %s (N=%d K=%d block_n=%d): prologue done at %lld cycles\n", sh.name, sh.N, sh.K, sh.bn, h_tr[600]);
       printf("  kb | producer: wait_begin empty_seen issued | mma: wait_begin full_seen committed\n");
-      const int nkb = sh.K / 128 * (sh.lm ? 3 : 1);
+      const int nkb = sh.K / 64 * (sh.lm ? 3 : 1);
       for (int kb = 0; kb < nkb && kb < 60; ++kb)
         printf("  %2d | %8lld %8lld %8lld | %8lld %8lld %8lld\n", kb, h_tr[kb * 4], h_tr[kb * 4 + 1], h_tr[kb * 4 + 2], h_tr[256 + kb * 4],
                h_tr[256 + kb * 4 + 1], h_tr[256 + kb * 4 + 2]);

@@ -45,15 +45,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   }
 }
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
 
 struct alignas(64) ProbeParams {
-  TmaDesc map;        // [K/64 atoms][rows][64] bf16, box = 2 atoms x box_rows x 64 = box_rows * 256 bytes
+  TmaDesc map;        // [K/64 atoms][rows][64] bf16, box = box_rows x 64 = box_rows * 128 bytes
   int box_rows;       // rows per TMA
   int tmas_per_stage; // 1..4
   int stages;
@@ -66,7 +66,7 @@ struct alignas(64) ProbeParams {
 __global__ void __launch_bounds__(64, 1) tma_stream_probe(const __grid_constant__ ProbeParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = p.box_rows * 256 * p.tmas_per_stage;
+  const int stage_bytes = p.box_rows * 128 * p.tmas_per_stage;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,16 +78,16 @@ __global__ void __launch_bounds__(64, 1) tma_stream_probe(const __grid_constant_
   __syncthreads();
   const int row_blocks = p.rows_total / p.box_rows;  // boxes along the row axis
   if (warp == 0 && lane == 0) {
-    // box index walks (row block, k-block) like a GEMM operand stream: 6 k-blocks per row block.  All indices advance
+    // box index walks (row block, k-block) like a GEMM operand stream: 12 k-blocks of 64 per row block.  All indices advance
     // incrementally: an integer division in this loop would cost more than the TMA issue it is trying to measure.
-    int kb = 0, rb = p.shared_source ? (int)((blockIdx.x * 7) % row_blocks) : (int)(((long)blockIdx.x * p.iters * p.tmas_per_stage / 6) % row_blocks);
+    int kb = 0, rb = p.shared_source ? (int)((blockIdx.x * 7) % row_blocks) : (int)(((long)blockIdx.x * p.iters * p.tmas_per_stage / 12) % row_blocks);
     int s = 0; uint32_t ph = 0;
     for (int it = 0; it < p.iters; ++it) {
       mbar_wait(&empty_bar[s], ph ^ 1);
       mbar_expect_tx(&full_bar[s], stage_bytes);
       for (int t = 0; t < p.tmas_per_stage; ++t) {
-        tma_load_3d(smem + (size_t)s * stage_bytes + (size_t)t * p.box_rows * 256, &p.map, &full_bar[s], 0, rb * p.box_rows, kb * 2);
-        if (++kb == 6) { kb = 0; if (++rb == row_blocks) rb = 0; }
+        tma_load_2d(smem + (size_t)s * stage_bytes + (size_t)t * p.box_rows * 128, &p.map, &full_bar[s], kb * 64, rb * p.box_rows);
+        if (++kb == 12) { kb = 0; if (++rb == row_blocks) rb = 0; }
       }
       if (++s == p.stages) { s = 0; ph ^= 1; }
     }
@@ -125,10 +125,10 @@ int main() {
         const size_t rows = shared_source ? 8192 : rows_big;  // 8192 rows = 12.6 MB: L2 resident
         OK(make_tma_2d_bf16(&p.map, buf, rows, K, K, c.box_rows));
         p.box_rows = c.box_rows; p.tmas_per_stage = c.tmas; p.stages = c.stages; p.rows_total = (int)rows; p.shared_source = shared_source;
-        const int stage_bytes = c.box_rows * 256 * c.tmas;
+        const int stage_bytes = c.box_rows * 128 * c.tmas;
         const size_t target = (size_t)(grid == 1 ? 64 : 24) << 20;  // bytes per CTA
         p.iters = (int)(target / stage_bytes);
-        if (!shared_source && (size_t)p.iters * grid * c.tmas * c.box_rows > rows_big * 6) p.iters = (int)(rows_big * 6 / ((size_t)grid * c.tmas * c.box_rows));
+        if (!shared_source && (size_t)p.iters * grid * c.tmas * c.box_rows > rows_big * 12) p.iters = (int)(rows_big * 12 / ((size_t)grid * c.tmas * c.box_rows));
         p.cycles = cyc;
         const size_t smem = (size_t)c.stages * stage_bytes + 2048;
         for (int rep = 0; rep < 2; ++rep) {  // first pass warms L2 / instruction cache
