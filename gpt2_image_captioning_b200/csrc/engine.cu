@@ -243,7 +243,7 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
     w->logits = c.take<float>((size_t)w->rows * e->V);
     w->n_parts_max = LMHEAD_F32_PARTS;
   } else {
-    w->n_parts_max = ceil_div(e->V, 32);
+    w->n_parts_max = 2 * ceil_div(e->V, 32);
     if (w->beams > 1) w->logits = c.take<float>((size_t)w->rows * e->V);  // beam search needs full rows for log-softmax + top-2K
   }
   if (w->beams > 1) {
@@ -292,7 +292,7 @@ static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, i
   }
   g.M = M; g.N = lin.N; g.K = lin.K; g.block_n = bn; g.split = e->split ? 1 : 0; g.epilogue = epilogue; g.bias = lin.bias;
   g.out = out; g.ld_out = ld_out; g.part_val = part_val; g.part_idx = part_idx;
-  if (n_parts) *n_parts = ceil_div(lin.N, bn);
+  if (n_parts) *n_parts = 2 * ceil_div(lin.N, bn);  // one (value, index) slot per (tile, column-parity epilogue warp)
   return launch_gemm_bf16(g, st);
 }
 

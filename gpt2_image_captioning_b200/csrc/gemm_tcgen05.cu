@@ -11,8 +11,8 @@
 //
 // Kernel shape: PERSISTENT, one CTA per SM walking 128 x BLOCK_N output tiles; BLOCK_K = 64 (one 128-byte swizzle atom),
 // a 4..8-stage TMA->MMA mbarrier ring that keeps streaming across tile boundaries, and two TMEM accumulators so the
-// epilogue of tile i overlaps the main loop of tile i+1.  6 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
-// issuer, warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).
+// epilogue of tile i overlaps the main loop of tile i+1.  10 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA
+// issuer, warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter on alternate 32-column chunks).
 //
 // Code-generation rules this file follows (measured round 1, profiles/r1b_gemm_timeline.txt):
 //  * the producer and MMA loops run with the WHOLE warp converged and issue through elect.sync.  Under `if (lane == 0)` the
@@ -160,14 +160,17 @@ struct alignas(64) GemmKernelParams {
   const float* bias;
   float* out_f32; int ld_f32;
   bf16* out_hi; bf16* out_lo; int ld_bf16;
-  float* part_val; int* part_idx;
+  float* part_val; int* part_idx;  // [2 * n_tiles][M]: one slot per (tile, column-parity warp)
+  // folded LayerNorm on the A operand (see launch_gemm_bf16): out = rstd_r * (acc - mean_r * colsum_n) + bias_n
+  const float2* ln_stats; int ln_parts; long ln_stats_ld; int ln_row_mul, ln_row_off; const float* ln_colsum;
+  float2* stats_out;  // [2 * n_tiles][M] (sum, sum of squares) of the values written, per row
   long long* trace;  // null; microbenchmark only: clock64 timeline of CTA 0's producer / MMA / epilogue warps
 };
 
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;   // one 128-byte swizzle atom per row
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_EPI_WARPS = 4;
+constexpr int GEMM_THREADS = 320;
+constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 32 * 128;  // per epilogue warp: 32 rows x 128 B, 16-byte chunks XOR-swizzled
 
 template <int BLOCK_N, bool SPLIT>
@@ -176,11 +179,11 @@ struct GemmTile {
   static constexpr int W_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;       // [BLOCK_N rows][128 B]
   static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES) * (SPLIT ? 2 : 1);
   // one persistent CTA per SM: spend (almost) all of its shared memory on the TMA ring
-  static constexpr int BUDGET = 227 * 1024 - 1024 /* alignment slack */ - 1024 /* barriers */ - 2 * BLOCK_N * 4 /* bias */ - GEMM_STAGING_BYTES;
+  static constexpr int BUDGET = 227 * 1024 - 1024 /* alignment slack */ - 1024 /* barriers */ - GEMM_STAGING_BYTES;
   static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static_assert(STAGES >= 3, "tile does not leave room for a 3-stage ring");
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024 + 2 * BLOCK_N * 4 + GEMM_STAGING_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 1024 + GEMM_STAGING_BYTES;
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;   // one accumulator buffer
   static constexpr int TMEM_NEED = 2 * ACC_COLS;                 // double-buffered: epilogue(i) overlaps main loop(i+1)
   static constexpr int TMEM_COLS = TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;  // power of two
@@ -198,7 +201,11 @@ __device__ __forceinline__ float epi_act(float x, bool precise) {
 // n_tile = t / m_tiles, so the ~148 tiles in flight share few W tiles and each is fetched from HBM once).
 // EPI: EPI_NONE / TANH / GELU / RELU (bias + activation), EPI_RESIDUAL (out_f32 += result), EPI_ARGMAX (per-tile row argmax
 // partials; optional fp32 logits tap).
-template <int BLOCK_N, bool SPLIT, int EPI>
+// OUT (what the epilogue stores -- compile-time so that the per-element code of one instantiation is a handful of instructions):
+enum GemmOut { OUT_NONE = 0 /* argmax partials only */, OUT_F32 = 1, OUT_BF16 = 2, OUT_BF16X2 = 3 /* hi + lo */, OUT_F32_BF16_STATS = 4 /* fused residual:
+                fp32 stream + its bf16 copy + per-row (sum, sum of squares) partials for the LayerNorm folded into the next GEMM */ };
+// FOLD: LayerNorm folded into this GEMM (see GemmBf16Args::ln_stats).
+template <int BLOCK_N, bool SPLIT, int EPI, int OUT, bool FOLD>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKernelParams p) {
   using Tile = GemmTile<BLOCK_N, SPLIT>;
   constexpr int STAGES = Tile::STAGES;
@@ -213,8 +220,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   const uint32_t tmem_full_bar = empty_bar + 8 * STAGES;     // [2]
   const uint32_t tmem_empty_bar = tmem_full_bar + 16;        // [2]
   const uint32_t tmem_slot = tmem_empty_bar + 16;
-  float* s_bias = reinterpret_cast<float*>(smem_gen + OFF_BAR + 1024);                        // [2][BLOCK_N]
-  float4* s_stage = reinterpret_cast<float4*>(smem_gen + OFF_BAR + 1024 + 2 * BLOCK_N * 4);   // [4 warps][32 rows][8 chunks]
+  float4* s_stage = reinterpret_cast<float4*>(smem_gen + OFF_BAR + 1024);  // [8 warps][32 rows][8 chunks]
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
@@ -314,143 +320,391 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers (lane = row) -> swizzled staging tile -> coalesced global stores =====
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int et = (warp - 2) * 32 + lane;  // 0..127 over the four epilogue warps
-    float4* stage = s_stage + (warp - 2) * 256;  // this warp's [32 rows][8 x 16 B]
+    // ===== epilogue: TMEM -> registers (lane = row) -> swizzled staging tile -> "coalesced domain" (lane = 16-byte chunk
+    // (lane & 7) of rows (lane >> 3) + 4 i) where bias / folded LayerNorm / activation / residual / argmax / row statistics
+    // are applied and whole 128-byte row segments are stored.  8 warps: TMEM lane quarter = warp & 3, and the two warps
+    // of a quarter take alternate 32-column chunks. =====
+    const int e = warp - 2, q = warp & 3, sub = e >> 2;
+    float4* stage = s_stage + e * 256;  // this warp's [32 rows][8 x 16 B]
     const bool vec_f32 = (p.ld_f32 % 4 == 0), vec_bf16 = (p.ld_bf16 % 4 == 0);
-    // coalesced domain: lane handles 16-byte chunk (lane & 7) of rows (lane >> 3) + 4 * i
     const int cchunk = lane & 7, crow0 = lane >> 3;
+    constexpr bool fold = FOLD;
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const uint32_t acc = local & 1, use = local >> 1;
       const int n_tile = tile / m_tiles;
       const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
       const int wrow0 = m0 + q * 32;  // first row of this warp's 32-row band
-      float* bias_s = s_bias + acc * BLOCK_N;
-      for (int c = et; c < BLOCK_N; c += 128) bias_s[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-      ptx::mbar_wait(tmem_full_bar + 8 * acc, use & 1);
-      ptx::tc_fence_after();
-      if (tracing && et == 0 && local < 8) p.trace[512 + local * 4 + 1] = clock64() - t_start;
-      const uint32_t tmem_acc = tmem_base + acc * Tile::ACC_COLS + ((uint32_t)(q * 32) << 16);
-      float best = -INFINITY;
-      int best_idx = 0x7fffffff;
+      if (EPI == EPI_ARGMAX && OUT == OUT_NONE) {
+        // ---- LM head on the product path: argmax straight from the TMEM registers (lane = row), nothing is staged or stored.
+        // (the staging tile would add ~20 % to the shared-memory traffic that bounds this kernel's main loop) ----
+        const int row = wrow0 + lane;
+        float mu = 0.f, rs = 1.f;
+        if (FOLD) {
+          float sx = 0.f, sq = 0.f;
+          if (row < p.M)
+            for (int part = 0; part < p.ln_parts; ++part) {
+              const float2 t = __ldcg(p.ln_stats + (size_t)part * p.ln_stats_ld + (size_t)row * p.ln_row_mul + p.ln_row_off);
+              sx += t.x;
+              sq += t.y;
+            }
+          const float inv_k = 1.0f / (float)p.K;
+          mu = sx * inv_k;
+          rs = rsqrtf(fmaxf(sq * inv_k - mu * mu, 0.f) + 1e-5f);
+        }
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        ptx::mbar_wait(tmem_full_bar + 8 * acc, use & 1);
+        ptx::tc_fence_after();
+        if (tracing && e == 0 && lane == 0 && local < 8) p.trace[512 + local * 4 + 1] = clock64() - t_start;
+        const uint32_t tmem_row = tmem_base + acc * Tile::ACC_COLS + ((uint32_t)(q * 32) << 16);
+        if (sub * 32 >= BLOCK_N) {
+          ptx::tc_fence_before();
+          if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
+        }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        const int col0 = n0 + c0;
-        // residual values of this chunk, fetched in the coalesced layout before the accumulator is touched
-        float4 res[8];
-        if (EPI == EPI_RESIDUAL && col0 < p.N) {
+        for (int c0 = sub * 32; c0 < BLOCK_N; c0 += 64) {
+          const int col0 = n0 + c0;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_row + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          if (c0 + 64 >= BLOCK_N) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
+          }
+          if (col0 >= p.N) continue;  // warp-uniform
+          const bool whole = col0 + 32 <= p.N;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = wrow0 + crow0 + 4 * i, col = col0 + cchunk * 4;
-            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < p.M) {
-              const float* src = p.out_f32 + (size_t)row * p.ld_f32 + col;
-              if (vec_f32 && col + 3 < p.N) res[i] = __ldcg(reinterpret_cast<const float4*>(src));
-              else {
-                if (col < p.N) res[i].x = __ldcg(src);
-                if (col + 1 < p.N) res[i].y = __ldcg(src + 1);
-                if (col + 2 < p.N) res[i].z = __ldcg(src + 2);
-                if (col + 3 < p.N) res[i].w = __ldcg(src + 3);
+          for (int c = 0; c < 8; ++c) {
+            // warp-uniform addresses: one broadcast transaction each
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int col = col0 + 4 * c;
+            if (whole) {
+              if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+              if (FOLD) cs4 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col));
+            } else {
+              if (p.bias) {
+                if (col < p.N) b4.x = __ldg(p.bias + col);
+                if (col + 1 < p.N) b4.y = __ldg(p.bias + col + 1);
+                if (col + 2 < p.N) b4.z = __ldg(p.bias + col + 2);
+                if (col + 3 < p.N) b4.w = __ldg(p.bias + col + 3);
+              }
+              if (FOLD) {
+                if (col < p.N) cs4.x = __ldg(p.ln_colsum + col);
+                if (col + 1 < p.N) cs4.y = __ldg(p.ln_colsum + col + 1);
+                if (col + 2 < p.N) cs4.z = __ldg(p.ln_colsum + col + 2);
+                if (col + 3 < p.N) cs4.w = __ldg(p.ln_colsum + col + 3);
+              }
+            }
+            float v0 = __uint_as_float(r[4 * c]), v1 = __uint_as_float(r[4 * c + 1]), v2 = __uint_as_float(r[4 * c + 2]), v3 = __uint_as_float(r[4 * c + 3]);
+            if (FOLD) {
+              v0 = rs * (v0 - mu * cs4.x); v1 = rs * (v1 - mu * cs4.y); v2 = rs * (v2 - mu * cs4.z); v3 = rs * (v3 - mu * cs4.w);
+            }
+            v0 += b4.x; v1 += b4.y; v2 += b4.z; v3 += b4.w;
+            // columns in increasing order with strict > : the lowest index among equal maxima survives
+            bool g;
+            g = (whole || col < p.N) && v0 > bv; bv = g ? v0 : bv; bi = g ? col : bi;
+            g = (whole || col + 1 < p.N) && v1 > bv; bv = g ? v1 : bv; bi = g ? col + 1 : bi;
+            g = (whole || col + 2 < p.N) && v2 > bv; bv = g ? v2 : bv; bi = g ? col + 2 : bi;
+            g = (whole || col + 3 < p.N) && v3 > bv; bv = g ? v3 : bv; bi = g ? col + 3 : bi;
+          }
+        }
+        if (row < p.M) {
+          const size_t slot = (size_t)(n_tile * 2 + sub) * p.M + row;
+          p.part_val[slot] = bv;
+          p.part_idx[slot] = bi;
+        }
+        if (tracing && e == 0 && lane == 0 && local < 8) p.trace[512 + local * 4 + 2] = clock64() - t_start;
+        continue;
+      }
+      // folded LayerNorm: per-row mean / rstd of the A operand from the producer's per-tile partial sums (sum, sum of squares)
+      float mean[8], rstd[8];
+      if (fold) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = wrow0 + crow0 + 4 * i;
+          float sx = 0.f, sq = 0.f;
+          if (row < p.M)
+            for (int part = cchunk; part < p.ln_parts; part += 8) {
+              const float2 t = __ldcg(p.ln_stats + (size_t)part * p.ln_stats_ld + (size_t)row * p.ln_row_mul + p.ln_row_off);
+              sx += t.x;
+              sq += t.y;
+            }
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            sx += __shfl_xor_sync(0xffffffffu, sx, o);
+            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          }
+          const float inv_k = 1.0f / (float)p.K;
+          const float mu = sx * inv_k;
+          mean[i] = mu;
+          rstd[i] = rsqrtf(fmaxf(sq * inv_k - mu * mu, 0.f) + 1e-5f);
+        }
+      }
+      float rsum[8], rsq[8], best[8];
+      int bidx[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { rsum[i] = 0.f; rsq[i] = 0.f; best[i] = -INFINITY; bidx[i] = 0x7fffffff; }
+      // operands of a chunk that do not depend on the accumulator (residual in the coalesced layout, bias, column sums) are
+      // requested one chunk ahead: the first chunk's before the accumulator wait, chunk c+1's while chunk c is processed
+      float4 res_n[8], b4_n = make_float4(0.f, 0.f, 0.f, 0.f), cs4_n = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto prefetch = [&](int c0) {
+        const int col0 = n0 + c0, col = col0 + cchunk * 4;
+        b4_n = make_float4(0.f, 0.f, 0.f, 0.f);
+        cs4_n = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col0 >= p.N) return;
+        if ((col0 + 32 <= p.N) && vec_f32 && vec_bf16) {
+          if (EPI == EPI_RESIDUAL) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = min(wrow0 + crow0 + 4 * i, p.M - 1);  // clamped: rows >= M are never stored
+              res_n[i] = __ldcg(reinterpret_cast<const float4*>(p.out_f32 + (size_t)row * p.ld_f32 + col));
+            }
+          }
+          if (p.bias) b4_n = __ldg(reinterpret_cast<const float4*>(p.bias + col));  // col is a multiple of 4: 16-byte aligned
+          if (FOLD) cs4_n = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col));
+        } else {
+          if (EPI == EPI_RESIDUAL) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = wrow0 + crow0 + 4 * i;
+              res_n[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (row < p.M) {
+                const float* src = p.out_f32 + (size_t)row * p.ld_f32 + col;
+                if (col < p.N) res_n[i].x = __ldcg(src);
+                if (col + 1 < p.N) res_n[i].y = __ldcg(src + 1);
+                if (col + 2 < p.N) res_n[i].z = __ldcg(src + 2);
+                if (col + 3 < p.N) res_n[i].w = __ldcg(src + 3);
               }
             }
           }
+          if (p.bias) {
+            if (col < p.N) b4_n.x = __ldg(p.bias + col);
+            if (col + 1 < p.N) b4_n.y = __ldg(p.bias + col + 1);
+            if (col + 2 < p.N) b4_n.z = __ldg(p.bias + col + 2);
+            if (col + 3 < p.N) b4_n.w = __ldg(p.bias + col + 3);
+          }
+          if (FOLD) {
+            if (col < p.N) cs4_n.x = __ldg(p.ln_colsum + col);
+            if (col + 1 < p.N) cs4_n.y = __ldg(p.ln_colsum + col + 1);
+            if (col + 2 < p.N) cs4_n.z = __ldg(p.ln_colsum + col + 2);
+            if (col + 3 < p.N) cs4_n.w = __ldg(p.ln_colsum + col + 3);
+          }
         }
+      };
+      if (sub * 32 < BLOCK_N) prefetch(sub * 32);
+      ptx::mbar_wait(tmem_full_bar + 8 * acc, use & 1);
+      ptx::tc_fence_after();
+      if (tracing && e == 0 && lane == 0 && local < 8) p.trace[512 + local * 4 + 1] = clock64() - t_start;
+      const uint32_t tmem_acc = tmem_base + acc * Tile::ACC_COLS + ((uint32_t)(q * 32) << 16);
+      if (sub * 32 >= BLOCK_N) {  // BLOCK_N == 32: the second warp of the quarter has no chunk, it only releases the accumulator
+        ptx::tc_fence_before();
+        if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
+      }
+#pragma unroll 1
+      for (int c0 = sub * 32; c0 < BLOCK_N; c0 += 64) {
+        const int col0 = n0 + c0, col = col0 + cchunk * 4;
+        const bool tr = tracing && e == 0 && lane == 0 && local == 0 && c0 < 128;
+        long long* trc = p.trace + 540 + (c0 >> 6) * 8;
+        if (tr) trc[0] = clock64() - t_start;
+        // whole chunk inside the matrix and every row pointer 16-byte aligned: the specialised path below
+        const bool fast = (col0 + 32 <= p.N) && vec_f32 && vec_bf16;
+        float4 res[8];
+        if (EPI == EPI_RESIDUAL) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) res[i] = res_n[i];
+        }
+        const float4 b4 = b4_n, cs4 = cs4_n;
+        if (c0 + 64 < BLOCK_N) prefetch(c0 + 64);
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_acc + (uint32_t)c0, r);
         ptx::tmem_ld_wait();
-        if (c0 + 32 >= BLOCK_N) {
-          // last TMEM read of this tile: hand the accumulator back to the MMA warp before doing the math / stores
+        if (tr) trc[1] = clock64() - t_start;
+        if (c0 + 64 >= BLOCK_N) {
+          // this warp's last TMEM read of the tile: hand the accumulator back to the MMA warp before the math / stores
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
         }
         if (col0 >= p.N) continue;  // warp-uniform
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = epi_act<EPI>(__uint_as_float(r[j]) + bias_s[c0 + j], SPLIT);
-        if (EPI == EPI_ARGMAX) {
-          if (col0 + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const bool gt = v[j] > best;  // strict > keeps the lowest index among equal maxima
-              best = gt ? v[j] : best;
-              best_idx = gt ? col0 + j : best_idx;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const bool gt = (col0 + j < p.N) && v[j] > best;
-              best = gt ? v[j] : best;
-              best_idx = gt ? col0 + j : best_idx;
-            }
-          }
-          if (p.out_f32 == nullptr) continue;  // product path: logits never reach HBM
-        }
         // lane = row  ->  staging tile (chunk position XOR row keeps both directions bank-conflict free)
         __syncwarp();  // previous chunk's readers are done with the staging tile
 #pragma unroll
-        for (int c = 0; c < 8; ++c) stage[lane * 8 + (c ^ (lane & 7))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        for (int c = 0; c < 8; ++c)
+          stage[lane * 8 + (c ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
+                                                           __uint_as_float(r[4 * c + 3]));
         __syncwarp();
+        if (tr) trc[2] = clock64() - t_start;
+        if (fast) {
+          // ---- specialised path: OUT / EPI / FOLD are compile-time, so this is a few instructions per element ----
+          if (tr) trc[3] = clock64() - t_start + (long long)(b4.x * 0.f);
+          const size_t rowoff = (size_t)(wrow0 + crow0);
+          float* pf = (OUT == OUT_F32 || OUT == OUT_F32_BF16_STATS) ? p.out_f32 + rowoff * p.ld_f32 + col : nullptr;
+          bf16* ph = (OUT == OUT_BF16 || OUT == OUT_BF16X2 || OUT == OUT_F32_BF16_STATS) ? p.out_hi + rowoff * p.ld_bf16 + col : nullptr;
+          bf16* pl = (OUT == OUT_BF16X2) ? p.out_lo + rowoff * p.ld_bf16 + col : nullptr;
+          const size_t step_f32 = (size_t)4 * p.ld_f32, step_bf = (size_t)4 * p.ld_bf16;
+          // three separate passes (load, math, store) so that the eight rows overlap instead of running as eight dependent
+          // load -> add -> convert -> store chains
+          float4 o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int lr = crow0 + 4 * i, row = wrow0 + lr, col = col0 + cchunk * 4;
-          float4 o = stage[lr * 8 + (cchunk ^ (lr & 7))];
-          if (row >= p.M || col >= p.N) continue;
-          if (EPI == EPI_RESIDUAL) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
+          for (int i = 0; i < 8; ++i) {
+            const int lr = crow0 + 4 * i;
+            o[i] = stage[lr * 8 + (cchunk ^ (lr & 7))];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (FOLD) {
+              o[i].x = rstd[i] * (o[i].x - mean[i] * cs4.x);
+              o[i].y = rstd[i] * (o[i].y - mean[i] * cs4.y);
+              o[i].z = rstd[i] * (o[i].z - mean[i] * cs4.z);
+              o[i].w = rstd[i] * (o[i].w - mean[i] * cs4.w);
+            }
+            o[i].x = epi_act<EPI>(o[i].x + b4.x, SPLIT);
+            o[i].y = epi_act<EPI>(o[i].y + b4.y, SPLIT);
+            o[i].z = epi_act<EPI>(o[i].z + b4.z, SPLIT);
+            o[i].w = epi_act<EPI>(o[i].w + b4.w, SPLIT);
+            if (EPI == EPI_RESIDUAL) { o[i].x += res[i].x; o[i].y += res[i].y; o[i].z += res[i].z; o[i].w += res[i].w; }
+          }
+          // rows of this warp's band that exist: all 32 unless this is the ragged last row tile (warp-uniform count)
+          const int rows_here = min(32, p.M - wrow0);
+          if (EPI == EPI_ARGMAX) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              // columns in increasing order with strict > : the lowest index among equal maxima survives
+              float bv = best[i];
+              int bi = bidx[i];
+              bool g;
+              g = o[i].x > bv; bv = g ? o[i].x : bv; bi = g ? col : bi;
+              g = o[i].y > bv; bv = g ? o[i].y : bv; bi = g ? col + 1 : bi;
+              g = o[i].z > bv; bv = g ? o[i].z : bv; bi = g ? col + 2 : bi;
+              g = o[i].w > bv; bv = g ? o[i].w : bv; bi = g ? col + 3 : bi;
+              const bool row_ok = crow0 + 4 * i < rows_here;
+              best[i] = row_ok ? bv : best[i];
+              bidx[i] = row_ok ? bi : bidx[i];
+            }
+          }
+          uint2 pkh[8], pkl[8];
+          if (OUT == OUT_BF16 || OUT == OUT_BF16X2 || OUT == OUT_F32_BF16_STATS) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(o[i].x, o[i].y), h23 = __floats2bfloat162_rn(o[i].z, o[i].w);
+              pkh[i].x = *reinterpret_cast<const uint32_t*>(&h01);
+              pkh[i].y = *reinterpret_cast<const uint32_t*>(&h23);
+              if (OUT == OUT_BF16X2 || OUT == OUT_F32_BF16_STATS) {
+                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                if (OUT == OUT_BF16X2) {
+                  const __nv_bfloat162 l01 = __floats2bfloat162_rn(o[i].x - f01.x, o[i].y - f01.y), l23 = __floats2bfloat162_rn(o[i].z - f23.x, o[i].w - f23.y);
+                  pkl[i].x = *reinterpret_cast<const uint32_t*>(&l01);
+                  pkl[i].y = *reinterpret_cast<const uint32_t*>(&l23);
+                } else {
+                  // row statistics over the values the next GEMM will actually read: the bf16 roundings
+                  const bool row_ok = crow0 + 4 * i < rows_here;
+                  const float ds = (f01.x + f01.y) + (f23.x + f23.y), dq = (f01.x * f01.x + f01.y * f01.y) + (f23.x * f23.x + f23.y * f23.y);
+                  rsum[i] += row_ok ? ds : 0.f;
+                  rsq[i] += row_ok ? dq : 0.f;
+                }
+              }
+            }
+          }
+          if (rows_here == 32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (OUT == OUT_F32 || OUT == OUT_F32_BF16_STATS) *reinterpret_cast<float4*>(pf + i * step_f32) = o[i];
+              if (OUT == OUT_BF16 || OUT == OUT_BF16X2 || OUT == OUT_F32_BF16_STATS) *reinterpret_cast<uint2*>(ph + i * step_bf) = pkh[i];
+              if (OUT == OUT_BF16X2) *reinterpret_cast<uint2*>(pl + i * step_bf) = pkl[i];
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (crow0 + 4 * i < rows_here) {
+                if (OUT == OUT_F32 || OUT == OUT_F32_BF16_STATS) *reinterpret_cast<float4*>(pf + i * step_f32) = o[i];
+                if (OUT == OUT_BF16 || OUT == OUT_BF16X2 || OUT == OUT_F32_BF16_STATS) *reinterpret_cast<uint2*>(ph + i * step_bf) = pkh[i];
+                if (OUT == OUT_BF16X2) *reinterpret_cast<uint2*>(pl + i * step_bf) = pkl[i];
+              }
+            }
+          }
+        } else {
+          // ---- generic path: ragged right edge (col0 + 32 > N) or unaligned leading dimensions ----
           const bool full4 = col + 3 < p.N;
-          if (p.out_f32) {
-            float* dst = p.out_f32 + (size_t)row * p.ld_f32 + col;
-            if (vec_f32 && full4) *reinterpret_cast<float4*>(dst) = o;
-            else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int lr = crow0 + 4 * i, row = wrow0 + lr;
+            float4 o = stage[lr * 8 + (cchunk ^ (lr & 7))];
+            if (fold) {
+              o.x = rstd[i] * (o.x - mean[i] * cs4.x);
+              o.y = rstd[i] * (o.y - mean[i] * cs4.y);
+              o.z = rstd[i] * (o.z - mean[i] * cs4.z);
+              o.w = rstd[i] * (o.w - mean[i] * cs4.w);
+            }
+            o.x = epi_act<EPI>(o.x + b4.x, SPLIT);
+            o.y = epi_act<EPI>(o.y + b4.y, SPLIT);
+            o.z = epi_act<EPI>(o.z + b4.z, SPLIT);
+            o.w = epi_act<EPI>(o.w + b4.w, SPLIT);
+            if (row >= p.M || col >= p.N) continue;
+            if (EPI == EPI_RESIDUAL) { o.x += res[i].x; o.y += res[i].y; o.z += res[i].z; o.w += res[i].w; }
+            if (EPI == EPI_ARGMAX) {
+              if (o.x > best[i]) { best[i] = o.x; bidx[i] = col; }
+              if (col + 1 < p.N && o.y > best[i]) { best[i] = o.y; bidx[i] = col + 1; }
+              if (col + 2 < p.N && o.z > best[i]) { best[i] = o.z; bidx[i] = col + 2; }
+              if (col + 3 < p.N && o.w > best[i]) { best[i] = o.w; bidx[i] = col + 3; }
+            }
+            if (p.out_f32) {
+              float* dst = p.out_f32 + (size_t)row * p.ld_f32 + col;
               dst[0] = o.x;
               if (col + 1 < p.N) dst[1] = o.y;
               if (col + 2 < p.N) dst[2] = o.z;
               if (col + 3 < p.N) dst[3] = o.w;
             }
-          }
-          if (p.out_hi) {
-            const __nv_bfloat162 h01 = __floats2bfloat162_rn(o.x, o.y), h23 = __floats2bfloat162_rn(o.z, o.w);
-            bf16* dh = p.out_hi + (size_t)row * p.ld_bf16 + col;
-            __nv_bfloat162 l01 = h01, l23 = h23;
-            if (p.out_lo) {
-              const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-              l01 = __floats2bfloat162_rn(o.x - f01.x, o.y - f01.y);
-              l23 = __floats2bfloat162_rn(o.z - f23.x, o.w - f23.y);
-            }
-            bf16* dl = p.out_lo ? p.out_lo + (size_t)row * p.ld_bf16 + col : nullptr;
-            if (vec_bf16 && full4) {
-              uint2 pk;
-              pk.x = *reinterpret_cast<const uint32_t*>(&h01);
-              pk.y = *reinterpret_cast<const uint32_t*>(&h23);
-              *reinterpret_cast<uint2*>(dh) = pk;
-              if (dl) {
-                pk.x = *reinterpret_cast<const uint32_t*>(&l01);
-                pk.y = *reinterpret_cast<const uint32_t*>(&l23);
-                *reinterpret_cast<uint2*>(dl) = pk;
-              }
-            } else {
-              const bf16 hv[4] = {h01.x, h01.y, h23.x, h23.y};
-              const bf16 lv[4] = {l01.x, l01.y, l23.x, l23.y};
+            float sv[4] = {o.x, o.y, o.z, o.w};
+            if (p.out_hi) {
+              bf16* dh = p.out_hi + (size_t)row * p.ld_bf16 + col;
+              bf16* dl = p.out_lo ? p.out_lo + (size_t)row * p.ld_bf16 + col : nullptr;
               for (int t = 0; t < 4; ++t)
                 if (col + t < p.N) {
-                  dh[t] = hv[t];
-                  if (dl) dl[t] = lv[t];
+                  const bf16 hb = __float2bfloat16_rn(sv[t]);
+                  dh[t] = hb;
+                  if (dl) dl[t] = __float2bfloat16_rn(sv[t] - __bfloat162float(hb));
+                  else sv[t] = __bfloat162float(hb);
                 }
             }
+            if (OUT == OUT_F32_BF16_STATS) {
+              for (int t = 0; t < 4; ++t)
+                if (col + t < p.N) { rsum[i] += sv[t]; rsq[i] += sv[t] * sv[t]; }
+            }
+            (void)full4;
+          }
+        }
+        if (tr) trc[4] = clock64() - t_start;
+      }
+      // per-(tile, column-parity) partials of each row: argmax pair and / or (sum, sum of squares)
+      if (EPI == EPI_ARGMAX || OUT == OUT_F32_BF16_STATS) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            if (EPI == EPI_ARGMAX) {
+              const float ov = __shfl_xor_sync(0xffffffffu, best[i], o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bidx[i], o);
+              if (ov > best[i] || (ov == best[i] && oi < bidx[i])) { best[i] = ov; bidx[i] = oi; }
+            }
+            if (OUT == OUT_F32_BF16_STATS) {
+              rsum[i] += __shfl_xor_sync(0xffffffffu, rsum[i], o);
+              rsq[i] += __shfl_xor_sync(0xffffffffu, rsq[i], o);
+            }
+          }
+          const int row = wrow0 + crow0 + 4 * i;
+          if (cchunk == 0 && row < p.M) {
+            const size_t slot = (size_t)(n_tile * 2 + sub) * p.M + row;
+            if (EPI == EPI_ARGMAX) {
+              p.part_val[slot] = best[i];
+              p.part_idx[slot] = bidx[i];
+            }
+            if (OUT == OUT_F32_BF16_STATS) p.stats_out[slot] = make_float2(rsum[i], rsq[i]);
           }
         }
       }
-      if (EPI == EPI_ARGMAX) {
-        const int row = wrow0 + lane;
-        if (row < p.M) {
-          p.part_val[(size_t)n_tile * p.M + row] = best;
-          p.part_idx[(size_t)n_tile * p.M + row] = best_idx;
-        }
-      }
-      if (tracing && et == 0 && local < 8) p.trace[512 + local * 4 + 2] = clock64() - t_start;
+      if (tracing && e == 0 && lane == 0 && local < 8) p.trace[512 + local * 4 + 2] = clock64() - t_start;
     }
   }
 
@@ -528,20 +782,24 @@ static int gemm_num_sms() {
   return sms;
 }
 
-template <int BLOCK_N, bool SPLIT, int EPI>
-static int configure_one() {
-  GIC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      GemmTile<BLOCK_N, SPLIT>::SMEM_BYTES));
-  return GIC_OK;
-}
+// The instantiated (EPI, OUT, FOLD) variants; anything else is refused by launch_gemm_bf16.
+#define GIC_GEMM_VARIANTS_COMMON(X) \
+  X(EPI_NONE, OUT_F32, false) X(EPI_TANH, OUT_F32, false) X(EPI_GELU, OUT_F32, false) X(EPI_RELU, OUT_F32, false) \
+  X(EPI_RESIDUAL, OUT_F32, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_ARGMAX, OUT_F32, false)
+#define GIC_GEMM_VARIANTS_BF16(X) \
+  X(EPI_NONE, OUT_BF16, false) X(EPI_NONE, OUT_BF16, true) X(EPI_TANH, OUT_BF16, false) X(EPI_GELU, OUT_BF16, false) \
+  X(EPI_GELU, OUT_BF16, true) X(EPI_RELU, OUT_BF16, false) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false) \
+  X(EPI_ARGMAX, OUT_NONE, true) X(EPI_ARGMAX, OUT_F32, true)
+#define GIC_GEMM_VARIANTS_SPLIT(X) X(EPI_NONE, OUT_BF16X2, false) X(EPI_TANH, OUT_BF16X2, false) X(EPI_GELU, OUT_BF16X2, false) X(EPI_RELU, OUT_BF16X2, false)
+
 template <int BLOCK_N, bool SPLIT>
 static int configure_cfg() {
-  GIC_TRY((configure_one<BLOCK_N, SPLIT, EPI_NONE>()));
-  GIC_TRY((configure_one<BLOCK_N, SPLIT, EPI_TANH>()));
-  GIC_TRY((configure_one<BLOCK_N, SPLIT, EPI_GELU>()));
-  GIC_TRY((configure_one<BLOCK_N, SPLIT, EPI_RELU>()));
-  GIC_TRY((configure_one<BLOCK_N, SPLIT, EPI_RESIDUAL>()));
-  GIC_TRY((configure_one<BLOCK_N, SPLIT, EPI_ARGMAX>()));
+#define X(E, O, F)                                                                                                                \
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, E, O, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      GemmTile<BLOCK_N, SPLIT>::SMEM_BYTES));
+  GIC_GEMM_VARIANTS_COMMON(X)
+  if (SPLIT) { GIC_GEMM_VARIANTS_SPLIT(X) } else { GIC_GEMM_VARIANTS_BF16(X) }
+#undef X
   return GIC_OK;
 }
 
@@ -560,10 +818,10 @@ int gemm_bf16_configure() {
   return GIC_OK;
 }
 
-template <int BLOCK_N, bool SPLIT, int EPI>
+template <int BLOCK_N, bool SPLIT, int EPI, int OUT, bool FOLD>
 static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
   using Tile = GemmTile<BLOCK_N, SPLIT>;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, EPI>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, EPI, OUT, FOLD>;
   const long tiles = (long)ceil_div(kp.M, GEMM_BLOCK_M) * ceil_div(kp.N, BLOCK_N);
   const int sms = gemm_num_sms();
   dim3 grid((unsigned)(tiles < sms ? tiles : sms));  // persistent: one CTA per SM
@@ -573,17 +831,14 @@ static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
 }
 
 template <int BLOCK_N, bool SPLIT>
-static int launch_cfg(const GemmKernelParams& kp, int epi, cudaStream_t st) {
-  switch (epi) {
-    case EPI_NONE: return launch_one<BLOCK_N, SPLIT, EPI_NONE>(kp, st);
-    case EPI_TANH: return launch_one<BLOCK_N, SPLIT, EPI_TANH>(kp, st);
-    case EPI_GELU: return launch_one<BLOCK_N, SPLIT, EPI_GELU>(kp, st);
-    case EPI_RELU: return launch_one<BLOCK_N, SPLIT, EPI_RELU>(kp, st);
-    case EPI_RESIDUAL: return launch_one<BLOCK_N, SPLIT, EPI_RESIDUAL>(kp, st);
-    case EPI_ARGMAX: return launch_one<BLOCK_N, SPLIT, EPI_ARGMAX>(kp, st);
-  }
-  set_error("gemm_bf16: unknown epilogue %d", epi);
-  return GIC_ERR_INVALID;
+static int launch_cfg(const GemmKernelParams& kp, int epi, int out, bool fold, cudaStream_t st) {
+#define X(E, O, F) \
+  if (epi == E && out == O && fold == F) return launch_one<BLOCK_N, SPLIT, E, O, F>(kp, st);
+  GIC_GEMM_VARIANTS_COMMON(X)
+  if (SPLIT) { GIC_GEMM_VARIANTS_SPLIT(X) } else { GIC_GEMM_VARIANTS_BF16(X) }
+#undef X
+  set_error("gemm_bf16: no kernel for epilogue %d with output mode %d%s%s", epi, out, fold ? " + folded LayerNorm" : "", SPLIT ? " (bf16x2)" : "");
+  return GIC_ERR_UNSUPPORTED;
 }
 
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
@@ -595,24 +850,40 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   kp.mma_repeat = a.mma_repeat < 1 ? 1 : a.mma_repeat;
   kp.out_f32 = a.out.f32; kp.ld_f32 = a.ld_out; kp.out_hi = a.out.hi; kp.out_lo = a.out.lo; kp.ld_bf16 = a.ld_out;
   kp.part_val = a.part_val; kp.part_idx = a.part_idx; kp.trace = a.trace;
+  kp.ln_stats = a.ln_stats; kp.ln_parts = a.ln_parts; kp.ln_stats_ld = a.ln_stats_ld; kp.ln_row_mul = a.ln_row_mul; kp.ln_row_off = a.ln_row_off;
+  kp.ln_colsum = a.ln_colsum; kp.stats_out = a.stats_out;
+  GIC_REQUIRE(!a.ln_stats || (a.ln_colsum && a.ln_parts > 0), "gemm_bf16: folded LayerNorm needs the column sums and at least one statistics part");
   int epi = a.epilogue;
   if (a.part_val) {
     GIC_REQUIRE(a.epilogue == EPI_NONE && a.part_idx, "gemm_bf16: the fused argmax takes no activation and needs both partial buffers");
     epi = EPI_ARGMAX;
   }
   GIC_REQUIRE(!(epi == EPI_RESIDUAL && !a.out.f32), "gemm_bf16: residual epilogue needs the fp32 output");
+  const bool fold = a.ln_stats != nullptr;
+  int out = OUT_NONE;
+  if (a.stats_out) {
+    GIC_REQUIRE(epi == EPI_RESIDUAL && a.out.f32 && a.out.hi && !a.out.lo, "gemm_bf16: row statistics come with the fused residual epilogue (fp32 + bf16 outputs)");
+    out = OUT_F32_BF16_STATS;
+  } else if (a.out.f32) {
+    GIC_REQUIRE(!a.out.hi && !a.out.lo, "gemm_bf16: fp32 and bf16 outputs together only in the fused residual epilogue");
+    out = OUT_F32;
+  } else if (a.out.hi) {
+    out = a.out.lo ? OUT_BF16X2 : OUT_BF16;
+  } else {
+    GIC_REQUIRE(epi == EPI_ARGMAX, "gemm_bf16: no output buffer");
+  }
   if (a.split) {
     switch (a.block_n) {
-      case 32: return launch_cfg<32, true>(kp, epi, st);
-      case 64: return launch_cfg<64, true>(kp, epi, st);
+      case 32: return launch_cfg<32, true>(kp, epi, out, fold, st);
+      case 64: return launch_cfg<64, true>(kp, epi, out, fold, st);
     }
   } else {
     switch (a.block_n) {
-      case 32: return launch_cfg<32, false>(kp, epi, st);
-      case 64: return launch_cfg<64, false>(kp, epi, st);
-      case 128: return launch_cfg<128, false>(kp, epi, st);
-      case 192: return launch_cfg<192, false>(kp, epi, st);
-      case 256: return launch_cfg<256, false>(kp, epi, st);
+      case 32: return launch_cfg<32, false>(kp, epi, out, fold, st);
+      case 64: return launch_cfg<64, false>(kp, epi, out, fold, st);
+      case 128: return launch_cfg<128, false>(kp, epi, out, fold, st);
+      case 192: return launch_cfg<192, false>(kp, epi, out, fold, st);
+      case 256: return launch_cfg<256, false>(kp, epi, out, fold, st);
     }
   }
   set_error("gemm_bf16: unsupported block_n %d", a.block_n);

@@ -43,8 +43,14 @@ struct GemmBf16Args {
   const float* bias = nullptr;     // [N] or null
   ActOut out;                      // fp32 (EPI_RESIDUAL: in-place +=) and/or bf16 hi/lo, row stride ld_out
   int ld_out = 0;
-  float* part_val = nullptr;       // fused LM-head argmax: [n_tiles][M] best value ...
+  float* part_val = nullptr;       // fused LM-head argmax: [2 * n_tiles][M] best value ...
   int* part_idx = nullptr;         // ... and its lowest column index (cols >= N masked)
+  // LayerNorm folded into the GEMM (A holds the RAW rows x, W was packed as gamma_k * W[n,k], bias as b_n + sum_k beta_k W[n,k]):
+  //   out[r,n] = rstd_r * (acc[r,n] - mean_r * ln_colsum[n]) + bias[n],   mean / rstd from sum_parts ln_stats[part][r * mul + off]
+  const float2* ln_stats = nullptr;  // [ln_parts][ln_stats_ld] (sum x, sum x^2) partials written by the producer of A
+  int ln_parts = 0; long ln_stats_ld = 0; int ln_row_mul = 1, ln_row_off = 0;
+  const float* ln_colsum = nullptr;  // [N] sum_k of the packed (bf16) gamma-folded weights
+  float2* stats_out = nullptr;       // [2 * n_tiles][M]: per-row (sum, sum of squares) of the values this GEMM writes, per tile half
   long long* trace = nullptr;      // microbenchmark only: device buffer of >= 640 int64 for CTA 0's clock64 timeline
 };
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st);

@@ -177,6 +177,9 @@ int main(int argc, char** argv) {
                h_tr[256 + kb * 4 + 1], h_tr[256 + kb * 4 + 2]);
       for (int t = 0; t < (sh.lm ? 3 : 1); ++t)
         printf("  epilogue tile %d: wait_begin %lld  accumulator_seen %lld  done %lld\n", t, h_tr[512 + t * 4], h_tr[512 + t * 4 + 1], h_tr[512 + t * 4 + 2]);
+      for (int c = 0; c < 2; ++c)
+        printf("  epilogue warp 0 chunk %d: begin %lld  tmem_loaded %lld  staged %lld  bias_loaded %lld  stored %lld\n", c, h_tr[540 + c * 8], h_tr[541 + c * 8],
+               h_tr[542 + c * 8], h_tr[543 + c * 8], h_tr[544 + c * 8]);
     }
     return 0;
   }
