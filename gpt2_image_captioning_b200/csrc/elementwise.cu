@@ -64,12 +64,13 @@ int launch_layernorm(const float* x, long x_row_stride, const float* w, const fl
 // HF Conv1D weights are [in,out]; every GEMM here wants W as [N,K] K-major, so Conv1D weights are transposed once.
 // 32x32 smem tile transpose, coalesced on both sides.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void pack_weight_kernel(const float* __restrict__ in, int R, int C, bool transpose, ActOut out) {
+__global__ void pack_weight_kernel(const float* __restrict__ in, int R, int C, bool transpose, ActOut out, const float* __restrict__ scale_k) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * C + c] : 0.f;
+    // k (the in-feature index the LayerNorm gamma scales) is the source ROW when the weight is transposed, else the column
+    tile[i][threadIdx.x] = (r < R && c < C) ? in[(size_t)r * C + c] * (scale_k ? scale_k[transpose ? r : c] : 1.0f) : 0.f;
   }
   __syncthreads();
   if (!transpose) {
@@ -85,11 +86,84 @@ __global__ void pack_weight_kernel(const float* __restrict__ in, int R, int C, b
   }
 }
 
-int launch_pack_weight(const float* in, int R, int C, bool transpose, ActOut out, cudaStream_t st) {
+int launch_pack_weight(const float* in, int R, int C, bool transpose, ActOut out, cudaStream_t st, const float* scale_k) {
   dim3 grid(ceil_div(C, 32), ceil_div(R, 32)), block(32, 8);
   GIC_REQUIRE(grid.y <= 65535, "pack_weight: too many rows (%d)", R);
-  pack_weight_kernel<<<grid, block, 0, st>>>(in, R, C, transpose, out);
+  pack_weight_kernel<<<grid, block, 0, st>>>(in, R, C, transpose, out, scale_k);
   GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return GIC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LayerNorm folded into the following GEMM (bf16 engine, decode + prefill):
+//   LN(x) . W^T + b = rstd * (x . (gamma * W)^T - mean * colsum) + (b + W . beta),   colsum[n] = sum_k gamma_k W[n,k]
+// The GEMM consumes the RAW rows (bf16 copy of the residual stream) and applies mean / rstd per row in its epilogue, so the
+// 25 LayerNorm launches of a decode step disappear (HF GPT2Block ln_1 / ln_2 and ln_f, HF:models/gpt2/modeling_gpt2.py:273,304,628).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) fold_ln_kernel(const bf16* __restrict__ w_packed, const float* __restrict__ w_src, bool transposed,
+                                                      const float* __restrict__ beta, const float* __restrict__ bias, float* __restrict__ colsum,
+                                                      float* __restrict__ bias_out, int N, int K) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float cs = 0.f, bs = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    cs += __bfloat162float(w_packed[(size_t)n * K + k]);  // what the tensor core will really multiply by
+    bs += beta[k] * (transposed ? w_src[(size_t)k * N + n] : w_src[(size_t)n * K + k]);
+  }
+  cs = warp_sum(cs);
+  bs = warp_sum(bs);
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_out[n] = (bias ? bias[n] : 0.f) + bs;
+  }
+}
+
+int launch_fold_ln(const bf16* w_packed, const float* w_src, bool transposed, const float* beta, const float* bias, float* colsum,
+                   float* bias_out, int N, int K, cudaStream_t st) {
+  fold_ln_kernel<<<ceil_div(N, 4), 128, 0, st>>>(w_packed, w_src, transposed, beta, bias, colsum, bias_out, N, K);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return GIC_OK;
+}
+
+template <int MAXV>
+__global__ void __launch_bounds__(128) row_stats_kernel(const float* x, long x_row_stride, bf16* __restrict__ xb, float2* __restrict__ stats,
+                                                        int rows, int d) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  if (warp >= rows) return;
+  pdl_wait();
+  const float* xr = x + (size_t)warp * x_row_stride;
+  float v[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < d ? __ldcg(xr + c) : 0.f;
+  }
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    const bf16 b = __float2bfloat16_rn(v[i]);
+    const float f = __bfloat162float(b);
+    if (c < d) {
+      xb[(size_t)warp * d + c] = b;
+      s += f;
+      q += f * f;
+    }
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if (lane == 0) stats[warp] = make_float2(s, q);
+}
+
+int launch_row_stats(const float* x, long x_row_stride, bf16* xb, float2* stats, int rows, int d, cudaStream_t st) {
+  GIC_REQUIRE(rows > 0 && d > 0 && d <= 32 * 40, "row_stats: unsupported rows=%d d=%d (d <= 1280)", rows, d);
+  const int blocks = ceil_div(rows, 4);
+  auto kern = d <= 32 * 4 ? row_stats_kernel<4> : d <= 32 * 24 ? row_stats_kernel<24> : d <= 32 * 32 ? row_stats_kernel<32> : row_stats_kernel<40>;
+  GIC_CHECK_CUDA(launch_kernel(kern, dim3(blocks), dim3(128), 0, st, x, x_row_stride, xb, stats, rows, d));
   note_launch();
   return GIC_OK;
 }

@@ -37,6 +37,7 @@ struct Linear {  // y = x . W^T + b with W packed as [N,K] K-major
   bf16* w_hi = nullptr;
   bf16* w_lo = nullptr;
   float* bias = nullptr;
+  float* colsum = nullptr;     // non-null: a LayerNorm is folded into this layer (w = gamma * W, bias = b + W . beta), see launch_fold_ln
   TmaDesc tm_hi[5], tm_lo[5];  // per box height in kBoxRows
 };
 struct Norm { float* w = nullptr; float* b = nullptr; };
@@ -63,7 +64,8 @@ struct Workspace {
   void* kv = nullptr;              // [L][2][rows][H][t_max][64]
   size_t kv_layer_elems = 0;       // elements of one K (or V) plane of one layer
   float* logits = nullptr;         // [rows, V] fp32 (F32 mode)
-  float* part_val = nullptr; int* part_idx = nullptr; int n_parts_max = 0;
+  float* part_val = nullptr; int* part_idx = nullptr; int n_parts_max = 0;  // [rows][n_parts_max]
+  float2* ln_stats = nullptr; int ln_parts_max = 0;  // [ln_parts_max][m_max] row (sum, sum of squares) partials (folded LayerNorm)
   int64_t* ids = nullptr;          // [rows, max_new]
   unsigned char* finished = nullptr; int* first_eos = nullptr;
   int *d_step = nullptr, *d_pos = nullptr, *done_counter = nullptr;
@@ -81,6 +83,10 @@ struct gic_engine {
   gic_config cfg;
   int d = 0, L = 0, H = 0, V = 0, P_img = 0, P_task = 0, E = 0;
   bool split = false;  // BF16X2
+  bool fuse_ln = false;  // BF16: ln_1 / ln_2 folded into the GEMM that follows them (no LayerNorm launches inside the GPT-2 blocks)
+  bool fuse_lnf = false; // ... and ln_f into the LM head (GIC_LNF_FUSE=1).  Off by default: measured round 1, the folded head re-reads the
+                         // row statistics and column sums for each of its ~10 tiles per CTA and costs 79 us against 3.8 + 55 us
+  bf16* wte_gather = nullptr;  // BF16: unfolded bf16 embedding table for the next-token gather
   bool tc = false;     // tensor-core modes (BF16 / BF16X2)
   std::vector<void*> allocs;
   size_t weight_bytes = 0;
@@ -154,7 +160,8 @@ static int copy_vec(gic_engine* e, float** dst, const float* src, size_t n, cuda
 }
 
 // in: fp32 [N,K] (transpose = false, nn.Linear / wte) or [K,N] (transpose = true, HF Conv1D)
-static int pack_linear(gic_engine* e, Linear* lin, const float* w, const float* bias, int N, int K, bool transpose, cudaStream_t st) {
+static int pack_linear(gic_engine* e, Linear* lin, const float* w, const float* bias, int N, int K, bool transpose, cudaStream_t st,
+                       const float* ln_gamma = nullptr, const float* ln_beta = nullptr) {
   GIC_REQUIRE(w != nullptr, "null weight pointer");
   lin->N = N;
   lin->K = K;
@@ -173,8 +180,13 @@ static int pack_linear(gic_engine* e, Linear* lin, const float* w, const float* 
   }
   // source is [R,C]: transpose -> [C,R] = [N,K]
   const int R = transpose ? K : N, C = transpose ? N : K;
-  GIC_TRY(launch_pack_weight(w, R, C, transpose, out, st));
-  if (bias) GIC_TRY(copy_vec(e, &lin->bias, bias, N, st));
+  GIC_TRY(launch_pack_weight(w, R, C, transpose, out, st, ln_gamma));
+  if (ln_gamma) {
+    GIC_REQUIRE(e->tc && !e->split && ln_beta, "LayerNorm folding is a bf16-engine feature");
+    GIC_TRY(dev_alloc(e, (void**)&lin->colsum, (size_t)N * sizeof(float)));
+    GIC_TRY(dev_alloc(e, (void**)&lin->bias, (size_t)N * sizeof(float)));
+    GIC_TRY(launch_fold_ln(lin->w_hi, w, transpose, ln_beta, bias, lin->colsum, lin->bias, N, K, st));
+  } else if (bias) GIC_TRY(copy_vec(e, &lin->bias, bias, N, st));
   if (e->tc) {
     GIC_REQUIRE(K % 64 == 0, "tensor-core modes need K (%d) to be a multiple of 64", K);
     for (int i = 0; i < 5; ++i) {
@@ -259,6 +271,10 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
     bs.beam_idx = c.take<int>(w->rows); bs.next_tok = c.take<int>(w->rows);
     bs.cand_score = c.take<float>((size_t)2 * w->rows); bs.cand_idx = c.take<int>((size_t)2 * w->rows);
   }
+  if (e->fuse_ln) {
+    w->ln_parts_max = ceil_div(d, 32);
+    w->ln_stats = c.take<float2>((size_t)w->ln_parts_max * m);
+  }
   w->part_val = c.take<float>((size_t)w->n_parts_max * w->rows);
   w->part_idx = c.take<int>((size_t)w->n_parts_max * w->rows);
   w->ids = c.take<int64_t>((size_t)w->rows * (max_new > 0 ? max_new : 1));
@@ -274,8 +290,18 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
 // building blocks
 // ---------------------------------------------------------------------------------------------------------------
 // out = epi(A . W^T + b).  A: Act with M rows of K (dense).  Outputs follow `out` (row stride ld_out).
+// folded-LayerNorm plumbing of one GEMM call: where the A rows' statistics come from / where this GEMM's output statistics go
+struct LnIo {
+  const float2* stats_in = nullptr; int parts_in = 0; long stats_ld = 0; int row_mul = 1, row_off = 0;
+  float2* stats_out = nullptr;
+  long a_row_stride = 0;  // A rows are `a_row_stride` elements apart (0: dense)
+};
+// number of statistics parts a residual GEMM leaves behind: one per 32 output columns, whatever the tile width or M
+// (so that a row's LayerNorm statistics are summed in the same order in any batch)
+static int residual_stats_parts(const gic_engine* e, int M) { (void)M; return ceil_div(e->d, 32); }
+
 static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, int epilogue, ActOut out, int ld_out, cudaStream_t st,
-                  float* part_val = nullptr, int* part_idx = nullptr, int* n_parts = nullptr) {
+                  float* part_val = nullptr, int* part_idx = nullptr, int* n_parts = nullptr, int part_ld = 0, const LnIo* ln = nullptr) {
   if (!e->tc) {
     GIC_REQUIRE(out.f32 != nullptr, "fp32 linear needs an fp32 output");
     return launch_sgemm_nt(A.f32, lin.K, lin.w_f32, lin.bias, out.f32, ld_out, M, lin.N, lin.K, epilogue, st);
@@ -284,14 +310,19 @@ static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, i
   const int bn = gemm_bf16_pick_block_n(M, lin.N, e->split ? 1 : 0);
   const int bi = box_rows_index(bn);
   GIC_REQUIRE(bi >= 0, "no W tensor map for box height %d", bn);
-  GIC_TRY(make_tma_2d_bf16(&g.a_hi, A.hi, M, lin.K, lin.K, 128));
+  GIC_TRY(make_tma_2d_bf16(&g.a_hi, A.hi, M, lin.K, (ln && ln->a_row_stride) ? ln->a_row_stride : lin.K, 128));
   g.w_hi = lin.tm_hi[bi];
   if (e->split) {
     GIC_TRY(make_tma_2d_bf16(&g.a_lo, A.lo, M, lin.K, lin.K, 128));
     g.w_lo = lin.tm_lo[bi];
   }
   g.M = M; g.N = lin.N; g.K = lin.K; g.block_n = bn; g.split = e->split ? 1 : 0; g.epilogue = epilogue; g.bias = lin.bias;
-  g.out = out; g.ld_out = ld_out; g.part_val = part_val; g.part_idx = part_idx;
+  g.out = out; g.ld_out = ld_out; g.part_val = part_val; g.part_idx = part_idx; g.part_ld = part_ld;
+  GIC_REQUIRE((lin.colsum != nullptr) == (ln != nullptr && ln->stats_in != nullptr), "linear: folded-LayerNorm weights and row statistics must come together");
+  if (ln) {
+    g.ln_stats = ln->stats_in; g.ln_parts = ln->parts_in; g.ln_stats_ld = ln->stats_ld; g.ln_row_mul = ln->row_mul; g.ln_row_off = ln->row_off;
+    g.ln_colsum = lin.colsum; g.stats_out = ln->stats_out;
+  }
   if (n_parts) *n_parts = 2 * ceil_div(lin.N, bn);  // one (value, index) slot per (tile, column-parity epilogue warp)
   return launch_gemm_bf16(g, st);
 }
@@ -303,26 +334,48 @@ static ActOut qkv_out(const Workspace& w) {
   return o;
 }
 
-// one GPT-2 block over M rows of the residual stream `h` (HF GPT2Block.forward :262-309)
-static int gpt_layer(const gic_engine* e, const Workspace& w, int l, float* h, int M, bool prefill, cudaStream_t st) {
-  const GptLayer& Lw = e->layers[l];
-  const int d = e->d;
-  { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, d, Lw.ln1.w, Lw.ln1.b, w.a.out(), M, d, st)); }
-  { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_qkv", st); GIC_TRY(linear(e, Lw.attn, w.a, M, EPI_NONE, qkv_out(w), 3 * d, st)); }
+// attention sub-step shared by both layer variants
+static int attention(const gic_engine* e, const Workspace& w, int l, int M, bool prefill, cudaStream_t st) {
+  ProfScope ps(e, prefill ? "attn_prefill" : "attn_decode", st);
   if (e->cfg.dtype == GIC_DTYPE_BF16) {
-    ProfScope ps(e, prefill ? "attn_prefill" : "attn_decode", st);
     bf16* kc = (bf16*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
     bf16* vc = kc + w.kv_layer_elems;
-    if (prefill) GIC_TRY(launch_attn_prefill<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, w.beams, st));
-    else GIC_TRY(launch_attn_decode<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st));
-  } else {
-    ProfScope ps(e, prefill ? "attn_prefill" : "attn_decode", st);
-    float* kc = (float*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
-    float* vc = kc + w.kv_layer_elems;
-    if (prefill) GIC_TRY(launch_attn_prefill<float>(w.qkv_f32, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, w.beams, st));
-    else GIC_TRY(launch_attn_decode<float>(w.qkv_f32, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st));
+    if (prefill) return launch_attn_prefill<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, w.beams, st);
+    return launch_attn_decode<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st);
   }
+  float* kc = (float*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
+  float* vc = kc + w.kv_layer_elems;
+  if (prefill) return launch_attn_prefill<float>(w.qkv_f32, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, w.beams, st);
+  return launch_attn_decode<float>(w.qkv_f32, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st);
+}
+
+// one GPT-2 block over M rows of the residual stream `h` (HF GPT2Block.forward :262-309).
+// bf16 engine (fuse_ln): w.a holds bf16(h) and w.ln_stats its per-row (sum, sum of squares) in `parts_in` parts on entry;
+// both are refreshed by the residual GEMMs, so the block is 5 launches: qkv, attention, proj, fc, fc2.
+static int gpt_layer(const gic_engine* e, const Workspace& w, int l, float* h, int M, bool prefill, cudaStream_t st, int parts_in = 0) {
+  const GptLayer& Lw = e->layers[l];
+  const int d = e->d;
   ActOut hres; hres.f32 = h;
+  if (e->fuse_ln) {
+    const int parts_res = residual_stats_parts(e, M);
+    LnIo in; in.stats_in = w.ln_stats; in.parts_in = parts_in; in.stats_ld = w.m_max;
+    LnIo res; res.stats_out = w.ln_stats; res.stats_ld = w.m_max;
+    ActOut hres2 = hres; hres2.hi = w.a.hi;
+    { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_qkv", st);
+      GIC_TRY(linear(e, Lw.attn, w.a, M, EPI_NONE, qkv_out(w), 3 * d, st, nullptr, nullptr, nullptr, 0, &in)); }
+    GIC_TRY(attention(e, w, l, M, prefill, st));
+    { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_proj", st);
+      GIC_TRY(linear(e, Lw.proj, w.o, M, EPI_RESIDUAL, hres2, d, st, nullptr, nullptr, nullptr, 0, &res)); }
+    in.parts_in = parts_res;
+    { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_fc", st);
+      GIC_TRY(linear(e, Lw.fc, w.a, M, EPI_GELU, w.f.out(), 4 * d, st, nullptr, nullptr, nullptr, 0, &in)); }
+    { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_fc2", st);
+      GIC_TRY(linear(e, Lw.fc2, w.f, M, EPI_RESIDUAL, hres2, d, st, nullptr, nullptr, nullptr, 0, &res)); }
+    return GIC_OK;
+  }
+  { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, d, Lw.ln1.w, Lw.ln1.b, w.a.out(), M, d, st)); }
+  { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_qkv", st); GIC_TRY(linear(e, Lw.attn, w.a, M, EPI_NONE, qkv_out(w), 3 * d, st)); }
+  GIC_TRY(attention(e, w, l, M, prefill, st));
   { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_proj", st); GIC_TRY(linear(e, Lw.proj, w.o, M, EPI_RESIDUAL, hres, d, st)); }
   { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, d, Lw.ln2.w, Lw.ln2.b, w.a.out(), M, d, st)); }
   { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_fc", st); GIC_TRY(linear(e, Lw.fc, w.a, M, EPI_GELU, w.f.out(), 4 * d, st)); }
@@ -330,37 +383,57 @@ static int gpt_layer(const gic_engine* e, const Workspace& w, int l, float* h, i
   return GIC_OK;
 }
 
-// ln_f on `rows` rows (row r at h + r*stride) -> LM head -> (val, idx) partials -> finalize (token, EOS rules, next input)
-static int lm_head_and_token(const gic_engine* e, const Workspace& w, const float* h, long row_stride, int rows, float* logits_tap,
-                             cudaStream_t st) {
+// every layer over M rows; the statistics parts of layer 0's input come from the caller (1 after row_stats / finalize)
+static int gpt_layers(const gic_engine* e, const Workspace& w, float* h, int M, bool prefill, cudaStream_t st) {
+  for (int l = 0; l < e->L; ++l) GIC_TRY(gpt_layer(e, w, l, h, M, prefill, st, l == 0 ? 1 : residual_stats_parts(e, M)));
+  return GIC_OK;
+}
+
+// ln_f on `rows` rows (row r at h + r*stride) -> LM head -> (val, idx) partials -> finalize (token, EOS rules, next input).
+// body_rows: the M the layers ran over (prefill: B*P, rows = B picks position P-1 of every sequence).
+static int lm_head_and_token(const gic_engine* e, const Workspace& w, const float* h_buf, long first_off, long row_stride, int rows, int body_rows,
+                             float* logits_tap, cudaStream_t st) {
   const int d = e->d;
-  { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, row_stride, e->lnf.w, e->lnf.b, w.a.out(), rows, d, st)); }
+  const float* h = h_buf + first_off;
   int n_parts = 0;
-  if (!e->tc) {
-    float* lg = logits_tap ? logits_tap : w.logits;
-    ActOut o; o.f32 = lg;
-    { ProfScope ps(e, "lm_head", st); GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st)); }
-    { ProfScope ps(e, "argmax", st); GIC_TRY(launch_argmax_partials(lg, rows, e->V, w.part_val, w.part_idx, st)); }
-    n_parts = LMHEAD_F32_PARTS;
-  } else {
+  if (e->fuse_ln && e->fuse_lnf) {
+    // rows of bf16(h) in w.a at the same (stride, offset) as h in its buffer; statistics indexed by the body row
+    const long off = first_off;
+    Act a = w.a; a.hi += off;
+    LnIo in; in.stats_in = w.ln_stats; in.parts_in = e->L > 0 ? residual_stats_parts(e, body_rows) : 1; in.stats_ld = w.m_max;
+    in.row_mul = (int)(row_stride / d); in.row_off = (int)(off / d); in.a_row_stride = row_stride;
     ActOut o; o.f32 = logits_tap;  // null on the product path: logits never reach HBM
     ProfScope ps(e, "lm_head", st);
-    GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st, w.part_val, w.part_idx, &n_parts));
+    GIC_TRY(linear(e, e->lm_head, a, rows, EPI_NONE, o, e->V, st, w.part_val, w.part_idx, &n_parts, w.n_parts_max, &in));
+  } else {
+    { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, row_stride, e->lnf.w, e->lnf.b, w.a.out(), rows, d, st)); }
+    if (!e->tc) {
+      float* lg = logits_tap ? logits_tap : w.logits;
+      ActOut o; o.f32 = lg;
+      { ProfScope ps(e, "lm_head", st); GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st)); }
+      { ProfScope ps(e, "argmax", st); GIC_TRY(launch_argmax_partials(lg, rows, e->V, w.part_val, w.part_idx, w.n_parts_max, st)); }
+      n_parts = LMHEAD_F32_PARTS;
+    } else {
+      ActOut o; o.f32 = logits_tap;  // null on the product path: logits never reach HBM
+      ProfScope ps(e, "lm_head", st);
+      GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st, w.part_val, w.part_idx, &n_parts, w.n_parts_max));
+    }
   }
   ProfScope psf(e, "finalize", st);
   FinalizeArgs fa;
-  fa.part_val = w.part_val; fa.part_idx = w.part_idx; fa.n_parts = n_parts;
+  fa.part_val = w.part_val; fa.part_idx = w.part_idx; fa.n_parts = n_parts; fa.part_ld = w.n_parts_max;
   fa.B = rows; fa.d = d; fa.eos = e->cfg.eos_token_id; fa.max_new = w.max_new; fa.P = w.P; fa.n_pos = e->cfg.n_positions;
   fa.d_step = w.d_step; fa.d_pos = w.d_pos; fa.done_counter = w.done_counter;
   fa.finished = w.finished; fa.first_eos = w.first_eos; fa.ids_out = w.ids;
-  fa.wte_f32 = e->wte_f32; fa.wte_bf16 = e->wte_f32 ? nullptr : e->lm_head.w_hi;
+  fa.wte_f32 = e->wte_f32; fa.wte_bf16 = e->wte_f32 ? nullptr : e->wte_gather;
   fa.wpe = e->wpe; fa.h_next = w.h_dec;
+  fa.hb_next = e->fuse_ln ? w.a.hi : nullptr; fa.stats_next = e->fuse_ln ? w.ln_stats : nullptr;
   return launch_finalize_token(fa, st);
 }
 
 static int decode_step(const gic_engine* e, const Workspace& w, float* logits_tap, cudaStream_t st) {
-  for (int l = 0; l < e->L; ++l) GIC_TRY(gpt_layer(e, w, l, w.h_dec, w.rows, false, st));
-  return lm_head_and_token(e, w, w.h_dec, e->d, w.rows, logits_tap, st);
+  GIC_TRY(gpt_layers(e, w, w.h_dec, w.rows, false, st));
+  return lm_head_and_token(e, w, w.h_dec, 0, e->d, w.rows, w.rows, logits_tap, st);
 }
 
 // view of rows [row0, row0 + nrows) of a workspace, with its own device-side step / position counters (`sub`)
@@ -381,6 +454,7 @@ static Workspace slice_rows(const gic_engine* e, const Workspace& w, int row0, i
   if (e->cfg.dtype == GIC_DTYPE_BF16) s.kv = (bf16*)w.kv + (size_t)row0 * kv_row;
   else s.kv = (float*)w.kv + (size_t)row0 * kv_row;
   if (s.logits) s.logits += (size_t)row0 * e->V;
+  if (s.ln_stats) s.ln_stats += row0;
   s.part_val += (size_t)w.n_parts_max * row0;
   s.part_idx += (size_t)w.n_parts_max * row0;
   s.ids += (size_t)row0 * w.max_new;
@@ -507,6 +581,12 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
   e->P_img = cfg->prefix_length; e->P_task = cfg->task_prefix_length; e->E = cfg->embed_dim;
   e->tc = cfg->dtype != GIC_DTYPE_F32;
   e->split = cfg->dtype == GIC_DTYPE_BF16X2;
+  {
+    const char* nf = getenv("GIC_NO_LNFUSE");
+    e->fuse_ln = cfg->dtype == GIC_DTYPE_BF16 && !(nf && nf[0] == '1');
+    const char* hf = getenv("GIC_LNF_FUSE");
+    e->fuse_lnf = e->fuse_ln && hf && hf[0] == '1';
+  }
   const char* ng = getenv("GIC_NO_GRAPH");
   e->use_graph = !(ng && ng[0] == '1');
   if (e->tc) {
@@ -553,7 +633,16 @@ int gic_engine_load_gpt2(gic_engine* e, const gic_gpt2_weights* w, void* stream)
   GIC_REQUIRE(!e->gpt_loaded, "GPT-2 weights already loaded; create a new engine to reload");
   cudaStream_t st = (cudaStream_t)stream;
   const int d = e->d;
-  GIC_TRY(pack_linear(e, &e->lm_head, w->wte, nullptr, e->V, d, false, st));
+  // bf16 engine: ln_f is folded into the LM head (the tied table then differs from the embedding table, kept separately)
+  const bool fold_head = e->fuse_ln && e->fuse_lnf;
+  GIC_TRY(pack_linear(e, &e->lm_head, w->wte, nullptr, e->V, d, false, st, fold_head ? w->lnf_w : nullptr, fold_head ? w->lnf_b : nullptr));
+  if (fold_head) {
+    GIC_TRY(dev_alloc(e, (void**)&e->wte_gather, (size_t)e->V * d * sizeof(bf16)));
+    ActOut go; go.hi = e->wte_gather;
+    GIC_TRY(launch_convert(w->wte, go, (size_t)e->V * d, st));
+  } else {
+    e->wte_gather = e->lm_head.w_hi;
+  }
   if (e->cfg.dtype == GIC_DTYPE_F32) e->wte_f32 = e->lm_head.w_f32;
   else if (e->cfg.dtype == GIC_DTYPE_BF16X2) GIC_TRY(copy_vec(e, &e->wte_f32, w->wte, (size_t)e->V * d, st));
   GIC_TRY(copy_vec(e, &e->wpe, w->wpe, (size_t)e->cfg.n_positions * d, st));
@@ -564,9 +653,10 @@ int gic_engine_load_gpt2(gic_engine* e, const gic_gpt2_weights* w, void* stream)
     GptLayer& D = e->layers[l];
     GIC_TRY(copy_norm(e, &D.ln1, s.ln1_w, s.ln1_b, d, st));
     GIC_TRY(copy_norm(e, &D.ln2, s.ln2_w, s.ln2_b, d, st));
-    GIC_TRY(pack_linear(e, &D.attn, s.attn_w, s.attn_b, 3 * d, d, true, st));   // Conv1D [d,3d] -> [3d,d]
+    // Conv1D [d,3d] -> [3d,d]; bf16 engine: ln_1 folded into c_attn, ln_2 into c_fc
+    GIC_TRY(pack_linear(e, &D.attn, s.attn_w, s.attn_b, 3 * d, d, true, st, e->fuse_ln ? s.ln1_w : nullptr, e->fuse_ln ? s.ln1_b : nullptr));
     GIC_TRY(pack_linear(e, &D.proj, s.proj_w, s.proj_b, d, d, true, st));
-    GIC_TRY(pack_linear(e, &D.fc, s.fc_w, s.fc_b, 4 * d, d, true, st));
+    GIC_TRY(pack_linear(e, &D.fc, s.fc_w, s.fc_b, 4 * d, d, true, st, e->fuse_ln ? s.ln2_w : nullptr, e->fuse_ln ? s.ln2_b : nullptr));
     GIC_TRY(pack_linear(e, &D.fc2, s.fc2_w, s.fc2_b, d, 4 * d, true, st));
   }
   e->gpt_loaded = true;
@@ -667,9 +757,10 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
   GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));
   // ---- prefill over the P prefix tokens of every row ----
-  for (int l = 0; l < e->L; ++l) GIC_TRY(gpt_layer(e, w, l, w.h, B * P, true, st));
+  if (e->fuse_ln) GIC_TRY(launch_row_stats(w.h, d, w.a.hi, w.ln_stats, B * P, d, st));
+  GIC_TRY(gpt_layers(e, w, w.h, B * P, true, st));
   // only the last position feeds the LM head (the reference computes all positions and keeps [:, -1, :], src/models.py:398)
-  GIC_TRY(lm_head_and_token(e, w, w.h + (size_t)(P - 1) * d, (long)P * d, B, logits_out, st));
+  GIC_TRY(lm_head_and_token(e, w, w.h, (long)(P - 1) * d, (long)P * d, B, B * P, logits_out, st));
 
   // ---- decode: max_new-1 identical steps; positions / step index live on the device ----
   const int steps = max_new - 1;
@@ -703,9 +794,17 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
 }
 
 // ln_f -> LM head with the full fp32 logit rows materialised (beam search needs log-softmax + top-2K over beams x V)
-static int lm_head_logits(const gic_engine* e, const Workspace& w, const float* h, long row_stride, int rows, cudaStream_t st) {
-  { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, row_stride, e->lnf.w, e->lnf.b, w.a.out(), rows, e->d, st)); }
+static int lm_head_logits(const gic_engine* e, const Workspace& w, const float* h_buf, long first_off, long row_stride, int rows, int body_rows,
+                          cudaStream_t st) {
   ActOut o; o.f32 = w.logits;
+  if (e->fuse_ln && e->fuse_lnf) {
+    Act a = w.a; a.hi += first_off;
+    LnIo in; in.stats_in = w.ln_stats; in.parts_in = e->L > 0 ? residual_stats_parts(e, body_rows) : 1; in.stats_ld = w.m_max;
+    in.row_mul = (int)(row_stride / e->d); in.row_off = (int)(first_off / e->d); in.a_row_stride = row_stride;
+    ProfScope ps(e, "lm_head", st);
+    return linear(e, e->lm_head, a, rows, EPI_NONE, o, e->V, st, nullptr, nullptr, nullptr, 0, &in);
+  }
+  { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h_buf + first_off, row_stride, e->lnf.w, e->lnf.b, w.a.out(), rows, e->d, st)); }
   ProfScope ps(e, "lm_head", st);
   return linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st);
 }
@@ -725,8 +824,9 @@ int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int
   { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
   GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));
   // prefill once per image; its K/V land in cache row b*beams and the first reorder fans them out to every beam
-  for (int l = 0; l < e->L; ++l) GIC_TRY(gpt_layer(e, w, l, w.h, B * P, true, st));
-  GIC_TRY(lm_head_logits(e, w, w.h + (size_t)(P - 1) * d, (long)P * d, B, st));
+  if (e->fuse_ln) GIC_TRY(launch_row_stats(w.h, d, w.a.hi, w.ln_stats, B * P, d, st));
+  GIC_TRY(gpt_layers(e, w, w.h, B * P, true, st));
+  GIC_TRY(lm_head_logits(e, w, w.h, (long)(P - 1) * d, (long)P * d, B, B * P, st));
   const size_t esz = e->cfg.dtype == GIC_DTYPE_BF16 ? sizeof(bf16) : sizeof(float);
   (void)esz;
   for (int t = 0; t < max_new; ++t) {
@@ -743,10 +843,11 @@ int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int
       else
         GIC_TRY(launch_kv_reorder<float>((const float*)w.kv, (float*)w.kv2, w.beam.beam_idx, e->L, rows, e->H, P + t, w.t_max, st)); }
     { void* tmp = w.kv; w.kv = w.kv2; w.kv2 = tmp; }
-    GIC_TRY(launch_beam_embed(w.beam.next_tok, e->wte_f32, e->wte_f32 ? nullptr : e->lm_head.w_hi, e->wpe, P + t, d, w.h_dec, rows, st));
+    GIC_TRY(launch_beam_embed(w.beam.next_tok, e->wte_f32, e->wte_f32 ? nullptr : e->wte_gather, e->wpe, P + t, d, w.h_dec, rows, st));
     GIC_TRY(launch_set_int(w.d_pos, P + t, st));
-    for (int l = 0; l < e->L; ++l) GIC_TRY(gpt_layer(e, w, l, w.h_dec, rows, false, st));
-    GIC_TRY(lm_head_logits(e, w, w.h_dec, d, rows, st));
+    if (e->fuse_ln) GIC_TRY(launch_row_stats(w.h_dec, d, w.a.hi, w.ln_stats, rows, d, st));
+    GIC_TRY(gpt_layers(e, w, w.h_dec, rows, false, st));
+    GIC_TRY(lm_head_logits(e, w, w.h_dec, 0, d, rows, rows, st));
   }
   GIC_TRY(launch_beam_finalize(w.beam, max_new & 1, ids_out, scores_out, gen_len_out, st));
   return join_stream(e, user);

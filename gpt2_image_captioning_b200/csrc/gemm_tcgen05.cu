@@ -160,10 +160,10 @@ struct alignas(64) GemmKernelParams {
   const float* bias;
   float* out_f32; int ld_f32;
   bf16* out_hi; bf16* out_lo; int ld_bf16;
-  float* part_val; int* part_idx;  // [2 * n_tiles][M]: one slot per (tile, column-parity warp)
+  float* part_val; int* part_idx; int part_ld;  // [M][part_ld]: slot (tile * 2 + column-parity warp) of each row
   // folded LayerNorm on the A operand (see launch_gemm_bf16): out = rstd_r * (acc - mean_r * colsum_n) + bias_n
   const float2* ln_stats; int ln_parts; long ln_stats_ld; int ln_row_mul, ln_row_off; const float* ln_colsum;
-  float2* stats_out;  // [2 * n_tiles][M] (sum, sum of squares) of the values written, per row
+  float2* stats_out;  // [ceil(N / 32)][ln_stats_ld] (sum, sum of squares) of the values written, per row and 32-column chunk
   long long* trace;  // null; microbenchmark only: clock64 timeline of CTA 0's producer / MMA / epilogue warps
 };
 
@@ -342,12 +342,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         float mu = 0.f, rs = 1.f;
         if (FOLD) {
           float sx = 0.f, sq = 0.f;
-          if (row < p.M)
-            for (int part = 0; part < p.ln_parts; ++part) {
-              const float2 t = __ldcg(p.ln_stats + (size_t)part * p.ln_stats_ld + (size_t)row * p.ln_row_mul + p.ln_row_off);
-              sx += t.x;
-              sq += t.y;
+          if (row < p.M) {
+            // fixed order (8 interleaved partial sums, then a tree): batch-invariant, and the 8 loads of a round overlap
+            const float2* sp = p.ln_stats + (size_t)row * p.ln_row_mul + p.ln_row_off;
+            float ax[8], aq[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { ax[u] = 0.f; aq[u] = 0.f; }
+            for (int part = 0; part < p.ln_parts; part += 8) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (part + u < p.ln_parts) {
+                  const float2 t = __ldcg(sp + (size_t)(part + u) * p.ln_stats_ld);
+                  ax[u] += t.x;
+                  aq[u] += t.y;
+                }
             }
+            sx = ((ax[0] + ax[1]) + (ax[2] + ax[3])) + ((ax[4] + ax[5]) + (ax[6] + ax[7]));
+            sq = ((aq[0] + aq[1]) + (aq[2] + aq[3])) + ((aq[4] + aq[5]) + (aq[6] + aq[7]));
+          }
           const float inv_k = 1.0f / (float)p.K;
           mu = sx * inv_k;
           rs = rsqrtf(fmaxf(sq * inv_k - mu * mu, 0.f) + 1e-5f);
@@ -365,6 +377,33 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
 #pragma unroll 1
         for (int c0 = sub * 32; c0 < BLOCK_N; c0 += 64) {
           const int col0 = n0 + c0;
+          const bool whole = col0 + 32 <= p.N;
+          // bias / column sums of the chunk: warp-uniform addresses (one broadcast transaction each), all sixteen requested
+          // before the accumulator is read so that their L2 latency is paid once per chunk, not once per use
+          float4 b4[8], cs4[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int col = col0 + 4 * c;
+            b4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cs4[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (whole) {
+              if (p.bias) b4[c] = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+              if (FOLD) cs4[c] = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col));
+            } else {
+              if (p.bias) {
+                if (col < p.N) b4[c].x = __ldg(p.bias + col);
+                if (col + 1 < p.N) b4[c].y = __ldg(p.bias + col + 1);
+                if (col + 2 < p.N) b4[c].z = __ldg(p.bias + col + 2);
+                if (col + 3 < p.N) b4[c].w = __ldg(p.bias + col + 3);
+              }
+              if (FOLD) {
+                if (col < p.N) cs4[c].x = __ldg(p.ln_colsum + col);
+                if (col + 1 < p.N) cs4[c].y = __ldg(p.ln_colsum + col + 1);
+                if (col + 2 < p.N) cs4[c].z = __ldg(p.ln_colsum + col + 2);
+                if (col + 3 < p.N) cs4[c].w = __ldg(p.ln_colsum + col + 3);
+              }
+            }
+          }
           uint32_t r[32];
           ptx::tmem_ld_32x32(tmem_row + (uint32_t)c0, r);
           ptx::tmem_ld_wait();
@@ -374,34 +413,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
           }
           if (col0 >= p.N) continue;  // warp-uniform
-          const bool whole = col0 + 32 <= p.N;
+          const float nrm = -rs * mu;  // v = rs * acc - rs * mu * colsum + bias
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            // warp-uniform addresses: one broadcast transaction each
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), cs4 = make_float4(0.f, 0.f, 0.f, 0.f);
             const int col = col0 + 4 * c;
-            if (whole) {
-              if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-              if (FOLD) cs4 = __ldg(reinterpret_cast<const float4*>(p.ln_colsum + col));
-            } else {
-              if (p.bias) {
-                if (col < p.N) b4.x = __ldg(p.bias + col);
-                if (col + 1 < p.N) b4.y = __ldg(p.bias + col + 1);
-                if (col + 2 < p.N) b4.z = __ldg(p.bias + col + 2);
-                if (col + 3 < p.N) b4.w = __ldg(p.bias + col + 3);
-              }
-              if (FOLD) {
-                if (col < p.N) cs4.x = __ldg(p.ln_colsum + col);
-                if (col + 1 < p.N) cs4.y = __ldg(p.ln_colsum + col + 1);
-                if (col + 2 < p.N) cs4.z = __ldg(p.ln_colsum + col + 2);
-                if (col + 3 < p.N) cs4.w = __ldg(p.ln_colsum + col + 3);
-              }
-            }
             float v0 = __uint_as_float(r[4 * c]), v1 = __uint_as_float(r[4 * c + 1]), v2 = __uint_as_float(r[4 * c + 2]), v3 = __uint_as_float(r[4 * c + 3]);
             if (FOLD) {
-              v0 = rs * (v0 - mu * cs4.x); v1 = rs * (v1 - mu * cs4.y); v2 = rs * (v2 - mu * cs4.z); v3 = rs * (v3 - mu * cs4.w);
+              v0 = fmaf(rs, v0, fmaf(nrm, cs4[c].x, b4[c].x));
+              v1 = fmaf(rs, v1, fmaf(nrm, cs4[c].y, b4[c].y));
+              v2 = fmaf(rs, v2, fmaf(nrm, cs4[c].z, b4[c].z));
+              v3 = fmaf(rs, v3, fmaf(nrm, cs4[c].w, b4[c].w));
+            } else {
+              v0 += b4[c].x; v1 += b4[c].y; v2 += b4[c].z; v3 += b4[c].w;
             }
-            v0 += b4.x; v1 += b4.y; v2 += b4.z; v3 += b4.w;
             // columns in increasing order with strict > : the lowest index among equal maxima survives
             bool g;
             g = (whole || col < p.N) && v0 > bv; bv = g ? v0 : bv; bi = g ? col : bi;
@@ -411,7 +435,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           }
         }
         if (row < p.M) {
-          const size_t slot = (size_t)(n_tile * 2 + sub) * p.M + row;
+          const size_t slot = (size_t)row * p.part_ld + (n_tile * 2 + sub);
           p.part_val[slot] = bv;
           p.part_idx[slot] = bi;
         }
@@ -421,25 +445,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
       // folded LayerNorm: per-row mean / rstd of the A operand from the producer's per-tile partial sums (sum, sum of squares)
       float mean[8], rstd[8];
       if (fold) {
+        // the eight lanes that share a row split the parts between them (part = lane & 7, + 8, ...): parts in the outer loop
+        // so that the eight rows' loads of a round are in flight together; fixed order -> the same result in any batch
+        float sx[8], sq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sx[i] = 0.f; sq[i] = 0.f; }
+        for (int part = cchunk; part < p.ln_parts; part += 8) {
+          const float2* sp = p.ln_stats + (size_t)part * p.ln_stats_ld + p.ln_row_off;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = min(wrow0 + crow0 + 4 * i, p.M - 1);
+            const float2 t = __ldcg(sp + (size_t)row * p.ln_row_mul);
+            sx[i] += t.x;
+            sq[i] += t.y;
+          }
+        }
+        const float inv_k = 1.0f / (float)p.K;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int row = wrow0 + crow0 + 4 * i;
-          float sx = 0.f, sq = 0.f;
-          if (row < p.M)
-            for (int part = cchunk; part < p.ln_parts; part += 8) {
-              const float2 t = __ldcg(p.ln_stats + (size_t)part * p.ln_stats_ld + (size_t)row * p.ln_row_mul + p.ln_row_off);
-              sx += t.x;
-              sq += t.y;
-            }
 #pragma unroll
           for (int o = 1; o < 8; o <<= 1) {
-            sx += __shfl_xor_sync(0xffffffffu, sx, o);
-            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            sx[i] += __shfl_xor_sync(0xffffffffu, sx[i], o);
+            sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
           }
-          const float inv_k = 1.0f / (float)p.K;
-          const float mu = sx * inv_k;
+          const float mu = sx[i] * inv_k;
           mean[i] = mu;
-          rstd[i] = rsqrtf(fmaxf(sq * inv_k - mu * mu, 0.f) + 1e-5f);
+          rstd[i] = rsqrtf(fmaxf(sq[i] * inv_k - mu * mu, 0.f) + 1e-5f);
         }
       }
       float rsum[8], rsq[8], best[8];
@@ -675,32 +706,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             (void)full4;
           }
         }
+        if (OUT == OUT_F32_BF16_STATS) {
+          // one statistics part per 32-column chunk (index = global column / 32): the summation order then depends only on the
+          // column, never on the tile width or the batch size, so a row's result is the same in any batch
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              rsum[i] += __shfl_xor_sync(0xffffffffu, rsum[i], o);
+              rsq[i] += __shfl_xor_sync(0xffffffffu, rsq[i], o);
+            }
+            const int row = wrow0 + crow0 + 4 * i;
+            if (cchunk == 0 && row < p.M) p.stats_out[(size_t)(col0 >> 5) * p.ln_stats_ld + row] = make_float2(rsum[i], rsq[i]);
+            rsum[i] = 0.f;
+            rsq[i] = 0.f;
+          }
+        }
         if (tr) trc[4] = clock64() - t_start;
       }
-      // per-(tile, column-parity) partials of each row: argmax pair and / or (sum, sum of squares)
-      if (EPI == EPI_ARGMAX || OUT == OUT_F32_BF16_STATS) {
+      // per-(tile, column-parity) argmax partials of each row
+      if (EPI == EPI_ARGMAX) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
 #pragma unroll
           for (int o = 1; o < 8; o <<= 1) {
-            if (EPI == EPI_ARGMAX) {
-              const float ov = __shfl_xor_sync(0xffffffffu, best[i], o);
-              const int oi = __shfl_xor_sync(0xffffffffu, bidx[i], o);
-              if (ov > best[i] || (ov == best[i] && oi < bidx[i])) { best[i] = ov; bidx[i] = oi; }
-            }
-            if (OUT == OUT_F32_BF16_STATS) {
-              rsum[i] += __shfl_xor_sync(0xffffffffu, rsum[i], o);
-              rsq[i] += __shfl_xor_sync(0xffffffffu, rsq[i], o);
-            }
+            const float ov = __shfl_xor_sync(0xffffffffu, best[i], o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx[i], o);
+            if (ov > best[i] || (ov == best[i] && oi < bidx[i])) { best[i] = ov; bidx[i] = oi; }
           }
           const int row = wrow0 + crow0 + 4 * i;
           if (cchunk == 0 && row < p.M) {
-            const size_t slot = (size_t)(n_tile * 2 + sub) * p.M + row;
-            if (EPI == EPI_ARGMAX) {
-              p.part_val[slot] = best[i];
-              p.part_idx[slot] = bidx[i];
-            }
-            if (OUT == OUT_F32_BF16_STATS) p.stats_out[slot] = make_float2(rsum[i], rsq[i]);
+            const size_t slot = (size_t)row * p.part_ld + (n_tile * 2 + sub);
+            p.part_val[slot] = best[i];
+            p.part_idx[slot] = bidx[i];
           }
         }
       }
@@ -789,7 +827,7 @@ static int gemm_num_sms() {
 #define GIC_GEMM_VARIANTS_BF16(X) \
   X(EPI_NONE, OUT_BF16, false) X(EPI_NONE, OUT_BF16, true) X(EPI_TANH, OUT_BF16, false) X(EPI_GELU, OUT_BF16, false) \
   X(EPI_GELU, OUT_BF16, true) X(EPI_RELU, OUT_BF16, false) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false) \
-  X(EPI_ARGMAX, OUT_NONE, true) X(EPI_ARGMAX, OUT_F32, true)
+  X(EPI_ARGMAX, OUT_NONE, true) X(EPI_ARGMAX, OUT_F32, true) X(EPI_NONE, OUT_F32, true)
 #define GIC_GEMM_VARIANTS_SPLIT(X) X(EPI_NONE, OUT_BF16X2, false) X(EPI_TANH, OUT_BF16X2, false) X(EPI_GELU, OUT_BF16X2, false) X(EPI_RELU, OUT_BF16X2, false)
 
 template <int BLOCK_N, bool SPLIT>
@@ -849,13 +887,14 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.bias = a.bias;
   kp.mma_repeat = a.mma_repeat < 1 ? 1 : a.mma_repeat;
   kp.out_f32 = a.out.f32; kp.ld_f32 = a.ld_out; kp.out_hi = a.out.hi; kp.out_lo = a.out.lo; kp.ld_bf16 = a.ld_out;
-  kp.part_val = a.part_val; kp.part_idx = a.part_idx; kp.trace = a.trace;
+  kp.part_val = a.part_val; kp.part_idx = a.part_idx; kp.part_ld = a.part_ld; kp.trace = a.trace;
   kp.ln_stats = a.ln_stats; kp.ln_parts = a.ln_parts; kp.ln_stats_ld = a.ln_stats_ld; kp.ln_row_mul = a.ln_row_mul; kp.ln_row_off = a.ln_row_off;
   kp.ln_colsum = a.ln_colsum; kp.stats_out = a.stats_out;
   GIC_REQUIRE(!a.ln_stats || (a.ln_colsum && a.ln_parts > 0), "gemm_bf16: folded LayerNorm needs the column sums and at least one statistics part");
   int epi = a.epilogue;
   if (a.part_val) {
     GIC_REQUIRE(a.epilogue == EPI_NONE && a.part_idx, "gemm_bf16: the fused argmax takes no activation and needs both partial buffers");
+    GIC_REQUIRE(a.part_ld >= 2 * ceil_div(a.N, a.block_n), "gemm_bf16: argmax partial rows too short (%d slots for %d)", a.part_ld, 2 * ceil_div(a.N, a.block_n));
     epi = EPI_ARGMAX;
   }
   GIC_REQUIRE(!(epi == EPI_RESIDUAL && !a.out.f32), "gemm_bf16: residual epilogue needs the fp32 output");
@@ -863,6 +902,7 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   int out = OUT_NONE;
   if (a.stats_out) {
     GIC_REQUIRE(epi == EPI_RESIDUAL && a.out.f32 && a.out.hi && !a.out.lo, "gemm_bf16: row statistics come with the fused residual epilogue (fp32 + bf16 outputs)");
+    GIC_REQUIRE(a.ln_stats_ld >= a.M, "gemm_bf16: statistics leading dimension %ld < M %d", a.ln_stats_ld, a.M);
     out = OUT_F32_BF16_STATS;
   } else if (a.out.f32) {
     GIC_REQUIRE(!a.out.hi && !a.out.lo, "gemm_bf16: fp32 and bf16 outputs together only in the fused residual epilogue");

@@ -43,14 +43,15 @@ struct GemmBf16Args {
   const float* bias = nullptr;     // [N] or null
   ActOut out;                      // fp32 (EPI_RESIDUAL: in-place +=) and/or bf16 hi/lo, row stride ld_out
   int ld_out = 0;
-  float* part_val = nullptr;       // fused LM-head argmax: [2 * n_tiles][M] best value ...
+  float* part_val = nullptr;       // fused LM-head argmax: [M][part_ld] best value per (tile, column-parity warp) slot ...
   int* part_idx = nullptr;         // ... and its lowest column index (cols >= N masked)
+  int part_ld = 0;                 // slots per row (>= 2 * n_tiles)
   // LayerNorm folded into the GEMM (A holds the RAW rows x, W was packed as gamma_k * W[n,k], bias as b_n + sum_k beta_k W[n,k]):
   //   out[r,n] = rstd_r * (acc[r,n] - mean_r * ln_colsum[n]) + bias[n],   mean / rstd from sum_parts ln_stats[part][r * mul + off]
   const float2* ln_stats = nullptr;  // [ln_parts][ln_stats_ld] (sum x, sum x^2) partials written by the producer of A
   int ln_parts = 0; long ln_stats_ld = 0; int ln_row_mul = 1, ln_row_off = 0;
   const float* ln_colsum = nullptr;  // [N] sum_k of the packed (bf16) gamma-folded weights
-  float2* stats_out = nullptr;       // [2 * n_tiles][M]: per-row (sum, sum of squares) of the values this GEMM writes, per tile half
+  float2* stats_out = nullptr;       // [ceil(N / 32)][ln_stats_ld]: per-row (sum, sum of squares) of the values this GEMM writes, per 32-column chunk
   long long* trace = nullptr;      // microbenchmark only: device buffer of >= 640 int64 for CTA 0's clock64 timeline
 };
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st);
@@ -60,7 +61,14 @@ int gemm_bf16_configure();  // cudaFuncSetAttribute for every instantiation (cal
 
 // ---- elementwise.cu -----------------------------------------------------------------------------------------------
 int launch_layernorm(const float* x, long x_row_stride, const float* w, const float* b, ActOut y, int rows, int d, cudaStream_t st);
-int launch_pack_weight(const float* in, int R, int C, bool transpose, ActOut out, cudaStream_t st);
+// scale_k (optional, [K]): multiply every weight by scale_k[k] -- LayerNorm gamma folded into the weight (K = in-features)
+int launch_pack_weight(const float* in, int R, int C, bool transpose, ActOut out, cudaStream_t st, const float* scale_k = nullptr);
+// LayerNorm folding, load time: colsum[n] = sum_k float(w_packed[n,k]);  bias_out[n] = bias[n] + sum_k beta[k] * w(n,k)
+// (w_src: the original fp32 weight, [K,N] when `transposed` else [N,K])
+int launch_fold_ln(const bf16* w_packed, const float* w_src, bool transposed, const float* beta, const float* bias, float* colsum,
+                   float* bias_out, int N, int K, cudaStream_t st);
+// raw rows for a GEMM with folded LayerNorm: xb = bf16(x), stats[row] = (sum xb, sum xb^2)
+int launch_row_stats(const float* x, long x_row_stride, bf16* xb, float2* stats, int rows, int d, cudaStream_t st);
 int launch_convert(const float* in, ActOut out, size_t n, cudaStream_t st);
 int launch_embed_prefix(const float* prefix, int P_img, const float* task, int P_task, const float* wpe, float* h, float* prefix_out,
                         int B, int d, cudaStream_t st);
@@ -83,9 +91,9 @@ int launch_kv_reorder(const T* src, T* dst, const int* beam_idx, int L, int rows
 
 // ---- lmhead.cu ----------------------------------------------------------------------------------------------------
 constexpr int LMHEAD_F32_PARTS = 8;
-int launch_argmax_partials(const float* logits, int B, int V, float* part_val, int* part_idx, cudaStream_t st);
+int launch_argmax_partials(const float* logits, int B, int V, float* part_val, int* part_idx, int part_ld, cudaStream_t st);
 struct FinalizeArgs {
-  const float* part_val; const int* part_idx; int n_parts;  // [n_parts][B]
+  const float* part_val; const int* part_idx; int n_parts, part_ld;  // [B][part_ld], the first n_parts slots of a row are valid
   int B, d, eos, max_new, P, n_pos;
   int* d_step;              // device scalar: index of the token being produced; advanced by the kernel
   int* d_pos;               // device scalar: KV position of the token fed to the next decode step
@@ -96,6 +104,8 @@ struct FinalizeArgs {
   const float* wte_f32; const bf16* wte_bf16;  // exactly one: embedding table [V,d]
   const float* wpe;         // [n_pos, d]
   float* h_next;            // [B, d] fp32: next-step input = wte[tok] + wpe[P + step]
+  bf16* hb_next;            // optional [B, d]: its bf16 copy (A operand of the first GEMM with folded LayerNorm) ...
+  float2* stats_next;       // ... and [B] (sum, sum of squares) of that copy
 };
 int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st);
 int launch_init_decode_state(unsigned char* finished, int* first_eos, int B, int max_new, int* d_step, int* d_pos, int* done_counter,

@@ -37,7 +37,7 @@ __device__ __forceinline__ void block_argmax(float& v, int& idx, float* sv, int*
 }
 
 // fp32 mode: logits [B,V] were materialised by the CUDA-core GEMM; scan them in LMHEAD_F32_PARTS column slabs per row.
-__global__ void __launch_bounds__(256) argmax_partials_kernel(const float* logits, int B, int V, float* part_val, int* part_idx) {
+__global__ void __launch_bounds__(256) argmax_partials_kernel(const float* logits, int B, int V, float* part_val, int* part_idx, int part_ld) {
   __shared__ float sv[8];
   __shared__ int si[8];
   const int b = blockIdx.x, part = blockIdx.y;
@@ -54,14 +54,14 @@ __global__ void __launch_bounds__(256) argmax_partials_kernel(const float* logit
   }
   block_argmax(v, idx, sv, si);
   if (threadIdx.x == 0) {
-    part_val[(size_t)part * B + b] = v;
-    part_idx[(size_t)part * B + b] = idx;
+    part_val[(size_t)b * part_ld + part] = v;
+    part_idx[(size_t)b * part_ld + part] = idx;
   }
 }
 
-int launch_argmax_partials(const float* logits, int B, int V, float* part_val, int* part_idx, cudaStream_t st) {
+int launch_argmax_partials(const float* logits, int B, int V, float* part_val, int* part_idx, int part_ld, cudaStream_t st) {
   dim3 grid(B, LMHEAD_F32_PARTS);
-  GIC_CHECK_CUDA(launch_kernel(argmax_partials_kernel, grid, dim3(256), 0, st, logits, B, V, part_val, part_idx));
+  GIC_CHECK_CUDA(launch_kernel(argmax_partials_kernel, grid, dim3(256), 0, st, logits, B, V, part_val, part_idx, part_ld));
   note_launch();
   return GIC_OK;
 }
@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
   float v = -INFINITY;
   int idx = 0x7fffffff;
   for (int p = threadIdx.x; p < a.n_parts; p += blockDim.x) {
-    const float pv = __ldcg(a.part_val + (size_t)p * a.B + b);
-    const int pi = __ldcg(a.part_idx + (size_t)p * a.B + b);
+    const float pv = __ldcg(a.part_val + (size_t)b * a.part_ld + p);
+    const int pi = __ldcg(a.part_idx + (size_t)b * a.part_ld + p);
     if (better(pv, pi, v, idx)) { v = pv; idx = pi; }
   }
   block_argmax(v, idx, sv, si);
@@ -98,16 +98,29 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
   __syncthreads();
   const int tok = s_tok;
   const int pos = a.P + step;  // position of this token when it is fed back
+  float ssum = 0.f, ssq = 0.f;
   if (pos < a.n_pos) {
     const float* pe = a.wpe + (size_t)pos * a.d;
     float* hn = a.h_next + (size_t)b * a.d;
-    if (a.wte_f32) {
-      const float* te = a.wte_f32 + (size_t)tok * a.d;
-      for (int c = threadIdx.x; c < a.d; c += blockDim.x) hn[c] = te[c] + pe[c];
-    } else {
-      const bf16* te = a.wte_bf16 + (size_t)tok * a.d;
-      for (int c = threadIdx.x; c < a.d; c += blockDim.x) hn[c] = __bfloat162float(te[c]) + pe[c];
+    for (int c = threadIdx.x; c < a.d; c += blockDim.x) {
+      const float x = (a.wte_f32 ? a.wte_f32[(size_t)tok * a.d + c] : __bfloat162float(a.wte_bf16[(size_t)tok * a.d + c])) + pe[c];
+      hn[c] = x;
+      if (a.hb_next) {
+        const bf16 xb = __float2bfloat16_rn(x);
+        a.hb_next[(size_t)b * a.d + c] = xb;
+        const float xf = __bfloat162float(xb);
+        ssum += xf;
+        ssq += xf * xf;
+      }
     }
+  }
+  if (a.stats_next) {  // block-uniform
+    __shared__ float s_sum[4], s_sq[4];
+    ssum = warp_sum(ssum);
+    ssq = warp_sum(ssq);
+    if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = ssum; s_sq[threadIdx.x >> 5] = ssq; }
+    __syncthreads();
+    if (threadIdx.x == 0) a.stats_next[b] = make_float2((s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]), (s_sq[0] + s_sq[1]) + (s_sq[2] + s_sq[3]));
   }
   // the last block to finish advances the device-side step / position counters (all blocks have read them by then)
   __threadfence();

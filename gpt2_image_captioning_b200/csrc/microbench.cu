@@ -122,7 +122,7 @@ int main(int argc, char** argv) {
         GemmBf16Args g;
         OK(make_tma_2d_bf16(&g.a_hi, a, B, d, d, 128));
         OK(make_tma_2d_bf16(&g.w_hi, wte, V, d, d, bn));
-        g.M = B; g.N = V; g.K = d; g.block_n = bn; g.part_val = pv; g.part_idx = pi; g.mma_repeat = rep;
+        g.M = B; g.N = V; g.K = d; g.block_n = bn; g.part_val = pv; g.part_idx = pi; g.part_ld = 2048; g.mma_repeat = rep;
         float us = time_loop(st, 20, [&](int) { OK(launch_gemm_bf16(g, st)); });
         if (rep == 1) base = us;
         const double tiles_per_cta = (double)((B + 127) / 128) * ((V + bn - 1) / bn) / 148.0;
@@ -143,7 +143,7 @@ int main(int argc, char** argv) {
       OK(make_tma_2d_bf16(&g.a_hi, a, B, d, d, 128));
       OK(make_tma_2d_bf16(&g.w_hi, wte, V, d, d, bn));
       g.M = B; g.N = V; g.K = d; g.block_n = bn;
-      if (mode == 1) { g.part_val = pv; g.part_idx = pi; }
+      if (mode == 1) { g.part_val = pv; g.part_idx = pi; g.part_ld = 2048; }
       if (mode == 2) { g.out.hi = big; g.ld_out = V; }
       float us = time_loop(st, 20, [&](int) { OK(launch_gemm_bf16(g, st)); });
       printf("epi_probe block_n=%3d %-14s: %8.2f us  %.1f TFLOP/s\n", bn, mode == 0 ? "no output" : mode == 1 ? "argmax" : "bf16 stores", us,
@@ -162,7 +162,7 @@ int main(int argc, char** argv) {
       OK(make_tma_2d_bf16(&g.a_hi, sh.A, B, sh.K, sh.K, 128));
       OK(make_tma_2d_bf16(&g.w_hi, sh.W, sh.N, sh.K, sh.K, sh.bn));
       g.M = B; g.N = sh.N; g.K = sh.K; g.block_n = sh.bn; g.bias = bias;
-      if (sh.lm) { g.part_val = pv; g.part_idx = pi; g.bias = nullptr; } else { g.out.hi = o; g.ld_out = sh.N; }
+      if (sh.lm) { g.part_val = pv; g.part_idx = pi; g.part_ld = 2048; g.bias = nullptr; } else { g.out.hi = o; g.ld_out = sh.N; }
       for (int i = 0; i < 3; ++i) OK(launch_gemm_bf16(g, st));
       CK(cudaMemsetAsync(tr, 0, 640 * 8, st));
       g.trace = tr;
@@ -196,29 +196,40 @@ int main(int argc, char** argv) {
   struct Shape { const char* name; int N, K; std::vector<bf16*>* w; int epi; bool res; };
   Shape shapes[] = {{"qkv", 3 * d, d, &w_qkv, EPI_NONE, false}, {"proj", d, d, &w_proj, EPI_RESIDUAL, true},
                     {"fc", 4 * d, d, &w_fc, EPI_GELU, false}, {"fc2", d, 4 * d, &w_fc2, EPI_RESIDUAL, true}};
-  for (auto& s : shapes) {
-    for (int bn : {64, 128, 192, 256}) {
-      std::vector<GemmBf16Args> args(SETS);
-      for (int i = 0; i < SETS; ++i) {
-        GemmBf16Args& g = args[i];
-        OK(make_tma_2d_bf16(&g.a_hi, a, B, s.K, s.K, 128));
-        OK(make_tma_2d_bf16(&g.w_hi, (*s.w)[i], s.N, s.K, s.K, bn));
-        g.M = B; g.N = s.N; g.K = s.K; g.block_n = bn; g.epilogue = s.epi; g.bias = bias; g.ld_out = s.N;
-        if (s.res) g.out.f32 = h; else g.out.hi = (s.N == 3 * d ? qkv : o);
+  float2* stats = (float2*)dmalloc((size_t)64 * B * 8);  // [parts][B]
+  float* colsum = (float*)dmalloc((size_t)V * 4);
+  float* bias_v = (float*)dmalloc((size_t)V * 4);
+  for (int fused = 0; fused < 2; ++fused)
+    for (auto& s : shapes) {
+      for (int bn : {64, 128, 192, 256}) {
+        if (fused && bn != gemm_bf16_pick_block_n(B, s.N, 0)) continue;
+        std::vector<GemmBf16Args> args(SETS);
+        for (int i = 0; i < SETS; ++i) {
+          GemmBf16Args& g = args[i];
+          OK(make_tma_2d_bf16(&g.a_hi, a, B, s.K, s.K, 128));
+          OK(make_tma_2d_bf16(&g.w_hi, (*s.w)[i], s.N, s.K, s.K, bn));
+          g.M = B; g.N = s.N; g.K = s.K; g.block_n = bn; g.epilogue = s.epi; g.bias = bias; g.ld_out = s.N;
+          if (s.res) g.out.f32 = h; else g.out.hi = (s.N == 3 * d ? qkv : o);
+          if (fused) {  // LayerNorm folded: statistics in for qkv / fc, bf16 copy + statistics out for the residual GEMMs
+            if (s.res) { g.out.hi = o; g.stats_out = stats; g.ln_stats_ld = B; }
+            else { g.ln_stats = stats; g.ln_parts = d / 32; g.ln_stats_ld = B; g.ln_colsum = colsum; }
+          }
+        }
+        float us = time_loop(st, 240, [&](int i) { OK(launch_gemm_bf16(args[i % SETS], st)); });
+        printf("gemm %-4s%s M=%d N=%d K=%d block_n=%3d: %7.2f us  %6.1f TFLOP/s  (picked %d)\n", s.name, fused ? " +LN" : "    ", B, s.N, s.K, bn, us,
+               2.0 * B * s.N * s.K / us * 1e-6, gemm_bf16_pick_block_n(B, s.N, 0));
       }
-      float us = time_loop(st, 240, [&](int i) { OK(launch_gemm_bf16(args[i % SETS], st)); });
-      printf("gemm %-4s M=%d N=%d K=%d block_n=%3d: %7.2f us  %6.1f TFLOP/s  (picked %d)\n", s.name, B, s.N, s.K, bn, us,
-             2.0 * B * s.N * s.K / us * 1e-6, gemm_bf16_pick_block_n(B, s.N, 0));
     }
-  }
-  for (int bn : {128, 192, 256}) {
-    GemmBf16Args g;
-    OK(make_tma_2d_bf16(&g.a_hi, a, B, d, d, 128));
-    OK(make_tma_2d_bf16(&g.w_hi, wte, V, d, d, bn));
-    g.M = B; g.N = V; g.K = d; g.block_n = bn; g.part_val = pv; g.part_idx = pi;
-    float us = time_loop(st, 50, [&](int) { OK(launch_gemm_bf16(g, st)); });
-    printf("lm_head M=%d N=%d K=%d block_n=%d: %.2f us  %.1f TFLOP/s\n", B, V, d, bn, us, 2.0 * B * V * d / us * 1e-6);
-  }
+  for (int fused = 0; fused < 2; ++fused)
+    for (int bn : {128, 192, 256}) {
+      GemmBf16Args g;
+      OK(make_tma_2d_bf16(&g.a_hi, a, B, d, d, 128));
+      OK(make_tma_2d_bf16(&g.w_hi, wte, V, d, d, bn));
+      g.M = B; g.N = V; g.K = d; g.block_n = bn; g.part_val = pv; g.part_idx = pi; g.part_ld = 2048;
+      if (fused) { g.ln_stats = stats; g.ln_parts = d / 32; g.ln_stats_ld = B; g.ln_colsum = colsum; g.bias = bias_v; }
+      float us = time_loop(st, 50, [&](int) { OK(launch_gemm_bf16(g, st)); });
+      printf("lm_head%s M=%d N=%d K=%d block_n=%d: %.2f us  %.1f TFLOP/s\n", fused ? " +LN" : "    ", B, V, d, bn, us, 2.0 * B * V * d / us * 1e-6);
+    }
   // ---- decode attention ----
   for (int ctx : {11, 25, 39}) {
     int pos = ctx - 1;
