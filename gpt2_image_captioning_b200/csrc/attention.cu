@@ -12,6 +12,8 @@
 //  kv_reorder   : beam-search cache gather, index_select(0, beam_idx) per layer (HF:cache_utils.py:81-85).
 //
 // KV cache layout (one layer): K [rows][H][T_max][64], V the same; element type T (bf16 or fp32).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace gic {
@@ -152,8 +154,227 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const T* qkv, T* kcach
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 decode attention, bulk-copy pipeline (the product path).  One persistent CTA per SM, 8 warps; every warp walks its
+// own list of (row, head) items and streams their K / V rows (contiguous pos x 128 bytes each) into its private
+// shared-memory ring with cp.async.bulk + mbarrier, up to DEC_STAGES chunks of 32 keys ahead.  The copy engine keeps
+// ~100 KB per SM in flight without holding registers, so the HBM stream does not stall on the softmax arithmetic or on
+// block scheduling (the one-warp-per-item kernel above pays a ~9 us launch / wave ramp per layer: 23 us for 79 MB).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int DEC_WARPS = 16;
+constexpr int DEC_CHUNK = 16;   // keys per stage
+constexpr int DEC_STAGES = 3;   // per warp
+constexpr int DEC_STAGE_BYTES = 2 * DEC_CHUNK * HD * 2;  // K chunk + V chunk, bf16
+constexpr int DEC_SMEM_BYTES = DEC_WARPS * DEC_STAGES * DEC_STAGE_BYTES + DEC_WARPS * DEC_STAGES * 8 + 128;
+
+__device__ __forceinline__ uint32_t dec_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void dec_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void dec_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(DEC_WARPS * 32, 1) attn_decode_bulk_kernel(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out,
+                                                                           const int* d_pos, int rows, int H, int t_max) {
+  extern __shared__ uint8_t dec_smem_raw[];
+  const uint32_t smem_base = (dec_smem_u32(dec_smem_raw) + 127u) & ~127u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring = smem_base + warp * (DEC_STAGES * DEC_STAGE_BYTES);
+  const uint32_t bars = smem_base + DEC_WARPS * DEC_STAGES * DEC_STAGE_BYTES + warp * (DEC_STAGES * 8);
+  pdl_launch_dependents();
+  if (lane == 0) {
+    for (int s = 0; s < DEC_STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8 * s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  pdl_wait();
+  const int pos = __ldcg(d_pos);  // tokens already cached == position of the new token
+  const int d = H * HD;
+  const int n_items = rows * H;
+  const int wstride = gridDim.x * DEC_WARPS;
+  const int w0 = blockIdx.x * DEC_WARPS + warp;
+  const int nch = (pos + DEC_CHUNK - 1) / DEC_CHUNK;  // chunks per item (0 when nothing is cached yet)
+  const int my_items = w0 < n_items ? (n_items - 1 - w0) / wstride + 1 : 0;
+  const int total_chunks = my_items * nch;
+  const int g = lane >> 3, sub = lane & 7;  // 4 lane groups of 8: a group takes keys g, g + 4, ... of a chunk
+
+  // producer side (lane 0): chunk n of this warp's stream -> stage n % DEC_STAGES
+  auto issue = [&](int n) {
+    const int item = w0 + (n / nch) * wstride, c = n % nch;
+    const int row = item / H, h = item % H;
+    const int nkeys = min(DEC_CHUNK, pos - c * DEC_CHUNK);
+    const uint32_t bytes = (uint32_t)nkeys * HD * 2;
+    const int s = n % DEC_STAGES;
+    const size_t off = (((size_t)row * H + h) * t_max + (size_t)c * DEC_CHUNK) * HD;
+    const uint32_t bar = bars + 8 * s, dst = ring + s * DEC_STAGE_BYTES;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * bytes) : "memory");
+    dec_bulk_load(dst, kcache + off, bytes, bar);
+    dec_bulk_load(dst + DEC_CHUNK * HD * 2, vcache + off, bytes, bar);
+  };
+  if (lane == 0)
+    for (int n = 0; n < DEC_STAGES - 1 && n < total_chunks; ++n) issue(n);
+
+  int n = 0;
+  // q / k / v of the new token are requested one item ahead (they come from L2: the qkv GEMM has just written them)
+  Vec16<bf16> qv_n, knew_n, vnew_n;
+  auto load_new = [&](int item) {
+    const bf16* qrow = qkv + (size_t)(item / H) * 3 * d + (item % H) * HD;
+    qv_n.load(qrow + sub * 8);
+    knew_n.load(qrow + d + sub * 8);
+    vnew_n.load(qrow + 2 * d + sub * 8);
+  };
+  if (my_items > 0) load_new(w0);
+  for (int ii = 0; ii < my_items; ++ii) {
+    const int item = w0 + ii * wstride;
+    const int row = item / H, h = item % H;
+    const Vec16<bf16> qv = qv_n, knew = knew_n, vnew = vnew_n;
+    if (ii + 1 < my_items) load_new(item + wstride);
+    float qf[8];
+    qv.unpack(qf);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qf[i] *= 0.125f;  // 1/sqrt(64), HF :211-220 (sdpa default scale)
+    // the new token (position pos): its K / V come straight from the qkv row and are appended to the cache by group 0
+    float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    {
+      float kf[8];
+      knew.unpack(kf);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s = fmaf(qf[i], kf[i], s);
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (g == 0) {
+        m = s;
+        l = 1.f;
+        vnew.unpack(acc);
+        bf16* kdst = kcache + (((size_t)row * H + h) * t_max + pos) * HD + sub * 8;
+        bf16* vdst = vcache + (((size_t)row * H + h) * t_max + pos) * HD + sub * 8;
+        knew.store(kdst);
+        vnew.store(vdst);
+      }
+    }
+    for (int c = 0; c < nch; ++c, ++n) {
+      // keep the ring full: the stage freed by the previous chunk takes chunk n + DEC_STAGES - 1
+      if (lane == 0 && n + DEC_STAGES - 1 < total_chunks) issue(n + DEC_STAGES - 1);
+      const int s = n % DEC_STAGES;
+      dec_mbar_wait(bars + 8 * s, (uint32_t)((n / DEC_STAGES) & 1));
+      const int nkeys = min(DEC_CHUNK, pos - c * DEC_CHUNK);
+      const uint32_t kst = ring + s * DEC_STAGE_BYTES + sub * 16, vst = kst + DEC_CHUNK * HD * 2;
+      float sc[DEC_CHUNK / 4];
+      float bm = m;
+#pragma unroll
+      for (int u = 0; u < DEC_CHUNK / 4; ++u) {
+        const int j = u * 4 + g;
+        Vec16<bf16> kv;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(kv.raw.x), "=r"(kv.raw.y), "=r"(kv.raw.z), "=r"(kv.raw.w) : "r"(kst + j * (HD * 2)));
+        float kf[8];
+        kv.unpack(kf);
+        float sdot = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sdot = fmaf(qf[i], kf[i], sdot);
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+        sc[u] = j < nkeys ? sdot : -INFINITY;  // rows beyond nkeys hold stale bytes of an earlier chunk: masked here
+        bm = fmaxf(bm, sc[u]);
+      }
+      if (bm > -INFINITY) {
+        const float scale = (m == -INFINITY) ? 0.f : expf(m - bm);
+        l *= scale;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] *= scale;
+#pragma unroll
+        for (int u = 0; u < DEC_CHUNK / 4; ++u) {
+          const int j = u * 4 + g;
+          if (j < nkeys) {
+            const float pr = expf(sc[u] - bm);
+            l += pr;
+            Vec16<bf16> vv;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(vv.raw.x), "=r"(vv.raw.y), "=r"(vv.raw.z), "=r"(vv.raw.w) : "r"(vst + j * (HD * 2)));
+            float vf[8];
+            vv.unpack(vf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(pr, vf[i], acc[i]);
+          }
+        }
+        m = bm;
+      }
+      __syncwarp();  // every lane is done reading this stage before lane 0 may refill it (next iteration's issue)
+    }
+    // merge the 4 lane groups
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, o);
+      const float ol = __shfl_xor_sync(0xffffffffu, l, o);
+      const float nm = fmaxf(m, om);
+      const float sa = (m == -INFINITY) ? 0.f : expf(m - nm);
+      const float sb = (om == -INFINITY) ? 0.f : expf(om - nm);
+      l = l * sa + ol * sb;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float oa = __shfl_xor_sync(0xffffffffu, acc[i], o);
+        acc[i] = acc[i] * sa + oa * sb;
+      }
+      m = nm;
+    }
+    if (g == 0) {
+      const float inv = 1.0f / l;
+      float of[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) of[i] = acc[i] * inv;
+      Vec16<bf16> ov;
+      ov.pack(of);
+      ov.store(out + (size_t)row * d + h * HD + sub * 8);
+    }
+  }
+}
+
+static int g_dec_sms = 0;
+// opt the bulk-copy kernel into its shared memory size once (engine creation: outside any stream capture)
+int attn_decode_configure() {
+  if (g_dec_sms > 0) return GIC_OK;
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES));
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  g_dec_sms = sms;
+  return GIC_OK;
+}
+
+static int launch_attn_decode_bulk(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos, int rows, int H, int t_max,
+                                   cudaStream_t st) {
+  GIC_TRY(attn_decode_configure());
+  const int sms = g_dec_sms;
+  const int items = rows * H;
+  const int grid = min(sms, ceil_div(items, DEC_WARPS));
+  GIC_CHECK_CUDA(launch_kernel(attn_decode_bulk_kernel, dim3(grid), dim3(DEC_WARPS * 32), (size_t)DEC_SMEM_BYTES, st, qkv, kcache, vcache, out, d_pos,
+                               rows, H, t_max));
+  note_launch();
+  return GIC_OK;
+}
+
+static bool decode_bulk_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* v = getenv("GIC_ATTN_SIMPLE"); on = (v && v[0] == '1') ? 0 : 1; }
+  return on == 1;
+}
+template <typename T> struct IsBf16 { static constexpr bool value = false; };
+template <> struct IsBf16<bf16> { static constexpr bool value = true; };
+
 template <typename T>
 int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows, int H, int t_max, cudaStream_t st) {
+  if (IsBf16<T>::value && out.hi && !out.lo && !out.f32 && decode_bulk_enabled())
+    return launch_attn_decode_bulk((const bf16*)qkv, (bf16*)kcache, (bf16*)vcache, out.hi, d_pos, rows, H, t_max, st);
   const int warps = rows * H;
   const int blocks = ceil_div(warps, 4);
   const size_t smem = 0;

@@ -592,6 +592,7 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
   if (e->tc) {
     int r = gic::tma_init();
     if (r == GIC_OK) r = gic::gemm_bf16_configure();
+    if (r == GIC_OK) r = gic::attn_decode_configure();
     if (r != GIC_OK) { delete e; return r; }
   }
   const char* sb = getenv("GIC_SUBBATCH");

@@ -112,7 +112,7 @@ int main(int argc, char** argv) {
   }
   bf16* wte = (bf16*)dmalloc((size_t)V * d * 2);
   float* pv = (float*)dmalloc((size_t)2048 * B * 4); int* pi = (int*)dmalloc((size_t)2048 * B * 4);
-  OK(tma_init()); OK(gemm_bf16_configure());
+  OK(tma_init()); OK(gemm_bf16_configure()); OK(attn_decode_configure());
 
   // ---- tensor-pipe probe: the LM-head GEMM with every MMA re-issued R times (no extra operand traffic) ----
   if (argc > 2 && atoi(argv[2]) == 2) {
