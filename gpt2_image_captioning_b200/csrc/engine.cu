@@ -65,6 +65,7 @@ struct Workspace {
   size_t kv_layer_elems = 0;       // elements of one K (or V) plane of one layer
   float* logits = nullptr;         // [rows, V] fp32 (F32 mode)
   float* part_val = nullptr; int* part_idx = nullptr; int n_parts_max = 0;  // [rows][n_parts_max]
+  float* splitk_ws = nullptr; size_t splitk_ws_floats = 0; int* splitk_counters = nullptr;  // split-K partials / per-tile arrival counters
   float2* ln_stats = nullptr; int ln_parts_max = 0;  // [ln_parts_max][m_max] row (sum, sum of squares) partials (folded LayerNorm)
   int64_t* ids = nullptr;          // [rows, max_new]
   unsigned char* finished = nullptr; int* first_eos = nullptr;
@@ -84,6 +85,8 @@ struct gic_engine {
   int d = 0, L = 0, H = 0, V = 0, P_img = 0, P_task = 0, E = 0;
   bool split = false;  // BF16X2
   bool fuse_ln = false;  // BF16: ln_1 / ln_2 folded into the GEMM that follows them (no LayerNorm launches inside the GPT-2 blocks)
+  bool use_splitk = false;  // GIC_SPLITK=1 turns the K split of the decode-size residual GEMMs on.  Off by default: measured round 1
+                            // (profiles/r1w_microbench.txt), fc2 with a 3-way K split + last-CTA reduction takes 22 us against 15 us unsplit
   bool fuse_lnf = false; // ... and ln_f into the LM head (GIC_LNF_FUSE=1).  Off by default: measured round 1, the folded head re-reads the
                          // row statistics and column sums for each of its ~10 tiles per CTA and costs 79 us against 3.8 + 55 us
   bf16* wte_gather = nullptr;  // BF16: unfolded bf16 embedding table for the next-token gather
@@ -275,6 +278,11 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
     w->ln_parts_max = ceil_div(d, 32);
     w->ln_stats = c.take<float2>((size_t)w->ln_parts_max * m);
   }
+  if (e->tc && !e->split) {  // split-K is used by the decode-size residual GEMMs (few tiles, K up to 4 d)
+    w->splitk_ws_floats = (size_t)4 * w->rows * d;
+    w->splitk_ws = c.take<float>(w->splitk_ws_floats);
+    w->splitk_counters = c.take<int>(4096);
+  }
   w->part_val = c.take<float>((size_t)w->n_parts_max * w->rows);
   w->part_idx = c.take<int>((size_t)w->n_parts_max * w->rows);
   w->ids = c.take<int64_t>((size_t)w->rows * (max_new > 0 ? max_new : 1));
@@ -295,6 +303,7 @@ struct LnIo {
   const float2* stats_in = nullptr; int parts_in = 0; long stats_ld = 0; int row_mul = 1, row_off = 0;
   float2* stats_out = nullptr;
   long a_row_stride = 0;  // A rows are `a_row_stride` elements apart (0: dense)
+  float* splitk_ws = nullptr; size_t splitk_ws_floats = 0; int* splitk_counters = nullptr;  // set: this GEMM may split K
 };
 // number of statistics parts a residual GEMM leaves behind: one per 32 output columns, whatever the tile width or M
 // (so that a row's LayerNorm statistics are summed in the same order in any batch)
@@ -307,7 +316,13 @@ static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, i
     return launch_sgemm_nt(A.f32, lin.K, lin.w_f32, lin.bias, out.f32, ld_out, M, lin.N, lin.K, epilogue, st);
   }
   GemmBf16Args g;
-  const int bn = gemm_bf16_pick_block_n(M, lin.N, e->split ? 1 : 0);
+  int bn = 0, sk = 1;
+  if (ln && ln->splitk_ws && !part_val && e->use_splitk) {
+    sk = gemm_bf16_split_k_for(lin.N, lin.K);
+    if ((size_t)sk * M * lin.N > ln->splitk_ws_floats) sk = 1;
+  }
+  gemm_bf16_pick(M, lin.N, lin.K, e->split ? 1 : 0, sk, &bn);
+  if (sk > 1) { g.split_k = sk; g.splitk_ws = ln->splitk_ws; g.splitk_counters = ln->splitk_counters; }
   const int bi = box_rows_index(bn);
   GIC_REQUIRE(bi >= 0, "no W tensor map for box height %d", bn);
   GIC_TRY(make_tma_2d_bf16(&g.a_hi, A.hi, M, lin.K, (ln && ln->a_row_stride) ? ln->a_row_stride : lin.K, 128));
@@ -360,6 +375,7 @@ static int gpt_layer(const gic_engine* e, const Workspace& w, int l, float* h, i
     const int parts_res = residual_stats_parts(e, M);
     LnIo in; in.stats_in = w.ln_stats; in.parts_in = parts_in; in.stats_ld = w.m_max;
     LnIo res; res.stats_out = w.ln_stats; res.stats_ld = w.m_max;
+    if (!prefill) { res.splitk_ws = w.splitk_ws; res.splitk_ws_floats = w.splitk_ws_floats; res.splitk_counters = w.splitk_counters; }
     ActOut hres2 = hres; hres2.hi = w.a.hi;
     { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_qkv", st);
       GIC_TRY(linear(e, Lw.attn, w.a, M, EPI_NONE, qkv_out(w), 3 * d, st, nullptr, nullptr, nullptr, 0, &in)); }
@@ -584,6 +600,8 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
   {
     const char* nf = getenv("GIC_NO_LNFUSE");
     e->fuse_ln = cfg->dtype == GIC_DTYPE_BF16 && !(nf && nf[0] == '1');
+    const char* sk = getenv("GIC_SPLITK");
+    e->use_splitk = sk && sk[0] == '1';
     const char* hf = getenv("GIC_LNF_FUSE");
     e->fuse_lnf = e->fuse_ln && hf && hf[0] == '1';
   }
@@ -754,6 +772,7 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   GIC_TRY(fork_stream(e, user));
 
   GIC_TRY(launch_init_decode_state(w.finished, w.first_eos, B, max_new, w.d_step, w.d_pos, w.done_counter, P, st));
+  if (w.splitk_counters) GIC_CHECK_CUDA(cudaMemsetAsync(w.splitk_counters, 0, 4096 * sizeof(int), st));
   if (e->profiling) GIC_TRY(launch_spin(150000000LL, st));  // ~75 ms: lets the host queue ahead so events time the device only
   { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
   GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));
@@ -822,6 +841,7 @@ int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int
   const int d = e->d, B = batch, P = w.P, nb = num_beams, rows = w.rows, K = 2 * nb;
   GIC_TRY(fork_stream(e, user));
   GIC_TRY(launch_beam_init(w.beam, st));
+  if (w.splitk_counters) GIC_CHECK_CUDA(cudaMemsetAsync(w.splitk_counters, 0, 4096 * sizeof(int), st));
   { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
   GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));
   // prefill once per image; its K/V land in cache row b*beams and the first reorder fans them out to every beam
@@ -949,6 +969,67 @@ int gic_test_gemm(int dtype, const float* A, const float* W, const float* bias, 
   if (r == GIC_OK) r = launch_gemm_bf16(g, st);
   cudaError_t ce = cudaStreamSynchronize(st);
   cudaFree(a_hi); cudaFree(w_hi); cudaFree(a_lo); cudaFree(w_lo);
+  if (r != GIC_OK) return r;
+  GIC_CHECK_CUDA(ce);
+  return GIC_OK;
+}
+
+// The fused bf16 MLP sub-block exactly as a decode / prefill layer runs it, on caller data (kernel-level parity test):
+//   xb, stats = row_stats(h);  f = gelu(LN_folded(xb) . Wfc^T + bfc)  [bf16];  h += f . Wfc2^T + bfc2  (+ bf16 copy + statistics),
+// fc2 optionally K-split.  h [M,d] fp32 in/out; hb_out [M,d] bf16; stats_out [d/32][M] float2 (sum, sum of squares of hb_out).
+int gic_test_ln_mlp(float* h, const float* gamma, const float* beta, const float* wfc, const float* bfc, const float* wfc2, const float* bfc2,
+                    void* hb_out, void* stats_out, int M, int d, int split_k, void* stream) {
+  GIC_REQUIRE(h && gamma && beta && wfc && bfc && wfc2 && bfc2 && hb_out && stats_out, "null argument");
+  GIC_REQUIRE(d % 64 == 0 && split_k >= 1 && split_k <= 4, "d must be a multiple of 64 and split_k in [1, 4]");
+  cudaStream_t st = (cudaStream_t)stream;
+  GIC_TRY(gic_device_check());
+  GIC_TRY(gic::tma_init());
+  GIC_TRY(gic::gemm_bf16_configure());
+  const int d4 = 4 * d;
+  bf16 *xb = nullptr, *wfc_p = nullptr, *wfc2_p = nullptr, *f = nullptr;
+  float *colsum = nullptr, *bias_f = nullptr, *ws = nullptr;
+  float2* stats = nullptr;
+  int* counters = nullptr;
+  std::vector<void*> owned;
+  auto take = [&](void** p, size_t bytes) { cudaError_t ce = cudaMalloc(p, bytes); if (ce == cudaSuccess) owned.push_back(*p); return ce; };
+  int r = GIC_OK;
+  do {
+    if (take((void**)&xb, (size_t)M * d * 2) || take((void**)&wfc_p, (size_t)d4 * d * 2) || take((void**)&wfc2_p, (size_t)d * d4 * 2) ||
+        take((void**)&f, (size_t)M * d4 * 2) || take((void**)&colsum, (size_t)d4 * 4) || take((void**)&bias_f, (size_t)d4 * 4) ||
+        take((void**)&stats, (size_t)M * 8) || take((void**)&ws, (size_t)split_k * M * d * 4) || take((void**)&counters, 4096 * 4)) {
+      set_error("gic_test_ln_mlp: cudaMalloc failed"); r = GIC_ERR_CUDA; break;
+    }
+    if (cudaMemsetAsync(counters, 0, 4096 * 4, st) != cudaSuccess) { set_error("memset failed"); r = GIC_ERR_CUDA; break; }
+    ActOut o1; o1.hi = wfc_p;
+    ActOut o2; o2.hi = wfc2_p;
+    if ((r = launch_pack_weight(wfc, d4, d, false, o1, st, gamma)) != GIC_OK) break;      // nn.Linear layout [N,K], gamma folded
+    if ((r = launch_fold_ln(wfc_p, wfc, false, beta, bfc, colsum, bias_f, d4, d, st)) != GIC_OK) break;
+    if ((r = launch_pack_weight(wfc2, d, d4, false, o2, st)) != GIC_OK) break;
+    if ((r = launch_row_stats(h, d, xb, stats, M, d, st)) != GIC_OK) break;
+    {
+      GemmBf16Args g;
+      int bn = 0;
+      gemm_bf16_pick(M, d4, d, 0, 1, &bn);
+      if ((r = make_tma_2d_bf16(&g.a_hi, xb, M, d, d, 128)) != GIC_OK) break;
+      if ((r = make_tma_2d_bf16(&g.w_hi, wfc_p, d4, d, d, bn)) != GIC_OK) break;
+      g.M = M; g.N = d4; g.K = d; g.block_n = bn; g.epilogue = EPI_GELU; g.bias = bias_f; g.out.hi = f; g.ld_out = d4;
+      g.ln_stats = stats; g.ln_parts = 1; g.ln_stats_ld = M; g.ln_colsum = colsum;
+      if ((r = launch_gemm_bf16(g, st)) != GIC_OK) break;
+    }
+    {
+      GemmBf16Args g;
+      int bn = 0;
+      gemm_bf16_pick(M, d, d4, 0, split_k, &bn);
+      if ((r = make_tma_2d_bf16(&g.a_hi, f, M, d4, d4, 128)) != GIC_OK) break;
+      if ((r = make_tma_2d_bf16(&g.w_hi, wfc2_p, d, d4, d4, bn)) != GIC_OK) break;
+      g.M = M; g.N = d; g.K = d4; g.block_n = bn; g.epilogue = EPI_RESIDUAL; g.bias = bfc2; g.out.f32 = h; g.out.hi = (bf16*)hb_out; g.ld_out = d;
+      g.stats_out = (float2*)stats_out; g.ln_stats_ld = M;
+      if (split_k > 1) { g.split_k = split_k; g.splitk_ws = ws; g.splitk_counters = counters; }
+      if ((r = launch_gemm_bf16(g, st)) != GIC_OK) break;
+    }
+  } while (0);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  for (void* p : owned) cudaFree(p);
   if (r != GIC_OK) return r;
   GIC_CHECK_CUDA(ce);
   return GIC_OK;

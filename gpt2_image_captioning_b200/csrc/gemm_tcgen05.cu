@@ -163,6 +163,9 @@ struct alignas(64) GemmKernelParams {
   float* part_val; int* part_idx; int part_ld;  // [M][part_ld]: slot (tile * 2 + column-parity warp) of each row
   // folded LayerNorm on the A operand (see launch_gemm_bf16): out = rstd_r * (acc - mean_r * colsum_n) + bias_n
   const float2* ln_stats; int ln_parts; long ln_stats_ld; int ln_row_mul, ln_row_off; const float* ln_colsum;
+  // split-K (see launch_gemm_bf16): `split_k` CTAs share one output tile, each over K / split_k; fp32 partials go to splitk_ws
+  // [split_k][M][N] and the CTA that arrives last at splitk_counters[tile] sums them in split order and runs the epilogue
+  int split_k; float* splitk_ws; int* splitk_counters;
   float2* stats_out;  // [ceil(N / 32)][ln_stats_ld] (sum, sum of squares) of the values written, per row and 32-column chunk
   long long* trace;  // null; microbenchmark only: clock64 timeline of CTA 0's producer / MMA / epilogue warps
 };
@@ -205,7 +208,9 @@ __device__ __forceinline__ float epi_act(float x, bool precise) {
 enum GemmOut { OUT_NONE = 0 /* argmax partials only */, OUT_F32 = 1, OUT_BF16 = 2, OUT_BF16X2 = 3 /* hi + lo */, OUT_F32_BF16_STATS = 4 /* fused residual:
                 fp32 stream + its bf16 copy + per-row (sum, sum of squares) partials for the LayerNorm folded into the next GEMM */ };
 // FOLD: LayerNorm folded into this GEMM (see GemmBf16Args::ln_stats).
-template <int BLOCK_N, bool SPLIT, int EPI, int OUT, bool FOLD>
+// RAGGED: N % 32 != 0 or a leading dimension that is not a multiple of 4 -- only these instantiations carry the slow generic
+// store path (every kernel here runs once per launch with a cold instruction cache: code size is latency).
+template <int BLOCK_N, bool SPLIT, int EPI, int OUT, bool FOLD, bool RAGGED>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKernelParams p) {
   using Tile = GemmTile<BLOCK_N, SPLIT>;
   constexpr int STAGES = Tile::STAGES;
@@ -220,6 +225,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   const uint32_t tmem_full_bar = empty_bar + 8 * STAGES;     // [2]
   const uint32_t tmem_empty_bar = tmem_full_bar + 16;        // [2]
   const uint32_t tmem_slot = tmem_empty_bar + 16;
+  volatile int* s_flag = reinterpret_cast<volatile int*>(smem_gen + OFF_BAR + 512);  // split-K: "this CTA arrived last" broadcast
   float4* s_stage = reinterpret_cast<float4*>(smem_gen + OFF_BAR + 1024);  // [8 warps][32 rows][8 chunks]
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // warp-uniform by construction
@@ -228,6 +234,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int total_tiles = m_tiles * n_tiles;
   const int nk = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int total_work = total_tiles * p.split_k;  // work item w: tile = w % total_tiles, K slice = w / total_tiles
   pdl_launch_dependents();  // let the next kernel's CTAs be scheduled behind this grid (see common.cuh)
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
   const long long t_start = tracing ? clock64() : 0;
@@ -262,9 +269,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   if (warp == 0) {
     // ===== TMA producer: streams k-blocks of successive tiles through the ring without pausing at tile boundaries =====
     uint32_t s = 0, ph = 0, it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      const int tile = work % total_tiles, ks = work / total_tiles;
       const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
-      for (int kb = 0; kb < nk; ++kb, ++it) {
+      const int kb_end = (int)((long)(ks + 1) * nk / p.split_k);
+      for (int kb = (int)((long)ks * nk / p.split_k); kb < kb_end; ++kb, ++it) {
         ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
         if (ptx::elect_one()) {
           const uint32_t st = smem_base + s * Tile::STAGE_BYTES;
@@ -285,12 +294,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     // ===== MMA issuer (one elected lane, whole warp converged), alternating between the two TMEM accumulators =====
     constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
     uint32_t s = 0, ph = 0, it = 0, local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++local) {
+      const int ks = work / total_tiles;
+      const int kb_begin = (int)((long)ks * nk / p.split_k), kb_end = (int)((long)(ks + 1) * nk / p.split_k);
       const uint32_t acc = local & 1, use = local >> 1;
       ptx::mbar_wait(tmem_empty_bar + 8 * acc, (use & 1) ^ 1);  // epilogue has drained this accumulator (passes at first use)
       ptx::tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * Tile::ACC_COLS;
-      for (int kb = 0; kb < nk; ++kb, ++it) {
+      for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
         ptx::mbar_wait(full_bar + 8 * s, ph);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -304,7 +315,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
 #pragma unroll
             for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
               const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per k-step inside the 128-byte swizzle row
-              ptx::umma_bf16(tmem_acc, a_hi + koff, w_hi + koff, idesc, (kb | k | rep) != 0);
+              ptx::umma_bf16(tmem_acc, a_hi + koff, w_hi + koff, idesc, ((kb - kb_begin) | k | rep) != 0);
               if (SPLIT) {
                 ptx::umma_bf16(tmem_acc, a_hi + koff, w_lo + koff, idesc, 1);
                 ptx::umma_bf16(tmem_acc, a_lo + koff, w_hi + koff, idesc, 1);
@@ -312,7 +323,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             }
           }
           ptx::umma_commit(empty_bar + 8 * s);                          // smem slot is free once these MMAs have read it
-          if (kb == nk - 1) ptx::umma_commit(tmem_full_bar + 8 * acc);  // accumulator complete
+          if (kb == kb_end - 1) ptx::umma_commit(tmem_full_bar + 8 * acc);  // accumulator complete
           if (tracing && it < 60) p.trace[256 + it * 4 + 2] = clock64() - t_start;
         }
         __syncwarp();
@@ -330,7 +341,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     const int cchunk = lane & 7, crow0 = lane >> 3;
     constexpr bool fold = FOLD;
     uint32_t local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++local) {
+      const int tile = work % total_tiles, ks = work / total_tiles;
       const uint32_t acc = local & 1, use = local >> 1;
       const int n_tile = tile / m_tiles;
       const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
@@ -485,7 +497,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         b4_n = make_float4(0.f, 0.f, 0.f, 0.f);
         cs4_n = make_float4(0.f, 0.f, 0.f, 0.f);
         if (col0 >= p.N) return;
-        if ((col0 + 32 <= p.N) && vec_f32 && vec_bf16) {
+        if (!RAGGED || ((col0 + 32 <= p.N) && vec_f32 && vec_bf16)) {
           if (EPI == EPI_RESIDUAL) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -524,14 +536,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           }
         }
       };
-      if (sub * 32 < BLOCK_N) prefetch(sub * 32);
-      ptx::mbar_wait(tmem_full_bar + 8 * acc, use & 1);
-      ptx::tc_fence_after();
-      if (tracing && e == 0 && lane == 0 && local < 8) p.trace[512 + local * 4 + 1] = clock64() - t_start;
+      // split-K: phase 0 parks this CTA's raw fp32 partial tile in the workspace; the CTA that arrives last at the tile's
+      // counter runs phase 1 = the normal epilogue on the sum of all partials (added in split order: deterministic)
+      const bool split = EPI == EPI_RESIDUAL && p.split_k > 1;  // (the K split is offered for the residual GEMMs only)
       const uint32_t tmem_acc = tmem_base + acc * Tile::ACC_COLS + ((uint32_t)(q * 32) << 16);
-      if (sub * 32 >= BLOCK_N) {  // BLOCK_N == 32: the second warp of the quarter has no chunk, it only releases the accumulator
-        ptx::tc_fence_before();
-        if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
+#pragma unroll 1
+      for (int phase = 0; phase < (split ? 2 : 1); ++phase) {
+      const bool to_ws = split && phase == 0, from_ws = split && phase == 1;
+      if (!to_ws && sub * 32 < BLOCK_N) prefetch(sub * 32);
+      if (phase == 0) {
+        ptx::mbar_wait(tmem_full_bar + 8 * acc, use & 1);
+        ptx::tc_fence_after();
+        if (tracing && e == 0 && lane == 0 && local < 8) p.trace[512 + local * 4 + 1] = clock64() - t_start;
+        if (sub * 32 >= BLOCK_N) {  // BLOCK_N == 32: the second warp of the quarter has no chunk, it only releases the accumulator
+          ptx::tc_fence_before();
+          if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
+        }
       }
 #pragma unroll 1
       for (int c0 = sub * 32; c0 < BLOCK_N; c0 += 64) {
@@ -540,32 +560,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         long long* trc = p.trace + 540 + (c0 >> 6) * 8;
         if (tr) trc[0] = clock64() - t_start;
         // whole chunk inside the matrix and every row pointer 16-byte aligned: the specialised path below
-        const bool fast = (col0 + 32 <= p.N) && vec_f32 && vec_bf16;
+        const bool fast = !RAGGED || ((col0 + 32 <= p.N) && vec_f32 && vec_bf16);
         float4 res[8];
         if (EPI == EPI_RESIDUAL) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) res[i] = res_n[i];
         }
         const float4 b4 = b4_n, cs4 = cs4_n;
-        if (c0 + 64 < BLOCK_N) prefetch(c0 + 64);
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_acc + (uint32_t)c0, r);
-        ptx::tmem_ld_wait();
-        if (tr) trc[1] = clock64() - t_start;
-        if (c0 + 64 >= BLOCK_N) {
-          // this warp's last TMEM read of the tile: hand the accumulator back to the MMA warp before the math / stores
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
-        }
-        if (col0 >= p.N) continue;  // warp-uniform
-        // lane = row  ->  staging tile (chunk position XOR row keeps both directions bank-conflict free)
-        __syncwarp();  // previous chunk's readers are done with the staging tile
+        if (!to_ws && c0 + 64 < BLOCK_N) prefetch(c0 + 64);
+        if (!from_ws) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_acc + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          if (tr) trc[1] = clock64() - t_start;
+          if (c0 + 64 >= BLOCK_N) {
+            // this warp's last TMEM read of the tile: hand the accumulator back to the MMA warp before the math / stores
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
+          }
+          if (col0 >= p.N) continue;  // warp-uniform
+          // lane = row  ->  staging tile (chunk position XOR row keeps both directions bank-conflict free)
+          __syncwarp();  // previous chunk's readers are done with the staging tile
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          stage[lane * 8 + (c ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
-                                                           __uint_as_float(r[4 * c + 3]));
-        __syncwarp();
+          for (int c = 0; c < 8; ++c)
+            stage[lane * 8 + (c ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]), __uint_as_float(r[4 * c + 2]),
+                                                             __uint_as_float(r[4 * c + 3]));
+          __syncwarp();
+        } else if (col0 >= p.N) continue;
         if (tr) trc[2] = clock64() - t_start;
         if (fast) {
           // ---- specialised path: OUT / EPI / FOLD are compile-time, so this is a few instructions per element ----
@@ -578,10 +600,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           // three separate passes (load, math, store) so that the eight rows overlap instead of running as eight dependent
           // load -> add -> convert -> store chains
           float4 o[8];
+          if (!from_ws) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int lr = crow0 + 4 * i;
-            o[i] = stage[lr * 8 + (cchunk ^ (lr & 7))];
+            for (int i = 0; i < 8; ++i) {
+              const int lr = crow0 + 4 * i;
+              o[i] = stage[lr * 8 + (cchunk ^ (lr & 7))];
+            }
+          }
+          if (split) {
+            // (split-K runs on whole, aligned tiles only -- launch_gemm_bf16 checks -- so every chunk takes this path)
+            const int rows_ok = min(32, p.M - wrow0);
+            float* wsp = p.splitk_ws + ((size_t)(wrow0 + crow0)) * p.N + col;
+            const size_t ws_row4 = (size_t)4 * p.N, ws_split = (size_t)p.M * p.N;
+            if (to_ws) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (crow0 + 4 * i < rows_ok) __stcg(reinterpret_cast<float4*>(wsp + (size_t)ks * ws_split + i * ws_row4), o[i]);
+              continue;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int sp = 0; sp < p.split_k; ++sp) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (crow0 + 4 * i < rows_ok) {
+                  const float4 t = __ldcg(reinterpret_cast<const float4*>(wsp + (size_t)sp * ws_split + i * ws_row4));
+                  o[i].x += t.x; o[i].y += t.y; o[i].z += t.z; o[i].w += t.w;
+                }
+            }
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -655,7 +701,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
               }
             }
           }
-        } else {
+        } else if (RAGGED) {
           // ---- generic path: ragged right edge (col0 + 32 > N) or unaligned leading dimensions ----
           const bool full4 = col + 3 < p.N;
 #pragma unroll
@@ -724,6 +770,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         }
         if (tr) trc[4] = clock64() - t_start;
       }
+      if (to_ws) {
+        // publish the partial, count arrivals at this tile; only the last CTA goes on to phase 1
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
+        if (e == 0 && lane == 0) {
+          const int old = atomicAdd(p.splitk_counters + tile, 1);
+          *s_flag = (old == p.split_k - 1) ? 1 : 0;
+          if (old == p.split_k - 1) p.splitk_counters[tile] = 0;  // self-cleaning: ready for the next launch
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int last = *s_flag;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read the flag before a later tile may overwrite it
+        if (!last) break;
+        __threadfence();
+      }
+      }  // phase
       // per-(tile, column-parity) argmax partials of each row
       if (EPI == EPI_ARGMAX) {
 #pragma unroll
@@ -790,24 +852,39 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t col
   return GIC_OK;
 }
 
-// Tile width: minimise rounds x operand bytes per k-block, rounds = ceil(tiles / #SMs): wide tiles re-read the activation
-// slab less often, narrow ones keep all SMs busy when M is small.
-int gemm_bf16_pick_block_n(int M, int N, int split) {
+// Tile width and K split.  Cost model from the round-1 timelines (profiles/): a 64-deep k-block of a 128 x bn tile takes
+// 256 + 2 bn cycles (shared-memory port: TMA writes + UMMA operand reads), a CTA's epilogue ~600 + 500 per 64 columns, and a
+// split-K tile pays ~3000 for parking / re-reading the partials.  rounds = ceil(work items / #SMs).
+void gemm_bf16_pick(int M, int N, int K, int split, int split_k, int* block_n) {
   static const int wide[] = {256, 192, 128, 64, 32};
-  static const int narrow[] = {64, 32};  // split (bf16x2) stages carry four operand tiles
+  static const int narrow[] = {64, 32};  // bf16x2 stages carry four operand tiles
   const int* cand = split ? narrow : wide;
   const int n_cand = split ? 2 : 5;
   const long m_tiles = ceil_div(M, GEMM_BLOCK_M);
-  const int sms = 148;
-  int best = cand[0];
+  const int nk = ceil_div(K, GEMM_BLOCK_K);
+  const int sms = 148, S = split_k < 1 ? 1 : split_k;
   long best_cost = -1;
+  *block_n = cand[0];
   for (int i = 0; i < n_cand; ++i) {
     const int bn = cand[i];
     const long tiles = m_tiles * ceil_div(N, bn);
-    const long cost = ((tiles + sms - 1) / sms) * (16384 + 128L * bn);  // relative operand bytes per k-block
-    if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
+    const long rounds = (tiles * S + sms - 1) / sms;
+    const long cost = rounds * (ceil_div(nk, S) * (256 + 2 * bn) * (split ? 3 : 1) + 600 + 500L * ceil_div(bn, 64) + (S > 1 ? 3000 : 0));
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; *block_n = bn; }
   }
-  return best;
+}
+// K split of the decode-size residual GEMMs: a function of the SHAPE only (never of M), so that a row's fp32 summation
+// order -- and with it its tokens -- does not depend on the batch it is generated in
+int gemm_bf16_split_k_for(int N, int K) {
+  if (N % 32 != 0) return 1;
+  const int nk = ceil_div(K, GEMM_BLOCK_K);
+  int S = (nk + 8) / 16;
+  return S < 1 ? 1 : (S > 4 ? 4 : S);
+}
+int gemm_bf16_pick_block_n(int M, int N, int split) {
+  int bn;
+  gemm_bf16_pick(M, N, 768, split, 1, &bn);
+  return bn;
 }
 
 static int gemm_num_sms() {
@@ -821,19 +898,24 @@ static int gemm_num_sms() {
 }
 
 // The instantiated (EPI, OUT, FOLD) variants; anything else is refused by launch_gemm_bf16.
+// X(epilogue, output mode, folded LayerNorm, ragged): fp32 outputs exist in both the aligned and the ragged flavour (the LM
+// head's N = 50257, odd test shapes); bf16 outputs are always aligned (every GPT-2 / mapper width is a multiple of 64)
 #define GIC_GEMM_VARIANTS_COMMON(X) \
-  X(EPI_NONE, OUT_F32, false) X(EPI_TANH, OUT_F32, false) X(EPI_GELU, OUT_F32, false) X(EPI_RELU, OUT_F32, false) \
-  X(EPI_RESIDUAL, OUT_F32, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_ARGMAX, OUT_F32, false)
+  X(EPI_NONE, OUT_F32, false, false) X(EPI_TANH, OUT_F32, false, false) X(EPI_GELU, OUT_F32, false, false) X(EPI_RELU, OUT_F32, false, false) \
+  X(EPI_RESIDUAL, OUT_F32, false, false) X(EPI_ARGMAX, OUT_NONE, false, false) \
+  X(EPI_NONE, OUT_F32, false, true) X(EPI_TANH, OUT_F32, false, true) X(EPI_GELU, OUT_F32, false, true) X(EPI_RELU, OUT_F32, false, true) \
+  X(EPI_RESIDUAL, OUT_F32, false, true) X(EPI_ARGMAX, OUT_F32, false, true)
 #define GIC_GEMM_VARIANTS_BF16(X) \
-  X(EPI_NONE, OUT_BF16, false) X(EPI_NONE, OUT_BF16, true) X(EPI_TANH, OUT_BF16, false) X(EPI_GELU, OUT_BF16, false) \
-  X(EPI_GELU, OUT_BF16, true) X(EPI_RELU, OUT_BF16, false) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false) \
-  X(EPI_ARGMAX, OUT_NONE, true) X(EPI_ARGMAX, OUT_F32, true) X(EPI_NONE, OUT_F32, true)
-#define GIC_GEMM_VARIANTS_SPLIT(X) X(EPI_NONE, OUT_BF16X2, false) X(EPI_TANH, OUT_BF16X2, false) X(EPI_GELU, OUT_BF16X2, false) X(EPI_RELU, OUT_BF16X2, false)
+  X(EPI_NONE, OUT_BF16, false, false) X(EPI_NONE, OUT_BF16, true, false) X(EPI_TANH, OUT_BF16, false, false) X(EPI_GELU, OUT_BF16, false, false) \
+  X(EPI_GELU, OUT_BF16, true, false) X(EPI_RELU, OUT_BF16, false, false) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false, false) \
+  X(EPI_ARGMAX, OUT_NONE, true, false) X(EPI_ARGMAX, OUT_F32, true, true) X(EPI_NONE, OUT_F32, true, true)
+#define GIC_GEMM_VARIANTS_SPLIT(X) \
+  X(EPI_NONE, OUT_BF16X2, false, false) X(EPI_TANH, OUT_BF16X2, false, false) X(EPI_GELU, OUT_BF16X2, false, false) X(EPI_RELU, OUT_BF16X2, false, false)
 
 template <int BLOCK_N, bool SPLIT>
 static int configure_cfg() {
-#define X(E, O, F)                                                                                                                \
-  GIC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, E, O, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+#define X(E, O, F, R)                                                                                                                \
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, E, O, F, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       GemmTile<BLOCK_N, SPLIT>::SMEM_BYTES));
   GIC_GEMM_VARIANTS_COMMON(X)
   if (SPLIT) { GIC_GEMM_VARIANTS_SPLIT(X) } else { GIC_GEMM_VARIANTS_BF16(X) }
@@ -856,11 +938,12 @@ int gemm_bf16_configure() {
   return GIC_OK;
 }
 
-template <int BLOCK_N, bool SPLIT, int EPI, int OUT, bool FOLD>
+template <int BLOCK_N, bool SPLIT, int EPI, int OUT, bool FOLD, bool RAGGED>
 static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
   using Tile = GemmTile<BLOCK_N, SPLIT>;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, EPI, OUT, FOLD>;
-  const long tiles = (long)ceil_div(kp.M, GEMM_BLOCK_M) * ceil_div(kp.N, BLOCK_N);
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, EPI, OUT, FOLD, RAGGED>;
+  const long tiles = (long)ceil_div(kp.M, GEMM_BLOCK_M) * ceil_div(kp.N, BLOCK_N) * kp.split_k;
+
   const int sms = gemm_num_sms();
   dim3 grid((unsigned)(tiles < sms ? tiles : sms));  // persistent: one CTA per SM
   GIC_CHECK_CUDA(launch_kernel(kern, grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st, kp));
@@ -868,10 +951,15 @@ static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
   return GIC_OK;
 }
 
+// (epilogue, output, fold) combinations that exist only in the ragged flavour (test / logits-tap paths)
+static bool has_aligned(int epi, int out, bool fold) { return !((epi == EPI_ARGMAX && out == OUT_F32) || (epi == EPI_NONE && out == OUT_F32 && fold)); }
+
 template <int BLOCK_N, bool SPLIT>
 static int launch_cfg(const GemmKernelParams& kp, int epi, int out, bool fold, cudaStream_t st) {
-#define X(E, O, F) \
-  if (epi == E && out == O && fold == F) return launch_one<BLOCK_N, SPLIT, E, O, F>(kp, st);
+  // the aligned flavour when the shape allows it and it exists, else the ragged one
+  const bool aligned = kp.N % 32 == 0 && kp.ld_f32 % 4 == 0 && kp.ld_bf16 % 4 == 0;
+#define X(E, O, F, R) \
+  if (epi == E && out == O && fold == F && (R || aligned || O == OUT_NONE) && (!R || !aligned || !has_aligned(E, O, F))) return launch_one<BLOCK_N, SPLIT, E, O, F, R>(kp, st);
   GIC_GEMM_VARIANTS_COMMON(X)
   if (SPLIT) { GIC_GEMM_VARIANTS_SPLIT(X) } else { GIC_GEMM_VARIANTS_BF16(X) }
 #undef X
@@ -890,6 +978,7 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   kp.part_val = a.part_val; kp.part_idx = a.part_idx; kp.part_ld = a.part_ld; kp.trace = a.trace;
   kp.ln_stats = a.ln_stats; kp.ln_parts = a.ln_parts; kp.ln_stats_ld = a.ln_stats_ld; kp.ln_row_mul = a.ln_row_mul; kp.ln_row_off = a.ln_row_off;
   kp.ln_colsum = a.ln_colsum; kp.stats_out = a.stats_out;
+  kp.split_k = a.split_k < 1 ? 1 : a.split_k; kp.splitk_ws = a.splitk_ws; kp.splitk_counters = a.splitk_counters;
   GIC_REQUIRE(!a.ln_stats || (a.ln_colsum && a.ln_parts > 0), "gemm_bf16: folded LayerNorm needs the column sums and at least one statistics part");
   int epi = a.epilogue;
   if (a.part_val) {
@@ -911,6 +1000,11 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
     out = a.out.lo ? OUT_BF16X2 : OUT_BF16;
   } else {
     GIC_REQUIRE(epi == EPI_ARGMAX, "gemm_bf16: no output buffer");
+  }
+  if (kp.split_k > 1) {
+    GIC_REQUIRE(epi != EPI_ARGMAX && a.splitk_ws && a.splitk_counters, "gemm_bf16: split-K needs its workspace / counters and a storing epilogue");
+    GIC_REQUIRE(a.N % 32 == 0 && a.ld_out % 4 == 0, "gemm_bf16: split-K needs N %% 32 == 0 and aligned outputs");
+    GIC_REQUIRE(ceil_div(a.K, GEMM_BLOCK_K) >= kp.split_k, "gemm_bf16: more K slices than k-blocks");
   }
   if (a.split) {
     switch (a.block_n) {

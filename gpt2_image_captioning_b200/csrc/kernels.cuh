@@ -52,10 +52,15 @@ struct GemmBf16Args {
   int ln_parts = 0; long ln_stats_ld = 0; int ln_row_mul = 1, ln_row_off = 0;
   const float* ln_colsum = nullptr;  // [N] sum_k of the packed (bf16) gamma-folded weights
   float2* stats_out = nullptr;       // [ceil(N / 32)][ln_stats_ld]: per-row (sum, sum of squares) of the values this GEMM writes, per 32-column chunk
+  // split-K for short-and-wide problems (few output tiles, long K): split_k CTAs per tile, deterministic last-CTA reduction
+  int split_k = 1; float* splitk_ws = nullptr;  /* [split_k][M][N] fp32 */  int* splitk_counters = nullptr;  /* [tiles], zero on entry and exit */
   long long* trace = nullptr;      // microbenchmark only: device buffer of >= 640 int64 for CTA 0's clock64 timeline
 };
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st);
 int gemm_bf16_pick_block_n(int M, int N, int split);
+// tile width for an M x N x K problem cut into split_k K slices (split: bf16x2 operands)
+void gemm_bf16_pick(int M, int N, int K, int split, int split_k, int* block_n);
+int gemm_bf16_split_k_for(int N, int K);  // K split of a decode-size residual GEMM: depends on the shape only
 
 int gemm_bf16_configure();  // cudaFuncSetAttribute for every instantiation (call once, outside stream capture)
 

@@ -155,14 +155,19 @@ int main(int argc, char** argv) {
   // ---- main-loop timeline of CTA 0 (clock64 deltas from kernel entry) ----
   if (argc > 2 && atoi(argv[2]) == 4) {
     long long* tr = (long long*)dmalloc(640 * 8);
-    struct Shape { const char* name; bf16* A; bf16* W; int N, K, bn; bool lm; };
-    Shape shapes[] = {{"qkv", a, w_qkv[0], 3 * d, d, 128, false}, {"fc2", a, w_fc2[0], d, 4 * d, 64, false}, {"lm_head", a, wte, V, d, 128, true}};
+    struct Shape { const char* name; bf16* A; bf16* W; int N, K, bn; bool lm; int sk; };
+    float* skws = (float*)dmalloc((size_t)4 * B * d * 4);
+    int* skcnt = (int*)dmalloc(4096 * 4);
+    float2* stats = (float2*)dmalloc((size_t)64 * B * 8);
+    Shape shapes[] = {{"qkv", a, w_qkv[0], 3 * d, d, 128, false, 1}, {"fc2", a, w_fc2[0], d, 4 * d, 64, false, 1}, {"fc2 split-K 3", a, w_fc2[0], d, 4 * d, 128, false, 3},
+                      {"lm_head", a, wte, V, d, 128, true, 1}};
     for (const Shape& sh : shapes) {
       GemmBf16Args g;
       OK(make_tma_2d_bf16(&g.a_hi, sh.A, B, sh.K, sh.K, 128));
       OK(make_tma_2d_bf16(&g.w_hi, sh.W, sh.N, sh.K, sh.K, sh.bn));
       g.M = B; g.N = sh.N; g.K = sh.K; g.block_n = sh.bn; g.bias = bias;
       if (sh.lm) { g.part_val = pv; g.part_idx = pi; g.part_ld = 2048; g.bias = nullptr; } else { g.out.hi = o; g.ld_out = sh.N; }
+      if (sh.sk > 1) { g.epilogue = EPI_RESIDUAL; g.out.f32 = h; g.stats_out = stats; g.ln_stats_ld = B; g.split_k = sh.sk; g.splitk_ws = skws; g.splitk_counters = skcnt; }
       for (int i = 0; i < 3; ++i) OK(launch_gemm_bf16(g, st));
       CK(cudaMemsetAsync(tr, 0, 640 * 8, st));
       g.trace = tr;
@@ -199,10 +204,16 @@ int main(int argc, char** argv) {
   float2* stats = (float2*)dmalloc((size_t)64 * B * 8);  // [parts][B]
   float* colsum = (float*)dmalloc((size_t)V * 4);
   float* bias_v = (float*)dmalloc((size_t)V * 4);
-  for (int fused = 0; fused < 2; ++fused)
+  float* skws = (float*)dmalloc((size_t)4 * B * d * 4);
+  int* skcnt = (int*)dmalloc(4096 * 4);
+  for (int fused = 0; fused < 3; ++fused)  // 2: fused + K split (residual GEMMs)
     for (auto& s : shapes) {
+      const int sk = fused == 2 ? gemm_bf16_split_k_for(s.N, s.K) : 1;
+      if (fused == 2 && (!s.res || sk == 1)) continue;
+      int bn_pick = 0;
+      gemm_bf16_pick(B, s.N, s.K, 0, sk, &bn_pick);
       for (int bn : {64, 128, 192, 256}) {
-        if (fused && bn != gemm_bf16_pick_block_n(B, s.N, 0)) continue;
+        if (fused && bn != bn_pick && !(fused == 2 && bn <= 256)) continue;
         std::vector<GemmBf16Args> args(SETS);
         for (int i = 0; i < SETS; ++i) {
           GemmBf16Args& g = args[i];
@@ -211,13 +222,13 @@ int main(int argc, char** argv) {
           g.M = B; g.N = s.N; g.K = s.K; g.block_n = bn; g.epilogue = s.epi; g.bias = bias; g.ld_out = s.N;
           if (s.res) g.out.f32 = h; else g.out.hi = (s.N == 3 * d ? qkv : o);
           if (fused) {  // LayerNorm folded: statistics in for qkv / fc, bf16 copy + statistics out for the residual GEMMs
-            if (s.res) { g.out.hi = o; g.stats_out = stats; g.ln_stats_ld = B; }
+            if (s.res) { g.out.hi = o; g.stats_out = stats; g.ln_stats_ld = B; if (sk > 1) { g.split_k = sk; g.splitk_ws = skws; g.splitk_counters = skcnt; } }
             else { g.ln_stats = stats; g.ln_parts = d / 32; g.ln_stats_ld = B; g.ln_colsum = colsum; }
           }
         }
         float us = time_loop(st, 240, [&](int i) { OK(launch_gemm_bf16(args[i % SETS], st)); });
-        printf("gemm %-4s%s M=%d N=%d K=%d block_n=%3d: %7.2f us  %6.1f TFLOP/s  (picked %d)\n", s.name, fused ? " +LN" : "    ", B, s.N, s.K, bn, us,
-               2.0 * B * s.N * s.K / us * 1e-6, gemm_bf16_pick_block_n(B, s.N, 0));
+        printf("gemm %-4s%s M=%d N=%d K=%d block_n=%3d: %7.2f us  %6.1f TFLOP/s  (picked %d)\n", s.name, fused == 2 ? " +LN split-K" : fused ? " +LN" : "    ", B,
+               s.N, s.K, bn, us, 2.0 * B * s.N * s.K / us * 1e-6, bn_pick);
       }
     }
   for (int fused = 0; fused < 2; ++fused)

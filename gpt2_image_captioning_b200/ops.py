@@ -88,6 +88,15 @@ def test_gemm(dtype: int, A: torch.Tensor, W: torch.Tensor, bias: torch.Tensor |
     _capi.check(L.gic_test_gemm(dtype, _ptr(A), _ptr(W), _ptr(bias), _ptr(C), A.shape[0], W.shape[0], A.shape[1], epilogue, _stream()))
 
 
+@torch.library.custom_op("gic::test_ln_mlp", mutates_args=("h", "hb_out", "stats_out"))
+def test_ln_mlp(h: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, wfc: torch.Tensor, bfc: torch.Tensor, wfc2: torch.Tensor,
+                bfc2: torch.Tensor, hb_out: torch.Tensor, stats_out: torch.Tensor, split_k: int) -> None:
+    _need_cuda(h, gamma, beta, wfc, bfc, wfc2, bfc2, hb_out, stats_out)
+    L = _capi.lib()
+    _capi.check(L.gic_test_ln_mlp(_ptr(h), _ptr(gamma), _ptr(beta), _ptr(wfc), _ptr(bfc), _ptr(wfc2), _ptr(bfc2), _ptr(hb_out),
+                                  _ptr(stats_out), h.shape[0], h.shape[1], split_k, _stream()))
+
+
 @torch.library.custom_op("gic::test_layernorm", mutates_args=("y",))
 def test_layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, y: torch.Tensor) -> None:
     _need_cuda(x, w, b, y)

@@ -182,6 +182,10 @@ GIC_API int gic_profile_read(gic_engine* e, gic_profile_entry* out, int max_entr
 /* C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias[N]) ; epilogue: 0 none, 1 tanh, 2 gelu_tanh, 3 relu, 4 += residual(fp32 C in place).
  * dtype F32: A,W,C fp32 (CUDA cores).  BF16 / BF16X2: A,W fp32 inputs are packed internally, C fp32. */
 GIC_API int gic_test_gemm(int dtype, const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int epilogue, void* stream);
+/* fused bf16 MLP sub-block (LayerNorm folded into c_fc, GELU, c_proj + residual with bf16 copy + row statistics, optional
+ * split-K) on caller data -- the kernel-level parity hook for HF GPT2Block's ln_2 + GPT2MLP (HF:models/gpt2/modeling_gpt2.py:238-243,304-307) */
+GIC_API int gic_test_ln_mlp(float* h, const float* gamma, const float* beta, const float* wfc, const float* bfc, const float* wfc2, const float* bfc2,
+                            void* hb_out, void* stats_out, int M, int d, int split_k, void* stream);
 GIC_API int gic_test_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int d, void* stream);
 
 #ifdef __cplusplus

@@ -89,6 +89,50 @@ def test_gemm_tcgen05_epilogues(epi):
     assert (C.double() - ref).abs().max().item() <= 2e-4
 
 
+@pytest.mark.parametrize("M,d,split_k", [(1024, 768, 1), (1024, 768, 3), (388, 768, 3), (70, 128, 2), (200, 1024, 4), (1300, 256, 1)])
+def test_fused_ln_mlp_block(M, d, split_k):
+    """ln_2 folded into c_fc (row statistics in, gamma / beta in the packed weight and bias), GELU, c_proj + residual with the
+    bf16 copy and the per-32-column row statistics of the new residual stream, fc2 optionally K-split: against the same
+    block in fp64 on the bf16-rounded operands (HF GPT2Block ln_2 + GPT2MLP)."""
+    ops, capi = _ops()
+    g = torch.Generator(device="cpu").manual_seed(M + d + split_k)
+    h0 = torch.randn(M, d, generator=g) * 1.5 + 0.3
+    gamma = 1.0 + 0.1 * torch.randn(d, generator=g)
+    beta = 0.1 * torch.randn(d, generator=g)
+    wfc = torch.randn(4 * d, d, generator=g) * 0.03
+    bfc = torch.randn(4 * d, generator=g) * 0.1
+    wfc2 = torch.randn(d, 4 * d, generator=g) * 0.03
+    bfc2 = torch.randn(d, generator=g) * 0.1
+    h = h0.clone().to(DEV)
+    hb = torch.empty(M, d, dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros(d // 32, M, 2, device=DEV)
+    ops.test_ln_mlp(h, gamma.to(DEV), beta.to(DEV), wfc.to(DEV), bfc.to(DEV), wfc2.to(DEV), bfc2.to(DEV), hb, stats, split_k)
+    torch.cuda.synchronize()
+    # reference with the engine's rounding points: xb = bf16(h); W' = bf16(gamma * Wfc); f = bf16(gelu(...)); W2 = bf16(Wfc2)
+    xb = h0.bfloat16().double()
+    mu = xb.mean(dim=1, keepdim=True)
+    var = (xb * xb).mean(dim=1, keepdim=True) - mu * mu
+    rstd = 1.0 / torch.sqrt(var + 1e-5)
+    w1 = (wfc * gamma).bfloat16().double()
+    pre = rstd * (xb @ w1.t() - mu * w1.sum(dim=1)) + (bfc.double() + wfc.double() @ beta.double())
+    f = oc.gelu_new(pre.float()).bfloat16().double()
+    ref = h0.double() + f @ wfc2.bfloat16().double().t() + bfc2.double()
+    err = (h.cpu().double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 4e-3 * scale, f"fused block: max abs err {err} (scale {scale})"  # one bf16 ulp of the GELU output here and there
+    # the bf16 copy and its statistics are exact functions of what was written
+    assert torch.equal(hb.cpu(), h.cpu().bfloat16())
+    hbf = hb.cpu().float().double().view(M, d // 32, 32)
+    want = torch.stack((hbf.sum(dim=2), (hbf * hbf).sum(dim=2)), dim=2).permute(1, 0, 2)  # [d/32][M][2]
+    got = stats.cpu().double()
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-4)
+    # split-K sums the partials in a fixed order: bit-identical across runs
+    h2 = h0.clone().to(DEV)
+    ops.test_ln_mlp(h2, gamma.to(DEV), beta.to(DEV), wfc.to(DEV), bfc.to(DEV), wfc2.to(DEV), bfc2.to(DEV), hb, stats, split_k)
+    torch.cuda.synchronize()
+    assert torch.equal(h2, h)
+
+
 @pytest.mark.parametrize("rows,d", [(1, 768), (1000, 768), (33, 1024), (7, 1280), (5, 128)])
 def test_layernorm(rows, d):
     ops, _ = _ops()
