@@ -161,11 +161,13 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const T* qkv, T* kcach
 // ~100 KB per SM in flight without holding registers, so the HBM stream does not stall on the softmax arithmetic or on
 // block scheduling (the one-warp-per-item kernel above pays a ~9 us launch / wave ramp per layer: 23 us for 79 MB).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int DEC_WARPS = 16;
-constexpr int DEC_CHUNK = 16;   // keys per stage
-constexpr int DEC_STAGES = 3;   // per warp
-constexpr int DEC_STAGE_BYTES = 2 * DEC_CHUNK * HD * 2;  // K chunk + V chunk, bf16
-constexpr int DEC_SMEM_BYTES = DEC_WARPS * DEC_STAGES * DEC_STAGE_BYTES + DEC_WARPS * DEC_STAGES * 8 + 128;
+// ring geometry: DEC_WARPS warps per CTA, DEC_CHUNK keys per stage, DEC_STAGES stages per warp (~196 KB of smem per SM in each
+// of the shapes below; which one runs is picked from the microbenchmark, see launch_attn_decode_bulk)
+template <int DEC_WARPS, int DEC_CHUNK, int DEC_STAGES>
+struct DecCfg {
+  static constexpr int STAGE_BYTES = 2 * DEC_CHUNK * HD * 2;  // K chunk + V chunk, bf16
+  static constexpr int SMEM_BYTES = DEC_WARPS * DEC_STAGES * STAGE_BYTES + DEC_WARPS * DEC_STAGES * 8 + 128;
+};
 
 __device__ __forceinline__ uint32_t dec_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dec_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -183,8 +185,10 @@ __device__ __forceinline__ void dec_mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+template <int DEC_WARPS, int DEC_CHUNK, int DEC_STAGES>
 __global__ void __launch_bounds__(DEC_WARPS * 32, 1) attn_decode_bulk_kernel(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out,
                                                                            const int* d_pos, int rows, int H, int t_max) {
+  constexpr int DEC_STAGE_BYTES = DecCfg<DEC_WARPS, DEC_CHUNK, DEC_STAGES>::STAGE_BYTES;
   extern __shared__ uint8_t dec_smem_raw[];
   const uint32_t smem_base = (dec_smem_u32(dec_smem_raw) + 127u) & ~127u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -339,11 +343,237 @@ __global__ void __launch_bounds__(DEC_WARPS * 32, 1) attn_decode_bulk_kernel(con
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 decode attention on the warp-level tensor cores (mma.sync m16n8k16), same bulk-copy ring as above.
+// The SIMT kernel above executes ~530 warp instructions per 16-key chunk (unpack + FMA + shuffle trees) and is ISSUE bound:
+// ncu shows 67 % issue-slot utilisation with 4 warps per scheduler at 4.3 TB/s, against 5.9 TB/s for a plain streaming read of
+// the same bytes (profiles/r1z_attn_*.txt).  Here a chunk is 4 ldmatrix + 8 mma for S = q.K^T and 4 ldmatrix.trans + 16 mma
+// for O += P.V (P split into bf16 hi + lo so that the probabilities keep ~16 mantissa bits).
+//
+// The bulk copy lays a chunk out linearly ([key][64 dims], 128-byte rows), which would make every ldmatrix a 16-way bank
+// conflict (8 rows 128 bytes apart).  Instead of a swizzled copy, the MATRIX ROWS are skewed: the row of key r reads 16-byte
+// column (j ^ (r & 7)), so the eight rows of a matrix hit all 32 banks.  The skew is undone by the other operand:
+//   S:  A row g holds q with its 16-byte columns permuted by ^g, so C[g][n] is a true dot product only for n == g: the
+//       score of key g (n-tile 0) and key 8 + g (n-tile 1) sit on the diagonal, in lane (g, t = g >> 1), register g & 1.
+//   O:  A = P with P[k] placed in row (k & 7) only -- exactly the diagonal positions the scores came out in, so P never moves
+//       between lanes.  Accumulator j of row r then holds the partial output of dims column (j ^ r) from keys = r mod 8, and
+//       a 3-step exchange at the end of the item (14 shuffles) sums the 8 rows while un-skewing: lane (g, t) ends with dims
+//       8 g + 2 t, + 1, i.e. the warp stores one coalesced 128-byte row.
+// The new token's K / V row is written into the free slot behind the cached keys of the item's last chunk (and appended to
+// the cache), so all pos + 1 keys go through the same path.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+// D (+)= A . B, A rows 8..15 are zero (a1 = a3 = 0): only c0, c1 (row = lane / 4) are meaningful
+__device__ __forceinline__ void mma_16816_top(float& c0, float& c1, float& c2, float& c3, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+               : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int MMA_CHUNK = 16;                          // keys per stage
+constexpr int MMA_STAGE_BYTES = 2 * MMA_CHUNK * HD * 2;  // K chunk + V chunk
+template <int WARPS, int STAGES>
+struct DecMmaCfg { static constexpr int SMEM_BYTES = WARPS * STAGES * MMA_STAGE_BYTES + WARPS * STAGES * 8 + 128; };
+
+template <int WARPS, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos,
+                                                                      int rows, int H, int t_max) {
+  extern __shared__ uint8_t dec_smem_raw[];
+  const uint32_t smem_base = (dec_smem_u32(dec_smem_raw) + 127u) & ~127u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring = smem_base + warp * (STAGES * MMA_STAGE_BYTES);
+  const uint32_t bars = smem_base + WARPS * STAGES * MMA_STAGE_BYTES + warp * (STAGES * 8);
+  pdl_launch_dependents();
+  if (lane == 0) {
+    for (int s = 0; s < STAGES; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8 * s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // zero this warp's ring: rows of a stage that no copy has filled yet are multiplied by P = 0 and must not hold NaN / Inf
+  for (int i = lane; i < STAGES * MMA_STAGE_BYTES / 16; i += 32)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ring + i * 16), "r"(0u) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes above before the bulk copies into the same bytes
+  __syncwarp();
+  pdl_wait();
+  const int pos = __ldcg(d_pos);  // tokens already cached == position of the new token
+  const int d = H * HD;
+  const int n_items = rows * H;
+  const int wstride = gridDim.x * WARPS;
+  const int w0 = blockIdx.x * WARPS + warp;
+  const int nch = pos / MMA_CHUNK + 1;  // chunks covering the pos cached keys + the new one
+  const int my_items = w0 < n_items ? (n_items - 1 - w0) / wstride + 1 : 0;
+  const int total_chunks = my_items * nch;
+  const int g = lane >> 2, t = lane & 3;
+
+  // producer side (lane 0): chunk n of this warp's stream -> stage n % STAGES (the cached keys of the chunk only).
+  // K / V of item i start at i * t_max * 64 elements of their plane (item = row * H + head).
+  int p_item = w0, p_c = 0, p_s = 0;  // producer cursor: item, chunk of the item, stage
+  auto issue_next = [&]() {
+    const int nkeys = min(MMA_CHUNK, pos - p_c * MMA_CHUNK);  // cached keys in this chunk (0..16)
+    const uint32_t bytes = (uint32_t)nkeys * HD * 2;
+    const size_t off = ((size_t)p_item * t_max + (size_t)p_c * MMA_CHUNK) * HD;
+    const uint32_t bar = bars + 8 * p_s, dst = ring + p_s * MMA_STAGE_BYTES;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * bytes) : "memory");
+    if (bytes > 0) {
+      dec_bulk_load(dst, kcache + off, bytes, bar);
+      dec_bulk_load(dst + MMA_CHUNK * HD * 2, vcache + off, bytes, bar);
+    }
+    if (++p_c == nch) { p_c = 0; p_item += wstride; }
+    if (++p_s == STAGES) p_s = 0;
+  };
+  int issued = 0;
+  if (lane == 0)
+    for (; issued < STAGES - 1 && issued < total_chunks; ++issued) issue_next();
+
+  // q in A-fragment order for row g (16-byte column j of q sits where column j ^ g is expected) and the new token's k / v
+  // (16 bytes per lane & 7), requested one item ahead
+  uint32_t qa_n[8];
+  uint4 knew_n, vnew_n;
+  auto load_new = [&](int item) {
+    const int row = item / H;
+    const bf16* qrow = qkv + (size_t)item * HD + (size_t)row * 2 * d;  // row * 3 d + head * 64
+    const uint32_t* q32 = reinterpret_cast<const uint32_t*>(qrow);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qa_n[j] = __ldcg(q32 + 4 * (j ^ g) + t);
+    knew_n = __ldcg(reinterpret_cast<const uint4*>(qrow + d) + (lane & 7));
+    vnew_n = __ldcg(reinterpret_cast<const uint4*>(qrow + 2 * d) + (lane & 7));
+  };
+  if (my_items > 0) load_new(w0);
+  const __nv_bfloat162 eighth = __floats2bfloat162_rn(0.125f, 0.125f);  // 1/sqrt(64), HF :211-220 (sdpa default scale); exact in bf16
+  // ldmatrix row addresses inside a stage (r = lane & 7 is the matrix row, m = lane >> 3 the matrix of the x4):
+  //   K (plain): key 8 (m >> 1) + r, 16-byte column (2 ks + (m & 1)) ^ r   ->  (b0, b1) of n-tile 0, then of n-tile 1
+  //   V (trans): key 8 (m & 1) + r, 16-byte column (2 jj + (m >> 1)) ^ r   ->  (b0, b1) of accumulator 2 jj, then of 2 jj + 1
+  const int r8 = lane & 7, mlo = (lane >> 3) & 1, mhi = lane >> 4;
+  const uint32_t k_row_off = (uint32_t)((8 * mhi + r8) * (HD * 2));
+  const uint32_t v_row_off = (uint32_t)(MMA_CHUNK * HD * 2 + (8 * mlo + r8) * (HD * 2));
+  const bool diag = t == (g >> 1);  // this lane holds the scores of keys g and 8 + g of a chunk
+  const bool odd = g & 1;
+  int c_s = 0;
+  uint32_t c_ph = 0;
+  for (int ii = 0; ii < my_items; ++ii) {
+    const int item = w0 + ii * wstride;
+    uint32_t qa[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __nv_bfloat162 v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&qa_n[i]), eighth);
+      qa[i] = *reinterpret_cast<uint32_t*>(&v);
+    }
+    const uint4 knew = knew_n, vnew = vnew_n;
+    if (ii + 1 < my_items) load_new(item + wstride);
+    float m = -INFINITY, l = 0.f;  // running maximum (warp-uniform) and this lane's share of the running sum
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] = 0.f; o[j][1] = 0.f; o[j][2] = 0.f; o[j][3] = 0.f; }
+    for (int c = 0; c < nch; ++c) {
+      // keep the ring full: the stage freed by the previous chunk takes the next chunk of the stream
+      if (lane == 0 && issued < total_chunks) { issue_next(); ++issued; }
+      const uint32_t st = ring + c_s * MMA_STAGE_BYTES;
+      const int cached = min(MMA_CHUNK, pos - c * MMA_CHUNK);  // cached keys of this chunk
+      const bool last = c == nch - 1;                            // ... followed by the new token in slot `cached` (< 16 here)
+      if (last && lane < 8) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + cached * (HD * 2) + lane * 16), "r"(knew.x), "r"(knew.y), "r"(knew.z), "r"(knew.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + MMA_CHUNK * HD * 2 + cached * (HD * 2) + lane * 16), "r"(vnew.x), "r"(vnew.y), "r"(vnew.z), "r"(vnew.w) : "memory");
+        const size_t coff = ((size_t)item * t_max + pos) * HD + lane * 8;
+        *reinterpret_cast<uint4*>(kcache + coff) = knew;  // append to the cache (HF:cache_utils.py:102-121)
+        *reinterpret_cast<uint4*>(vcache + coff) = vnew;
+      }
+      dec_mbar_wait(bars + 8 * c_s, c_ph);
+      __syncwarp();  // the new token's row is visible to every lane's ldmatrix
+      const int nkeys = cached + (last ? 1 : 0);
+      // ---- S = q . K^T over the 16 key slots (diagonal entries only) ----
+      // (two accumulator sets per n-tile: dependent chains of two MMAs instead of four)
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f}, u0[4] = {0.f, 0.f, 0.f, 0.f}, u1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 4; ks += 2) {
+        uint32_t b00, b01, b10, b11, c00, c01, c10, c11;
+        ldsm_x4(st + k_row_off + 16 * ((2 * ks + mlo) ^ r8), b00, b01, b10, b11);
+        ldsm_x4(st + k_row_off + 16 * ((2 * ks + 2 + mlo) ^ r8), c00, c01, c10, c11);
+        mma_16816_top(s0[0], s0[1], s0[2], s0[3], qa[2 * ks], qa[2 * ks + 1], b00, b01);
+        mma_16816_top(s1[0], s1[1], s1[2], s1[3], qa[2 * ks], qa[2 * ks + 1], b10, b11);
+        mma_16816_top(u0[0], u0[1], u0[2], u0[3], qa[2 * ks + 2], qa[2 * ks + 3], c00, c01);
+        mma_16816_top(u1[0], u1[1], u1[2], u1[3], qa[2 * ks + 2], qa[2 * ks + 3], c10, c11);
+      }
+      // slots >= nkeys hold stale bytes -> masked by selection
+      float sv0 = odd ? s0[1] + u0[1] : s0[0] + u0[0], sv1 = odd ? s1[1] + u1[1] : s1[0] + u1[0];  // keys g and 8 + g (meaningful on the diagonal lanes)
+      if (!diag || g >= nkeys) sv0 = -INFINITY;
+      if (!diag || 8 + g >= nkeys) sv1 = -INFINITY;
+      float cm = fmaxf(sv0, sv1);
+      asm volatile("redux.sync.max.f32 %0, %0, 0xffffffff;" : "+f"(cm));  // sm_100a: one warp-wide float reduction instead of five shuffles
+      const float mn = fmaxf(m, cm);                 // finite: every chunk holds at least one valid key
+      const float mnl = mn * LOG2E;
+      const float scale = exp2f(m * LOG2E - mnl);    // 0 at the first chunk (m = -inf)
+      m = mn;
+      const float p0 = exp2f(fmaf(sv0, LOG2E, -mnl)), p1 = exp2f(fmaf(sv1, LOG2E, -mnl));  // 0 off the diagonal and for masked slots
+      l = l * scale + (p0 + p1);
+      // P as bf16 hi + lo, in row g at k = g (a0) and k = 8 + g (a2): element g & 1 of the register pair
+      const float p0h = __bfloat162float(__float2bfloat16_rn(p0)), p1h = __bfloat162float(__float2bfloat16_rn(p1));
+      const uint32_t a0h = odd ? pack_bf16x2(0.f, p0h) : pack_bf16x2(p0h, 0.f), a2h = odd ? pack_bf16x2(0.f, p1h) : pack_bf16x2(p1h, 0.f);
+      const uint32_t a0l = odd ? pack_bf16x2(0.f, p0 - p0h) : pack_bf16x2(p0 - p0h, 0.f), a2l = odd ? pack_bf16x2(0.f, p1 - p1h) : pack_bf16x2(p1 - p1h, 0.f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o[j][0] *= scale; o[j][1] *= scale; }
+      // ---- O += P . V (accumulator j of row r: dims column j ^ r, keys = r mod 8) ----
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint32_t v00, v01, v10, v11;
+        ldsm_x4_trans(st + v_row_off + 16 * ((2 * jj + mhi) ^ r8), v00, v01, v10, v11);
+        mma_16816_top(o[2 * jj][0], o[2 * jj][1], o[2 * jj][2], o[2 * jj][3], a0h, a2h, v00, v01);
+        mma_16816_top(o[2 * jj + 1][0], o[2 * jj + 1][1], o[2 * jj + 1][2], o[2 * jj + 1][3], a0h, a2h, v10, v11);
+        mma_16816_top(o[2 * jj][0], o[2 * jj][1], o[2 * jj][2], o[2 * jj][3], a0l, a2l, v00, v01);
+        mma_16816_top(o[2 * jj + 1][0], o[2 * jj + 1][1], o[2 * jj + 1][2], o[2 * jj + 1][3], a0l, a2l, v10, v11);
+      }
+      if (last) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the new token's row before a later copy overwrites it
+      __syncwarp();  // every lane is done reading this stage before lane 0 may refill it (next iteration's issue)
+      if (++c_s == STAGES) { c_s = 0; c_ph ^= 1; }
+    }
+#pragma unroll
+    for (int x = 1; x < 32; x <<= 1) l += __shfl_xor_sync(0xffffffffu, l, x);
+    const float inv = 1.0f / l;
+    // sum the 8 rows and undo the column skew: at step b a lane keeps the accumulators j with bit b clear and adds the
+    // partner row's accumulator j ^ (1 << b) (the same dims column there); lane (g, t) ends with dims column g in o[0]
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      o[j][0] += __shfl_xor_sync(0xffffffffu, o[j + 1][0], 4);
+      o[j][1] += __shfl_xor_sync(0xffffffffu, o[j + 1][1], 4);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 4) {
+      o[j][0] += __shfl_xor_sync(0xffffffffu, o[j + 2][0], 8);
+      o[j][1] += __shfl_xor_sync(0xffffffffu, o[j + 2][1], 8);
+    }
+    o[0][0] += __shfl_xor_sync(0xffffffffu, o[4][0], 16);
+    o[0][1] += __shfl_xor_sync(0xffffffffu, o[4][1], 16);
+    // out row of the item = item * 64 elements (row * d + head * 64): dims 8 g + 2 t, + 1 -> one 128-byte row per warp
+    *reinterpret_cast<uint32_t*>(out + (size_t)item * HD + 8 * g + 2 * t) = pack_bf16x2(o[0][0] * inv, o[0][1] * inv);
+  }
+}
+
 static int g_dec_sms = 0;
-// opt the bulk-copy kernel into its shared memory size once (engine creation: outside any stream capture)
+constexpr int DEC_PRODUCT_VARIANT = 12;  // mma.sync kernel, 12 warps x 4 stages (profiles/r1aa_microbench.txt)
+static int g_dec_variant = DEC_PRODUCT_VARIANT;  // microbenchmark / test knob (attn_decode_set_variant); < 0 = back to the product shape
+void attn_decode_set_variant(int v) { g_dec_variant = v < 0 ? DEC_PRODUCT_VARIANT : v; }
+#define GIC_DEC_VARIANTS(X) X(0, 16, 16, 3) X(1, 32, 8, 3)
+#define GIC_DEC_MMA_VARIANTS(X) X(10, 16, 3) X(11, 8, 6) X(12, 12, 4) X(13, 8, 5) X(14, 4, 12)
+// opt the bulk-copy kernels into their shared memory size once (engine creation: outside any stream capture)
 int attn_decode_configure() {
   if (g_dec_sms > 0) return GIC_OK;
-  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DEC_SMEM_BYTES));
+#define X(ID, W, C, S) \
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_bulk_kernel<W, C, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg<W, C, S>::SMEM_BYTES));
+  GIC_DEC_VARIANTS(X)
+#undef X
+#define X(ID, W, S) \
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<W, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<W, S>::SMEM_BYTES));
+  GIC_DEC_MMA_VARIANTS(X)
+#undef X
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
@@ -354,13 +584,30 @@ int attn_decode_configure() {
 static int launch_attn_decode_bulk(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos, int rows, int H, int t_max,
                                    cudaStream_t st) {
   GIC_TRY(attn_decode_configure());
-  const int sms = g_dec_sms;
+  const int sms = cta_limit() > 0 && cta_limit() < g_dec_sms ? cta_limit() : g_dec_sms;
   const int items = rows * H;
-  const int grid = min(sms, ceil_div(items, DEC_WARPS));
-  GIC_CHECK_CUDA(launch_kernel(attn_decode_bulk_kernel, dim3(grid), dim3(DEC_WARPS * 32), (size_t)DEC_SMEM_BYTES, st, qkv, kcache, vcache, out, d_pos,
-                               rows, H, t_max));
-  note_launch();
-  return GIC_OK;
+#define X(ID, W, C, S)                                                                                                              \
+  if (g_dec_variant == ID) {                                                                                                         \
+    const int grid = min(sms, ceil_div(items, W));                                                                                   \
+    GIC_CHECK_CUDA(launch_kernel(attn_decode_bulk_kernel<W, C, S>, dim3(grid), dim3(W * 32), (size_t)DecCfg<W, C, S>::SMEM_BYTES, st, qkv, kcache, \
+                                 vcache, out, d_pos, rows, H, t_max));                                                               \
+    note_launch();                                                                                                                   \
+    return GIC_OK;                                                                                                                   \
+  }
+  GIC_DEC_VARIANTS(X)
+#undef X
+#define X(ID, W, S)                                                                                                                  \
+  if (g_dec_variant == ID) {                                                                                                         \
+    const int grid = min(sms, ceil_div(items, W));                                                                                   \
+    GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<W, S>, dim3(grid), dim3(W * 32), (size_t)DecMmaCfg<W, S>::SMEM_BYTES, st, qkv, kcache, \
+                                 vcache, out, d_pos, rows, H, t_max));                                                               \
+    note_launch();                                                                                                                   \
+    return GIC_OK;                                                                                                                   \
+  }
+  GIC_DEC_MMA_VARIANTS(X)
+#undef X
+  set_error("attn_decode: unknown kernel variant %d", g_dec_variant);
+  return GIC_ERR_UNSUPPORTED;
 }
 
 static bool decode_bulk_enabled() {

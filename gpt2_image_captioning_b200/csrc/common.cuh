@@ -44,6 +44,10 @@ void note_launch();  // every kernel launch of the library reports here (gic_lau
 // init, TMEM alloc, descriptor prefetch) while it finishes; they touch global memory only after griddepcontrol.wait,
 // which returns when all earlier grids have completed and flushed.  GIC_NO_PDL=1 turns the launch attribute off.
 bool pdl_enabled();
+// Persistent kernels (GEMM, decode attention) size their grids to min(work, cta_limit()): the whole device unless the engine is
+// issuing one of several concurrent row-group chains, each of which is given its share of the SMs (set_cta_limit(0) = all).
+int cta_limit();
+void set_cta_limit(int ctas);
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};

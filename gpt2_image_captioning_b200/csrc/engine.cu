@@ -115,9 +115,10 @@ struct gic_engine {
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   // decode runs as two half-batches on two streams (captured as two branches of one graph): the HBM-bound attention of
   // one half overlaps the operand-delivery-bound GEMMs of the other and each fills the other's launch gaps
-  cudaStream_t stream2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int sub_batches = 1;  // measured round 1: 2 is ~5 % slower (persistent GEMM CTAs own their SMs); GIC_SUBBATCH=2 enables
+  static constexpr int MAX_SUB = 8;
+  cudaStream_t sub_stream[MAX_SUB] = {};  // [0] unused (= stream)
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
+  int sub_batches = 1;  // GIC_SUBBATCH=n: decode as n row groups (whole 128-row GEMM tiles) on n streams, each kernel limited to 1/n of the SMs
   // per-kernel-class CUDA-event profiling (bench.py roofline leg); generate runs eagerly while enabled
   bool profiling = false;
   struct ProfRec { const char* cat; cudaEvent_t a, b; };
@@ -125,6 +126,10 @@ struct gic_engine {
 };
 
 namespace gic {
+
+static thread_local int g_cta_limit = 0;
+int cta_limit() { return g_cta_limit; }
+void set_cta_limit(int ctas) { g_cta_limit = ctas < 0 ? 0 : ctas; }
 
 bool pdl_enabled() {
   static int on = -1;
@@ -288,9 +293,9 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
   w->ids = c.take<int64_t>((size_t)w->rows * (max_new > 0 ? max_new : 1));
   w->finished = c.take<unsigned char>(w->rows);
   w->first_eos = c.take<int>(w->rows);
-  w->d_step = c.take<int>(2);  // [sub-batch]
-  w->d_pos = c.take<int>(2);
-  w->done_counter = c.take<int>(2);
+  w->d_step = c.take<int>(gic_engine::MAX_SUB);  // [sub-batch]
+  w->d_pos = c.take<int>(gic_engine::MAX_SUB);
+  w->done_counter = c.take<int>(gic_engine::MAX_SUB);
   w->bytes = align_up(c.off, 1024) + 1024;
 }
 
@@ -479,18 +484,32 @@ static Workspace slice_rows(const gic_engine* e, const Workspace& w, int row0, i
   return s;
 }
 
-// one decode step for every row: two half-batches on two streams when the batch is large enough (see gic_engine)
+// one decode step for every row: as `sub_batches` row groups of whole 128-row GEMM tiles, each on its own stream and with
+// every persistent kernel limited to its share of the SMs (see gic_engine), when the batch is large enough
 static int decode_step_all(gic_engine* e, const Workspace& w, float* logits_tap, cudaStream_t st) {
-  if (e->sub_batches < 2 || w.rows < 512 || logits_tap) return decode_step(e, w, logits_tap, st);
-  const int r0 = ((w.rows / 2 + 127) / 128) * 128;  // first half rounded up to whole 128-row GEMM tiles
-  const Workspace a = slice_rows(e, w, 0, r0, 0), b = slice_rows(e, w, r0, w.rows - r0, 1);
+  int S = e->sub_batches;
+  const int tiles = (w.rows + 127) / 128;
+  if (S > tiles) S = tiles;
+  if (S < 2 || logits_tap) return decode_step(e, w, logits_tap, st);
+  const int rows_per = ((tiles + S - 1) / S) * 128;
+  S = (w.rows + rows_per - 1) / rows_per;
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   GIC_CHECK_CUDA(cudaEventRecord(e->ev_fork, st));
-  GIC_CHECK_CUDA(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
-  GIC_TRY(decode_step(e, a, nullptr, st));
-  GIC_TRY(decode_step(e, b, nullptr, e->stream2));
-  GIC_CHECK_CUDA(cudaEventRecord(e->ev_join, e->stream2));
-  GIC_CHECK_CUDA(cudaStreamWaitEvent(st, e->ev_join, 0));
-  return GIC_OK;
+  set_cta_limit(sms / S);
+  int r = GIC_OK;
+  for (int i = 0; i < S && r == GIC_OK; ++i) {
+    const int row0 = i * rows_per, n = (w.rows - row0 < rows_per) ? w.rows - row0 : rows_per;
+    const Workspace sw = slice_rows(e, w, row0, n, i);
+    cudaStream_t si = i == 0 ? st : e->sub_stream[i];
+    if (i > 0 && cudaStreamWaitEvent(si, e->ev_fork, 0) != cudaSuccess) { r = GIC_ERR_CUDA; break; }
+    r = decode_step(e, sw, nullptr, si);
+    if (r == GIC_OK && i > 0 && (cudaEventRecord(e->ev_join[i], si) != cudaSuccess || cudaStreamWaitEvent(st, e->ev_join[i], 0) != cudaSuccess)) r = GIC_ERR_CUDA;
+  }
+  set_cta_limit(0);
+  if (r == GIC_ERR_CUDA) set_error("decode_step_all: stream fork / join failed: %s", cudaGetErrorString(cudaGetLastError()));
+  return r;
 }
 
 // mapping network: image embeddings [B,E] -> prefix tokens fp32 [B,P_img,d] in w.prefix
@@ -614,13 +633,15 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
     if (r != GIC_OK) { delete e; return r; }
   }
   const char* sb = getenv("GIC_SUBBATCH");
-  if (sb && sb[0] == '2') e->sub_batches = 2;
-  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+  if (sb && sb[0] >= '1' && sb[0] <= '8') e->sub_batches = sb[0] - '0';
+  bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 1; i < gic_engine::MAX_SUB && ok; ++i)
+    ok = cudaStreamCreateWithFlags(&e->sub_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
     gic::set_error("could not create the engine stream / events: %s", cudaGetErrorString(cudaGetLastError()));
     delete e;
     return GIC_ERR_CUDA;
@@ -637,8 +658,10 @@ int gic_engine_destroy(gic_engine* e) {
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-  if (e->ev_join) cudaEventDestroy(e->ev_join);
-  if (e->stream2) cudaStreamDestroy(e->stream2);
+  for (int i = 1; i < gic_engine::MAX_SUB; ++i) {
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+    if (e->sub_stream[i]) cudaStreamDestroy(e->sub_stream[i]);
+  }
   if (e->stream) cudaStreamDestroy(e->stream);
   for (void* p : e->allocs) cudaFree(p);
   delete e;
@@ -1039,6 +1062,32 @@ int gic_test_layernorm(const float* x, const float* w, const float* b, float* y,
   GIC_REQUIRE(x && w && b && y, "null argument");
   ActOut o; o.f32 = y;
   return launch_layernorm(x, d, w, b, o, rows, d, (cudaStream_t)stream);
+}
+
+// One decode-attention launch on caller data (kernel-level parity hook for GPT2Attention with T_q = 1 over a KV cache,
+// HF:models/gpt2/modeling_gpt2.py:185-220): qkv [rows, 3 H 64] bf16, K / V caches [rows][H][t_max][64] bf16 holding `pos` tokens;
+// appends the new token's K / V at position pos and writes out [rows, H 64] bf16.  variant: ring / kernel shape (0 = product).
+int gic_test_attn_decode(const void* qkv, void* kcache, void* vcache, void* out, int pos, int rows, int H, int t_max, int variant, void* stream) {
+  GIC_REQUIRE(qkv && kcache && vcache && out, "null argument");
+  GIC_REQUIRE(pos >= 0 && pos < t_max && rows > 0 && H > 0, "bad shape: pos %d t_max %d rows %d H %d", pos, t_max, rows, H);
+  cudaStream_t st = (cudaStream_t)stream;
+  GIC_TRY(gic_device_check());
+  GIC_TRY(gic::attn_decode_configure());
+  int* d_pos = nullptr;
+  GIC_CHECK_CUDA(cudaMalloc((void**)&d_pos, sizeof(int)));
+  cudaError_t ce = cudaMemcpyAsync(d_pos, &pos, sizeof(int), cudaMemcpyHostToDevice, st);
+  int r = GIC_OK;
+  if (ce == cudaSuccess) {
+    ActOut o; o.hi = (bf16*)out;
+    gic::attn_decode_set_variant(variant);
+    r = launch_attn_decode<bf16>((const bf16*)qkv, (bf16*)kcache, (bf16*)vcache, o, d_pos, rows, H, t_max, st);
+    gic::attn_decode_set_variant(-1);
+    ce = cudaStreamSynchronize(st);
+  }
+  cudaFree(d_pos);
+  if (r != GIC_OK) return r;
+  GIC_CHECK_CUDA(ce);
+  return GIC_OK;
 }
 
 }  // extern "C"

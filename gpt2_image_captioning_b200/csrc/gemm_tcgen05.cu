@@ -862,7 +862,7 @@ void gemm_bf16_pick(int M, int N, int K, int split, int split_k, int* block_n) {
   const int n_cand = split ? 2 : 5;
   const long m_tiles = ceil_div(M, GEMM_BLOCK_M);
   const int nk = ceil_div(K, GEMM_BLOCK_K);
-  const int sms = 148, S = split_k < 1 ? 1 : split_k;
+  const int sms = cta_limit() > 0 && cta_limit() < 148 ? cta_limit() : 148, S = split_k < 1 ? 1 : split_k;
   long best_cost = -1;
   *block_n = cand[0];
   for (int i = 0; i < n_cand; ++i) {
@@ -944,8 +944,8 @@ static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, EPI, OUT, FOLD, RAGGED>;
   const long tiles = (long)ceil_div(kp.M, GEMM_BLOCK_M) * ceil_div(kp.N, BLOCK_N) * kp.split_k;
 
-  const int sms = gemm_num_sms();
-  dim3 grid((unsigned)(tiles < sms ? tiles : sms));  // persistent: one CTA per SM
+  const int sms = cta_limit() > 0 && cta_limit() < gemm_num_sms() ? cta_limit() : gemm_num_sms();
+  dim3 grid((unsigned)(tiles < sms ? tiles : sms));  // persistent: one CTA per SM (of this chain's share, see cta_limit)
   GIC_CHECK_CUDA(launch_kernel(kern, grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st, kp));
   note_launch();
   return GIC_OK;

@@ -89,6 +89,7 @@ int launch_attn_prefill(const T* qkv, T* kcache, T* vcache, ActOut out, int B, i
                         cudaStream_t st);
 template <typename T>
 int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows, int H, int t_max, cudaStream_t st);
+void attn_decode_set_variant(int v);  // microbenchmark: ring geometry of the bulk-copy decode kernel (0 = product)
 int attn_decode_configure();  // cudaFuncSetAttribute for the bulk-copy decode kernel (call once, outside stream capture)
 template <typename T>
 int launch_attn_encoder(const T* qkv, ActOut out, int B, int S, int H, int hd, cudaStream_t st);

@@ -149,10 +149,10 @@ __global__ void init_decode_state_kernel(unsigned char* finished, int* first_eos
     first_eos[i] = max_new;
   }
   if (i == 0) {
-    // counter set 0: the whole batch through prefill and token 0, then the first half-batch; set 1: the second half-batch,
-    // which starts decoding at step 1 with its input token at position P
+    // counter set 0: the whole batch through prefill and token 0, then the first row group; sets 1..7: the other row groups,
+    // which start decoding at step 1 with their input token at position P
     d_step[0] = 0; d_pos[0] = P - 1; done_counter[0] = 0;
-    d_step[1] = 1; d_pos[1] = P; done_counter[1] = 0;
+    for (int s = 1; s < 8; ++s) { d_step[s] = 1; d_pos[s] = P; done_counter[s] = 0; }
   }
 }
 

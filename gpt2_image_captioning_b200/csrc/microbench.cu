@@ -26,6 +26,9 @@ static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap); }
 const char* get_error() { return g_err; }
 void note_launch() {}
+static int g_cta_limit = 0;
+int cta_limit() { return g_cta_limit; }
+void set_cta_limit(int c) { g_cta_limit = c; }
 bool pdl_enabled() { static int on = -1; if (on < 0) { const char* v = getenv("GIC_NO_PDL"); on = (v && v[0] == '1') ? 0 : 1; } return on == 1; }
 }  // namespace gic
 
@@ -59,6 +62,19 @@ static float time_loop(cudaStream_t st, int iters, F f) {
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, a, b));
   return ms * 1000.f / iters;  // us per iteration
+}
+
+__global__ void stream_read_kernel(const uint4* p, size_t n16, unsigned* sink) {
+  unsigned acc = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x * 4 + threadIdx.x; i < n16; i += stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = (i + u * blockDim.x < n16) ? __ldcs(p + i + u * blockDim.x) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc ^= v[u].x ^ v[u].y ^ v[u].z ^ v[u].w;
+  }
+  if (acc == 0x12345678u) *sink = acc;
 }
 
 int main(int argc, char** argv) {
@@ -113,6 +129,18 @@ int main(int argc, char** argv) {
   bf16* wte = (bf16*)dmalloc((size_t)V * d * 2);
   float* pv = (float*)dmalloc((size_t)2048 * B * 4); int* pi = (int*)dmalloc((size_t)2048 * B * 4);
   OK(tma_init()); OK(gemm_bf16_configure()); OK(attn_decode_configure());
+
+  // ---- mode 5 <variant> <ctx>: a handful of decode-attention launches of one kernel variant (the ncu target) ----
+  if (argc > 4 && atoi(argv[2]) == 5) {
+    const int variant = atoi(argv[3]), ctx = atoi(argv[4]);
+    int pos = ctx - 1;
+    CK(cudaMemcpy(dpos, &pos, 4, cudaMemcpyHostToDevice));
+    attn_decode_set_variant(variant);
+    ActOut y; y.hi = o;
+    float us = time_loop(st, 6, [&](int i) { OK(launch_attn_decode<bf16>(qkv, kc[i % SETS], vc[i % SETS], y, dpos, B, H, t_max, st)); });
+    printf("attn_decode v%d rows=%d ctx=%d: %.2f us (6 launches)\n", variant, B, ctx, us);
+    return 0;
+  }
 
   // ---- tensor-pipe probe: the LM-head GEMM with every MMA re-issued R times (no extra operand traffic) ----
   if (argc > 2 && atoi(argv[2]) == 2) {
@@ -241,14 +269,29 @@ int main(int argc, char** argv) {
       float us = time_loop(st, 50, [&](int) { OK(launch_gemm_bf16(g, st)); });
       printf("lm_head%s M=%d N=%d K=%d block_n=%d: %.2f us  %.1f TFLOP/s\n", fused ? " +LN" : "    ", B, V, d, bn, us, 2.0 * B * V * d / us * 1e-6);
     }
-  // ---- decode attention ----
+  // ---- decode attention: ring geometries of the bulk-copy kernel (variant 0 = product) ----
+  for (int variant : {0, 1, 10, 11, 12, 13, 14}) {
+    attn_decode_set_variant(variant);
+    for (int ctx : {11, 25, 39}) {
+      int pos = ctx - 1;
+      CK(cudaMemcpy(dpos, &pos, 4, cudaMemcpyHostToDevice));
+      ActOut y; y.hi = o;
+      float us = time_loop(st, 240, [&](int i) { OK(launch_attn_decode<bf16>(qkv, kc[i % SETS], vc[i % SETS], y, dpos, B, H, t_max, st)); });
+      const double bytes = 2.0 * B * d * (2.0 * ctx + 2 + 3 + 1);
+      printf("attn_decode v%d rows=%d ctx=%d: %.2f us  %.0f GB/s\n", variant, B, ctx, us, bytes / us * 1e-3);
+    }
+  }
+  attn_decode_set_variant(0);
+  // ---- what a kernel of this size can reach at all: plain streaming read of the same number of bytes (one launch each) ----
+  const size_t stream_set = (size_t)160 << 20;
+  uint8_t* stream_buf = (uint8_t*)dmalloc(stream_set * SETS);
   for (int ctx : {11, 25, 39}) {
-    int pos = ctx - 1;
-    CK(cudaMemcpy(dpos, &pos, 4, cudaMemcpyHostToDevice));
-    ActOut y; y.hi = o;
-    float us = time_loop(st, 240, [&](int i) { OK(launch_attn_decode<bf16>(qkv, kc[i % SETS], vc[i % SETS], y, dpos, B, H, t_max, st)); });
-    const double bytes = 2.0 * B * d * (2.0 * ctx + 2 + 3 + 1);
-    printf("attn_decode rows=%d ctx=%d: %.2f us  %.0f GB/s\n", B, ctx, us, bytes / us * 1e-3);
+    const size_t bytes = (size_t)(2.0 * B * d * (2.0 * ctx + 2 + 3 + 1));
+    const size_t n16 = bytes / 16;
+    float us = time_loop(st, 240, [&](int i) {
+      stream_read_kernel<<<148 * 4, 512, 0, st>>>((const uint4*)(stream_buf + (size_t)(i % SETS) * stream_set), n16, (unsigned*)pi);
+    });
+    printf("stream_read %zu MB (ctx=%d equivalent): %.2f us  %.0f GB/s\n", bytes >> 20, ctx, us, bytes / us * 1e-3);
   }
   return 0;
 }

@@ -97,6 +97,15 @@ def test_ln_mlp(h: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, wfc: t
                                   _ptr(stats_out), h.shape[0], h.shape[1], split_k, _stream()))
 
 
+@torch.library.custom_op("gic::test_attn_decode", mutates_args=("kcache", "vcache", "out"))
+def test_attn_decode(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, out: torch.Tensor, pos: int, variant: int) -> None:
+    """qkv [rows, 3*H*64] bf16; kcache / vcache [rows, H, t_max, 64] bf16; out [rows, H*64] bf16."""
+    _need_cuda(qkv, kcache, vcache, out)
+    L = _capi.lib()
+    rows, H, t_max = kcache.shape[0], kcache.shape[1], kcache.shape[2]
+    _capi.check(L.gic_test_attn_decode(qkv.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), out.data_ptr(), pos, rows, H, t_max, variant, _stream()))
+
+
 @torch.library.custom_op("gic::test_layernorm", mutates_args=("y",))
 def test_layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, y: torch.Tensor) -> None:
     _need_cuda(x, w, b, y)

@@ -186,6 +186,9 @@ GIC_API int gic_test_gemm(int dtype, const float* A, const float* W, const float
  * split-K) on caller data -- the kernel-level parity hook for HF GPT2Block's ln_2 + GPT2MLP (HF:models/gpt2/modeling_gpt2.py:238-243,304-307) */
 GIC_API int gic_test_ln_mlp(float* h, const float* gamma, const float* beta, const float* wfc, const float* bfc, const float* wfc2, const float* bfc2,
                             void* hb_out, void* stats_out, int M, int d, int split_k, void* stream);
+/* one decode-attention launch on caller data: qkv [rows, 3*H*64] bf16, K / V caches [rows][H][t_max][64] bf16 with `pos` cached tokens;
+ * appends the new K / V at `pos`, writes out [rows, H*64] bf16 (HF:models/gpt2/modeling_gpt2.py:185-220 for one query).  variant < 0: product kernel */
+GIC_API int gic_test_attn_decode(const void* qkv, void* kcache, void* vcache, void* out, int pos, int rows, int H, int t_max, int variant, void* stream);
 GIC_API int gic_test_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int d, void* stream);
 
 #ifdef __cplusplus

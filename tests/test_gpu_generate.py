@@ -198,6 +198,22 @@ def test_graph_and_eager_decode_agree(monkeypatch):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("dtype,groups", [("bf16", "2"), ("bf16", "4"), ("bf16", "8"), ("fp32", "3")])
+def test_row_group_decode_agrees_with_single_chain(monkeypatch, dtype, groups):
+    """GIC_SUBBATCH=n decodes n row groups on n streams inside one graph (rows never interact): same tokens,
+    also with a ragged last group and EOS rows."""
+    g = gu.load("tiny_mlp_eos")
+    xx = oc.synthetic_embeddings(700, 64, seed=11)
+    model, _, _ = gpu_util.product_model(g, dtype)
+    a = model.generate(image_embeddings=xx.to(DEV), max_length=12, temperature=0.0)
+    monkeypatch.setenv("GIC_SUBBATCH", groups)
+    model2, _, _ = gpu_util.product_model(g, dtype)
+    b = model2.generate(image_embeddings=xx.to(DEV), max_length=12, temperature=0.0)
+    c = model2.generate(image_embeddings=xx[:300].to(DEV), max_length=12, temperature=0.0)
+    assert torch.equal(a, b)
+    assert torch.equal(a[:300, : c.shape[1]], c) and bool((a[:300, c.shape[1]:] == g.get("eos", oc.EOS_TOKEN_ID)).all())
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_ragged_batches_and_row_independence(dtype):
     """Rows never interact: any batch split gives the same tokens; B = 1, odd sizes, > 128 rows."""

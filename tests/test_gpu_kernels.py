@@ -133,6 +133,39 @@ def test_fused_ln_mlp_block(M, d, split_k):
     assert torch.equal(h2, h)
 
 
+@pytest.mark.parametrize("variant", [-1, 0, 1, 10, 11, 12, 14])
+@pytest.mark.parametrize("rows,H,pos,t_max", [(3, 12, 0, 8), (5, 12, 1, 40), (64, 12, 15, 40), (33, 16, 16, 40), (130, 12, 38, 40), (17, 20, 69, 72), (300, 12, 31, 40)])
+def test_attn_decode_kernel(variant, rows, H, pos, t_max):
+    """One query per (row, head) against `pos` cached keys + its own: softmax(q K^T / 8) V in fp64 on the same bf16 inputs;
+    the new K / V must land at cache position `pos` and nothing else in the cache may change."""
+    ops, _ = _ops()
+    g = torch.Generator(device="cpu").manual_seed(rows * 1000 + pos)
+    d = H * 64
+    qkv = (torch.randn(rows, 3 * d, generator=g) * 1.5).bfloat16()
+    kc = torch.randn(rows, H, t_max, 64, generator=g).bfloat16()
+    vc = torch.randn(rows, H, t_max, 64, generator=g).bfloat16()
+    kc[:, :, pos:] = float("nan")  # slots that hold no token yet must never be read
+    vc[:, :, pos:] = float("nan")
+    out = torch.zeros(rows, d, dtype=torch.bfloat16, device=DEV)
+    kd, vd = kc.to(DEV), vc.to(DEV)
+    ops.test_attn_decode(qkv.to(DEV), kd, vd, out, pos, variant)
+    torch.cuda.synchronize()
+    q = qkv[:, :d].double().view(rows, H, 1, 64)
+    kn = qkv[:, d:2 * d].view(rows, H, 1, 64)
+    vn = qkv[:, 2 * d:].view(rows, H, 1, 64)
+    K = torch.cat((kc[:, :, :pos], kn), dim=2).double()
+    V = torch.cat((vc[:, :, :pos], vn), dim=2).double()
+    p = torch.softmax((q @ K.transpose(2, 3)) / 8.0, dim=-1)
+    ref = (p @ V).view(rows, d)
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err <= 2.0 ** -8 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+    kc2, vc2 = kc.clone(), vc.clone()
+    kc2[:, :, pos] = kn[:, :, 0]
+    vc2[:, :, pos] = vn[:, :, 0]
+    same = lambda a, b: torch.equal(a.view(torch.int16), b.view(torch.int16))  # bit-exact, NaN slots included
+    assert same(kd.cpu(), kc2) and same(vd.cpu(), vc2)
+
+
 @pytest.mark.parametrize("rows,d", [(1, 768), (1000, 768), (33, 1024), (7, 1280), (5, 128)])
 def test_layernorm(rows, d):
     ops, _ = _ops()
