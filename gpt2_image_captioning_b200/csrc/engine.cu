@@ -28,8 +28,9 @@ const char* get_error() { return g_err; }
 // packed weights
 // ---------------------------------------------------------------------------------------------------------------
 // W tensor maps are keyed by their box height = block_n
-static const int kBoxRows[5] = {32, 64, 128, 192, 256};
-static int box_rows_index(int rows) { for (int i = 0; i < 5; ++i) if (kBoxRows[i] == rows) return i; return -1; }
+static const int kNumBoxes = 6;
+static const int kBoxRows[kNumBoxes] = {32, 64, 96, 128, 192, 256};  // (96: half of a CTA pair's 192-wide tile)
+static int box_rows_index(int rows) { for (int i = 0; i < kNumBoxes; ++i) if (kBoxRows[i] == rows) return i; return -1; }
 
 struct Linear {  // y = x . W^T + b with W packed as [N,K] K-major
   int N = 0, K = 0;
@@ -38,7 +39,7 @@ struct Linear {  // y = x . W^T + b with W packed as [N,K] K-major
   bf16* w_lo = nullptr;
   float* bias = nullptr;
   float* colsum = nullptr;     // non-null: a LayerNorm is folded into this layer (w = gamma * W, bias = b + W . beta), see launch_fold_ln
-  TmaDesc tm_hi[5], tm_lo[5];  // per box height in kBoxRows
+  TmaDesc tm_hi[kNumBoxes], tm_lo[kNumBoxes];  // per box height in kBoxRows
 };
 struct Norm { float* w = nullptr; float* b = nullptr; };
 struct GptLayer { Norm ln1, ln2; Linear attn, proj, fc, fc2; };
@@ -197,7 +198,7 @@ static int pack_linear(gic_engine* e, Linear* lin, const float* w, const float* 
   } else if (bias) GIC_TRY(copy_vec(e, &lin->bias, bias, N, st));
   if (e->tc) {
     GIC_REQUIRE(K % 64 == 0, "tensor-core modes need K (%d) to be a multiple of 64", K);
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < kNumBoxes; ++i) {
       GIC_TRY(make_tma_2d_bf16(&lin->tm_hi[i], lin->w_hi, N, K, K, kBoxRows[i]));
       if (e->split) GIC_TRY(make_tma_2d_bf16(&lin->tm_lo[i], lin->w_lo, N, K, K, kBoxRows[i]));
     }
@@ -326,10 +327,17 @@ static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, i
     sk = gemm_bf16_split_k_for(lin.N, lin.K);
     if ((size_t)sk * M * lin.N > ln->splitk_ws_floats) sk = 1;
   }
-  gemm_bf16_pick(M, lin.N, lin.K, e->split ? 1 : 0, sk, &bn);
+  // CTA pairs (cta_group::2) exist for the fused-LayerNorm engine's GEMMs: folded qkv / fc, residual + statistics, LM-head argmax
+  const bool folded_in = ln && ln->stats_in, stats_out = ln && ln->stats_out;
+  const bool pair_kernel = e->fuse_ln && !e->split && sk == 1 &&
+                           ((part_val && !out.f32 && !folded_in) || (!part_val && folded_in && out.hi && !out.f32 && (epilogue == EPI_NONE || epilogue == EPI_GELU)) ||
+                            (!part_val && stats_out && epilogue == EPI_RESIDUAL));
+  int pair = 0;
+  gemm_bf16_pick(M, lin.N, lin.K, e->split ? 1 : 0, sk, &bn, pair_kernel ? &pair : nullptr);
   if (sk > 1) { g.split_k = sk; g.splitk_ws = ln->splitk_ws; g.splitk_counters = ln->splitk_counters; }
-  const int bi = box_rows_index(bn);
-  GIC_REQUIRE(bi >= 0, "no W tensor map for box height %d", bn);
+  g.pair = pair;
+  const int bi = box_rows_index(pair ? bn / 2 : bn);
+  GIC_REQUIRE(bi >= 0, "no W tensor map for box height %d", pair ? bn / 2 : bn);
   GIC_TRY(make_tma_2d_bf16(&g.a_hi, A.hi, M, lin.K, (ln && ln->a_row_stride) ? ln->a_row_stride : lin.K, 128));
   g.w_hi = lin.tm_hi[bi];
   if (e->split) {
@@ -982,9 +990,12 @@ int gic_test_gemm(int dtype, const float* A, const float* W, const float* bias, 
   int r = launch_convert(A, ao, na, st);
   if (r == GIC_OK) r = launch_convert(W, wo, nw, st);
   GemmBf16Args g;
-  const int bn = gemm_bf16_pick_block_n(M, N, split ? 1 : 0);
+  int bn = 0, pair = 0;
+  const bool pair_kernel = !split && epilogue == EPI_NONE && N % 32 == 0;  // the one fp32-output CTA-pair instantiation
+  gemm_bf16_pick(M, N, K, split ? 1 : 0, 1, &bn, pair_kernel ? &pair : nullptr);
+  g.pair = pair;
   if (r == GIC_OK) r = make_tma_2d_bf16(&g.a_hi, a_hi, M, K, K, 128);
-  if (r == GIC_OK) r = make_tma_2d_bf16(&g.w_hi, w_hi, N, K, K, bn);
+  if (r == GIC_OK) r = make_tma_2d_bf16(&g.w_hi, w_hi, N, K, K, pair ? bn / 2 : bn);
   if (r == GIC_OK && split) r = make_tma_2d_bf16(&g.a_lo, a_lo, M, K, K, 128);
   if (r == GIC_OK && split) r = make_tma_2d_bf16(&g.w_lo, w_lo, N, K, K, bn);
   g.M = M; g.N = N; g.K = K; g.block_n = bn; g.split = split; g.epilogue = epilogue; g.bias = bias;
@@ -1031,20 +1042,22 @@ int gic_test_ln_mlp(float* h, const float* gamma, const float* beta, const float
     if ((r = launch_row_stats(h, d, xb, stats, M, d, st)) != GIC_OK) break;
     {
       GemmBf16Args g;
-      int bn = 0;
-      gemm_bf16_pick(M, d4, d, 0, 1, &bn);
+      int bn = 0, pair = 0;
+      gemm_bf16_pick(M, d4, d, 0, 1, &bn, &pair);
+      g.pair = pair;
       if ((r = make_tma_2d_bf16(&g.a_hi, xb, M, d, d, 128)) != GIC_OK) break;
-      if ((r = make_tma_2d_bf16(&g.w_hi, wfc_p, d4, d, d, bn)) != GIC_OK) break;
+      if ((r = make_tma_2d_bf16(&g.w_hi, wfc_p, d4, d, d, pair ? bn / 2 : bn)) != GIC_OK) break;
       g.M = M; g.N = d4; g.K = d; g.block_n = bn; g.epilogue = EPI_GELU; g.bias = bias_f; g.out.hi = f; g.ld_out = d4;
       g.ln_stats = stats; g.ln_parts = 1; g.ln_stats_ld = M; g.ln_colsum = colsum;
       if ((r = launch_gemm_bf16(g, st)) != GIC_OK) break;
     }
     {
       GemmBf16Args g;
-      int bn = 0;
-      gemm_bf16_pick(M, d, d4, 0, split_k, &bn);
+      int bn = 0, pair = 0;
+      gemm_bf16_pick(M, d, d4, 0, split_k, &bn, &pair);
+      g.pair = pair;
       if ((r = make_tma_2d_bf16(&g.a_hi, f, M, d4, d4, 128)) != GIC_OK) break;
-      if ((r = make_tma_2d_bf16(&g.w_hi, wfc2_p, d, d4, d4, bn)) != GIC_OK) break;
+      if ((r = make_tma_2d_bf16(&g.w_hi, wfc2_p, d, d4, d4, pair ? bn / 2 : bn)) != GIC_OK) break;
       g.M = M; g.N = d; g.K = d4; g.block_n = bn; g.epilogue = EPI_RESIDUAL; g.bias = bfc2; g.out.f32 = h; g.out.hi = (bf16*)hb_out; g.ld_out = d;
       g.stats_out = (float2*)stats_out; g.ln_stats_ld = M;
       if (split_k > 1) { g.split_k = split_k; g.splitk_ws = ws; g.splitk_counters = counters; }

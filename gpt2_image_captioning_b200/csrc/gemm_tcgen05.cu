@@ -129,6 +129,58 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on the two SMs of a TPC issue ONE 256-row MMA; each stages its own 128 rows of A
+// and half of the W tile, so a W byte is delivered to (and read from) shared memory once per pair instead of once per CTA ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion is counted on the LEADER CTA's mbarrier (same offset; the peer bit of the shared::cluster address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {  // one warp in EACH CTA of the pair, same dst offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs of the pair once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the mbarrier at this offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
 }  // namespace ptx
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -176,10 +228,10 @@ constexpr int GEMM_THREADS = 320;
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_STAGING_BYTES = GEMM_EPI_WARPS * 32 * 128;  // per epilogue warp: 32 rows x 128 B, 16-byte chunks XOR-swizzled
 
-template <int BLOCK_N, bool SPLIT>
+template <int BLOCK_N, bool SPLIT, bool PAIR = false>
 struct GemmTile {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;  // [128 rows][128 B]
-  static constexpr int W_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;       // [BLOCK_N rows][128 B]
+  static constexpr int W_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * GEMM_BLOCK_K * 2;  // [BLOCK_N rows][128 B]; a CTA of a pair holds half of them
   static constexpr int STAGE_BYTES = (A_BYTES + W_BYTES) * (SPLIT ? 2 : 1);
   // one persistent CTA per SM: spend (almost) all of its shared memory on the TMA ring
   static constexpr int BUDGET = 227 * 1024 - 1024 /* alignment slack */ - 1024 /* barriers */ - GEMM_STAGING_BYTES;
@@ -210,9 +262,14 @@ enum GemmOut { OUT_NONE = 0 /* argmax partials only */, OUT_F32 = 1, OUT_BF16 = 
 // FOLD: LayerNorm folded into this GEMM (see GemmBf16Args::ln_stats).
 // RAGGED: N % 32 != 0 or a leading dimension that is not a multiple of 4 -- only these instantiations carry the slow generic
 // store path (every kernel here runs once per launch with a cold instruction cache: code size is latency).
-template <int BLOCK_N, bool SPLIT, int EPI, int OUT, bool FOLD, bool RAGGED>
+// PAIR: launched as clusters of two CTAs that share one 256 x BLOCK_N output tile (cta_group::2, see ptx:: above): CTA rank r owns
+// rows [128 r, 128 r + 128) of it (its own A tile, TMEM accumulator and epilogue) and stages W rows [r BLOCK_N / 2, (r + 1) BLOCK_N / 2).
+// Only the leader (rank 0) issues MMAs; both CTAs' TMA loads are counted on the leader's full barrier, the leader's commits
+// arrive on both CTAs' empty / accumulator-full barriers, and both epilogues release the accumulator on the leader's barrier.
+template <int BLOCK_N, bool SPLIT, int EPI, int OUT, bool FOLD, bool RAGGED, bool PAIR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKernelParams p) {
-  using Tile = GemmTile<BLOCK_N, SPLIT>;
+  using Tile = GemmTile<BLOCK_N, SPLIT, PAIR>;
+  static_assert(!PAIR || (!SPLIT && BLOCK_N % 32 == 0), "CTA pairs: bf16 operands, W halves of whole swizzle atoms");
   constexpr int STAGES = Tile::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment; everything below is addressed through 32-bit shared-window
@@ -232,9 +289,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   const int lane = threadIdx.x & 31;
   const int m_tiles = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int total_tiles = m_tiles * n_tiles;
+  // units along M: single 128-row tiles, or 256-row tiles shared by a CTA pair (this CTA: rows 128 * rank onwards)
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0;
+  const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles, m_per_unit = PAIR ? 2 : 1;
+  const int total_tiles = m_units * n_tiles;
   const int nk = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int total_work = total_tiles * p.split_k;  // work item w: tile = w % total_tiles, K slice = w / total_tiles
+  const int work0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, work_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   pdl_launch_dependents();  // let the next kernel's CTAs be scheduled behind this grid (see common.cuh)
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
   const long long t_start = tracing ? clock64() : 0;
@@ -252,14 +313,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tmem_full_bar + 8 * a, 1);
-      ptx::mbar_init(tmem_empty_bar + 8 * a, GEMM_EPI_WARPS);  // one arrival per epilogue warp
+      ptx::mbar_init(tmem_empty_bar + 8 * a, GEMM_EPI_WARPS * (PAIR ? 2 : 1));  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, Tile::TMEM_COLS);
+  if (warp == 1) {
+    if (PAIR) ptx::tmem_alloc_pair(tmem_slot, Tile::TMEM_COLS);
+    else ptx::tmem_alloc(tmem_slot, Tile::TMEM_COLS);
+  }
   ptx::tc_fence_before();
   __syncthreads();
+  if (PAIR) ptx::cluster_sync_all();  // both CTAs' barriers exist before the peer's TMA / commits / arrivals may touch them
   ptx::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -269,18 +334,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   if (warp == 0) {
     // ===== TMA producer: streams k-blocks of successive tiles through the ring without pausing at tile boundaries =====
     uint32_t s = 0, ph = 0, it = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+    for (int work = work0; work < total_work; work += work_stride) {
       const int tile = work % total_tiles, ks = work / total_tiles;
-      const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = (tile / m_tiles) * BLOCK_N;
+      const int m0 = ((tile % m_units) * m_per_unit + (int)rank) * GEMM_BLOCK_M, n0 = (tile / m_units) * BLOCK_N;
       const int kb_end = (int)((long)(ks + 1) * nk / p.split_k);
       for (int kb = (int)((long)ks * nk / p.split_k); kb < kb_end; ++kb, ++it) {
         ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
         if (ptx::elect_one()) {
           const uint32_t st = smem_base + s * Tile::STAGE_BYTES;
           const uint32_t fb = full_bar + 8 * s;
+          if (PAIR) {
+            // the leader's full barrier counts the bytes of both CTAs' loads (its arrival is the only pending one, so the
+            // phase cannot complete before it has armed the count, even if the peer's bytes land first)
+            if (rank == 0) ptx::mbar_expect_tx(fb, 2 * Tile::STAGE_BYTES);
+            ptx::tma_load_2d_pair(st, &p.a_hi, fb, kb * GEMM_BLOCK_K, m0);
+            ptx::tma_load_2d_pair(st + Tile::A_BYTES, &p.w_hi, fb, kb * GEMM_BLOCK_K, n0 + (int)rank * (BLOCK_N / 2));
+          } else {
           ptx::mbar_expect_tx(fb, Tile::STAGE_BYTES);
           ptx::tma_load_2d(st, &p.a_hi, fb, kb * GEMM_BLOCK_K, m0);
           ptx::tma_load_2d(st + Tile::A_BYTES, &p.w_hi, fb, kb * GEMM_BLOCK_K, n0);
+          }
           if (SPLIT) {
             ptx::tma_load_2d(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, fb, kb * GEMM_BLOCK_K, m0);
             ptx::tma_load_2d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, fb, kb * GEMM_BLOCK_K, n0);
@@ -292,9 +365,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected lane, whole warp converged), alternating between the two TMEM accumulators =====
-    constexpr uint32_t idesc = make_idesc_bf16(GEMM_BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M, BLOCK_N);
     uint32_t s = 0, ph = 0, it = 0, local = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++local) {
+    for (int work = (PAIR && rank != 0) ? total_work : work0; work < total_work; work += work_stride, ++local) {  // (pair: the leader only)
       const int ks = work / total_tiles;
       const int kb_begin = (int)((long)ks * nk / p.split_k), kb_end = (int)((long)(ks + 1) * nk / p.split_k);
       const uint32_t acc = local & 1, use = local >> 1;
@@ -315,15 +388,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
 #pragma unroll
             for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
               const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per k-step inside the 128-byte swizzle row
-              ptx::umma_bf16(tmem_acc, a_hi + koff, w_hi + koff, idesc, ((kb - kb_begin) | k | rep) != 0);
+              if (PAIR) ptx::umma_bf16_pair(tmem_acc, a_hi + koff, w_hi + koff, idesc, ((kb - kb_begin) | k | rep) != 0);
+              else ptx::umma_bf16(tmem_acc, a_hi + koff, w_hi + koff, idesc, ((kb - kb_begin) | k | rep) != 0);
               if (SPLIT) {
                 ptx::umma_bf16(tmem_acc, a_hi + koff, w_lo + koff, idesc, 1);
                 ptx::umma_bf16(tmem_acc, a_lo + koff, w_hi + koff, idesc, 1);
               }
             }
           }
+          if (PAIR) {
+            ptx::umma_commit_pair(empty_bar + 8 * s);                          // both CTAs' smem slots are free once these MMAs have read them
+            if (kb == kb_end - 1) ptx::umma_commit_pair(tmem_full_bar + 8 * acc);  // both CTAs' halves of the accumulator are complete
+          } else {
           ptx::umma_commit(empty_bar + 8 * s);                          // smem slot is free once these MMAs have read it
           if (kb == kb_end - 1) ptx::umma_commit(tmem_full_bar + 8 * acc);  // accumulator complete
+          }
           if (tracing && it < 60) p.trace[256 + it * 4 + 2] = clock64() - t_start;
         }
         __syncwarp();
@@ -341,11 +420,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     const int cchunk = lane & 7, crow0 = lane >> 3;
     constexpr bool fold = FOLD;
     uint32_t local = 0;
-    for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++local) {
+    // hand an accumulator back to the MMA warp (pair: the leader's, from both CTAs)
+    auto release_acc = [&](uint32_t a) {
+      if (PAIR) ptx::mbar_arrive_cluster(tmem_empty_bar + 8 * a, 0);
+      else ptx::mbar_arrive(tmem_empty_bar + 8 * a);
+    };
+    for (int work = work0; work < total_work; work += work_stride, ++local) {
       const int tile = work % total_tiles, ks = work / total_tiles;
       const uint32_t acc = local & 1, use = local >> 1;
-      const int n_tile = tile / m_tiles;
-      const int m0 = (tile % m_tiles) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
+      const int n_tile = tile / m_units;
+      const int m0 = ((tile % m_units) * m_per_unit + (int)rank) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
       const int wrow0 = m0 + q * 32;  // first row of this warp's 32-row band
       if (EPI == EPI_ARGMAX && OUT == OUT_NONE) {
         // ---- LM head on the product path: argmax straight from the TMEM registers (lane = row), nothing is staged or stored.
@@ -384,7 +468,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         const uint32_t tmem_row = tmem_base + acc * Tile::ACC_COLS + ((uint32_t)(q * 32) << 16);
         if (sub * 32 >= BLOCK_N) {
           ptx::tc_fence_before();
-          if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
+          if (lane == 0) release_acc(acc);
         }
 #pragma unroll 1
         for (int c0 = sub * 32; c0 < BLOCK_N; c0 += 64) {
@@ -422,7 +506,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           if (c0 + 64 >= BLOCK_N) {
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
+            if (lane == 0) release_acc(acc);
           }
           if (col0 >= p.N) continue;  // warp-uniform
           const float nrm = -rs * mu;  // v = rs * acc - rs * mu * colsum + bias
@@ -550,7 +634,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         if (tracing && e == 0 && lane == 0 && local < 8) p.trace[512 + local * 4 + 1] = clock64() - t_start;
         if (sub * 32 >= BLOCK_N) {  // BLOCK_N == 32: the second warp of the quarter has no chunk, it only releases the accumulator
           ptx::tc_fence_before();
-          if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
+          if (lane == 0) release_acc(acc);
         }
       }
 #pragma unroll 1
@@ -577,7 +661,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             // this warp's last TMEM read of the tile: hand the accumulator back to the MMA warp before the math / stores
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(tmem_empty_bar + 8 * acc);
+            if (lane == 0) release_acc(acc);
           }
           if (col0 >= p.N) continue;  // warp-uniform
           // lane = row  ->  staging tile (chunk position XOR row keeps both directions bank-conflict free)
@@ -810,7 +894,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, Tile::TMEM_COLS);
+  if (PAIR) ptx::cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the pair's MMAs / remote arrivals may still touch it
+  if (warp == 1) {
+    if (PAIR) ptx::tmem_dealloc_pair(tmem_base, Tile::TMEM_COLS);
+    else ptx::tmem_dealloc(tmem_base, Tile::TMEM_COLS);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -855,7 +943,10 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t col
 // Tile width and K split.  Cost model from the round-1 timelines (profiles/): a 64-deep k-block of a 128 x bn tile takes
 // 256 + 2 bn cycles (shared-memory port: TMA writes + UMMA operand reads), a CTA's epilogue ~600 + 500 per 64 columns, and a
 // split-K tile pays ~3000 for parking / re-reading the partials.  rounds = ceil(work items / #SMs).
-void gemm_bf16_pick(int M, int N, int K, int split, int split_k, int* block_n) {
+// pair (optional): set to 1 when a CTA pair (cta_group::2, 256-row tiles, see the kernel) is expected to be faster; a pair's k-block
+// takes max(256 + bn, 2 bn) cycles per CTA (half of the W tile each; the MMA itself needs 2 bn) and there are #SMs / 2 pairs.
+// GIC_GEMM_PAIR=0 never pairs, =2 pairs whenever the shape allows it (tests).
+void gemm_bf16_pick(int M, int N, int K, int split, int split_k, int* block_n, int* pair) {
   static const int wide[] = {256, 192, 128, 64, 32};
   static const int narrow[] = {64, 32};  // bf16x2 stages carry four operand tiles
   const int* cand = split ? narrow : wide;
@@ -872,6 +963,27 @@ void gemm_bf16_pick(int M, int N, int K, int split, int split_k, int* block_n) {
     const long cost = rounds * (ceil_div(nk, S) * (256 + 2 * bn) * (split ? 3 : 1) + 600 + 500L * ceil_div(bn, 64) + (S > 1 ? 3000 : 0));
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; *block_n = bn; }
   }
+  if (!pair) return;
+  *pair = 0;
+  const char* pv = getenv("GIC_GEMM_PAIR");
+  const int mode = pv ? atoi(pv) : 1;
+  if (mode == 0 || split || S > 1 || (m_tiles & 1) || cta_limit() > 0) return;
+  // measured (profiles/r1ag_microbench.txt): a pair saves ~110 cycles per k-block and costs ~2500 per launch (cluster scheduling + two
+  // cluster barriers), so it pays for long K (fc2: 15.4 -> 14.0 us at M = 1024, 59 -> 51 us at M = 10240) and for the many-round LM
+  // head (55.9 -> 49.1 us, 1.61 PFLOP/s = this box's cuBLAS burst rate), not for the single-round K = 768 GEMMs (+0.6 us)
+  if (mode != 2 && !(nk >= 32 || N >= 8192)) return;
+  static const int pair_bn[] = {256, 192, 128, 64};
+  long best_pair = -1;
+  int bn_pair = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = pair_bn[i];
+    const long units = (m_tiles / 2) * ceil_div(N, bn);
+    const long rounds = (units + sms / 2 - 1) / (sms / 2);
+    const long kb = 256 + bn > 2 * bn ? 256 + bn : 2 * bn;
+    const long cost = rounds * ((long)nk * kb + 600 + 500L * ceil_div(bn, 64));
+    if (best_pair < 0 || cost < best_pair) { best_pair = cost; bn_pair = bn; }
+  }
+  if (mode == 2 || best_pair < best_cost) { *pair = 1; *block_n = bn_pair; }
 }
 // K split of the decode-size residual GEMMs: a function of the SHAPE only (never of M), so that a row's fp32 summation
 // order -- and with it its tokens -- does not depend on the batch it is generated in
@@ -883,7 +995,7 @@ int gemm_bf16_split_k_for(int N, int K) {
 }
 int gemm_bf16_pick_block_n(int M, int N, int split) {
   int bn;
-  gemm_bf16_pick(M, N, 768, split, 1, &bn);
+  gemm_bf16_pick(M, N, 768, split, 1, &bn, nullptr);
   return bn;
 }
 
@@ -912,6 +1024,21 @@ static int gemm_num_sms() {
 #define GIC_GEMM_VARIANTS_SPLIT(X) \
   X(EPI_NONE, OUT_BF16X2, false, false) X(EPI_TANH, OUT_BF16X2, false, false) X(EPI_GELU, OUT_BF16X2, false, false) X(EPI_RELU, OUT_BF16X2, false, false)
 
+// CTA-pair instantiations (aligned shapes, bf16 operands): the fused decode / prefill GEMMs, the LM head, and the plain fp32-output
+// GEMM of the kernel test hook
+#define GIC_GEMM_VARIANTS_PAIR(X) \
+  X(EPI_NONE, OUT_BF16, true) X(EPI_GELU, OUT_BF16, true) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_NONE, OUT_F32, false)
+
+template <int BLOCK_N>
+static int configure_pair() {
+#define X(E, O, F)                                                                                                                         \
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, false, E, O, F, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      GemmTile<BLOCK_N, false, true>::SMEM_BYTES));
+  GIC_GEMM_VARIANTS_PAIR(X)
+#undef X
+  return GIC_OK;
+}
+
 template <int BLOCK_N, bool SPLIT>
 static int configure_cfg() {
 #define X(E, O, F, R)                                                                                                                \
@@ -934,6 +1061,10 @@ int gemm_bf16_configure() {
   GIC_TRY((configure_cfg<256, false>()));
   GIC_TRY((configure_cfg<32, true>()));
   GIC_TRY((configure_cfg<64, true>()));
+  GIC_TRY((configure_pair<64>()));
+  GIC_TRY((configure_pair<128>()));
+  GIC_TRY((configure_pair<192>()));
+  GIC_TRY((configure_pair<256>()));
   done = true;
   return GIC_OK;
 }
@@ -949,6 +1080,56 @@ static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
   GIC_CHECK_CUDA(launch_kernel(kern, grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st, kp));
   note_launch();
   return GIC_OK;
+}
+
+// one cluster of two CTAs per 256 x BLOCK_N tile; persistent over as many pairs as can be co-resident (a pair needs both SMs of a TPC)
+template <int BLOCK_N, int EPI, int OUT, bool FOLD>
+static int launch_one_pair(const GemmKernelParams& kp, cudaStream_t st) {
+  using Tile = GemmTile<BLOCK_N, false, true>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, false, EPI, OUT, FOLD, false, true>;
+  static int max_pairs = 0;
+  if (max_pairs == 0) {
+    int n = 0;
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3(2 * 74); q.blockDim = dim3(GEMM_THREADS); q.dynamicSmemBytes = Tile::SMEM_BYTES;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    q.attrs = qa; q.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) { cudaGetLastError(); n = gemm_num_sms() / 2; }
+    max_pairs = n;
+  }
+  const long units = (long)(ceil_div(kp.M, GEMM_BLOCK_M) / 2) * ceil_div(kp.N, BLOCK_N);
+  const long pairs = units < max_pairs ? units : max_pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Tile::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+  ++na;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  GIC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
+  note_launch();
+  return GIC_OK;
+}
+
+template <int BLOCK_N>
+static int launch_cfg_pair(const GemmKernelParams& kp, int epi, int out, bool fold, cudaStream_t st) {
+#define X(E, O, F) \
+  if (epi == E && out == O && fold == F) return launch_one_pair<BLOCK_N, E, O, F>(kp, st);
+  GIC_GEMM_VARIANTS_PAIR(X)
+#undef X
+  set_error("gemm_bf16: no CTA-pair kernel for epilogue %d with output mode %d%s", epi, out, fold ? " + folded LayerNorm" : "");
+  return GIC_ERR_UNSUPPORTED;
 }
 
 // (epilogue, output, fold) combinations that exist only in the ragged flavour (test / logits-tap paths)
@@ -1005,6 +1186,19 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
     GIC_REQUIRE(epi != EPI_ARGMAX && a.splitk_ws && a.splitk_counters, "gemm_bf16: split-K needs its workspace / counters and a storing epilogue");
     GIC_REQUIRE(a.N % 32 == 0 && a.ld_out % 4 == 0, "gemm_bf16: split-K needs N %% 32 == 0 and aligned outputs");
     GIC_REQUIRE(ceil_div(a.K, GEMM_BLOCK_K) >= kp.split_k, "gemm_bf16: more K slices than k-blocks");
+  }
+  if (a.pair) {
+    GIC_REQUIRE(!a.split && kp.split_k == 1, "gemm_bf16: CTA pairs take plain bf16 operands and no K split");
+    GIC_REQUIRE(ceil_div(a.M, GEMM_BLOCK_M) % 2 == 0, "gemm_bf16: CTA pairs need an even number of 128-row tiles (M = %d)", a.M);
+    GIC_REQUIRE(out == OUT_NONE || (a.N % 32 == 0 && a.ld_out % 4 == 0), "gemm_bf16: CTA pairs need N %% 32 == 0 and aligned outputs");
+    switch (a.block_n) {
+      case 64: return launch_cfg_pair<64>(kp, epi, out, fold, st);
+      case 128: return launch_cfg_pair<128>(kp, epi, out, fold, st);
+      case 192: return launch_cfg_pair<192>(kp, epi, out, fold, st);
+      case 256: return launch_cfg_pair<256>(kp, epi, out, fold, st);
+    }
+    set_error("gemm_bf16: unsupported block_n %d for a CTA pair", a.block_n);
+    return GIC_ERR_UNSUPPORTED;
   }
   if (a.split) {
     switch (a.block_n) {

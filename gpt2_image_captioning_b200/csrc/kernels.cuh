@@ -53,13 +53,15 @@ struct GemmBf16Args {
   const float* ln_colsum = nullptr;  // [N] sum_k of the packed (bf16) gamma-folded weights
   float2* stats_out = nullptr;       // [ceil(N / 32)][ln_stats_ld]: per-row (sum, sum of squares) of the values this GEMM writes, per 32-column chunk
   // split-K for short-and-wide problems (few output tiles, long K): split_k CTAs per tile, deterministic last-CTA reduction
+  int pair = 0;  // CTA pairs: 256 x block_n tiles by two CTAs (cta_group::2); w_hi's box holds block_n / 2 rows
   int split_k = 1; float* splitk_ws = nullptr;  /* [split_k][M][N] fp32 */  int* splitk_counters = nullptr;  /* [tiles], zero on entry and exit */
   long long* trace = nullptr;      // microbenchmark only: device buffer of >= 640 int64 for CTA 0's clock64 timeline
 };
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st);
 int gemm_bf16_pick_block_n(int M, int N, int split);
 // tile width for an M x N x K problem cut into split_k K slices (split: bf16x2 operands)
-void gemm_bf16_pick(int M, int N, int K, int split, int split_k, int* block_n);
+// pair (may be null): out, 1 = run as CTA pairs (cta_group::2); the W tensor map's box is then block_n / 2 rows and GemmBf16Args::pair is set
+void gemm_bf16_pick(int M, int N, int K, int split, int split_k, int* block_n, int* pair = nullptr);
 int gemm_bf16_split_k_for(int N, int K);  // K split of a decode-size residual GEMM: depends on the shape only
 
 int gemm_bf16_configure();  // cudaFuncSetAttribute for every instantiation (call once, outside stream capture)

@@ -234,43 +234,63 @@ int main(int argc, char** argv) {
   float* bias_v = (float*)dmalloc((size_t)V * 4);
   float* skws = (float*)dmalloc((size_t)4 * B * d * 4);
   int* skcnt = (int*)dmalloc(4096 * 4);
-  for (int fused = 0; fused < 3; ++fused)  // 2: fused + K split (residual GEMMs)
+  // fused: 0 plain, 1 LayerNorm folded / statistics out (the engine's kernels), 2 the same as CTA pairs (cta_group::2)
+  for (int fused = 0; fused < 3; ++fused)
     for (auto& s : shapes) {
-      const int sk = fused == 2 ? gemm_bf16_split_k_for(s.N, s.K) : 1;
-      if (fused == 2 && (!s.res || sk == 1)) continue;
-      int bn_pick = 0;
-      gemm_bf16_pick(B, s.N, s.K, 0, sk, &bn_pick);
+      int bn_pick = 0, pair_pick = 0;
+      gemm_bf16_pick(B, s.N, s.K, 0, 1, &bn_pick, fused == 2 ? &pair_pick : nullptr);
       for (int bn : {64, 128, 192, 256}) {
-        if (fused && bn != bn_pick && !(fused == 2 && bn <= 256)) continue;
+        if (fused == 1 && bn != bn_pick) continue;
+        const int pair = fused == 2;
         std::vector<GemmBf16Args> args(SETS);
         for (int i = 0; i < SETS; ++i) {
           GemmBf16Args& g = args[i];
           OK(make_tma_2d_bf16(&g.a_hi, a, B, s.K, s.K, 128));
-          OK(make_tma_2d_bf16(&g.w_hi, (*s.w)[i], s.N, s.K, s.K, bn));
-          g.M = B; g.N = s.N; g.K = s.K; g.block_n = bn; g.epilogue = s.epi; g.bias = bias; g.ld_out = s.N;
+          OK(make_tma_2d_bf16(&g.w_hi, (*s.w)[i], s.N, s.K, s.K, pair ? bn / 2 : bn));
+          g.M = B; g.N = s.N; g.K = s.K; g.block_n = bn; g.epilogue = s.epi; g.bias = bias; g.ld_out = s.N; g.pair = pair;
           if (s.res) g.out.f32 = h; else g.out.hi = (s.N == 3 * d ? qkv : o);
           if (fused) {  // LayerNorm folded: statistics in for qkv / fc, bf16 copy + statistics out for the residual GEMMs
-            if (s.res) { g.out.hi = o; g.stats_out = stats; g.ln_stats_ld = B; if (sk > 1) { g.split_k = sk; g.splitk_ws = skws; g.splitk_counters = skcnt; } }
+            if (s.res) { g.out.hi = o; g.stats_out = stats; g.ln_stats_ld = B; }
             else { g.ln_stats = stats; g.ln_parts = d / 32; g.ln_stats_ld = B; g.ln_colsum = colsum; }
           }
         }
         float us = time_loop(st, 240, [&](int i) { OK(launch_gemm_bf16(args[i % SETS], st)); });
-        printf("gemm %-4s%s M=%d N=%d K=%d block_n=%3d: %7.2f us  %6.1f TFLOP/s  (picked %d)\n", s.name, fused == 2 ? " +LN split-K" : fused ? " +LN" : "    ", B,
-               s.N, s.K, bn, us, 2.0 * B * s.N * s.K / us * 1e-6, bn_pick);
+        printf("gemm %-4s%s M=%d N=%d K=%d block_n=%3d: %7.2f us  %6.1f TFLOP/s  (picked %d%s)\n", s.name, fused == 2 ? " +LN pair" : fused ? " +LN     " : "         ", B,
+               s.N, s.K, bn, us, 2.0 * B * s.N * s.K / us * 1e-6, bn_pick, pair_pick ? " pair" : "");
       }
     }
-  for (int fused = 0; fused < 2; ++fused)
+  // prefill-size GEMMs (M = 10 B rows), single CTAs vs pairs
+  {
+    const int Mp = 10 * B;
+    bf16* ap = (bf16*)dmalloc((size_t)Mp * 4 * d * 2);
+    bf16* op = (bf16*)dmalloc((size_t)Mp * 4 * d * 2);
+    float* hp = (float*)dmalloc((size_t)Mp * d * 4);
+    float2* statsp = (float2*)dmalloc((size_t)64 * Mp * 8);
+    for (auto& s : shapes)
+      for (int pair = 0; pair < 2; ++pair)
+        for (int bn : {128, 192, 256}) {
+          GemmBf16Args g;
+          OK(make_tma_2d_bf16(&g.a_hi, ap, Mp, s.K, s.K, 128));
+          OK(make_tma_2d_bf16(&g.w_hi, (*s.w)[0], s.N, s.K, s.K, pair ? bn / 2 : bn));
+          g.M = Mp; g.N = s.N; g.K = s.K; g.block_n = bn; g.epilogue = s.epi; g.bias = bias; g.ld_out = s.N; g.pair = pair;
+          if (s.res) { g.out.f32 = hp; g.out.hi = op; g.stats_out = statsp; g.ln_stats_ld = Mp; }
+          else { g.out.hi = op; g.ln_stats = statsp; g.ln_parts = d / 32; g.ln_stats_ld = Mp; g.ln_colsum = colsum; }
+          float us = time_loop(st, 40, [&](int) { OK(launch_gemm_bf16(g, st)); });
+          printf("prefill gemm %-4s%s M=%d N=%d K=%d block_n=%3d: %7.2f us  %6.1f TFLOP/s\n", s.name, pair ? " pair" : "     ", Mp, s.N, s.K, bn, us,
+                 2.0 * Mp * s.N * s.K / us * 1e-6);
+        }
+  }
+  for (int pair = 0; pair < 2; ++pair)
     for (int bn : {128, 192, 256}) {
       GemmBf16Args g;
       OK(make_tma_2d_bf16(&g.a_hi, a, B, d, d, 128));
-      OK(make_tma_2d_bf16(&g.w_hi, wte, V, d, d, bn));
-      g.M = B; g.N = V; g.K = d; g.block_n = bn; g.part_val = pv; g.part_idx = pi; g.part_ld = 2048;
-      if (fused) { g.ln_stats = stats; g.ln_parts = d / 32; g.ln_stats_ld = B; g.ln_colsum = colsum; g.bias = bias_v; }
+      OK(make_tma_2d_bf16(&g.w_hi, wte, V, d, d, pair ? bn / 2 : bn));
+      g.M = B; g.N = V; g.K = d; g.block_n = bn; g.part_val = pv; g.part_idx = pi; g.part_ld = 2048; g.pair = pair;
       float us = time_loop(st, 50, [&](int) { OK(launch_gemm_bf16(g, st)); });
-      printf("lm_head%s M=%d N=%d K=%d block_n=%d: %.2f us  %.1f TFLOP/s\n", fused ? " +LN" : "    ", B, V, d, bn, us, 2.0 * B * V * d / us * 1e-6);
+      printf("lm_head%s M=%d N=%d K=%d block_n=%d: %.2f us  %.1f TFLOP/s\n", pair ? " pair" : "     ", B, V, d, bn, us, 2.0 * B * V * d / us * 1e-6);
     }
   // ---- decode attention: ring geometries of the bulk-copy kernel (variant 0 = product) ----
-  for (int variant : {0, 1, 10, 11, 12, 13, 14}) {
+  for (int variant : {0, 10, 12}) {
     attn_decode_set_variant(variant);
     for (int ctx : {11, 25, 39}) {
       int pos = ctx - 1;

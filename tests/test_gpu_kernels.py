@@ -74,6 +74,53 @@ def test_gemm_tcgen05(M, N, K, mode):
     assert err <= tol * scale, f"{mode} M={M} N={N} K={K}: max abs err {err} (scale {scale})"
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 64, 64), (256, 256, 128), (512, 2304, 768), (1024, 768, 3072), (1000, 3072, 768), (2048, 50272, 64), (10240, 768, 768)])
+def test_gemm_cta_pair(monkeypatch, M, N, K):
+    """cta_group::2: two CTAs share a 256-row tile (each its own A rows and half of the W tile).  GIC_GEMM_PAIR=2 forces the pair
+    kernel wherever the shape allows it; the result must equal the single-CTA kernel's bit for bit (same products, same order)."""
+    ops, capi = _ops()
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) * 0.05).to(DEV)
+    b = torch.randn(N, generator=g).to(DEV)
+    C1 = torch.empty(M, N, device=DEV)
+    C2 = torch.empty(M, N, device=DEV)
+    monkeypatch.setenv("GIC_GEMM_PAIR", "0")
+    ops.test_gemm(capi.DTYPE_BF16, A, W, b, C1, 0)
+    monkeypatch.setenv("GIC_GEMM_PAIR", "2")
+    ops.test_gemm(capi.DTYPE_BF16, A, W, b, C2, 0)
+    torch.cuda.synchronize()
+    ref = A.bfloat16().double() @ W.bfloat16().double().t() + b.double()
+    scale = (A.double().abs() @ W.double().abs().t()).max().item()
+    err = (C2.double() - ref).abs().max().item()
+    assert err <= 2e-5 * scale, f"pair M={M} N={N} K={K}: max abs err {err} (scale {scale})"
+    assert torch.equal(C1, C2)
+
+
+@pytest.mark.parametrize("M,d", [(1024, 768), (388, 768), (256, 128), (1300, 256)])
+def test_fused_ln_mlp_block_cta_pair(monkeypatch, M, d):
+    """the fused MLP sub-block with both GEMMs forced onto CTA pairs (where the tile count is even): same bits as single CTAs"""
+    ops, capi = _ops()
+    g = torch.Generator(device="cpu").manual_seed(M + d)
+    h0 = torch.randn(M, d, generator=g) * 1.5 + 0.3
+    gamma = 1.0 + 0.1 * torch.randn(d, generator=g)
+    beta = 0.1 * torch.randn(d, generator=g)
+    wfc = torch.randn(4 * d, d, generator=g) * 0.03
+    bfc = torch.randn(4 * d, generator=g) * 0.1
+    wfc2 = torch.randn(d, 4 * d, generator=g) * 0.03
+    bfc2 = torch.randn(d, generator=g) * 0.1
+    outs = []
+    for mode in ("0", "2"):
+        monkeypatch.setenv("GIC_GEMM_PAIR", mode)
+        h = h0.clone().to(DEV)
+        hb = torch.empty(M, d, dtype=torch.bfloat16, device=DEV)
+        stats = torch.zeros(d // 32, M, 2, device=DEV)
+        ops.test_ln_mlp(h, gamma.to(DEV), beta.to(DEV), wfc.to(DEV), bfc.to(DEV), wfc2.to(DEV), bfc2.to(DEV), hb, stats, 1)
+        torch.cuda.synchronize()
+        outs.append((h.cpu(), hb.cpu(), stats.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
 @pytest.mark.parametrize("epi", [1, 2, 3, 4])
 def test_gemm_tcgen05_epilogues(epi):
     ops, capi = _ops()
