@@ -1103,4 +1103,17 @@ int gic_test_attn_decode(const void* qkv, void* kcache, void* vcache, void* out,
   return GIC_OK;
 }
 
+// One causal prefill-attention launch on caller data (GPT2Attention over the S prefix tokens of every row, HF:models/gpt2/modeling_gpt2.py:185-220):
+// qkv [rows * S, 3 H 64] bf16 -> out [rows * S, H 64] bf16, K / V written to caches [rows][H][t_max][64] at positions 0..S-1.
+int gic_test_attn_prefill(const void* qkv, void* kcache, void* vcache, void* out, int rows, int S, int H, int t_max, void* stream) {
+  GIC_REQUIRE(qkv && kcache && vcache && out, "null argument");
+  GIC_REQUIRE(S >= 1 && S <= t_max && rows > 0 && H > 0, "bad shape: S %d t_max %d rows %d H %d", S, t_max, rows, H);
+  cudaStream_t st = (cudaStream_t)stream;
+  GIC_TRY(gic_device_check());
+  ActOut o; o.hi = (bf16*)out;
+  GIC_TRY(launch_attn_prefill<bf16>((const bf16*)qkv, (bf16*)kcache, (bf16*)vcache, o, rows, S, H, t_max, 1, st));
+  GIC_CHECK_CUDA(cudaStreamSynchronize(st));
+  return GIC_OK;
+}
+
 }  // extern "C"

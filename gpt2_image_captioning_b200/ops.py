@@ -106,6 +106,15 @@ def test_attn_decode(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tens
     _capi.check(L.gic_test_attn_decode(qkv.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), out.data_ptr(), pos, rows, H, t_max, variant, _stream()))
 
 
+@torch.library.custom_op("gic::test_attn_prefill", mutates_args=("kcache", "vcache", "out"))
+def test_attn_prefill(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, out: torch.Tensor, S: int) -> None:
+    """qkv [rows*S, 3*H*64] bf16; kcache / vcache [rows, H, t_max, 64] bf16; out [rows*S, H*64] bf16."""
+    _need_cuda(qkv, kcache, vcache, out)
+    L = _capi.lib()
+    rows, H, t_max = kcache.shape[0], kcache.shape[1], kcache.shape[2]
+    _capi.check(L.gic_test_attn_prefill(qkv.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), out.data_ptr(), rows, S, H, t_max, _stream()))
+
+
 @torch.library.custom_op("gic::test_layernorm", mutates_args=("y",))
 def test_layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, y: torch.Tensor) -> None:
     _need_cuda(x, w, b, y)

@@ -213,6 +213,32 @@ def test_attn_decode_kernel(variant, rows, H, pos, t_max):
     assert same(kd.cpu(), kc2) and same(vd.cpu(), vc2)
 
 
+@pytest.mark.parametrize("rows,H,S,t_max", [(3, 12, 1, 8), (37, 12, 10, 40), (9, 16, 16, 20), (11, 16, 17, 72), (6, 12, 40, 70), (5, 20, 64, 64), (2, 12, 70, 80)])
+def test_attn_prefill_kernel(rows, H, S, t_max):
+    """causal attention over the S prefix tokens of every (row, head) in fp64 on the same bf16 inputs; K / V of the S tokens
+    must land in the cache and the rest of the cache must stay untouched (S = 70 takes the generic kernel)."""
+    ops, _ = _ops()
+    g = torch.Generator(device="cpu").manual_seed(rows * 100 + S)
+    d = H * 64
+    qkv = (torch.randn(rows * S, 3 * d, generator=g) * 1.5).bfloat16()
+    kc = torch.full((rows, H, t_max, 64), float("nan")).bfloat16()
+    vc = torch.full((rows, H, t_max, 64), float("nan")).bfloat16()
+    out = torch.zeros(rows * S, d, dtype=torch.bfloat16, device=DEV)
+    kd, vd = kc.to(DEV), vc.to(DEV)
+    ops.test_attn_prefill(qkv.to(DEV), kd, vd, out, S)
+    torch.cuda.synchronize()
+    q, k, v = (qkv[:, i * d:(i + 1) * d].view(rows, S, H, 64).permute(0, 2, 1, 3) for i in range(3))
+    sc = (q.double() @ k.double().transpose(2, 3)) / 8.0
+    sc = sc.masked_fill(torch.triu(torch.ones(S, S, dtype=torch.bool), diagonal=1), float("-inf"))
+    ref = (torch.softmax(sc, dim=-1) @ v.double()).permute(0, 2, 1, 3).reshape(rows * S, d)
+    err = (out.cpu().double() - ref).abs().max().item()
+    assert err <= 2.0 ** -8 * max(1.0, ref.abs().max().item()), f"max abs err {err}"
+    kc[:, :, :S] = k
+    vc[:, :, :S] = v
+    same = lambda a, b: torch.equal(a.contiguous().view(torch.int16), b.contiguous().view(torch.int16))
+    assert same(kd.cpu(), kc) and same(vd.cpu(), vc)
+
+
 @pytest.mark.parametrize("rows,d", [(1, 768), (1000, 768), (33, 1024), (7, 1280), (5, 128)])
 def test_layernorm(rows, d):
     ops, _ = _ops()
