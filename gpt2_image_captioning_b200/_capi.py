@@ -78,6 +78,10 @@ SIGNATURES = {
     "gic_generate_beam": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),
     "gic_kv_reorder": (C.c_int, [C.c_void_p, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gic_topk_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gic_topk_tc_supported": (C.c_int, [C.c_int, C.c_int]),
+    "gic_topk_tc_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gic_pack_bf16x2": (C.c_int, [_fp, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "gic_topk_ip_tc": (C.c_int, [_fp, _fp, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),
     "gic_topk_ip": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),
     "gic_select_caption_rows": (C.c_int, [_fp, _fp, C.c_int, C.c_int, _fp, _fp, C.c_int, C.c_int, _fp, C.c_void_p]),
     "gic_gather_aggregate_add": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_void_p]),

@@ -590,8 +590,12 @@ int gic_abi_version(void) { return GIC_ABI_VERSION; }
 int gic_device_check(void) {
   int dev = 0;
   GIC_CHECK_CUDA(cudaGetDevice(&dev));
+  // (cudaGetDeviceProperties takes milliseconds and is called from per-request entry points: ask once per device)
+  static unsigned char checked[64] = {0};
+  if (dev >= 0 && dev < 64 && checked[dev]) return GIC_OK;
   cudaDeviceProp prop;
   GIC_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major == 10 && dev >= 0 && dev < 64) checked[dev] = 1;
   if (prop.major != 10) {
     gic::set_error("device %d (%s) is sm_%d%d; this library contains sm_100a code only", dev, prop.name, prop.major, prop.minor);
     return GIC_ERR_UNSUPPORTED;
@@ -914,6 +918,23 @@ int gic_kv_reorder(gic_engine* e, const void* kv_src, void* kv_dst, const int32_
 }
 
 size_t gic_topk_workspace_bytes(int batch, int n_rows, int dim, int k) { return gic::topk_workspace_bytes(batch, n_rows, dim, k); }
+
+int gic_topk_tc_supported(int dim, int k) { return gic::topk_tc_supported(dim, k) ? 1 : 0; }
+size_t gic_topk_tc_workspace_bytes(int batch, int n_rows, int dim, int k) { return gic::topk_tc_workspace_bytes(batch, n_rows, dim, k); }
+
+int gic_pack_bf16x2(const float* src, void* hi, void* lo, size_t n, void* stream) {
+  GIC_REQUIRE(src && hi && lo, "null argument");
+  ActOut o; o.hi = (bf16*)hi; o.lo = (bf16*)lo;
+  return launch_convert(src, o, n, (cudaStream_t)stream);
+}
+
+int gic_topk_ip_tc(const float* q, const float* db, const void* db_hi, const void* db_lo, float db_norm_max, int batch, int n_rows, int dim, int k,
+                   float* scores_out, int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream) {
+  GIC_REQUIRE(q && db && db_hi && db_lo && scores_out && idx_out && workspace, "null argument");
+  GIC_TRY(gic_device_check());
+  return launch_topk_ip_tc(q, db, (const bf16*)db_hi, (const bf16*)db_lo, db_norm_max, batch, n_rows, dim, k, scores_out, idx_out, workspace,
+                           workspace_bytes, (cudaStream_t)stream);
+}
 
 int gic_topk_ip(const float* q, const float* db, int batch, int n_rows, int dim, int k, float* scores_out, int64_t* idx_out, void* workspace,
                 size_t workspace_bytes, void* stream) {

@@ -1069,6 +1069,8 @@ int gemm_bf16_configure() {
   return GIC_OK;
 }
 
+static thread_local bool g_gemm_no_pdl = false;  // set by launch_gemm_bf16 from GemmBf16Args::no_pdl for the launch it issues
+
 template <int BLOCK_N, bool SPLIT, int EPI, int OUT, bool FOLD, bool RAGGED>
 static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
   using Tile = GemmTile<BLOCK_N, SPLIT>;
@@ -1077,7 +1079,12 @@ static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
 
   const int sms = cta_limit() > 0 && cta_limit() < gemm_num_sms() ? cta_limit() : gemm_num_sms();
   dim3 grid((unsigned)(tiles < sms ? tiles : sms));  // persistent: one CTA per SM (of this chain's share, see cta_limit)
-  GIC_CHECK_CUDA(launch_kernel(kern, grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st, kp));
+  if (g_gemm_no_pdl) {
+    kern<<<grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st>>>(kp);
+    GIC_CHECK_CUDA(cudaGetLastError());
+  } else {
+    GIC_CHECK_CUDA(launch_kernel(kern, grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st, kp));
+  }
   note_launch();
   return GIC_OK;
 }
@@ -1149,6 +1156,7 @@ static int launch_cfg(const GemmKernelParams& kp, int epi, int out, bool fold, c
 }
 
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
+  struct NoPdlScope { bool prev; explicit NoPdlScope(bool v) : prev(g_gemm_no_pdl) { g_gemm_no_pdl = v; } ~NoPdlScope() { g_gemm_no_pdl = prev; } } no_pdl_scope(a.no_pdl != 0);
   GIC_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm_bf16: empty problem");
   GIC_REQUIRE(a.K % 8 == 0, "gemm_bf16: K (%d) must be a multiple of 8", a.K);
   GemmKernelParams kp;

@@ -53,6 +53,8 @@ struct GemmBf16Args {
   const float* ln_colsum = nullptr;  // [N] sum_k of the packed (bf16) gamma-folded weights
   float2* stats_out = nullptr;       // [ceil(N / 32)][ln_stats_ld]: per-row (sum, sum of squares) of the values this GEMM writes, per 32-column chunk
   // split-K for short-and-wide problems (few output tiles, long K): split_k CTAs per tile, deterministic last-CTA reduction
+  int no_pdl = 0;  // launch in plain stream order (no programmatic dependent launch): for callers that mix these launches with ordinary
+                   // <<<>>> launches outside a graph -- measured: the host then blocks for milliseconds inside cudaLaunchKernelEx
   int pair = 0;  // CTA pairs: 256 x block_n tiles by two CTAs (cta_group::2); w_hi's box holds block_n / 2 rows
   int split_k = 1; float* splitk_ws = nullptr;  /* [split_k][M][N] fp32 */  int* splitk_counters = nullptr;  /* [tiles], zero on entry and exit */
   long long* trace = nullptr;      // microbenchmark only: device buffer of >= 640 int64 for CTA 0's clock64 timeline
@@ -143,6 +145,11 @@ int launch_beam_finalize(const BeamState& s, int final_buf, int64_t* ids_out, fl
 
 // ---- retrieval.cu -------------------------------------------------------------------------------------------------
 size_t topk_workspace_bytes(int B, int N, int D, int k);
+// tensor-core candidate scan (bf16x2 tcgen05) + exact re-scoring + certificate / exact fix-up: the exact path's scores and indices
+bool topk_tc_supported(int D, int k);
+size_t topk_tc_workspace_bytes(int B, int N, int D, int k);
+int launch_topk_ip_tc(const float* q, const float* db, const bf16* db_hi, const bf16* db_lo, float db_norm_max, int B, int N, int D, int k,
+                      float* scores, int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t st);
 int launch_topk_ip(const float* q, const float* db, int B, int N, int D, int k, float* scores, int64_t* idx, void* ws, size_t ws_bytes,
                    cudaStream_t st);
 int launch_select_caption_rows(const float* scores, const int64_t* idx, int B, int k_searched, const int64_t* cap_row_start,

@@ -8,6 +8,10 @@
 // sgemm_fp32.cu -- exact fp32 products so indices match the fp32 reference), then one block per query keeps a running
 // (score desc, index asc) top-k: per-thread sorted lists in registers, merged through shared memory.  The full [B, N]
 // score matrix is never materialised.
+#include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace gic {
@@ -22,6 +26,42 @@ size_t topk_workspace_bytes(int B, int N, int D, int k) {
 }
 
 __device__ __forceinline__ bool cand_better(float v, long i, float bv, long bi) { return v > bv || (v == bv && i < bi); }
+
+// the per-thread sorted lists of a block -> its k best (score desc, index asc) into scores / idx of row b
+template <int KMAX>
+__device__ __forceinline__ void topk_block_merge(const float (&lv)[KMAX], const long (&li)[KMAX], int k, float* cv, long* ci, float* rv, long* ri,
+                                                 int* rslot, float* __restrict__ scores, int64_t* __restrict__ idx, int b) {
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j)
+    if (j < k) { cv[threadIdx.x * k + j] = lv[j]; ci[threadIdx.x * k + j] = li[j]; }
+  __syncthreads();
+
+  const int ncand = blockDim.x * k;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int out = 0; out < k; ++out) {
+    float bv = -INFINITY; long bi = 0x7fffffffffffffffL; int bslot = -1;
+    for (int s = threadIdx.x; s < ncand; s += blockDim.x)
+      if (cand_better(cv[s], ci[s], bv, bi)) { bv = cv[s]; bi = ci[s]; bslot = s; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int os = __shfl_xor_sync(0xffffffffu, bslot, o);
+      if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bslot = os; }
+    }
+    if (lane == 0) { rv[warp] = bv; ri[warp] = bi; rslot[warp] = bslot; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < nw; ++w)
+        if (cand_better(rv[w], ri[w], bv, bi)) { bv = rv[w]; bi = ri[w]; bslot = rslot[w]; }
+      const bool valid = bslot >= 0 && bi != 0x7fffffffffffffffL;
+      scores[(size_t)b * k + out] = valid ? bv : -INFINITY;
+      idx[(size_t)b * k + out] = valid ? (int64_t)bi : -1;
+      if (bslot >= 0) { cv[bslot] = -INFINITY; ci[bslot] = 0x7fffffffffffffffL; }
+    }
+    __syncthreads();
+  }
+}
 
 template <int KMAX>
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ chunk_scores, int chunk_rows, long chunk_base, int k,
@@ -65,36 +105,7 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < KMAX; ++j)
-    if (j < k) { cv[threadIdx.x * k + j] = lv[j]; ci[threadIdx.x * k + j] = li[j]; }
-  __syncthreads();
-
-  const int ncand = blockDim.x * k;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int out = 0; out < k; ++out) {
-    float bv = -INFINITY; long bi = 0x7fffffffffffffffL; int bslot = -1;
-    for (int s = threadIdx.x; s < ncand; s += blockDim.x)
-      if (cand_better(cv[s], ci[s], bv, bi)) { bv = cv[s]; bi = ci[s]; bslot = s; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      const int os = __shfl_xor_sync(0xffffffffu, bslot, o);
-      if (cand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bslot = os; }
-    }
-    if (lane == 0) { rv[warp] = bv; ri[warp] = bi; rslot[warp] = bslot; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < nw; ++w)
-        if (cand_better(rv[w], ri[w], bv, bi)) { bv = rv[w]; bi = ri[w]; bslot = rslot[w]; }
-      const bool valid = bslot >= 0 && bi != 0x7fffffffffffffffL;
-      scores[(size_t)b * k + out] = valid ? bv : -INFINITY;
-      idx[(size_t)b * k + out] = valid ? (int64_t)bi : -1;
-      if (bslot >= 0) { cv[bslot] = -INFINITY; ci[bslot] = 0x7fffffffffffffffL; }
-    }
-    __syncthreads();
-  }
+  topk_block_merge<KMAX>(lv, li, k, cv, ci, rv, ri, rslot, scores, idx, b);
 }
 
 __global__ void topk_init_kernel(float* scores, int64_t* idx, size_t n) {
@@ -124,6 +135,282 @@ int launch_topk_ip(const float* q, const float* db, int B, int N, int D, int k, 
     GIC_CHECK_CUDA(cudaGetLastError());
   note_launch();
   }
+  return GIC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tensor-core top-k with the exact path's results.  The fp32 scan above runs at ~27 TFLOP/s on the CUDA cores (23 ms for
+// 1024 queries over the 591 753-row caption matrix, profiles/r1ak_configs.jsonl).  Here the scan is a bf16x2 tcgen05 GEMM
+// (operands split hi + lo, three MMAs per product: error <= ~2.3e-5 |q||d|), which only has to find CANDIDATES:
+//   1. per chunk: approximate scores -> every scan thread (256 per query) keeps its four best and the largest score it DROPPED;
+//      at the end the 32 best of the 1024 survivors become the candidates and U = the largest score dropped anywhere
+//      (the sorted-insertion merge above costs ~1 ms per 32 768-row chunk at k = 16 and more at 32: too slow for this path);
+//   2. every candidate is re-scored exactly: one thread per candidate, fp32 FMA chain over the dims in ascending order --
+//      the summation order of sgemm_nt_kernel, so scores AND ranks are bit-identical to the exact path;
+//   3. certificate: U bounds every non-candidate's approximate score, so its exact score is at most U + eps,
+//      eps = 6e-5 |q| max|d|.  If the k-th exact score is above that, no outsider can enter (or tie into) the top k.
+//      Otherwise the row is flagged and ONE block rescans the whole database for it exactly (no host round trip; with
+//      spacings of ~1e-3 between the leading scores of a 10^5..10^6-row database this practically never runs).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TOPK_TC_CAND = 32;
+constexpr int TOPK_TC_MAXK = 16;
+constexpr int TOPK_TC_THREADS = 256;  // scan threads per query ...
+constexpr int TOPK_TC_KEEP = 4;       // ... each keeps this many of its best approximate scores
+
+size_t topk_tc_workspace_bytes(int B, int N, int D, int k) {
+  (void)k;
+  const size_t chunk = (size_t)(N < TOPK_CHUNK ? N : TOPK_CHUNK);
+  return align_up((size_t)B * chunk * sizeof(float), 256) + 2 * align_up((size_t)B * D * sizeof(bf16), 256) +
+         align_up((size_t)B * TOPK_TC_CAND * sizeof(float), 256) + align_up((size_t)B * TOPK_TC_CAND * sizeof(int64_t), 256) +
+         align_up(((size_t)B + 1) * sizeof(int), 256) +  // flags [B] + the number of flagged queries
+         align_up((size_t)B * TOPK_TC_THREADS * TOPK_TC_KEEP * sizeof(float), 256) + align_up((size_t)B * TOPK_TC_THREADS * TOPK_TC_KEEP * sizeof(int), 256) +
+         align_up((size_t)B * TOPK_TC_THREADS * sizeof(float), 256) + align_up((size_t)B * sizeof(float), 256) + 256;  // scan state + bounds
+}
+
+// exact fp32 inner product in the summation order of the exact path (ascending k, one FMA chain from 0)
+__device__ __forceinline__ float dot_exact(const float* __restrict__ q_s, const float* __restrict__ row, int D) {
+  float acc = 0.f;
+  for (int k = 0; k < D; k += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(row + k);
+    acc = fmaf(q_s[k], v.x, acc);
+    acc = fmaf(q_s[k + 1], v.y, acc);
+    acc = fmaf(q_s[k + 2], v.z, acc);
+    acc = fmaf(q_s[k + 3], v.w, acc);
+  }
+  return acc;
+}
+
+// scan one chunk of approximate scores: thread t of query b looks at columns t, t + 256, ... and updates its TOPK_TC_KEEP best +
+// drop bound.  (A query is flagged when one thread's columns hold more than TOPK_TC_KEEP of the rows that matter: with 256 threads
+// and 4 kept that is ~C(k,5) / 256^4 < 1e-6 per query for k <= 16.)
+__global__ void __launch_bounds__(TOPK_TC_THREADS) topk_tc_scan_kernel(const float* __restrict__ chunk_scores, int chunk_rows, int chunk_base, int first,
+                                                                       float* __restrict__ st_v, int* __restrict__ st_i, float* __restrict__ st_u) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  const size_t so = ((size_t)b * TOPK_TC_THREADS + t) * TOPK_TC_KEEP;
+  float v[TOPK_TC_KEEP], u = -INFINITY;
+  int ix[TOPK_TC_KEEP];
+#pragma unroll
+  for (int j = 0; j < TOPK_TC_KEEP; ++j) { v[j] = -INFINITY; ix[j] = -1; }
+  if (!first) {
+#pragma unroll
+    for (int j = 0; j < TOPK_TC_KEEP; ++j) { v[j] = st_v[so + j]; ix[j] = st_i[so + j]; }
+    u = st_u[(size_t)b * TOPK_TC_THREADS + t];
+  }
+  const float* row = chunk_scores + (size_t)b * chunk_rows;
+  for (int c = t; c < chunk_rows; c += TOPK_TC_THREADS) {
+    const float x = row[c];
+    if (x > v[TOPK_TC_KEEP - 1]) {  // (columns arrive in ascending index order, so on equal scores the earlier index stays)
+      u = fmaxf(u, v[TOPK_TC_KEEP - 1]);
+      float pv = x; int pi = chunk_base + c;
+#pragma unroll
+      for (int j = 0; j < TOPK_TC_KEEP; ++j)
+        if (pv > v[j]) { const float tv = v[j]; const int ti = ix[j]; v[j] = pv; ix[j] = pi; pv = tv; pi = ti; }
+    } else {
+      u = fmaxf(u, x);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < TOPK_TC_KEEP; ++j) { st_v[so + j] = v[j]; st_i[so + j] = ix[j]; }
+  st_u[(size_t)b * TOPK_TC_THREADS + t] = u;
+}
+
+// the TOPK_TC_CAND best of a query's 256 x TOPK_TC_KEEP survivors -> candidate list; bound[b] = the largest approximate score that is
+// NOT a candidate
+__global__ void __launch_bounds__(TOPK_TC_THREADS) topk_tc_select_kernel(const float* __restrict__ st_v, const int* __restrict__ st_i,
+                                                                         const float* __restrict__ st_u, float* __restrict__ cand_score,
+                                                                         int64_t* __restrict__ cand_idx, float* __restrict__ bound) {
+  constexpr int KEEP = TOPK_TC_KEEP;
+  __shared__ float sv[KEEP * TOPK_TC_THREADS];
+  __shared__ int si[KEEP * TOPK_TC_THREADS];
+  __shared__ float rv[8];
+  __shared__ int rs[8];
+  const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const size_t so = ((size_t)b * TOPK_TC_THREADS + t) * KEEP;
+#pragma unroll
+  for (int j = 0; j < KEEP; ++j) { sv[KEEP * t + j] = st_v[so + j]; si[KEEP * t + j] = st_i[so + j]; }
+  float u = st_u[(size_t)b * TOPK_TC_THREADS + t];
+  __syncthreads();
+  for (int out = 0; out < TOPK_TC_CAND; ++out) {
+    // block argmax over the survivors still in the pool (ties: lower slot; any consistent rule will do for candidates)
+    float bv = sv[KEEP * t]; int bs = KEEP * t;
+#pragma unroll
+    for (int j = 1; j < KEEP; ++j)
+      if (sv[KEEP * t + j] > bv) { bv = sv[KEEP * t + j]; bs = KEEP * t + j; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+      if (ov > bv || (ov == bv && os < bs)) { bv = ov; bs = os; }
+    }
+    if (lane == 0) { rv[warp] = bv; rs[warp] = bs; }
+    __syncthreads();
+    if (t == 0) {
+      for (int w = 1; w < TOPK_TC_THREADS / 32; ++w)
+        if (rv[w] > bv || (rv[w] == bv && rs[w] < bs)) { bv = rv[w]; bs = rs[w]; }
+      const bool valid = si[bs] >= 0;
+      cand_score[(size_t)b * TOPK_TC_CAND + out] = valid ? bv : -INFINITY;
+      cand_idx[(size_t)b * TOPK_TC_CAND + out] = valid ? (int64_t)si[bs] : -1;
+      sv[bs] = -INFINITY; si[bs] = -1;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < KEEP; ++j) u = fmaxf(u, sv[KEEP * t + j]);  // survivors that did not make the list count as dropped
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
+  if (lane == 0) rv[warp] = u;
+  __syncthreads();
+  if (t == 0) {
+    for (int w = 1; w < TOPK_TC_THREADS / 32; ++w) u = fmaxf(u, rv[w]);
+    bound[b] = u;
+  }
+}
+
+// one block (TOPK_TC_CAND threads) per query: exact scores of its candidates, exact (score desc, index asc) top k, certificate
+__global__ void __launch_bounds__(TOPK_TC_CAND) topk_rescore_kernel(const float* __restrict__ q, const float* __restrict__ db, int D, int k,
+                                                                    const int64_t* __restrict__ cand_idx, const float* __restrict__ bound,
+                                                                    float db_norm_max, float* __restrict__ scores, int64_t* __restrict__ idx,
+                                                                    int* __restrict__ flags) {
+  extern __shared__ float q_s[];  // [D]
+  __shared__ float ev[TOPK_TC_CAND];
+  __shared__ long ei[TOPK_TC_CAND];
+  __shared__ float s_kth;
+  const int b = blockIdx.x, j = threadIdx.x;
+  float qq = 0.f;
+  for (int c = j; c < D; c += TOPK_TC_CAND) { const float v = q[(size_t)b * D + c]; q_s[c] = v; qq += v * v; }
+  qq = warp_sum(qq);  // the block is one warp
+  __syncwarp();
+  const int64_t gi = cand_idx[(size_t)b * TOPK_TC_CAND + j];
+  const float e = gi >= 0 ? dot_exact(q_s, db + (size_t)gi * D, D) : -INFINITY;
+  ev[j] = e;
+  ei[j] = gi >= 0 ? (long)gi : 0x7fffffffffffffffL;
+  if (j == 0) s_kth = -INFINITY;
+  __syncwarp();
+  int rank = 0;
+  for (int i = 0; i < TOPK_TC_CAND; ++i)  // (empty slots are all alike: ordered by slot)
+    rank += (cand_better(ev[i], ei[i], e, ei[j]) || (ev[i] == e && ei[i] == ei[j] && i < j)) ? 1 : 0;
+  if (rank < k) {
+    scores[(size_t)b * k + rank] = gi >= 0 ? e : -INFINITY;
+    idx[(size_t)b * k + rank] = gi;
+    if (rank == k - 1) s_kth = e;
+  }
+  __syncwarp();
+  if (j == 0) {
+    // bound[b] = the largest approximate score of any row outside the candidate list (-inf when the list holds every row)
+    const float u = bound[b];
+    const float eps = 6e-5f * sqrtf(qq) * db_norm_max;
+    flags[b] = (u > -INFINITY && !(s_kth > u + eps)) ? 1 : 0;
+  }
+}
+
+// flagged rows only: exact scan of the whole database by one block (the exact path's scores and tie rule)
+template <int KMAX>
+__global__ void __launch_bounds__(256) topk_exact_row_kernel(const float* __restrict__ q, const float* __restrict__ db, long N, int D, int k,
+                                                             const int* __restrict__ flags, float* __restrict__ scores, int64_t* __restrict__ idx) {
+  extern __shared__ unsigned char sm_raw[];
+  const int b = blockIdx.x;
+  if (!flags[b]) return;
+  if (threadIdx.x == 0) atomicAdd(const_cast<int*>(flags) + gridDim.x, 1);  // diagnostics: flags[B] counts the rescanned queries
+  float* q_s = reinterpret_cast<float*>(sm_raw);                                        // [D]
+  float* cv = q_s + D;                                                                   // [nthreads * k]
+  long* ci = reinterpret_cast<long*>(sm_raw + ((((size_t)D + (size_t)blockDim.x * k) * sizeof(float) + 7) & ~(size_t)7));  // [nthreads * k]
+  __shared__ float rv[8];
+  __shared__ long ri[8];
+  __shared__ int rslot[8];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) q_s[c] = q[(size_t)b * D + c];
+  __syncthreads();
+  float lv[KMAX];
+  long li[KMAX];
+#pragma unroll
+  for (int j = 0; j < KMAX; ++j) { lv[j] = -INFINITY; li[j] = 0x7fffffffffffffffL; }
+  for (long c = threadIdx.x; c < N; c += blockDim.x) {
+    const float v = dot_exact(q_s, db + (size_t)c * D, D);
+    float wv = -INFINITY; long wi = 0x7fffffffffffffffL;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j)
+      if (j == k - 1) { wv = lv[j]; wi = li[j]; }
+    if (cand_better(v, c, wv, wi)) {
+      float pv = v; long pi = c;
+#pragma unroll
+      for (int j = 0; j < KMAX; ++j) {
+        if (j < k && cand_better(pv, pi, lv[j], li[j])) {
+          const float tv = lv[j]; const long ti = li[j];
+          lv[j] = pv; li[j] = pi; pv = tv; pi = ti;
+        }
+      }
+    }
+  }
+  topk_block_merge<KMAX>(lv, li, k, cv, ci, rv, ri, rslot, scores, idx, b);
+}
+
+bool topk_tc_supported(int D, int k) { return D % 64 == 0 && D <= 2048 && k <= TOPK_TC_MAXK; }
+
+int launch_topk_ip_tc(const float* q, const float* db, const bf16* db_hi, const bf16* db_lo, float db_norm_max, int B, int N, int D, int k,
+                      float* scores, int64_t* idx, void* ws, size_t ws_bytes, cudaStream_t st) {
+  GIC_REQUIRE(B > 0 && N > 0 && D > 0 && k > 0, "topk_ip_tc: empty problem B=%d N=%d D=%d k=%d", B, N, D, k);
+  GIC_REQUIRE((long)N < 0x7fffffffL, "topk_ip_tc: N too large");
+  GIC_REQUIRE(topk_tc_supported(D, k), "topk_ip_tc: needs D %% 64 == 0, D <= 2048 and k <= %d (D=%d k=%d); use the exact path", TOPK_TC_MAXK, D, k);
+  GIC_REQUIRE(ws_bytes >= topk_tc_workspace_bytes(B, N, D, k), "topk_ip_tc: workspace too small");
+  GIC_TRY(tma_init());
+  GIC_TRY(gemm_bf16_configure());
+  const size_t chunk = (size_t)(N < TOPK_CHUNK ? N : TOPK_CHUNK);
+  unsigned char* w8 = reinterpret_cast<unsigned char*>(align_up((size_t)ws, 256));
+  float* chunk_scores = reinterpret_cast<float*>(w8); w8 += align_up((size_t)B * chunk * sizeof(float), 256);
+  bf16* q_hi = reinterpret_cast<bf16*>(w8); w8 += align_up((size_t)B * D * sizeof(bf16), 256);
+  bf16* q_lo = reinterpret_cast<bf16*>(w8); w8 += align_up((size_t)B * D * sizeof(bf16), 256);
+  float* cand_score = reinterpret_cast<float*>(w8); w8 += align_up((size_t)B * TOPK_TC_CAND * sizeof(float), 256);
+  int64_t* cand_idx = reinterpret_cast<int64_t*>(w8); w8 += align_up((size_t)B * TOPK_TC_CAND * sizeof(int64_t), 256);
+  int* flags = reinterpret_cast<int*>(w8); w8 += align_up(((size_t)B + 1) * sizeof(int), 256);
+  float* st_v = reinterpret_cast<float*>(w8); w8 += align_up((size_t)B * TOPK_TC_THREADS * TOPK_TC_KEEP * sizeof(float), 256);
+  int* st_i = reinterpret_cast<int*>(w8); w8 += align_up((size_t)B * TOPK_TC_THREADS * TOPK_TC_KEEP * sizeof(int), 256);
+  float* st_u = reinterpret_cast<float*>(w8); w8 += align_up((size_t)B * TOPK_TC_THREADS * sizeof(float), 256);
+  float* bound = reinterpret_cast<float*>(w8);
+
+  static const bool trace_host = getenv("GIC_TRACE_HOST") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+  const auto t0 = now();
+  ActOut qo; qo.hi = q_hi; qo.lo = q_lo;
+  GIC_TRY(launch_convert(q, qo, (size_t)B * D, st));
+  const auto t1 = now();
+  double t_enc = 0, t_gemm = 0, t_scan = 0;
+  GemmBf16Args g;
+  g.no_pdl = 1;  // plain stream order: these launches alternate with ordinary <<<>>> launches on the caller's stream (see kernels.cuh)
+  GIC_TRY(make_tma_2d_bf16(&g.a_hi, q_hi, B, D, D, 128));
+  GIC_TRY(make_tma_2d_bf16(&g.a_lo, q_lo, B, D, D, 128));
+  for (long base = 0; base < N; base += TOPK_CHUNK) {
+    const int rows = (int)((N - base) < TOPK_CHUNK ? (N - base) : TOPK_CHUNK);
+    const auto c0 = now();
+    GIC_TRY(make_tma_2d_bf16(&g.w_hi, db_hi + (size_t)base * D, rows, D, D, 64));
+    GIC_TRY(make_tma_2d_bf16(&g.w_lo, db_lo + (size_t)base * D, rows, D, D, 64));
+    const auto c1 = now();
+    g.M = B; g.N = rows; g.K = D; g.block_n = 64; g.split = 1; g.epilogue = EPI_NONE; g.bias = nullptr;
+    g.out = ActOut(); g.out.f32 = chunk_scores; g.ld_out = rows;
+    GIC_TRY(launch_gemm_bf16(g, st));
+    const auto c2 = now();
+    topk_tc_scan_kernel<<<B, TOPK_TC_THREADS, 0, st>>>(chunk_scores, rows, (int)base, base == 0 ? 1 : 0, st_v, st_i, st_u);
+    GIC_CHECK_CUDA(cudaGetLastError());
+    note_launch();
+    const auto c3 = now();
+    t_enc += us(c0, c1); t_gemm += us(c1, c2); t_scan += us(c2, c3);
+  }
+  const auto t2 = now();
+  topk_tc_select_kernel<<<B, TOPK_TC_THREADS, 0, st>>>(st_v, st_i, st_u, cand_score, cand_idx, bound);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  GIC_CHECK_CUDA(cudaMemsetAsync(flags + B, 0, sizeof(int), st));
+  topk_rescore_kernel<<<B, TOPK_TC_CAND, (size_t)D * sizeof(float), st>>>(q, db, D, k, cand_idx, bound, db_norm_max, scores, idx, flags);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  const int fthreads = k <= 8 ? 256 : 128;  // candidate lists + the query must fit 48 KB of shared memory
+  const size_t fsmem = align_up(((size_t)D + fthreads * (size_t)k) * sizeof(float), 8) + fthreads * (size_t)k * sizeof(long);
+  GIC_REQUIRE(fsmem <= 48 * 1024, "topk_ip_tc: fix-up kernel shared memory %zu", fsmem);
+  topk_exact_row_kernel<TOPK_TC_MAXK><<<B, fthreads, fsmem, st>>>(q, db, (long)N, D, k, flags, scores, idx);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  if (trace_host)
+    fprintf(stderr, "topk_ip_tc host us: convert %.0f | chunks %.0f (encode %.0f gemm-launch %.0f scan-launch %.0f) | tail %.0f\n", us(t0, t1), us(t1, t2), t_enc,
+            t_gemm, t_scan, us(t2, now()));
   return GIC_OK;
 }
 

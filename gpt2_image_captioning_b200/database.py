@@ -11,6 +11,8 @@ Search is EXACT (IndexFlatIP semantics, ties -> lowest index): a quality superse
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -20,10 +22,22 @@ from . import _capi, ops
 class _GpuFlatIndex:
     """faiss.IndexFlatIP-like view of one device matrix."""
 
-    def __init__(self, matrix: torch.Tensor):
+    def __init__(self, matrix: torch.Tensor, tensor_cores: bool | None = None):
         self.matrix = matrix
         self.ntotal, self.d = int(matrix.shape[0]), int(matrix.shape[1])
         self._ws: torch.Tensor | None = None
+        # tensor-core scan (bf16x2 tcgen05 candidates + exact re-scoring + certificate, include/gic_b200.h gic_topk_ip_tc): same
+        # scores and indices as the exact fp32 scan.  GIC_RETRIEVAL_EXACT=1 keeps the fp32 CUDA-core scan.
+        if tensor_cores is None:
+            tensor_cores = os.environ.get("GIC_RETRIEVAL_EXACT", "0") != "1"
+        self.hi = self.lo = None
+        self.norm_max = 0.0
+        if tensor_cores and self.ntotal > 0 and self.d % 64 == 0 and self.d <= 2048 and matrix.is_cuda:
+            self.hi = torch.empty(matrix.shape, dtype=torch.bfloat16, device=matrix.device)
+            self.lo = torch.empty(matrix.shape, dtype=torch.bfloat16, device=matrix.device)
+            with torch.cuda.device(matrix.device):
+                ops.pack_bf16x2(matrix, self.hi, self.lo)
+            self.norm_max = float(torch.linalg.vector_norm(matrix, dim=1).max().item())
 
     def search_device(self, q: torch.Tensor, k: int):
         q = q.to(device=self.matrix.device, dtype=torch.float32).contiguous()
@@ -34,12 +48,17 @@ class _GpuFlatIndex:
         idx = torch.empty(B, k, dtype=torch.int64, device=q.device)
         if B == 0:
             return scores, idx
-        need = int(_capi.lib().gic_topk_workspace_bytes(B, self.ntotal, self.d, k))
+        lib = _capi.lib()
+        tc = self.hi is not None and bool(lib.gic_topk_tc_supported(self.d, k))
+        need = int((lib.gic_topk_tc_workspace_bytes if tc else lib.gic_topk_workspace_bytes)(B, self.ntotal, self.d, k))
         if self._ws is None or self._ws.numel() < need:
             self._ws = None
             self._ws = torch.empty(need, dtype=torch.uint8, device=q.device)
         with torch.cuda.device(q.device):
-            ops.topk_ip(q, self.matrix, k, scores, idx, self._ws)
+            if tc:
+                ops.topk_ip_tc(q, self.matrix, self.hi, self.lo, self.norm_max, k, scores, idx, self._ws)
+            else:
+                ops.topk_ip(q, self.matrix, k, scores, idx, self._ws)
         return scores, idx
 
     def search(self, x, k: int):

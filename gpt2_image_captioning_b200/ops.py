@@ -64,6 +64,23 @@ def topk_ip(queries: torch.Tensor, db: torch.Tensor, k: int, scores_out: torch.T
                               _ptr(workspace), workspace.numel(), _stream()))
 
 
+@torch.library.custom_op("gic::pack_bf16x2", mutates_args=("hi", "lo"))
+def pack_bf16x2(src: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor) -> None:
+    """src fp32 -> hi = bf16(src), lo = bf16(src - hi) (same shape, bf16): the operands of the bf16x2 tensor-core mode."""
+    _need_cuda(src, hi, lo)
+    L = _capi.lib()
+    _capi.check(L.gic_pack_bf16x2(_ptr(src), hi.data_ptr(), lo.data_ptr(), src.numel(), _stream()))
+
+
+@torch.library.custom_op("gic::topk_ip_tc", mutates_args=("scores_out", "idx_out", "workspace"))
+def topk_ip_tc(queries: torch.Tensor, db: torch.Tensor, db_hi: torch.Tensor, db_lo: torch.Tensor, db_norm_max: float, k: int,
+               scores_out: torch.Tensor, idx_out: torch.Tensor, workspace: torch.Tensor) -> None:
+    _need_cuda(queries, db, db_hi, db_lo, scores_out, idx_out, workspace)
+    L = _capi.lib()
+    _capi.check(L.gic_topk_ip_tc(_ptr(queries), _ptr(db), db_hi.data_ptr(), db_lo.data_ptr(), float(db_norm_max), queries.shape[0], db.shape[0],
+                                 db.shape[1], k, _ptr(scores_out), _ptr(idx_out), _ptr(workspace), workspace.numel(), _stream()))
+
+
 @torch.library.custom_op("gic::select_caption_rows", mutates_args=("rows_out",))
 def select_caption_rows(scores: torch.Tensor, idx: torch.Tensor, cap_row_start: torch.Tensor, cap_row_ids: torch.Tensor | None,
                         top_i: int, top_k: int, rows_out: torch.Tensor) -> None:

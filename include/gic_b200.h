@@ -154,6 +154,16 @@ GIC_API int gic_kv_reorder(gic_engine* e, const void* kv_src, void* kv_dst, cons
 GIC_API size_t gic_topk_workspace_bytes(int batch, int n_rows, int dim, int k);
 GIC_API int gic_topk_ip(const float* queries, const float* db, int batch, int n_rows, int dim, int k,
                 float* scores_out, int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream);
+/* The same search with the scan on the tensor cores: a bf16x2 (hi + lo operands) tcgen05 GEMM finds 32 candidates per query, which are
+ * re-scored exactly in fp32 in the exact path's summation order; a per-query certificate (worst candidate's approximate score + error
+ * bound < k-th exact score) proves no other row can enter the top k, and an uncertified query is rescanned exactly on the device.
+ * Scores and indices are therefore those of gic_topk_ip.  Needs dim % 64 == 0 and k <= 16 (gic_topk_tc_supported); db_hi / db_lo =
+ * gic_pack_bf16x2(db) [n_rows, dim] bf16 each, db_norm_max = the largest row norm of db. */
+GIC_API int gic_topk_tc_supported(int dim, int k);
+GIC_API size_t gic_topk_tc_workspace_bytes(int batch, int n_rows, int dim, int k);
+GIC_API int gic_pack_bf16x2(const float* src, void* hi, void* lo, size_t n, void* stream);
+GIC_API int gic_topk_ip_tc(const float* queries, const float* db, const void* db_hi, const void* db_lo, float db_norm_max, int batch, int n_rows,
+                           int dim, int k, float* scores_out, int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* replaces the Python hit filter + caption-row selection (faiss_store.py:160-183,208-229) on integer ids:
  * image hits -> first top_i with idx != -1 and score <= 0.9999 -> their caption rows via a CSR table

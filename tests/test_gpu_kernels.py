@@ -285,6 +285,33 @@ def test_topk_ip_exact_indices(B, N, k):
         assert pos == sorted(pos)
 
 
+@pytest.mark.parametrize("B,N,D,k", [(7, 300, 64, 5), (33, 70000, 128, 15), (1024, 40000, 512, 16), (5, 20, 64, 16)])
+def test_topk_ip_tensor_core_path_equals_exact_path(B, N, D, k):
+    """bf16x2 tcgen05 candidate scan + exact re-scoring + certificate (gic_topk_ip_tc): scores and indices bit-identical to the
+    fp32 scan, with exact ties (duplicate rows), k > N padding, and rows whose certificate fails (forced by lying about the
+    database norm: eps becomes huge, so every query takes the exact fix-up scan)."""
+    from gpt2_image_captioning_b200.database import _GpuFlatIndex
+    rng = np.random.default_rng(B + N + D + k)
+    db = rng.standard_normal((N, D)).astype(np.float32)
+    db /= np.linalg.norm(db, axis=1, keepdims=True)
+    if N > 50:
+        db[N // 2] = db[3]
+        db[N - 1] = db[3]
+    q = rng.standard_normal((B, D)).astype(np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    q[0] = db[3]
+    dbt = torch.from_numpy(db).to(DEV)
+    exact = _GpuFlatIndex(dbt, tensor_cores=False)
+    tc = _GpuFlatIndex(dbt, tensor_cores=True)
+    assert tc.hi is not None and exact.hi is None
+    se, ie = exact.search(q, k)
+    st, it = tc.search(q, k)
+    assert np.array_equal(ie, it) and np.array_equal(se, st)
+    tc.norm_max = 1e6  # no certificate can hold: every row goes through the exact fix-up kernel
+    sf, i_f = tc.search(q, k)
+    assert np.array_equal(ie, i_f) and np.array_equal(se, sf)
+
+
 def test_topk_ip_integer_scores_bit_exact():
     """Integer-valued vectors make every inner product exact in fp32, so scores AND indices must be bit-identical."""
     from gpt2_image_captioning_b200.database import _GpuFlatIndex
