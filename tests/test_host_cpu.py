@@ -201,3 +201,71 @@ def test_sharded_generate_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "SHARDED_OK" in outs[0]
+
+
+class _FakeTok:
+    eos_token_id = 50256
+
+    def batch_decode(self, ids, skip_special_tokens=True):
+        return [" ".join(str(int(t)) for t in row if not (skip_special_tokens and int(t) == self.eos_token_id)) for row in ids]
+
+
+class _FakeCaptioner(torch.nn.Module):
+    """deterministic, row-independent stand-in for ImageCaptioningModel.generate (counts the rows it is asked to caption)"""
+
+    def __init__(self):
+        super().__init__()
+        self.tokenizer = _FakeTok()
+        self.rows = 0
+        self.batches = []
+
+    def generate(self, image_embeddings, max_length=50, temperature=1.0, top_p=0.9, **kw):
+        self.rows += image_embeddings.shape[0]
+        self.batches.append(image_embeddings.shape[0])
+        base = (image_embeddings[:, 0] * 1000).round().long()
+        return torch.stack([base + t for t in range(max_length)], dim=1)
+
+
+def test_dedupe_before_generate_matches_the_reference_loop(tmp_path):
+    """generate_predictions == the reference's generate_and_evaluate loop (src/eval.py:199-224: caption every item, keep the first
+    per image_id), with one generated row per distinct image instead of one per caption item."""
+    from gpt2_image_captioning_b200 import generate_predictions, load_embeddings_pt
+    g = torch.Generator().manual_seed(0)
+    n_img = 23
+    emb = torch.rand(n_img, 8, generator=g)
+    owner = torch.tensor([i for i in range(n_img) for _ in range(1 + i % 5)])  # 1..5 caption items per image, grouped like CocoDataset
+    items = [{"image_id": int(100 + o), "image_embedding": emb[o]} for o in owner]
+
+    class DS(torch.utils.data.Dataset):
+        tokenizer = _FakeTok()
+
+        def __len__(self):
+            return len(items)
+
+        def __getitem__(self, i):
+            return items[i]
+
+    # the reference loop, restated
+    ref_model, want, seen = _FakeCaptioner(), [], set()
+    for s in range(0, len(items), 7):
+        chunk = items[s:s + 7]
+        caps = ref_model.tokenizer.batch_decode(ref_model.generate(torch.stack([c["image_embedding"] for c in chunk]), max_length=6, temperature=0.0))
+        for c, cap in zip(chunk, caps):
+            if c["image_id"] not in seen:
+                seen.add(c["image_id"])
+                want.append({"image_id": c["image_id"], "caption": cap})
+    model = _FakeCaptioner()
+    got = generate_predictions(model, DS(), batch_size=7, max_length=6, temperature=0.0, device="cpu")
+    assert got == want
+    assert model.rows == n_img and ref_model.rows == len(items)
+    assert model.batches == [7, 7, 7, 2]  # full batches of distinct images, then the remainder
+    with pytest.raises(ValueError, match="deterministic"):
+        generate_predictions(model, DS(), temperature=1.0, device="cpu")
+    # the extractors' .pt format
+    path = tmp_path / "emb.pt"
+    torch.save({"filenames": [f"{i}.jpg" for i in range(n_img)], "embeddings": emb}, path)
+    names, e2 = load_embeddings_pt(str(path))
+    assert names[3] == "3.jpg" and torch.equal(e2, emb)
+    torch.save({"embeddings": emb}, path)
+    with pytest.raises(ValueError):
+        load_embeddings_pt(str(path))
