@@ -75,6 +75,7 @@ SIGNATURES = {
     "gic_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "gic_mapper_forward": (C.c_int, [C.c_void_p, _fp, C.c_int, _fp, _fp, C.c_size_t, C.c_void_p]),
     "gic_generate_greedy": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),
+    "gic_generate_sample": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_ulonglong, _fp, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),
     "gic_generate_beam": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),
     "gic_kv_reorder": (C.c_int, [C.c_void_p, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gic_topk_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -92,6 +93,7 @@ SIGNATURES = {
     "gic_test_layernorm": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_void_p]),
     "gic_test_attn_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gic_test_attn_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "gic_test_sample_top_p": (C.c_int, [_fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_ulonglong, C.c_int, _fp, C.c_void_p]),
     "gic_test_ln_mlp": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 

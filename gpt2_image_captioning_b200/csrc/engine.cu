@@ -119,6 +119,8 @@ struct gic_engine {
   static constexpr int MAX_SUB = 8;
   cudaStream_t sub_stream[MAX_SUB] = {};  // [0] unused (= stream)
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
+  // temperature / top-p sampling (gic_generate_sample): set for the duration of one call
+  struct SampleCfg { bool on = false; float temperature = 1.f, top_p = 1.f; unsigned long long seed = 0; float* logits = nullptr; } sample;
   int sub_batches = 1;  // GIC_SUBBATCH=n: decode as n row groups (whole 128-row GEMM tiles) on n streams, each kernel limited to 1/n of the SMs
   // per-kernel-class CUDA-event profiling (bench.py roofline leg); generate runs eagerly while enabled
   bool profiling = false;
@@ -447,6 +449,14 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
       ProfScope ps(e, "lm_head", st);
       GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st, w.part_val, w.part_idx, &n_parts, w.n_parts_max));
     }
+  }
+  if (e->sample.on) {
+    // sampling: the step's logits were tapped into e->sample.logits; the drawn token replaces the argmax partials
+    GIC_REQUIRE(logits_tap != nullptr, "sampling needs the logits tap");
+    ProfScope pss(e, "sample", st);
+    GIC_TRY(launch_sample_top_p(logits_tap, rows, e->V, e->sample.temperature, e->sample.top_p, e->sample.seed, w.d_step, -1, w.part_val, w.part_idx,
+                                w.n_parts_max, st));
+    n_parts = 1;
   }
   ProfScope psf(e, "finalize", st);
   FinalizeArgs fa;
@@ -821,8 +831,8 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   const int steps = max_new - 1;
   const bool graph_ok = e->use_graph && !e->profiling && logits_out == nullptr && steps >= 2;
   if (!graph_ok) {
-    for (int s = 1; s <= steps; ++s)
-      GIC_TRY(decode_step_all(e, w, logits_out ? logits_out + (size_t)s * B * e->V : nullptr, st));
+    for (int s = 1; s <= steps; ++s)  // (sampling reuses one [B, V] buffer; the parity tap keeps every step's logits)
+      GIC_TRY(decode_step_all(e, w, logits_out ? (e->sample.on ? logits_out : logits_out + (size_t)s * B * e->V) : nullptr, st));
   } else {
     if (!(e->graph_exec && e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new)) {
       if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
@@ -846,6 +856,19 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   GIC_CHECK_CUDA(cudaMemcpyAsync(ids_out, w.ids, (size_t)B * max_new * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   if (gen_len_out) GIC_TRY(launch_gen_len(w.first_eos, B, max_new, gen_len_out, st));
   return join_stream(e, user);
+}
+
+// the `temperature > 0` branch of ImageCaptioningModel.generate (src/models.py:400-449): the greedy driver with every step's
+// logits tapped into logits_scratch and the token drawn by sample_top_p_kernel (eager launches: the tap disables the graph)
+int gic_generate_sample(gic_engine* e, const float* x, int batch, int max_new, float temperature, float top_p, unsigned long long seed,
+                        int64_t* ids_out, int32_t* gen_len_out, float* logits_scratch, void* workspace, size_t workspace_bytes, void* stream) {
+  GIC_TRY(check_ready(e));
+  GIC_REQUIRE(logits_scratch != nullptr, "null argument");
+  GIC_REQUIRE(temperature > 0.f && top_p > 0.f, "sampling needs temperature > 0 and top_p > 0 (temperature %g, top_p %g)", temperature, top_p);
+  e->sample.on = true; e->sample.temperature = temperature; e->sample.top_p = top_p; e->sample.seed = seed; e->sample.logits = logits_scratch;
+  const int r = gic_generate_greedy(e, x, batch, max_new, ids_out, gen_len_out, logits_scratch, workspace, workspace_bytes, stream);
+  e->sample.on = false;
+  return r;
 }
 
 // ln_f -> LM head with the full fp32 logit rows materialised (beam search needs log-softmax + top-2K over beams x V)
@@ -1134,6 +1157,22 @@ int gic_test_attn_prefill(const void* qkv, void* kcache, void* vcache, void* out
   ActOut o; o.hi = (bf16*)out;
   GIC_TRY(launch_attn_prefill<bf16>((const bf16*)qkv, (bf16*)kcache, (bf16*)vcache, o, rows, S, H, t_max, 1, st));
   GIC_CHECK_CUDA(cudaStreamSynchronize(st));
+  return GIC_OK;
+}
+
+// one sampling launch on caller data: logits dev fp32 [B, V] -> tokens dev int32 [B] (kernel-level hook for src/models.py:400-449)
+int gic_test_sample_top_p(const float* logits, int B, int V, float temperature, float top_p, unsigned long long seed, int step, int32_t* tokens_out,
+                          void* stream) {
+  GIC_REQUIRE(logits && tokens_out && B > 0 && V > 0 && step >= 0, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  GIC_TRY(gic_device_check());
+  float* pv = nullptr;
+  GIC_CHECK_CUDA(cudaMalloc((void**)&pv, (size_t)B * sizeof(float)));
+  int r = launch_sample_top_p(logits, B, V, temperature, top_p, seed, nullptr, step, pv, tokens_out, 1, st);
+  cudaError_t ce = cudaStreamSynchronize(st);
+  cudaFree(pv);
+  if (r != GIC_OK) return r;
+  GIC_CHECK_CUDA(ce);
   return GIC_OK;
 }
 

@@ -119,6 +119,10 @@ struct FinalizeArgs {
   float2* stats_next;       // ... and [B] (sum, sum of squares) of that copy
 };
 int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st);
+// temperature / top-p sampling of one token per row from fp32 logits [B, V] (src/models.py:400-449); the token goes to slot 0 of the
+// row's (value, index) partials.  step: *d_step unless step_override >= 0 (the Philox counter is (row, step)).
+int launch_sample_top_p(const float* logits, int B, int V, float temperature, float top_p, unsigned long long seed, const int* d_step,
+                        int step_override, float* part_val, int* part_idx, int part_ld, cudaStream_t st);
 int launch_init_decode_state(unsigned char* finished, int* first_eos, int B, int max_new, int* d_step, int* d_pos, int* done_counter,
                              int P, cudaStream_t st);
 int launch_gen_len(const int* first_eos, int B, int max_new, int* gen_len_out, cudaStream_t st);

@@ -66,6 +66,148 @@ int launch_argmax_partials(const float* logits, int B, int V, float* part_val, i
   return GIC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Temperature / nucleus (top-p) sampling: the `temperature > 0` branch of ImageCaptioningModel.generate
+// (src/models.py:400-449).  One block per row keeps the row's V unnormalised probabilities exp((z_i - max) / T) in shared
+// memory (50 257 x 4 B = 196 KB).  The reference sorts the row, takes the cumulative softmax and keeps every token up to and
+// including the first whose cumulative probability exceeds top_p (:413-432); the same set is {p_i >= tau} for
+// tau = the largest probability value whose tail mass sum_{p_i >= tau} p_i / S still exceeds top_p, found by bisection over the
+// float bit patterns (31 block-wide sums from shared memory, no sort).  The token is then drawn from the kept mass in index
+// order with one Philox4x32-10 uniform per (seed, row, step).  Parity with torch.multinomial is distributional only.
+// The token is handed to finalize_token_kernel as a single (value, index) "partial", so the EOS rules are shared with greedy.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
+  const unsigned long long p = (unsigned long long)a * b;
+  *hi = (uint32_t)(p >> 32);
+  return (uint32_t)p;
+}
+__device__ __forceinline__ float philox_uniform(unsigned long long seed, uint32_t c0, uint32_t c1) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t x0 = c0, x1 = c1, x2 = 0u, x3 = 0u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t h0, h1;
+    const uint32_t l0 = mulhilo32(0xD2511F53u, x0, &h0), l1 = mulhilo32(0xCD9E8D57u, x2, &h1);
+    const uint32_t y0 = h1 ^ x1 ^ k0, y1 = l1, y2 = h0 ^ x3 ^ k1, y3 = l0;
+    x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return (float)(x0 >> 8) * (1.0f / 16777216.0f);  // [0, 1)
+}
+
+constexpr int SAMPLE_THREADS = 512;
+
+__device__ __forceinline__ float sample_block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();  // `red` may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < SAMPLE_THREADS / 32; ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS) sample_top_p_kernel(const float* __restrict__ logits, int V, float inv_temperature, float top_p,
+                                                                      unsigned long long seed, const int* __restrict__ d_step, int step_override,
+                                                                      float* __restrict__ part_val, int* __restrict__ part_idx, int part_ld) {
+  extern __shared__ float prob[];  // [V]
+  __shared__ float red[SAMPLE_THREADS / 32];
+  __shared__ float s_scan[SAMPLE_THREADS];
+  __shared__ int s_tok;
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float* z = logits + (size_t)b * V;
+  float m = -INFINITY;
+  for (int i = t; i < V; i += SAMPLE_THREADS) m = fmaxf(m, z[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((t & 31) == 0) red[t >> 5] = m;
+  __syncthreads();
+  for (int w = 0; w < SAMPLE_THREADS / 32; ++w) m = fmaxf(m, red[w]);
+  float s = 0.f;
+  for (int i = t; i < V; i += SAMPLE_THREADS) {
+    const float p = expf((z[i] - m) * inv_temperature);  // softmax(z / T) up to the common factor
+    prob[i] = p;
+    s += p;
+  }
+  const float S = sample_block_sum(s, red);
+  // tau: bit pattern of the smallest kept probability.  Invariant: tail(lo) > top_p * S >= tail(hi)   (tail(t) = sum of p >= t)
+  uint32_t lo = 0u, hi = __float_as_uint(1.0f) + 1u;
+  if (top_p < 1.0f) {
+    const float want = top_p * S;
+    while (hi - lo > 1u) {
+      const uint32_t mid = lo + ((hi - lo) >> 1);
+      float a = 0.f;
+      for (int i = t; i < V; i += SAMPLE_THREADS) {
+        const float p = prob[i];
+        a += (__float_as_uint(p) >= mid) ? p : 0.f;
+      }
+      const float tail = sample_block_sum(a, red);
+      if (tail > want) lo = mid; else hi = mid;  // (block-uniform: every thread holds the same sum)
+    }
+  }
+  // draw from the kept mass in index order: thread t owns the contiguous slice [t * seg, (t + 1) * seg)
+  const int seg = (V + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
+  const int i0 = t * seg, i1 = min(V, i0 + seg);
+  float part = 0.f;
+  for (int i = i0; i < i1; ++i) {
+    const float p = prob[i];
+    part += (__float_as_uint(p) >= lo) ? p : 0.f;
+  }
+  s_scan[t] = part;
+  if (t == 0) s_tok = -1;
+  __syncthreads();
+  if (t == 0) {  // serial inclusive scan of 512 partials
+    float run = 0.f;
+    for (int j = 0; j < SAMPLE_THREADS; ++j) { run += s_scan[j]; s_scan[j] = run; }
+  }
+  __syncthreads();
+  const float total = s_scan[SAMPLE_THREADS - 1];
+  const int step = step_override >= 0 ? step_override : __ldcg(d_step);
+  const float target = philox_uniform(seed, (uint32_t)b, (uint32_t)step) * total;
+  const float before = t == 0 ? 0.f : s_scan[t - 1];
+  if (part > 0.f && target >= before && target < s_scan[t]) {
+    float run = before;
+    int tok = -1;
+    for (int i = i0; i < i1; ++i) {
+      const float p = prob[i];
+      if (__float_as_uint(p) >= lo) {
+        tok = i;  // the last kept token of the slice catches rounding at its upper edge
+        run += p;
+        if (target < run) break;
+      }
+    }
+    s_tok = tok;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int tok = s_tok;
+    if (tok < 0) {  // target landed on / beyond the total through rounding: the last kept token of the row
+      for (int i = V - 1; i >= 0; --i)
+        if (__float_as_uint(prob[i]) >= lo) { tok = i; break; }
+    }
+    part_val[(size_t)b * part_ld] = 1.0f;
+    part_idx[(size_t)b * part_ld] = tok;
+  }
+}
+
+int launch_sample_top_p(const float* logits, int B, int V, float temperature, float top_p, unsigned long long seed, const int* d_step,
+                        int step_override, float* part_val, int* part_idx, int part_ld, cudaStream_t st) {
+  GIC_REQUIRE(temperature > 0.f, "sample_top_p: temperature must be > 0 (0 is the greedy path)");
+  GIC_REQUIRE(top_p > 0.f, "sample_top_p: top_p must be > 0");
+  const size_t smem = (size_t)V * sizeof(float);
+  GIC_REQUIRE(smem <= 200 * 1024, "sample_top_p: a row of %d probabilities does not fit in shared memory", V);
+  static bool configured = false;
+  if (!configured) {
+    GIC_CHECK_CUDA(cudaFuncSetAttribute(sample_top_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  sample_top_p_kernel<<<B, SAMPLE_THREADS, smem, st>>>(logits, V, 1.0f / temperature, top_p, seed, d_step, step_override, part_val, part_idx, part_ld);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return GIC_OK;
+}
+
 // One block per row: reduce the partial maxima, apply the EOS rules, record the token and build the next input.
 __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
   __shared__ float sv[4];

@@ -177,6 +177,21 @@ class CaptionEngine:
             ops.generate_greedy(self.handle, x, max_new_tokens, ids, gen_len, logits, self.workspace(B, max_new_tokens))
         return (ids, gen_len, logits) if return_logits else (ids, gen_len)
 
+    def generate_sample(self, x: torch.Tensor, max_new_tokens: int, temperature: float = 1.0, top_p: float = 0.9, seed: int | None = None):
+        """Temperature / nucleus sampling (src/models.py:400-449): ids int64 [B, max_new_tokens], gen_len int32 [1].  `seed` keys the
+        device Philox stream; by default it is drawn from torch's global CPU generator, so torch.manual_seed makes runs repeatable."""
+        x = self._check_x(x)
+        B = x.shape[0]
+        ids = torch.empty(B, max_new_tokens, dtype=torch.int64, device=self.device)
+        gen_len = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if B > 0 and max_new_tokens > 0:
+            scratch = torch.empty(B, self.vocab, dtype=torch.float32, device=self.device)
+            ops.generate_sample(self.handle, x, max_new_tokens, float(temperature), float(top_p), int(seed), ids, gen_len, scratch,
+                                self.workspace(B, max_new_tokens))
+        return ids, gen_len
+
     def generate_beam(self, x: torch.Tensor, max_new_tokens: int, num_beams: int = 5, length_penalty: float = 1.0):
         """ids int64 [B, max_new_tokens] (eos padded), scores fp32 [B], gen_len int32 [1] = longest selected hypothesis."""
         x = self._check_x(x)

@@ -94,10 +94,8 @@ class _EngineMixin:
         self.eval()  # src/models.py:351
         device = image_embeddings.device
         batch = image_embeddings.shape[0]
-        if temperature != 0:
-            raise NotImplementedError(
-                "temperature > 0 / top-p sampling (src/models.py:407-449) is not on the B200 path yet; use temperature=0.0 "
-                "(the reference's validation default, config.yml:42)")
+        if temperature < 0:
+            raise ValueError(f"temperature must be >= 0, got {temperature}")
         if max_length <= 0 or batch == 0:
             # max_length == 0 -> [B, 0] (src/models.py:471-473); an empty batch stops at once (`is_finished.all()` of an
             # empty tensor is True, :390) -> [0, 0]
@@ -105,10 +103,16 @@ class _EngineMixin:
         eng = self._get_engine()
         beams = int(getattr(self, "num_beams", 1) or 1)
         with torch.cuda.device(eng.device):
+            if beams > 1 and temperature > 0:
+                raise NotImplementedError("beam search is deterministic: use temperature=0.0 with num_beams > 1")
             if beams > 1:
                 ids, _, gen_len = eng.generate_beam(image_embeddings, max_length, beams, float(getattr(self, "length_penalty", 1.0)))
                 return ids[:, : int(gen_len.item())].to(device)  # HF crops to the longest selected hypothesis
-            ids, gen_len = eng.generate_greedy(image_embeddings, max_length)
+            if temperature > 0:
+                # temperature / top-p sampling (src/models.py:400-449); top_p >= 1 samples the full softmax (:407)
+                ids, gen_len = eng.generate_sample(image_embeddings, max_length, float(temperature), float(top_p))
+            else:
+                ids, gen_len = eng.generate_greedy(image_embeddings, max_length)
             # one D2H read at the end of the loop (the reference syncs every step, src/models.py:390)
             n = int(gen_len.item())
         return ids[:, :n].to(device)

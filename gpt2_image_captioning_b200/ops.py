@@ -38,6 +38,24 @@ def generate_greedy(engine: int, image_embeddings: torch.Tensor, max_new_tokens:
                                       _ptr(gen_len_out), _ptr(logits_out), _ptr(workspace), workspace.numel(), _stream()))
 
 
+@torch.library.custom_op("gic::generate_sample", mutates_args=("ids_out", "gen_len_out", "logits_scratch", "workspace"))
+def generate_sample(engine: int, image_embeddings: torch.Tensor, max_new_tokens: int, temperature: float, top_p: float, seed: int,
+                    ids_out: torch.Tensor, gen_len_out: torch.Tensor, logits_scratch: torch.Tensor, workspace: torch.Tensor) -> None:
+    _need_cuda(image_embeddings, ids_out, gen_len_out, logits_scratch, workspace)
+    L = _capi.lib()
+    _capi.check(L.gic_generate_sample(engine, _ptr(image_embeddings), image_embeddings.shape[0], max_new_tokens, float(temperature), float(top_p),
+                                      int(seed), _ptr(ids_out), _ptr(gen_len_out), _ptr(logits_scratch), _ptr(workspace), workspace.numel(),
+                                      _stream()))
+
+
+@torch.library.custom_op("gic::test_sample_top_p", mutates_args=("tokens_out",))
+def test_sample_top_p(logits: torch.Tensor, temperature: float, top_p: float, seed: int, step: int, tokens_out: torch.Tensor) -> None:
+    _need_cuda(logits, tokens_out)
+    L = _capi.lib()
+    _capi.check(L.gic_test_sample_top_p(_ptr(logits), logits.shape[0], logits.shape[1], float(temperature), float(top_p), int(seed), int(step),
+                                        _ptr(tokens_out), _stream()))
+
+
 @torch.library.custom_op("gic::generate_beam", mutates_args=("ids_out", "scores_out", "gen_len_out", "workspace"))
 def generate_beam(engine: int, image_embeddings: torch.Tensor, max_new_tokens: int, num_beams: int, length_penalty: float,
                   ids_out: torch.Tensor, scores_out: torch.Tensor, gen_len_out: torch.Tensor, workspace: torch.Tensor) -> None:

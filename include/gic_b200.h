@@ -133,6 +133,14 @@ GIC_API int gic_generate_greedy(gic_engine* e, const float* image_embeddings /* 
                         int64_t* ids_out, int32_t* gen_len_out, float* logits_out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* replaces the sampling branch of ImageCaptioningModel.generate (src/models.py:400-449, temperature > 0): logits / temperature,
+ * nucleus filter (keep the sorted tokens up to and including the first whose cumulative probability exceeds top_p; top_p >= 1 keeps
+ * all), one multinomial draw per row and step from a Philox4x32-10 stream keyed by (seed, row, step).  Same outputs and EOS rules as
+ * gic_generate_greedy; logits_scratch: dev fp32 [B, V].  Parity with torch.multinomial is distributional. */
+GIC_API int gic_generate_sample(gic_engine* e, const float* image_embeddings /* dev [B,E] */, int batch, int max_new_tokens, float temperature,
+                                float top_p, unsigned long long seed, int64_t* ids_out, int32_t* gen_len_out, float* logits_scratch,
+                                void* workspace, size_t workspace_bytes, void* stream);
+
 /* Beam search (not in the reference; semantics of HF GenerationMixin._beam_search, generation/utils.py:3076-3385,
  * do_sample=False, early_stopping=False, length_penalty given, num_return_sequences=1, eos = pad): ids_out dev int64
  * [B, max_new_tokens] = best finished hypothesis per image padded with eos; scores_out dev fp32 [B] (may be NULL) its
@@ -202,6 +210,9 @@ GIC_API int gic_test_attn_decode(const void* qkv, void* kcache, void* vcache, vo
 /* one causal prefill-attention launch on caller data: qkv [rows*S, 3*H*64] bf16 -> out [rows*S, H*64] bf16; K / V land in the caches
  * [rows][H][t_max][64] at positions 0..S-1 (HF:models/gpt2/modeling_gpt2.py:185-220, HF:cache_utils.py:102-121) */
 GIC_API int gic_test_attn_prefill(const void* qkv, void* kcache, void* vcache, void* out, int rows, int S, int H, int t_max, void* stream);
+/* one sampling launch on caller data: logits dev fp32 [B, V] -> tokens dev int32 [B] (src/models.py:400-449) */
+GIC_API int gic_test_sample_top_p(const float* logits, int B, int V, float temperature, float top_p, unsigned long long seed, int step,
+                                  int32_t* tokens_out, void* stream);
 GIC_API int gic_test_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int d, void* stream);
 
 #ifdef __cplusplus

@@ -247,8 +247,8 @@ def test_generate_api_contract():
     assert out_cpu.device.type == "cpu" and torch.equal(out_cpu, out.cpu())
     assert model.generate(image_embeddings=x[:4].to(DEV), max_length=0, temperature=0.0).shape == (4, 0)
     assert model.generate(image_embeddings=x[:0].to(DEV), max_length=5, temperature=0.0).shape == (0, 0)
-    with pytest.raises(NotImplementedError):
-        model.generate(image_embeddings=x[:4].to(DEV), max_length=5, temperature=1.0)
+    with pytest.raises(ValueError):
+        model.generate(image_embeddings=x[:4].to(DEV), max_length=5, temperature=-1.0)
     with pytest.raises(ValueError):
         model.generate(image_embeddings=torch.zeros(4, 63, device=DEV), max_length=5, temperature=0.0)
     assert not model.training  # generate() puts the module in eval mode (src/models.py:351)
@@ -279,3 +279,35 @@ def test_full_size_bf16_properties():
     _report(test="full_size_bf16_split_invariance", rows=int(rows_same.numel()), rows_identical=int(rows_same.sum()))
     assert bool(rows_same.all())
     assert int(a.min()) >= 0 and int(a.max()) < 50257
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_sampling_path_behaviour(dtype):
+    """generate() with the reference's DEFAULT arguments (temperature 1.0, top_p 0.9, src/models.py:331-332) runs on the device:
+    repeatable under torch.manual_seed, different across seeds, EOS rows stay EOS (:453-460), the trim rule holds, and a tiny
+    temperature with a tight nucleus reproduces the greedy tokens."""
+    g = gu.load("tiny_mlp_eos")
+    model, _, x = gpu_util.product_model(g, dtype)
+    xx = x[:24].to(DEV)
+    eos = int(g.get("eos", oc.EOS_TOKEN_ID))
+    torch.manual_seed(7)
+    a = model.generate(image_embeddings=xx)  # defaults: max_length 50, temperature 1.0, top_p 0.9
+    torch.manual_seed(7)
+    b = model.generate(image_embeddings=xx)
+    torch.manual_seed(8)
+    c = model.generate(image_embeddings=xx)
+    assert a.dtype == torch.int64 and a.shape[0] == 24 and 1 <= a.shape[1] <= 50
+    assert torch.equal(a, b)
+    assert a.shape != c.shape or not torch.equal(a, c)
+    vocab = model.gpt.config.vocab_size
+    assert int(a.min()) >= 0 and int(a.max()) < vocab
+    for row in a.cpu().tolist():
+        if eos in row:
+            first = row.index(eos)
+            assert all(t == eos for t in row[first:])
+    if a.shape[1] < 50:  # stopped early: every row finished, and the last column holds some row's FIRST eos
+        ac = a.cpu()
+        assert bool((ac == eos).any(dim=1).all()) and bool(((ac == eos).sum(dim=1) == 1).any())
+    greedy = model.generate(image_embeddings=xx, max_length=12, temperature=0.0)
+    cold = model.generate(image_embeddings=xx, max_length=12, temperature=1e-3, top_p=0.5)
+    assert torch.equal(greedy, cold)

@@ -239,6 +239,47 @@ def test_attn_prefill_kernel(rows, H, S, t_max):
     assert same(kd.cpu(), kc) and same(vd.cpu(), vc)
 
 
+@pytest.mark.parametrize("temperature,top_p", [(1.0, 0.9), (0.7, 0.5), (1.5, 1.0), (1.0, 0.05)])
+def test_sample_top_p_kernel_distribution(temperature, top_p):
+    """40 000 draws from one logit row: every token lies in the reference's nucleus (its own torch expression, src/models.py:413-432)
+    and the empirical distribution matches the renormalised softmax (total variation); a second row with a different nucleus
+    is sampled in the same launch."""
+    ops, _ = _ops()
+    V, n = 3000, 40000
+    g = torch.Generator(device="cpu").manual_seed(int(temperature * 100 + top_p * 1000))
+    rows = torch.stack((torch.randn(V, generator=g) * 2.0, torch.randn(V, generator=g) * 4.0))
+    which = torch.arange(n) % 2
+    logits = rows[which].to(DEV).contiguous()
+    tok = torch.empty(n, dtype=torch.int32, device=DEV)
+    ops.test_sample_top_p(logits, temperature, top_p, 1234, 3, tok)
+    torch.cuda.synchronize()
+    tok2 = torch.empty_like(tok)
+    ops.test_sample_top_p(logits, temperature, top_p, 1234, 3, tok2)  # same (seed, row, step) -> same draws
+    ops.test_sample_top_p(logits, temperature, top_p, 1234, 4, tok)  # (keep tok2 as the reference draw; another step differs)
+    torch.cuda.synchronize()
+    assert not torch.equal(tok, tok2)
+    ops.test_sample_top_p(logits, temperature, top_p, 1234, 3, tok)
+    torch.cuda.synchronize()
+    assert torch.equal(tok, tok2)
+    tok = tok.cpu().long()
+    for r in range(2):
+        z = rows[r:r + 1] / temperature
+        if top_p < 1.0:  # the reference's nucleus mask
+            sl, si = torch.sort(z, descending=True)
+            cp = torch.cumsum(torch.softmax(sl, dim=-1), dim=-1)
+            rem = cp > top_p
+            rem[:, 1:] = rem[:, :-1].clone()
+            rem[:, 0] = False
+            z = z.masked_fill(rem.scatter(1, si, rem), float("-inf"))
+        want = torch.softmax(z, dim=-1)[0].double()
+        draws = tok[which == r]
+        assert bool((want[draws] > 0).all()), "a token outside the nucleus was drawn"
+        emp = torch.bincount(draws, minlength=V).double() / draws.numel()
+        tv = 0.5 * (emp - want).abs().sum().item()
+        kept = int((want > 0).sum())
+        assert tv < 0.02 + 0.6 * (kept / draws.numel()) ** 0.5, (r, tv, kept)
+
+
 @pytest.mark.parametrize("rows,d", [(1, 768), (1000, 768), (33, 1024), (7, 1280), (5, 128)])
 def test_layernorm(rows, d):
     ops, _ = _ops()
