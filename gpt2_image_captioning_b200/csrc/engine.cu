@@ -109,7 +109,7 @@ struct gic_engine {
   cudaGraphExec_t graph_exec = nullptr;
   void* graph_ws = nullptr; int graph_B = 0, graph_max_new = 0;
   bool use_graph = true;
-  int graph_nodes = 0;
+  int graph_nodes = 0, graph_steps = 1;  // kernel nodes / decode steps held by graph_exec
   // all generate work runs on this private stream (the caller's stream may be the legacy default stream, which cannot
   // be captured into a graph); it is forked from / joined to the caller's stream with events
   cudaStream_t stream = nullptr;
@@ -838,8 +838,13 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
       if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
       cudaGraph_t graph = nullptr;
       const unsigned long long before = g_launches;
+      // all max_new - 1 steps in ONE graph (GIC_GRAPH_PER_STEP=1: one step per graph, replayed): no launch gap and an unbroken
+      // programmatic-dependent-launch chain between the finalize of step s and the first GEMM of step s + 1
+      static const bool per_step = [] { const char* v = getenv("GIC_GRAPH_PER_STEP"); return v && v[0] == '1'; }();
+      e->graph_steps = per_step ? 1 : steps;
       GIC_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      int r = decode_step_all(e, w, nullptr, st);
+      int r = GIC_OK;
+      for (int s = 0; s < e->graph_steps && r == GIC_OK; ++s) r = decode_step_all(e, w, nullptr, st);
       cudaError_t ce = cudaStreamEndCapture(st, &graph);
       e->graph_nodes = (int)(g_launches - before);  // captured, not executed
       g_launches = before;
@@ -850,8 +855,8 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
       GIC_CHECK_CUDA(ce);
       e->graph_ws = workspace; e->graph_B = B; e->graph_max_new = max_new;
     }
-    for (int s = 1; s <= steps; ++s) GIC_CHECK_CUDA(cudaGraphLaunch(e->graph_exec, st));
-    g_launches += (unsigned long long)e->graph_nodes * steps;
+    for (int s = 0; s < steps; s += e->graph_steps) GIC_CHECK_CUDA(cudaGraphLaunch(e->graph_exec, st));
+    g_launches += (unsigned long long)e->graph_nodes * (steps / e->graph_steps);
   }
   GIC_CHECK_CUDA(cudaMemcpyAsync(ids_out, w.ids, (size_t)B * max_new * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   if (gen_len_out) GIC_TRY(launch_gen_len(w.first_eos, B, max_new, gen_len_out, st));
