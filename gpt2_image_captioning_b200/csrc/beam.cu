@@ -14,82 +14,67 @@ namespace gic {
 
 __device__ __forceinline__ bool bcand_better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
 
-// logits: [B * rows_per_image, V] fp32 (rows_per_image = beams; = 1 at step 0 where only beam 0 is live)
-template <int KMAX>
-__global__ void __launch_bounds__(256) beam_topk_kernel(const float* __restrict__ logits, int rows_per_image, int n_live,
-                                                        const float* __restrict__ run_score, int beams, int V, int K,
-                                                        float* __restrict__ cand_score, int* __restrict__ cand_idx) {
-  extern __shared__ unsigned char sm_raw[];
-  float* cv = reinterpret_cast<float*>(sm_raw);                                  // [256 * K]
-  int* ci = reinterpret_cast<int*>(sm_raw + (size_t)blockDim.x * K * sizeof(float));  // [256 * K]
-  __shared__ float red_m[8], red_s[8], lse[16];
-  __shared__ float rv[8];
-  __shared__ int ri[8], rslot[8];
-  const int b = blockIdx.x;
+// logits: [B * rows_per_image, V] fp32 (rows_per_image = beams; = 1 at step 0 where only beam 0 is live).
+// Three launches, one block per LIVE ROW for the two passes over the logits (the first version ran one block per image with a
+// single dependent load in flight per thread: 4.5 ms per step for B = 1024 x 5 beams, 20x the time the 2 GB of reads need):
+//   beam_lse_kernel      log-sum-exp of a row (eight independent loads in flight per thread)
+//   beam_rowtopk_kernel  the row's K best continuations by (logit - lse) + running score, ties -> lowest flat index j V + c
+//   beam_merge_kernel    per image: the K best of its n_live x K row candidates (an image's top K is inside its rows' top Ks)
+constexpr int BEAM_UNROLL = 8;
+
+__global__ void __launch_bounds__(256) beam_lse_kernel(const float* __restrict__ logits, int rows_per_image, int n_live, int V,
+                                                       float* __restrict__ lse /* [B * rows_per_image] */) {
+  __shared__ float red_m[8], red_s[8];
+  const int b = blockIdx.x / n_live, j = blockIdx.x % n_live;
+  const float* row = logits + ((size_t)b * rows_per_image + j) * V;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-
-  // ---- log-sum-exp of each live row (online max / sum) ----
-  for (int j = 0; j < n_live; ++j) {
-    const float* row = logits + ((size_t)b * rows_per_image + j) * V;
-    float m = -INFINITY, s = 0.f;
-    for (int c = threadIdx.x; c < V; c += blockDim.x) {
-      const float x = row[c];
-      if (x > m) { s = s * expf(m - x) + 1.f; m = x; }
-      else s += expf(x - m);
-    }
+  float m = -INFINITY, s = 0.f;
+  for (int c0 = threadIdx.x; c0 < V; c0 += blockDim.x * BEAM_UNROLL) {
+    float x[BEAM_UNROLL];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
-      const float nm = fmaxf(m, om);
-      s = (m == -INFINITY ? 0.f : s * expf(m - nm)) + (om == -INFINITY ? 0.f : os * expf(om - nm));
-      m = nm;
+    for (int u = 0; u < BEAM_UNROLL; ++u) {
+      const int c = c0 + u * blockDim.x;
+      x[u] = c < V ? row[c] : -INFINITY;
     }
-    if (lane == 0) { red_m[warp] = m; red_s[warp] = s; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float M = red_m[0], S = red_s[0];
-      for (int w = 1; w < nw; ++w) {
-        const float nm = fmaxf(M, red_m[w]);
-        S = S * expf(M - nm) + red_s[w] * expf(red_m[w] - nm);
-        M = nm;
-      }
-      lse[j] = M + logf(S);
-    }
-    __syncthreads();
-  }
-
-  // ---- per-thread sorted top-K of (logit - lse + running score) over the live rows ----
-  float lv[KMAX];
-  int li[KMAX];
+    float bm = x[0];
 #pragma unroll
-  for (int j = 0; j < KMAX; ++j) { lv[j] = -INFINITY; li[j] = 0x7fffffff; }
-  for (int j = 0; j < n_live; ++j) {
-    const float* row = logits + ((size_t)b * rows_per_image + j) * V;
-    const float base = run_score[(size_t)b * beams + j];
-    const float l = lse[j];
-    for (int c = threadIdx.x; c < V; c += blockDim.x) {
-      const float v = (row[c] - l) + base;  // log_softmax first, then + running score (HF :3252-3256,3283)
-      const int gi = j * V + c;
-      float wv = -INFINITY; int wi = 0x7fffffff;
+    for (int u = 1; u < BEAM_UNROLL; ++u) bm = fmaxf(bm, x[u]);
+    const float nm = fmaxf(m, bm);  // finite: x[0] is a real logit
+    float add = 0.f;
 #pragma unroll
-      for (int t = 0; t < KMAX; ++t)
-        if (t == K - 1) { wv = lv[t]; wi = li[t]; }
-      if (bcand_better(v, gi, wv, wi)) {
-        float pv = v; int pi = gi;
-#pragma unroll
-        for (int t = 0; t < KMAX; ++t)
-          if (t < K && bcand_better(pv, pi, lv[t], li[t])) {
-            const float tv = lv[t]; const int ti = li[t];
-            lv[t] = pv; li[t] = pi; pv = tv; pi = ti;
-          }
-      }
-    }
+    for (int u = 0; u < BEAM_UNROLL; ++u) add += expf(x[u] - nm);  // exp(-inf) = 0 for the padding slots
+    s = (m == -INFINITY ? 0.f : s * expf(m - nm)) + add;
+    m = nm;
   }
 #pragma unroll
-  for (int t = 0; t < KMAX; ++t)
-    if (t < K) { cv[threadIdx.x * K + t] = lv[t]; ci[threadIdx.x * K + t] = li[t]; }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, s, o);
+    const float nm = fmaxf(m, om);
+    s = (m == -INFINITY ? 0.f : s * expf(m - nm)) + (om == -INFINITY ? 0.f : os * expf(om - nm));
+    m = nm;
+  }
+  if (lane == 0) { red_m[warp] = m; red_s[warp] = s; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float M = red_m[0], S = red_s[0];
+    for (int w = 1; w < nw; ++w) {
+      const float nm = fmaxf(M, red_m[w]);
+      S = (M == -INFINITY ? 0.f : S * expf(M - nm)) + (red_m[w] == -INFINITY ? 0.f : red_s[w] * expf(red_m[w] - nm));
+      M = nm;
+    }
+    lse[(size_t)b * rows_per_image + j] = M + logf(S);
+  }
+}
+
+// the block's per-thread sorted lists -> its K best (value desc, index asc) into out_v / out_i
+template <int K>
+__device__ __forceinline__ void beam_block_merge(const float (&lv)[K], const int (&li)[K], float* cv, int* ci, float* rv, int* ri, int* rslot,
+                                                 float* __restrict__ out_v, int* __restrict__ out_i) {
+#pragma unroll
+  for (int t = 0; t < K; ++t) { cv[threadIdx.x * K + t] = lv[t]; ci[threadIdx.x * K + t] = li[t]; }
   __syncthreads();
   const int ncand = blockDim.x * K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int out = 0; out < K; ++out) {
     float bv = -INFINITY; int bi = 0x7fffffff, bslot = -1;
     for (int s = threadIdx.x; s < ncand; s += blockDim.x)
@@ -105,21 +90,119 @@ __global__ void __launch_bounds__(256) beam_topk_kernel(const float* __restrict_
     if (threadIdx.x == 0) {
       for (int w = 1; w < nw; ++w)
         if (bcand_better(rv[w], ri[w], bv, bi)) { bv = rv[w]; bi = ri[w]; bslot = rslot[w]; }
-      cand_score[(size_t)b * K + out] = bv;
-      cand_idx[(size_t)b * K + out] = bi;
+      out_v[out] = bv;
+      out_i[out] = bi;
       if (bslot >= 0) { cv[bslot] = -INFINITY; ci[bslot] = 0x7fffffff; }
     }
     __syncthreads();
   }
 }
 
+template <int K>
+__global__ void __launch_bounds__(256) beam_rowtopk_kernel(const float* __restrict__ logits, int rows_per_image, int n_live,
+                                                           const float* __restrict__ run_score, const float* __restrict__ lse, int beams, int V,
+                                                           float* __restrict__ row_val, int* __restrict__ row_idx /* [B * rows_per_image, K] */) {
+  extern __shared__ unsigned char sm_raw[];
+  float* cv = reinterpret_cast<float*>(sm_raw);                                  // [256 * K]
+  int* ci = reinterpret_cast<int*>(sm_raw + (size_t)blockDim.x * K * sizeof(float));  // [256 * K]
+  __shared__ float rv[8];
+  __shared__ int ri[8], rslot[8];
+  const int b = blockIdx.x / n_live, j = blockIdx.x % n_live;
+  const size_t r = (size_t)b * rows_per_image + j;
+  const float* row = logits + r * V;
+  const float base = run_score[(size_t)b * beams + j], l = lse[r];
+  float lv[K];
+  int li[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) { lv[t] = -INFINITY; li[t] = 0x7fffffff; }
+  for (int c0 = threadIdx.x; c0 < V; c0 += blockDim.x * BEAM_UNROLL) {
+    float x[BEAM_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BEAM_UNROLL; ++u) {
+      const int c = c0 + u * blockDim.x;
+      x[u] = c < V ? row[c] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < BEAM_UNROLL; ++u) {
+      const int c = c0 + u * blockDim.x;
+      const float v = (x[u] - l) + base;  // log_softmax first, then + running score (HF :3252-3256,3283)
+      const int gi = j * V + c;
+      if (c < V && bcand_better(v, gi, lv[K - 1], li[K - 1])) {
+        float pv = v; int pi = gi;
+#pragma unroll
+        for (int t = 0; t < K; ++t)
+          if (bcand_better(pv, pi, lv[t], li[t])) {
+            const float tv = lv[t]; const int ti = li[t];
+            lv[t] = pv; li[t] = pi; pv = tv; pi = ti;
+          }
+      }
+    }
+  }
+  beam_block_merge<K>(lv, li, cv, ci, rv, ri, rslot, row_val + r * K, row_idx + r * K);
+}
+
+// one warp per image: the K best of its n_live x K row candidates
+__global__ void __launch_bounds__(32) beam_merge_kernel(const float* __restrict__ row_val, const int* __restrict__ row_idx, int rows_per_image,
+                                                        int n_live, int K, float* __restrict__ cand_score, int* __restrict__ cand_idx) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int n = n_live * K;  // <= 8 * 16 = 128 candidates: up to 4 per lane
+  float v[4];
+  int ix[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int s = lane + 32 * u;
+    const bool ok = s < n;
+    const size_t src = ((size_t)b * rows_per_image + (ok ? s / K : 0)) * K + (ok ? s % K : 0);
+    v[u] = ok ? row_val[src] : -INFINITY;
+    ix[u] = ok ? row_idx[src] : 0x7fffffff;
+  }
+  for (int out = 0; out < K; ++out) {
+    float bv = v[0]; int bi = ix[0], bu = 0;
+#pragma unroll
+    for (int u = 1; u < 4; ++u)
+      if (bcand_better(v[u], ix[u], bv, bi)) { bv = v[u]; bi = ix[u]; bu = u; }
+    int bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o), ol = __shfl_xor_sync(0xffffffffu, bl, o), ou = __shfl_xor_sync(0xffffffffu, bu, o);
+      if (bcand_better(ov, oi, bv, bi) || (ov == bv && oi == bi && ol < bl)) { bv = ov; bi = oi; bl = ol; bu = ou; }
+    }
+    if (lane == 0) { cand_score[(size_t)b * K + out] = bv; cand_idx[(size_t)b * K + out] = bi; }
+    if (lane == bl) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u == bu) { v[u] = -INFINITY; ix[u] = 0x7fffffff; }
+    }
+  }
+}
+
+template <int K>
+static int launch_beam_rowtopk(const float* logits, int B, int rows_per_image, int n_live, const float* run_score, const float* lse, int beams,
+                               int V, float* row_val, int* row_idx, cudaStream_t st) {
+  const size_t smem = (size_t)256 * K * (sizeof(float) + sizeof(int));
+  beam_rowtopk_kernel<K><<<B * n_live, 256, smem, st>>>(logits, rows_per_image, n_live, run_score, lse, beams, V, row_val, row_idx);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return GIC_OK;
+}
+
 int launch_beam_topk(const float* logits, int B, int rows_per_image, int n_live, const float* run_score, int beams, int V, int K,
-                     float* cand_score, int* cand_idx, cudaStream_t st) {
-  GIC_REQUIRE(K >= 1 && K <= 16 && beams <= 8 && n_live <= beams, "beam_topk: beams %d / K %d out of range (beams <= 8)", beams, K);
-  const int nthreads = 256;
-  const size_t smem = (size_t)nthreads * K * (sizeof(float) + sizeof(int));
-  if (K <= 8) beam_topk_kernel<8><<<B, nthreads, smem, st>>>(logits, rows_per_image, n_live, run_score, beams, V, K, cand_score, cand_idx);
-  else beam_topk_kernel<16><<<B, nthreads, smem, st>>>(logits, rows_per_image, n_live, run_score, beams, V, K, cand_score, cand_idx);
+                     float* lse, float* row_val, int* row_idx, float* cand_score, int* cand_idx, cudaStream_t st) {
+  GIC_REQUIRE(K == 2 * beams && beams >= 2 && beams <= 8 && n_live >= 1 && n_live <= beams, "beam_topk: beams %d / K %d / live %d out of range", beams, K, n_live);
+  beam_lse_kernel<<<B * n_live, 256, 0, st>>>(logits, rows_per_image, n_live, V, lse);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  switch (K) {
+    case 4: GIC_TRY(launch_beam_rowtopk<4>(logits, B, rows_per_image, n_live, run_score, lse, beams, V, row_val, row_idx, st)); break;
+    case 6: GIC_TRY(launch_beam_rowtopk<6>(logits, B, rows_per_image, n_live, run_score, lse, beams, V, row_val, row_idx, st)); break;
+    case 8: GIC_TRY(launch_beam_rowtopk<8>(logits, B, rows_per_image, n_live, run_score, lse, beams, V, row_val, row_idx, st)); break;
+    case 10: GIC_TRY(launch_beam_rowtopk<10>(logits, B, rows_per_image, n_live, run_score, lse, beams, V, row_val, row_idx, st)); break;
+    case 12: GIC_TRY(launch_beam_rowtopk<12>(logits, B, rows_per_image, n_live, run_score, lse, beams, V, row_val, row_idx, st)); break;
+    case 14: GIC_TRY(launch_beam_rowtopk<14>(logits, B, rows_per_image, n_live, run_score, lse, beams, V, row_val, row_idx, st)); break;
+    default: GIC_TRY(launch_beam_rowtopk<16>(logits, B, rows_per_image, n_live, run_score, lse, beams, V, row_val, row_idx, st)); break;
+  }
+  beam_merge_kernel<<<B, 32, 0, st>>>(row_val, row_idx, rows_per_image, n_live, K, cand_score, cand_idx);
   GIC_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return GIC_OK;

@@ -281,6 +281,7 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
     bs.unsat = c.take<unsigned char>(B);
     bs.beam_idx = c.take<int>(w->rows); bs.next_tok = c.take<int>(w->rows);
     bs.cand_score = c.take<float>((size_t)2 * w->rows); bs.cand_idx = c.take<int>((size_t)2 * w->rows);
+    bs.lse = c.take<float>(w->rows); bs.row_val = c.take<float>((size_t)2 * w->beams * w->rows); bs.row_idx = c.take<int>((size_t)2 * w->beams * w->rows);
   }
   if (e->fuse_ln) {
     w->ln_parts_max = ceil_div(d, 32);
@@ -916,7 +917,8 @@ int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int
   for (int t = 0; t < max_new; ++t) {
     const int live = t == 0 ? 1 : nb;  // only beam 0 is live at the first step (running scores 0, -1e9, ...)
     { ProfScope ps(e, "beam_topk", st);
-      GIC_TRY(launch_beam_topk(w.logits, B, live, live, w.beam.run_score, nb, e->V, K, w.beam.cand_score, w.beam.cand_idx, st)); }
+      GIC_TRY(launch_beam_topk(w.logits, B, live, live, w.beam.run_score, nb, e->V, K, w.beam.lse, w.beam.row_val, w.beam.row_idx, w.beam.cand_score,
+                               w.beam.cand_idx, st)); }
     const float denom = (float)pow((double)(t + 1), (double)length_penalty);
     { ProfScope ps(e, "beam_update", st); GIC_TRY(launch_beam_update(w.beam, t, denom, st)); }
     if (t + 1 == max_new) break;

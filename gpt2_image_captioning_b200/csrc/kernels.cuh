@@ -137,10 +137,12 @@ struct BeamState {
   unsigned char* unsat;                   // [B] early-stop heuristic still unsatisfied
   int* beam_idx; int* next_tok;           // [B * beams] parent cache row / token of every surviving beam
   float* cand_score; int* cand_idx;       // [B, 2 * beams]
+  float* lse; float* row_val; int* row_idx;  // [B * beams], [B * beams, 2 * beams]: per-row log-sum-exp and top-2*beams continuations
 };
 int launch_beam_init(const BeamState& s, cudaStream_t st);
 int launch_beam_topk(const float* logits, int B, int rows_per_image, int n_live, const float* run_score, int beams, int V, int K,
-                     float* cand_score, int* cand_idx, cudaStream_t st);
+                     float* lse /* [B * rows_per_image] */, float* row_val, int* row_idx /* [B * rows_per_image, K] */, float* cand_score,
+                     int* cand_idx, cudaStream_t st);
 int launch_beam_update(const BeamState& s, int step, float len_denom, cudaStream_t st);
 int launch_beam_embed(const int* next_tok, const float* wte_f32, const bf16* wte_bf16, const float* wpe, int pos, int d, float* h, int rows,
                       cudaStream_t st);
