@@ -386,9 +386,13 @@ constexpr int MMA_STAGE_BYTES = 2 * MMA_CHUNK * HD * 2;  // K chunk + V chunk
 template <int WARPS, int STAGES>
 struct DecMmaCfg { static constexpr int SMEM_BYTES = WARPS * STAGES * MMA_STAGE_BYTES + WARPS * STAGES * 8 + 128; };
 
-template <int WARPS, int STAGES>
+// INDIRECT (beam search): the cache is never reordered.  Row r's first n_prefix positions are read from the prefill row of its image
+// ((r / beams) * beams), position n_prefix + g from cache row anc[r * anc_ld + g] -- the row that generated the g-th token of r's
+// current hypothesis (beam_ancestry_kernel) -- and the new token is appended to r's own row.  This replaces HF's
+// DynamicCache.reorder_cache (HF:cache_utils.py:81-85), a 2 x 28 GB gather per step at config 3.
+template <int WARPS, int STAGES, bool INDIRECT>
 __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos,
-                                                                      int rows, int H, int t_max) {
+                                                                      int rows, int H, int t_max, const int* anc, int anc_ld, int n_prefix, int beams) {
   extern __shared__ uint8_t dec_smem_raw[];
   const uint32_t smem_base = (dec_smem_u32(dec_smem_raw) + 127u) & ~127u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -418,21 +422,43 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
   // producer side (lane 0): chunk n of this warp's stream -> stage n % STAGES (the cached keys of the chunk only).
   // K / V of item i start at i * t_max * 64 elements of their plane (item = row * H + head).
   int p_item = w0, p_c = 0, p_s = 0;  // producer cursor: item, chunk of the item, stage
+  // direct: lane 0 issues; INDIRECT: the whole warp calls it (lane 0: barrier + the contiguous prefix part, lane l: generated key l)
   auto issue_next = [&]() {
     const int nkeys = min(MMA_CHUNK, pos - p_c * MMA_CHUNK);  // cached keys in this chunk (0..16)
     const uint32_t bytes = (uint32_t)nkeys * HD * 2;
-    const size_t off = ((size_t)p_item * t_max + (size_t)p_c * MMA_CHUNK) * HD;
     const uint32_t bar = bars + 8 * p_s, dst = ring + p_s * MMA_STAGE_BYTES;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * bytes) : "memory");
-    if (bytes > 0) {
-      dec_bulk_load(dst, kcache + off, bytes, bar);
-      dec_bulk_load(dst + MMA_CHUNK * HD * 2, vcache + off, bytes, bar);
+    if (!INDIRECT) {
+      const size_t off = ((size_t)p_item * t_max + (size_t)p_c * MMA_CHUNK) * HD;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * bytes) : "memory");
+      if (bytes > 0) {
+        dec_bulk_load(dst, kcache + off, bytes, bar);
+        dec_bulk_load(dst + MMA_CHUNK * HD * 2, vcache + off, bytes, bar);
+      }
+    } else {
+      const int prow = p_item / H, ph = p_item - prow * H;
+      const int k0 = p_c * MMA_CHUNK;                        // first key of the chunk
+      const int npre = max(0, min(nkeys, n_prefix - k0));    // ... of which this many come from the image's prefill row
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * bytes) : "memory");
+        if (npre > 0) {
+          const size_t off = ((((size_t)(prow / beams) * beams) * H + ph) * t_max + k0) * HD;
+          dec_bulk_load(dst, kcache + off, (uint32_t)npre * HD * 2, bar);
+          dec_bulk_load(dst + MMA_CHUNK * HD * 2, vcache + off, (uint32_t)npre * HD * 2, bar);
+        }
+      }
+      const int j = npre + lane;  // slot of the chunk served by this lane
+      if (j < nkeys) {
+        const int src_row = __ldcg(anc + (size_t)prow * anc_ld + (k0 + j - n_prefix));
+        const size_t off = ((((size_t)src_row) * H + ph) * t_max + k0 + j) * HD;
+        dec_bulk_load(dst + j * (HD * 2), kcache + off, HD * 2, bar);
+        dec_bulk_load(dst + MMA_CHUNK * HD * 2 + j * (HD * 2), vcache + off, HD * 2, bar);
+      }
     }
     if (++p_c == nch) { p_c = 0; p_item += wstride; }
     if (++p_s == STAGES) p_s = 0;
   };
   int issued = 0;
-  if (lane == 0)
+  if (INDIRECT || lane == 0)
     for (; issued < STAGES - 1 && issued < total_chunks; ++issued) issue_next();
 
   // q in A-fragment order for row g (16-byte column j of q sits where column j ^ g is expected) and the new token's k / v
@@ -476,7 +502,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
     for (int j = 0; j < 8; ++j) { o[j][0] = 0.f; o[j][1] = 0.f; o[j][2] = 0.f; o[j][3] = 0.f; }
     for (int c = 0; c < nch; ++c) {
       // keep the ring full: the stage freed by the previous chunk takes the next chunk of the stream
-      if (lane == 0 && issued < total_chunks) { issue_next(); ++issued; }
+      if ((INDIRECT || lane == 0) && issued < total_chunks) { issue_next(); ++issued; }
       const uint32_t st = ring + c_s * MMA_STAGE_BYTES;
       const int cached = min(MMA_CHUNK, pos - c * MMA_CHUNK);  // cached keys of this chunk
       const bool last = c == nch - 1;                            // ... followed by the new token in slot `cached` (< 16 here)
@@ -571,9 +597,10 @@ int attn_decode_configure() {
   GIC_DEC_VARIANTS(X)
 #undef X
 #define X(ID, W, S) \
-  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<W, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<W, S>::SMEM_BYTES));
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<W, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<W, S>::SMEM_BYTES));
   GIC_DEC_MMA_VARIANTS(X)
 #undef X
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<12, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<12, 4>::SMEM_BYTES));
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
@@ -599,8 +626,8 @@ static int launch_attn_decode_bulk(const bf16* qkv, bf16* kcache, bf16* vcache, 
 #define X(ID, W, S)                                                                                                                  \
   if (g_dec_variant == ID) {                                                                                                         \
     const int grid = min(sms, ceil_div(items, W));                                                                                   \
-    GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<W, S>, dim3(grid), dim3(W * 32), (size_t)DecMmaCfg<W, S>::SMEM_BYTES, st, qkv, kcache, \
-                                 vcache, out, d_pos, rows, H, t_max));                                                               \
+    GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<W, S, false>, dim3(grid), dim3(W * 32), (size_t)DecMmaCfg<W, S>::SMEM_BYTES, st, qkv, kcache, \
+                                 vcache, out, d_pos, rows, H, t_max, (const int*)nullptr, 0, 0, 1));                                 \
     note_launch();                                                                                                                   \
     return GIC_OK;                                                                                                                   \
   }
@@ -608,6 +635,24 @@ static int launch_attn_decode_bulk(const bf16* qkv, bf16* kcache, bf16* vcache, 
 #undef X
   set_error("attn_decode: unknown kernel variant %d", g_dec_variant);
   return GIC_ERR_UNSUPPORTED;
+}
+
+// beam search without cache reordering (see attn_decode_mma_kernel INDIRECT)
+int launch_attn_decode_indirect(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos, int rows, int H, int t_max, const int* anc,
+                                int anc_ld, int n_prefix, int beams, cudaStream_t st) {
+  GIC_TRY(attn_decode_configure());
+  GIC_REQUIRE(anc != nullptr && beams >= 1 && n_prefix >= 0, "attn_decode_indirect: bad ancestry arguments");
+  const int sms = cta_limit() > 0 && cta_limit() < g_dec_sms ? cta_limit() : g_dec_sms;
+  const int grid = min(sms, ceil_div(rows * H, 12));
+  GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<12, 4, true>, dim3(grid), dim3(12 * 32), (size_t)DecMmaCfg<12, 4>::SMEM_BYTES, st, qkv, kcache, vcache,
+                               out, d_pos, rows, H, t_max, anc, anc_ld, n_prefix, beams));
+  note_launch();
+  return GIC_OK;
+}
+bool attn_decode_indirect_available() {
+  const char* v = getenv("GIC_ATTN_SIMPLE");
+  const char* r = getenv("GIC_BEAM_REORDER");  // =1: physical cache reorder (kv_reorder_kernel) instead of the ancestry table
+  return !(v && v[0] == '1') && !(r && r[0] == '1');
 }
 
 static bool decode_bulk_enabled() {

@@ -335,6 +335,22 @@ __global__ void __launch_bounds__(128) beam_embed_kernel(const int* __restrict__
   }
 }
 
+__global__ void beam_ancestry_kernel(const int* __restrict__ anc_old, int* __restrict__ anc_new, const int* __restrict__ beam_idx, int rows, int ld, int t) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * t) return;
+  const int r = i / t, g = i - r * t;
+  const int p = beam_idx[r];
+  anc_new[(size_t)r * ld + g] = (g == t - 1) ? p : anc_old[(size_t)p * ld + g];
+}
+
+int launch_beam_ancestry(const int* anc_old, int* anc_new, const int* beam_idx, int rows, int ld, int t, cudaStream_t st) {
+  if (t <= 0) return GIC_OK;
+  beam_ancestry_kernel<<<ceil_div(rows * t, 256), 256, 0, st>>>(anc_old, anc_new, beam_idx, rows, ld, t);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return GIC_OK;
+}
+
 int launch_beam_embed(const int* next_tok, const float* wte_f32, const bf16* wte_bf16, const float* wpe, int pos, int d, float* h, int rows,
                       cudaStream_t st) {
   beam_embed_kernel<<<rows, 128, 0, st>>>(next_tok, wte_f32, wte_bf16, wpe, pos, d, h);

@@ -72,7 +72,8 @@ struct Workspace {
   unsigned char* finished = nullptr; int* first_eos = nullptr;
   int *d_step = nullptr, *d_pos = nullptr, *done_counter = nullptr;
   // beam search only
-  void* kv2 = nullptr;             // second KV cache (reorder target; the two swap every step)
+  void* kv2 = nullptr;             // second KV cache (reorder target; the two swap every step); null with the ancestry table
+  const int* anc = nullptr; int anc_ld = 0;  // beam search without reordering: ancestry table of the current step (see attention.cu)
   BeamState beam;
   size_t bytes = 0;
 };
@@ -85,6 +86,7 @@ struct gic_engine {
   gic_config cfg;
   int d = 0, L = 0, H = 0, V = 0, P_img = 0, P_task = 0, E = 0;
   bool split = false;  // BF16X2
+  bool beam_indirect = false;  // BF16 beam search: no KV reorder, decode attention reads through an ancestry table (GIC_BEAM_REORDER=1: gather)
   bool fuse_ln = false;  // BF16: ln_1 / ln_2 folded into the GEMM that follows them (no LayerNorm launches inside the GPT-2 blocks)
   bool use_splitk = false;  // GIC_SPLITK=1 turns the K split of the decode-size residual GEMMs on.  Off by default: measured round 1
                             // (profiles/r1w_microbench.txt), fc2 with a 3-way K split + last-CTA reduction takes 22 us against 15 us unsplit
@@ -270,9 +272,12 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
     if (w->beams > 1) w->logits = c.take<float>((size_t)w->rows * e->V);  // beam search needs full rows for log-softmax + top-2K
   }
   if (w->beams > 1) {
-    if (e->cfg.dtype == GIC_DTYPE_BF16) w->kv2 = c.take<bf16>(kv_elems);
-    else w->kv2 = c.take<float>(kv_elems);
     BeamState& bs = w->beam;
+    if (e->beam_indirect) {  // no second cache: attention follows the beams' ancestry instead
+      bs.anc[0] = c.take<int>((size_t)w->rows * (max_new > 0 ? max_new : 1));
+      bs.anc[1] = c.take<int>((size_t)w->rows * (max_new > 0 ? max_new : 1));
+    } else if (e->cfg.dtype == GIC_DTYPE_BF16) w->kv2 = c.take<bf16>(kv_elems);
+    else w->kv2 = c.take<float>(kv_elems);
     const size_t nseq = (size_t)w->rows * (max_new > 0 ? max_new : 1);
     bs.B = B; bs.beams = w->beams; bs.max_new = max_new; bs.V = e->V; bs.eos = e->cfg.eos_token_id;
     for (int i = 0; i < 2; ++i) { bs.run_seq[i] = c.take<int>(nseq); bs.fin_seq[i] = c.take<int>(nseq); }
@@ -372,6 +377,7 @@ static int attention(const gic_engine* e, const Workspace& w, int l, int M, bool
     bf16* kc = (bf16*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
     bf16* vc = kc + w.kv_layer_elems;
     if (prefill) return launch_attn_prefill<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, w.beams, st);
+    if (w.anc) return launch_attn_decode_indirect(w.qkv_bf16, kc, vc, w.o.hi, w.d_pos, M, e->H, w.t_max, w.anc, w.anc_ld, w.P, w.beams, st);
     return launch_attn_decode<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st);
   }
   float* kc = (float*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
@@ -642,6 +648,7 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
   {
     const char* nf = getenv("GIC_NO_LNFUSE");
     e->fuse_ln = cfg->dtype == GIC_DTYPE_BF16 && !(nf && nf[0] == '1');
+    e->beam_indirect = cfg->dtype == GIC_DTYPE_BF16 && gic::attn_decode_indirect_available();
     const char* sk = getenv("GIC_SPLITK");
     e->use_splitk = sk && sk[0] == '1';
     const char* hf = getenv("GIC_LNF_FUSE");
@@ -923,12 +930,19 @@ int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int
     { ProfScope ps(e, "beam_update", st); GIC_TRY(launch_beam_update(w.beam, t, denom, st)); }
     if (t + 1 == max_new) break;
     // reorder_cache: dst[row] = src[beam_idx[row]] over the P + t cached positions, then swap the two caches
-    { ProfScope ps(e, "kv_reorder", st);
+    if (e->beam_indirect) {
+      // no gather: record where each surviving hypothesis' generated positions live (its parents' cache rows)
+      ProfScope ps(e, "kv_reorder", st);
+      GIC_TRY(launch_beam_ancestry(w.beam.anc[t & 1], w.beam.anc[(t + 1) & 1], w.beam.beam_idx, rows, max_new, t, st));
+      w.anc = w.beam.anc[(t + 1) & 1]; w.anc_ld = max_new;
+    } else {
+      ProfScope ps(e, "kv_reorder", st);
       if (e->cfg.dtype == GIC_DTYPE_BF16)
         GIC_TRY(launch_kv_reorder<bf16>((const bf16*)w.kv, (bf16*)w.kv2, w.beam.beam_idx, e->L, rows, e->H, P + t, w.t_max, st));
       else
-        GIC_TRY(launch_kv_reorder<float>((const float*)w.kv, (float*)w.kv2, w.beam.beam_idx, e->L, rows, e->H, P + t, w.t_max, st)); }
-    { void* tmp = w.kv; w.kv = w.kv2; w.kv2 = tmp; }
+        GIC_TRY(launch_kv_reorder<float>((const float*)w.kv, (float*)w.kv2, w.beam.beam_idx, e->L, rows, e->H, P + t, w.t_max, st));
+      void* tmp = w.kv; w.kv = w.kv2; w.kv2 = tmp;
+    }
     GIC_TRY(launch_beam_embed(w.beam.next_tok, e->wte_f32, e->wte_f32 ? nullptr : e->wte_gather, e->wpe, P + t, d, w.h_dec, rows, st));
     GIC_TRY(launch_set_int(w.d_pos, P + t, st));
     if (e->fuse_ln) GIC_TRY(launch_row_stats(w.h_dec, d, w.a.hi, w.ln_stats, rows, d, st));

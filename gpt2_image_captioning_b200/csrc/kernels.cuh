@@ -93,6 +93,10 @@ int launch_attn_prefill(const T* qkv, T* kcache, T* vcache, ActOut out, int B, i
                         cudaStream_t st);
 template <typename T>
 int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows, int H, int t_max, cudaStream_t st);
+// bf16 decode attention through a beam-ancestry table instead of a reordered cache (beam search); see attention.cu
+int launch_attn_decode_indirect(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos, int rows, int H, int t_max, const int* anc,
+                                int anc_ld, int n_prefix, int beams, cudaStream_t st);
+bool attn_decode_indirect_available();
 void attn_decode_set_variant(int v);  // microbenchmark: ring geometry of the bulk-copy decode kernel (0 = product)
 int attn_decode_configure();  // cudaFuncSetAttribute for the bulk-copy decode kernel (call once, outside stream capture)
 template <typename T>
@@ -137,6 +141,7 @@ struct BeamState {
   unsigned char* unsat;                   // [B] early-stop heuristic still unsatisfied
   int* beam_idx; int* next_tok;           // [B * beams] parent cache row / token of every surviving beam
   float* cand_score; int* cand_idx;       // [B, 2 * beams]
+  int* anc[2];                            // [B * beams, max_new] ancestry tables (double-buffered): cache row of every generated position
   float* lse; float* row_val; int* row_idx;  // [B * beams], [B * beams, 2 * beams]: per-row log-sum-exp and top-2*beams continuations
 };
 int launch_beam_init(const BeamState& s, cudaStream_t st);
@@ -144,6 +149,8 @@ int launch_beam_topk(const float* logits, int B, int rows_per_image, int n_live,
                      float* lse /* [B * rows_per_image] */, float* row_val, int* row_idx /* [B * rows_per_image, K] */, float* cand_score,
                      int* cand_idx, cudaStream_t st);
 int launch_beam_update(const BeamState& s, int step, float len_denom, cudaStream_t st);
+// anc_new[r][g] = g == t - 1 ? beam_idx[r] : anc_old[beam_idx[r]][g] for g < t (t = tokens generated so far)
+int launch_beam_ancestry(const int* anc_old, int* anc_new, const int* beam_idx, int rows, int ld, int t, cudaStream_t st);
 int launch_beam_embed(const int* next_tok, const float* wte_f32, const bf16* wte_bf16, const float* wpe, int pos, int d, float* h, int rows,
                       cudaStream_t st);
 int launch_set_int(int* p, int v, cudaStream_t st);

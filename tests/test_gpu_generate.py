@@ -162,6 +162,26 @@ def test_beam_search_matches_hf_generation(name, dtype, emb_total):
     assert all(rows_same), (ids, ref)
 
 
+@pytest.mark.parametrize("name,beams,rows", [("tiny_mlp_beam5", 5, 8), ("tiny_mlp_beam5", 3, 37), ("c3_medium_tfm_beam5", 5, 6), ("tiny_mlp_eos", 4, 40)])
+def test_bf16_beam_search_ancestry_table_equals_cache_reorder(monkeypatch, name, beams, rows):
+    """bf16 beam search reads the KV cache through an ancestry table (no reorder); GIC_BEAM_REORDER=1 runs HF's
+    reorder_cache gather instead (HF:cache_utils.py:81-85).  Attention sees the same keys in the same slots either way, so the
+    hypotheses must be identical -- also with EOS-terminated hypotheses and a transformer mapper with P = 40."""
+    g = gu.load(name)
+    outs = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("GIC_BEAM_REORDER", mode)
+        model, _, x0 = gpu_util.product_model(g, "bf16")
+        xx = oc.synthetic_embeddings(rows, int(x0.shape[1]), seed=21)
+        model.num_beams = beams
+        outs.append(model.generate(image_embeddings=xx.to(DEV), max_length=14, temperature=0.0).cpu())
+        eng = model._get_engine()
+        ws_bytes = eng.workspace(rows, 14, beams).numel()
+        outs.append(ws_bytes)
+    assert torch.equal(outs[0], outs[2]), (outs[0], outs[2])
+    assert outs[1] < outs[3]  # no second cache
+
+
 def test_kv_reorder_gathers_rows():
     from gpt2_image_captioning_b200 import ops
     g = gu.load("tiny_mlp_eos")
