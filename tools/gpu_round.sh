@@ -36,10 +36,10 @@ if has full; then
 print(2 + 75 + 11 * 7)
 PY
 ); fi
-  timeout 300 python tools/profile_step.py --max-length 6 > $OUT/${TAG}_plain2.log 2>&1 &&
+  timeout 300 python tools/profile_step.py --max-length ${NCU_MAXLEN:-6} > $OUT/${TAG}_plain2.log 2>&1 &&
   timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on \
       -k regex:'gemm_bf16_tcgen05|attn_decode|layernorm|finalize' -s $SKIP -c ${NCU_COUNT:-10} -f -o $OUT/${TAG}_step \
-      python tools/profile_step.py --max-length 6 > $OUT/${TAG}_ncu_full.log 2>&1
+      python tools/profile_step.py --max-length ${NCU_MAXLEN:-6} > $OUT/${TAG}_ncu_full.log 2>&1
   echo "ncu full rc=$?"
 fi
 du -sh $OUT

@@ -1,13 +1,19 @@
-"""Per-kernel-class device time of one full-size config-3 batch (GPT-2 medium, transformer mapper, P=40, beam 5)."""
+"""Per-kernel-class device time of one full-size batch of a secondary config (c3 | c4 | c5) via the engine's event profiling."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
 from tools.bench_configs import build
 dev = torch.device("cuda:0")
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-model = build(dict(n_embd=1024, n_layer=24, n_head=16), "tfm", 512, 40, "bf16", dev, beams=5)
-x = bench.synthetic_pool(B, 512).to(dev)
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+if cfg == "c3":
+    model = build(dict(n_embd=1024, n_layer=24, n_head=16), "tfm", 512, 40, "bf16", dev, beams=5); E = 512
+elif cfg == "c4":
+    model = build(dict(n_embd=1280, n_layer=36, n_head=20), "mlp", 1024, 10, "bf16", dev); E = 1024
+else:
+    model = build(bench.MODEL, "mlp", 512, 10, "bf16", dev); E = 512
+x = bench.synthetic_pool(B, E).to(dev)
 model.generate(image_embeddings=x, max_length=30, temperature=0.0)
 eng = model._get_engine()
 eng.profile(True)
