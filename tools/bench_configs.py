@@ -72,7 +72,7 @@ def main():
         model = build(dict(n_embd=1024, n_layer=24, n_head=16), "tfm", 512, 40, a.dtype, dev, beams=5)
         x = bench.synthetic_pool(B, 512).to(dev)
         ms, ids = timed(lambda: model.generate(image_embeddings=x, max_length=N, temperature=0.0))
-        print(json.dumps({"config": "c3: GPT-2 medium + 8-layer transformer mapper, prefix_len 40, beam 5, KV reorder", "batch": B, "dtype": a.dtype,
+        print(json.dumps({"config": "c3: GPT-2 medium + 8-layer transformer mapper, prefix_len 40, beam 5 (ancestry-table KV)", "batch": B, "dtype": a.dtype,
                           "ms_per_batch": ms, "captions_per_s": B / ms * 1e3, "ids_shape": list(ids.shape)}), flush=True)
         del model
         torch.cuda.empty_cache()
