@@ -2,11 +2,16 @@
 //
 //  attn_decode  : one new query per (row, head) against the KV cache -- the HBM-bound half of a decode step.
 //                 Replaces GPT2Attention.forward's cache `torch.cat` + SDPA for T_q = 1
-//                 (HF:models/gpt2/modeling_gpt2.py:185-220, HF:cache_utils.py:102-121).  One warp per (row, head);
-//                 K/V rows are 128 B (bf16) / 256 B (fp32): 8 / 16 lanes take one key with 128-bit loads, so a warp
-//                 iteration reads 4 / 2 consecutive keys = 512 contiguous bytes.  fp32 scores, warp-shuffle softmax.
-//                 The new token's K/V are appended to the cache in the same kernel (no separate cat/copy).
-//  attn_prefill : causal attention over the P prefix tokens of a row, writing K/V into the cache (prefill).
+//                 (HF:models/gpt2/modeling_gpt2.py:185-220, HF:cache_utils.py:102-121).  The new token's K/V are appended to
+//                 the cache in the same kernel (no separate cat/copy).  Three kernels:
+//                   attn_decode_mma_kernel   bf16 product path: persistent CTAs, per-warp cp.async.bulk + mbarrier ring, S and
+//                                            P.V on mma.sync with skewed conflict-free ldmatrix; INDIRECT = beam search through
+//                                            an ancestry table instead of a reordered cache
+//                   attn_decode_bulk_kernel  the same ring with SIMT math (issue bound; kept for comparison, variants 0 / 1)
+//                   attn_decode_kernel       fp32 / bf16x2 modes: one warp per (row, head), 8 / 16 lanes per key with 128-bit
+//                                            loads (512 contiguous bytes per warp iteration), fp32 scores, warp-shuffle softmax
+//  attn_prefill : causal attention over the P prefix tokens of a row, writing K/V into the cache (prefill);
+//                 attn_prefill_mma_kernel (bf16, P <= 64) or attn_seq_kernel.
 //  attn_encoder : bidirectional attention of nn.TransformerEncoderLayer's MHA (torch:nn/modules/transformer.py:946-950)
 //                 for the transformer mapping network (src/models.py:129-139), head_dim = d/8.
 //  kv_reorder   : beam-search cache gather, index_select(0, beam_idx) per layer (HF:cache_utils.py:81-85).
@@ -155,7 +160,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const T* qkv, T* kcach
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// bf16 decode attention, bulk-copy pipeline (the product path).  One persistent CTA per SM, 8 warps; every warp walks its
+// bf16 decode attention, bulk-copy pipeline with SIMT math (superseded by attn_decode_mma_kernel below, which keeps this ring).
+// One persistent CTA per SM; every warp walks its
 // own list of (row, head) items and streams their K / V rows (contiguous pos x 128 bytes each) into its private
 // shared-memory ring with cp.async.bulk + mbarrier, up to DEC_STAGES chunks of 32 keys ahead.  The copy engine keeps
 // ~100 KB per SM in flight without holding registers, so the HBM stream does not stall on the softmax arithmetic or on
