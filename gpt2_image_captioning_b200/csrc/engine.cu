@@ -353,6 +353,7 @@ static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, i
     g.w_lo = lin.tm_lo[bi];
   }
   g.M = M; g.N = lin.N; g.K = lin.K; g.block_n = bn; g.split = e->split ? 1 : 0; g.epilogue = epilogue; g.bias = lin.bias;
+  g.w_static = 1;  // packed at load time
   g.out = out; g.ld_out = ld_out; g.part_val = part_val; g.part_idx = part_idx; g.part_ld = part_ld;
   GIC_REQUIRE((lin.colsum != nullptr) == (ln != nullptr && ln->stats_in != nullptr), "linear: folded-LayerNorm weights and row statistics must come together");
   if (ln) {

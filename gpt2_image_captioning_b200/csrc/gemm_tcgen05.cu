@@ -218,6 +218,7 @@ struct alignas(64) GemmKernelParams {
   // split-K (see launch_gemm_bf16): `split_k` CTAs share one output tile, each over K / split_k; fp32 partials go to splitk_ws
   // [split_k][M][N] and the CTA that arrives last at splitk_counters[tile] sums them in split order and runs the epilogue
   int split_k; float* splitk_ws; int* splitk_counters;
+  int w_static;  // W may be fetched before griddepcontrol.wait (see the kernel)
   float2* stats_out;  // [ceil(N / 32)][ln_stats_ld] (sum, sum of squares) of the values written, per row and 32-column chunk
   long long* trace;  // null; microbenchmark only: clock64 timeline of CTA 0's producer / MMA / epilogue warps
 };
@@ -329,6 +330,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (tracing && threadIdx.x == 0) p.trace[600] = clock64() - t_start;  // prologue done
+  // Weights never depend on the previous kernel: the W halves of the first tile's first ring stages are requested BEFORE
+  // griddepcontrol.wait, while the previous kernel's stragglers are still running; after the wait only the A halves are missing
+  // (w_static: the caller vouches that W was not written by the kernel launched just before this one)
+  uint32_t pre = 0;
+  if (!SPLIT && warp == 0 && p.w_static && p.split_k == 1 && work0 < total_work) {
+    pre = (uint32_t)(nk < STAGES ? nk : STAGES);
+    if (ptx::elect_one()) {
+      const int n0 = ((work0 % total_tiles) / m_units) * BLOCK_N;
+      for (uint32_t ps = 0; ps < pre; ++ps) {
+        const uint32_t fb = full_bar + 8 * ps;
+        if (PAIR) {  // (both CTAs' barriers exist: the cluster barrier above)
+          if (rank == 0) ptx::mbar_expect_tx(fb, 2 * Tile::STAGE_BYTES);
+          ptx::tma_load_2d_pair(smem_base + ps * Tile::STAGE_BYTES + Tile::A_BYTES, &p.w_hi, fb, (int)ps * GEMM_BLOCK_K, n0 + (int)rank * (BLOCK_N / 2));
+        } else {
+          ptx::mbar_expect_tx(fb, Tile::STAGE_BYTES);
+          ptx::tma_load_2d(smem_base + ps * Tile::STAGE_BYTES + Tile::A_BYTES, &p.w_hi, fb, (int)ps * GEMM_BLOCK_K, n0);
+        }
+      }
+    }
+    __syncwarp();
+  }
   pdl_wait();  // prologue above overlapped the previous kernel; its outputs are visible from here on
 
   if (warp == 0) {
@@ -343,12 +365,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         if (ptx::elect_one()) {
           const uint32_t st = smem_base + s * Tile::STAGE_BYTES;
           const uint32_t fb = full_bar + 8 * s;
-          if (PAIR) {
+          if (PAIR && it < pre) {
+            ptx::tma_load_2d_pair(st, &p.a_hi, fb, kb * GEMM_BLOCK_K, m0);  // barrier armed and W halves requested before the wait
+          } else if (PAIR) {
             // the leader's full barrier counts the bytes of both CTAs' loads (its arrival is the only pending one, so the
             // phase cannot complete before it has armed the count, even if the peer's bytes land first)
             if (rank == 0) ptx::mbar_expect_tx(fb, 2 * Tile::STAGE_BYTES);
             ptx::tma_load_2d_pair(st, &p.a_hi, fb, kb * GEMM_BLOCK_K, m0);
             ptx::tma_load_2d_pair(st + Tile::A_BYTES, &p.w_hi, fb, kb * GEMM_BLOCK_K, n0 + (int)rank * (BLOCK_N / 2));
+          } else if (it < pre) {
+            ptx::tma_load_2d(st, &p.a_hi, fb, kb * GEMM_BLOCK_K, m0);  // barrier armed and W requested before the wait
           } else {
           ptx::mbar_expect_tx(fb, Tile::STAGE_BYTES);
           ptx::tma_load_2d(st, &p.a_hi, fb, kb * GEMM_BLOCK_K, m0);
@@ -1168,6 +1194,7 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   kp.ln_stats = a.ln_stats; kp.ln_parts = a.ln_parts; kp.ln_stats_ld = a.ln_stats_ld; kp.ln_row_mul = a.ln_row_mul; kp.ln_row_off = a.ln_row_off;
   kp.ln_colsum = a.ln_colsum; kp.stats_out = a.stats_out;
   kp.split_k = a.split_k < 1 ? 1 : a.split_k; kp.splitk_ws = a.splitk_ws; kp.splitk_counters = a.splitk_counters;
+  kp.w_static = a.w_static;
   GIC_REQUIRE(!a.ln_stats || (a.ln_colsum && a.ln_parts > 0), "gemm_bf16: folded LayerNorm needs the column sums and at least one statistics part");
   int epi = a.epilogue;
   if (a.part_val) {

@@ -53,6 +53,8 @@ struct GemmBf16Args {
   const float* ln_colsum = nullptr;  // [N] sum_k of the packed (bf16) gamma-folded weights
   float2* stats_out = nullptr;       // [ceil(N / 32)][ln_stats_ld]: per-row (sum, sum of squares) of the values this GEMM writes, per 32-column chunk
   // split-K for short-and-wide problems (few output tiles, long K): split_k CTAs per tile, deterministic last-CTA reduction
+  int w_static = 0;  // the weights were written long before this launch (engine weights): their first tiles may be fetched before
+                     // griddepcontrol.wait, i.e. while the previous kernel is still finishing
   int no_pdl = 0;  // launch in plain stream order (no programmatic dependent launch): for callers that mix these launches with ordinary
                    // <<<>>> launches outside a graph -- measured: the host then blocks for milliseconds inside cudaLaunchKernelEx
   int pair = 0;  // CTA pairs: 256 x block_n tiles by two CTAs (cta_group::2); w_hi's box holds block_n / 2 rows

@@ -247,7 +247,7 @@ int main(int argc, char** argv) {
           GemmBf16Args& g = args[i];
           OK(make_tma_2d_bf16(&g.a_hi, a, B, s.K, s.K, 128));
           OK(make_tma_2d_bf16(&g.w_hi, (*s.w)[i], s.N, s.K, s.K, pair ? bn / 2 : bn));
-          g.M = B; g.N = s.N; g.K = s.K; g.block_n = bn; g.epilogue = s.epi; g.bias = bias; g.ld_out = s.N; g.pair = pair;
+          g.M = B; g.N = s.N; g.K = s.K; g.block_n = bn; g.epilogue = s.epi; g.bias = bias; g.ld_out = s.N; g.pair = pair; g.w_static = 1;
           if (s.res) g.out.f32 = h; else g.out.hi = (s.N == 3 * d ? qkv : o);
           if (fused) {  // LayerNorm folded: statistics in for qkv / fc, bf16 copy + statistics out for the residual GEMMs
             if (s.res) { g.out.hi = o; g.stats_out = stats; g.ln_stats_ld = B; }
