@@ -28,6 +28,10 @@
 
 #include "kernels.cuh"
 
+#ifndef GIC_PAIR_PRELOAD
+#define GIC_PAIR_PRELOAD 0  // W preload before griddepcontrol.wait for CTA pairs too (single CTAs always preload)
+#endif
+
 namespace gic {
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -334,7 +338,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   // griddepcontrol.wait, while the previous kernel's stragglers are still running; after the wait only the A halves are missing
   // (w_static: the caller vouches that W was not written by the kernel launched just before this one)
   uint32_t pre = 0;
-  if (!SPLIT && warp == 0 && p.w_static && p.split_k == 1 && work0 < total_work) {
+  constexpr bool PAIR_PRELOAD = GIC_PAIR_PRELOAD != 0;
+  if (!SPLIT && (!PAIR || PAIR_PRELOAD) && warp == 0 && p.w_static && p.split_k == 1 && work0 < total_work) {
     pre = (uint32_t)(nk < STAGES ? nk : STAGES);
     if (ptx::elect_one()) {
       const int n0 = ((work0 % total_tiles) / m_units) * BLOCK_N;
