@@ -29,7 +29,7 @@
 #include "kernels.cuh"
 
 #ifndef GIC_PAIR_PRELOAD
-#define GIC_PAIR_PRELOAD 0  // W preload before griddepcontrol.wait for CTA pairs too (single CTAs always preload)
+#define GIC_PAIR_PRELOAD 1  // W preload before griddepcontrol.wait for CTA pairs too (0: single CTAs only)
 #endif
 
 namespace gic {
