@@ -994,6 +994,12 @@ int gic_select_caption_rows(const float* scores, const int64_t* idx, int batch, 
                                     (cudaStream_t)stream);
 }
 
+int gic_gather_attention_add(const float* q, const float* cap_db, const int64_t* rows, int batch, int top_k, int dim, const float* attn_w,
+                             const float* attn_b, float* out, void* stream) {
+  GIC_REQUIRE(q && cap_db && rows && attn_w && attn_b && out, "null argument");
+  return launch_gather_attention_add(q, cap_db, rows, batch, top_k, dim, attn_w, attn_b, out, (cudaStream_t)stream);
+}
+
 int gic_gather_aggregate_add(const float* q, const float* cap_db, const int64_t* rows, int batch, int top_k, int dim, int aggregation,
                              float* out, void* stream) {
   GIC_REQUIRE(q && cap_db && rows && out, "null argument");

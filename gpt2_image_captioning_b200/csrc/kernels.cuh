@@ -169,6 +169,8 @@ int launch_topk_ip(const float* q, const float* db, int B, int N, int D, int k, 
                    cudaStream_t st);
 int launch_select_caption_rows(const float* scores, const int64_t* idx, int B, int k_searched, const int64_t* cap_row_start,
                                const int64_t* cap_row_ids, int top_i, int top_k, int64_t* rows_out, cudaStream_t st);
+int launch_gather_attention_add(const float* q, const float* cap_db, const int64_t* rows, int B, int top_k, int D, const float* attn_w,
+                                const float* attn_b, float* out, cudaStream_t st);
 int launch_gather_aggregate_add(const float* q, const float* cap_db, const int64_t* rows, int B, int top_k, int D, int aggregation,
                                 float* out, cudaStream_t st);
 

@@ -506,4 +506,62 @@ int launch_gather_aggregate_add(const float* q, const float* cap_db, const int64
   return GIC_OK;
 }
 
+// RetrievalAggregator "attention" (src/models.py:606-616): score_j = w . r_j + b over the top_k gathered rows (zero rows for -1 padding,
+// whose score is b), softmax over j, out = q + sum_j weight_j r_j
+__global__ void __launch_bounds__(256) gather_attention_add_kernel(const float* __restrict__ q, const float* __restrict__ cap_db,
+                                                                   const int64_t* __restrict__ rows, int top_k, int D, const float* __restrict__ attn_w,
+                                                                   const float* __restrict__ attn_b, float* __restrict__ out) {
+  __shared__ float red[8];
+  __shared__ float sc[64];
+  const int b = blockIdx.x;
+  const int64_t* r = rows + (size_t)b * top_k;
+  constexpr int MAXC = 8;  // D <= 2048
+  float w[MAXC];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) { const int c = threadIdx.x + i * 256; w[i] = c < D ? attn_w[c] : 0.f; }
+  const float bias = attn_b[0];
+  for (int j = 0; j < top_k; ++j) {
+    const int64_t ri = r[j];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = threadIdx.x + i * 256;
+      dot += (ri >= 0 && c < D) ? cap_db[(size_t)ri * D + c] * w[i] : 0.f;
+    }
+    const float s = block_sum_256(dot, red) + bias;
+    if (threadIdx.x == 0) sc[j] = s;
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int j = 0; j < top_k; ++j) m = fmaxf(m, sc[j]);
+  float den = 0.f;
+  for (int j = 0; j < top_k; ++j) den += expf(sc[j] - m);
+  float acc[MAXC];
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) acc[i] = 0.f;
+  for (int j = 0; j < top_k; ++j) {
+    const int64_t ri = r[j];
+    const float wt = expf(sc[j] - m) / den;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+      const int c = threadIdx.x + i * 256;
+      if (ri >= 0 && c < D) acc[i] = fmaf(wt, cap_db[(size_t)ri * D + c], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = threadIdx.x + i * 256;
+    if (c < D) out[(size_t)b * D + c] = q[(size_t)b * D + c] + acc[i];
+  }
+}
+
+int launch_gather_attention_add(const float* q, const float* cap_db, const int64_t* rows, int B, int top_k, int D, const float* attn_w,
+                                const float* attn_b, float* out, cudaStream_t st) {
+  GIC_REQUIRE(D <= 2048 && D > 0 && top_k > 0 && top_k <= 64, "gather_attention_add: unsupported D=%d top_k=%d (top_k <= 64)", D, top_k);
+  gather_attention_add_kernel<<<B, 256, 0, st>>>(q, cap_db, rows, top_k, D, attn_w, attn_b, out);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return GIC_OK;
+}
+
 }  // namespace gic

@@ -126,10 +126,25 @@ class GpuFlatStore:
         out = self.caption_index.matrix[rows.clamp(min=0)]
         return out * (rows >= 0).unsqueeze(-1).to(out.dtype)
 
-    def retrieve_and_aggregate(self, image_embeddings: torch.Tensor, top_i: int, top_k: int, aggregation: str = "mean") -> torch.Tensor:
-        """query + pooled retrieved captions, float32 [B, D] on the input's device (src/models.py:763-768)."""
-        if aggregation not in _capi.AGG:
+    def retrieve_and_aggregate(self, image_embeddings: torch.Tensor, top_i: int, top_k: int, aggregation: str = "mean",
+                               attention_weight: torch.Tensor | None = None, attention_bias: torch.Tensor | None = None) -> torch.Tensor:
+        """query + pooled retrieved captions, float32 [B, D] on the input's device (src/models.py:763-768).  aggregation
+        "attention" takes RetrievalAggregator.attention_proj's weight [1, D] and bias [1] (:606-616)."""
+        if aggregation not in _capi.AGG and aggregation != "attention":
             raise ValueError(f"Unknown aggregation_type: {aggregation}")
+        if aggregation == "attention":
+            if attention_weight is None or attention_bias is None:
+                raise ValueError("attention pooling needs attention_proj's weight and bias")
+            src_device = image_embeddings.device
+            q = image_embeddings.to(device=self.device, dtype=torch.float32).contiguous()
+            rows = self.retrieve_rows(q, top_i, top_k)
+            out = torch.empty_like(q)
+            if q.shape[0]:
+                w = attention_weight.detach().to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+                bb = attention_bias.detach().to(device=self.device, dtype=torch.float32).reshape(-1).contiguous()
+                with torch.cuda.device(self.device):
+                    ops.gather_attention_add(q, self.caption_index.matrix, rows, w, bb, out)
+            return out.to(src_device)
         src_device = image_embeddings.device
         q = image_embeddings.to(device=self.device, dtype=torch.float32).contiguous()
         rows = self.retrieve_rows(q, top_i, top_k)

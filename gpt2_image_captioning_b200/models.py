@@ -229,9 +229,10 @@ class RetrievalAugmentedTransformer(ImageCaptioningModel):
             raise TypeError("db_store must be a gpt2_image_captioning_b200.database.GpuFlatStore (build one with "
                             "GpuFlatStore.from_faiss_store(store) or GpuFlatStore(image_matrix, caption_matrix, ...))")
         kind = self.aggregator.aggregation_type
-        if kind == "attention":  # learned pooling: gather on the GPU store, pool in PyTorch
-            retrieved = db_store.retrieve_caption_embeddings(image_embeddings, top_i=top_i, top_k=top_k)
-            return self.aggregator(image_embeddings.to(retrieved.device), retrieved).to(image_embeddings.device)
+        if kind == "attention":  # learned pooling (src/models.py:606-616), fused with the gather like the other modes
+            proj = self.aggregator.attention_proj
+            return db_store.retrieve_and_aggregate(image_embeddings, top_i=top_i, top_k=top_k, aggregation=kind,
+                                                   attention_weight=proj.weight, attention_bias=proj.bias)
         return db_store.retrieve_and_aggregate(image_embeddings, top_i=top_i, top_k=top_k, aggregation=kind)
 
     def _retrieve_batch(self, db_store, image_embeddings: torch.Tensor, top_i: int, top_k: int) -> torch.Tensor:

@@ -108,6 +108,15 @@ def select_caption_rows(scores: torch.Tensor, idx: torch.Tensor, cap_row_start: 
                                           _ptr(cap_row_ids), top_i, top_k, _ptr(rows_out), _stream()))
 
 
+@torch.library.custom_op("gic::gather_attention_add", mutates_args=("out",))
+def gather_attention_add(queries: torch.Tensor, cap_db: torch.Tensor, rows: torch.Tensor, attn_w: torch.Tensor, attn_b: torch.Tensor,
+                         out: torch.Tensor) -> None:
+    _need_cuda(queries, cap_db, rows, attn_w, attn_b, out)
+    L = _capi.lib()
+    _capi.check(L.gic_gather_attention_add(_ptr(queries), _ptr(cap_db), _ptr(rows), queries.shape[0], rows.shape[1], queries.shape[1],
+                                           _ptr(attn_w), _ptr(attn_b), _ptr(out), _stream()))
+
+
 @torch.library.custom_op("gic::gather_aggregate_add", mutates_args=("out",))
 def gather_aggregate_add(queries: torch.Tensor, cap_db: torch.Tensor, rows: torch.Tensor, aggregation: int, out: torch.Tensor) -> None:
     _need_cuda(queries, cap_db, rows, out)

@@ -185,6 +185,10 @@ GIC_API int gic_select_caption_rows(const float* scores, const int64_t* idx, int
  * src/models.py:589-625): out[b] = q[b] + agg_k(cap_db[rows[b,k]]) with zero rows for -1 (padding counts in the mean). */
 GIC_API int gic_gather_aggregate_add(const float* queries, const float* cap_db, const int64_t* rows, int batch, int top_k, int dim,
                              int aggregation, float* out, void* stream);
+/* the "attention" pooling of RetrievalAggregator (src/models.py:606-616): weights = softmax_k(attention_proj(r_k)), out[b] = q[b] + sum_k
+ * weights_k r_k over the gathered rows (zero rows for -1: their score is the bias).  attn_w dev fp32 [dim], attn_b dev fp32 [1]. */
+GIC_API int gic_gather_attention_add(const float* queries, const float* cap_db, const int64_t* rows, int batch, int top_k, int dim,
+                                     const float* attn_w, const float* attn_b, float* out, void* stream);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------------------ */
 /* kernels launched by this library in this process so far (CUDA-graph replays count their kernel nodes) */

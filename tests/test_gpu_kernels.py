@@ -402,6 +402,12 @@ def test_retrieval_against_reference_fixture():
     want_sn = q + torch.nn.functional.normalize(torch.nn.functional.normalize(ret, p=2, dim=2).sum(dim=1), p=2, dim=1)
     np.testing.assert_allclose(store.retrieve_and_aggregate(q, 4, 10, "max").numpy(), want_max.numpy(), atol=1e-6)
     np.testing.assert_allclose(store.retrieve_and_aggregate(q, 4, 10, "sum_norm").numpy(), want_sn.numpy(), atol=2e-6)
+    proj = torch.nn.Linear(512, 1)
+    torch.nn.init.normal_(proj.weight, std=0.5)
+    want_at = q + (ret * torch.softmax(proj(ret), dim=1)).sum(dim=1)
+    got_at = store.retrieve_and_aggregate(q, 4, 10, "attention", attention_weight=proj.weight, attention_bias=proj.bias)
+    # (scores w . r are O(10) here -- unnormalised rows, std-0.5 weights -- so fp32 summation order moves the softmax weights by ~1e-6)
+    np.testing.assert_allclose(got_at.numpy(), want_at.detach().numpy(), atol=2e-5)
     # duck-typed faiss surface
     s, ix = store.image_index.search(g["q"][:3], 14)
     assert s.shape == (3, 14) and ix.dtype == np.int64
