@@ -71,6 +71,7 @@ struct Workspace {
   int64_t* ids = nullptr;          // [rows, max_new]
   unsigned char* finished = nullptr; int* first_eos = nullptr;
   int *d_step = nullptr, *d_pos = nullptr, *done_counter = nullptr;
+  int *fin_counter = nullptr, *all_done = nullptr;  // [sub-batch] rows finished in the current step / every row has emitted EOS
   // beam search only
   void* kv2 = nullptr;             // second KV cache (reorder target; the two swap every step); null with the ancestry table
   const int* anc = nullptr; int anc_ld = 0;  // beam search without reordering: ancestry table of the current step (see attention.cu)
@@ -112,6 +113,9 @@ struct gic_engine {
   void* graph_ws = nullptr; int graph_B = 0, graph_max_new = 0;
   bool use_graph = true;
   int graph_nodes = 0, graph_steps = 1;  // kernel nodes / decode steps held by graph_exec
+  // early exit (src/models.py:390-391): the host looks at the `all rows finished` flag of chunk c - 1 while chunk c runs
+  int* h_done = nullptr;  // pinned [2]
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
   // all generate work runs on this private stream (the caller's stream may be the legacy default stream, which cannot
   // be captured into a graph); it is forked from / joined to the caller's stream with events
   cudaStream_t stream = nullptr;
@@ -305,6 +309,8 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
   w->d_step = c.take<int>(gic_engine::MAX_SUB);  // [sub-batch]
   w->d_pos = c.take<int>(gic_engine::MAX_SUB);
   w->done_counter = c.take<int>(gic_engine::MAX_SUB);
+  w->fin_counter = c.take<int>(gic_engine::MAX_SUB);
+  w->all_done = c.take<int>(gic_engine::MAX_SUB);
   w->bytes = align_up(c.off, 1024) + 1024;
 }
 
@@ -470,7 +476,7 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
   FinalizeArgs fa;
   fa.part_val = w.part_val; fa.part_idx = w.part_idx; fa.n_parts = n_parts; fa.part_ld = w.n_parts_max;
   fa.B = rows; fa.d = d; fa.eos = e->cfg.eos_token_id; fa.max_new = w.max_new; fa.P = w.P; fa.n_pos = e->cfg.n_positions;
-  fa.d_step = w.d_step; fa.d_pos = w.d_pos; fa.done_counter = w.done_counter;
+  fa.d_step = w.d_step; fa.d_pos = w.d_pos; fa.done_counter = w.done_counter; fa.fin_counter = w.fin_counter; fa.all_done = w.all_done;
   fa.finished = w.finished; fa.first_eos = w.first_eos; fa.ids_out = w.ids;
   fa.wte_f32 = e->wte_f32; fa.wte_bf16 = e->wte_f32 ? nullptr : e->wte_gather;
   fa.wpe = e->wpe; fa.h_next = w.h_dec;
@@ -506,7 +512,7 @@ static Workspace slice_rows(const gic_engine* e, const Workspace& w, int row0, i
   s.part_idx += (size_t)w.n_parts_max * row0;
   s.ids += (size_t)row0 * w.max_new;
   s.finished += row0; s.first_eos += row0;
-  s.d_step += sub; s.d_pos += sub; s.done_counter += sub;
+  s.d_step += sub; s.d_pos += sub; s.done_counter += sub; s.fin_counter += sub; s.all_done += sub;
   return s;
 }
 
@@ -669,6 +675,9 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
             cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&e->h_done, 2 * sizeof(int), cudaHostAllocDefault) == cudaSuccess &&
+       cudaEventCreateWithFlags(&e->ev_done[0], cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&e->ev_done[1], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 1; i < gic_engine::MAX_SUB && ok; ++i)
     ok = cudaStreamCreateWithFlags(&e->sub_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
@@ -689,6 +698,8 @@ int gic_engine_destroy(gic_engine* e) {
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  for (int i = 0; i < 2; ++i) if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]);
+  if (e->h_done) cudaFreeHost(e->h_done);
   for (int i = 1; i < gic_engine::MAX_SUB; ++i) {
     if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
     if (e->sub_stream[i]) cudaStreamDestroy(e->sub_stream[i]);
@@ -825,7 +836,8 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   const int d = e->d, B = batch, P = w.P;
   GIC_TRY(fork_stream(e, user));
 
-  GIC_TRY(launch_init_decode_state(w.finished, w.first_eos, B, max_new, w.d_step, w.d_pos, w.done_counter, P, st));
+  GIC_TRY(launch_init_decode_state(w.finished, w.first_eos, B, max_new, w.d_step, w.d_pos, w.done_counter, P, w.fin_counter, w.all_done, w.ids,
+                                   e->cfg.eos_token_id, st));
   if (w.splitk_counters) GIC_CHECK_CUDA(cudaMemsetAsync(w.splitk_counters, 0, 4096 * sizeof(int), st));
   if (e->profiling) GIC_TRY(launch_spin(150000000LL, st));  // ~75 ms: lets the host queue ahead so events time the device only
   { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
@@ -836,36 +848,61 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   // only the last position feeds the LM head (the reference computes all positions and keeps [:, -1, :], src/models.py:398)
   GIC_TRY(lm_head_and_token(e, w, w.h, (long)(P - 1) * d, (long)P * d, B, B * P, logits_out, st));
 
-  // ---- decode: max_new-1 identical steps; positions / step index live on the device ----
+  // ---- decode: max_new-1 identical steps; positions / step index live on the device.  They run in chunks of DECODE_CHUNK steps
+  // (one CUDA graph per chunk); while chunk c runs the host reads chunk c-1's "every row has emitted EOS" flag and stops
+  // launching once it is set -- the reference's `if is_finished.all(): break` (src/models.py:390-391) without a per-step sync.
+  // Random-init weights never emit EOS, so the headline benchmark runs every chunk. ----
   const int steps = max_new - 1;
+  constexpr int DECODE_CHUNK = 4;
   const bool graph_ok = e->use_graph && !e->profiling && logits_out == nullptr && steps >= 2;
-  if (!graph_ok) {
-    for (int s = 1; s <= steps; ++s)  // (sampling reuses one [B, V] buffer; the parity tap keeps every step's logits)
-      GIC_TRY(decode_step_all(e, w, logits_out ? (e->sample.on ? logits_out : logits_out + (size_t)s * B * e->V) : nullptr, st));
-  } else {
-    if (!(e->graph_exec && e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new)) {
-      if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
-      cudaGraph_t graph = nullptr;
-      const unsigned long long before = g_launches;
-      // all max_new - 1 steps in ONE graph (GIC_GRAPH_PER_STEP=1: one step per graph, replayed): no launch gap and an unbroken
-      // programmatic-dependent-launch chain between the finalize of step s and the first GEMM of step s + 1
-      static const bool per_step = [] { const char* v = getenv("GIC_GRAPH_PER_STEP"); return v && v[0] == '1'; }();
-      e->graph_steps = per_step ? 1 : steps;
-      GIC_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      int r = GIC_OK;
-      for (int s = 0; s < e->graph_steps && r == GIC_OK; ++s) r = decode_step_all(e, w, nullptr, st);
-      cudaError_t ce = cudaStreamEndCapture(st, &graph);
-      e->graph_nodes = (int)(g_launches - before);  // captured, not executed
-      g_launches = before;
-      if (r != GIC_OK) { if (graph) cudaGraphDestroy(graph); return r; }
-      GIC_CHECK_CUDA(ce);
-      ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
-      cudaGraphDestroy(graph);
-      GIC_CHECK_CUDA(ce);
-      e->graph_ws = workspace; e->graph_B = B; e->graph_max_new = max_new;
+  static const bool per_step = [] { const char* v = getenv("GIC_GRAPH_PER_STEP"); return v && v[0] == '1'; }();
+  const char* ne = getenv("GIC_NO_EARLY_EXIT");  // (read per call: a test flips it inside one process)
+  const bool no_early = ne && ne[0] == '1';
+  const bool early = !no_early && e->sub_batches < 2 && !(logits_out && !e->sample.on) && e->h_done != nullptr;
+  const int chunk = (graph_ok && per_step) ? 1 : (early ? DECODE_CHUNK : (graph_ok ? steps : DECODE_CHUNK));
+  auto eager_step = [&](int s) {
+    return decode_step_all(e, w, logits_out ? (e->sample.on ? logits_out : logits_out + (size_t)s * B * e->V) : nullptr, st);
+  };
+  int s_next = 1;  // next decode step (1-based, as the logits tap is indexed)
+  // the steps that do not fill a whole chunk go first, as ordinary launches (the host is far ahead of the device after prefill)
+  const int lead = graph_ok ? steps % chunk : 0;
+  for (; s_next <= lead; ++s_next) GIC_TRY(eager_step(s_next));
+  if (graph_ok && steps - lead > 0 &&
+      !(e->graph_exec && e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new && e->graph_steps == chunk)) {
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    const unsigned long long before = g_launches;
+    e->graph_steps = chunk;
+    GIC_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int r = GIC_OK;
+    for (int s = 0; s < chunk && r == GIC_OK; ++s) r = decode_step_all(e, w, nullptr, st);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    e->graph_nodes = (int)(g_launches - before);  // captured, not executed
+    g_launches = before;
+    if (r != GIC_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+    GIC_CHECK_CUDA(ce);
+    ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    GIC_CHECK_CUDA(ce);
+    e->graph_ws = workspace; e->graph_B = B; e->graph_max_new = max_new;
+  }
+  for (int c = 0; s_next <= steps; ++c) {
+    const int n = steps - s_next + 1 < chunk ? steps - s_next + 1 : chunk;
+    if (graph_ok) {
+      GIC_CHECK_CUDA(cudaGraphLaunch(e->graph_exec, st));
+      g_launches += (unsigned long long)e->graph_nodes;
+    } else {
+      for (int i = 0; i < n; ++i) GIC_TRY(eager_step(s_next + i));
     }
-    for (int s = 0; s < steps; s += e->graph_steps) GIC_CHECK_CUDA(cudaGraphLaunch(e->graph_exec, st));
-    g_launches += (unsigned long long)e->graph_nodes * (steps / e->graph_steps);
+    s_next += n;
+    if (early && s_next <= steps) {
+      GIC_CHECK_CUDA(cudaMemcpyAsync(e->h_done + (c & 1), w.all_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+      GIC_CHECK_CUDA(cudaEventRecord(e->ev_done[c & 1], st));
+      if (c >= 1) {
+        GIC_CHECK_CUDA(cudaEventSynchronize(e->ev_done[(c - 1) & 1]));
+        if (e->h_done[(c - 1) & 1]) break;  // (chunk c is already queued: at most one chunk runs past the end)
+      }
+    }
   }
   GIC_CHECK_CUDA(cudaMemcpyAsync(ids_out, w.ids, (size_t)B * max_new * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   if (gen_len_out) GIC_TRY(launch_gen_len(w.first_eos, B, max_new, gen_len_out, st));

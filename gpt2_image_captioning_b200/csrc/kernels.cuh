@@ -115,6 +115,7 @@ struct FinalizeArgs {
   int* d_step;              // device scalar: index of the token being produced; advanced by the kernel
   int* d_pos;               // device scalar: KV position of the token fed to the next decode step
   int* done_counter;        // device scalar used to elect the last block
+  int* fin_counter = nullptr; int* all_done = nullptr;  // optional: rows finished this step / set to 1 once every row has emitted EOS
   unsigned char* finished;  // [B]
   int* first_eos;           // [B]; max_new = never
   int64_t* ids_out;         // [B, max_new]
@@ -130,7 +131,7 @@ int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st);
 int launch_sample_top_p(const float* logits, int B, int V, float temperature, float top_p, unsigned long long seed, const int* d_step,
                         int step_override, float* part_val, int* part_idx, int part_ld, cudaStream_t st);
 int launch_init_decode_state(unsigned char* finished, int* first_eos, int B, int max_new, int* d_step, int* d_pos, int* done_counter,
-                             int P, cudaStream_t st);
+                             int P, int* fin_counter, int* all_done, int64_t* ids, int eos, cudaStream_t st);
 int launch_gen_len(const int* first_eos, int B, int max_new, int* gen_len_out, cudaStream_t st);
 int launch_spin(long long cycles, cudaStream_t st);  // profiling aid (see lmhead.cu)
 

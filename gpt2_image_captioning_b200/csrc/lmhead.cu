@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
     if (fin) tok = a.eos;  // :458-460
     a.ids_out[(size_t)b * a.max_new + step] = (int64_t)tok;
     s_tok = tok;
+    if (fin && a.fin_counter) atomicAdd(a.fin_counter, 1);  // rows finished after this step (for the host's early exit)
   }
   __syncthreads();
   const int tok = s_tok;
@@ -273,6 +274,10 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
       *a.done_counter = 0;
       *a.d_pos = pos;
       *a.d_step = step + 1;
+      if (a.fin_counter) {  // every row has emitted EOS: the reference loop would stop before the next step (src/models.py:390-391)
+        const int nf = atomicExch(a.fin_counter, 0);
+        if (nf == (int)gridDim.x) *a.all_done = 1;
+      }
     }
   }
 }
@@ -284,12 +289,15 @@ int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st) {
 }
 
 __global__ void init_decode_state_kernel(unsigned char* finished, int* first_eos, int B, int max_new, int* d_step, int* d_pos,
-                                         int* done_counter, int P) {
+                                         int* done_counter, int P, int* fin_counter, int* all_done, int64_t* ids, int eos) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
     finished[i] = 0;
     first_eos[i] = max_new;
   }
+  // steps that are never run (every row finished early) read as EOS, what the rows would have kept emitting (:458-460)
+  for (size_t j = i; j < (size_t)B * max_new; j += (size_t)gridDim.x * blockDim.x) ids[j] = (int64_t)eos;
+  if (i < 8) { fin_counter[i] = 0; all_done[i] = 0; }
   if (i == 0) {
     // counter set 0: the whole batch through prefill and token 0, then the first row group; sets 1..7: the other row groups,
     // which start decoding at step 1 with their input token at position P
@@ -299,8 +307,9 @@ __global__ void init_decode_state_kernel(unsigned char* finished, int* first_eos
 }
 
 int launch_init_decode_state(unsigned char* finished, int* first_eos, int B, int max_new, int* d_step, int* d_pos, int* done_counter,
-                             int P, cudaStream_t st) {
-  init_decode_state_kernel<<<ceil_div(B, 256), 256, 0, st>>>(finished, first_eos, B, max_new, d_step, d_pos, done_counter, P);
+                             int P, int* fin_counter, int* all_done, int64_t* ids, int eos, cudaStream_t st) {
+  init_decode_state_kernel<<<ceil_div(B, 256), 256, 0, st>>>(finished, first_eos, B, max_new, d_step, d_pos, done_counter, P, fin_counter, all_done, ids,
+                                                             eos);
   GIC_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return GIC_OK;

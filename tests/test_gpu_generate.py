@@ -331,3 +331,33 @@ def test_sampling_path_behaviour(dtype):
     greedy = model.generate(image_embeddings=xx, max_length=12, temperature=0.0)
     cold = model.generate(image_embeddings=xx, max_length=12, temperature=1e-3, top_p=0.5)
     assert torch.equal(greedy, cold)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_early_exit_once_every_row_has_finished(monkeypatch, dtype):
+    """The reference loop stops before a step once every row has emitted EOS (src/models.py:390-391).  The engine runs the decode
+    steps in chunks and stops launching them when the device reports that state: same tokens and L_gen as running every step
+    (GIC_NO_EARLY_EXIT=1), with fewer kernel launches."""
+    from gpt2_image_captioning_b200 import CaptionEngine
+    g = gu.load("tiny_mlp_eos")
+    model, oracle, x = gpu_util.product_model(g, dtype)
+    pool = oc.synthetic_embeddings(96, int(x.shape[1]), seed=5)
+    eos = int(g.get("eos", oc.EOS_TOKEN_ID))
+    all_ids = oracle.generate(pool, 48, kv_cache=True)
+    early_rows = [i for i, row in enumerate(all_ids.tolist()) if eos in row[:20]]
+    assert len(early_rows) >= 8, "the EOS fixture is expected to finish a good share of its rows early"
+    xx = pool[early_rows[:24]]
+    want = oracle.generate(xx, 48, kv_cache=True)
+    assert want.shape[1] <= 20
+    n0 = CaptionEngine.launch_count()
+    a = model.generate(image_embeddings=xx.to(DEV), max_length=48, temperature=0.0).cpu()
+    n1 = CaptionEngine.launch_count()
+    monkeypatch.setenv("GIC_NO_EARLY_EXIT", "1")
+    model2, _, _ = gpu_util.product_model(g, dtype)
+    m0 = CaptionEngine.launch_count()
+    b = model2.generate(image_embeddings=xx.to(DEV), max_length=48, temperature=0.0).cpu()
+    m1 = CaptionEngine.launch_count()
+    assert torch.equal(a, b)
+    if dtype == "fp32":
+        assert torch.equal(a, want)
+    assert (n1 - n0) < (m1 - m0), (n1 - n0, m1 - m0)
