@@ -23,6 +23,7 @@
 
 namespace gic {
 
+
 constexpr int HD = 64;  // GPT-2 head_dim (small/medium/large: n_embd / n_head = 64)
 
 template <typename T>
@@ -398,7 +399,7 @@ struct DecMmaCfg { static constexpr int SMEM_BYTES = WARPS * STAGES * MMA_STAGE_
 // DynamicCache.reorder_cache (HF:cache_utils.py:81-85), a 2 x 28 GB gather per step at config 3.
 template <int WARPS, int STAGES, bool INDIRECT>
 __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos,
-                                                                      int rows, int H, int t_max, const int* anc, int anc_ld, int n_prefix, int beams) {
+                                                                      int rows, int H, int t_max, const int* anc, int anc_ld, int n_prefix, int beams, StepTrace step_trace) {
   extern __shared__ uint8_t dec_smem_raw[];
   const uint32_t smem_base = (dec_smem_u32(dec_smem_raw) + 127u) & ~127u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes above before the bulk copies into the same bytes
   __syncwarp();
   pdl_wait();
+  const int tslot = trace_begin(step_trace, TRACE_ATTN_DECODE, 0);
   const int pos = __ldcg(d_pos);  // tokens already cached == position of the new token
   const int d = H * HD;
   const int n_items = rows * H;
@@ -587,6 +589,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
     // out row of the item = item * 64 elements (row * d + head * 64): dims 8 g + 2 t, + 1 -> one 128-byte row per warp
     *reinterpret_cast<uint32_t*>(out + (size_t)item * HD + 8 * g + 2 * t) = pack_bf16x2(o[0][0] * inv, o[0][1] * inv);
   }
+  trace_end(step_trace, tslot);
 }
 
 static int g_dec_sms = 0;
@@ -633,7 +636,7 @@ static int launch_attn_decode_bulk(const bf16* qkv, bf16* kcache, bf16* vcache, 
   if (g_dec_variant == ID) {                                                                                                         \
     const int grid = min(sms, ceil_div(items, W));                                                                                   \
     GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<W, S, false>, dim3(grid), dim3(W * 32), (size_t)DecMmaCfg<W, S>::SMEM_BYTES, st, qkv, kcache, \
-                                 vcache, out, d_pos, rows, H, t_max, (const int*)nullptr, 0, 0, 1));                                 \
+                                 vcache, out, d_pos, rows, H, t_max, (const int*)nullptr, 0, 0, 1, trace_desc()));                                 \
     note_launch();                                                                                                                   \
     return GIC_OK;                                                                                                                   \
   }
@@ -651,7 +654,7 @@ int launch_attn_decode_indirect(const bf16* qkv, bf16* kcache, bf16* vcache, bf1
   const int sms = cta_limit() > 0 && cta_limit() < g_dec_sms ? cta_limit() : g_dec_sms;
   const int grid = min(sms, ceil_div(rows * H, 12));
   GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<12, 4, true>, dim3(grid), dim3(12 * 32), (size_t)DecMmaCfg<12, 4>::SMEM_BYTES, st, qkv, kcache, vcache,
-                               out, d_pos, rows, H, t_max, anc, anc_ld, n_prefix, beams));
+                               out, d_pos, rows, H, t_max, anc, anc_ld, n_prefix, beams, trace_desc()));
   note_launch();
   return GIC_OK;
 }

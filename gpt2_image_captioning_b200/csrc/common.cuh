@@ -12,7 +12,11 @@ namespace gic {
 // ---- error plumbing: never throw across the C ABI; record a message, return a code --------------
 void set_error(const char* fmt, ...);
 const char* get_error();
-void note_launch();  // every kernel launch of the library reports here (gic_launch_count)
+void note_launch();
+struct StepTrace;
+StepTrace trace_desc();             // descriptor for the NEXT launch (a fresh slot per call; null buffer: off), passed to the kernel by value
+bool trace_on();
+unsigned int trace_generation();   // bumped by every install: a captured graph holds the descriptor it was captured with  // every kernel launch of the library reports here (gic_launch_count)
 
 #define GIC_CHECK_CUDA(expr)                                                                  \
   do {                                                                                        \
@@ -68,6 +72,29 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 typedef __nv_bfloat16 bf16;
+
+// ---- in-situ step timeline (tools/step_timeline.py) ---------------------------------------------------------------
+// Thread 0 of EVERY block of the decode-step kernels stamps %globaltimer after griddepcontrol.wait and at its end; the launch's
+// record (kind, begin_ns = min over blocks, end_ns = max over blocks) lives in slot `slot` of a device buffer, the slot being
+// handed out by the host per launch (trace_desc(): null buffer = tracing off, the launch carries a null pointer and pays
+// nothing).  The tool pre-fills begin with ~0 and end with 0.  A captured graph keeps the slots it was captured with, so the
+// traced run captures all decode steps into one graph.
+struct StepTrace { unsigned long long* buf; unsigned int slot; unsigned int cap; };
+enum TraceKind { TRACE_GEMM = 1, TRACE_ATTN_DECODE = 2, TRACE_LAYERNORM = 3, TRACE_FINALIZE = 4, TRACE_ATTN_PREFILL = 5 };
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) : : "memory");  // (memory clobber: must not drift across barriers / waits)
+  return t;
+}
+__device__ __forceinline__ int trace_begin(const StepTrace& tr, int kind, int detail) {
+  if (threadIdx.x != 0 || tr.buf == nullptr || tr.slot >= tr.cap) return -1;
+  if (blockIdx.x == 0) tr.buf[3 * tr.slot] = ((unsigned long long)(unsigned int)detail << 8) | (unsigned long long)kind;
+  atomicMin(tr.buf + 3 * tr.slot + 1, globaltimer_ns());
+  return (int)tr.slot;
+}
+__device__ __forceinline__ void trace_end(const StepTrace& tr, int slot) {
+  if (slot >= 0) atomicMax(tr.buf + 3 * slot + 2, globaltimer_ns());
+}
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }

@@ -4,6 +4,7 @@
 
 namespace gic {
 
+
 // ---------------------------------------------------------------------------------------------------------------
 // LayerNorm (nn.LayerNorm, eps 1e-5, biased variance): ln_1 / ln_2 / ln_f of HF GPT2Block
 // (HF:models/gpt2/modeling_gpt2.py:273,304,628) and norm1/norm2 of nn.TransformerEncoderLayer.
@@ -11,12 +12,13 @@ namespace gic {
 // ---------------------------------------------------------------------------------------------------------------
 template <int MAXV>
 __global__ void __launch_bounds__(128) layernorm_kernel(const float* x, long x_row_stride, const float* __restrict__ w,
-                                                        const float* __restrict__ b, ActOut y, int rows, int d) {
+                                                        const float* __restrict__ b, ActOut y, int rows, int d, StepTrace step_trace) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents();
   if (warp >= rows) return;
   pdl_wait();
+  const int tslot = trace_begin(step_trace, TRACE_LAYERNORM, 0);
   const float* xr = x + (size_t)warp * x_row_stride;
   // every load (row, gamma, beta) is issued before the first store: the output pointers may alias as far as the compiler
   // knows, and interleaving loads with stores serialises one memory round trip per element (ncu: 25 k cycles per warp)
@@ -48,13 +50,14 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const float* x, long x_r
     const int c = lane + i * 32;
     if (c < d) y.write((size_t)warp * d + c, v[i]);
   }
+  trace_end(step_trace, tslot);
 }
 
 int launch_layernorm(const float* x, long x_row_stride, const float* w, const float* b, ActOut y, int rows, int d, cudaStream_t st) {
   GIC_REQUIRE(rows > 0 && d > 0 && d <= 32 * 40, "layernorm: unsupported rows=%d d=%d (d <= 1280)", rows, d);
   const int blocks = ceil_div(rows, 4);
   auto kern = d <= 32 * 4 ? layernorm_kernel<4> : d <= 32 * 24 ? layernorm_kernel<24> : d <= 32 * 32 ? layernorm_kernel<32> : layernorm_kernel<40>;
-  GIC_CHECK_CUDA(launch_kernel(kern, dim3(blocks), dim3(128), 0, st, x, x_row_stride, w, b, y, rows, d));
+  GIC_CHECK_CUDA(launch_kernel(kern, dim3(blocks), dim3(128), 0, st, x, x_row_stride, w, b, y, rows, d, trace_desc()));
   note_launch();
   return GIC_OK;
 }

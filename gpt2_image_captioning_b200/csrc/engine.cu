@@ -113,6 +113,7 @@ struct gic_engine {
   void* graph_ws = nullptr; int graph_B = 0, graph_max_new = 0;
   bool use_graph = true;
   int graph_nodes = 0, graph_steps = 1;  // kernel nodes / decode steps held by graph_exec
+  unsigned int graph_trace_gen = 0;        // trace_generation() the graph was captured under
   // early exit (src/models.py:390-391): the host looks at the `all rows finished` flag of chunk c - 1 while chunk c runs
   int* h_done = nullptr;  // pinned [2]
   cudaEvent_t ev_done[2] = {nullptr, nullptr};
@@ -135,6 +136,16 @@ struct gic_engine {
 };
 
 namespace gic {
+
+static StepTrace g_step_trace = {nullptr, 0, 0};
+static unsigned int g_trace_gen = 0;
+StepTrace trace_desc() {
+  StepTrace t = g_step_trace;
+  if (t.buf) ++g_step_trace.slot;  // one slot per launch
+  return t;
+}
+bool trace_on() { return g_step_trace.buf != nullptr; }
+unsigned int trace_generation() { return g_trace_gen; }
 
 static thread_local int g_cta_limit = 0;
 int cta_limit() { return g_cta_limit; }
@@ -858,7 +869,8 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   static const bool per_step = [] { const char* v = getenv("GIC_GRAPH_PER_STEP"); return v && v[0] == '1'; }();
   const char* ne = getenv("GIC_NO_EARLY_EXIT");  // (read per call: a test flips it inside one process)
   const bool no_early = ne && ne[0] == '1';
-  const bool early = !no_early && e->sub_batches < 2 && !(logits_out && !e->sample.on) && e->h_done != nullptr;
+  // (a traced run keeps one record per launch: one graph holding every step, no replays)
+  const bool early = !no_early && !gic::trace_on() && e->sub_batches < 2 && !(logits_out && !e->sample.on) && e->h_done != nullptr;
   const int chunk = (graph_ok && per_step) ? 1 : (early ? DECODE_CHUNK : (graph_ok ? steps : DECODE_CHUNK));
   auto eager_step = [&](int s) {
     return decode_step_all(e, w, logits_out ? (e->sample.on ? logits_out : logits_out + (size_t)s * B * e->V) : nullptr, st);
@@ -868,7 +880,7 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   const int lead = graph_ok ? steps % chunk : 0;
   for (; s_next <= lead; ++s_next) GIC_TRY(eager_step(s_next));
   if (graph_ok && steps - lead > 0 &&
-      !(e->graph_exec && e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new && e->graph_steps == chunk)) {
+      !(e->graph_exec && e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new && e->graph_steps == chunk && e->graph_trace_gen == gic::trace_generation())) {
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
     const unsigned long long before = g_launches;
@@ -884,7 +896,7 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
     ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
     cudaGraphDestroy(graph);
     GIC_CHECK_CUDA(ce);
-    e->graph_ws = workspace; e->graph_B = B; e->graph_max_new = max_new;
+    e->graph_ws = workspace; e->graph_B = B; e->graph_max_new = max_new; e->graph_trace_gen = gic::trace_generation();
   }
   for (int c = 0; s_next <= steps; ++c) {
     const int n = steps - s_next + 1 < chunk ? steps - s_next + 1 : chunk;
@@ -1238,6 +1250,16 @@ int gic_test_sample_top_p(const float* logits, int B, int V, float temperature, 
   cudaFree(pv);
   if (r != GIC_OK) return r;
   GIC_CHECK_CUDA(ce);
+  return GIC_OK;
+}
+
+// in-situ timeline of the decode-step kernels (tools/step_timeline.py): install a device buffer of `cap` (kind, begin_ns, end_ns) uint64
+// records, pre-filled with (0, ~0, 0); every GEMM / decode attention / ln_f / finalize launch takes the next record.  buf = NULL uninstalls.
+int gic_trace_install(void* buf, unsigned int cap) {
+  gic::g_step_trace.buf = (unsigned long long*)buf;
+  gic::g_step_trace.slot = 0;
+  gic::g_step_trace.cap = buf ? cap : 0;
+  ++gic::g_trace_gen;  // graphs captured under the previous descriptor are re-captured
   return GIC_OK;
 }
 

@@ -34,6 +34,7 @@
 
 namespace gic {
 
+
 // ---------------------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------------------------
@@ -223,6 +224,7 @@ struct alignas(64) GemmKernelParams {
   // [split_k][M][N] and the CTA that arrives last at splitk_counters[tile] sums them in split order and runs the epilogue
   int split_k; float* splitk_ws; int* splitk_counters;
   int w_static;  // W may be fetched before griddepcontrol.wait (see the kernel)
+  StepTrace step_trace;  // in-situ timeline (common.cuh); null buffer = off
   float2* stats_out;  // [ceil(N / 32)][ln_stats_ld] (sum, sum of squares) of the values written, per row and 32-column chunk
   long long* trace;  // null; microbenchmark only: clock64 timeline of CTA 0's producer / MMA / epilogue warps
 };
@@ -357,6 +359,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     __syncwarp();
   }
   pdl_wait();  // prologue above overlapped the previous kernel; its outputs are visible from here on
+  const int tslot = trace_begin(p.step_trace, TRACE_GEMM, (BLOCK_N << 4) | (EPI << 1) | (PAIR ? 1 : 0));
 
   if (warp == 0) {
     // ===== TMA producer: streams k-blocks of successive tiles through the ring without pausing at tile boundaries =====
@@ -925,6 +928,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
 
   ptx::tc_fence_before();
   __syncthreads();
+  trace_end(p.step_trace, tslot);
   if (PAIR) ptx::cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the pair's MMAs / remote arrivals may still touch it
   if (warp == 1) {
     if (PAIR) ptx::tmem_dealloc_pair(tmem_base, Tile::TMEM_COLS);
@@ -1200,6 +1204,7 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   kp.ln_colsum = a.ln_colsum; kp.stats_out = a.stats_out;
   kp.split_k = a.split_k < 1 ? 1 : a.split_k; kp.splitk_ws = a.splitk_ws; kp.splitk_counters = a.splitk_counters;
   kp.w_static = a.w_static;
+  kp.step_trace = trace_desc();
   GIC_REQUIRE(!a.ln_stats || (a.ln_colsum && a.ln_parts > 0), "gemm_bf16: folded LayerNorm needs the column sums and at least one statistics part");
   int epi = a.epilogue;
   if (a.part_val) {

@@ -115,6 +115,7 @@ struct FinalizeArgs {
   int* d_step;              // device scalar: index of the token being produced; advanced by the kernel
   int* d_pos;               // device scalar: KV position of the token fed to the next decode step
   int* done_counter;        // device scalar used to elect the last block
+  StepTrace step_trace = {nullptr, 0, 0};  // filled by launch_finalize_token
   int* fin_counter = nullptr; int* all_done = nullptr;  // optional: rows finished this step / set to 1 once every row has emitted EOS
   unsigned char* finished;  // [B]
   int* first_eos;           // [B]; max_new = never

@@ -7,6 +7,7 @@
 
 namespace gic {
 
+
 __device__ __forceinline__ bool better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }
 
 __device__ __forceinline__ void block_argmax(float& v, int& idx, float* sv, int* si) {
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
   const int b = blockIdx.x;
   pdl_launch_dependents();
   pdl_wait();
+  const int tslot = trace_begin(a.step_trace, TRACE_FINALIZE, 0);
   const int step = __ldcg(a.d_step);
   float v = -INFINITY;
   int idx = 0x7fffffff;
@@ -279,10 +281,12 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
         if (nf == (int)gridDim.x) *a.all_done = 1;
       }
     }
-  }
+  }  trace_end(a.step_trace, tslot);
 }
 
-int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st) {
+int launch_finalize_token(const FinalizeArgs& a0, cudaStream_t st) {
+  FinalizeArgs a = a0;
+  a.step_trace = trace_desc();
   GIC_CHECK_CUDA(launch_kernel(finalize_token_kernel, dim3(a.B), dim3(128), 0, st, a));
   note_launch();
   return GIC_OK;

@@ -24,6 +24,9 @@ static thread_local char g_err[1024] = "";
 void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap); }
 const char* get_error() { return g_err; }
 void note_launch() {}
+StepTrace trace_desc() { return StepTrace{nullptr, 0, 0}; }
+bool trace_on() { return false; }
+unsigned int trace_generation() { return 0; }
 static int g_cta_limit = 0;
 int cta_limit() { return g_cta_limit; }
 void set_cta_limit(int c) { g_cta_limit = c; }

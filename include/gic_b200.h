@@ -217,6 +217,10 @@ GIC_API int gic_test_attn_prefill(const void* qkv, void* kcache, void* vcache, v
 /* one sampling launch on caller data: logits dev fp32 [B, V] -> tokens dev int32 [B] (src/models.py:400-449) */
 GIC_API int gic_test_sample_top_p(const float* logits, int B, int V, float temperature, float top_p, unsigned long long seed, int step,
                                   int32_t* tokens_out, void* stream);
+/* in-situ timeline: every GEMM / decode-attention / ln_f / finalize launch takes the next record of buf (dev uint64 [3 * cap], pre-filled
+ * with (0, ~0, 0)): kind | detail << 8, begin_ns = min over its blocks of %globaltimer after griddepcontrol.wait, end_ns = max over its
+ * blocks at their end.  While installed, generate captures all decode steps into one graph.  buf = NULL: off. */
+GIC_API int gic_trace_install(void* buf, unsigned int cap);
 GIC_API int gic_test_layernorm(const float* x, const float* w, const float* b, float* y, int rows, int d, void* stream);
 
 #ifdef __cplusplus
