@@ -247,15 +247,40 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
   if (pos < a.n_pos) {
     const float* pe = a.wpe + (size_t)pos * a.d;
     float* hn = a.h_next + (size_t)b * a.d;
-    for (int c = threadIdx.x; c < a.d; c += blockDim.x) {
-      const float x = (a.wte_f32 ? a.wte_f32[(size_t)tok * a.d + c] : __bfloat162float(a.wte_bf16[(size_t)tok * a.d + c])) + pe[c];
-      hn[c] = x;
-      if (a.hb_next) {
-        const bf16 xb = __float2bfloat16_rn(x);
-        a.hb_next[(size_t)b * a.d + c] = xb;
-        const float xf = __bfloat162float(xb);
-        ssum += xf;
-        ssq += xf * xf;
+    if (a.wte_bf16 && a.d % 8 == 0) {
+      // bf16 table: one 16-byte load of the embedding + two of the position row per thread, one round trip for the whole row
+      for (int c = threadIdx.x * 8; c < a.d; c += blockDim.x * 8) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(a.wte_bf16 + (size_t)tok * a.d + c);
+        const float4 p0 = *reinterpret_cast<const float4*>(pe + c), p1 = *reinterpret_cast<const float4*>(pe + c + 4);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const float2 e0 = __bfloat1622float2(h2[0]), e1 = __bfloat1622float2(h2[1]), e2 = __bfloat1622float2(h2[2]), e3 = __bfloat1622float2(h2[3]);
+        const float x[8] = {e0.x + p0.x, e0.y + p0.y, e1.x + p0.z, e1.y + p0.w, e2.x + p1.x, e2.y + p1.y, e3.x + p1.z, e3.y + p1.w};
+        *reinterpret_cast<float4*>(hn + c) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4*>(hn + c + 4) = make_float4(x[4], x[5], x[6], x[7]);
+        if (a.hb_next) {
+          uint4 ob;
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ob);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            o2[u] = __floats2bfloat162_rn(x[2 * u], x[2 * u + 1]);
+            const float2 xf = __bfloat1622float2(o2[u]);
+            ssum += xf.x + xf.y;
+            ssq += xf.x * xf.x + xf.y * xf.y;
+          }
+          *reinterpret_cast<uint4*>(a.hb_next + (size_t)b * a.d + c) = ob;
+        }
+      }
+    } else {
+      for (int c = threadIdx.x; c < a.d; c += blockDim.x) {
+        const float x = (a.wte_f32 ? a.wte_f32[(size_t)tok * a.d + c] : __bfloat162float(a.wte_bf16[(size_t)tok * a.d + c])) + pe[c];
+        hn[c] = x;
+        if (a.hb_next) {
+          const bf16 xb = __float2bfloat16_rn(x);
+          a.hb_next[(size_t)b * a.d + c] = xb;
+          const float xf = __bfloat162float(xb);
+          ssum += xf;
+          ssq += xf * xf;
+        }
       }
     }
   }
@@ -281,7 +306,8 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
         if (nf == (int)gridDim.x) *a.all_done = 1;
       }
     }
-  }  trace_end(a.step_trace, tslot);
+  }
+  trace_end(a.step_trace, tslot);
 }
 
 int launch_finalize_token(const FinalizeArgs& a0, cudaStream_t st) {
