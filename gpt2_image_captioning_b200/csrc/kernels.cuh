@@ -55,8 +55,8 @@ struct GemmBf16Args {
   // split-K for short-and-wide problems (few output tiles, long K): split_k CTAs per tile, deterministic last-CTA reduction
   int w_static = 0;  // the weights were written long before this launch (engine weights): their first tiles may be fetched before
                      // griddepcontrol.wait, i.e. while the previous kernel is still finishing
-  int no_pdl = 0;  // launch in plain stream order (no programmatic dependent launch): for callers that mix these launches with ordinary
-                   // <<<>>> launches outside a graph -- measured: the host then blocks for milliseconds inside cudaLaunchKernelEx
+  int no_pdl = 0;  // launch in plain stream order (no programmatic dependent launch): for callers outside the engine's launch chain, whose
+                   // neighbours are ordinary <<<>>> launches (the retrieval scan)
   int pair = 0;  // CTA pairs: 256 x block_n tiles by two CTAs (cta_group::2); w_hi's box holds block_n / 2 rows
   int split_k = 1; float* splitk_ws = nullptr;  /* [split_k][M][N] fp32 */  int* splitk_counters = nullptr;  /* [tiles], zero on entry and exit */
   long long* trace = nullptr;      // microbenchmark only: device buffer of >= 640 int64 for CTA 0's clock64 timeline

@@ -375,7 +375,7 @@ int launch_topk_ip_tc(const float* q, const float* db, const bf16* db_hi, const 
   const auto t1 = now();
   double t_enc = 0, t_gemm = 0, t_scan = 0;
   GemmBf16Args g;
-  g.no_pdl = 1;  // plain stream order: these launches alternate with ordinary <<<>>> launches on the caller's stream (see kernels.cuh)
+  g.no_pdl = 1;  // plain stream order: these launches alternate with ordinary <<<>>> launches on the caller's stream
   GIC_TRY(make_tma_2d_bf16(&g.a_hi, q_hi, B, D, D, 128));
   GIC_TRY(make_tma_2d_bf16(&g.a_lo, q_lo, B, D, D, 128));
   for (long base = 0; base < N; base += TOPK_CHUNK) {
