@@ -16,7 +16,7 @@ import os
 import numpy as np
 import torch
 
-from . import _capi, ops
+from . import _capi, faiss_files, ops
 
 
 class _GpuFlatIndex:
@@ -106,6 +106,36 @@ class GpuFlatStore:
                 return np.asarray(index.reconstruct_n(0, index.ntotal), dtype=np.float32)
             return np.stack([index.reconstruct(i) for i in range(index.ntotal)]).astype(np.float32)
         return cls(matrix(store.image_index), matrix(store.caption_index), store.image_metadata, store.caption_metadata, device)
+
+    @classmethod
+    def from_directory(cls, db_directory: str, device="cuda") -> "GpuFlatStore | None":
+        """`create_faiss_store(db_directory)` (src/database/faiss_store.py:55-104) without faiss: reads the raw vectors out
+        of `image_index.faiss` / `caption_index.faiss` (flat or HNSW-flat, faiss_files.py) plus the two metadata pickles
+        and uploads them; None when the directory is incomplete, like the reference."""
+        loaded = faiss_files.read_store_directory(db_directory)
+        if loaded is None:
+            return None
+        return cls(*loaded, device=device)
+
+    @classmethod
+    def from_embedding_files(cls, image_embedding_file_path: str, caption_embedding_file_path: str, device="cuda") -> "GpuFlatStore":
+        """`run_faiss_indexing_pipeline` (src/database/faiss_indexing.py:18-150) for the exact GPU store: the "index build"
+        is the upload of the two matrices.  Image file: `{"filenames", "embeddings"}`; caption file: list of
+        `{"filenames": name, "embeddings": [{"embedding", "caption_id"}, ...]}` (captions of unknown images are skipped)."""
+        image_data = torch.load(image_embedding_file_path, weights_only=True)
+        caption_data = torch.load(caption_embedding_file_path, weights_only=False)
+        names = list(image_data["filenames"])
+        img = image_data["embeddings"].to(torch.float32)
+        cap, meta = faiss_files.flatten_caption_entries(caption_data, names)
+        if cap.size == 0:
+            cap = np.zeros((0, img.shape[1]), np.float32)
+        return cls(img, cap, names, meta, device)
+
+    def save(self, db_directory: str) -> None:
+        """`save_faiss_store` (src/database/faiss_store.py:107-129): the same four files, indices written as IndexFlatIP,
+        readable by the reference's `create_faiss_store` and by `from_directory`."""
+        faiss_files.write_store_directory(db_directory, self.image_index.matrix.cpu().numpy(), self.caption_index.matrix.cpu().numpy(),
+                                          self.image_metadata, self.caption_metadata)
 
     def close(self) -> None:  # API compatibility (faiss_store.py:50-52)
         pass

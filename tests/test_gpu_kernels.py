@@ -412,3 +412,35 @@ def test_retrieval_against_reference_fixture():
     s, ix = store.image_index.search(g["q"][:3], 14)
     assert s.shape == (3, 14) and ix.dtype == np.int64
     assert np.array_equal(store.caption_index.reconstruct(7), cap[7])
+
+
+def test_store_from_faiss_directory_and_embedding_files(tmp_path):
+    """GpuFlatStore.from_directory / .from_embedding_files / .save: the store read back from the
+    reference's on-disk layout answers exactly like the one built from the matrices."""
+    from gpt2_image_captioning_b200 import GpuFlatStore, faiss_files
+    rng = np.random.default_rng(11)
+    n_img, D = 300, 64
+    img = rng.standard_normal((n_img, D)).astype(np.float32)
+    img /= np.linalg.norm(img, axis=1, keepdims=True)
+    owner = np.repeat(np.arange(n_img), rng.integers(0, 6, n_img))
+    cap = rng.standard_normal((len(owner), D)).astype(np.float32)
+    names = [f"img_{i:06d}.jpg" for i in range(n_img)]
+    meta = [{"filename": names[o], "caption_id": int(j)} for j, o in enumerate(owner)]
+    a = GpuFlatStore(img, cap, names, meta, device=DEV)
+    assert GpuFlatStore.from_directory(str(tmp_path / "nothing_here"), device=DEV) is None
+    a.save(str(tmp_path / "db"))
+    b = GpuFlatStore.from_directory(str(tmp_path / "db"), device=DEV)
+    entries = [{"filenames": names[i], "embeddings": [{"embedding": torch.from_numpy(cap[j]), "caption_id": int(j)}
+                                                      for j in np.nonzero(owner == i)[0]]} for i in range(n_img)]
+    torch.save({"filenames": names, "embeddings": torch.from_numpy(img)}, tmp_path / "img.pt")
+    torch.save(entries, tmp_path / "cap.pt")
+    c = GpuFlatStore.from_embedding_files(str(tmp_path / "img.pt"), str(tmp_path / "cap.pt"), device=DEV)
+    q = torch.from_numpy(rng.standard_normal((17, D)).astype(np.float32)).to(DEV)
+    want_rows = a.retrieve_rows(q, top_i=4, top_k=10)
+    want_aug = a.retrieve_and_aggregate(q, 4, 10, "mean")
+    for other in (b, c):
+        assert other.image_metadata == names and other.caption_metadata == meta
+        assert torch.equal(other.image_index.matrix, a.image_index.matrix) and torch.equal(other.caption_index.matrix, a.caption_index.matrix)
+        assert torch.equal(other.retrieve_rows(q, top_i=4, top_k=10), want_rows)
+        assert torch.equal(other.retrieve_and_aggregate(q, 4, 10, "mean"), want_aug)
+    assert faiss_files.locate_vectors(str(tmp_path / "db" / "image_index.faiss"))[:2] == (D, n_img)
