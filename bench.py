@@ -351,12 +351,76 @@ def run_reference(args, rank: int, world: int) -> dict | None:
     }
 
 
+def run_reference_cuda(args, rank: int, world: int) -> dict | None:
+    """Not part of the driver contract (SURVEY.md 8(d) "also worth reporting"): the reference's algorithm through stock
+    PyTorch / HF CUDA kernels on the same B200 -- what a user of the reference gets by `model.to("cuda")` -- so the product arm
+    has a same-device bar next to the CPU one.  Two variants: the reference's cache-less fp32 loop (src/models.py:327-477
+    restated around HF GPT2LMHeadModel, host sync per step) and HF `generate` with its KV cache in bf16 (the strongest
+    stock-library configuration of the same model)."""
+    if rank != 0:
+        return None
+    import torch
+    o, oc = reference_generator()
+    dev = torch.device("cuda:0")
+    K, W, N, B = args.steps, args.warmup, args.max_length, args.batch
+    gpt, mapper = o.gpt.to(dev).eval(), o.mapper.to(dev).eval()
+    pool = oc.synthetic_embeddings(POOL_ROWS, E, 1).to(dev)
+    wte = gpt.transformer.wte.weight
+
+    @torch.no_grad()
+    def cacheless(x):
+        cur = mapper(x)
+        finished = torch.zeros(x.shape[0], dtype=torch.bool, device=dev)
+        toks = []
+        for _ in range(N):
+            if bool(finished.all()):
+                break
+            nxt = torch.argmax(gpt(inputs_embeds=cur).logits[:, -1, :] / 1.0, dim=-1)
+            finished = finished | nxt.eq(50256)
+            nxt = torch.where(finished, torch.full_like(nxt, 50256), nxt)
+            toks.append(nxt.unsqueeze(-1))
+            cur = torch.cat((cur, wte[nxt].unsqueeze(1)), dim=1)
+        return torch.cat(toks, dim=1)
+
+    def timed(fn):
+        for i in range(W):
+            fn(pool[(i * B) % (POOL_ROWS - B):][:B])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            ids = fn(pool[((W + i) * B) % (POOL_ROWS - B):][:B])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / K, ids
+
+    ms32, ids32 = timed(cacheless)
+    import copy
+    gpt16, mapper16 = copy.deepcopy(gpt).to(torch.bfloat16), copy.deepcopy(mapper).to(torch.bfloat16)
+
+    @torch.no_grad()
+    def hf_cached(x):
+        return gpt16.generate(inputs_embeds=mapper16(x.to(torch.bfloat16)), do_sample=False, max_new_tokens=N, min_new_tokens=N,
+                              eos_token_id=50256, pad_token_id=50256, use_cache=True)
+
+    ms16, ids16 = timed(hf_cached)
+    return {
+        "impl": "reference-cuda", "metric": "captions/sec (GPT-2 greedy, 30 tokens/caption)", "value": B / ms32 * 1e3, "unit": "captions/s",
+        "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms32, "higher_is_better": True, "dtype": "f32",
+        "data": "synthetic (same seeded embeddings / random-init weights as the B200 arm)",
+        "config": {"workload": f"configs[1] model, batch {B}, the reference's cache-less generate loop on cuda:0 through stock PyTorch/HF kernels"},
+        "variants": {"fp32_cacheless_reference_loop": {"captions_per_s": B / ms32 * 1e3, "ms_per_step": ms32, "tokens": int(ids32.shape[1])},
+                     "bf16_hf_generate_kv_cache": {"captions_per_s": B / ms16 * 1e3, "ms_per_step": ms16, "tokens": int(ids16.shape[1])}},
+        "gpu_launches": 0,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-cuda"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "bf16x2", "fp32"])
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--max-length", type=int, default=30)
@@ -367,6 +431,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         line = run_reference(args, rank, world)
+    elif args.impl == "reference-cuda":
+        line = run_reference_cuda(args, rank, world)
     else:
         if world != args.gpus and world == 1 and args.gpus > 1:
             # launched without torchrun: re-exec under torch.distributed.run on this node
