@@ -163,7 +163,6 @@ def run_product(args, rank: int, world: int, local_rank: int) -> dict | None:
         dist.init_process_group("nccl", device_id=dev)
     B, N, K, W = args.batch, args.max_length, args.steps, max(3, args.warmup)
     model = build_product_model(args.dtype, dev)
-    eng = model._get_engine()
     pool = synthetic_pool(POOL_ROWS, E)
     pool_dev = pool.to(dev)
     pool_pin = pool.pin_memory()
@@ -187,16 +186,37 @@ def run_product(args, rank: int, world: int, local_rank: int) -> dict | None:
         return float(t.item())
 
     # ---- device-resident throughput -------------------------------------------------------------------------------------
-    for i in range(W):
-        eng.generate_greedy(dev_batches[i % len(dev_batches)], N)
+    # F batches in flight per GPU (gpt2_image_captioning_b200/inflight.py: one stream + engine slot + host thread each; the worker
+    # streams wait for this stream and are joined back into it, so the events below bracket all of them)
+    from gpt2_image_captioning_b200.inflight import map_batches
+    F = max(1, args.in_flight)
+
+    def dev_step(x):
+        return model._get_engine().generate_greedy(x, N)
+
+    def host_step(x):
+        return model.generate(image_embeddings=x, max_length=N, temperature=0.0)
+
+    def timed_device(f: int) -> float:
+        map_batches(dev_step, [dev_batches[i % len(dev_batches)] for i in range(max(W, f))], f)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        map_batches(dev_step, dev_batches[:K], f)
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1))
+
+    eng = model._get_engine()
+    seq_ms = timed_device(1) if F > 1 else None
+    map_batches(dev_step, [dev_batches[i % len(dev_batches)] for i in range(max(W, F))], F)
     barrier()
     launches0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         barrier()
         e0.record()
-        for i in range(K):
-            ids, gen_len = eng.generate_greedy(dev_batches[i], N)
+        map_batches(dev_step, dev_batches[:K], F)
         e1.record()
         barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -204,12 +224,10 @@ def run_product(args, rank: int, world: int, local_rank: int) -> dict | None:
     value = world * B * K / (ms_total / 1e3)
 
     # ---- end to end through the public API, host buffers ---------------------------------------------------------------------
-    for i in range(2):
-        model.generate(image_embeddings=host_batches[i], max_length=N, temperature=0.0)
+    map_batches(host_step, host_batches[:max(2, F)], F)
     barrier()
     t0 = time.perf_counter()
-    for i in range(K):
-        out = model.generate(image_embeddings=host_batches[i], max_length=N, temperature=0.0)
+    out = map_batches(host_step, host_batches[:K], F)[-1]
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     assert out.device.type == "cpu" and tuple(out.shape) == (B, N)
@@ -270,7 +288,8 @@ def run_product(args, rank: int, world: int, local_rank: int) -> dict | None:
     step_ms_graph = (ms_total / K - prefill_ms) / max(1, N - 1)
     step_roof = {"alg_bytes": byt, "alg_flops": flo, "t_hbm_us": byt / (pk["hbm_gbs"] * 1e9) * 1e6,
                  "t_tensor_us": flo / (pk["tf_sustained"] * 1e12) * 1e6, "measured_us": step_ms_graph * 1e3,
-                 "achieved_GBps": byt / (step_ms_graph * 1e-3) / 1e9, "achieved_TFLOPs": flo / (step_ms_graph * 1e-3) / 1e12}
+                 "achieved_GBps": byt / (step_ms_graph * 1e-3) / 1e9, "achieved_TFLOPs": flo / (step_ms_graph * 1e-3) / 1e12,
+                 "note": f"measured_us = (batch time - prefill) / {N - 1} with {F} batches in flight: throughput-effective, not one chain's latency"}
     step_roof["frac_of_max_bound"] = max(step_roof["t_hbm_us"], step_roof["t_tensor_us"]) / step_roof["measured_us"]
 
     in_graph = in_graph_timeline(eng, dev_batches[0], N, B, d, s, pk)
@@ -280,9 +299,11 @@ def run_product(args, rank: int, world: int, local_rank: int) -> dict | None:
         "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic (seeded L2-normalised 512-d embeddings, random-init weights; no network for COCO / checkpoints)",
         "config": {"workload": "configs[1]: GPT-2 small (124M) + MLP mapping net, prefix_len 10, greedy 30 tokens, batch 1024 per GPU, "
-                               "5k-row synthetic embedding pool, image-sharded", "batch_per_gpu": B, "max_length": N,
+                               f"{F} batches in flight per GPU, 5k-row synthetic embedding pool, image-sharded", "batch_per_gpu": B, "max_length": N, "batches_in_flight_per_gpu": F,
                    "l2": "per-step working set (0.25 GB bf16 weights + up to 1.5 GB KV cache) exceeds the 126 MB L2; no flush needed"},
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+        "in_flight_1": None if seq_ms is None else {"value": world * B * K / (seq_ms / 1e3), "ms_per_step": seq_ms / K,
+                                                    "note": "the same K batches one after the other on one stream"},
         "roofline": roof, "roofline_in_graph": in_graph, "decode_step_roofline": step_roof, "kernel_classes": classes,
     }
     if world == 1 and not args.no_cpu_baseline:
@@ -425,6 +446,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--max-length", type=int, default=30)
     ap.add_argument("--cpu-rows", type=int, default=16)
+    ap.add_argument("--in-flight", type=int, default=2, help="batches of --batch rows running concurrently per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))

@@ -8,8 +8,9 @@ from .models import (ImageCaptioningModel, MLPMappingNetwork, RetrievalAggregato
 from .engine import CaptionEngine
 from .database import GpuFlatStore
 from .sharding import shard_range, generate_sharded
+from .inflight import map_batches
 from .evaluation import generate_predictions, generate_and_evaluate, load_embeddings_pt, generate_for_embeddings
 
 __all__ = ["ImageCaptioningModel", "MLPMappingNetwork", "TransformerMappingNetwork", "RetrievalAggregator",
            "RetrievalAugmentedTransformer", "accelerate", "CaptionEngine", "GpuFlatStore", "shard_range", "generate_sharded",
-           "generate_predictions", "generate_and_evaluate", "load_embeddings_pt", "generate_for_embeddings"]
+           "map_batches", "generate_predictions", "generate_and_evaluate", "load_embeddings_pt", "generate_for_embeddings"]

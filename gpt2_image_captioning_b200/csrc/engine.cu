@@ -1,6 +1,7 @@
 // Host side of libgic_b200.so: the opaque engine (packed weights), workspace carving, the generate drivers
 // (mapper -> prefill -> KV-cached decode loop, captured in a CUDA graph) and the extern "C" entry points.
 // See include/gic_b200.h for the contract and the reference lines each entry point replaces.
+#include <atomic>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -158,8 +159,10 @@ bool pdl_enabled() {
 }
 
 // kernels launched by this library (graph replays count their kernel nodes) -- bench.py's `gpu_launches`
-static unsigned long long g_launches = 0;
-void note_launch() { ++g_launches; }
+// (atomic + a per-thread count: engines may be driven from several host threads, one stream each)
+static std::atomic<unsigned long long> g_launches{0};
+static thread_local unsigned long long tl_launches = 0;
+void note_launch() { ++tl_launches; g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 struct ProfScope {
   gic_engine* e; cudaStream_t st; bool on;
@@ -883,14 +886,15 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
       !(e->graph_exec && e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new && e->graph_steps == chunk && e->graph_trace_gen == gic::trace_generation())) {
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
-    const unsigned long long before = g_launches;
+    const unsigned long long before = tl_launches;
     e->graph_steps = chunk;
     GIC_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int r = GIC_OK;
     for (int s = 0; s < chunk && r == GIC_OK; ++s) r = decode_step_all(e, w, nullptr, st);
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    e->graph_nodes = (int)(g_launches - before);  // captured, not executed
-    g_launches = before;
+    e->graph_nodes = (int)(tl_launches - before);  // captured, not executed
+    g_launches.fetch_sub(tl_launches - before, std::memory_order_relaxed);
+    tl_launches = before;
     if (r != GIC_OK) { if (graph) cudaGraphDestroy(graph); return r; }
     GIC_CHECK_CUDA(ce);
     ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
@@ -902,7 +906,7 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
     const int n = steps - s_next + 1 < chunk ? steps - s_next + 1 : chunk;
     if (graph_ok) {
       GIC_CHECK_CUDA(cudaGraphLaunch(e->graph_exec, st));
-      g_launches += (unsigned long long)e->graph_nodes;
+      g_launches.fetch_add((unsigned long long)e->graph_nodes, std::memory_order_relaxed);
     } else {
       for (int i = 0; i < n; ++i) GIC_TRY(eager_step(s_next + i));
     }
@@ -1056,7 +1060,7 @@ int gic_gather_aggregate_add(const float* q, const float* cap_db, const int64_t*
   return launch_gather_aggregate_add(q, cap_db, rows, batch, top_k, dim, aggregation, out, (cudaStream_t)stream);
 }
 
-unsigned long long gic_launch_count(void) { return gic::g_launches; }
+unsigned long long gic_launch_count(void) { return gic::g_launches.load(std::memory_order_relaxed); }
 
 int gic_profile_enable(gic_engine* e, int on) {
   GIC_REQUIRE(e != nullptr, "null engine");

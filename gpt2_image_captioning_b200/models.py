@@ -11,6 +11,7 @@ plain PyTorch as in the reference and is outside the accelerated path.  There is
 """
 from __future__ import annotations
 
+import threading
 from typing import Literal
 
 import torch
@@ -18,6 +19,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .engine import CaptionEngine
+from .inflight import current_slot
+
+_ENGINE_LOCK = threading.Lock()
 
 __all__ = ["MLPMappingNetwork", "TransformerMappingNetwork", "ImageCaptioningModel", "RetrievalAggregator",
            "RetrievalAugmentedTransformer", "accelerate"]
@@ -74,20 +78,27 @@ class _EngineMixin:
                 tuple((p.data_ptr(), p._version) for p in params))
 
     def _get_engine(self) -> CaptionEngine:
+        """The engine of the calling thread's slot (inflight.current_slot(); slot 0 outside inflight.map_batches).  Every slot
+        owns an engine handle -- packed weights, workspace, CUDA graph -- so batches in different slots can run concurrently."""
         key = self._engine_key()
-        eng = self.__dict__.get("_engine")
-        if eng is None or self.__dict__.get("_engine_key_cached") != key:
-            if eng is not None:
-                eng.close()
-            mapper = self.mapping_network
-            if isinstance(mapper, MLPMappingNetwork) or hasattr(mapper, "model"):
-                act = mapper.model[1]
-                if not isinstance(act, nn.Tanh):
-                    raise NotImplementedError(f"the engine implements the reference's default Tanh mapper activation, not {type(act).__name__}")
-            task = getattr(self, "task_prefix_embeds", None)
-            eng = CaptionEngine(self.gpt, mapper, int(self.tokenizer.eos_token_id), task_prefix_embeds=task, dtype=self.engine_dtype)
-            self.__dict__["_engine"] = eng
-            self.__dict__["_engine_key_cached"] = key
+        with _ENGINE_LOCK:
+            engines = self.__dict__.setdefault("_engines", {})
+            if self.__dict__.get("_engine_key_cached") != key:
+                for old in engines.values():
+                    old.close()
+                engines.clear()
+                self.__dict__["_engine_key_cached"] = key
+            slot = current_slot()
+            eng = engines.get(slot)
+            if eng is None:
+                mapper = self.mapping_network
+                if isinstance(mapper, MLPMappingNetwork) or hasattr(mapper, "model"):
+                    act = mapper.model[1]
+                    if not isinstance(act, nn.Tanh):
+                        raise NotImplementedError(f"the engine implements the reference's default Tanh mapper activation, not {type(act).__name__}")
+                task = getattr(self, "task_prefix_embeds", None)
+                eng = CaptionEngine(self.gpt, mapper, int(self.tokenizer.eos_token_id), task_prefix_embeds=task, dtype=self.engine_dtype)
+                engines[slot] = eng
         return eng
 
     def _generate_on_engine(self, image_embeddings: torch.Tensor, max_length: int, temperature: float, top_p: float) -> torch.Tensor:

@@ -21,29 +21,33 @@ def shard_range(n_rows: int, rank: int, world_size: int) -> tuple[int, int]:
 
 
 def generate_batches(generate_fn: Callable[[torch.Tensor], torch.Tensor], embeddings: torch.Tensor, max_length: int,
-                     batch_size: int, eos_token_id: int = EOS_PAD) -> torch.Tensor:
+                     batch_size: int, eos_token_id: int = EOS_PAD, in_flight: int = 1) -> torch.Tensor:
     """Run `generate_fn` (one reference-style `model.generate` call per batch) over `embeddings` and return int64
     [n, max_length] on the CPU, each batch's [b, L_gen] right-padded with EOS (what every finished row would have
-    produced had the loop continued, src/models.py:458-460)."""
+    produced had the loop continued, src/models.py:458-460).  `in_flight` > 1 keeps that many batches running
+    concurrently on the GPU (inflight.map_batches: one stream + engine slot + host thread each); same ids."""
+    from .inflight import map_batches
+
     out = torch.full((embeddings.shape[0], max_length), eos_token_id, dtype=torch.int64)
-    for s in range(0, embeddings.shape[0], batch_size):
-        ids = generate_fn(embeddings[s:s + batch_size])
-        out[s:s + ids.shape[0], : ids.shape[1]] = ids.to("cpu")
+    starts = list(range(0, embeddings.shape[0], batch_size))
+    results = map_batches(lambda s: generate_fn(embeddings[s:s + batch_size]).to("cpu"), starts, in_flight)
+    for s, ids in zip(starts, results):
+        out[s:s + ids.shape[0], : ids.shape[1]] = ids
     return out
 
 
 def generate_sharded(generate_fn: Callable[[torch.Tensor], torch.Tensor], embeddings: torch.Tensor, max_length: int,
-                     batch_size: int, eos_token_id: int = EOS_PAD, group=None, dst: int = 0) -> torch.Tensor | None:
+                     batch_size: int, eos_token_id: int = EOS_PAD, group=None, dst: int = 0, in_flight: int = 1) -> torch.Tensor | None:
     """Every rank captions rows shard_range(n, rank, world) of the SAME `embeddings` tensor; rank `dst` returns the
     full [n, max_length] int64 result in the original row order, other ranks return None.
     Without an initialised process group this is the single-GPU loop."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()):
-        return generate_batches(generate_fn, embeddings, max_length, batch_size, eos_token_id)
+        return generate_batches(generate_fn, embeddings, max_length, batch_size, eos_token_id, in_flight)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     lo, hi = shard_range(embeddings.shape[0], rank, world)
-    mine = generate_batches(generate_fn, embeddings[lo:hi], max_length, batch_size, eos_token_id)
+    mine = generate_batches(generate_fn, embeddings[lo:hi], max_length, batch_size, eos_token_id, in_flight)
     parts = [None] * world if rank == dst else None
     dist.gather_object((lo, hi, mine.numpy()), parts, dst=dst, group=group)  # host gather of token ids only
     if rank != dst:

@@ -361,3 +361,23 @@ def test_early_exit_once_every_row_has_finished(monkeypatch, dtype):
     if dtype == "fp32":
         assert torch.equal(a, want)
     assert (n1 - n0) < (m1 - m0), (n1 - n0, m1 - m0)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_batches_in_flight_give_the_sequential_ids(dtype):
+    """generate_for_embeddings(in_flight=2 / 3): batches on concurrent streams, one engine slot each (inflight.py), ragged
+    last batch; ids must equal the one-batch-at-a-time loop, from device and from pinned host inputs."""
+    from gpt2_image_captioning_b200 import ImageCaptioningModel, MLPMappingNetwork, generate_for_embeddings
+    from oracle.ref_harness import StubTokenizer
+    spec = oc.ModelSpec(gpt="tiny", embed_dim=64, prefix_length=4)
+    gpt, mapper_ref = oc.build_modules(spec)
+    mapper = MLPMappingNetwork(prefix_length=4, embed_dim=64, gpt_dim=128)
+    mapper.load_state_dict(mapper_ref.state_dict())
+    model = ImageCaptioningModel(mapper, tokenizer=StubTokenizer(), gpt=gpt, engine_dtype=dtype).to(DEV)
+    x = oc.synthetic_embeddings(150, 64, 3)
+    want = generate_for_embeddings(model, x, batch_size=32, max_length=9, device=DEV, in_flight=1)
+    assert len(model.__dict__["_engines"]) == 1
+    for f, src in [(2, x), (3, x.pin_memory()), (2, x.to(DEV))]:
+        got = generate_for_embeddings(model, src, batch_size=32, max_length=9, device=DEV, in_flight=f)
+        assert got.device.type == "cpu" and torch.equal(got, want), f
+    assert sorted(model.__dict__["_engines"]) == [0, 1, 2]

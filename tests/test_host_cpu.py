@@ -269,3 +269,36 @@ def test_dedupe_before_generate_matches_the_reference_loop(tmp_path):
     torch.save({"embeddings": emb}, path)
     with pytest.raises(ValueError):
         load_embeddings_pt(str(path))
+
+
+def test_map_batches_order_slots_and_errors():
+    """inflight.map_batches: results in batch order, batch i on slot i % in_flight, in_flight = 1 stays on the calling thread,
+    worker exceptions reach the caller."""
+    import threading
+    from gpt2_image_captioning_b200.inflight import current_slot, map_batches
+    main = threading.get_ident()
+    seen = map_batches(lambda b: (b, current_slot(), threading.get_ident()), list(range(7)), in_flight=3)
+    assert [s[0] for s in seen] == list(range(7)) and [s[1] for s in seen] == [i % 3 for i in range(7)]
+    assert all(s[2] != main for s in seen)
+    seq = map_batches(lambda b: (b, current_slot(), threading.get_ident()), list(range(4)), in_flight=1)
+    assert all(s[1] == 0 and s[2] == main for s in seq)
+    assert map_batches(lambda b: b, [], in_flight=2) == [] and current_slot() == 0
+
+    def boom(b):
+        if b == 3:
+            raise KeyError("batch 3")
+        return b
+    with pytest.raises(KeyError, match="batch 3"):
+        map_batches(boom, list(range(6)), in_flight=2)
+
+
+def test_generate_batches_in_flight_equals_sequential():
+    from gpt2_image_captioning_b200.sharding import generate_batches
+    x = torch.arange(23 * 4, dtype=torch.float32).reshape(23, 4)
+
+    def fake_generate(e):  # [b, L_gen] with a batch-dependent L_gen, like a trimmed reference batch
+        L = 3 + int(e[0, 0].item()) % 3
+        return (e[:, :1].long() + torch.arange(L)).contiguous()
+    a = generate_batches(fake_generate, x, 6, 5, in_flight=1)
+    b = generate_batches(fake_generate, x, 6, 5, in_flight=3)
+    assert a.shape == (23, 6) and torch.equal(a, b)
