@@ -536,7 +536,16 @@ static int decode_step_all(gic_engine* e, const Workspace& w, float* logits_tap,
   int S = e->sub_batches;
   const int tiles = (w.rows + 127) / 128;
   if (S > tiles) S = tiles;
-  if (S < 2 || logits_tap) return decode_step(e, w, logits_tap, st);
+  if (S < 2 || logits_tap) {
+    // GIC_CTA_LIMIT=n (experiment knob): every persistent kernel of the decode chain takes at most n CTAs, so that the chains of
+    // several batches in flight (inflight.py) run side by side instead of taking turns on the whole GPU
+    static const int lim = [] { const char* v = getenv("GIC_CTA_LIMIT"); return v ? atoi(v) : 0; }();
+    if (lim <= 0) return decode_step(e, w, logits_tap, st);
+    set_cta_limit(lim);
+    const int r = decode_step(e, w, logits_tap, st);
+    set_cta_limit(0);
+    return r;
+  }
   const int rows_per = ((tiles + S - 1) / S) * 128;
   S = (w.rows + rows_per - 1) / rows_per;
   int sms = 148, dev = 0;
