@@ -17,6 +17,7 @@ import numpy as np
 import torch
 
 from . import _capi, faiss_files, ops
+from .inflight import current_slot
 
 
 class _GpuFlatIndex:
@@ -25,7 +26,7 @@ class _GpuFlatIndex:
     def __init__(self, matrix: torch.Tensor, tensor_cores: bool | None = None):
         self.matrix = matrix
         self.ntotal, self.d = int(matrix.shape[0]), int(matrix.shape[1])
-        self._ws: torch.Tensor | None = None
+        self._ws: dict[int, torch.Tensor] = {}  # scan workspace per in-flight slot (inflight.py): slots search concurrently
         # tensor-core scan (bf16x2 tcgen05 candidates + exact re-scoring + certificate, include/gic_b200.h gic_topk_ip_tc): same
         # scores and indices as the exact fp32 scan.  GIC_RETRIEVAL_EXACT=1 keeps the fp32 CUDA-core scan.
         if tensor_cores is None:
@@ -51,14 +52,16 @@ class _GpuFlatIndex:
         lib = _capi.lib()
         tc = self.hi is not None and bool(lib.gic_topk_tc_supported(self.d, k))
         need = int((lib.gic_topk_tc_workspace_bytes if tc else lib.gic_topk_workspace_bytes)(B, self.ntotal, self.d, k))
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = None
-            self._ws = torch.empty(need, dtype=torch.uint8, device=q.device)
+        slot = current_slot()
+        ws = self._ws.get(slot)
+        if ws is None or ws.numel() < need:
+            self._ws.pop(slot, None)
+            ws = self._ws[slot] = torch.empty(need, dtype=torch.uint8, device=q.device)
         with torch.cuda.device(q.device):
             if tc:
-                ops.topk_ip_tc(q, self.matrix, self.hi, self.lo, self.norm_max, k, scores, idx, self._ws)
+                ops.topk_ip_tc(q, self.matrix, self.hi, self.lo, self.norm_max, k, scores, idx, ws)
             else:
-                ops.topk_ip(q, self.matrix, k, scores, idx, self._ws)
+                ops.topk_ip(q, self.matrix, k, scores, idx, ws)
         return scores, idx
 
     def search(self, x, k: int):

@@ -381,3 +381,45 @@ def test_batches_in_flight_give_the_sequential_ids(dtype):
         got = generate_for_embeddings(model, src, batch_size=32, max_length=9, device=DEV, in_flight=f)
         assert got.device.type == "cpu" and torch.equal(got, want), f
     assert sorted(model.__dict__["_engines"]) == [0, 1, 2]
+
+
+def test_rat_generate_end_to_end_and_in_flight():
+    """RetrievalAugmentedTransformer.generate(db_store, top_k, top_i, image_embeddings, ...) (src/models.py:748-785): retrieval +
+    mean-add on the device store, then the greedy engine; tokens equal the oracle's generate on the same augmented embeddings, the
+    augmented embeddings equal the oracle's retrieval restatement, and batches in flight (per-slot scan workspaces) change nothing."""
+    from gpt2_image_captioning_b200 import GpuFlatStore, MLPMappingNetwork, RetrievalAugmentedTransformer, map_batches
+    from oracle.ref_harness import StubTokenizer
+    spec = oc.ModelSpec(gpt="tiny", embed_dim=64, prefix_length=4)
+    gpt, mapper_ref = oc.build_modules(spec)
+    oracle = oc.CaptionOracle(spec, gpt, mapper_ref)
+    rng = np.random.default_rng(21)
+    n_img, D = 2000, 64
+    img = rng.standard_normal((n_img, D)).astype(np.float32)
+    img /= np.linalg.norm(img, axis=1, keepdims=True)
+    counts = rng.integers(0, 7, n_img)
+    owner = np.repeat(np.arange(n_img), counts)
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    cap = rng.standard_normal((len(owner), D)).astype(np.float32)
+    cap /= np.linalg.norm(cap, axis=1, keepdims=True)
+    names = [f"img_{i:06d}.jpg" for i in range(n_img)]
+    store = GpuFlatStore(img, cap, names, [{"filename": names[o], "caption_id": j} for j, o in enumerate(owner)], device=DEV)
+    x = oc.synthetic_embeddings(90, D, 4)
+    x[5] = torch.from_numpy(img[17])  # an exact database row: its own hit is dropped by the > 0.9999 filter
+    want_aug, _ = oc.retrieve_and_aggregate(img, cap, lambda im: list(range(starts[im], starts[im + 1])), x.numpy(), top_i=4, top_k=10)
+
+    mapper = MLPMappingNetwork(prefix_length=4, embed_dim=D, gpt_dim=128)
+    mapper.load_state_dict(mapper_ref.state_dict())
+    model = RetrievalAugmentedTransformer(D, 4, "mean", mapper, tokenizer=StubTokenizer(), gpt=gpt, engine_dtype="fp32").to(DEV)
+    aug = model._augment(store, x.to(DEV), top_i=4, top_k=10)
+    np.testing.assert_allclose(aug.cpu().numpy(), want_aug, atol=1e-6)
+    got = model.generate(store, 10, 4, x.to(DEV), max_length=8, temperature=0.0)
+    assert got.device.type == "cuda" and got.dtype == torch.int64
+    gpt.to("cpu")
+    assert torch.equal(got.cpu(), oracle.generate(aug.cpu(), 8, kv_cache=True))
+    gpt.to(DEV)
+    batches = [x[s:s + 32] for s in range(0, 90, 32)]
+    seq = [model.generate(store, 10, 4, b, max_length=8, temperature=0.0) for b in batches]
+    par = map_batches(lambda b: model.generate(store, 10, 4, b, max_length=8, temperature=0.0), batches, in_flight=2)
+    assert all(p.device.type == "cpu" and torch.equal(p, s) for p, s in zip(par, seq))
+    assert torch.equal(torch.cat(seq), got.cpu())
+    assert sorted(store.image_index._ws) == [0, 1]
