@@ -451,6 +451,11 @@ def main():
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    # stdout carries exactly one JSON line: route fd 1 to stderr while the run is on (NCCL prints its version banner to stdout at
+    # the first collective, warnings of libraries may follow) and write the line to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         line = run_reference(args, rank, world)
     elif args.impl == "reference-cuda":
@@ -463,7 +468,8 @@ def main():
             sys.exit(subprocess.call(cmd))
         line = run_product(args, rank, world, local_rank)
     if line is not None:
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":

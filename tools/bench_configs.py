@@ -28,17 +28,27 @@ class Tok:
     eos_token_id = 50256
 
 
+IN_FLIGHT = 1
+
+
 def timed(fn, warmup=2, reps=3):
+    """ms per call of fn; with --in-flight F every repetition runs F calls concurrently (inflight.map_batches) and the time is per call."""
+    from gpt2_image_captioning_b200.inflight import map_batches
+    F = IN_FLIGHT
+
+    def rep():
+        return fn() if F == 1 else map_batches(lambda _: fn(), list(range(F)), F)[-1]
+
     for _ in range(warmup):
-        out = fn()
+        out = rep()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps):
-        out = fn()
+        out = rep()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / reps, out
+    return a.elapsed_time(b) / (reps * F), out
 
 
 def build(dims, mapper_kind, E, P, dtype, dev, beams=1, rat=False):
@@ -58,12 +68,15 @@ def build(dims, mapper_kind, E, P, dtype, dev, beams=1, rat=False):
 
 
 def main():
+    global IN_FLIGHT
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="c3,c4,c5")
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--max-length", type=int, default=30)
+    ap.add_argument("--in-flight", type=int, default=2, help="batches running concurrently (inflight.py); 1 = one at a time")
     a = ap.parse_args()
+    IN_FLIGHT = max(1, a.in_flight)
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     B, N = a.batch, a.max_length
@@ -72,7 +85,7 @@ def main():
         model = build(dict(n_embd=1024, n_layer=24, n_head=16), "tfm", 512, 40, a.dtype, dev, beams=5)
         x = bench.synthetic_pool(B, 512).to(dev)
         ms, ids = timed(lambda: model.generate(image_embeddings=x, max_length=N, temperature=0.0))
-        print(json.dumps({"config": "c3: GPT-2 medium + 8-layer transformer mapper, prefix_len 40, beam 5 (ancestry-table KV)", "batch": B, "dtype": a.dtype,
+        print(json.dumps({"config": "c3: GPT-2 medium + 8-layer transformer mapper, prefix_len 40, beam 5 (ancestry-table KV)", "batch": B, "dtype": a.dtype, "in_flight": IN_FLIGHT,
                           "ms_per_batch": ms, "captions_per_s": B / ms * 1e3, "ids_shape": list(ids.shape)}), flush=True)
         del model
         torch.cuda.empty_cache()
@@ -80,7 +93,7 @@ def main():
         model = build(dict(n_embd=1280, n_layer=36, n_head=20), "mlp", 1024, 10, a.dtype, dev)
         x = bench.synthetic_pool(B, 1024).to(dev)
         ms, ids = timed(lambda: model.generate(image_embeddings=x, max_length=N, temperature=0.0))
-        print(json.dumps({"config": "c4: GPT-2 large + MLP mapper, 1024-d embeddings, greedy", "batch": B, "dtype": a.dtype, "ms_per_batch": ms,
+        print(json.dumps({"config": "c4: GPT-2 large + MLP mapper, 1024-d embeddings, greedy", "batch": B, "dtype": a.dtype, "in_flight": IN_FLIGHT, "ms_per_batch": ms,
                           "captions_per_s": B / ms * 1e3, "ids_shape": list(ids.shape)}), flush=True)
         del model
         torch.cuda.empty_cache()
@@ -96,11 +109,13 @@ def main():
         store = GpuFlatStore(img, cap, names, [{"filename": names[min(j // 5, n_img - 1)]} for j in range(n_cap)], device=dev)
         model = build(bench.MODEL, "mlp", 512, 10, a.dtype, dev, rat=True)
         x = bench.synthetic_pool(B, 512).to(dev)
+        keep, IN_FLIGHT = IN_FLIGHT, 1  # the two retrieval-only timings are single calls
         ms_r, _ = timed(lambda: store.retrieve_and_aggregate(x, top_i=5, top_k=5))
         ms_s, _ = timed(lambda: store.caption_index.search_device(x, 5))
+        IN_FLIGHT = keep
         ms, ids = timed(lambda: model.generate(store, 5, 5, image_embeddings=x, max_length=N, temperature=0.0))
         print(json.dumps({"config": "c5: RAT, top-5 over 118 287 images -> caption rows of 591 753 -> mean-add, GPT-2 small greedy", "batch": B,
-                          "dtype": a.dtype, "ms_per_batch": ms, "captions_per_s": B / ms * 1e3, "retrieve_and_aggregate_ms": ms_r,
+                          "dtype": a.dtype, "in_flight": IN_FLIGHT, "ms_per_batch": ms, "captions_per_s": B / ms * 1e3, "retrieve_and_aggregate_ms": ms_r,
                           "top5_over_591753_rows_ms": ms_s, "top5_scan_TFLOPs": 2.0 * B * n_cap * 512 / ms_s * 1e-9,
                           "ids_shape": list(ids.shape)}), flush=True)
 
