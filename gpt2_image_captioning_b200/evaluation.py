@@ -30,13 +30,14 @@ def first_seen(image_ids: Iterable[int], seen: set[int]) -> list[int]:
 
 def generate_predictions(model, dataset, batch_size: int = 32, num_workers: int = 0, max_length: int = 50, temperature: float = 0.0,
                          top_p: float = 0.9, device: torch.device | str | None = None, db_store=None, top_k: int | None = None,
-                         top_i: int | None = None, tokenizer=None) -> list[dict[str, Any]]:
+                         top_i: int | None = None, tokenizer=None, in_flight: int = 2) -> list[dict[str, Any]]:
     """One caption per distinct image of `dataset` (items with `image_id` and `image_embedding`), in first-seen order.
 
     `dataset` may be a torch Dataset (wrapped in a DataLoader exactly like src/eval.py:191-193) or any iterable of batches
     `{"image_id": LongTensor[b], "image_embedding": FloatTensor[b, E]}`.  With `db_store` the RAT signature is used
     (src/eval.py:281-289).  Unique rows are accumulated across loader batches so that `generate` always sees full batches of
-    `batch_size` distinct images."""
+    `batch_size` distinct images; `in_flight` of them run concurrently on the GPU (inflight.py), decoding to text stays on the
+    calling thread."""
     from torch.utils.data import DataLoader, Dataset
 
     if temperature != 0:
@@ -47,35 +48,42 @@ def generate_predictions(model, dataset, batch_size: int = 32, num_workers: int 
     model.eval()
     batches = DataLoader(dataset, batch_size=batch_size, shuffle=False, num_workers=num_workers) if isinstance(dataset, Dataset) else dataset
     tokenizer = tokenizer or getattr(dataset, "tokenizer", None) or model.tokenizer
-    predictions: list[dict[str, Any]] = []
     seen: set[int] = set()
     pend_ids: list[int] = []
     pend_emb: list[torch.Tensor] = []
+    work: list[tuple[list[int], torch.Tensor]] = []  # full batches of distinct images, in first-seen order
 
-    def flush(n: int) -> None:
+    def cut(n: int) -> None:
         emb = torch.cat(pend_emb, dim=0)
-        take, rest = emb[:n].to(device), emb[n:]
-        kw = dict(image_embeddings=take, max_length=max_length, temperature=temperature, top_p=top_p)
-        if db_store is not None:
-            kw.update(db_store=db_store, top_k=top_k, top_i=top_i)
-        captions = tokenizer.batch_decode(model.generate(**kw), skip_special_tokens=True)
-        predictions.extend({"image_id": i, "caption": c} for i, c in zip(pend_ids[:n], captions))
+        work.append((pend_ids[:n], emb[:n]))
         del pend_ids[:n]
         pend_emb.clear()
-        if rest.shape[0]:
-            pend_emb.append(rest)
+        if emb.shape[0] > n:
+            pend_emb.append(emb[n:])
 
-    with torch.no_grad():
-        for batch in batches:
-            ids = batch["image_id"].tolist() if torch.is_tensor(batch["image_id"]) else list(batch["image_id"])
-            keep = first_seen(ids, seen)
-            if keep:
-                pend_ids.extend(int(ids[p]) for p in keep)
-                pend_emb.append(batch["image_embedding"][keep])
-            while len(pend_ids) >= batch_size:
-                flush(batch_size)
-        if pend_ids:
-            flush(len(pend_ids))
+    for batch in batches:  # embeddings are precomputed: one pass over the loader costs I/O only (10 MB for val2017)
+        ids = batch["image_id"].tolist() if torch.is_tensor(batch["image_id"]) else list(batch["image_id"])
+        keep = first_seen(ids, seen)
+        if keep:
+            pend_ids.extend(int(ids[p]) for p in keep)
+            pend_emb.append(batch["image_embedding"][keep])
+        while len(pend_ids) >= batch_size:
+            cut(batch_size)
+    if pend_ids:
+        cut(len(pend_ids))
+
+    def run(item) -> torch.Tensor:
+        kw = dict(image_embeddings=item[1].to(device), max_length=max_length, temperature=temperature, top_p=top_p)
+        if db_store is not None:
+            kw.update(db_store=db_store, top_k=top_k, top_i=top_i)
+        with torch.no_grad():
+            return model.generate(**kw).to("cpu")
+
+    from .inflight import map_batches
+    predictions: list[dict[str, Any]] = []
+    for (ids, _), tokens in zip(work, map_batches(run, work, in_flight)):  # `in_flight` batches run concurrently on the GPU
+        captions = tokenizer.batch_decode(tokens, skip_special_tokens=True)
+        predictions.extend({"image_id": i, "caption": c} for i, c in zip(ids, captions))
     return predictions
 
 

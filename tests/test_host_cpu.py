@@ -258,7 +258,10 @@ def test_dedupe_before_generate_matches_the_reference_loop(tmp_path):
     got = generate_predictions(model, DS(), batch_size=7, max_length=6, temperature=0.0, device="cpu")
     assert got == want
     assert model.rows == n_img and ref_model.rows == len(items)
-    assert model.batches == [7, 7, 7, 2]  # full batches of distinct images, then the remainder
+    assert sorted(model.batches) == [2, 7, 7, 7]  # full batches of distinct images + the remainder (two in flight: any order)
+    one = _FakeCaptioner()
+    assert generate_predictions(one, DS(), batch_size=7, max_length=6, temperature=0.0, device="cpu", in_flight=1) == want
+    assert one.batches == [7, 7, 7, 2]
     with pytest.raises(ValueError, match="deterministic"):
         generate_predictions(model, DS(), temperature=1.0, device="cpu")
     # the extractors' .pt format
