@@ -25,6 +25,19 @@ def current_slot() -> int:
     return getattr(_tls, "slot", 0)
 
 
+_streams: dict[tuple[int, int], "torch.cuda.Stream"] = {}
+
+
+def _slot_stream(device: int, slot: int):
+    """One long-lived stream per (device, slot): the caching allocator keeps a pool per stream, so fresh streams on every call would
+    mean fresh cudaMallocs for every call's buffers."""
+    key = (device, slot)
+    st = _streams.get(key)
+    if st is None:
+        st = _streams[key] = torch.cuda.Stream(device)
+    return st
+
+
 def map_batches(fn: Callable, batches: Sequence, in_flight: int = 2) -> list:
     n = len(batches)
     in_flight = max(1, min(int(in_flight), n))
@@ -35,7 +48,7 @@ def map_batches(fn: Callable, batches: Sequence, in_flight: int = 2) -> list:
     errors: list = []
     device = torch.cuda.current_device() if cuda else None
     caller = torch.cuda.current_stream() if cuda else None
-    streams = [torch.cuda.Stream(device) for _ in range(in_flight)] if cuda else [None] * in_flight
+    streams = [_slot_stream(device, j) for j in range(in_flight)] if cuda else [None] * in_flight
 
     def work(slot: int) -> None:
         _tls.slot = slot
