@@ -12,7 +12,8 @@
  *   - every function returns GIC_OK (0) or a negative error code and never throws;
  *     gic_last_error() returns the message of the last failure on the calling thread
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are asynchronous
- *     on that stream unless stated otherwise; one host thread per engine handle
+ *     on that stream unless stated otherwise; one host thread per engine handle at a time, different handles may be
+ *     driven concurrently from different host threads on different streams (batches in flight: inflight.py)
  *   - there is no CPU fallback: without a CUDA device every compute call fails with GIC_ERR_CUDA
  */
 #ifndef GIC_B200_H_
