@@ -153,6 +153,52 @@ def in_graph_timeline(eng, x, N: int, B: int, d: int, s: int, pk: dict) -> dict 
             "method": "%globaltimer: first block past griddepcontrol.wait .. last block's end, every launch inside the CUDA graph"}
 
 
+def attn_back_to_back(dev, B: int, N: int, s: int, pk: dict, traffic) -> dict:
+    """The dominant HBM-bound kernel timed with CUDA events the way it runs in a decode step: for every step t = 1 .. N-1 the 12 layers'
+    launches back to back (one cache plane per layer, 1.5 GB in all: nothing is found in L2), events around each group of 12
+    (include/gic_b200.h gic_bench_attn_decode).  Bytes per launch: K, V [B, ctx, d] read, new K / V appended, q|k|v read, o written."""
+    import ctypes as C
+    import torch
+    from gpt2_image_captioning_b200 import _capi
+    lib = _capi.lib()
+    d, L, H = MODEL["n_embd"], MODEL["n_layer"], MODEL["n_head"]
+    t_max = P + N
+    g = torch.Generator(device=dev).manual_seed(3)
+    qkv = torch.randn(B, 3 * d, device=dev, generator=g).to(torch.bfloat16)
+    kc = torch.randn(L * B * H * t_max * 64, device=dev, generator=g).to(torch.bfloat16)
+    vc = torch.randn(L * B * H * t_max * 64, device=dev, generator=g).to(torch.bfloat16)
+    out = torch.empty(B, d, device=dev, dtype=torch.bfloat16)
+    d_pos = torch.zeros(1, dtype=torch.int32, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def group():
+        _capi.check(lib.gic_bench_attn_decode(C.c_void_p(qkv.data_ptr()), C.c_void_p(kc.data_ptr()), C.c_void_p(vc.data_ptr()),
+                                              C.c_void_p(out.data_ptr()), C.c_void_p(d_pos.data_ptr()), B, H, t_max, L, L, st))
+
+    ms = byt = 0.0
+    launches = 0
+    for rep in range(4):  # rep 0 = warm-up
+        pairs = []
+        for t in range(1, N):
+            d_pos.fill_(P + t - 1)  # tokens already cached; the launch appends one and attends P + t
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            group()
+            e1.record()
+            pairs.append((e0, e1, t))
+        torch.cuda.synchronize()
+        if rep:
+            for e0, e1, t in pairs:
+                ms += e0.elapsed_time(e1)
+                byt += L * s * B * d * (2 * (P + t) + 2 + 3 + 1)
+                launches += L
+    ach = byt / (ms * 1e-3) / 1e9
+    return {"kernel": "attn_decode", "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+            "traffic": traffic, "peak_source": pk["source"], "avg_us": ms / launches * 1e3, "launches": launches,
+            "method": f"CUDA events around each decode step's {L} attention launches issued back to back (one KV plane per layer, contexts "
+                      f"{P + 1}..{P + N - 1}, 3 repetitions); roofline_eager_events times every launch alone, roofline_in_graph inside the CUDA graph"}
+
+
 def run_product(args, rank: int, world: int, local_rank: int) -> dict | None:
     import torch
     import torch.distributed as dist
@@ -279,6 +325,9 @@ def run_product(args, rank: int, world: int, local_rank: int) -> dict | None:
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["traffic"] = traffic
     roof["peak_source"] = pk["source"] + (" (sustained)" if roof["bound"] == "tensor" else "")
+    roof_eager = roof
+    if dom == "attn_decode" and args.dtype == "bf16":
+        roof = attn_back_to_back(dev, B, N, s, pk, traffic)
     # whole decode step against max(t_HBM, t_tensor)  
     byt, flo = algorithmic_decode_step(B, ctx_mean, s)
     decode_ms = sum(v["total_ms"] for n, v in prof.items() if n in decode_names + ["layernorm", "finalize", "argmax"]) - \
@@ -304,7 +353,7 @@ def run_product(args, rank: int, world: int, local_rank: int) -> dict | None:
         "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
         "in_flight_1": None if seq_ms is None else {"value": world * B * K / (seq_ms / 1e3), "ms_per_step": seq_ms / K,
                                                     "note": "the same K batches one after the other on one stream"},
-        "roofline": roof, "roofline_in_graph": in_graph, "decode_step_roofline": step_roof, "kernel_classes": classes,
+        "roofline": roof, "roofline_eager_events": roof_eager, "roofline_in_graph": in_graph, "decode_step_roofline": step_roof, "kernel_classes": classes,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(rows=args.cpu_rows, max_length=N)

@@ -1237,6 +1237,23 @@ int gic_test_attn_decode(const void* qkv, void* kcache, void* vcache, void* out,
   return GIC_OK;
 }
 
+// Measurement hook: back-to-back product decode-attention launches over `planes` cache planes, asynchronous on `stream` (see the header).
+int gic_bench_attn_decode(const void* qkv, void* kcache, void* vcache, void* out, const int* d_pos, int rows, int H, int t_max, int planes,
+                          int launches, void* stream) {
+  GIC_REQUIRE(qkv && kcache && vcache && out && d_pos, "null argument");
+  GIC_REQUIRE(rows > 0 && H > 0 && t_max > 0 && planes > 0 && launches > 0, "bad shape: rows %d H %d t_max %d planes %d launches %d", rows, H, t_max, planes, launches);
+  cudaStream_t st = (cudaStream_t)stream;
+  GIC_TRY(gic_device_check());
+  GIC_TRY(gic::attn_decode_configure());
+  const size_t plane = (size_t)rows * H * t_max * 64;
+  ActOut o; o.hi = (bf16*)out;
+  for (int i = 0; i < launches; ++i) {
+    const size_t off = (size_t)(i % planes) * plane;
+    GIC_TRY(launch_attn_decode<bf16>((const bf16*)qkv, (bf16*)kcache + off, (bf16*)vcache + off, o, d_pos, rows, H, t_max, st));
+  }
+  return GIC_OK;
+}
+
 // One causal prefill-attention launch on caller data (GPT2Attention over the S prefix tokens of every row, HF:models/gpt2/modeling_gpt2.py:185-220):
 // qkv [rows * S, 3 H 64] bf16 -> out [rows * S, H 64] bf16, K / V written to caches [rows][H][t_max][64] at positions 0..S-1.
 int gic_test_attn_prefill(const void* qkv, void* kcache, void* vcache, void* out, int rows, int S, int H, int t_max, void* stream) {

@@ -212,6 +212,11 @@ GIC_API int gic_test_ln_mlp(float* h, const float* gamma, const float* beta, con
 /* one decode-attention launch on caller data: qkv [rows, 3*H*64] bf16, K / V caches [rows][H][t_max][64] bf16 with `pos` cached tokens;
  * appends the new K / V at `pos`, writes out [rows, H*64] bf16 (HF:models/gpt2/modeling_gpt2.py:185-220 for one query).  variant < 0: product kernel */
 GIC_API int gic_test_attn_decode(const void* qkv, void* kcache, void* vcache, void* out, int pos, int rows, int H, int t_max, int variant, void* stream);
+/* measurement hook (bench.py `roofline`): `launches` back-to-back product decode-attention launches, ASYNCHRONOUS on `stream` (the caller
+ * brackets them with CUDA events); launch i works on cache plane i % planes (kcache / vcache + plane * rows*H*t_max*64 elements), the way
+ * the 12 layers of a decode step do, so consecutive launches do not find each other's lines in L2.  d_pos: dev int, tokens already cached. */
+GIC_API int gic_bench_attn_decode(const void* qkv, void* kcache, void* vcache, void* out, const int* d_pos, int rows, int H, int t_max, int planes,
+                                  int launches, void* stream);
 /* one causal prefill-attention launch on caller data: qkv [rows*S, 3*H*64] bf16 -> out [rows*S, H*64] bf16; K / V land in the caches
  * [rows][H][t_max][64] at positions 0..S-1 (HF:models/gpt2/modeling_gpt2.py:185-220, HF:cache_utils.py:102-121) */
 GIC_API int gic_test_attn_prefill(const void* qkv, void* kcache, void* vcache, void* out, int rows, int S, int H, int t_max, void* stream);
