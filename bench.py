@@ -514,6 +514,7 @@ def main():
             # launched without torchrun: re-exec under torch.distributed.run on this node
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr",
                    "127.0.0.1", "--master-port", "29577", os.path.abspath(__file__)] + sys.argv[1:]
+            os.dup2(json_fd, 1)  # the ranks inherit the real stdout; rank 0 prints the line
             sys.exit(subprocess.call(cmd))
         line = run_product(args, rank, world, local_rank)
     if line is not None:
