@@ -6,8 +6,14 @@ Same class names, constructor arguments, method signatures, return types and sta
 src/eval.py:189-210,281-289) run unchanged.  Parameters stay ordinary `nn.Parameter`s owned by PyTorch; the engine's
 packed copies are derived from them and re-derived when they change (load_saved_parameters, .to(), training steps).
 
-Only `generate` (greedy / beam) is on the CUDA path.  `forward` (teacher-forced training, src/models.py:237-325) is
-plain PyTorch as in the reference and is outside the accelerated path.  There is no CPU fallback for `generate`.
+Only `generate` (greedy / sampling / beam) is on the CUDA path.  `forward` (teacher-forced training, src/models.py:237-325,
+717-746) is plain differentiable PyTorch as in the reference and is outside the accelerated path (the RAT forward uses the
+device kNN only to FETCH the retrieved rows; pooling goes through the `RetrievalAggregator` module so that its parameters
+receive gradients).  There is no CPU fallback for `generate`.
+
+The engine's packed weights are keyed on every parameter's `(data_ptr, _version)`; code that edits weights through
+`p.data` (which does not bump `_version`) must call `model.invalidate_engine()` -- `load_saved_parameters`, `load_state_dict`
+and `train()` do.
 """
 from __future__ import annotations
 
@@ -76,6 +82,16 @@ class _EngineMixin:
             params.append(self.task_prefix_embeds)
         return (self.engine_dtype, str(params[0].device), int(self.tokenizer.eos_token_id),
                 tuple((p.data_ptr(), p._version) for p in params))
+
+    def invalidate_engine(self) -> None:
+        """Drop the packed weight copies; the next `generate` re-derives them from the module's current parameters.  Needed only
+        after in-place edits through `p.data` (EMA, clipping, HF-style `_init_weights`), which the `(data_ptr, _version)` key
+        cannot see."""
+        with _ENGINE_LOCK:
+            for old in self.__dict__.get("_engines", {}).values():
+                old.close()
+            self.__dict__.get("_engines", {}).clear()
+            self.__dict__["_engine_key_cached"] = None
 
     def _get_engine(self) -> CaptionEngine:
         """The engine of the calling thread's slot (inflight.current_slot(); slot 0 outside inflight.map_batches).  Every slot
@@ -198,6 +214,12 @@ class ImageCaptioningModel(_EngineMixin, nn.Module):
         missing = [k for k in result.missing_keys if not k.startswith("gpt.")]
         if missing:
             raise ValueError(f"Missing keys found in the checkpoint that are not from frozen GPT weights: {missing}")
+        self.invalidate_engine()
+
+    def train(self, mode: bool = True):
+        if mode:  # weights are about to change; `generate` re-packs them on its next call
+            self.invalidate_engine()
+        return super().train(mode)
 
 
 class RetrievalAggregator(nn.Module):
@@ -227,7 +249,8 @@ class RetrievalAggregator(nn.Module):
 
 class RetrievalAugmentedTransformer(ImageCaptioningModel):
     """RAT: kNN over the image matrix -> caption rows -> aggregate + add -> generate (src/models.py:628-785).
-    `db_store` is a `gpt2_image_captioning_b200.database.GpuFlatStore` (FAISS-flavoured duck type, src/models.py:673)."""
+    `db_store` is a `gpt2_image_captioning_b200.database.GpuFlatStore` or any FAISS-flavoured store of the reference
+    (duck type of src/models.py:673; uploaded to HBM once and cached, see `_device_store`)."""
 
     def __init__(self, embed_dim: int, max_workers: int = 4,
                  aggregation_type: Literal["mean", "max", "sum_norm", "attention"] = "mean", *args, **kwargs) -> None:
@@ -235,23 +258,57 @@ class RetrievalAugmentedTransformer(ImageCaptioningModel):
         self.max_workers = max_workers
         self.aggregator = RetrievalAggregator(embed_dim, aggregation_type)
 
+    def _device_store(self, db_store):
+        """The HBM-resident store behind `db_store`.  A `GpuFlatStore` is used as it is; any other FAISS-flavoured store --
+        the reference dispatches on `hasattr(db_store, "image_index")` (src/models.py:673) and its callers pass
+        `create_faiss_store(...)` straight in (src/eval.py:281-289) -- is uploaded ONCE (raw vectors of both indices + metadata,
+        `GpuFlatStore.from_faiss_store`) and cached per store object."""
+        if hasattr(db_store, "retrieve_and_aggregate"):
+            return db_store
+        if not hasattr(db_store, "image_index"):
+            raise NotImplementedError("only FAISS-flavoured stores (objects with .image_index / .caption_index, src/models.py:673) run on "
+                                      "the B200 path; the ObjectBox backend of the reference is out of scope (SURVEY.md section 2, row 6)")
+        from .database import GpuFlatStore
+
+        cache = self.__dict__.setdefault("_store_cache", {})
+        hit = cache.get(id(db_store))
+        if hit is not None and hit[0]() is db_store:
+            return hit[1]
+        import weakref
+
+        dev = next(self.mapping_network.parameters()).device
+        gpu_store = GpuFlatStore.from_faiss_store(db_store, device=dev)
+        try:
+            ref = weakref.ref(db_store, lambda _r, k=id(db_store): cache.pop(k, None))
+        except TypeError:  # not weak-referenceable: keep it alive with the cache entry
+            ref = (lambda obj: (lambda: obj))(db_store)
+        cache[id(db_store)] = (ref, gpu_store)
+        return gpu_store
+
     def _augment(self, db_store, image_embeddings: torch.Tensor, top_i: int, top_k: int) -> torch.Tensor:
-        if not hasattr(db_store, "retrieve_and_aggregate"):
-            raise TypeError("db_store must be a gpt2_image_captioning_b200.database.GpuFlatStore (build one with "
-                            "GpuFlatStore.from_faiss_store(store) or GpuFlatStore(image_matrix, caption_matrix, ...))")
+        """Fused, non-differentiable retrieve + pool + add for `generate` (runs under no_grad on detached tensors)."""
+        store = self._device_store(db_store)
         kind = self.aggregator.aggregation_type
         if kind == "attention":  # learned pooling (src/models.py:606-616), fused with the gather like the other modes
             proj = self.aggregator.attention_proj
-            return db_store.retrieve_and_aggregate(image_embeddings, top_i=top_i, top_k=top_k, aggregation=kind,
-                                                   attention_weight=proj.weight, attention_bias=proj.bias)
-        return db_store.retrieve_and_aggregate(image_embeddings, top_i=top_i, top_k=top_k, aggregation=kind)
+            return store.retrieve_and_aggregate(image_embeddings, top_i=top_i, top_k=top_k, aggregation=kind,
+                                                attention_weight=proj.weight, attention_bias=proj.bias)
+        return store.retrieve_and_aggregate(image_embeddings, top_i=top_i, top_k=top_k, aggregation=kind)
 
     def _retrieve_batch(self, db_store, image_embeddings: torch.Tensor, top_i: int, top_k: int) -> torch.Tensor:
-        return db_store.retrieve_caption_embeddings(image_embeddings, top_i=top_i, top_k=top_k)
+        """float32 [B, top_k, E] retrieved caption embeddings on the input's device (src/models.py:655-695), a constant w.r.t. autograd
+        exactly as in the reference (which goes through numpy)."""
+        store = self._device_store(db_store)
+        with torch.no_grad():
+            out = store.retrieve_caption_embeddings(image_embeddings.detach(), top_i=top_i, top_k=top_k)
+        return out.to(image_embeddings.device)
 
     def forward(self, db_store, top_i: int, top_k: int, caption_token_ids: torch.Tensor, image_embeddings: torch.Tensor,
                 attention_mask: torch.Tensor | None = None, labels: torch.Tensor | None = None):
-        augmented = self._augment(db_store, image_embeddings, top_i, top_k)
+        # training path (src/models.py:717-746): retrieval is a constant, pooling + add go through the differentiable module so
+        # that `aggregator.attention_proj` (and anything upstream of image_embeddings) receives gradients
+        retrieved = self._retrieve_batch(db_store, image_embeddings, top_i, top_k)
+        augmented = self.aggregator(image_embeddings, retrieved)
         return super().forward(caption_token_ids=caption_token_ids, image_embeddings=augmented, attention_mask=attention_mask,
                                labels=labels)
 

@@ -173,7 +173,8 @@ def round_bf16(t: torch.Tensor) -> torch.Tensor:
     return t.bfloat16().float()
 
 
-def gpt2_forward(w: dict, inputs_embeds: torch.Tensor, kv: list | None = None, last_only: bool = False, rnd=_identity):
+def gpt2_forward(w: dict, inputs_embeds: torch.Tensor, kv: list | None = None, last_only: bool = False, rnd=_identity,
+                 rnd_w=None, rnd_kv=None, rnd_head=None):
     """GPT2LMHeadModel.forward(inputs_embeds=) restated (HF:models/gpt2/modeling_gpt2.py:658-726,
     GPT2Model.forward :522-636, GPT2Block :262-309, GPT2Attention :144-226, GPT2MLP :238-243).
 
@@ -184,17 +185,22 @@ def gpt2_forward(w: dict, inputs_embeds: torch.Tensor, kv: list | None = None, l
     `rnd` (identity by default) is applied wherever the CUDA engine's bf16 mode stores a GEMM operand or the KV
     cache in bfloat16 (LayerNorm outputs, q/k/v, attention output, GELU output, every weight matrix): with
     rnd=round_bf16 this is a CPU emulation of that mode (fp32 accumulation, residual stream and logits), used to
-    separate "bf16 rounding" from "kernel bug" in the parity tests.
+    separate "bf16 rounding" from "kernel bug" in the parity tests.  `rnd_w` / `rnd_kv` (default: same as
+    `rnd`) give the weight matrices and the q/k/v (KV-cache) stores their own rounding, so that mixed
+    schemes (fp16 activations with split weights, fp32 KV ...) can be screened on the CPU; `rnd_head` = (activation,
+    weight) roundings of the LM head alone (default: those of the body).
     Returns fp32 logits [B, T, V] (or [B, 1, V] if last_only)."""
     B, T, d = inputs_embeds.shape
     H = w["n_head"]
     hd = d // H
+    rw = rnd if rnd_w is None else rnd_w
+    rkv = rnd if rnd_kv is None else rnd_kv
     past = 0 if not kv or kv[0] is None else kv[0][0].shape[2]
     pos = torch.arange(past, past + T)
     h = inputs_embeds + w["wpe"][pos]  # HF :579-585 -- prefix tokens also get wpe
     for li, lw in enumerate(w["layers"]):
         a = rnd(layer_norm(h, lw["ln1_w"], lw["ln1_b"]))
-        qkv = rnd(a @ rnd(lw["attn_w"]) + lw["attn_b"])  # Conv1D = addmm(bias, x, W[in,out])
+        qkv = rkv(a @ rw(lw["attn_w"]) + lw["attn_b"])  # Conv1D = addmm(bias, x, W[in,out])
         q, k, v = qkv.split(d, dim=-1)
         q = q.view(B, T, H, hd).transpose(1, 2)
         k = k.view(B, T, H, hd).transpose(1, 2)
@@ -209,13 +215,14 @@ def gpt2_forward(w: dict, inputs_embeds: torch.Tensor, kv: list | None = None, l
         causal = torch.ones(S, S, dtype=torch.bool).tril()[S - T:, :]
         att = att.masked_fill(~causal, float("-inf")).softmax(-1)
         o = rnd((att @ v).transpose(1, 2).reshape(B, T, d))
-        h = h + (o @ rnd(lw["proj_w"]) + lw["proj_b"])
+        h = h + (o @ rw(lw["proj_w"]) + lw["proj_b"])
         m = rnd(layer_norm(h, lw["ln2_w"], lw["ln2_b"]))
-        h = h + (rnd(gelu_new(m @ rnd(lw["fc_w"]) + lw["fc_b"])) @ rnd(lw["fc2_w"]) + lw["fc2_b"])
+        h = h + (rnd(gelu_new(m @ rw(lw["fc_w"]) + lw["fc_b"])) @ rw(lw["fc2_w"]) + lw["fc2_b"])
     if last_only:
         h = h[:, -1:, :]
-    h = rnd(layer_norm(h, w["lnf_w"], w["lnf_b"]))
-    return h @ rnd(w["wte"]).t()
+    rha, rhw = (rnd, rw) if rnd_head is None else rnd_head
+    h = rha(layer_norm(h, w["lnf_w"], w["lnf_b"]))
+    return h @ rhw(w["wte"]).t()
 
 
 def mlp_mapper(mw: dict, x: torch.Tensor, prefix_length: int, rnd=_identity) -> torch.Tensor:
