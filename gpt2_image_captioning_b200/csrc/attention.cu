@@ -19,6 +19,8 @@
 // KV cache layout (one layer): K [rows][H][T_max][64], V the same; element type T (bf16 or fp32).
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "kernels.cuh"
 
 namespace gic {
@@ -376,15 +378,40 @@ __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
-// D (+)= A . B, A rows 8..15 are zero (a1 = a3 = 0): only c0, c1 (row = lane / 4) are meaningful
+// D (+)= A . B, A rows 8..15 are zero (a1 = a3 = 0): only c0, c1 (row = lane / 4) are meaningful.
+// F16: the operands are IEEE half (q / K / V / P of the bf16x2 engine, whose KV cache is fp16: 11 significant bits in the same
+// 2 bytes -- rounding q / k / v to bf16 alone costs 6 % of the captions on random-init weights, to fp16 none,
+// profiles/r2_precision_screen.jsonl KVonly_*)
+template <bool F16>
 __device__ __forceinline__ void mma_16816_top(float& c0, float& c1, float& c2, float& c3, uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
-               : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+  if (F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                 : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c0), "+f"(c1), "+f"(c2), "+f"(c3)
+                 : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+// 16-bit operand pair in the kernel's element type, and the value a single element rounds to
+template <bool F16> __device__ __forceinline__ uint32_t pack_op2(float lo, float hi) { return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+template <bool F16> __device__ __forceinline__ float round_op(float v) { return F16 ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v)); }
+// q * 1/8 on a packed pair (1/sqrt(64), HF :211-220 sdpa default scale; exact in both formats short of underflow)
+template <bool F16> __device__ __forceinline__ uint32_t scale_eighth(uint32_t q) {
+  if (F16) {
+    const __half2 v = __hmul2(*reinterpret_cast<const __half2*>(&q), __floats2half2_rn(0.125f, 0.125f));
+    return *reinterpret_cast<const uint32_t*>(&v);
+  }
+  const __nv_bfloat162 v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&q), __floats2bfloat162_rn(0.125f, 0.125f));
+  return *reinterpret_cast<const uint32_t*>(&v);
 }
 
 constexpr float LOG2E = 1.4426950408889634f;
@@ -397,9 +424,12 @@ struct DecMmaCfg { static constexpr int SMEM_BYTES = WARPS * STAGES * MMA_STAGE_
 // ((r / beams) * beams), position n_prefix + g from cache row anc[r * anc_ld + g] -- the row that generated the g-th token of r's
 // current hypothesis (beam_ancestry_kernel) -- and the new token is appended to r's own row.  This replaces HF's
 // DynamicCache.reorder_cache (HF:cache_utils.py:81-85), a 2 x 28 GB gather per step at config 3.
-template <int WARPS, int STAGES, bool INDIRECT>
+// F16: q / k / v and the cache are IEEE half (typed bf16* here: 2-byte elements either way) and the output is written as a bf16
+// hi + lo pair (out, out_lo) -- the A operand of the bf16x2 c_proj GEMM.
+template <int WARPS, int STAGES, bool INDIRECT, bool F16 = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos,
-                                                                      int rows, int H, int t_max, const int* anc, int anc_ld, int n_prefix, int beams, StepTrace step_trace) {
+                                                                      int rows, int H, int t_max, const int* anc, int anc_ld, int n_prefix, int beams, StepTrace step_trace,
+                                                                      bf16* out_lo) {
   extern __shared__ uint8_t dec_smem_raw[];
   const uint32_t smem_base = (dec_smem_u32(dec_smem_raw) + 127u) & ~127u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -483,7 +513,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
     vnew_n = __ldcg(reinterpret_cast<const uint4*>(qrow + 2 * d) + (lane & 7));
   };
   if (my_items > 0) load_new(w0);
-  const __nv_bfloat162 eighth = __floats2bfloat162_rn(0.125f, 0.125f);  // 1/sqrt(64), HF :211-220 (sdpa default scale); exact in bf16
   // ldmatrix row addresses inside a stage (r = lane & 7 is the matrix row, m = lane >> 3 the matrix of the x4):
   //   K (plain): key 8 (m >> 1) + r, 16-byte column (2 ks + (m & 1)) ^ r   ->  (b0, b1) of n-tile 0, then of n-tile 1
   //   V (trans): key 8 (m & 1) + r, 16-byte column (2 jj + (m >> 1)) ^ r   ->  (b0, b1) of accumulator 2 jj, then of 2 jj + 1
@@ -498,10 +527,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
     const int item = w0 + ii * wstride;
     uint32_t qa[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      __nv_bfloat162 v = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&qa_n[i]), eighth);
-      qa[i] = *reinterpret_cast<uint32_t*>(&v);
-    }
+    for (int i = 0; i < 8; ++i) qa[i] = scale_eighth<F16>(qa_n[i]);
     const uint4 knew = knew_n, vnew = vnew_n;
     if (ii + 1 < my_items) load_new(item + wstride);
     float m = -INFINITY, l = 0.f;  // running maximum (warp-uniform) and this lane's share of the running sum
@@ -532,10 +558,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
         uint32_t b00, b01, b10, b11, c00, c01, c10, c11;
         ldsm_x4(st + k_row_off + 16 * ((2 * ks + mlo) ^ r8), b00, b01, b10, b11);
         ldsm_x4(st + k_row_off + 16 * ((2 * ks + 2 + mlo) ^ r8), c00, c01, c10, c11);
-        mma_16816_top(s0[0], s0[1], s0[2], s0[3], qa[2 * ks], qa[2 * ks + 1], b00, b01);
-        mma_16816_top(s1[0], s1[1], s1[2], s1[3], qa[2 * ks], qa[2 * ks + 1], b10, b11);
-        mma_16816_top(u0[0], u0[1], u0[2], u0[3], qa[2 * ks + 2], qa[2 * ks + 3], c00, c01);
-        mma_16816_top(u1[0], u1[1], u1[2], u1[3], qa[2 * ks + 2], qa[2 * ks + 3], c10, c11);
+        mma_16816_top<F16>(s0[0], s0[1], s0[2], s0[3], qa[2 * ks], qa[2 * ks + 1], b00, b01);
+        mma_16816_top<F16>(s1[0], s1[1], s1[2], s1[3], qa[2 * ks], qa[2 * ks + 1], b10, b11);
+        mma_16816_top<F16>(u0[0], u0[1], u0[2], u0[3], qa[2 * ks + 2], qa[2 * ks + 3], c00, c01);
+        mma_16816_top<F16>(u1[0], u1[1], u1[2], u1[3], qa[2 * ks + 2], qa[2 * ks + 3], c10, c11);
       }
       // slots >= nkeys hold stale bytes -> masked by selection
       float sv0 = odd ? s0[1] + u0[1] : s0[0] + u0[0], sv1 = odd ? s1[1] + u1[1] : s1[0] + u1[0];  // keys g and 8 + g (meaningful on the diagonal lanes)
@@ -550,9 +576,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
       const float p0 = exp2f(fmaf(sv0, LOG2E, -mnl)), p1 = exp2f(fmaf(sv1, LOG2E, -mnl));  // 0 off the diagonal and for masked slots
       l = l * scale + (p0 + p1);
       // P as bf16 hi + lo, in row g at k = g (a0) and k = 8 + g (a2): element g & 1 of the register pair
-      const float p0h = __bfloat162float(__float2bfloat16_rn(p0)), p1h = __bfloat162float(__float2bfloat16_rn(p1));
-      const uint32_t a0h = odd ? pack_bf16x2(0.f, p0h) : pack_bf16x2(p0h, 0.f), a2h = odd ? pack_bf16x2(0.f, p1h) : pack_bf16x2(p1h, 0.f);
-      const uint32_t a0l = odd ? pack_bf16x2(0.f, p0 - p0h) : pack_bf16x2(p0 - p0h, 0.f), a2l = odd ? pack_bf16x2(0.f, p1 - p1h) : pack_bf16x2(p1 - p1h, 0.f);
+      const float p0h = round_op<F16>(p0), p1h = round_op<F16>(p1);
+      const uint32_t a0h = odd ? pack_op2<F16>(0.f, p0h) : pack_op2<F16>(p0h, 0.f), a2h = odd ? pack_op2<F16>(0.f, p1h) : pack_op2<F16>(p1h, 0.f);
+      const uint32_t a0l = odd ? pack_op2<F16>(0.f, p0 - p0h) : pack_op2<F16>(p0 - p0h, 0.f), a2l = odd ? pack_op2<F16>(0.f, p1 - p1h) : pack_op2<F16>(p1 - p1h, 0.f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { o[j][0] *= scale; o[j][1] *= scale; }
       // ---- O += P . V (accumulator j of row r: dims column j ^ r, keys = r mod 8) ----
@@ -560,10 +586,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
       for (int jj = 0; jj < 4; ++jj) {
         uint32_t v00, v01, v10, v11;
         ldsm_x4_trans(st + v_row_off + 16 * ((2 * jj + mhi) ^ r8), v00, v01, v10, v11);
-        mma_16816_top(o[2 * jj][0], o[2 * jj][1], o[2 * jj][2], o[2 * jj][3], a0h, a2h, v00, v01);
-        mma_16816_top(o[2 * jj + 1][0], o[2 * jj + 1][1], o[2 * jj + 1][2], o[2 * jj + 1][3], a0h, a2h, v10, v11);
-        mma_16816_top(o[2 * jj][0], o[2 * jj][1], o[2 * jj][2], o[2 * jj][3], a0l, a2l, v00, v01);
-        mma_16816_top(o[2 * jj + 1][0], o[2 * jj + 1][1], o[2 * jj + 1][2], o[2 * jj + 1][3], a0l, a2l, v10, v11);
+        mma_16816_top<F16>(o[2 * jj][0], o[2 * jj][1], o[2 * jj][2], o[2 * jj][3], a0h, a2h, v00, v01);
+        mma_16816_top<F16>(o[2 * jj + 1][0], o[2 * jj + 1][1], o[2 * jj + 1][2], o[2 * jj + 1][3], a0h, a2h, v10, v11);
+        mma_16816_top<F16>(o[2 * jj][0], o[2 * jj][1], o[2 * jj][2], o[2 * jj][3], a0l, a2l, v00, v01);
+        mma_16816_top<F16>(o[2 * jj + 1][0], o[2 * jj + 1][1], o[2 * jj + 1][2], o[2 * jj + 1][3], a0l, a2l, v10, v11);
       }
       if (last) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the new token's row before a later copy overwrites it
       __syncwarp();  // every lane is done reading this stage before lane 0 may refill it (next iteration's issue)
@@ -587,7 +613,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
     o[0][0] += __shfl_xor_sync(0xffffffffu, o[4][0], 16);
     o[0][1] += __shfl_xor_sync(0xffffffffu, o[4][1], 16);
     // out row of the item = item * 64 elements (row * d + head * 64): dims 8 g + 2 t, + 1 -> one 128-byte row per warp
-    *reinterpret_cast<uint32_t*>(out + (size_t)item * HD + 8 * g + 2 * t) = pack_bf16x2(o[0][0] * inv, o[0][1] * inv);
+    const float y0 = o[0][0] * inv, y1 = o[0][1] * inv;
+    const uint32_t yh = pack_bf16x2(y0, y1);
+    *reinterpret_cast<uint32_t*>(out + (size_t)item * HD + 8 * g + 2 * t) = yh;
+    if (F16) {  // the bf16x2 engine's operand: remainder of the bf16 rounding
+      const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yh));
+      *reinterpret_cast<uint32_t*>(out_lo + (size_t)item * HD + 8 * g + 2 * t) = pack_bf16x2(y0 - yf.x, y1 - yf.y);
+    }
   }
   trace_end(step_trace, tslot);
 }
@@ -610,6 +642,8 @@ int attn_decode_configure() {
   GIC_DEC_MMA_VARIANTS(X)
 #undef X
   GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<12, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<12, 4>::SMEM_BYTES));
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<12, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<12, 4>::SMEM_BYTES));
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<12, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<12, 4>::SMEM_BYTES));
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
@@ -636,7 +670,7 @@ static int launch_attn_decode_bulk(const bf16* qkv, bf16* kcache, bf16* vcache, 
   if (g_dec_variant == ID) {                                                                                                         \
     const int grid = min(sms, ceil_div(items, W));                                                                                   \
     GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<W, S, false>, dim3(grid), dim3(W * 32), (size_t)DecMmaCfg<W, S>::SMEM_BYTES, st, qkv, kcache, \
-                                 vcache, out, d_pos, rows, H, t_max, (const int*)nullptr, 0, 0, 1, trace_desc()));                                 \
+                                 vcache, out, d_pos, rows, H, t_max, (const int*)nullptr, 0, 0, 1, trace_desc(), (bf16*)nullptr));                 \
     note_launch();                                                                                                                   \
     return GIC_OK;                                                                                                                   \
   }
@@ -648,13 +682,31 @@ static int launch_attn_decode_bulk(const bf16* qkv, bf16* kcache, bf16* vcache, 
 
 // beam search without cache reordering (see attn_decode_mma_kernel INDIRECT)
 int launch_attn_decode_indirect(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos, int rows, int H, int t_max, const int* anc,
-                                int anc_ld, int n_prefix, int beams, cudaStream_t st) {
+                                int anc_ld, int n_prefix, int beams, cudaStream_t st, bf16* out_lo) {
   GIC_TRY(attn_decode_configure());
   GIC_REQUIRE(anc != nullptr && beams >= 1 && n_prefix >= 0, "attn_decode_indirect: bad ancestry arguments");
   const int sms = cta_limit() > 0 && cta_limit() < g_dec_sms ? cta_limit() : g_dec_sms;
   const int grid = min(sms, ceil_div(rows * H, 12));
-  GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<12, 4, true>, dim3(grid), dim3(12 * 32), (size_t)DecMmaCfg<12, 4>::SMEM_BYTES, st, qkv, kcache, vcache,
-                               out, d_pos, rows, H, t_max, anc, anc_ld, n_prefix, beams, trace_desc()));
+  if (out_lo)  // fp16 q / k / v / cache, hi + lo output (bf16x2 engine)
+    GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<12, 4, true, true>, dim3(grid), dim3(12 * 32), (size_t)DecMmaCfg<12, 4>::SMEM_BYTES, st, qkv, kcache,
+                                 vcache, out, d_pos, rows, H, t_max, anc, anc_ld, n_prefix, beams, trace_desc(), out_lo));
+  else
+    GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<12, 4, true>, dim3(grid), dim3(12 * 32), (size_t)DecMmaCfg<12, 4>::SMEM_BYTES, st, qkv, kcache, vcache,
+                                 out, d_pos, rows, H, t_max, anc, anc_ld, n_prefix, beams, trace_desc(), (bf16*)nullptr));
+  note_launch();
+  return GIC_OK;
+}
+
+// decode attention of the bf16x2 engine: fp16 q | k | v and KV cache (2-byte elements, typed bf16* for the shared plumbing), output as a
+// bf16 hi + lo pair
+int launch_attn_decode_f16(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out_hi, bf16* out_lo, const int* d_pos, int rows, int H, int t_max,
+                           cudaStream_t st) {
+  GIC_TRY(attn_decode_configure());
+  GIC_REQUIRE(out_hi && out_lo, "attn_decode_f16: needs both output halves");
+  const int sms = cta_limit() > 0 && cta_limit() < g_dec_sms ? cta_limit() : g_dec_sms;
+  const int grid = min(sms, ceil_div(rows * H, 12));
+  GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<12, 4, false, true>, dim3(grid), dim3(12 * 32), (size_t)DecMmaCfg<12, 4>::SMEM_BYTES, st, qkv, kcache,
+                               vcache, out_hi, d_pos, rows, H, t_max, (const int*)nullptr, 0, 0, 1, trace_desc(), out_lo));
   note_launch();
   return GIC_OK;
 }
@@ -783,15 +835,22 @@ static int launch_attn_seq(const T* qkv, T* kcache, T* vcache, ActOut out, int B
 // (FlashAttention-2 register reuse: the score accumulators become the P operand; P as bf16 hi + lo like the decode kernel).
 // attn_seq_kernel does the same job in 68 us per layer for B = 1024, P = 10 (scalar loads, one shuffle tree per key).
 // ---------------------------------------------------------------------------------------------------------------
+template <bool F16>
 __device__ __forceinline__ void mma_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  if (F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int NBLK>  // 16-token blocks staged per item: S <= 16 NBLK
+// F16: fp16 q / k / v / cache and a bf16 hi + lo output pair (out, out_lo), as in attn_decode_mma_kernel
+template <int NBLK, bool F16 = false>  // 16-token blocks staged per item: S <= 16 NBLK
 __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, int n_items, int S, int H,
-                                                             int t_max, int cache_row_mult) {
+                                                             int t_max, int cache_row_mult, bf16* out_lo) {
   constexpr int SP = 16 * NBLK;             // staged rows per matrix
   constexpr int MAT_BYTES = SP * HD * 2;    // q, k or v of one item
   extern __shared__ uint8_t pre_smem_raw[];
@@ -804,8 +863,7 @@ __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(const bf16* qkv, 
   if (item >= n_items) return;
   const int row = item / H, h = item - row * H;
   const int d = H * HD;
-  const __nv_bfloat162 eighth = __floats2bfloat162_rn(0.125f, 0.125f);  // 1/sqrt(64), exact in bf16
-  // ---- stage q (pre-scaled), k, v; append k, v to the cache (HF:cache_utils.py:102-121) ----
+  // ---- stage q (pre-scaled by 1/sqrt(64)), k, v; append k, v to the cache (HF:cache_utils.py:102-121) ----
   for (int i = lane; i < SP * 8; i += 32) {
     const int t = i >> 3, c = i & 7;
     uint4 qv = make_uint4(0, 0, 0, 0), kv = qv, vv = qv;  // rows >= S: zeros (P = 0 times V must stay finite)
@@ -817,9 +875,7 @@ __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(const bf16* qkv, 
       const size_t ci = (((size_t)row * cache_row_mult * H + h) * t_max + t) * HD + c * 8;
       *reinterpret_cast<uint4*>(kcache + ci) = kv;
       *reinterpret_cast<uint4*>(vcache + ci) = vv;
-      __nv_bfloat162* q2 = reinterpret_cast<__nv_bfloat162*>(&qv);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) q2[u] = __hmul2(q2[u], eighth);
+      qv.x = scale_eighth<F16>(qv.x); qv.y = scale_eighth<F16>(qv.y); qv.z = scale_eighth<F16>(qv.z); qv.w = scale_eighth<F16>(qv.w);
     }
     const uint32_t off = (uint32_t)(t * (HD * 2) + ((c ^ (t & 7)) << 4));
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(qs + off), "r"(qv.x), "r"(qv.y), "r"(qv.z), "r"(qv.w) : "memory");
@@ -850,8 +906,8 @@ __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(const bf16* qkv, 
         for (int kk = 0; kk < 4; ++kk) {
           uint32_t b00, b01, b10, b11;
           ldsm_x4(ks + krow * (HD * 2) + (((2 * kk + mlo) ^ (krow & 7)) << 4), b00, b01, b10, b11);
-          mma_16816(s0, qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b00, b01);
-          mma_16816(s1, qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b10, b11);
+          mma_16816<F16>(s0, qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b00, b01);
+          mma_16816<F16>(s1, qa[kk][0], qa[kk][1], qa[kk][2], qa[kk][3], b10, b11);
         }
       }
       // causal mask (HF GPT2Attention is_causal): key index <= query index; s?[0..1] row g, s?[2..3] row g + 8
@@ -882,10 +938,9 @@ __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(const bf16* qkv, 
       uint32_t ph[4], pl[4];  // A fragments of P: (row g, keys 2t..), (row g + 8, keys 2t..), (row g, keys 8 + 2t..), (row g + 8, keys 8 + 2t..)
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(p[2 * u], p[2 * u + 1]);
-        const float2 hf = __bfloat1622float2(hh);
-        ph[u] = *reinterpret_cast<const uint32_t*>(&hh);
-        pl[u] = pack_bf16x2(p[2 * u] - hf.x, p[2 * u + 1] - hf.y);
+        const float h0 = round_op<F16>(p[2 * u]), h1 = round_op<F16>(p[2 * u + 1]);
+        ph[u] = pack_op2<F16>(h0, h1);
+        pl[u] = pack_op2<F16>(p[2 * u] - h0, p[2 * u + 1] - h1);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) { o[j][0] *= sc0; o[j][1] *= sc0; o[j][2] *= sc1; o[j][3] *= sc1; }
@@ -895,10 +950,10 @@ __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(const bf16* qkv, 
         for (int jj = 0; jj < 4; ++jj) {
           uint32_t v00, v01, v10, v11;
           ldsm_x4_trans(vs + vrow * (HD * 2) + (((2 * jj + mhi) ^ (vrow & 7)) << 4), v00, v01, v10, v11);
-          mma_16816(o[2 * jj], ph[0], ph[1], ph[2], ph[3], v00, v01);
-          mma_16816(o[2 * jj + 1], ph[0], ph[1], ph[2], ph[3], v10, v11);
-          mma_16816(o[2 * jj], pl[0], pl[1], pl[2], pl[3], v00, v01);
-          mma_16816(o[2 * jj + 1], pl[0], pl[1], pl[2], pl[3], v10, v11);
+          mma_16816<F16>(o[2 * jj], ph[0], ph[1], ph[2], ph[3], v00, v01);
+          mma_16816<F16>(o[2 * jj + 1], ph[0], ph[1], ph[2], ph[3], v10, v11);
+          mma_16816<F16>(o[2 * jj], pl[0], pl[1], pl[2], pl[3], v00, v01);
+          mma_16816<F16>(o[2 * jj + 1], pl[0], pl[1], pl[2], pl[3], v10, v11);
         }
       }
     }
@@ -906,37 +961,59 @@ __global__ void __launch_bounds__(128) attn_prefill_mma_kernel(const bf16* qkv, 
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
     // the block's 16 output rows go back through the (now consumed) q rows of this block, then out as whole 16-byte chunks
-    __syncwarp();
+    // (F16: a second pass carries the remainders of the bf16 rounding to out_lo)
+#pragma unroll 1
+    for (int pass = 0; pass < (F16 ? 2 : 1); ++pass) {
+      __syncwarp();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ra = qb * 16 + g, rb = ra + 8;
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(qs + ra * (HD * 2) + ((j ^ (ra & 7)) << 4) + t4 * 4), "r"(pack_bf16x2(o[j][0] * i0, o[j][1] * i0)) : "memory");
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(qs + rb * (HD * 2) + ((j ^ (rb & 7)) << 4) + t4 * 4), "r"(pack_bf16x2(o[j][2] * i1, o[j][3] * i1)) : "memory");
-    }
-    __syncwarp();
-    for (int i = lane; i < 16 * 8; i += 32) {
-      const int tt = qb * 16 + (i >> 3), c = i & 7;
-      if (tt < S) {
-        uint4 v;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(qs + tt * (HD * 2) + ((c ^ (tt & 7)) << 4)));
-        *reinterpret_cast<uint4*>(out + ((size_t)row * S + tt) * d + h * HD + c * 8) = v;
+      for (int j = 0; j < 8; ++j) {
+        const int ra = qb * 16 + g, rb = ra + 8;
+        float y0 = o[j][0] * i0, y1 = o[j][1] * i0, y2 = o[j][2] * i1, y3 = o[j][3] * i1;
+        if (pass == 1) {
+          y0 -= __bfloat162float(__float2bfloat16_rn(y0)); y1 -= __bfloat162float(__float2bfloat16_rn(y1));
+          y2 -= __bfloat162float(__float2bfloat16_rn(y2)); y3 -= __bfloat162float(__float2bfloat16_rn(y3));
+        }
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(qs + ra * (HD * 2) + ((j ^ (ra & 7)) << 4) + t4 * 4), "r"(pack_bf16x2(y0, y1)) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(qs + rb * (HD * 2) + ((j ^ (rb & 7)) << 4) + t4 * 4), "r"(pack_bf16x2(y2, y3)) : "memory");
+      }
+      __syncwarp();
+      bf16* dst = pass == 0 ? out : out_lo;
+      for (int i = lane; i < 16 * 8; i += 32) {
+        const int tt = qb * 16 + (i >> 3), c = i & 7;
+        if (tt < S) {
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(qs + tt * (HD * 2) + ((c ^ (tt & 7)) << 4)));
+          *reinterpret_cast<uint4*>(dst + ((size_t)row * S + tt) * d + h * HD + c * 8) = v;
+        }
       }
     }
   }
 }
 
-template <int NBLK>
+template <int NBLK, bool F16 = false>
 static int launch_attn_prefill_mma(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, int B, int S, int H, int t_max, int cache_row_mult,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, bf16* out_lo = nullptr) {
   const size_t smem = (size_t)4 * 3 * (16 * NBLK) * HD * 2 + 128;
-  auto kern = attn_prefill_mma_kernel<NBLK>;
-  static bool configured = false;
-  if (!configured && smem > 48 * 1024) GIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  configured = true;
+  auto kern = attn_prefill_mma_kernel<NBLK, F16>;
+  static std::atomic<bool> configured{false};
+  if (!configured.load(std::memory_order_acquire) && smem > 48 * 1024) GIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  configured.store(true, std::memory_order_release);
   const int items = B * H;
-  GIC_CHECK_CUDA(launch_kernel(kern, dim3(ceil_div(items, 4)), dim3(128), smem, st, qkv, kcache, vcache, out, items, S, H, t_max, cache_row_mult));
+  GIC_CHECK_CUDA(launch_kernel(kern, dim3(ceil_div(items, 4)), dim3(128), smem, st, qkv, kcache, vcache, out, items, S, H, t_max, cache_row_mult, out_lo));
   note_launch();
   return GIC_OK;
+}
+
+// causal prefill attention of the bf16x2 engine (fp16 q | k | v and cache, hi + lo output); prefixes longer than 64 tokens are not
+// supported in this mode (the reference's configurations use 10 / 40 + a short task prompt)
+int launch_attn_prefill_f16(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out_hi, bf16* out_lo, int B, int P, int H, int t_max, int cache_row_mult,
+                            cudaStream_t st) {
+  GIC_REQUIRE(P <= t_max && out_hi && out_lo, "attn_prefill_f16: bad arguments");
+  GIC_REQUIRE(P <= 64, "bf16x2 engine: the prefix (image + task tokens) may hold at most 64 tokens, got %d", P);
+  if (P <= 16) return launch_attn_prefill_mma<1, true>(qkv, kcache, vcache, out_hi, B, P, H, t_max, cache_row_mult, st, out_lo);
+  if (P <= 32) return launch_attn_prefill_mma<2, true>(qkv, kcache, vcache, out_hi, B, P, H, t_max, cache_row_mult, st, out_lo);
+  if (P <= 48) return launch_attn_prefill_mma<3, true>(qkv, kcache, vcache, out_hi, B, P, H, t_max, cache_row_mult, st, out_lo);
+  return launch_attn_prefill_mma<4, true>(qkv, kcache, vcache, out_hi, B, P, H, t_max, cache_row_mult, st, out_lo);
 }
 
 template <typename T>

@@ -1,6 +1,7 @@
 // Shared helpers for the sm_100a caption-generation kernels.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>

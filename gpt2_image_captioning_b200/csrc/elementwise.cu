@@ -104,14 +104,15 @@ int launch_pack_weight(const float* in, int R, int C, bool transpose, ActOut out
 // The GEMM consumes the RAW rows (bf16 copy of the residual stream) and applies mean / rstd per row in its epilogue, so the
 // 25 LayerNorm launches of a decode step disappear (HF GPT2Block ln_1 / ln_2 and ln_f, HF:models/gpt2/modeling_gpt2.py:273,304,628).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) fold_ln_kernel(const bf16* __restrict__ w_packed, const float* __restrict__ w_src, bool transposed,
-                                                      const float* __restrict__ beta, const float* __restrict__ bias, float* __restrict__ colsum,
-                                                      float* __restrict__ bias_out, int N, int K) {
+__global__ void __launch_bounds__(128) fold_ln_kernel(const bf16* __restrict__ w_packed, const bf16* __restrict__ w_packed_lo, const float* __restrict__ w_src,
+                                                      bool transposed, const float* __restrict__ beta, const float* __restrict__ bias,
+                                                      float* __restrict__ colsum, float* __restrict__ bias_out, int N, int K) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (n >= N) return;
   float cs = 0.f, bs = 0.f;
   for (int k = lane; k < K; k += 32) {
     cs += __bfloat162float(w_packed[(size_t)n * K + k]);  // what the tensor core will really multiply by
+    if (w_packed_lo) cs += __bfloat162float(w_packed_lo[(size_t)n * K + k]);  // (bf16x2: hi + lo)
     bs += beta[k] * (transposed ? w_src[(size_t)k * N + n] : w_src[(size_t)n * K + k]);
   }
   cs = warp_sum(cs);
@@ -123,16 +124,16 @@ __global__ void __launch_bounds__(128) fold_ln_kernel(const bf16* __restrict__ w
 }
 
 int launch_fold_ln(const bf16* w_packed, const float* w_src, bool transposed, const float* beta, const float* bias, float* colsum,
-                   float* bias_out, int N, int K, cudaStream_t st) {
-  fold_ln_kernel<<<ceil_div(N, 4), 128, 0, st>>>(w_packed, w_src, transposed, beta, bias, colsum, bias_out, N, K);
+                   float* bias_out, int N, int K, cudaStream_t st, const bf16* w_packed_lo) {
+  fold_ln_kernel<<<ceil_div(N, 4), 128, 0, st>>>(w_packed, w_packed_lo, w_src, transposed, beta, bias, colsum, bias_out, N, K);
   GIC_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return GIC_OK;
 }
 
 template <int MAXV>
-__global__ void __launch_bounds__(128) row_stats_kernel(const float* x, long x_row_stride, bf16* __restrict__ xb, float2* __restrict__ stats,
-                                                        int rows, int d) {
+__global__ void __launch_bounds__(128) row_stats_kernel(const float* x, long x_row_stride, bf16* __restrict__ xb, bf16* __restrict__ xb_lo,
+                                                        float2* __restrict__ stats, int rows, int d) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -150,9 +151,14 @@ __global__ void __launch_bounds__(128) row_stats_kernel(const float* x, long x_r
   for (int i = 0; i < MAXV; ++i) {
     const int c = lane + i * 32;
     const bf16 b = __float2bfloat16_rn(v[i]);
-    const float f = __bfloat162float(b);
+    float f = __bfloat162float(b);
     if (c < d) {
       xb[(size_t)warp * d + c] = b;
+      if (xb_lo) {  // bf16x2: the operand is hi + lo (exact in fp32), and the statistics are those of the sum
+        const bf16 l = __float2bfloat16_rn(v[i] - f);
+        xb_lo[(size_t)warp * d + c] = l;
+        f += __bfloat162float(l);
+      }
       s += f;
       q += f * f;
     }
@@ -162,11 +168,11 @@ __global__ void __launch_bounds__(128) row_stats_kernel(const float* x, long x_r
   if (lane == 0) stats[warp] = make_float2(s, q);
 }
 
-int launch_row_stats(const float* x, long x_row_stride, bf16* xb, float2* stats, int rows, int d, cudaStream_t st) {
+int launch_row_stats(const float* x, long x_row_stride, bf16* xb, float2* stats, int rows, int d, cudaStream_t st, bf16* xb_lo) {
   GIC_REQUIRE(rows > 0 && d > 0 && d <= 32 * 40, "row_stats: unsupported rows=%d d=%d (d <= 1280)", rows, d);
   const int blocks = ceil_div(rows, 4);
   auto kern = d <= 32 * 4 ? row_stats_kernel<4> : d <= 32 * 24 ? row_stats_kernel<24> : d <= 32 * 32 ? row_stats_kernel<32> : row_stats_kernel<40>;
-  GIC_CHECK_CUDA(launch_kernel(kern, dim3(blocks), dim3(128), 0, st, x, x_row_stride, xb, stats, rows, d));
+  GIC_CHECK_CUDA(launch_kernel(kern, dim3(blocks), dim3(128), 0, st, x, x_row_stride, xb, xb_lo, stats, rows, d));
   note_launch();
   return GIC_OK;
 }

@@ -61,9 +61,9 @@ struct Workspace {
   float* prefix = nullptr;         // mapper output [B, P_img, d] fp32
   float* h = nullptr;              // residual stream [m_max, d] fp32
   float* h_dec = nullptr;          // decode residual [rows, d] fp32
-  float* qkv_f32 = nullptr;        // [m_max, 3d]  (F32 / BF16X2)
-  bf16* qkv_bf16 = nullptr;        //              (BF16)
-  void* kv = nullptr;              // [L][2][rows][H][t_max][64]
+  float* qkv_f32 = nullptr;        // [m_max, 3d]  (F32; BF16X2: the transformer mapper's encoder layers only)
+  bf16* qkv_bf16 = nullptr;        //              (BF16: bf16; BF16X2: IEEE half behind the same 2-byte type -- GPT-2 layers)
+  void* kv = nullptr;              // [L][2][rows][H][t_max][64]  (F32: float; BF16: bf16; BF16X2: IEEE half)
   size_t kv_layer_elems = 0;       // elements of one K (or V) plane of one layer
   float* logits = nullptr;         // [rows, V] fp32 (F32 mode)
   float* part_val = nullptr; int* part_idx = nullptr; int n_parts_max = 0;  // [rows][n_parts_max]
@@ -89,7 +89,7 @@ struct gic_engine {
   int d = 0, L = 0, H = 0, V = 0, P_img = 0, P_task = 0, E = 0;
   bool split = false;  // BF16X2
   bool beam_indirect = false;  // BF16 beam search: no KV reorder, decode attention reads through an ancestry table (GIC_BEAM_REORDER=1: gather)
-  bool fuse_ln = false;  // BF16: ln_1 / ln_2 folded into the GEMM that follows them (no LayerNorm launches inside the GPT-2 blocks)
+  bool fuse_ln = false;  // BF16 / BF16X2: ln_1 / ln_2 folded into the GEMM that follows them (no LayerNorm launches inside the GPT-2 blocks)
   bool use_splitk = false;  // GIC_SPLITK=1 turns the K split of the decode-size residual GEMMs on.  Off by default: measured round 1
                             // (profiles/r1w_microbench.txt), fc2 with a 3-way K split + last-CTA reduction takes 22 us against 15 us unsplit
   bool fuse_lnf = false; // ... and ln_f into the LM head (GIC_LNF_FUSE=1).  Off by default: measured round 1, the folded head re-reads the
@@ -213,10 +213,10 @@ static int pack_linear(gic_engine* e, Linear* lin, const float* w, const float* 
   const int R = transpose ? K : N, C = transpose ? N : K;
   GIC_TRY(launch_pack_weight(w, R, C, transpose, out, st, ln_gamma));
   if (ln_gamma) {
-    GIC_REQUIRE(e->tc && !e->split && ln_beta, "LayerNorm folding is a bf16-engine feature");
+    GIC_REQUIRE(e->tc && ln_beta, "LayerNorm folding is a tensor-core-engine feature");
     GIC_TRY(dev_alloc(e, (void**)&lin->colsum, (size_t)N * sizeof(float)));
     GIC_TRY(dev_alloc(e, (void**)&lin->bias, (size_t)N * sizeof(float)));
-    GIC_TRY(launch_fold_ln(lin->w_hi, w, transpose, ln_beta, bias, lin->colsum, lin->bias, N, K, st));
+    GIC_TRY(launch_fold_ln(lin->w_hi, w, transpose, ln_beta, bias, lin->colsum, lin->bias, N, K, st, lin->w_lo));
   } else if (bias) GIC_TRY(copy_vec(e, &lin->bias, bias, N, st));
   if (e->tc) {
     GIC_REQUIRE(K % 64 == 0, "tensor-core modes need K (%d) to be a multiple of 64", K);
@@ -256,6 +256,9 @@ static void carve_act(const gic_engine* e, Carver& c, Act* a, size_t n) {
   }
 }
 
+// the KV cache (and q | k | v) hold 2-byte elements: bf16 in the BF16 engine, IEEE half in the fused BF16X2 engine
+static bool kv16(const gic_engine* e) { return e->cfg.dtype == GIC_DTYPE_BF16 || (e->split && e->fuse_ln); }
+
 static void carve(const gic_engine* e, void* base, int B, int max_new, int beams, Workspace* w) {
   const int d = e->d;
   w->B = B; w->beams = beams < 1 ? 1 : beams; w->rows = B * w->beams; w->max_new = max_new;
@@ -276,11 +279,12 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
   carve_act(e, c, &w->a, (size_t)m * d);
   carve_act(e, c, &w->o, (size_t)m * d);
   carve_act(e, c, &w->f, (size_t)m * 4 * d);
-  if (e->cfg.dtype == GIC_DTYPE_BF16) w->qkv_bf16 = c.take<bf16>((size_t)m * 3 * d);
-  else w->qkv_f32 = c.take<float>((size_t)m * 3 * d);
+  if (kv16(e)) w->qkv_bf16 = c.take<bf16>((size_t)m * 3 * d);
+  if (!kv16(e)) w->qkv_f32 = c.take<float>((size_t)m * 3 * d);
+  else if (e->split && S_map > 0) w->qkv_f32 = c.take<float>((size_t)B * S_map * 3 * d);  // the transformer mapper's layers stay unfused
   w->kv_layer_elems = (size_t)w->rows * e->H * w->t_max * 64;
   const size_t kv_elems = (size_t)e->L * 2 * w->kv_layer_elems;
-  if (e->cfg.dtype == GIC_DTYPE_BF16) w->kv = c.take<bf16>(kv_elems);
+  if (kv16(e)) w->kv = c.take<bf16>(kv_elems);
   else w->kv = c.take<float>(kv_elems);
   if (!e->tc) {
     w->logits = c.take<float>((size_t)w->rows * e->V);
@@ -294,7 +298,7 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
     if (e->beam_indirect) {  // no second cache: attention follows the beams' ancestry instead
       bs.anc[0] = c.take<int>((size_t)w->rows * (max_new > 0 ? max_new : 1));
       bs.anc[1] = c.take<int>((size_t)w->rows * (max_new > 0 ? max_new : 1));
-    } else if (e->cfg.dtype == GIC_DTYPE_BF16) w->kv2 = c.take<bf16>(kv_elems);
+    } else if (kv16(e)) w->kv2 = c.take<bf16>(kv_elems);
     else w->kv2 = c.take<float>(kv_elems);
     const size_t nseq = (size_t)w->rows * (max_new > 0 ? max_new : 1);
     bs.B = B; bs.beams = w->beams; bs.max_new = max_new; bs.V = e->V; bs.eos = e->cfg.eos_token_id;
@@ -310,7 +314,7 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
     w->ln_parts_max = ceil_div(d, 32);
     w->ln_stats = c.take<float2>((size_t)w->ln_parts_max * m);
   }
-  if (e->tc && !e->split) {  // split-K is used by the decode-size residual GEMMs (few tiles, K up to 4 d)
+  if (e->tc && !e->split) {  // split-K may be used by the decode-size residual GEMMs (few tiles, K up to 4 d)
     w->splitk_ws_floats = (size_t)4 * w->rows * d;
     w->splitk_ws = c.take<float>(w->splitk_ws_floats);
     w->splitk_counters = c.take<int>(4096);
@@ -344,7 +348,8 @@ struct LnIo {
 static int residual_stats_parts(const gic_engine* e, int M) { (void)M; return ceil_div(e->d, 32); }
 
 static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, int epilogue, ActOut out, int ld_out, cudaStream_t st,
-                  float* part_val = nullptr, int* part_idx = nullptr, int* n_parts = nullptr, int part_ld = 0, const LnIo* ln = nullptr) {
+                  float* part_val = nullptr, int* part_idx = nullptr, int* n_parts = nullptr, int part_ld = 0, const LnIo* ln = nullptr,
+                  bool out_f16 = false) {
   if (!e->tc) {
     GIC_REQUIRE(out.f32 != nullptr, "fp32 linear needs an fp32 output");
     return launch_sgemm_nt(A.f32, lin.K, lin.w_f32, lin.bias, out.f32, ld_out, M, lin.N, lin.K, epilogue, st);
@@ -357,24 +362,33 @@ static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, i
   }
   // CTA pairs (cta_group::2) exist for the fused-LayerNorm engine's GEMMs: folded qkv / fc, residual + statistics, LM-head argmax
   const bool folded_in = ln && ln->stats_in, stats_out = ln && ln->stats_out;
-  const bool pair_kernel = e->fuse_ln && !e->split && sk == 1 &&
-                           ((part_val && !out.f32 && !folded_in) || (!part_val && folded_in && out.hi && !out.f32 && (epilogue == EPI_NONE || epilogue == EPI_GELU)) ||
+  // (bf16x2: folded qkv -> fp16, folded fc + GELU -> hi + lo, residual + hi / lo copies + statistics, LM-head argmax)
+  const bool pair_kernel = e->fuse_ln && sk == 1 &&
+                           ((part_val && !out.f32 && !folded_in) ||
+                            (!part_val && folded_in && out.hi && !out.f32 && (e->split ? ((epilogue == EPI_NONE && out_f16) || (epilogue == EPI_GELU && out.lo)) : (epilogue == EPI_NONE || epilogue == EPI_GELU))) ||
                             (!part_val && stats_out && epilogue == EPI_RESIDUAL));
   int pair = 0;
   gemm_bf16_pick(M, lin.N, lin.K, e->split ? 1 : 0, sk, &bn, pair_kernel ? &pair : nullptr);
   if (sk > 1) { g.split_k = sk; g.splitk_ws = ln->splitk_ws; g.splitk_counters = ln->splitk_counters; }
   g.pair = pair;
+  // the wide bf16x2 tiles exist for the fused GPT-2 layer's GEMMs, the LM head and plain fp32 outputs only (gemm_tcgen05.cu
+  // GIC_GEMM_VARIANTS_SPLIT_WIDE); everything else in that mode (mapper GEMMs) stays on the narrow tiles
+  if (e->split && !pair && bn > 64) {
+    const bool wide_ok = (folded_in && ((epilogue == EPI_NONE && out_f16) || (epilogue == EPI_GELU && out.lo))) || (stats_out && epilogue == EPI_RESIDUAL) ||
+                         (part_val && !folded_in) || (!part_val && !folded_in && !stats_out && epilogue == EPI_NONE && out.f32 && !out.hi);
+    if (!wide_ok) bn = 64;
+  }
   const int bi = box_rows_index(pair ? bn / 2 : bn);
   GIC_REQUIRE(bi >= 0, "no W tensor map for box height %d", pair ? bn / 2 : bn);
   GIC_TRY(make_tma_2d_bf16(&g.a_hi, A.hi, M, lin.K, (ln && ln->a_row_stride) ? ln->a_row_stride : lin.K, 128));
   g.w_hi = lin.tm_hi[bi];
   if (e->split) {
-    GIC_TRY(make_tma_2d_bf16(&g.a_lo, A.lo, M, lin.K, lin.K, 128));
+    GIC_TRY(make_tma_2d_bf16(&g.a_lo, A.lo, M, lin.K, (ln && ln->a_row_stride) ? ln->a_row_stride : lin.K, 128));
     g.w_lo = lin.tm_lo[bi];
   }
   g.M = M; g.N = lin.N; g.K = lin.K; g.block_n = bn; g.split = e->split ? 1 : 0; g.epilogue = epilogue; g.bias = lin.bias;
   g.w_static = 1;  // packed at load time
-  g.out = out; g.ld_out = ld_out; g.part_val = part_val; g.part_idx = part_idx; g.part_ld = part_ld;
+  g.out = out; g.out_f16 = out_f16 ? 1 : 0; g.ld_out = ld_out; g.part_val = part_val; g.part_idx = part_idx; g.part_ld = part_ld;
   GIC_REQUIRE((lin.colsum != nullptr) == (ln != nullptr && ln->stats_in != nullptr), "linear: folded-LayerNorm weights and row statistics must come together");
   if (ln) {
     g.ln_stats = ln->stats_in; g.ln_parts = ln->parts_in; g.ln_stats_ld = ln->stats_ld; g.ln_row_mul = ln->row_mul; g.ln_row_off = ln->row_off;
@@ -384,16 +398,24 @@ static int linear(const gic_engine* e, const Linear& lin, const Act& A, int M, i
   return launch_gemm_bf16(g, st);
 }
 
-static ActOut qkv_out(const Workspace& w) {
+// q | k | v of the UNFUSED layers (fp32 / unfused engines, and the transformer mapper's encoder layers in every mode)
+static ActOut qkv_out(const gic_engine* e, const Workspace& w) {
   ActOut o;
-  o.f32 = w.qkv_f32;
-  o.hi = w.qkv_bf16;
+  if (e->cfg.dtype == GIC_DTYPE_BF16) o.hi = w.qkv_bf16;
+  else o.f32 = w.qkv_f32;
   return o;
 }
 
 // attention sub-step shared by both layer variants
 static int attention(const gic_engine* e, const Workspace& w, int l, int M, bool prefill, cudaStream_t st) {
   ProfScope ps(e, prefill ? "attn_prefill" : "attn_decode", st);
+  if (e->split && e->fuse_ln) {  // fp16 q | k | v and cache, bf16 hi + lo output
+    bf16* kc = (bf16*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
+    bf16* vc = kc + w.kv_layer_elems;
+    if (prefill) return launch_attn_prefill_f16(w.qkv_bf16, kc, vc, w.o.hi, w.o.lo, w.B, w.P, e->H, w.t_max, w.beams, st);
+    if (w.anc) return launch_attn_decode_indirect(w.qkv_bf16, kc, vc, w.o.hi, w.d_pos, M, e->H, w.t_max, w.anc, w.anc_ld, w.P, w.beams, st, w.o.lo);
+    return launch_attn_decode_f16(w.qkv_bf16, kc, vc, w.o.hi, w.o.lo, w.d_pos, M, e->H, w.t_max, st);
+  }
   if (e->cfg.dtype == GIC_DTYPE_BF16) {
     bf16* kc = (bf16*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
     bf16* vc = kc + w.kv_layer_elems;
@@ -419,9 +441,10 @@ static int gpt_layer(const gic_engine* e, const Workspace& w, int l, float* h, i
     LnIo in; in.stats_in = w.ln_stats; in.parts_in = parts_in; in.stats_ld = w.m_max;
     LnIo res; res.stats_out = w.ln_stats; res.stats_ld = w.m_max;
     if (!prefill) { res.splitk_ws = w.splitk_ws; res.splitk_ws_floats = w.splitk_ws_floats; res.splitk_counters = w.splitk_counters; }
-    ActOut hres2 = hres; hres2.hi = w.a.hi;
+    ActOut hres2 = hres; hres2.hi = w.a.hi; hres2.lo = w.a.lo;  // (lo: bf16x2 only)
+    ActOut qo; qo.hi = w.qkv_bf16;
     { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_qkv", st);
-      GIC_TRY(linear(e, Lw.attn, w.a, M, EPI_NONE, qkv_out(w), 3 * d, st, nullptr, nullptr, nullptr, 0, &in)); }
+      GIC_TRY(linear(e, Lw.attn, w.a, M, EPI_NONE, qo, 3 * d, st, nullptr, nullptr, nullptr, 0, &in, e->split)); }
     GIC_TRY(attention(e, w, l, M, prefill, st));
     { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_proj", st);
       GIC_TRY(linear(e, Lw.proj, w.o, M, EPI_RESIDUAL, hres2, d, st, nullptr, nullptr, nullptr, 0, &res)); }
@@ -433,7 +456,7 @@ static int gpt_layer(const gic_engine* e, const Workspace& w, int l, float* h, i
     return GIC_OK;
   }
   { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, d, Lw.ln1.w, Lw.ln1.b, w.a.out(), M, d, st)); }
-  { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_qkv", st); GIC_TRY(linear(e, Lw.attn, w.a, M, EPI_NONE, qkv_out(w), 3 * d, st)); }
+  { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_qkv", st); GIC_TRY(linear(e, Lw.attn, w.a, M, EPI_NONE, qkv_out(e, w), 3 * d, st)); }
   GIC_TRY(attention(e, w, l, M, prefill, st));
   { ProfScope ps(e, prefill ? "prefill_gemm" : "gemm_proj", st); GIC_TRY(linear(e, Lw.proj, w.o, M, EPI_RESIDUAL, hres, d, st)); }
   { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, d, Lw.ln2.w, Lw.ln2.b, w.a.out(), M, d, st)); }
@@ -494,7 +517,7 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
   fa.finished = w.finished; fa.first_eos = w.first_eos; fa.ids_out = w.ids;
   fa.wte_f32 = e->wte_f32; fa.wte_bf16 = e->wte_f32 ? nullptr : e->wte_gather;
   fa.wpe = e->wpe; fa.h_next = w.h_dec;
-  fa.hb_next = e->fuse_ln ? w.a.hi : nullptr; fa.stats_next = e->fuse_ln ? w.ln_stats : nullptr;
+  fa.hb_next = e->fuse_ln ? w.a.hi : nullptr; fa.hb_next_lo = e->fuse_ln ? w.a.lo : nullptr; fa.stats_next = e->fuse_ln ? w.ln_stats : nullptr;
   return launch_finalize_token(fa, st);
 }
 
@@ -518,7 +541,7 @@ static Workspace slice_rows(const gic_engine* e, const Workspace& w, int row0, i
   if (s.qkv_bf16) s.qkv_bf16 += (size_t)row0 * 3 * d;
   s.h_dec += (size_t)row0 * d;
   const size_t kv_row = (size_t)e->H * w.t_max * 64;  // the per-layer plane stride (kv_layer_elems) keeps the full row count
-  if (e->cfg.dtype == GIC_DTYPE_BF16) s.kv = (bf16*)w.kv + (size_t)row0 * kv_row;
+  if (kv16(e)) s.kv = (bf16*)w.kv + (size_t)row0 * kv_row;
   else s.kv = (float*)w.kv + (size_t)row0 * kv_row;
   if (s.logits) s.logits += (size_t)row0 * e->V;
   if (s.ln_stats) s.ln_stats += row0;
@@ -592,7 +615,7 @@ static int mapper_forward(const gic_engine* e, const Workspace& w, const float* 
   for (size_t l = 0; l < e->tfm_layers.size(); ++l) {
     const TfmLayer& T = e->tfm_layers[l];
     GIC_TRY(launch_layernorm(w.h, d, T.n1.w, T.n1.b, w.a.out(), M, d, st));
-    GIC_TRY(linear(e, T.in_proj, w.a, M, EPI_NONE, qkv_out(w), 3 * d, st));
+    GIC_TRY(linear(e, T.in_proj, w.a, M, EPI_NONE, qkv_out(e, w), 3 * d, st));
     if (e->cfg.dtype == GIC_DTYPE_BF16) GIC_TRY(launch_attn_encoder<bf16>(w.qkv_bf16, w.o.out(), B, S, heads, d / heads, st));
     else GIC_TRY(launch_attn_encoder<float>(w.qkv_f32, w.o.out(), B, S, heads, d / heads, st));
     GIC_TRY(linear(e, T.out_proj, w.o, M, EPI_RESIDUAL, hres, d, st));
@@ -677,8 +700,8 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
   e->split = cfg->dtype == GIC_DTYPE_BF16X2;
   {
     const char* nf = getenv("GIC_NO_LNFUSE");
-    e->fuse_ln = cfg->dtype == GIC_DTYPE_BF16 && !(nf && nf[0] == '1');
-    e->beam_indirect = cfg->dtype == GIC_DTYPE_BF16 && gic::attn_decode_indirect_available();
+    e->fuse_ln = e->tc && !(nf && nf[0] == '1');  // GIC_NO_LNFUSE=1: LayerNorm as its own kernel; BF16X2 then also keeps fp32 q | k | v and cache
+    e->beam_indirect = e->fuse_ln && gic::attn_decode_indirect_available();
     const char* sk = getenv("GIC_SPLITK");
     e->use_splitk = sk && sk[0] == '1';
     const char* hf = getenv("GIC_LNF_FUSE");
@@ -823,8 +846,10 @@ static int prepare_ws(const gic_engine* e, void* workspace, size_t workspace_byt
   GIC_REQUIRE(batch > 0, "batch must be positive (got %d)", batch);
   GIC_REQUIRE(max_new >= 0, "max_new_tokens must be >= 0");
   GIC_REQUIRE(workspace != nullptr, "null workspace");
-  GIC_REQUIRE(e->P_img + e->P_task + max_new <= e->cfg.n_positions, "prefix + max_new_tokens (%d) exceeds n_positions (%d)",
-              e->P_img + e->P_task + max_new, e->cfg.n_positions);
+  // the last generated token is never fed back (src/models.py:466-469 runs after the final step but its result is unused), so the
+  // largest position embedded is P + max_new - 2; the reference accepts max_length up to n_positions - P + 1
+  GIC_REQUIRE(e->P_img + e->P_task + max_new - 1 <= e->cfg.n_positions, "prefix + max_new_tokens - 1 (%d) exceeds n_positions (%d)",
+              e->P_img + e->P_task + max_new - 1, e->cfg.n_positions);
   void* aligned = (void*)align_up((size_t)workspace, 1024);
   const size_t lost = (size_t)((unsigned char*)aligned - (unsigned char*)workspace);
   carve(e, aligned, batch, max_new, beams, w);
@@ -866,7 +891,7 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
   GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));
   // ---- prefill over the P prefix tokens of every row ----
-  if (e->fuse_ln) GIC_TRY(launch_row_stats(w.h, d, w.a.hi, w.ln_stats, B * P, d, st));
+  if (e->fuse_ln) GIC_TRY(launch_row_stats(w.h, d, w.a.hi, w.ln_stats, B * P, d, st, w.a.lo));
   GIC_TRY(gpt_layers(e, w, w.h, B * P, true, st));
   // only the last position feeds the LM head (the reference computes all positions and keeps [:, -1, :], src/models.py:398)
   GIC_TRY(lm_head_and_token(e, w, w.h, (long)(P - 1) * d, (long)P * d, B, B * P, logits_out, st));
@@ -979,11 +1004,9 @@ int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int
   { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
   GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));
   // prefill once per image; its K/V land in cache row b*beams and the first reorder fans them out to every beam
-  if (e->fuse_ln) GIC_TRY(launch_row_stats(w.h, d, w.a.hi, w.ln_stats, B * P, d, st));
+  if (e->fuse_ln) GIC_TRY(launch_row_stats(w.h, d, w.a.hi, w.ln_stats, B * P, d, st, w.a.lo));
   GIC_TRY(gpt_layers(e, w, w.h, B * P, true, st));
   GIC_TRY(lm_head_logits(e, w, w.h, (long)(P - 1) * d, (long)P * d, B, B * P, st));
-  const size_t esz = e->cfg.dtype == GIC_DTYPE_BF16 ? sizeof(bf16) : sizeof(float);
-  (void)esz;
   for (int t = 0; t < max_new; ++t) {
     const int live = t == 0 ? 1 : nb;  // only beam 0 is live at the first step (running scores 0, -1e9, ...)
     { ProfScope ps(e, "beam_topk", st);
@@ -1000,7 +1023,7 @@ int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int
       w.anc = w.beam.anc[(t + 1) & 1]; w.anc_ld = max_new;
     } else {
       ProfScope ps(e, "kv_reorder", st);
-      if (e->cfg.dtype == GIC_DTYPE_BF16)
+      if (kv16(e))
         GIC_TRY(launch_kv_reorder<bf16>((const bf16*)w.kv, (bf16*)w.kv2, w.beam.beam_idx, e->L, rows, e->H, P + t, w.t_max, st));
       else
         GIC_TRY(launch_kv_reorder<float>((const float*)w.kv, (float*)w.kv2, w.beam.beam_idx, e->L, rows, e->H, P + t, w.t_max, st));
@@ -1008,7 +1031,7 @@ int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int
     }
     GIC_TRY(launch_beam_embed(w.beam.next_tok, e->wte_f32, e->wte_f32 ? nullptr : e->wte_gather, e->wpe, P + t, d, w.h_dec, rows, st));
     GIC_TRY(launch_set_int(w.d_pos, P + t, st));
-    if (e->fuse_ln) GIC_TRY(launch_row_stats(w.h_dec, d, w.a.hi, w.ln_stats, rows, d, st));
+    if (e->fuse_ln) GIC_TRY(launch_row_stats(w.h_dec, d, w.a.hi, w.ln_stats, rows, d, st, w.a.lo));
     GIC_TRY(gpt_layers(e, w, w.h_dec, rows, false, st));
     GIC_TRY(lm_head_logits(e, w, w.h_dec, 0, d, rows, rows, st));
   }
@@ -1019,7 +1042,7 @@ int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int
 int gic_kv_reorder(gic_engine* e, const void* kv_src, void* kv_dst, const int32_t* beam_idx, int rows, int ctx_len, int t_max, void* stream) {
   GIC_REQUIRE(e && kv_src && kv_dst && beam_idx, "null argument");
   GIC_REQUIRE(rows > 0 && ctx_len >= 0 && ctx_len <= t_max, "bad sizes rows=%d ctx_len=%d t_max=%d", rows, ctx_len, t_max);
-  if (e->cfg.dtype == GIC_DTYPE_BF16)
+  if (kv16(e))
     return launch_kv_reorder<bf16>((const bf16*)kv_src, (bf16*)kv_dst, beam_idx, e->L, rows, e->H, ctx_len, t_max, (cudaStream_t)stream);
   return launch_kv_reorder<float>((const float*)kv_src, (float*)kv_dst, beam_idx, e->L, rows, e->H, ctx_len, t_max, (cudaStream_t)stream);
 }
@@ -1127,6 +1150,7 @@ int gic_test_gemm(int dtype, const float* A, const float* W, const float* bias, 
   int bn = 0, pair = 0;
   const bool pair_kernel = !split && epilogue == EPI_NONE && N % 32 == 0;  // the one fp32-output CTA-pair instantiation
   gemm_bf16_pick(M, N, K, split ? 1 : 0, 1, &bn, pair_kernel ? &pair : nullptr);
+  if (split && bn > 64 && epilogue != EPI_NONE) bn = 64;  // the wide bf16x2 tiles carry the engine's epilogues only
   g.pair = pair;
   if (r == GIC_OK) r = make_tma_2d_bf16(&g.a_hi, a_hi, M, K, K, 128);
   if (r == GIC_OK) r = make_tma_2d_bf16(&g.w_hi, w_hi, N, K, K, pair ? bn / 2 : bn);

@@ -23,7 +23,10 @@
 //  * epilogue stores go through a per-warp swizzled staging tile so that a warp writes whole 128-byte row segments
 //    (lane = row in the TMEM layout would scatter every store instruction over 32 rows).
 // BF16X2 ("split") mode: A = A_hi + A_lo, W = W_hi + W_lo (each bf16); three MMAs per k-step
-// (hi.hi + hi.lo + lo.hi) into the same accumulator give ~16 mantissa bits.
+// (hi.hi + hi.lo + lo.hi) into the same accumulator give ~16 mantissa bits.  Round 2: the split mode has the same fused
+// layer structure as the bf16 one -- LayerNorm folded in (FOLD), fp16 q/k/v out (OUT_F16), residual + hi/lo copy + row
+// statistics (OUT_F32_BF16X2_STATS), wide tiles and CTA pairs -- because it is the mode that meets the north-star caption
+// tolerance (>= 99 % of captions identical to the fp32 reference; profiles/r2_precision_screen.jsonl: no 1- or 2-MMA scheme does).
 #include <cuda.h>
 
 #include "kernels.cuh"
@@ -265,7 +268,9 @@ __device__ __forceinline__ float epi_act(float x, bool precise) {
 // partials; optional fp32 logits tap).
 // OUT (what the epilogue stores -- compile-time so that the per-element code of one instantiation is a handful of instructions):
 enum GemmOut { OUT_NONE = 0 /* argmax partials only */, OUT_F32 = 1, OUT_BF16 = 2, OUT_BF16X2 = 3 /* hi + lo */, OUT_F32_BF16_STATS = 4 /* fused residual:
-                fp32 stream + its bf16 copy + per-row (sum, sum of squares) partials for the LayerNorm folded into the next GEMM */ };
+                fp32 stream + its bf16 copy + per-row (sum, sum of squares) partials for the LayerNorm folded into the next GEMM */,
+               OUT_F16 = 5 /* IEEE half through out_hi: q | k | v of the split mode (fp16 KV cache) */,
+               OUT_F32_BF16X2_STATS = 6 /* fused residual of the split mode: fp32 stream + hi + lo copies + statistics of hi + lo */ };
 // FOLD: LayerNorm folded into this GEMM (see GemmBf16Args::ln_stats).
 // RAGGED: N % 32 != 0 or a leading dimension that is not a multiple of 4 -- only these instantiations carry the slow generic
 // store path (every kernel here runs once per launch with a cold instruction cache: code size is latency).
@@ -276,7 +281,7 @@ enum GemmOut { OUT_NONE = 0 /* argmax partials only */, OUT_F32 = 1, OUT_BF16 = 
 template <int BLOCK_N, bool SPLIT, int EPI, int OUT, bool FOLD, bool RAGGED, bool PAIR = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmKernelParams p) {
   using Tile = GemmTile<BLOCK_N, SPLIT, PAIR>;
-  static_assert(!PAIR || (!SPLIT && BLOCK_N % 32 == 0), "CTA pairs: bf16 operands, W halves of whole swizzle atoms");
+  static_assert(!PAIR || BLOCK_N % 32 == 0, "CTA pairs: W halves of whole swizzle atoms");
   constexpr int STAGES = Tile::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled TMA/UMMA tiles need 1024-byte alignment; everything below is addressed through 32-bit shared-window
@@ -341,18 +346,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   // (w_static: the caller vouches that W was not written by the kernel launched just before this one)
   uint32_t pre = 0;
   constexpr bool PAIR_PRELOAD = GIC_PAIR_PRELOAD != 0;
-  if (!SPLIT && (!PAIR || PAIR_PRELOAD) && warp == 0 && p.w_static && p.split_k == 1 && work0 < total_work) {
+  if ((!PAIR || PAIR_PRELOAD) && warp == 0 && p.w_static && p.split_k == 1 && work0 < total_work) {
     pre = (uint32_t)(nk < STAGES ? nk : STAGES);
     if (ptx::elect_one()) {
       const int n0 = ((work0 % total_tiles) / m_units) * BLOCK_N;
       for (uint32_t ps = 0; ps < pre; ++ps) {
         const uint32_t fb = full_bar + 8 * ps;
+        const uint32_t st = smem_base + ps * Tile::STAGE_BYTES;
         if (PAIR) {  // (both CTAs' barriers exist: the cluster barrier above)
           if (rank == 0) ptx::mbar_expect_tx(fb, 2 * Tile::STAGE_BYTES);
-          ptx::tma_load_2d_pair(smem_base + ps * Tile::STAGE_BYTES + Tile::A_BYTES, &p.w_hi, fb, (int)ps * GEMM_BLOCK_K, n0 + (int)rank * (BLOCK_N / 2));
+          ptx::tma_load_2d_pair(st + Tile::A_BYTES, &p.w_hi, fb, (int)ps * GEMM_BLOCK_K, n0 + (int)rank * (BLOCK_N / 2));
+          if (SPLIT) ptx::tma_load_2d_pair(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, fb, (int)ps * GEMM_BLOCK_K, n0 + (int)rank * (BLOCK_N / 2));
         } else {
           ptx::mbar_expect_tx(fb, Tile::STAGE_BYTES);
-          ptx::tma_load_2d(smem_base + ps * Tile::STAGE_BYTES + Tile::A_BYTES, &p.w_hi, fb, (int)ps * GEMM_BLOCK_K, n0);
+          ptx::tma_load_2d(st + Tile::A_BYTES, &p.w_hi, fb, (int)ps * GEMM_BLOCK_K, n0);
+          if (SPLIT) ptx::tma_load_2d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, fb, (int)ps * GEMM_BLOCK_K, n0);
         }
       }
     }
@@ -373,24 +381,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         if (ptx::elect_one()) {
           const uint32_t st = smem_base + s * Tile::STAGE_BYTES;
           const uint32_t fb = full_bar + 8 * s;
+          // stage layout: [A_hi][W_hi] and, in split mode, [A_lo][W_lo] behind them
           if (PAIR && it < pre) {
             ptx::tma_load_2d_pair(st, &p.a_hi, fb, kb * GEMM_BLOCK_K, m0);  // barrier armed and W halves requested before the wait
+            if (SPLIT) ptx::tma_load_2d_pair(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, fb, kb * GEMM_BLOCK_K, m0);
           } else if (PAIR) {
             // the leader's full barrier counts the bytes of both CTAs' loads (its arrival is the only pending one, so the
             // phase cannot complete before it has armed the count, even if the peer's bytes land first)
             if (rank == 0) ptx::mbar_expect_tx(fb, 2 * Tile::STAGE_BYTES);
             ptx::tma_load_2d_pair(st, &p.a_hi, fb, kb * GEMM_BLOCK_K, m0);
             ptx::tma_load_2d_pair(st + Tile::A_BYTES, &p.w_hi, fb, kb * GEMM_BLOCK_K, n0 + (int)rank * (BLOCK_N / 2));
+            if (SPLIT) {
+              ptx::tma_load_2d_pair(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, fb, kb * GEMM_BLOCK_K, m0);
+              ptx::tma_load_2d_pair(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, fb, kb * GEMM_BLOCK_K, n0 + (int)rank * (BLOCK_N / 2));
+            }
           } else if (it < pre) {
             ptx::tma_load_2d(st, &p.a_hi, fb, kb * GEMM_BLOCK_K, m0);  // barrier armed and W requested before the wait
+            if (SPLIT) ptx::tma_load_2d(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, fb, kb * GEMM_BLOCK_K, m0);
           } else {
-          ptx::mbar_expect_tx(fb, Tile::STAGE_BYTES);
-          ptx::tma_load_2d(st, &p.a_hi, fb, kb * GEMM_BLOCK_K, m0);
-          ptx::tma_load_2d(st + Tile::A_BYTES, &p.w_hi, fb, kb * GEMM_BLOCK_K, n0);
-          }
-          if (SPLIT) {
-            ptx::tma_load_2d(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, fb, kb * GEMM_BLOCK_K, m0);
-            ptx::tma_load_2d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, fb, kb * GEMM_BLOCK_K, n0);
+            ptx::mbar_expect_tx(fb, Tile::STAGE_BYTES);
+            ptx::tma_load_2d(st, &p.a_hi, fb, kb * GEMM_BLOCK_K, m0);
+            ptx::tma_load_2d(st + Tile::A_BYTES, &p.w_hi, fb, kb * GEMM_BLOCK_K, n0);
+            if (SPLIT) {
+              ptx::tma_load_2d(st + Tile::A_BYTES + Tile::W_BYTES, &p.a_lo, fb, kb * GEMM_BLOCK_K, m0);
+              ptx::tma_load_2d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, fb, kb * GEMM_BLOCK_K, n0);
+            }
           }
           if (tracing && it < 60) p.trace[it * 4 + 2] = clock64() - t_start;
         }
@@ -424,7 +439,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
               const uint64_t koff = (uint64_t)((k * 16 * 2) >> 4);  // 32 bytes per k-step inside the 128-byte swizzle row
               if (PAIR) ptx::umma_bf16_pair(tmem_acc, a_hi + koff, w_hi + koff, idesc, ((kb - kb_begin) | k | rep) != 0);
               else ptx::umma_bf16(tmem_acc, a_hi + koff, w_hi + koff, idesc, ((kb - kb_begin) | k | rep) != 0);
-              if (SPLIT) {
+              if (SPLIT && PAIR) {
+                ptx::umma_bf16_pair(tmem_acc, a_hi + koff, w_lo + koff, idesc, 1);
+                ptx::umma_bf16_pair(tmem_acc, a_lo + koff, w_hi + koff, idesc, 1);
+              } else if (SPLIT) {
                 ptx::umma_bf16(tmem_acc, a_hi + koff, w_lo + koff, idesc, 1);
                 ptx::umma_bf16(tmem_acc, a_lo + koff, w_hi + koff, idesc, 1);
               }
@@ -711,9 +729,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           // ---- specialised path: OUT / EPI / FOLD are compile-time, so this is a few instructions per element ----
           if (tr) trc[3] = clock64() - t_start + (long long)(b4.x * 0.f);
           const size_t rowoff = (size_t)(wrow0 + crow0);
-          float* pf = (OUT == OUT_F32 || OUT == OUT_F32_BF16_STATS) ? p.out_f32 + rowoff * p.ld_f32 + col : nullptr;
-          bf16* ph = (OUT == OUT_BF16 || OUT == OUT_BF16X2 || OUT == OUT_F32_BF16_STATS) ? p.out_hi + rowoff * p.ld_bf16 + col : nullptr;
-          bf16* pl = (OUT == OUT_BF16X2) ? p.out_lo + rowoff * p.ld_bf16 + col : nullptr;
+          constexpr bool W_F32 = OUT == OUT_F32 || OUT == OUT_F32_BF16_STATS || OUT == OUT_F32_BF16X2_STATS;
+          constexpr bool W_HI = OUT == OUT_BF16 || OUT == OUT_BF16X2 || OUT == OUT_F32_BF16_STATS || OUT == OUT_F16 || OUT == OUT_F32_BF16X2_STATS;
+          constexpr bool W_LO = OUT == OUT_BF16X2 || OUT == OUT_F32_BF16X2_STATS;
+          constexpr bool W_STATS = OUT == OUT_F32_BF16_STATS || OUT == OUT_F32_BF16X2_STATS;
+          float* pf = W_F32 ? p.out_f32 + rowoff * p.ld_f32 + col : nullptr;
+          bf16* ph = W_HI ? p.out_hi + rowoff * p.ld_bf16 + col : nullptr;
+          bf16* pl = W_LO ? p.out_lo + rowoff * p.ld_bf16 + col : nullptr;
           const size_t step_f32 = (size_t)4 * p.ld_f32, step_bf = (size_t)4 * p.ld_bf16;
           // three separate passes (load, math, store) so that the eight rows overlap instead of running as eight dependent
           // load -> add -> convert -> store chains
@@ -780,20 +802,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             }
           }
           uint2 pkh[8], pkl[8];
-          if (OUT == OUT_BF16 || OUT == OUT_BF16X2 || OUT == OUT_F32_BF16_STATS) {
+          if (OUT == OUT_F16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __half2 h01 = __floats2half2_rn(o[i].x, o[i].y), h23 = __floats2half2_rn(o[i].z, o[i].w);
+              pkh[i].x = *reinterpret_cast<const uint32_t*>(&h01);
+              pkh[i].y = *reinterpret_cast<const uint32_t*>(&h23);
+            }
+          } else if (W_HI) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const __nv_bfloat162 h01 = __floats2bfloat162_rn(o[i].x, o[i].y), h23 = __floats2bfloat162_rn(o[i].z, o[i].w);
               pkh[i].x = *reinterpret_cast<const uint32_t*>(&h01);
               pkh[i].y = *reinterpret_cast<const uint32_t*>(&h23);
-              if (OUT == OUT_BF16X2 || OUT == OUT_F32_BF16_STATS) {
-                const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-                if (OUT == OUT_BF16X2) {
+              if (W_LO || W_STATS) {
+                float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+                if (W_LO) {
                   const __nv_bfloat162 l01 = __floats2bfloat162_rn(o[i].x - f01.x, o[i].y - f01.y), l23 = __floats2bfloat162_rn(o[i].z - f23.x, o[i].w - f23.y);
                   pkl[i].x = *reinterpret_cast<const uint32_t*>(&l01);
                   pkl[i].y = *reinterpret_cast<const uint32_t*>(&l23);
-                } else {
-                  // row statistics over the values the next GEMM will actually read: the bf16 roundings
+                  if (W_STATS) {  // hi + lo is exact in fp32 (8 + 8 significant bits)
+                    const float2 g01 = __bfloat1622float2(l01), g23 = __bfloat1622float2(l23);
+                    f01.x += g01.x; f01.y += g01.y; f23.x += g23.x; f23.y += g23.y;
+                  }
+                }
+                if (W_STATS) {
+                  // row statistics over the values the next GEMM will actually read: the bf16 (or hi + lo) roundings
                   const bool row_ok = crow0 + 4 * i < rows_here;
                   const float ds = (f01.x + f01.y) + (f23.x + f23.y), dq = (f01.x * f01.x + f01.y * f01.y) + (f23.x * f23.x + f23.y * f23.y);
                   rsum[i] += row_ok ? ds : 0.f;
@@ -805,17 +839,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           if (rows_here == 32) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if (OUT == OUT_F32 || OUT == OUT_F32_BF16_STATS) *reinterpret_cast<float4*>(pf + i * step_f32) = o[i];
-              if (OUT == OUT_BF16 || OUT == OUT_BF16X2 || OUT == OUT_F32_BF16_STATS) *reinterpret_cast<uint2*>(ph + i * step_bf) = pkh[i];
-              if (OUT == OUT_BF16X2) *reinterpret_cast<uint2*>(pl + i * step_bf) = pkl[i];
+              if (W_F32) *reinterpret_cast<float4*>(pf + i * step_f32) = o[i];
+              if (W_HI) *reinterpret_cast<uint2*>(ph + i * step_bf) = pkh[i];
+              if (W_LO) *reinterpret_cast<uint2*>(pl + i * step_bf) = pkl[i];
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               if (crow0 + 4 * i < rows_here) {
-                if (OUT == OUT_F32 || OUT == OUT_F32_BF16_STATS) *reinterpret_cast<float4*>(pf + i * step_f32) = o[i];
-                if (OUT == OUT_BF16 || OUT == OUT_BF16X2 || OUT == OUT_F32_BF16_STATS) *reinterpret_cast<uint2*>(ph + i * step_bf) = pkh[i];
-                if (OUT == OUT_BF16X2) *reinterpret_cast<uint2*>(pl + i * step_bf) = pkl[i];
+                if (W_F32) *reinterpret_cast<float4*>(pf + i * step_f32) = o[i];
+                if (W_HI) *reinterpret_cast<uint2*>(ph + i * step_bf) = pkh[i];
+                if (W_LO) *reinterpret_cast<uint2*>(pl + i * step_bf) = pkl[i];
               }
             }
           }
@@ -870,7 +904,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             (void)full4;
           }
         }
-        if (OUT == OUT_F32_BF16_STATS) {
+        if (OUT == OUT_F32_BF16_STATS || OUT == OUT_F32_BF16X2_STATS) {
           // one statistics part per 32-column chunk (index = global column / 32): the summation order then depends only on the
           // column, never on the tile width or the batch size, so a row's result is the same in any batch
 #pragma unroll
@@ -983,30 +1017,34 @@ int make_tma_2d_bf16(TmaDesc* out, const void* base, uint64_t rows, uint64_t col
 // GIC_GEMM_PAIR=0 never pairs, =2 pairs whenever the shape allows it (tests).
 void gemm_bf16_pick(int M, int N, int K, int split, int split_k, int* block_n, int* pair) {
   static const int wide[] = {256, 192, 128, 64, 32};
-  static const int narrow[] = {64, 32};  // bf16x2 stages carry four operand tiles
+  static const int narrow[] = {128, 64, 32};  // bf16x2 stages carry four operand tiles: 64 KB per stage at 128 columns (3 stages)
   const int* cand = split ? narrow : wide;
-  const int n_cand = split ? 2 : 5;
+  const int n_cand = split ? 3 : 5;
   const long m_tiles = ceil_div(M, GEMM_BLOCK_M);
   const int nk = ceil_div(K, GEMM_BLOCK_K);
   const int sms = cta_limit() > 0 && cta_limit() < 148 ? cta_limit() : 148, S = split_k < 1 ? 1 : split_k;
+  // cycles per 64-deep k-block of a 128 x bn tile: the shared-memory port (TMA writes + UMMA operand reads, 256 + 2 bn per operand
+  // set) against the tensor pipe (2 bn per MMA; bf16x2: two operand sets, three MMAs)
+  auto kb_single = [&](int bn) -> long { return split ? (6L * bn > 2L * (256 + 2 * bn) ? 6L * bn : 2L * (256 + 2 * bn)) : 256 + 2L * bn; };
   long best_cost = -1;
   *block_n = cand[0];
   for (int i = 0; i < n_cand; ++i) {
     const int bn = cand[i];
     const long tiles = m_tiles * ceil_div(N, bn);
     const long rounds = (tiles * S + sms - 1) / sms;
-    const long cost = rounds * (ceil_div(nk, S) * (256 + 2 * bn) * (split ? 3 : 1) + 600 + 500L * ceil_div(bn, 64) + (S > 1 ? 3000 : 0));
+    const long cost = rounds * (ceil_div(nk, S) * kb_single(bn) + 600 + 500L * ceil_div(bn, 64) + (S > 1 ? 3000 : 0));
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; *block_n = bn; }
   }
   if (!pair) return;
   *pair = 0;
   const char* pv = getenv("GIC_GEMM_PAIR");
   const int mode = pv ? atoi(pv) : 1;
-  if (mode == 0 || split || S > 1 || (m_tiles & 1) || cta_limit() > 0) return;
+  if (mode == 0 || S > 1 || (m_tiles & 1) || cta_limit() > 0) return;
   // measured (profiles/r1ag_microbench.txt): a pair saves ~110 cycles per k-block and costs ~2500 per launch (cluster scheduling + two
   // cluster barriers), so it pays for long K (fc2: 15.4 -> 14.0 us at M = 1024, 59 -> 51 us at M = 10240) and for the many-round LM
-  // head (55.9 -> 49.1 us, 1.61 PFLOP/s = this box's cuBLAS burst rate), not for the single-round K = 768 GEMMs (+0.6 us)
-  if (mode != 2 && !(nk >= 32 || N >= 8192)) return;
+  // head (55.9 -> 49.1 us, 1.61 PFLOP/s = this box's cuBLAS burst rate), not for the single-round K = 768 GEMMs (+0.6 us).
+  // bf16x2: every shape is a candidate (a pair halves the W bytes of both operand sets); the cost model decides.
+  if (mode != 2 && !split && !(nk >= 32 || N >= 8192)) return;
   static const int pair_bn[] = {256, 192, 128, 64};
   long best_pair = -1;
   int bn_pair = 0;
@@ -1014,8 +1052,9 @@ void gemm_bf16_pick(int M, int N, int K, int split, int split_k, int* block_n, i
     const int bn = pair_bn[i];
     const long units = (m_tiles / 2) * ceil_div(N, bn);
     const long rounds = (units + sms / 2 - 1) / (sms / 2);
-    const long kb = 256 + bn > 2 * bn ? 256 + bn : 2 * bn;
-    const long cost = rounds * ((long)nk * kb + 600 + 500L * ceil_div(bn, 64));
+    long kb = 256 + bn > 2 * bn ? 256 + bn : 2 * bn;
+    if (split) kb = 2L * (256 + bn) > 6L * bn ? 2L * (256 + bn) : 6L * bn;
+    const long cost = rounds * ((long)nk * kb + 600 + 500L * ceil_div(bn, 64)) + (split ? 2500 : 0);  // (bf16: the gate above stands in for the launch overhead)
     if (best_pair < 0 || cost < best_pair) { best_pair = cost; bn_pair = bn; }
   }
   if (mode == 2 || best_pair < best_cost) { *pair = 1; *block_n = bn_pair; }
@@ -1057,12 +1096,20 @@ static int gemm_num_sms() {
   X(EPI_GELU, OUT_BF16, true, false) X(EPI_RELU, OUT_BF16, false, false) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false, false) \
   X(EPI_ARGMAX, OUT_NONE, true, false) X(EPI_ARGMAX, OUT_F32, true, true) X(EPI_NONE, OUT_F32, true, true)
 #define GIC_GEMM_VARIANTS_SPLIT(X) \
-  X(EPI_NONE, OUT_BF16X2, false, false) X(EPI_TANH, OUT_BF16X2, false, false) X(EPI_GELU, OUT_BF16X2, false, false) X(EPI_RELU, OUT_BF16X2, false, false)
+  X(EPI_NONE, OUT_BF16X2, false, false) X(EPI_TANH, OUT_BF16X2, false, false) X(EPI_GELU, OUT_BF16X2, false, false) X(EPI_RELU, OUT_BF16X2, false, false) \
+  X(EPI_NONE, OUT_F16, true, false) X(EPI_GELU, OUT_BF16X2, true, false) X(EPI_RESIDUAL, OUT_F32_BF16X2_STATS, false, false)
+// the fused GPT-2 layer of the split mode on wide tiles (folded qkv -> fp16, folded fc + GELU -> hi + lo, residual + copies + statistics)
+// and the LM head; the narrow tiles (32 / 64) keep the full list above for the mappers and the test hooks
+#define GIC_GEMM_VARIANTS_SPLIT_WIDE(X) \
+  X(EPI_NONE, OUT_F16, true, false) X(EPI_GELU, OUT_BF16X2, true, false) X(EPI_RESIDUAL, OUT_F32_BF16X2_STATS, false, false) \
+  X(EPI_ARGMAX, OUT_NONE, false, false) X(EPI_NONE, OUT_F32, false, false) X(EPI_NONE, OUT_F32, false, true) X(EPI_ARGMAX, OUT_F32, false, true)
 
 // CTA-pair instantiations (aligned shapes, bf16 operands): the fused decode / prefill GEMMs, the LM head, and the plain fp32-output
 // GEMM of the kernel test hook
 #define GIC_GEMM_VARIANTS_PAIR(X) \
   X(EPI_NONE, OUT_BF16, true) X(EPI_GELU, OUT_BF16, true) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_NONE, OUT_F32, false)
+#define GIC_GEMM_VARIANTS_PAIR_SPLIT(X) \
+  X(EPI_NONE, OUT_F16, true) X(EPI_GELU, OUT_BF16X2, true) X(EPI_RESIDUAL, OUT_F32_BF16X2_STATS, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_NONE, OUT_F32, false)
 
 template <int BLOCK_N>
 static int configure_pair() {
@@ -1070,6 +1117,21 @@ static int configure_pair() {
   GIC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, false, E, O, F, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       GemmTile<BLOCK_N, false, true>::SMEM_BYTES));
   GIC_GEMM_VARIANTS_PAIR(X)
+#undef X
+#define X(E, O, F)                                                                                                                        \
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, true, E, O, F, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      GemmTile<BLOCK_N, true, true>::SMEM_BYTES));
+  GIC_GEMM_VARIANTS_PAIR_SPLIT(X)
+#undef X
+  return GIC_OK;
+}
+
+template <int BLOCK_N>
+static int configure_split_wide() {
+#define X(E, O, F, R)                                                                                                               \
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, true, E, O, F, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      GemmTile<BLOCK_N, true>::SMEM_BYTES));
+  GIC_GEMM_VARIANTS_SPLIT_WIDE(X)
 #undef X
   return GIC_OK;
 }
@@ -1080,7 +1142,7 @@ static int configure_cfg() {
   GIC_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, E, O, F, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       GemmTile<BLOCK_N, SPLIT>::SMEM_BYTES));
   GIC_GEMM_VARIANTS_COMMON(X)
-  if (SPLIT) { GIC_GEMM_VARIANTS_SPLIT(X) } else { GIC_GEMM_VARIANTS_BF16(X) }
+  if constexpr (SPLIT) { GIC_GEMM_VARIANTS_SPLIT(X) } else { GIC_GEMM_VARIANTS_BF16(X) }
 #undef X
   return GIC_OK;
 }
@@ -1096,6 +1158,7 @@ int gemm_bf16_configure() {
   GIC_TRY((configure_cfg<256, false>()));
   GIC_TRY((configure_cfg<32, true>()));
   GIC_TRY((configure_cfg<64, true>()));
+  GIC_TRY((configure_split_wide<128>()));
   GIC_TRY((configure_pair<64>()));
   GIC_TRY((configure_pair<128>()));
   GIC_TRY((configure_pair<192>()));
@@ -1125,10 +1188,10 @@ static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
 }
 
 // one cluster of two CTAs per 256 x BLOCK_N tile; persistent over as many pairs as can be co-resident (a pair needs both SMs of a TPC)
-template <int BLOCK_N, int EPI, int OUT, bool FOLD>
+template <int BLOCK_N, int EPI, int OUT, bool FOLD, bool SPLIT = false>
 static int launch_one_pair(const GemmKernelParams& kp, cudaStream_t st) {
-  using Tile = GemmTile<BLOCK_N, false, true>;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, false, EPI, OUT, FOLD, false, true>;
+  using Tile = GemmTile<BLOCK_N, SPLIT, true>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, SPLIT, EPI, OUT, FOLD, false, true>;
   static int max_pairs = 0;
   if (max_pairs == 0) {
     int n = 0;
@@ -1164,18 +1227,37 @@ static int launch_one_pair(const GemmKernelParams& kp, cudaStream_t st) {
   return GIC_OK;
 }
 
+// (epilogue, output, fold) combinations that exist only in the ragged flavour (test / logits-tap paths)
+static bool has_aligned(int epi, int out, bool fold) { return !((epi == EPI_ARGMAX && out == OUT_F32) || (epi == EPI_NONE && out == OUT_F32 && fold)); }
+
 template <int BLOCK_N>
-static int launch_cfg_pair(const GemmKernelParams& kp, int epi, int out, bool fold, cudaStream_t st) {
+static int launch_cfg_pair(const GemmKernelParams& kp, int epi, int out, bool fold, bool split, cudaStream_t st) {
+  if (!split) {
 #define X(E, O, F) \
   if (epi == E && out == O && fold == F) return launch_one_pair<BLOCK_N, E, O, F>(kp, st);
-  GIC_GEMM_VARIANTS_PAIR(X)
+    GIC_GEMM_VARIANTS_PAIR(X)
 #undef X
-  set_error("gemm_bf16: no CTA-pair kernel for epilogue %d with output mode %d%s", epi, out, fold ? " + folded LayerNorm" : "");
+  } else {
+#define X(E, O, F) \
+  if (epi == E && out == O && fold == F) return launch_one_pair<BLOCK_N, E, O, F, true>(kp, st);
+    GIC_GEMM_VARIANTS_PAIR_SPLIT(X)
+#undef X
+  }
+  set_error("gemm_bf16: no CTA-pair kernel for epilogue %d with output mode %d%s%s", epi, out, fold ? " + folded LayerNorm" : "", split ? " (bf16x2)" : "");
   return GIC_ERR_UNSUPPORTED;
 }
 
-// (epilogue, output, fold) combinations that exist only in the ragged flavour (test / logits-tap paths)
-static bool has_aligned(int epi, int out, bool fold) { return !((epi == EPI_ARGMAX && out == OUT_F32) || (epi == EPI_NONE && out == OUT_F32 && fold)); }
+template <int BLOCK_N>
+static int launch_cfg_split_wide(const GemmKernelParams& kp, int epi, int out, bool fold, cudaStream_t st) {
+  const bool aligned = kp.N % 32 == 0 && kp.ld_f32 % 4 == 0 && kp.ld_bf16 % 4 == 0;
+#define X(E, O, F, R) \
+  if (epi == E && out == O && fold == F && (R || aligned || O == OUT_NONE) && (!R || !aligned || !has_aligned(E, O, F))) return launch_one<BLOCK_N, true, E, O, F, R>(kp, st);
+  GIC_GEMM_VARIANTS_SPLIT_WIDE(X)
+#undef X
+  set_error("gemm_bf16: no wide bf16x2 kernel for epilogue %d with output mode %d%s", epi, out, fold ? " + folded LayerNorm" : "");
+  return GIC_ERR_UNSUPPORTED;
+}
+
 
 template <int BLOCK_N, bool SPLIT>
 static int launch_cfg(const GemmKernelParams& kp, int epi, int out, bool fold, cudaStream_t st) {
@@ -1184,7 +1266,7 @@ static int launch_cfg(const GemmKernelParams& kp, int epi, int out, bool fold, c
 #define X(E, O, F, R) \
   if (epi == E && out == O && fold == F && (R || aligned || O == OUT_NONE) && (!R || !aligned || !has_aligned(E, O, F))) return launch_one<BLOCK_N, SPLIT, E, O, F, R>(kp, st);
   GIC_GEMM_VARIANTS_COMMON(X)
-  if (SPLIT) { GIC_GEMM_VARIANTS_SPLIT(X) } else { GIC_GEMM_VARIANTS_BF16(X) }
+  if constexpr (SPLIT) { GIC_GEMM_VARIANTS_SPLIT(X) } else { GIC_GEMM_VARIANTS_BF16(X) }
 #undef X
   set_error("gemm_bf16: no kernel for epilogue %d with output mode %d%s%s", epi, out, fold ? " + folded LayerNorm" : "", SPLIT ? " (bf16x2)" : "");
   return GIC_ERR_UNSUPPORTED;
@@ -1216,9 +1298,13 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   const bool fold = a.ln_stats != nullptr;
   int out = OUT_NONE;
   if (a.stats_out) {
-    GIC_REQUIRE(epi == EPI_RESIDUAL && a.out.f32 && a.out.hi && !a.out.lo, "gemm_bf16: row statistics come with the fused residual epilogue (fp32 + bf16 outputs)");
+    GIC_REQUIRE(epi == EPI_RESIDUAL && a.out.f32 && a.out.hi, "gemm_bf16: row statistics come with the fused residual epilogue (fp32 + bf16 outputs)");
+    GIC_REQUIRE((a.out.lo != nullptr) == (a.split != 0), "gemm_bf16: the fused residual epilogue writes hi + lo copies in bf16x2 mode and a single bf16 copy otherwise");
     GIC_REQUIRE(a.ln_stats_ld >= a.M, "gemm_bf16: statistics leading dimension %ld < M %d", a.ln_stats_ld, a.M);
-    out = OUT_F32_BF16_STATS;
+    out = a.out.lo ? OUT_F32_BF16X2_STATS : OUT_F32_BF16_STATS;
+  } else if (a.out_f16) {
+    GIC_REQUIRE(a.out.hi && !a.out.lo && !a.out.f32, "gemm_bf16: the fp16 output goes through out.hi alone");
+    out = OUT_F16;
   } else if (a.out.f32) {
     GIC_REQUIRE(!a.out.hi && !a.out.lo, "gemm_bf16: fp32 and bf16 outputs together only in the fused residual epilogue");
     out = OUT_F32;
@@ -1233,14 +1319,14 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
     GIC_REQUIRE(ceil_div(a.K, GEMM_BLOCK_K) >= kp.split_k, "gemm_bf16: more K slices than k-blocks");
   }
   if (a.pair) {
-    GIC_REQUIRE(!a.split && kp.split_k == 1, "gemm_bf16: CTA pairs take plain bf16 operands and no K split");
+    GIC_REQUIRE(kp.split_k == 1, "gemm_bf16: CTA pairs take no K split");
     GIC_REQUIRE(ceil_div(a.M, GEMM_BLOCK_M) % 2 == 0, "gemm_bf16: CTA pairs need an even number of 128-row tiles (M = %d)", a.M);
     GIC_REQUIRE(out == OUT_NONE || (a.N % 32 == 0 && a.ld_out % 4 == 0), "gemm_bf16: CTA pairs need N %% 32 == 0 and aligned outputs");
     switch (a.block_n) {
-      case 64: return launch_cfg_pair<64>(kp, epi, out, fold, st);
-      case 128: return launch_cfg_pair<128>(kp, epi, out, fold, st);
-      case 192: return launch_cfg_pair<192>(kp, epi, out, fold, st);
-      case 256: return launch_cfg_pair<256>(kp, epi, out, fold, st);
+      case 64: return launch_cfg_pair<64>(kp, epi, out, fold, a.split != 0, st);
+      case 128: return launch_cfg_pair<128>(kp, epi, out, fold, a.split != 0, st);
+      case 192: return launch_cfg_pair<192>(kp, epi, out, fold, a.split != 0, st);
+      case 256: return launch_cfg_pair<256>(kp, epi, out, fold, a.split != 0, st);
     }
     set_error("gemm_bf16: unsupported block_n %d for a CTA pair", a.block_n);
     return GIC_ERR_UNSUPPORTED;
@@ -1249,6 +1335,7 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
     switch (a.block_n) {
       case 32: return launch_cfg<32, true>(kp, epi, out, fold, st);
       case 64: return launch_cfg<64, true>(kp, epi, out, fold, st);
+      case 128: return launch_cfg_split_wide<128>(kp, epi, out, fold, st);
     }
   } else {
     switch (a.block_n) {

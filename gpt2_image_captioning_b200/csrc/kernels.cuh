@@ -42,6 +42,7 @@ struct GemmBf16Args {
   int mma_repeat = 1;              // microbenchmark probe only (re-issues every MMA this many times)
   const float* bias = nullptr;     // [N] or null
   ActOut out;                      // fp32 (EPI_RESIDUAL: in-place +=) and/or bf16 hi/lo, row stride ld_out
+  int out_f16 = 0;                 // out.hi receives IEEE half instead of bf16 (q | k | v of the bf16x2 mode: fp16 KV cache)
   int ld_out = 0;
   float* part_val = nullptr;       // fused LM-head argmax: [M][part_ld] best value per (tile, column-parity warp) slot ...
   int* part_idx = nullptr;         // ... and its lowest column index (cols >= N masked)
@@ -76,10 +77,12 @@ int launch_layernorm(const float* x, long x_row_stride, const float* w, const fl
 int launch_pack_weight(const float* in, int R, int C, bool transpose, ActOut out, cudaStream_t st, const float* scale_k = nullptr);
 // LayerNorm folding, load time: colsum[n] = sum_k float(w_packed[n,k]);  bias_out[n] = bias[n] + sum_k beta[k] * w(n,k)
 // (w_src: the original fp32 weight, [K,N] when `transposed` else [N,K])
+// (w_packed_lo: the bf16x2 remainder of the packed weight; colsum then sums hi + lo)
 int launch_fold_ln(const bf16* w_packed, const float* w_src, bool transposed, const float* beta, const float* bias, float* colsum,
-                   float* bias_out, int N, int K, cudaStream_t st);
+                   float* bias_out, int N, int K, cudaStream_t st, const bf16* w_packed_lo = nullptr);
 // raw rows for a GEMM with folded LayerNorm: xb = bf16(x), stats[row] = (sum xb, sum xb^2)
-int launch_row_stats(const float* x, long x_row_stride, bf16* xb, float2* stats, int rows, int d, cudaStream_t st);
+// (xb_lo: bf16x2 remainder; the statistics are then those of hi + lo)
+int launch_row_stats(const float* x, long x_row_stride, bf16* xb, float2* stats, int rows, int d, cudaStream_t st, bf16* xb_lo = nullptr);
 int launch_convert(const float* in, ActOut out, size_t n, cudaStream_t st);
 int launch_embed_prefix(const float* prefix, int P_img, const float* task, int P_task, const float* wpe, float* h, float* prefix_out,
                         int B, int d, cudaStream_t st);
@@ -96,8 +99,14 @@ int launch_attn_prefill(const T* qkv, T* kcache, T* vcache, ActOut out, int B, i
 template <typename T>
 int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows, int H, int t_max, cudaStream_t st);
 // bf16 decode attention through a beam-ancestry table instead of a reordered cache (beam search); see attention.cu
+// (out_lo non-null: the fp16-cache / hi + lo output flavour of the bf16x2 engine)
 int launch_attn_decode_indirect(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos, int rows, int H, int t_max, const int* anc,
-                                int anc_ld, int n_prefix, int beams, cudaStream_t st);
+                                int anc_ld, int n_prefix, int beams, cudaStream_t st, bf16* out_lo = nullptr);
+// bf16x2 engine: q | k | v and the KV cache are IEEE half (2-byte elements, typed bf16* for the shared plumbing), the output a bf16 hi + lo pair
+int launch_attn_decode_f16(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out_hi, bf16* out_lo, const int* d_pos, int rows, int H, int t_max,
+                           cudaStream_t st);
+int launch_attn_prefill_f16(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out_hi, bf16* out_lo, int B, int P, int H, int t_max, int cache_row_mult,
+                            cudaStream_t st);
 bool attn_decode_indirect_available();
 void attn_decode_set_variant(int v);  // microbenchmark: ring geometry of the bulk-copy decode kernel (0 = product)
 int attn_decode_configure();  // cudaFuncSetAttribute for the bulk-copy decode kernel (call once, outside stream capture)
@@ -124,6 +133,7 @@ struct FinalizeArgs {
   const float* wpe;         // [n_pos, d]
   float* h_next;            // [B, d] fp32: next-step input = wte[tok] + wpe[P + step]
   bf16* hb_next;            // optional [B, d]: its bf16 copy (A operand of the first GEMM with folded LayerNorm) ...
+  bf16* hb_next_lo = nullptr;  // ... bf16x2: the remainder bf16(x - hi) (fp32 embedding table only) ...
   float2* stats_next;       // ... and [B] (sum, sum of squares) of that copy
 };
 int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st);

@@ -277,7 +277,12 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
         if (a.hb_next) {
           const bf16 xb = __float2bfloat16_rn(x);
           a.hb_next[(size_t)b * a.d + c] = xb;
-          const float xf = __bfloat162float(xb);
+          float xf = __bfloat162float(xb);
+          if (a.hb_next_lo) {  // bf16x2: hi + lo operand, statistics of the sum
+            const bf16 xl = __float2bfloat16_rn(x - xf);
+            a.hb_next_lo[(size_t)b * a.d + c] = xl;
+            xf += __bfloat162float(xl);
+          }
           ssum += xf;
           ssq += xf * xf;
         }
