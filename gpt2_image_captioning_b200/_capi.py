@@ -85,6 +85,7 @@ SIGNATURES = {
     "gic_topk_ip_tc": (C.c_int, [_fp, _fp, C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),
     "gic_topk_ip": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, C.c_void_p]),
     "gic_select_caption_rows": (C.c_int, [_fp, _fp, C.c_int, C.c_int, _fp, _fp, C.c_int, C.c_int, _fp, C.c_void_p]),
+    "gic_gather_caption_rows": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, C.c_void_p]),
     "gic_gather_attention_add": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_void_p]),
     "gic_gather_aggregate_add": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_void_p]),
     "gic_launch_count": (C.c_ulonglong, []),

@@ -67,6 +67,8 @@ struct Workspace {
   size_t kv_layer_elems = 0;       // elements of one K (or V) plane of one layer
   float* logits = nullptr;         // [rows, V] fp32 (F32 mode)
   float* part_val = nullptr; int* part_idx = nullptr; int n_parts_max = 0;  // [rows][n_parts_max]
+  float* part_val2 = nullptr;      // [rows][n_parts_max] runner-up value per slot (bf16x2 engine: exactly re-scored head)
+  int* rescore_stats = nullptr;    // [2] candidates re-scored / rows with more than 8 candidates, summed over the call (diagnostic)
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0; int* splitk_counters = nullptr;  // split-K partials / per-tile arrival counters
   float2* ln_stats = nullptr; int ln_parts_max = 0;  // [ln_parts_max][m_max] row (sum, sum of squares) partials (folded LayerNorm)
   int64_t* ids = nullptr;          // [rows, max_new]
@@ -94,6 +96,9 @@ struct gic_engine {
                             // (profiles/r1w_microbench.txt), fc2 with a 3-way K split + last-CTA reduction takes 22 us against 15 us unsplit
   bool fuse_lnf = false; // ... and ln_f into the LM head (GIC_LNF_FUSE=1).  Off by default: measured round 1, the folded head re-reads the
                          // row statistics and column sums for each of its ~10 tiles per CTA and costs 79 us against 3.8 + 55 us
+  bool rescore_head = false;  // BF16X2 greedy: the LM head runs with single bf16 operands (1 MMA per product) and the candidates within the rounding
+                              // margin of its maximum are re-scored exactly in fp32 (lm_head_rescore_kernel).  GIC_X2_HEAD_FULL=1: the 3-MMA head
+  float* wte_norm_max = nullptr;  // device scalar: max_n |wte[n]|_2 (the margin's weight-norm bound)
   bf16* wte_gather = nullptr;  // BF16: unfolded bf16 embedding table for the next-token gather
   bool tc = false;     // tensor-core modes (BF16 / BF16X2)
   std::vector<void*> allocs;
@@ -321,6 +326,10 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
   }
   w->part_val = c.take<float>((size_t)w->n_parts_max * w->rows);
   w->part_idx = c.take<int>((size_t)w->n_parts_max * w->rows);
+  if (e->rescore_head) {
+    w->part_val2 = c.take<float>((size_t)w->n_parts_max * w->rows);
+    w->rescore_stats = c.take<int>(2);
+  }
   w->ids = c.take<int64_t>((size_t)w->rows * (max_new > 0 ? max_new : 1));
   w->finished = c.take<unsigned char>(w->rows);
   w->first_eos = c.take<int>(w->rows);
@@ -489,7 +498,24 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
     GIC_TRY(linear(e, e->lm_head, a, rows, EPI_NONE, o, e->V, st, w.part_val, w.part_idx, &n_parts, w.n_parts_max, &in));
   } else {
     { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, row_stride, e->lnf.w, e->lnf.b, w.a.out(), rows, d, st)); }
-    if (!e->tc) {
+    if (e->rescore_head && !logits_tap) {
+      // single-MMA head on the hi halves + exact re-scoring of the near-maximal candidates (lmhead.cu)
+      GemmBf16Args g;
+      int bn = 0, pair = 0;
+      gemm_bf16_pick(rows, e->V, d, 0, 1, &bn, &pair);
+      const int bi = box_rows_index(pair ? bn / 2 : bn);
+      GIC_REQUIRE(bi >= 0, "no W tensor map for box height %d", pair ? bn / 2 : bn);
+      GIC_TRY(make_tma_2d_bf16(&g.a_hi, w.a.hi, rows, d, d, 128));
+      g.w_hi = e->lm_head.tm_hi[bi];
+      g.M = rows; g.N = e->V; g.K = d; g.block_n = bn; g.pair = pair; g.w_static = 1;
+      g.part_val = w.part_val; g.part_idx = w.part_idx; g.part_val2 = w.part_val2; g.part_ld = w.n_parts_max;
+      n_parts = 2 * ceil_div(e->V, bn);
+      { ProfScope ps(e, "lm_head", st); GIC_TRY(launch_gemm_bf16(g, st)); }
+      { ProfScope ps(e, "lm_head_rescore", st);
+        GIC_TRY(launch_lm_head_rescore(h, row_stride, e->lnf.w, e->lnf.b, e->wte_f32, e->wte_norm_max, w.part_val, w.part_idx, w.part_val2, n_parts,
+                                       w.n_parts_max, bn, rows, e->V, d, w.rescore_stats, st)); }
+      n_parts = 1;
+    } else if (!e->tc) {
       float* lg = logits_tap ? logits_tap : w.logits;
       ActOut o; o.f32 = lg;
       { ProfScope ps(e, "lm_head", st); GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st)); }
@@ -547,6 +573,7 @@ static Workspace slice_rows(const gic_engine* e, const Workspace& w, int row0, i
   if (s.ln_stats) s.ln_stats += row0;
   s.part_val += (size_t)w.n_parts_max * row0;
   s.part_idx += (size_t)w.n_parts_max * row0;
+  if (s.part_val2) s.part_val2 += (size_t)w.n_parts_max * row0;
   s.ids += (size_t)row0 * w.max_new;
   s.finished += row0; s.first_eos += row0;
   s.d_step += sub; s.d_pos += sub; s.done_counter += sub; s.fin_counter += sub; s.all_done += sub;
@@ -705,7 +732,9 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
     const char* sk = getenv("GIC_SPLITK");
     e->use_splitk = sk && sk[0] == '1';
     const char* hf = getenv("GIC_LNF_FUSE");
-    e->fuse_lnf = e->fuse_ln && hf && hf[0] == '1';
+    e->fuse_lnf = e->fuse_ln && !e->split && hf && hf[0] == '1';
+    const char* xh = getenv("GIC_X2_HEAD_FULL");
+    e->rescore_head = e->split && e->fuse_ln && !(xh && xh[0] == '1');
   }
   const char* ng = getenv("GIC_NO_GRAPH");
   e->use_graph = !(ng && ng[0] == '1');
@@ -775,6 +804,10 @@ int gic_engine_load_gpt2(gic_engine* e, const gic_gpt2_weights* w, void* stream)
   }
   if (e->cfg.dtype == GIC_DTYPE_F32) e->wte_f32 = e->lm_head.w_f32;
   else if (e->cfg.dtype == GIC_DTYPE_BF16X2) GIC_TRY(copy_vec(e, &e->wte_f32, w->wte, (size_t)e->V * d, st));
+  if (e->rescore_head) {
+    GIC_TRY(dev_alloc(e, (void**)&e->wte_norm_max, sizeof(float)));
+    GIC_TRY(launch_row_norm_max(e->wte_f32, e->V, d, e->wte_norm_max, st));
+  }
   GIC_TRY(copy_vec(e, &e->wpe, w->wpe, (size_t)e->cfg.n_positions * d, st));
   GIC_TRY(copy_norm(e, &e->lnf, w->lnf_w, w->lnf_b, d, st));
   e->layers.resize(e->L);
@@ -887,6 +920,7 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   GIC_TRY(launch_init_decode_state(w.finished, w.first_eos, B, max_new, w.d_step, w.d_pos, w.done_counter, P, w.fin_counter, w.all_done, w.ids,
                                    e->cfg.eos_token_id, st));
   if (w.splitk_counters) GIC_CHECK_CUDA(cudaMemsetAsync(w.splitk_counters, 0, 4096 * sizeof(int), st));
+  if (w.rescore_stats) GIC_CHECK_CUDA(cudaMemsetAsync(w.rescore_stats, 0, 2 * sizeof(int), st));
   if (e->profiling) GIC_TRY(launch_spin(150000000LL, st));  // ~75 ms: lets the host queue ahead so events time the device only
   { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
   GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));
@@ -1077,6 +1111,12 @@ int gic_select_caption_rows(const float* scores, const int64_t* idx, int batch, 
   GIC_REQUIRE(scores && idx && cap_row_start && rows_out, "null argument");
   return launch_select_caption_rows(scores, idx, batch, k_searched, cap_row_start, cap_row_ids, top_i, top_k, rows_out,
                                     (cudaStream_t)stream);
+}
+
+int gic_gather_caption_rows(const float* cap_db, const int64_t* rows, int batch, int top_k, int dim, float* out, void* stream) {
+  GIC_REQUIRE(cap_db && rows && out, "null argument");
+  GIC_REQUIRE(batch >= 0 && top_k > 0 && dim > 0, "bad sizes batch=%d top_k=%d dim=%d", batch, top_k, dim);
+  return launch_gather_caption_rows(cap_db, rows, batch * top_k, dim, out, (cudaStream_t)stream);
 }
 
 int gic_gather_attention_add(const float* q, const float* cap_db, const int64_t* rows, int batch, int top_k, int dim, const float* attn_w,

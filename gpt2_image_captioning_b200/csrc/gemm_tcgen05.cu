@@ -221,6 +221,7 @@ struct alignas(64) GemmKernelParams {
   float* out_f32; int ld_f32;
   bf16* out_hi; bf16* out_lo; int ld_bf16;
   float* part_val; int* part_idx; int part_ld;  // [M][part_ld]: slot (tile * 2 + column-parity warp) of each row
+  float* part_val2;  // EPI_ARGMAX2: the slot's second-best value (candidate generation for the exactly re-scored LM head)
   // folded LayerNorm on the A operand (see launch_gemm_bf16): out = rstd_r * (acc - mean_r * colsum_n) + bias_n
   const float2* ln_stats; int ln_parts; long ln_stats_ld; int ln_row_mul, ln_row_off; const float* ln_colsum;
   // split-K (see launch_gemm_bf16): `split_k` CTAs share one output tile, each over K / split_k; fp32 partials go to splitk_ws
@@ -257,7 +258,7 @@ struct GemmTile {
 template <int EPI>
 __device__ __forceinline__ float epi_act(float x, bool precise) {
   if (EPI == EPI_TANH) return tanhf(x);
-  if (EPI == EPI_GELU) return precise ? gelu_tanh(x) : gelu_tanh_fast(x);
+  if (EPI == EPI_GELU) return precise ? gelu_tanh_sigmoid(x) : gelu_tanh_fast(x);
   if (EPI == EPI_RELU) return fmaxf(x, 0.f);
   return x;
 }
@@ -483,7 +484,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
       const int n_tile = tile / m_units;
       const int m0 = ((tile % m_units) * m_per_unit + (int)rank) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
       const int wrow0 = m0 + q * 32;  // first row of this warp's 32-row band
-      if (EPI == EPI_ARGMAX && OUT == OUT_NONE) {
+      if ((EPI == EPI_ARGMAX || EPI == EPI_ARGMAX2) && OUT == OUT_NONE) {
         // ---- LM head on the product path: argmax straight from the TMEM registers (lane = row), nothing is staged or stored.
         // (the staging tile would add ~20 % to the shared-memory traffic that bounds this kernel's main loop) ----
         const int row = wrow0 + lane;
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           mu = sx * inv_k;
           rs = rsqrtf(fmaxf(sq * inv_k - mu * mu, 0.f) + 1e-5f);
         }
-        float bv = -INFINITY;
+        float bv = -INFINITY, bv2 = -INFINITY;  // best and (EPI_ARGMAX2) second-best value of the slot
         int bi = 0x7fffffff;
         ptx::mbar_wait(tmem_full_bar + 8 * acc, use & 1);
         ptx::tc_fence_after();
@@ -576,16 +577,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             }
             // columns in increasing order with strict > : the lowest index among equal maxima survives
             bool g;
-            g = (whole || col < p.N) && v0 > bv; bv = g ? v0 : bv; bi = g ? col : bi;
-            g = (whole || col + 1 < p.N) && v1 > bv; bv = g ? v1 : bv; bi = g ? col + 1 : bi;
-            g = (whole || col + 2 < p.N) && v2 > bv; bv = g ? v2 : bv; bi = g ? col + 2 : bi;
-            g = (whole || col + 3 < p.N) && v3 > bv; bv = g ? v3 : bv; bi = g ? col + 3 : bi;
+            if (EPI == EPI_ARGMAX2) {  // also the runner-up value: a displaced best becomes it, otherwise the larger of it and the newcomer
+              if (!whole) {
+                v0 = col < p.N ? v0 : -INFINITY; v1 = col + 1 < p.N ? v1 : -INFINITY; v2 = col + 2 < p.N ? v2 : -INFINITY; v3 = col + 3 < p.N ? v3 : -INFINITY;
+              }
+              g = v0 > bv; bv2 = g ? bv : fmaxf(bv2, v0); bv = g ? v0 : bv; bi = g ? col : bi;
+              g = v1 > bv; bv2 = g ? bv : fmaxf(bv2, v1); bv = g ? v1 : bv; bi = g ? col + 1 : bi;
+              g = v2 > bv; bv2 = g ? bv : fmaxf(bv2, v2); bv = g ? v2 : bv; bi = g ? col + 2 : bi;
+              g = v3 > bv; bv2 = g ? bv : fmaxf(bv2, v3); bv = g ? v3 : bv; bi = g ? col + 3 : bi;
+            } else {
+              g = (whole || col < p.N) && v0 > bv; bv = g ? v0 : bv; bi = g ? col : bi;
+              g = (whole || col + 1 < p.N) && v1 > bv; bv = g ? v1 : bv; bi = g ? col + 1 : bi;
+              g = (whole || col + 2 < p.N) && v2 > bv; bv = g ? v2 : bv; bi = g ? col + 2 : bi;
+              g = (whole || col + 3 < p.N) && v3 > bv; bv = g ? v3 : bv; bi = g ? col + 3 : bi;
+            }
           }
         }
         if (row < p.M) {
           const size_t slot = (size_t)row * p.part_ld + (n_tile * 2 + sub);
           p.part_val[slot] = bv;
           p.part_idx[slot] = bi;
+          if (EPI == EPI_ARGMAX2) p.part_val2[slot] = bv2;
         }
         if (tracing && e == 0 && lane == 0 && local < 8) p.trace[512 + local * 4 + 2] = clock64() - t_start;
         continue;
@@ -1094,7 +1106,7 @@ static int gemm_num_sms() {
 #define GIC_GEMM_VARIANTS_BF16(X) \
   X(EPI_NONE, OUT_BF16, false, false) X(EPI_NONE, OUT_BF16, true, false) X(EPI_TANH, OUT_BF16, false, false) X(EPI_GELU, OUT_BF16, false, false) \
   X(EPI_GELU, OUT_BF16, true, false) X(EPI_RELU, OUT_BF16, false, false) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false, false) \
-  X(EPI_ARGMAX, OUT_NONE, true, false) X(EPI_ARGMAX, OUT_F32, true, true) X(EPI_NONE, OUT_F32, true, true)
+  X(EPI_ARGMAX, OUT_NONE, true, false) X(EPI_ARGMAX, OUT_F32, true, true) X(EPI_NONE, OUT_F32, true, true) X(EPI_ARGMAX2, OUT_NONE, false, false)
 #define GIC_GEMM_VARIANTS_SPLIT(X) \
   X(EPI_NONE, OUT_BF16X2, false, false) X(EPI_TANH, OUT_BF16X2, false, false) X(EPI_GELU, OUT_BF16X2, false, false) X(EPI_RELU, OUT_BF16X2, false, false) \
   X(EPI_NONE, OUT_F16, true, false) X(EPI_GELU, OUT_BF16X2, true, false) X(EPI_RESIDUAL, OUT_F32_BF16X2_STATS, false, false)
@@ -1107,7 +1119,8 @@ static int gemm_num_sms() {
 // CTA-pair instantiations (aligned shapes, bf16 operands): the fused decode / prefill GEMMs, the LM head, and the plain fp32-output
 // GEMM of the kernel test hook
 #define GIC_GEMM_VARIANTS_PAIR(X) \
-  X(EPI_NONE, OUT_BF16, true) X(EPI_GELU, OUT_BF16, true) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_NONE, OUT_F32, false)
+  X(EPI_NONE, OUT_BF16, true) X(EPI_GELU, OUT_BF16, true) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_NONE, OUT_F32, false) \
+  X(EPI_ARGMAX2, OUT_NONE, false)
 #define GIC_GEMM_VARIANTS_PAIR_SPLIT(X) \
   X(EPI_NONE, OUT_F16, true) X(EPI_GELU, OUT_BF16X2, true) X(EPI_RESIDUAL, OUT_F32_BF16X2_STATS, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_NONE, OUT_F32, false)
 
@@ -1281,7 +1294,7 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.bias = a.bias;
   kp.mma_repeat = a.mma_repeat < 1 ? 1 : a.mma_repeat;
   kp.out_f32 = a.out.f32; kp.ld_f32 = a.ld_out; kp.out_hi = a.out.hi; kp.out_lo = a.out.lo; kp.ld_bf16 = a.ld_out;
-  kp.part_val = a.part_val; kp.part_idx = a.part_idx; kp.part_ld = a.part_ld; kp.trace = a.trace;
+  kp.part_val = a.part_val; kp.part_idx = a.part_idx; kp.part_ld = a.part_ld; kp.part_val2 = a.part_val2; kp.trace = a.trace;
   kp.ln_stats = a.ln_stats; kp.ln_parts = a.ln_parts; kp.ln_stats_ld = a.ln_stats_ld; kp.ln_row_mul = a.ln_row_mul; kp.ln_row_off = a.ln_row_off;
   kp.ln_colsum = a.ln_colsum; kp.stats_out = a.stats_out;
   kp.split_k = a.split_k < 1 ? 1 : a.split_k; kp.splitk_ws = a.splitk_ws; kp.splitk_counters = a.splitk_counters;
@@ -1292,7 +1305,8 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   if (a.part_val) {
     GIC_REQUIRE(a.epilogue == EPI_NONE && a.part_idx, "gemm_bf16: the fused argmax takes no activation and needs both partial buffers");
     GIC_REQUIRE(a.part_ld >= 2 * ceil_div(a.N, a.block_n), "gemm_bf16: argmax partial rows too short (%d slots for %d)", a.part_ld, 2 * ceil_div(a.N, a.block_n));
-    epi = EPI_ARGMAX;
+    epi = a.part_val2 ? EPI_ARGMAX2 : EPI_ARGMAX;
+    GIC_REQUIRE(!a.part_val2 || (!a.out.f32 && !a.out.hi && !a.ln_stats && !a.split), "gemm_bf16: the top-2 argmax epilogue is the plain bf16 head without outputs");
   }
   GIC_REQUIRE(!(epi == EPI_RESIDUAL && !a.out.f32), "gemm_bf16: residual epilogue needs the fp32 output");
   const bool fold = a.ln_stats != nullptr;
@@ -1311,10 +1325,10 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   } else if (a.out.hi) {
     out = a.out.lo ? OUT_BF16X2 : OUT_BF16;
   } else {
-    GIC_REQUIRE(epi == EPI_ARGMAX, "gemm_bf16: no output buffer");
+    GIC_REQUIRE(epi == EPI_ARGMAX || epi == EPI_ARGMAX2, "gemm_bf16: no output buffer");
   }
   if (kp.split_k > 1) {
-    GIC_REQUIRE(epi != EPI_ARGMAX && a.splitk_ws && a.splitk_counters, "gemm_bf16: split-K needs its workspace / counters and a storing epilogue");
+    GIC_REQUIRE(epi != EPI_ARGMAX && epi != EPI_ARGMAX2 && a.splitk_ws && a.splitk_counters, "gemm_bf16: split-K needs its workspace / counters and a storing epilogue");
     GIC_REQUIRE(a.N % 32 == 0 && a.ld_out % 4 == 0, "gemm_bf16: split-K needs N %% 32 == 0 and aligned outputs");
     GIC_REQUIRE(ceil_div(a.K, GEMM_BLOCK_K) >= kp.split_k, "gemm_bf16: more K slices than k-blocks");
   }

@@ -4,7 +4,8 @@
 
 namespace gic {
 
-enum Epilogue { EPI_NONE = 0, EPI_TANH = 1, EPI_GELU = 2, EPI_RELU = 3, EPI_RESIDUAL = 4, EPI_ARGMAX = 5 /* internal: set by part_val */ };
+enum Epilogue { EPI_NONE = 0, EPI_TANH = 1, EPI_GELU = 2, EPI_RELU = 3, EPI_RESIDUAL = 4, EPI_ARGMAX = 5 /* internal: set by part_val */,
+                EPI_ARGMAX2 = 6 /* internal: set by part_val2 (best + runner-up value per slot) */ };
 
 // Where a producer kernel writes an activation: fp32 and/or bf16 (hi) and/or the bf16 remainder (lo = bf16(v - hi),
 // the second half of a BF16X2 GEMM operand).  Any pointer may be null.
@@ -47,6 +48,7 @@ struct GemmBf16Args {
   float* part_val = nullptr;       // fused LM-head argmax: [M][part_ld] best value per (tile, column-parity warp) slot ...
   int* part_idx = nullptr;         // ... and its lowest column index (cols >= N masked)
   int part_ld = 0;                 // slots per row (>= 2 * n_tiles)
+  float* part_val2 = nullptr;      // optional [M][part_ld]: second-best value of each slot (lm_head_rescore_kernel's candidate test)
   // LayerNorm folded into the GEMM (A holds the RAW rows x, W was packed as gamma_k * W[n,k], bias as b_n + sum_k beta_k W[n,k]):
   //   out[r,n] = rstd_r * (acc[r,n] - mean_r * ln_colsum[n]) + bias[n],   mean / rstd from sum_parts ln_stats[part][r * mul + off]
   const float2* ln_stats = nullptr;  // [ln_parts][ln_stats_ld] (sum x, sum x^2) partials written by the producer of A
@@ -137,6 +139,12 @@ struct FinalizeArgs {
   float2* stats_next;       // ... and [B] (sum, sum of squares) of that copy
 };
 int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st);
+// exact greedy token from the single-MMA bf16 head's per-slot (best, column, runner-up) partials: candidates within the rounding margin of
+// the approximate maximum are re-scored in fp32 against ln_f(h) . wte_f32 (see lmhead.cu); result -> partial 0 of each row
+int launch_lm_head_rescore(const float* h, long h_row_stride, const float* lnw, const float* lnb, const float* wte_f32, const float* wte_norm_max,
+                           float* part_val, int* part_idx, const float* part_val2, int n_parts, int part_ld, int block_n, int rows, int V, int d,
+                           int* stats, cudaStream_t st);
+int launch_row_norm_max(const float* w, int N, int K, float* out, cudaStream_t st);
 // temperature / top-p sampling of one token per row from fp32 logits [B, V] (src/models.py:400-449); the token goes to slot 0 of the
 // row's (value, index) partials.  step: *d_step unless step_override >= 0 (the Philox counter is (row, step)).
 int launch_sample_top_p(const float* logits, int B, int V, float temperature, float top_p, unsigned long long seed, const int* d_step,
@@ -181,6 +189,7 @@ int launch_topk_ip(const float* q, const float* db, int B, int N, int D, int k, 
                    cudaStream_t st);
 int launch_select_caption_rows(const float* scores, const int64_t* idx, int B, int k_searched, const int64_t* cap_row_start,
                                const int64_t* cap_row_ids, int top_i, int top_k, int64_t* rows_out, cudaStream_t st);
+int launch_gather_caption_rows(const float* cap_db, const int64_t* rows, int n_rows, int D, float* out, cudaStream_t st);
 int launch_gather_attention_add(const float* q, const float* cap_db, const int64_t* rows, int B, int top_k, int D, const float* attn_w,
                                 const float* attn_b, float* out, cudaStream_t st);
 int launch_gather_aggregate_add(const float* q, const float* cap_db, const int64_t* rows, int B, int top_k, int D, int aggregation,

@@ -209,6 +209,146 @@ int launch_sample_top_p(const float* logits, int B, int V, float temperature, fl
   return GIC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Exact greedy token from an approximate LM head (bf16x2 engine).  The head runs ONCE on the tensor cores with single bf16
+// operands (a_hi . wte_hi, 1 MMA per product instead of 3) and its epilogue keeps, per (row, 64..128-column slot), the best
+// value, its column and the runner-up value.  Rounding both operands to bf16 moves a logit by at most
+//   delta = 2^-8 (1 + 2^-10) |a|_2 |wte_n|_2  (+ fp32 accumulation)  <=  DELTA_REL * |a|_2 * max_n |wte_n|_2,
+// so the true argmax is among the columns whose approximate logit is within 2 delta of the approximate maximum.  One block
+// per row recomputes ln_f(h) in fp32 (HF:models/gpt2/modeling_gpt2.py:628), collects those candidates -- the best column of
+// every slot within the margin, plus every column of a slot whose RUNNER-UP is within it -- and re-scores them with fp32
+// dot products against the fp32 embedding table (:705-706, tied head), lowest index on ties (torch.argmax, src/models.py:441).
+// The row's result is written as partial 0; finalize_token_kernel then runs with n_parts = 1.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr float RESCORE_DELTA_REL = 0.00390625f * 1.02f;  // 2^-8 with 2 % slack for the 2^-18 cross term and the fp32 accumulation
+constexpr int RESCORE_THREADS = 128;
+constexpr int RESCORE_MAX_CAND = 256;  // candidate list in shared memory; more than this (pathologically flat rows) -> all slots are rescanned
+
+__global__ void __launch_bounds__(RESCORE_THREADS) lm_head_rescore_kernel(const float* h, long h_row_stride, const float* __restrict__ lnw,
+                                                                          const float* __restrict__ lnb, const float* __restrict__ wte,
+                                                                          const float* __restrict__ wte_norm_max, float* part_val, int* part_idx,
+                                                                          const float* part_val2, int n_parts, int part_ld, int block_n, int V, int d,
+                                                                          int* stats /* [2]: candidates re-scored, rows that rescanned slots */) {
+  extern __shared__ float rs_a[];  // [d] ln_f(h) in fp32
+  __shared__ float red[RESCORE_THREADS / 32];
+  __shared__ int s_cand[RESCORE_MAX_CAND];
+  __shared__ int s_ncand;
+  __shared__ float s_bv[RESCORE_THREADS / 32];
+  __shared__ int s_bi[RESCORE_THREADS / 32];
+  const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  pdl_launch_dependents();
+  pdl_wait();
+  auto block_sum = [&](float v) {
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    return (red[0] + red[1]) + (red[2] + red[3]);
+  };
+  // ---- ln_f(h) in fp32, two-pass like layernorm_kernel ----
+  const float* hr = h + (size_t)b * h_row_stride;
+  float s = 0.f;
+  for (int c = t; c < d; c += RESCORE_THREADS) { const float v = __ldcg(hr + c); rs_a[c] = v; s += v; }
+  const float mean = block_sum(s) / (float)d;
+  float q = 0.f;
+  for (int c = t; c < d; c += RESCORE_THREADS) { const float v = rs_a[c] - mean; q += v * v; }
+  const float rstd = 1.0f / sqrtf(block_sum(q) / (float)d + 1e-5f);
+  float n2 = 0.f;
+  for (int c = t; c < d; c += RESCORE_THREADS) {
+    const float v = (rs_a[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
+    rs_a[c] = v;
+    n2 += v * v;
+  }
+  const float a_norm = sqrtf(block_sum(n2));
+  const float margin = 2.0f * RESCORE_DELTA_REL * a_norm * __ldg(wte_norm_max);
+  // ---- approximate maximum over the row's slots ----
+  const float* pv = part_val + (size_t)b * part_ld;
+  const int* pi = part_idx + (size_t)b * part_ld;
+  const float* pv2 = part_val2 + (size_t)b * part_ld;
+  float m = -INFINITY;
+  for (int p = t; p < n_parts; p += RESCORE_THREADS) m = fmaxf(m, __ldcg(pv + p));
+  m = warp_max(m);
+  __syncthreads();
+  if (lane == 0) red[warp] = m;
+  if (t == 0) s_ncand = 0;
+  __syncthreads();
+  m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  const float thr = m - margin;
+  // ---- candidates: the best column of every slot within the margin; a slot whose runner-up is within it contributes all its columns ----
+  for (int p = t; p < n_parts; p += RESCORE_THREADS) {
+    if (__ldcg(pv + p) >= thr) {
+      if (__ldcg(pv2 + p) >= thr) {
+        const int n0 = (p >> 1) * block_n + (p & 1) * 32;
+        for (int c0 = n0; c0 < (p >> 1) * block_n + block_n; c0 += 64)
+          for (int c = c0; c < c0 + 32 && c < V; ++c) {
+            const int k = atomicAdd(&s_ncand, 1);
+            if (k < RESCORE_MAX_CAND) s_cand[k] = c;
+          }
+      } else {
+        const int k = atomicAdd(&s_ncand, 1);
+        if (k < RESCORE_MAX_CAND) s_cand[k] = __ldcg(pi + p);
+      }
+    }
+  }
+  __syncthreads();
+  const int ncand_raw = s_ncand;
+  const bool overflow = ncand_raw > RESCORE_MAX_CAND;  // (block-uniform) pathologically flat row: every column within the margin is re-scored
+  const int ncand = overflow ? V : ncand_raw;
+  // ---- exact fp32 logits of the candidates: one warp per candidate, fixed summation order ----
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int k = warp; k < ncand; k += RESCORE_THREADS / 32) {
+    const int col = overflow ? k : s_cand[k];
+    const float* wr = wte + (size_t)col * d;
+    float acc = 0.f;
+    for (int c = lane * 4; c < d; c += 128) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + c));
+      acc = fmaf(rs_a[c], wv.x, acc); acc = fmaf(rs_a[c + 1], wv.y, acc); acc = fmaf(rs_a[c + 2], wv.z, acc); acc = fmaf(rs_a[c + 3], wv.w, acc);
+    }
+    acc = warp_sum(acc);
+    if (better(acc, col, bv, bi)) { bv = acc; bi = col; }
+  }
+  if (lane == 0) { s_bv[warp] = bv; s_bi[warp] = bi; }
+  __syncthreads();
+  if (t == 0) {
+    for (int w = 1; w < RESCORE_THREADS / 32; ++w)
+      if (better(s_bv[w], s_bi[w], bv, bi)) { bv = s_bv[w]; bi = s_bi[w]; }
+    part_val[(size_t)b * part_ld] = bv;
+    part_idx[(size_t)b * part_ld] = bi;
+    if (stats) {
+      atomicAdd(stats, ncand);
+      if (ncand > 8) atomicAdd(stats + 1, 1);
+    }
+  }
+}
+
+int launch_lm_head_rescore(const float* h, long h_row_stride, const float* lnw, const float* lnb, const float* wte_f32, const float* wte_norm_max,
+                           float* part_val, int* part_idx, const float* part_val2, int n_parts, int part_ld, int block_n, int rows, int V, int d,
+                           int* stats, cudaStream_t st) {
+  GIC_REQUIRE(d % 4 == 0 && d <= 4096 && n_parts >= 1 && part_ld >= n_parts, "lm_head_rescore: bad sizes d=%d n_parts=%d part_ld=%d", d, n_parts, part_ld);
+  GIC_CHECK_CUDA(launch_kernel(lm_head_rescore_kernel, dim3(rows), dim3(RESCORE_THREADS), (size_t)d * sizeof(float), st, h, h_row_stride, lnw, lnb, wte_f32,
+                               wte_norm_max, part_val, part_idx, part_val2, n_parts, part_ld, block_n, V, d, stats));
+  note_launch();
+  return GIC_OK;
+}
+
+// max_n |W[n, :]|_2 of a row-major fp32 matrix (load time; the rescoring margin's weight-norm bound)
+__global__ void __launch_bounds__(128) row_norm_max_kernel(const float* __restrict__ w, int N, int K, float* out) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) { const float v = w[(size_t)n * K + k]; s += v * v; }
+  s = warp_sum(s);
+  if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(s)));  // non-negative floats order like their bit patterns
+}
+int launch_row_norm_max(const float* w, int N, int K, float* out, cudaStream_t st) {
+  GIC_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+  row_norm_max_kernel<<<ceil_div(N, 4), 128, 0, st>>>(w, N, K, out);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return GIC_OK;
+}
+
 // One block per row: reduce the partial maxima, apply the EOS rules, record the token and build the next input.
 __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
   __shared__ float sv[4];

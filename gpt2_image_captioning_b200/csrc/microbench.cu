@@ -220,6 +220,75 @@ int main(int argc, char** argv) {
     return 0;
   }
 
+  // ---- mode 6: the bf16x2 (hi + lo operands, 3 MMAs per product) decode GEMMs in their fused form over every tile shape, the split
+  // LM head, and the fp16-cache decode attention next to the bf16 one ----
+  if (argc > 2 && atoi(argv[2]) == 6) {
+    bf16* a_lo = (bf16*)dmalloc((size_t)B * 4 * d * 2);
+    bf16* o_lo = (bf16*)dmalloc((size_t)B * 4 * d * 2);
+    std::vector<bf16*> l_qkv(SETS), l_proj(SETS), l_fc(SETS), l_fc2(SETS);
+    for (int s = 0; s < SETS; ++s) {
+      l_qkv[s] = (bf16*)dmalloc((size_t)3 * d * d * 2); l_proj[s] = (bf16*)dmalloc((size_t)d * d * 2);
+      l_fc[s] = (bf16*)dmalloc((size_t)4 * d * d * 2); l_fc2[s] = (bf16*)dmalloc((size_t)4 * d * d * 2);
+    }
+    bf16* wte_lo = (bf16*)dmalloc((size_t)V * d * 2);
+    float2* stats = (float2*)dmalloc((size_t)64 * B * 8);
+    float* colsum = (float*)dmalloc((size_t)V * 4);
+    struct Shape { const char* name; int N, K; std::vector<bf16*>*w, *wl; int epi; bool res; };
+    Shape shapes[] = {{"qkv", 3 * d, d, &w_qkv, &l_qkv, EPI_NONE, false}, {"proj", d, d, &w_proj, &l_proj, EPI_RESIDUAL, true},
+                      {"fc", 4 * d, d, &w_fc, &l_fc, EPI_GELU, false}, {"fc2", d, 4 * d, &w_fc2, &l_fc2, EPI_RESIDUAL, true}};
+    for (auto& s : shapes) {
+      int bn_pick = 0, pair_pick = 0;
+      gemm_bf16_pick(B, s.N, s.K, 1, 1, &bn_pick, &pair_pick);
+      for (int pair = 0; pair < 2; ++pair)
+        for (int bn : {64, 128, 192, 256}) {
+          if (!pair && bn > 128) continue;
+          if (pair && ((B + 127) / 128) % 2) continue;
+          std::vector<GemmBf16Args> args(SETS);
+          for (int i = 0; i < SETS; ++i) {
+            GemmBf16Args& g = args[i];
+            OK(make_tma_2d_bf16(&g.a_hi, a, B, s.K, s.K, 128));
+            OK(make_tma_2d_bf16(&g.a_lo, a_lo, B, s.K, s.K, 128));
+            OK(make_tma_2d_bf16(&g.w_hi, (*s.w)[i], s.N, s.K, s.K, pair ? bn / 2 : bn));
+            OK(make_tma_2d_bf16(&g.w_lo, (*s.wl)[i], s.N, s.K, s.K, pair ? bn / 2 : bn));
+            g.M = B; g.N = s.N; g.K = s.K; g.block_n = bn; g.split = 1; g.epilogue = s.epi; g.bias = bias; g.ld_out = s.N; g.pair = pair; g.w_static = 1;
+            if (s.res) { g.out.f32 = h; g.out.hi = o; g.out.lo = o_lo; g.stats_out = stats; g.ln_stats_ld = B; }
+            else {
+              g.ln_stats = stats; g.ln_parts = d / 32; g.ln_stats_ld = B; g.ln_colsum = colsum;
+              if (s.epi == EPI_NONE) { g.out.hi = qkv; g.out_f16 = 1; } else { g.out.hi = o; g.out.lo = o_lo; }
+            }
+          }
+          float us = time_loop(st, 240, [&](int i) { OK(launch_gemm_bf16(args[i % SETS], st)); });
+          printf("x2 gemm %-4s%s M=%d N=%d K=%d block_n=%3d: %7.2f us  %6.1f TFLOP/s algorithmic (x3 on the pipe)%s\n", s.name, pair ? " pair" : "     ", B, s.N, s.K, bn, us,
+                 2.0 * B * s.N * s.K / us * 1e-6, (bn == bn_pick && pair == pair_pick) ? "  <- picked" : "");
+        }
+    }
+    for (int pair = 0; pair < 2; ++pair)
+      for (int bn : {128, 192, 256}) {
+        if (!pair && bn > 128) continue;
+        GemmBf16Args g;
+        OK(make_tma_2d_bf16(&g.a_hi, a, B, d, d, 128));
+        OK(make_tma_2d_bf16(&g.a_lo, a_lo, B, d, d, 128));
+        OK(make_tma_2d_bf16(&g.w_hi, wte, V, d, d, pair ? bn / 2 : bn));
+        OK(make_tma_2d_bf16(&g.w_lo, wte_lo, V, d, d, pair ? bn / 2 : bn));
+        g.M = B; g.N = V; g.K = d; g.block_n = bn; g.split = 1; g.part_val = pv; g.part_idx = pi; g.part_ld = 2048; g.pair = pair;
+        float us = time_loop(st, 30, [&](int) { OK(launch_gemm_bf16(g, st)); });
+        printf("x2 lm_head%s M=%d N=%d K=%d block_n=%d: %.2f us  %.1f TFLOP/s algorithmic\n", pair ? " pair" : "     ", B, V, d, bn, us, 2.0 * B * V * d / us * 1e-6);
+      }
+    for (int f16 = 0; f16 < 2; ++f16)
+      for (int ctx : {11, 25, 39}) {
+        int pos = ctx - 1;
+        CK(cudaMemcpy(dpos, &pos, 4, cudaMemcpyHostToDevice));
+        ActOut y; y.hi = o;
+        float us = time_loop(st, 240, [&](int i) {
+          if (f16) OK(launch_attn_decode_f16(qkv, kc[i % SETS], vc[i % SETS], o, o_lo, dpos, B, H, t_max, st));
+          else OK(launch_attn_decode<bf16>(qkv, kc[i % SETS], vc[i % SETS], y, dpos, B, H, t_max, st));
+        });
+        const double bytes = 2.0 * B * d * (2.0 * ctx + 2 + 3 + 1 + (f16 ? 1 : 0));
+        printf("attn_decode %s rows=%d ctx=%d: %.2f us  %.0f GB/s\n", f16 ? "fp16 cache, hi+lo out" : "bf16                 ", B, ctx, us, bytes / us * 1e-3);
+      }
+    return 0;
+  }
+
   // ---- layernorm ----
   for (int rows : {32, 256, B, 4 * B}) {
     float* hh = (float*)dmalloc((size_t)rows * d * 4);

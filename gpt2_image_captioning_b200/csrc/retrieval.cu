@@ -506,6 +506,29 @@ int launch_gather_aggregate_add(const float* q, const float* cap_db, const int64
   return GIC_OK;
 }
 
+// get_caption_embeddings' reconstruct loop + zero padding (faiss_store.py:229-251) as one gather: out[b, j, :] = cap_db[rows[b, j]] or 0
+__global__ void __launch_bounds__(128) gather_caption_rows_kernel(const float* __restrict__ cap_db, const int64_t* __restrict__ rows, int D,
+                                                                  float* __restrict__ out) {
+  const int64_t ri = rows[blockIdx.x];
+  float* dst = out + (size_t)blockIdx.x * D;
+  const float* src = cap_db + (size_t)(ri < 0 ? 0 : ri) * D;
+  if ((D & 3) == 0) {
+    for (int c = threadIdx.x * 4; c < D; c += blockDim.x * 4)
+      *reinterpret_cast<float4*>(dst + c) = ri >= 0 ? *reinterpret_cast<const float4*>(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) dst[c] = ri >= 0 ? src[c] : 0.f;
+  }
+}
+
+int launch_gather_caption_rows(const float* cap_db, const int64_t* rows, int n_rows, int D, float* out, cudaStream_t st) {
+  GIC_REQUIRE(D > 0 && n_rows >= 0, "gather_caption_rows: bad sizes");
+  if (n_rows == 0) return GIC_OK;
+  gather_caption_rows_kernel<<<n_rows, 128, 0, st>>>(cap_db, rows, D, out);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return GIC_OK;
+}
+
 // RetrievalAggregator "attention" (src/models.py:606-616): score_j = w . r_j + b over the top_k gathered rows (zero rows for -1 padding,
 // whose score is b), softmax over j, out = q + sum_j weight_j r_j
 __global__ void __launch_bounds__(256) gather_attention_add_kernel(const float* __restrict__ q, const float* __restrict__ cap_db,

@@ -156,8 +156,11 @@ class GpuFlatStore:
     def retrieve_caption_embeddings(self, image_embeddings: torch.Tensor, top_i: int, top_k: int) -> torch.Tensor:
         """float32 [B, top_k, D], zero rows for padding -- what `_retrieve_batch` returns (src/models.py:655-695)."""
         rows = self.retrieve_rows(image_embeddings, top_i, top_k)
-        out = self.caption_index.matrix[rows.clamp(min=0)]
-        return out * (rows >= 0).unsqueeze(-1).to(out.dtype)
+        out = torch.empty(rows.shape[0], top_k, self.caption_index.d, dtype=torch.float32, device=self.device)
+        if rows.shape[0]:
+            with torch.cuda.device(self.device):
+                ops.gather_caption_rows(self.caption_index.matrix, rows, out)
+        return out
 
     def retrieve_and_aggregate(self, image_embeddings: torch.Tensor, top_i: int, top_k: int, aggregation: str = "mean",
                                attention_weight: torch.Tensor | None = None, attention_bias: torch.Tensor | None = None) -> torch.Tensor:

@@ -330,7 +330,7 @@ def accelerate(model, engine_dtype: str = "bf16", num_beams: int = 1):
         if not hasattr(model, attr):
             raise TypeError(f"accelerate() expects an ImageCaptioningModel-like object with .{attr}")
     model.engine_dtype, model.num_beams = engine_dtype, num_beams
-    for name in ("_engine_key", "_get_engine", "_generate_on_engine"):
+    for name in ("_engine_key", "_get_engine", "_generate_on_engine", "invalidate_engine"):
         setattr(model, name, types.MethodType(getattr(_EngineMixin, name), model))
 
     def generate(self, image_embeddings, max_length: int = 50, temperature: float = 1.0, top_p: float = 0.9):

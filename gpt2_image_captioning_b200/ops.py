@@ -108,6 +108,14 @@ def select_caption_rows(scores: torch.Tensor, idx: torch.Tensor, cap_row_start: 
                                           _ptr(cap_row_ids), top_i, top_k, _ptr(rows_out), _stream()))
 
 
+@torch.library.custom_op("gic::gather_caption_rows", mutates_args=("out",))
+def gather_caption_rows(cap_db: torch.Tensor, rows: torch.Tensor, out: torch.Tensor) -> None:
+    """out[b, j, :] = cap_db[rows[b, j]] (zero row for -1): fp32 [B, top_k, D]."""
+    _need_cuda(cap_db, rows, out)
+    L = _capi.lib()
+    _capi.check(L.gic_gather_caption_rows(_ptr(cap_db), _ptr(rows), rows.shape[0], rows.shape[1], cap_db.shape[1], _ptr(out), _stream()))
+
+
 @torch.library.custom_op("gic::gather_attention_add", mutates_args=("out",))
 def gather_attention_add(queries: torch.Tensor, cap_db: torch.Tensor, rows: torch.Tensor, attn_w: torch.Tensor, attn_b: torch.Tensor,
                          out: torch.Tensor) -> None:

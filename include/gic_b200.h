@@ -39,7 +39,9 @@ enum { GIC_OK = 0, GIC_ERR_INVALID = -1, GIC_ERR_CUDA = -2, GIC_ERR_UNSUPPORTED 
 /* arithmetic modes.  F32: CUDA-core FFMA GEMMs, fp32 everywhere (token-exact parity mode).
  * BF16: bf16 weights/activations/KV cache, tcgen05 MMA with fp32 TMEM accumulators, fp32 residual stream,
  * LayerNorm statistics, softmax and logits.  BF16X2: every GEMM operand split hi+lo (two bf16), three
- * tcgen05 MMAs per product -- ~16 mantissa bits on the tensor cores. */
+ * tcgen05 MMAs per product -- ~16 mantissa bits on the tensor cores -- with q | k | v and the KV cache in IEEE half
+ * (11 significant bits in the bf16 cache's bytes); the tensor-core mode that meets the north-star tolerance
+ * (>= 99 % of greedy captions identical to the fp32 reference) and the one the headline benchmark is quoted in. */
 enum { GIC_DTYPE_F32 = 0, GIC_DTYPE_BF16 = 1, GIC_DTYPE_BF16X2 = 2 };
 enum { GIC_MAPPER_MLP = 0, GIC_MAPPER_TRANSFORMER = 1 };
 enum { GIC_AGG_MEAN = 0, GIC_AGG_MAX = 1, GIC_AGG_SUM_NORM = 2 };
@@ -146,13 +148,15 @@ GIC_API int gic_generate_sample(gic_engine* e, const float* image_embeddings /* 
  * do_sample=False, early_stopping=False, length_penalty given, num_return_sequences=1, eos = pad): ids_out dev int64
  * [B, max_new_tokens] = best finished hypothesis per image padded with eos; scores_out dev fp32 [B] (may be NULL) its
  * length-normalised score; *gen_len_out dev int32 (may be NULL) the longest selected hypothesis (HF crops to it).
- * 2 <= num_beams <= 8.  The KV cache is reordered every step with the gic_kv_reorder gather. */
+ * 2 <= num_beams <= 8.  The tensor-core engines never reorder the KV cache: decode attention follows a per-hypothesis ancestry table
+ * (cache row of every generated position); the fp32 engine (and GIC_BEAM_REORDER=1) reorders with the gic_kv_reorder gather. */
 GIC_API int gic_generate_beam(gic_engine* e, const float* image_embeddings, int batch, int max_new_tokens, int num_beams,
                       float length_penalty, int64_t* ids_out, float* scores_out, int32_t* gen_len_out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* replaces DynamicCache.reorder_cache / index_select(0, beam_idx) per layer (HF cache_utils.py:81-85):
- * dst[l][kv][r] = src[l][kv][beam_idx[r]] for the first `ctx_len` positions.  Element type follows the engine dtype. */
+ * dst[l][kv][r] = src[l][kv][beam_idx[r]] for the first `ctx_len` positions.  Element type follows the engine dtype
+ * (F32: float; BF16 / BF16X2: 2-byte elements). */
 GIC_API int gic_kv_reorder(gic_engine* e, const void* kv_src, void* kv_dst, const int32_t* beam_idx /* dev [rows] */,
                    int rows, int ctx_len, int t_max, void* stream);
 
@@ -181,6 +185,11 @@ GIC_API int gic_topk_ip_tc(const float* queries, const float* db, const void* db
 GIC_API int gic_select_caption_rows(const float* scores, const int64_t* idx, int batch, int k_searched,
                             const int64_t* cap_row_start, const int64_t* cap_row_ids, int top_i, int top_k,
                             int64_t* rows_out, void* stream);
+
+/* replaces get_caption_embeddings' reconstruct loop and zero padding alone (faiss_store.py:229-251), for callers that pool with the
+ * differentiable RetrievalAggregator module (the training forward, src/models.py:733-735): out dev fp32 [B, top_k, dim],
+ * out[b, j] = cap_db[rows[b, j]] or a zero row for -1. */
+GIC_API int gic_gather_caption_rows(const float* cap_db, const int64_t* rows, int batch, int top_k, int dim, float* out, void* stream);
 
 /* replaces get_caption_embeddings' reconstruct loop + RetrievalAggregator.forward (faiss_store.py:229-251,
  * src/models.py:589-625): out[b] = q[b] + agg_k(cap_db[rows[b,k]]) with zero rows for -1 (padding counts in the mean). */

@@ -162,3 +162,36 @@ def test_oracle_equals_live_reference_on_fresh_inputs():
     want = model.generate(image_embeddings=x, max_length=9, temperature=0.0)
     got = oc.CaptionOracle(spec, gpt, mapper).generate(x, 9)
     assert torch.equal(want, got)
+
+
+@pytest.mark.parametrize("full,ref_made,rows", [("c2_small_mlp_full5000", "c2_small_mlp_first1024", 1024), ("c3_medium_tfm_full32", "c3_medium_tfm", 8),
+                                                ("c4_large_mlp_full16", "c4_large_mlp", 4), ("c3_medium_tfm_beam5_full32", "c3_medium_tfm_beam5", 4)])
+def test_full_fixtures_extend_the_reference_ones(full, ref_made, rows):
+    """The full-size fixtures (tests/golden/make_golden_full.py: oracle, KV-cached; beam through HF) agree token for token with the
+    fixtures the UNMODIFIED reference produced on every row they share -- same pinned weights (fingerprint), same embeddings."""
+    a, b = gu.load(full), gu.load(ref_made)
+    assert str(a["spec_gpt"]) == str(b["spec_gpt"]) and int(a["spec_prefix_length"]) == int(b["spec_prefix_length"])
+    if "fp_abs_sum" in a and "fp_abs_sum" in b:
+        assert abs(float(a["fp_abs_sum"]) - float(b["fp_abs_sum"])) <= 1e-9 * abs(float(b["fp_abs_sum"]))
+    ia, ib = a["ids"].astype(np.int64), b["ids"].astype(np.int64)
+    L = min(ia.shape[1], ib.shape[1])
+    assert ib.shape[0] == rows and np.array_equal(ia[:rows, :L], ib[:, :L])
+    if "min_gap" in a:  # the audit data: positive, and small somewhere in 5 000 captions (random-init margins)
+        assert (a["min_gap"] > 0).all() and a["min_gap"].shape[0] == ia.shape[0]
+
+
+def test_c5_fixture_is_consistent_with_the_restated_search_on_a_subset():
+    """The config-5 fixture (float64 scores, (score desc, index asc)) against oc.flat_ip_search -- the restatement of IndexFlatIP the
+    retrieval parity tests use -- on the first rows of the seeded database (the full 591 753-row check is the -m gpu test)."""
+    g = gu.load("c5_retrieval_full")
+    gen = torch.Generator().manual_seed(int(g["db_seed"]))
+    img = torch.randn(int(g["n_img"]), 512, generator=gen)
+    img /= img.norm(dim=-1, keepdim=True)
+    q = oc.synthetic_embeddings(1024, 512, 1)
+    q[:4] = img[torch.from_numpy(g["exact_rows"].astype(np.int64))]
+    s, i = oc.flat_ip_search(img.numpy(), q[:16].numpy(), 15)
+    ok = (i == g["img_idx"][:16].astype(np.int64)).all(axis=1) | (g["img_min_gap"][:16] < 1e-6)
+    assert ok.all()
+    np.testing.assert_allclose(s, g["img_scores"][:16], atol=2e-6, rtol=0)
+    assert (g["img_scores"][:4, 0] > 0.9999).all()  # the exact database rows are their own best hit ...
+    assert (g["rat_rows"][:4, 0] // 5 != g["exact_rows"]).all()  # ... and are filtered (faiss_store.py:160-163)
