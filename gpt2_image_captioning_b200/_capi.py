@@ -67,6 +67,7 @@ SIGNATURES = {
     "gic_device_check": (C.c_int, []),
     "gic_engine_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "gic_engine_destroy": (C.c_int, [C.c_void_p]),
+    "gic_engine_clone": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "gic_engine_load_gpt2": (C.c_int, [C.c_void_p, C.POINTER(Gpt2Weights), C.c_void_p]),
     "gic_engine_load_mlp_mapper": (C.c_int, [C.c_void_p, C.POINTER(MlpMapperWeights), C.c_void_p]),
     "gic_engine_load_tfm_mapper": (C.c_int, [C.c_void_p, C.POINTER(TfmMapperWeights), C.c_void_p]),

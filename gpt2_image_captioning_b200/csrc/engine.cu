@@ -674,12 +674,34 @@ static int check_ready(const gic_engine* e) {
   return GIC_OK;
 }
 
+// per-context resources of an engine handle: the private stream generate runs on, its fork / join events, the sub-batch streams and
+// the pinned early-exit flag
+static int create_context_resources(gic_engine* e) {
+  bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaHostAlloc((void**)&e->h_done, 4 * sizeof(int), cudaHostAllocDefault) == cudaSuccess &&
+       cudaEventCreateWithFlags(&e->ev_done[0], cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&e->ev_done[1], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 1; i < gic_engine::MAX_SUB && ok; ++i)
+    ok = cudaStreamCreateWithFlags(&e->sub_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    set_error("could not create the engine stream / events: %s", cudaGetErrorString(cudaGetLastError()));
+    return GIC_ERR_CUDA;
+  }
+  return GIC_OK;
+}
+
 }  // namespace gic
 
 // =================================================================================================================
 // C ABI
 // =================================================================================================================
 extern "C" {
+
+int gic_engine_destroy(gic_engine* e);
 
 const char* gic_last_error(void) { return gic::get_error(); }
 int gic_abi_version(void) { return GIC_ABI_VERSION; }
@@ -746,21 +768,28 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
   }
   const char* sb = getenv("GIC_SUBBATCH");
   if (sb && sb[0] >= '1' && sb[0] <= '8') e->sub_batches = sb[0] - '0';
-  bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && cudaHostAlloc((void**)&e->h_done, 2 * sizeof(int), cudaHostAllocDefault) == cudaSuccess &&
-       cudaEventCreateWithFlags(&e->ev_done[0], cudaEventDisableTiming) == cudaSuccess &&
-       cudaEventCreateWithFlags(&e->ev_done[1], cudaEventDisableTiming) == cudaSuccess;
-  for (int i = 1; i < gic_engine::MAX_SUB && ok; ++i)
-    ok = cudaStreamCreateWithFlags(&e->sub_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
-         cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
-  if (!ok) {
-    gic::set_error("could not create the engine stream / events: %s", cudaGetErrorString(cudaGetLastError()));
-    delete e;
-    return GIC_ERR_CUDA;
-  }
+  if (create_context_resources(e) != GIC_OK) { delete e; return GIC_ERR_CUDA; }
+  *out = e;
+  return GIC_OK;
+}
+
+// A second CONTEXT on the same packed weights: its own stream, events, CUDA-graph cache and early-exit state, so that another batch can
+// be in flight (inflight.py) without a second copy of the weights (every in-flight slot used to be a full engine).
+// The clone borrows every weight pointer and tensor map of `src`, owns none of them (gic_engine_weight_bytes == 0), and must be
+// destroyed before `src`.
+int gic_engine_clone(const gic_engine* src, gic_engine** out) {
+  GIC_REQUIRE(src != nullptr && out != nullptr, "null argument");
+  GIC_REQUIRE(src->gpt_loaded && src->mapper_loaded, "clone an engine after its weights are loaded");
+  gic_engine* e = new gic_engine(*src);
+  e->allocs.clear();
+  e->weight_bytes = 0;
+  e->graph_exec = nullptr; e->graph_ws = nullptr; e->graph_B = 0; e->graph_max_new = 0; e->graph_nodes = 0; e->graph_steps = 1;
+  e->prof.clear(); e->profiling = false;
+  e->sample = gic_engine::SampleCfg();
+  e->stream = nullptr; e->ev_in = e->ev_out = e->ev_fork = nullptr; e->h_done = nullptr;
+  e->ev_done[0] = e->ev_done[1] = nullptr;
+  for (int i = 0; i < gic_engine::MAX_SUB; ++i) { e->sub_stream[i] = nullptr; e->ev_join[i] = nullptr; }
+  if (create_context_resources(e) != GIC_OK) { gic_engine_destroy(e); return GIC_ERR_CUDA; }
   *out = e;
   return GIC_OK;
 }

@@ -107,6 +107,20 @@ class CaptionEngine:
             torch.cuda.current_stream().synchronize()
             del keep
 
+    def clone_context(self) -> "CaptionEngine":
+        """A second context on THIS engine's packed weights (own stream, workspace, KV cache, CUDA graph): what an extra in-flight
+        slot uses (inflight.py).  Holds a reference to its parent so the weights outlive it."""
+        c = object.__new__(CaptionEngine)
+        c.lib, c.device, c.dtype, c.cfg = self.lib, self.device, self.dtype, self.cfg
+        c.embed_dim, c.gpt_dim, c.vocab, c.prefix_total = self.embed_dim, self.gpt_dim, self.vocab, self.prefix_total
+        c._ws = None
+        c._parent = self
+        c._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _capi.check(self.lib.gic_engine_clone(self._handle, C.byref(c._handle)))
+        self.__dict__.setdefault("_children", []).append(c)
+        return c
+
     # ------------------------------------------------------------------------------------------------------------
     @property
     def handle(self) -> int:
@@ -140,6 +154,8 @@ class CaptionEngine:
         return int(_capi.lib().gic_launch_count())
 
     def close(self) -> None:
+        for child in self.__dict__.pop("_children", []):  # contexts borrowing these weights go first
+            child.close()
         if self._handle:
             self.lib.gic_engine_destroy(self._handle)
             self._handle = C.c_void_p()

@@ -107,13 +107,15 @@ def load_embeddings_pt(path: str) -> tuple[list[str], torch.Tensor]:
 
 
 def generate_for_embeddings(model, embeddings: torch.Tensor, batch_size: int = 1024, max_length: int = 50, device=None,
-                            in_flight: int = 2, **generate_kw) -> torch.Tensor:
+                            in_flight: int = 2, group=None, **generate_kw) -> torch.Tensor:
     """int64 [N, max_length] token ids (EOS-padded) for a whole embeddings matrix, sharded over the ranks of an initialised
     process group if there is one (sharding.generate_sharded; other ranks get None).  `in_flight` batches run concurrently per GPU
-    (inflight.py: +10 % captions/s at 2, each extra slot holds one more packed weight copy + workspace); ids do not depend on it."""
+    (inflight.py: +10 % captions/s at 2, each extra slot is one more engine context -- workspace, KV cache, CUDA graph -- on the same
+    packed weights); ids do not depend on it.  `group`: the process group of the final host gather (e.g. a gloo group next to an NCCL
+    default group, so that the ids travel host to host)."""
     from .sharding import generate_sharded
 
     device = torch.device(device) if device is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
     model = model.to(device).eval()
     fn = lambda x: model.generate(image_embeddings=x.to(device), max_length=max_length, temperature=0.0, **generate_kw)
-    return generate_sharded(fn, embeddings, max_length, batch_size, int(model.tokenizer.eos_token_id), in_flight=in_flight)
+    return generate_sharded(fn, embeddings, max_length, batch_size, int(model.tokenizer.eos_token_id), group=group, in_flight=in_flight)

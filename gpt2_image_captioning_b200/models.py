@@ -94,8 +94,9 @@ class _EngineMixin:
             self.__dict__["_engine_key_cached"] = None
 
     def _get_engine(self) -> CaptionEngine:
-        """The engine of the calling thread's slot (inflight.current_slot(); slot 0 outside inflight.map_batches).  Every slot
-        owns an engine handle -- packed weights, workspace, CUDA graph -- so batches in different slots can run concurrently."""
+        """The engine context of the calling thread's slot (inflight.current_slot(); slot 0 outside inflight.map_batches).  Slot 0
+        owns the packed weights; every other slot is a context cloned from it (own stream, workspace, KV cache, CUDA graph, NO second
+        weight copy), so batches in different slots can run concurrently."""
         key = self._engine_key()
         with _ENGINE_LOCK:
             engines = self.__dict__.setdefault("_engines", {})
@@ -106,6 +107,8 @@ class _EngineMixin:
                 self.__dict__["_engine_key_cached"] = key
             slot = current_slot()
             eng = engines.get(slot)
+            if eng is None and slot != 0 and 0 in engines:
+                eng = engines[slot] = engines[0].clone_context()
             if eng is None:
                 mapper = self.mapping_network
                 if isinstance(mapper, MLPMappingNetwork) or hasattr(mapper, "model"):
@@ -114,7 +117,9 @@ class _EngineMixin:
                         raise NotImplementedError(f"the engine implements the reference's default Tanh mapper activation, not {type(act).__name__}")
                 task = getattr(self, "task_prefix_embeds", None)
                 eng = CaptionEngine(self.gpt, mapper, int(self.tokenizer.eos_token_id), task_prefix_embeds=task, dtype=self.engine_dtype)
-                engines[slot] = eng
+                engines[0] = eng  # the weight owner
+                if slot != 0:
+                    eng = engines[slot] = eng.clone_context()
         return eng
 
     def _generate_on_engine(self, image_embeddings: torch.Tensor, max_length: int, temperature: float, top_p: float) -> torch.Tensor:

@@ -110,6 +110,10 @@ GIC_API int gic_device_check(void); /* GIC_OK iff device 0.. current device is s
 /* replaces: model construction + `.to(device)` (src/eval.py:189-190) for the engine's packed weights */
 GIC_API int gic_engine_create(const gic_config* cfg, gic_engine** out);
 GIC_API int gic_engine_destroy(gic_engine* e);
+/* another CONTEXT on the packed weights of `src` (own stream, events, CUDA-graph cache): lets a second batch be in flight on the same
+ * GPU without a second weight copy.  The clone owns no weights (gic_engine_weight_bytes == 0) and must be destroyed before `src`;
+ * one host thread per context at a time, different contexts may be driven concurrently. */
+GIC_API int gic_engine_clone(const gic_engine* src, gic_engine** out);
 GIC_API int gic_engine_load_gpt2(gic_engine* e, const gic_gpt2_weights* w, void* stream);
 GIC_API int gic_engine_load_mlp_mapper(gic_engine* e, const gic_mlp_mapper_weights* w, void* stream);
 GIC_API int gic_engine_load_tfm_mapper(gic_engine* e, const gic_tfm_mapper_weights* w, void* stream);

@@ -24,9 +24,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=1024)
 ap.add_argument("--max-length", type=int, default=30)
 ap.add_argument("--step", type=int, default=15)
+ap.add_argument("--dtype", default="bf16x2")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
-model = bench.build_product_model("bf16", dev)
+model = bench.build_product_model(a.dtype, dev)
 eng = model._get_engine()
 x = bench.synthetic_pool(bench.POOL_ROWS, bench.E)[: a.batch].to(dev)
 eng.generate_greedy(x, a.max_length)
@@ -50,7 +51,7 @@ if a.step >= len(fins):
 lo, hi = fins[a.step - 1] + 1, fins[a.step] + 1
 sel = rows[lo:hi]
 t0 = sel[0][0]
-print(f"# decode step {a.step} of {len(fins) - 1} (B = {a.batch}, GPT-2 small bf16): {len(sel)} launches, "
+print(f"# decode step {a.step} of {len(fins) - 1} (B = {a.batch}, GPT-2 small {a.dtype}): {len(sel)} launches, "
       f"{(sel[-1][1] - t0) / 1e3:.1f} us from the first kernel's begin to the last kernel's end")
 print(f"# {'kernel':28s} {'begin_us':>9s} {'kernel_us':>9s} {'gap_us':>7s}")
 tot_gap = tot_life = 0.0
