@@ -333,6 +333,7 @@ def run_product(args, rank: int, world: int, local_rank: int) -> dict | None:
     par = parity_table()
     for dt, m in modes.items():
         m["parity"] = par.get(dt)
+    eng = model._get_engine()  # (the jobs dropped the engine to make room for the GPT-2 large one)
     # ---- per-class CUDA-event timing of the same step (eager launches: every sample carries an isolated launch's ramp) ------
     eng.profile(True)
     eng.generate_greedy(dev_batches[0], N)

@@ -90,6 +90,7 @@ SIGNATURES = {
     "gic_gather_attention_add": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_void_p]),
     "gic_gather_aggregate_add": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_void_p]),
     "gic_launch_count": (C.c_ulonglong, []),
+    "gic_compaction_count": (C.c_ulonglong, []),
     "gic_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "gic_profile_read": (C.c_int, [C.c_void_p, C.POINTER(ProfileEntry), C.c_int, C.POINTER(C.c_int)]),
     "gic_test_gemm": (C.c_int, [C.c_int, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -30,7 +30,7 @@ constexpr int HD = 64;  // GPT-2 head_dim (small/medium/large: n_embd / n_head =
 
 template <typename T>
 __global__ void __launch_bounds__(128) attn_decode_kernel(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows,
-                                                          int H, int t_max) {
+                                                          int H, int t_max, const int* row_map) {
   constexpr int VEC = 16 / sizeof(T);   // elements per 128-bit load
   constexpr int LPK = HD / VEC;         // lanes per key: 8 (bf16) / 16 (fp32)
   constexpr int KPI = 32 / LPK;         // lane groups = keys per warp load instruction
@@ -46,10 +46,13 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const T* qkv, T* kcach
   const int pos = __ldcg(d_pos);  // tokens already cached == position of the new token
   const int g = lane / LPK, sub = lane % LPK;
   (void)t_max;
+  // compacted batches (finished rows dropped, engine.cu): slot `row` of the activations belongs to cache row row_map[row]; -1 = padding slot
+  const int crow = row_map ? __ldcg(row_map + row) : row;
+  if (crow < 0) return;
 
   const T* qrow = qkv + (size_t)row * 3 * d + h * HD;
-  T* kbase = kcache + ((size_t)row * H + h) * t_max * HD;
-  T* vbase = vcache + ((size_t)row * H + h) * t_max * HD;
+  T* kbase = kcache + ((size_t)crow * H + h) * t_max * HD;
+  T* vbase = vcache + ((size_t)crow * H + h) * t_max * HD;
 
   // Single pass with an online softmax per lane group (flash-decoding style): K and V of a batch of keys are loaded
   // together and the next batch is requested before the current one is consumed, so a warp keeps 2 x KPI x UNR rows of K
@@ -429,7 +432,7 @@ struct DecMmaCfg { static constexpr int SMEM_BYTES = WARPS * STAGES * MMA_STAGE_
 template <int WARPS, int STAGES, bool INDIRECT, bool F16 = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos,
                                                                       int rows, int H, int t_max, const int* anc, int anc_ld, int n_prefix, int beams, StepTrace step_trace,
-                                                                      bf16* out_lo) {
+                                                                      bf16* out_lo, const int* row_map) {
   extern __shared__ uint8_t dec_smem_raw[];
   const uint32_t smem_base = (dec_smem_u32(dec_smem_raw) + 127u) & ~127u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -457,6 +460,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
   const int total_chunks = my_items * nch;
   const int g = lane >> 2, t = lane & 3;
 
+  // compacted batches (finished rows dropped, engine.cu): activation slot r belongs to cache row row_map[r]; -1 = padding slot, which
+  // walks cache row 0 like any other item (the ring's bookkeeping stays uniform) but appends nothing
+  auto cache_item = [&](int item) -> int {
+    if (INDIRECT || row_map == nullptr) return item;
+    const int r = item / H, c = __ldcg(row_map + r);
+    return (c < 0 ? 0 : c) * H + (item - r * H);
+  };
   // producer side (lane 0): chunk n of this warp's stream -> stage n % STAGES (the cached keys of the chunk only).
   // K / V of item i start at i * t_max * 64 elements of their plane (item = row * H + head).
   int p_item = w0, p_c = 0, p_s = 0;  // producer cursor: item, chunk of the item, stage
@@ -466,7 +476,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
     const uint32_t bytes = (uint32_t)nkeys * HD * 2;
     const uint32_t bar = bars + 8 * p_s, dst = ring + p_s * MMA_STAGE_BYTES;
     if (!INDIRECT) {
-      const size_t off = ((size_t)p_item * t_max + (size_t)p_c * MMA_CHUNK) * HD;
+      const size_t off = ((size_t)cache_item(p_item) * t_max + (size_t)p_c * MMA_CHUNK) * HD;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * bytes) : "memory");
       if (bytes > 0) {
         dec_bulk_load(dst, kcache + off, bytes, bar);
@@ -525,6 +535,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
   uint32_t c_ph = 0;
   for (int ii = 0; ii < my_items; ++ii) {
     const int item = w0 + ii * wstride;
+    const bool live_slot = INDIRECT || row_map == nullptr || __ldcg(row_map + item / H) >= 0;
+    const int citem = cache_item(item);
     uint32_t qa[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) qa[i] = scale_eighth<F16>(qa_n[i]);
@@ -543,9 +555,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
       if (last && lane < 8) {
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + cached * (HD * 2) + lane * 16), "r"(knew.x), "r"(knew.y), "r"(knew.z), "r"(knew.w) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + MMA_CHUNK * HD * 2 + cached * (HD * 2) + lane * 16), "r"(vnew.x), "r"(vnew.y), "r"(vnew.z), "r"(vnew.w) : "memory");
-        const size_t coff = ((size_t)item * t_max + pos) * HD + lane * 8;
-        *reinterpret_cast<uint4*>(kcache + coff) = knew;  // append to the cache (HF:cache_utils.py:102-121)
-        *reinterpret_cast<uint4*>(vcache + coff) = vnew;
+        const size_t coff = ((size_t)citem * t_max + pos) * HD + lane * 8;
+        if (live_slot) {
+          *reinterpret_cast<uint4*>(kcache + coff) = knew;  // append to the cache (HF:cache_utils.py:102-121)
+          *reinterpret_cast<uint4*>(vcache + coff) = vnew;
+        }
       }
       dec_mbar_wait(bars + 8 * c_s, c_ph);
       __syncwarp();  // the new token's row is visible to every lane's ldmatrix
@@ -652,8 +666,9 @@ int attn_decode_configure() {
 }
 
 static int launch_attn_decode_bulk(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos, int rows, int H, int t_max,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, const int* row_map) {
   GIC_TRY(attn_decode_configure());
+  GIC_REQUIRE(row_map == nullptr || g_dec_variant >= 10, "attn_decode: the SIMT comparison kernels do not take a row map");
   const int sms = cta_limit() > 0 && cta_limit() < g_dec_sms ? cta_limit() : g_dec_sms;
   const int items = rows * H;
 #define X(ID, W, C, S)                                                                                                              \
@@ -670,7 +685,7 @@ static int launch_attn_decode_bulk(const bf16* qkv, bf16* kcache, bf16* vcache, 
   if (g_dec_variant == ID) {                                                                                                         \
     const int grid = min(sms, ceil_div(items, W));                                                                                   \
     GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<W, S, false>, dim3(grid), dim3(W * 32), (size_t)DecMmaCfg<W, S>::SMEM_BYTES, st, qkv, kcache, \
-                                 vcache, out, d_pos, rows, H, t_max, (const int*)nullptr, 0, 0, 1, trace_desc(), (bf16*)nullptr));                 \
+                                 vcache, out, d_pos, rows, H, t_max, (const int*)nullptr, 0, 0, 1, trace_desc(), (bf16*)nullptr, row_map));        \
     note_launch();                                                                                                                   \
     return GIC_OK;                                                                                                                   \
   }
@@ -689,10 +704,10 @@ int launch_attn_decode_indirect(const bf16* qkv, bf16* kcache, bf16* vcache, bf1
   const int grid = min(sms, ceil_div(rows * H, 12));
   if (out_lo)  // fp16 q / k / v / cache, hi + lo output (bf16x2 engine)
     GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<12, 4, true, true>, dim3(grid), dim3(12 * 32), (size_t)DecMmaCfg<12, 4>::SMEM_BYTES, st, qkv, kcache,
-                                 vcache, out, d_pos, rows, H, t_max, anc, anc_ld, n_prefix, beams, trace_desc(), out_lo));
+                                 vcache, out, d_pos, rows, H, t_max, anc, anc_ld, n_prefix, beams, trace_desc(), out_lo, (const int*)nullptr));
   else
     GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<12, 4, true>, dim3(grid), dim3(12 * 32), (size_t)DecMmaCfg<12, 4>::SMEM_BYTES, st, qkv, kcache, vcache,
-                                 out, d_pos, rows, H, t_max, anc, anc_ld, n_prefix, beams, trace_desc(), (bf16*)nullptr));
+                                 out, d_pos, rows, H, t_max, anc, anc_ld, n_prefix, beams, trace_desc(), (bf16*)nullptr, (const int*)nullptr));
   note_launch();
   return GIC_OK;
 }
@@ -700,13 +715,13 @@ int launch_attn_decode_indirect(const bf16* qkv, bf16* kcache, bf16* vcache, bf1
 // decode attention of the bf16x2 engine: fp16 q | k | v and KV cache (2-byte elements, typed bf16* for the shared plumbing), output as a
 // bf16 hi + lo pair
 int launch_attn_decode_f16(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out_hi, bf16* out_lo, const int* d_pos, int rows, int H, int t_max,
-                           cudaStream_t st) {
+                           cudaStream_t st, const int* row_map) {
   GIC_TRY(attn_decode_configure());
   GIC_REQUIRE(out_hi && out_lo, "attn_decode_f16: needs both output halves");
   const int sms = cta_limit() > 0 && cta_limit() < g_dec_sms ? cta_limit() : g_dec_sms;
   const int grid = min(sms, ceil_div(rows * H, 12));
   GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<12, 4, false, true>, dim3(grid), dim3(12 * 32), (size_t)DecMmaCfg<12, 4>::SMEM_BYTES, st, qkv, kcache,
-                               vcache, out_hi, d_pos, rows, H, t_max, (const int*)nullptr, 0, 0, 1, trace_desc(), out_lo));
+                               vcache, out_hi, d_pos, rows, H, t_max, (const int*)nullptr, 0, 0, 1, trace_desc(), out_lo, row_map));
   note_launch();
   return GIC_OK;
 }
@@ -725,18 +740,18 @@ template <typename T> struct IsBf16 { static constexpr bool value = false; };
 template <> struct IsBf16<bf16> { static constexpr bool value = true; };
 
 template <typename T>
-int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows, int H, int t_max, cudaStream_t st) {
+int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows, int H, int t_max, cudaStream_t st, const int* row_map) {
   if (IsBf16<T>::value && out.hi && !out.lo && !out.f32 && decode_bulk_enabled())
-    return launch_attn_decode_bulk((const bf16*)qkv, (bf16*)kcache, (bf16*)vcache, out.hi, d_pos, rows, H, t_max, st);
+    return launch_attn_decode_bulk((const bf16*)qkv, (bf16*)kcache, (bf16*)vcache, out.hi, d_pos, rows, H, t_max, st, row_map);
   const int warps = rows * H;
   const int blocks = ceil_div(warps, 4);
   const size_t smem = 0;
-  GIC_CHECK_CUDA(launch_kernel(attn_decode_kernel<T>, dim3(blocks), dim3(128), smem, st, qkv, kcache, vcache, out, d_pos, rows, H, t_max));
+  GIC_CHECK_CUDA(launch_kernel(attn_decode_kernel<T>, dim3(blocks), dim3(128), smem, st, qkv, kcache, vcache, out, d_pos, rows, H, t_max, row_map));
   note_launch();
   return GIC_OK;
 }
-template int launch_attn_decode<float>(const float*, float*, float*, ActOut, const int*, int, int, int, cudaStream_t);
-template int launch_attn_decode<bf16>(const bf16*, bf16*, bf16*, ActOut, const int*, int, int, int, cudaStream_t);
+template int launch_attn_decode<float>(const float*, float*, float*, ActOut, const int*, int, int, int, cudaStream_t, const int*);
+template int launch_attn_decode<bf16>(const bf16*, bf16*, bf16*, ActOut, const int*, int, int, int, cudaStream_t, const int*);
 
 // ---------------------------------------------------------------------------------------------------------------
 // Sequence attention: one block per (row, head), K/V of the row staged in shared memory as fp32, one warp per query.

@@ -81,7 +81,7 @@ typedef __nv_bfloat16 bf16;
 // nothing).  The tool pre-fills begin with ~0 and end with 0.  A captured graph keeps the slots it was captured with, so the
 // traced run captures all decode steps into one graph.
 struct StepTrace { unsigned long long* buf; unsigned int slot; unsigned int cap; };
-enum TraceKind { TRACE_GEMM = 1, TRACE_ATTN_DECODE = 2, TRACE_LAYERNORM = 3, TRACE_FINALIZE = 4, TRACE_ATTN_PREFILL = 5 };
+enum TraceKind { TRACE_GEMM = 1, TRACE_ATTN_DECODE = 2, TRACE_LAYERNORM = 3, TRACE_FINALIZE = 4, TRACE_ATTN_PREFILL = 5, TRACE_RESCORE = 6 };
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) : : "memory");  // (memory clobber: must not drift across barriers / waits)

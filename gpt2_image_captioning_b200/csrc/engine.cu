@@ -75,6 +75,11 @@ struct Workspace {
   unsigned char* finished = nullptr; int* first_eos = nullptr;
   int *d_step = nullptr, *d_pos = nullptr, *done_counter = nullptr;
   int *fin_counter = nullptr, *all_done = nullptr;  // [sub-batch] rows finished in the current step / every row has emitted EOS
+  int* live_rows = nullptr;        // [sub-batch] unfinished rows after the last step (the host sizes the compacted batch from it)
+  // finished-row compaction (greedy): slot -> caption row map of the compacted batch (null while the batch is whole), scratch for the move
+  const int* row_map = nullptr;
+  int* row_map_buf = nullptr; int* src_slot = nullptr;
+  float* h_tmp = nullptr; bf16* a_tmp_hi = nullptr; bf16* a_tmp_lo = nullptr; float2* stats_tmp = nullptr;
   // beam search only
   void* kv2 = nullptr;             // second KV cache (reorder target; the two swap every step); null with the ancestry table
   const int* anc = nullptr; int anc_ld = 0;  // beam search without reordering: ancestry table of the current step (see attention.cu)
@@ -115,10 +120,11 @@ struct gic_engine {
   Linear map1, map2;             // MLP
   Linear tfm_linear; float* tfm_prefix_const = nullptr; std::vector<TfmLayer> tfm_layers;
   // decode-step CUDA graph cache (one entry)
-  cudaGraphExec_t graph_exec = nullptr;
+  struct GraphEntry { int M; cudaGraphExec_t exec; int nodes; };  // one chunk of decode steps over M activation slots
+  std::vector<GraphEntry> graphs;  // M = the whole batch, plus one entry per compacted size used so far
   void* graph_ws = nullptr; int graph_B = 0, graph_max_new = 0;
   bool use_graph = true;
-  int graph_nodes = 0, graph_steps = 1;  // kernel nodes / decode steps held by graph_exec
+  int graph_steps = 1;  // decode steps held by each graph
   unsigned int graph_trace_gen = 0;        // trace_generation() the graph was captured under
   // early exit (src/models.py:390-391): the host looks at the `all rows finished` flag of chunk c - 1 while chunk c runs
   int* h_done = nullptr;  // pinned [2]
@@ -165,6 +171,7 @@ bool pdl_enabled() {
 
 // kernels launched by this library (graph replays count their kernel nodes) -- bench.py's `gpu_launches`
 // (atomic + a per-thread count: engines may be driven from several host threads, one stream each)
+static std::atomic<unsigned long long> g_compactions{0};  // finished-row compactions performed (gic_compaction_count)
 static std::atomic<unsigned long long> g_launches{0};
 static thread_local unsigned long long tl_launches = 0;
 void note_launch() { ++tl_launches; g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -338,6 +345,16 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
   w->done_counter = c.take<int>(gic_engine::MAX_SUB);
   w->fin_counter = c.take<int>(gic_engine::MAX_SUB);
   w->all_done = c.take<int>(gic_engine::MAX_SUB);
+  w->live_rows = c.take<int>(gic_engine::MAX_SUB);
+  if (w->beams == 1) {
+    w->row_map_buf = c.take<int>(w->rows); w->src_slot = c.take<int>(w->rows);
+    w->h_tmp = c.take<float>((size_t)w->rows * d);
+    if (e->fuse_ln) {
+      w->a_tmp_hi = c.take<bf16>((size_t)w->rows * d);
+      if (e->split) w->a_tmp_lo = c.take<bf16>((size_t)w->rows * d);
+      w->stats_tmp = c.take<float2>(w->rows);
+    }
+  }
   w->bytes = align_up(c.off, 1024) + 1024;
 }
 
@@ -423,19 +440,19 @@ static int attention(const gic_engine* e, const Workspace& w, int l, int M, bool
     bf16* vc = kc + w.kv_layer_elems;
     if (prefill) return launch_attn_prefill_f16(w.qkv_bf16, kc, vc, w.o.hi, w.o.lo, w.B, w.P, e->H, w.t_max, w.beams, st);
     if (w.anc) return launch_attn_decode_indirect(w.qkv_bf16, kc, vc, w.o.hi, w.d_pos, M, e->H, w.t_max, w.anc, w.anc_ld, w.P, w.beams, st, w.o.lo);
-    return launch_attn_decode_f16(w.qkv_bf16, kc, vc, w.o.hi, w.o.lo, w.d_pos, M, e->H, w.t_max, st);
+    return launch_attn_decode_f16(w.qkv_bf16, kc, vc, w.o.hi, w.o.lo, w.d_pos, M, e->H, w.t_max, st, w.row_map);
   }
   if (e->cfg.dtype == GIC_DTYPE_BF16) {
     bf16* kc = (bf16*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
     bf16* vc = kc + w.kv_layer_elems;
     if (prefill) return launch_attn_prefill<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, w.beams, st);
     if (w.anc) return launch_attn_decode_indirect(w.qkv_bf16, kc, vc, w.o.hi, w.d_pos, M, e->H, w.t_max, w.anc, w.anc_ld, w.P, w.beams, st);
-    return launch_attn_decode<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st);
+    return launch_attn_decode<bf16>(w.qkv_bf16, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st, w.row_map);
   }
   float* kc = (float*)w.kv + (size_t)(2 * l) * w.kv_layer_elems;
   float* vc = kc + w.kv_layer_elems;
   if (prefill) return launch_attn_prefill<float>(w.qkv_f32, kc, vc, w.o.out(), w.B, w.P, e->H, w.t_max, w.beams, st);
-  return launch_attn_decode<float>(w.qkv_f32, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st);
+  return launch_attn_decode<float>(w.qkv_f32, kc, vc, w.o.out(), w.d_pos, M, e->H, w.t_max, st, w.row_map);
 }
 
 // one GPT-2 block over M rows of the residual stream `h` (HF GPT2Block.forward :262-309).
@@ -513,7 +530,7 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
       { ProfScope ps(e, "lm_head", st); GIC_TRY(launch_gemm_bf16(g, st)); }
       { ProfScope ps(e, "lm_head_rescore", st);
         GIC_TRY(launch_lm_head_rescore(h, row_stride, e->lnf.w, e->lnf.b, e->wte_f32, e->wte_norm_max, w.part_val, w.part_idx, w.part_val2, n_parts,
-                                       w.n_parts_max, bn, rows, e->V, d, w.rescore_stats, st)); }
+                                       w.n_parts_max, bn, rows, e->V, d, w.rescore_stats, st, w.row_map)); }
       n_parts = 1;
     } else if (!e->tc) {
       float* lg = logits_tap ? logits_tap : w.logits;
@@ -540,7 +557,7 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
   fa.part_val = w.part_val; fa.part_idx = w.part_idx; fa.n_parts = n_parts; fa.part_ld = w.n_parts_max;
   fa.B = rows; fa.d = d; fa.eos = e->cfg.eos_token_id; fa.max_new = w.max_new; fa.P = w.P; fa.n_pos = e->cfg.n_positions;
   fa.d_step = w.d_step; fa.d_pos = w.d_pos; fa.done_counter = w.done_counter; fa.fin_counter = w.fin_counter; fa.all_done = w.all_done;
-  fa.finished = w.finished; fa.first_eos = w.first_eos; fa.ids_out = w.ids;
+  fa.finished = w.finished; fa.first_eos = w.first_eos; fa.ids_out = w.ids; fa.row_map = w.row_map; fa.live_rows = w.live_rows;
   fa.wte_f32 = e->wte_f32; fa.wte_bf16 = e->wte_f32 ? nullptr : e->wte_gather;
   fa.wpe = e->wpe; fa.h_next = w.h_dec;
   fa.hb_next = e->fuse_ln ? w.a.hi : nullptr; fa.hb_next_lo = e->fuse_ln ? w.a.lo : nullptr; fa.stats_next = e->fuse_ln ? w.ln_stats : nullptr;
@@ -576,7 +593,7 @@ static Workspace slice_rows(const gic_engine* e, const Workspace& w, int row0, i
   if (s.part_val2) s.part_val2 += (size_t)w.n_parts_max * row0;
   s.ids += (size_t)row0 * w.max_new;
   s.finished += row0; s.first_eos += row0;
-  s.d_step += sub; s.d_pos += sub; s.done_counter += sub; s.fin_counter += sub; s.all_done += sub;
+  s.d_step += sub; s.d_pos += sub; s.done_counter += sub; s.fin_counter += sub; s.all_done += sub; s.live_rows += sub;
   return s;
 }
 
@@ -783,7 +800,7 @@ int gic_engine_clone(const gic_engine* src, gic_engine** out) {
   gic_engine* e = new gic_engine(*src);
   e->allocs.clear();
   e->weight_bytes = 0;
-  e->graph_exec = nullptr; e->graph_ws = nullptr; e->graph_B = 0; e->graph_max_new = 0; e->graph_nodes = 0; e->graph_steps = 1;
+  e->graphs.clear(); e->graph_ws = nullptr; e->graph_B = 0; e->graph_max_new = 0; e->graph_steps = 1;
   e->prof.clear(); e->profiling = false;
   e->sample = gic_engine::SampleCfg();
   e->stream = nullptr; e->ev_in = e->ev_out = e->ev_fork = nullptr; e->h_done = nullptr;
@@ -797,7 +814,7 @@ int gic_engine_clone(const gic_engine* src, gic_engine** out) {
 int gic_engine_destroy(gic_engine* e) {
   if (!e) return GIC_OK;
   if (e->stream) cudaStreamSynchronize(e->stream);
-  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
   for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
@@ -935,17 +952,10 @@ int gic_mapper_forward(gic_engine* e, const float* x, int batch, float* prefix_o
   return join_stream(e, user);
 }
 
-int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, int64_t* ids_out, int32_t* gen_len_out, float* logits_out,
-                        void* workspace, size_t workspace_bytes, void* stream) {
-  GIC_TRY(check_ready(e));
-  GIC_REQUIRE(x && ids_out, "null argument");
-  GIC_REQUIRE(max_new >= 1, "max_new_tokens must be >= 1 (the caller handles 0, src/models.py:471-473)");
-  Workspace w;
-  GIC_TRY(prepare_ws(e, workspace, workspace_bytes, batch, max_new, 1, &w));
-  cudaStream_t user = (cudaStream_t)stream, st = e->stream;
-  const int d = e->d, B = batch, P = w.P;
-  GIC_TRY(fork_stream(e, user));
-
+// the body of gic_generate_greedy between fork_stream and join_stream (the caller joins on every path, errors included)
+static int generate_greedy_on_stream(gic_engine* e, const float* x, int max_new, int64_t* ids_out, int32_t* gen_len_out, float* logits_out,
+                                     void* workspace, Workspace& w, cudaStream_t st) {
+  const int d = e->d, B = w.B, P = w.P;
   GIC_TRY(launch_init_decode_state(w.finished, w.first_eos, B, max_new, w.d_step, w.d_pos, w.done_counter, P, w.fin_counter, w.all_done, w.ids,
                                    e->cfg.eos_token_id, st));
   if (w.splitk_counters) GIC_CHECK_CUDA(cudaMemsetAsync(w.splitk_counters, 0, 4096 * sizeof(int), st));
@@ -960,65 +970,121 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
   GIC_TRY(lm_head_and_token(e, w, w.h, (long)(P - 1) * d, (long)P * d, B, B * P, logits_out, st));
 
   // ---- decode: max_new-1 identical steps; positions / step index live on the device.  They run in chunks of DECODE_CHUNK steps
-  // (one CUDA graph per chunk); while chunk c runs the host reads chunk c-1's "every row has emitted EOS" flag and stops
-  // launching once it is set -- the reference's `if is_finished.all(): break` (src/models.py:390-391) without a per-step sync.
-  // Random-init weights never emit EOS, so the headline benchmark runs every chunk. ----
+  // (one CUDA graph per chunk); while chunk c runs the host reads chunk c-1's "every row has emitted EOS" flag and live-row count:
+  // it stops launching once the flag is set -- the reference's `if is_finished.all(): break` (src/models.py:390-391) without a
+  // per-step sync -- and SHRINKS the batch to the live rows when enough have finished (compact_rows_kernel: the reference finishes
+  // rows one by one, :453-460, and trained models stop at 10-20 of 50 tokens).  Random-init weights never emit EOS, so the headline
+  // benchmark runs every chunk at full size. ----
   const int steps = max_new - 1;
   constexpr int DECODE_CHUNK = 4;
   const bool graph_ok = e->use_graph && !e->profiling && logits_out == nullptr && steps >= 2;
   static const bool per_step = [] { const char* v = getenv("GIC_GRAPH_PER_STEP"); return v && v[0] == '1'; }();
   const char* ne = getenv("GIC_NO_EARLY_EXIT");  // (read per call: a test flips it inside one process)
   const bool no_early = ne && ne[0] == '1';
+  const char* nc = getenv("GIC_NO_COMPACT");
   // (a traced run keeps one record per launch: one graph holding every step, no replays)
   const bool early = !no_early && !gic::trace_on() && e->sub_batches < 2 && !(logits_out && !e->sample.on) && e->h_done != nullptr;
+  const bool compact = early && !(nc && nc[0] == '1') && !logits_out && w.row_map_buf != nullptr && B >= 256;
   const int chunk = (graph_ok && per_step) ? 1 : (early ? DECODE_CHUNK : (graph_ok ? steps : DECODE_CHUNK));
+  Workspace wc = w;  // the batch as the decode steps see it: all B rows, or the first M slots of the compacted state
   auto eager_step = [&](int s) {
-    return decode_step_all(e, w, logits_out ? (e->sample.on ? logits_out : logits_out + (size_t)s * B * e->V) : nullptr, st);
+    return decode_step_all(e, wc, logits_out ? (e->sample.on ? logits_out : logits_out + (size_t)s * B * e->V) : nullptr, st);
   };
   int s_next = 1;  // next decode step (1-based, as the logits tap is indexed)
   // the steps that do not fill a whole chunk go first, as ordinary launches (the host is far ahead of the device after prefill)
   const int lead = graph_ok ? steps % chunk : 0;
   for (; s_next <= lead; ++s_next) GIC_TRY(eager_step(s_next));
-  if (graph_ok && steps - lead > 0 &&
-      !(e->graph_exec && e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new && e->graph_steps == chunk && e->graph_trace_gen == gic::trace_generation())) {
-    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+  if (!(e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new && e->graph_steps == chunk && e->graph_trace_gen == gic::trace_generation())) {
+    for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+    e->graphs.clear();
+    e->graph_ws = workspace; e->graph_B = B; e->graph_max_new = max_new; e->graph_steps = chunk; e->graph_trace_gen = gic::trace_generation();
+  }
+  // the chunk graph over the current batch view (captured on first use, one per batch size)
+  auto chunk_graph = [&](const gic_engine::GraphEntry** out) -> int {
+    for (auto& g : e->graphs) if (g.M == wc.rows) { *out = &g; return GIC_OK; }
     cudaGraph_t graph = nullptr;
     const unsigned long long before = tl_launches;
-    e->graph_steps = chunk;
     GIC_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int r = GIC_OK;
-    for (int s = 0; s < chunk && r == GIC_OK; ++s) r = decode_step_all(e, w, nullptr, st);
+    for (int s = 0; s < chunk && r == GIC_OK; ++s) r = decode_step_all(e, wc, nullptr, st);
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    e->graph_nodes = (int)(tl_launches - before);  // captured, not executed
+    gic_engine::GraphEntry ge;
+    ge.M = wc.rows; ge.exec = nullptr;
+    ge.nodes = (int)(tl_launches - before);  // captured, not executed
     g_launches.fetch_sub(tl_launches - before, std::memory_order_relaxed);
     tl_launches = before;
     if (r != GIC_OK) { if (graph) cudaGraphDestroy(graph); return r; }
     GIC_CHECK_CUDA(ce);
-    ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+    ce = cudaGraphInstantiate(&ge.exec, graph, 0);
     cudaGraphDestroy(graph);
     GIC_CHECK_CUDA(ce);
-    e->graph_ws = workspace; e->graph_B = B; e->graph_max_new = max_new; e->graph_trace_gen = gic::trace_generation();
-  }
+    e->graphs.push_back(ge);
+    *out = &e->graphs.back();
+    return GIC_OK;
+  };
+  int m_pending = 0;  // > 0: shrink the batch to this many slots before the next chunk
   for (int c = 0; s_next <= steps; ++c) {
+    if (m_pending > 0) {
+      CompactArgs ca;
+      ca.finished = w.finished; ca.row_map_old = wc.row_map; ca.m_old = wc.rows; ca.m_new = m_pending; ca.d = d;
+      ca.row_map_new = w.row_map_buf; ca.src_slot = w.src_slot;
+      ca.h = w.h_dec; ca.h_tmp = w.h_tmp; ca.a_hi = e->fuse_ln ? w.a.hi : nullptr; ca.a_hi_tmp = w.a_tmp_hi;
+      ca.a_lo = e->fuse_ln ? w.a.lo : nullptr; ca.a_lo_tmp = w.a_tmp_lo; ca.stats = e->fuse_ln ? w.ln_stats : nullptr; ca.stats_tmp = w.stats_tmp;
+      { ProfScope ps(e, "compact_rows", st); GIC_TRY(launch_compact_rows(ca, st)); }
+      wc.rows = m_pending; wc.row_map = w.row_map_buf;
+      m_pending = 0;
+      g_compactions.fetch_add(1, std::memory_order_relaxed);
+    }
     const int n = steps - s_next + 1 < chunk ? steps - s_next + 1 : chunk;
     if (graph_ok) {
-      GIC_CHECK_CUDA(cudaGraphLaunch(e->graph_exec, st));
-      g_launches.fetch_add((unsigned long long)e->graph_nodes, std::memory_order_relaxed);
+      const gic_engine::GraphEntry* ge = nullptr;
+      GIC_TRY(chunk_graph(&ge));
+      GIC_CHECK_CUDA(cudaGraphLaunch(ge->exec, st));
+      g_launches.fetch_add((unsigned long long)ge->nodes, std::memory_order_relaxed);
     } else {
       for (int i = 0; i < n; ++i) GIC_TRY(eager_step(s_next + i));
     }
     s_next += n;
     if (early && s_next <= steps) {
-      GIC_CHECK_CUDA(cudaMemcpyAsync(e->h_done + (c & 1), w.all_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+      int* hd = e->h_done + 2 * (c & 1);  // {every row finished, live rows} after chunk c
+      GIC_CHECK_CUDA(cudaMemcpyAsync(hd, w.all_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+      GIC_CHECK_CUDA(cudaMemcpyAsync(hd + 1, w.live_rows, sizeof(int), cudaMemcpyDeviceToHost, st));
       GIC_CHECK_CUDA(cudaEventRecord(e->ev_done[c & 1], st));
       if (c >= 1) {
         GIC_CHECK_CUDA(cudaEventSynchronize(e->ev_done[(c - 1) & 1]));
-        if (e->h_done[(c - 1) & 1]) break;  // (chunk c is already queued: at most one chunk runs past the end)
+        const int* hp = e->h_done + 2 * ((c - 1) & 1);
+        if (hp[0]) break;  // (chunk c is already queued: at most one chunk runs past the end)
+        if (compact) {
+          // rows only ever finish, so the count after chunk c-1 bounds the live rows at any later time.  Sizes are multiples of 256 rows
+          // (whole CTA pairs of 128-row tiles), and a shrink must drop at least a quarter of the current slots to pay for its three launches
+          const int live = hp[1] < 1 ? 1 : hp[1];
+          const int m_new = live <= 128 ? 128 : ((live + 255) / 256) * 256;
+          if (m_new <= wc.rows - wc.rows / 4 && m_new < wc.rows) m_pending = m_new;
+        }
       }
     }
   }
   GIC_CHECK_CUDA(cudaMemcpyAsync(ids_out, w.ids, (size_t)B * max_new * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
   if (gen_len_out) GIC_TRY(launch_gen_len(w.first_eos, B, max_new, gen_len_out, st));
+  return GIC_OK;
+}
+
+int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, int64_t* ids_out, int32_t* gen_len_out, float* logits_out,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  GIC_TRY(check_ready(e));
+  GIC_REQUIRE(x && ids_out, "null argument");
+  GIC_REQUIRE(max_new >= 1, "max_new_tokens must be >= 1 (the caller handles 0, src/models.py:471-473)");
+  Workspace w;
+  GIC_TRY(prepare_ws(e, workspace, workspace_bytes, batch, max_new, 1, &w));
+  cudaStream_t user = (cudaStream_t)stream;
+  GIC_TRY(fork_stream(e, user));
+  const int r = generate_greedy_on_stream(e, x, max_new, ids_out, gen_len_out, logits_out, workspace, w, e->stream);
+  if (r != GIC_OK) {
+    // keep the caller's stream ordered behind whatever was queued before the failure (the error text of `r` stands)
+    if (cudaEventRecord(e->ev_out, e->stream) == cudaSuccess) cudaStreamWaitEvent(user, e->ev_out, 0);
+    cudaGetLastError();
+    return r;
+  }
   return join_stream(e, user);
 }
 
@@ -1162,6 +1228,7 @@ int gic_gather_aggregate_add(const float* q, const float* cap_db, const int64_t*
 }
 
 unsigned long long gic_launch_count(void) { return gic::g_launches.load(std::memory_order_relaxed); }
+unsigned long long gic_compaction_count(void) { return gic::g_compactions.load(std::memory_order_relaxed); }
 
 int gic_profile_enable(gic_engine* e, int on) {
   GIC_REQUIRE(e != nullptr, "null engine");

@@ -98,15 +98,17 @@ int launch_build_mapper_seq(const float* lin, const float* prefix_const, float* 
 template <typename T>
 int launch_attn_prefill(const T* qkv, T* kcache, T* vcache, ActOut out, int B, int P, int H, int t_max, int cache_row_mult,
                         cudaStream_t st);
+// row_map (optional, dev int [rows]): compacted batch -- activation slot r attends / appends to cache row row_map[r]; -1 = padding slot
 template <typename T>
-int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows, int H, int t_max, cudaStream_t st);
+int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int* d_pos, int rows, int H, int t_max, cudaStream_t st,
+                       const int* row_map = nullptr);
 // bf16 decode attention through a beam-ancestry table instead of a reordered cache (beam search); see attention.cu
 // (out_lo non-null: the fp16-cache / hi + lo output flavour of the bf16x2 engine)
 int launch_attn_decode_indirect(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos, int rows, int H, int t_max, const int* anc,
                                 int anc_ld, int n_prefix, int beams, cudaStream_t st, bf16* out_lo = nullptr);
 // bf16x2 engine: q | k | v and the KV cache are IEEE half (2-byte elements, typed bf16* for the shared plumbing), the output a bf16 hi + lo pair
 int launch_attn_decode_f16(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out_hi, bf16* out_lo, const int* d_pos, int rows, int H, int t_max,
-                           cudaStream_t st);
+                           cudaStream_t st, const int* row_map = nullptr);
 int launch_attn_prefill_f16(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out_hi, bf16* out_lo, int B, int P, int H, int t_max, int cache_row_mult,
                             cudaStream_t st);
 bool attn_decode_indirect_available();
@@ -137,13 +139,23 @@ struct FinalizeArgs {
   bf16* hb_next;            // optional [B, d]: its bf16 copy (A operand of the first GEMM with folded LayerNorm) ...
   bf16* hb_next_lo = nullptr;  // ... bf16x2: the remainder bf16(x - hi) (fp32 embedding table only) ...
   float2* stats_next;       // ... and [B] (sum, sum of squares) of that copy
+  const int* row_map = nullptr;  // compacted batch: caption row of activation slot b (-1 = padding slot); null = identity
+  int* live_rows = nullptr;      // optional device scalar: unfinished rows after this step
 };
 int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st);
 // exact greedy token from the single-MMA bf16 head's per-slot (best, column, runner-up) partials: candidates within the rounding margin of
 // the approximate maximum are re-scored in fp32 against ln_f(h) . wte_f32 (see lmhead.cu); result -> partial 0 of each row
 int launch_lm_head_rescore(const float* h, long h_row_stride, const float* lnw, const float* lnb, const float* wte_f32, const float* wte_norm_max,
                            float* part_val, int* part_idx, const float* part_val2, int n_parts, int part_ld, int block_n, int rows, int V, int d,
-                           int* stats, cudaStream_t st);
+                           int* stats, cudaStream_t st, const int* row_map = nullptr);
+// finished-row compaction between decode chunks (lmhead.cu): packs the live rows' next-step state to the first m_new slots and writes
+// the new slot -> caption-row map; the KV cache stays where it is
+struct CompactArgs {
+  const unsigned char* finished; const int* row_map_old; int m_old, m_new, d;
+  int* row_map_new; int* src_slot;
+  float* h; float* h_tmp; bf16* a_hi; bf16* a_hi_tmp; bf16* a_lo; bf16* a_lo_tmp; float2* stats; float2* stats_tmp;
+};
+int launch_compact_rows(const CompactArgs& c, cudaStream_t st);
 int launch_row_norm_max(const float* w, int N, int K, float* out, cudaStream_t st);
 // temperature / top-p sampling of one token per row from fp32 logits [B, V] (src/models.py:400-449); the token goes to slot 0 of the
 // row's (value, index) partials.  step: *d_step unless step_override >= 0 (the Philox counter is (row, step)).

@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(RESCORE_THREADS) lm_head_rescore_kernel(const 
                                                                           const float* __restrict__ lnb, const float* __restrict__ wte,
                                                                           const float* __restrict__ wte_norm_max, float* part_val, int* part_idx,
                                                                           const float* part_val2, int n_parts, int part_ld, int block_n, int V, int d,
-                                                                          int* stats /* [2]: candidates re-scored, rows that rescanned slots */) {
+                                                                          int* stats /* [2]: candidates re-scored, rows that rescanned slots */,
+                                                                          const int* row_map, StepTrace step_trace) {
   extern __shared__ float rs_a[];  // [d] ln_f(h) in fp32
   __shared__ float red[RESCORE_THREADS / 32];
   __shared__ int s_cand[RESCORE_MAX_CAND];
@@ -238,6 +239,8 @@ __global__ void __launch_bounds__(RESCORE_THREADS) lm_head_rescore_kernel(const 
   const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
   pdl_launch_dependents();
   pdl_wait();
+  if (row_map && __ldcg(row_map + b) < 0) return;  // padding slot of a compacted batch (its activations are garbage)
+  const int tslot = trace_begin(step_trace, TRACE_RESCORE, 0);
   auto block_sum = [&](float v) {
     v = warp_sum(v);
     __syncthreads();
@@ -320,14 +323,15 @@ __global__ void __launch_bounds__(RESCORE_THREADS) lm_head_rescore_kernel(const 
       if (ncand > 8) atomicAdd(stats + 1, 1);
     }
   }
+  trace_end(step_trace, tslot);
 }
 
 int launch_lm_head_rescore(const float* h, long h_row_stride, const float* lnw, const float* lnb, const float* wte_f32, const float* wte_norm_max,
                            float* part_val, int* part_idx, const float* part_val2, int n_parts, int part_ld, int block_n, int rows, int V, int d,
-                           int* stats, cudaStream_t st) {
+                           int* stats, cudaStream_t st, const int* row_map) {
   GIC_REQUIRE(d % 4 == 0 && d <= 4096 && n_parts >= 1 && part_ld >= n_parts, "lm_head_rescore: bad sizes d=%d n_parts=%d part_ld=%d", d, n_parts, part_ld);
   GIC_CHECK_CUDA(launch_kernel(lm_head_rescore_kernel, dim3(rows), dim3(RESCORE_THREADS), (size_t)d * sizeof(float), st, h, h_row_stride, lnw, lnb, wte_f32,
-                               wte_norm_max, part_val, part_idx, part_val2, n_parts, part_ld, block_n, V, d, stats));
+                               wte_norm_max, part_val, part_idx, part_val2, n_parts, part_ld, block_n, V, d, stats, row_map, trace_desc()));
   note_launch();
   return GIC_OK;
 }
@@ -354,37 +358,43 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
   __shared__ float sv[4];
   __shared__ int si[4];
   __shared__ int s_tok;
-  const int b = blockIdx.x;
+  const int b = blockIdx.x;  // activation slot; its caption is row `orig` of the call (compacted batches: row_map, -1 = padding slot)
   pdl_launch_dependents();
   pdl_wait();
   const int tslot = trace_begin(a.step_trace, TRACE_FINALIZE, 0);
   const int step = __ldcg(a.d_step);
+  const int orig = a.row_map ? __ldcg(a.row_map + b) : b;
+  const bool dead = orig < 0;  // block-uniform
   float v = -INFINITY;
   int idx = 0x7fffffff;
-  for (int p = threadIdx.x; p < a.n_parts; p += blockDim.x) {
+  for (int p = threadIdx.x; p < (dead ? 0 : a.n_parts); p += blockDim.x) {
     const float pv = __ldcg(a.part_val + (size_t)b * a.part_ld + p);
     const int pi = __ldcg(a.part_idx + (size_t)b * a.part_ld + p);
     if (better(pv, pi, v, idx)) { v = pv; idx = pi; }
   }
   block_argmax(v, idx, sv, si);
   if (threadIdx.x == 0) {
-    int tok = idx;
-    unsigned char fin = a.finished[b];
-    if (tok == a.eos && !fin) {  // src/models.py:453-455
-      fin = 1;
-      a.finished[b] = 1;
-      a.first_eos[b] = step;
+    int tok = a.eos;
+    unsigned char fin = 1;
+    if (!dead) {
+      tok = idx;
+      fin = a.finished[orig];
+      if (tok == a.eos && !fin) {  // src/models.py:453-455
+        fin = 1;
+        a.finished[orig] = 1;
+        a.first_eos[orig] = step;
+      }
+      if (fin) tok = a.eos;  // :458-460
+      a.ids_out[(size_t)orig * a.max_new + step] = (int64_t)tok;
     }
-    if (fin) tok = a.eos;  // :458-460
-    a.ids_out[(size_t)b * a.max_new + step] = (int64_t)tok;
     s_tok = tok;
-    if (fin && a.fin_counter) atomicAdd(a.fin_counter, 1);  // rows finished after this step (for the host's early exit)
+    if (fin && a.fin_counter) atomicAdd(a.fin_counter, 1);  // slots finished after this step (for the host's early exit / compaction)
   }
   __syncthreads();
   const int tok = s_tok;
   const int pos = a.P + step;  // position of this token when it is fed back
   float ssum = 0.f, ssq = 0.f;
-  if (pos < a.n_pos) {
+  if (pos < a.n_pos && !dead) {
     const float* pe = a.wpe + (size_t)pos * a.d;
     float* hn = a.h_next + (size_t)b * a.d;
     if (a.wte_bf16 && a.d % 8 == 0) {
@@ -449,6 +459,7 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
       if (a.fin_counter) {  // every row has emitted EOS: the reference loop would stop before the next step (src/models.py:390-391)
         const int nf = atomicExch(a.fin_counter, 0);
         if (nf == (int)gridDim.x) *a.all_done = 1;
+        if (a.live_rows) *a.live_rows = (int)gridDim.x - nf;  // unfinished rows: the host shrinks the batch to them (compact_rows_kernel)
       }
     }
   }
@@ -487,6 +498,80 @@ int launch_init_decode_state(unsigned char* finished, int* first_eos, int B, int
                                                              eos);
   GIC_CHECK_CUDA(cudaGetLastError());
   note_launch();
+  return GIC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Compaction of finished rows: the reference finishes rows individually (src/models.py:453-460) and trained
+// models stop at 10-20 of max_length = 50 tokens, so a batch soon carries mostly EOS-emitting rows.  Between two chunks of decode steps
+// the live rows' per-step state (next-step input h, its bf16 / hi + lo copy, its LayerNorm statistics) is packed to the front; the KV
+// cache does NOT move: slot i keeps attending cache row row_map[i].  compact_plan_kernel (one block) builds the new map with a stable
+// scan over the old slots, compact_move_kernel gathers the state through a scratch copy (slots only move down, but blocks run in
+// any order).  Slots [live, m_new) are padding (-1): their GEMM rows compute garbage that nothing reads.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) compact_plan_kernel(const unsigned char* __restrict__ finished, const int* row_map_old, int m_old, int m_new,
+                                                            int* row_map_new, int* src_slot /* [m_new]: old slot of new slot i, -1 = padding */) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (t == 0) s_base = 0;
+  __syncthreads();
+  for (int c0 = 0; c0 < m_old; c0 += 1024) {
+    const int i = c0 + t;
+    int orig = -1;
+    if (i < m_old) orig = row_map_old ? row_map_old[i] : i;
+    const int live = (orig >= 0 && !finished[orig]) ? 1 : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, live);
+    const int within = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (live) {
+      const int dst = before + within;  // (dst < m_new: the host sized m_new from a live count that can only have fallen since)
+      if (dst < m_new) { row_map_new[dst] = orig; src_slot[dst] = i; }
+    }
+    __syncthreads();
+    if (t == 0) { int tot = 0; for (int w = 0; w < 32; ++w) tot += s_warp[w]; s_base += tot; }
+    __syncthreads();
+  }
+  for (int i = s_base + t; i < m_new; i += 1024) { row_map_new[i] = -1; src_slot[i] = -1; }
+}
+
+// phase 0: scratch[i] = state[src_slot[i]]; phase 1: state[i] = scratch[i]   (one block per new slot)
+__global__ void __launch_bounds__(128) compact_move_kernel(const int* __restrict__ src_slot, int phase, int d, float* h, float* h_tmp, bf16* a_hi, bf16* a_hi_tmp,
+                                                           bf16* a_lo, bf16* a_lo_tmp, float2* stats, float2* stats_tmp) {
+  const int i = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int src = phase == 0 ? src_slot[i] : i;
+  if (src_slot[i] < 0) return;
+  float* hd = phase == 0 ? h_tmp : h; const float* hs = phase == 0 ? h : h_tmp;
+  for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) *reinterpret_cast<float4*>(hd + (size_t)i * d + c) = *reinterpret_cast<const float4*>(hs + (size_t)src * d + c);
+  if (a_hi) {
+    bf16* ad = phase == 0 ? a_hi_tmp : a_hi; const bf16* as = phase == 0 ? a_hi : a_hi_tmp;
+    for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8) *reinterpret_cast<uint4*>(ad + (size_t)i * d + c) = *reinterpret_cast<const uint4*>(as + (size_t)src * d + c);
+  }
+  if (a_lo) {
+    bf16* ad = phase == 0 ? a_lo_tmp : a_lo; const bf16* as = phase == 0 ? a_lo : a_lo_tmp;
+    for (int c = threadIdx.x * 8; c < d; c += blockDim.x * 8) *reinterpret_cast<uint4*>(ad + (size_t)i * d + c) = *reinterpret_cast<const uint4*>(as + (size_t)src * d + c);
+  }
+  if (stats && threadIdx.x == 0) {
+    if (phase == 0) stats_tmp[i] = stats[src]; else stats[i] = stats_tmp[i];
+  }
+}
+
+int launch_compact_rows(const CompactArgs& c, cudaStream_t st) {
+  GIC_REQUIRE(c.m_new > 0 && c.m_new <= c.m_old && c.d % 8 == 0, "compact_rows: bad sizes m_old=%d m_new=%d d=%d", c.m_old, c.m_new, c.d);
+  GIC_CHECK_CUDA(launch_kernel(compact_plan_kernel, dim3(1), dim3(1024), 0, st, c.finished, c.row_map_old, c.m_old, c.m_new, c.row_map_new, c.src_slot));
+  note_launch();
+  for (int phase = 0; phase < 2; ++phase) {
+    GIC_CHECK_CUDA(launch_kernel(compact_move_kernel, dim3(c.m_new), dim3(128), 0, st, (const int*)c.src_slot, phase, c.d, c.h, c.h_tmp, c.a_hi, c.a_hi_tmp, c.a_lo,
+                                 c.a_lo_tmp, c.stats, c.stats_tmp));
+    note_launch();
+  }
   return GIC_OK;
 }
 

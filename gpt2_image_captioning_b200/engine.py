@@ -153,6 +153,10 @@ class CaptionEngine:
     def launch_count() -> int:
         return int(_capi.lib().gic_launch_count())
 
+    @staticmethod
+    def compaction_count() -> int:
+        return int(_capi.lib().gic_compaction_count())
+
     def close(self) -> None:
         for child in self.__dict__.pop("_children", []):  # contexts borrowing these weights go first
             child.close()

@@ -135,7 +135,10 @@ GIC_API int gic_mapper_forward(gic_engine* e, const float* image_embeddings /* d
  * (ties -> lowest index), EOS rows keep emitting EOS (:453-460).  Always writes the full
  * ids_out dev int64 [B, max_new_tokens]; *gen_len_out (dev int32, may be NULL) receives L_gen of
  * :390-391 (the caller slices [:, :L_gen]).  logits_out (dev fp32 [max_new_tokens, B, V], may be NULL)
- * receives every step's last-position logits -- a parity/debug tap, not used by the product path. */
+ * receives every step's last-position logits -- a parity/debug tap, not used by the product path.
+ * Rows finish individually (:453-460): between chunks of 4 decode steps the call stops once every row has emitted EOS (:390-391) and
+ * shrinks the batch to its unfinished rows when at least a quarter of the slots can be dropped (GIC_NO_COMPACT=1 / GIC_NO_EARLY_EXIT=1
+ * turn these off; the tokens do not depend on them). */
 GIC_API int gic_generate_greedy(gic_engine* e, const float* image_embeddings /* dev [B,E] */, int batch, int max_new_tokens,
                         int64_t* ids_out, int32_t* gen_len_out, float* logits_out,
                         void* workspace, size_t workspace_bytes, void* stream);
@@ -207,6 +210,9 @@ GIC_API int gic_gather_attention_add(const float* queries, const float* cap_db, 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------------------ */
 /* kernels launched by this library in this process so far (CUDA-graph replays count their kernel nodes) */
 GIC_API unsigned long long gic_launch_count(void);
+/* finished-row compactions performed by gic_generate_greedy in this process so far (a batch whose rows emit EOS at different steps is
+ * shrunk to its live rows between chunks of decode steps; the KV cache stays in place behind a slot -> row map) */
+GIC_API unsigned long long gic_compaction_count(void);
 /* while enabled, generate calls run without the CUDA graph and bracket every kernel class with CUDA events on the
  * launch stream; gic_profile_read synchronises and returns per-class launch counts and summed device time.
  * A "class" spans one logical op (e.g. "attn_decode", "gemm_qkv", "lm_head", "layernorm", "prefill_gemm"). */

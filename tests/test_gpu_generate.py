@@ -421,3 +421,29 @@ def test_rat_generate_end_to_end_and_in_flight():
     assert all(p.device.type == "cpu" and torch.equal(p, s) for p, s in zip(par, seq))
     assert torch.equal(torch.cat(seq), got.cpu())
     assert sorted(store.image_index._ws) == [0, 1]
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16x2", "bf16"])
+@pytest.mark.parametrize("rows", [300, 1100])
+def test_finished_row_compaction_is_token_exact(monkeypatch, dtype, rows):
+    """Rows finish individually (src/models.py:453-460).  Between chunks of decode steps the engine shrinks the batch to its unfinished
+    rows (state packed to the front, KV cache read through a slot -> row map): same tokens and L_gen as decoding every row to the end
+    (GIC_NO_COMPACT=1), and in fp32 the oracle's tokens."""
+    from gpt2_image_captioning_b200 import CaptionEngine
+    g = gu.load("tiny_mlp_eos")
+    model, oracle, x = gpu_util.product_model(g, dtype)
+    pool = oc.synthetic_embeddings(rows, int(x.shape[1]), seed=15)
+    n0 = CaptionEngine.compaction_count()
+    a = model.generate(image_embeddings=pool.to(DEV), max_length=40, temperature=0.0).cpu()
+    n1 = CaptionEngine.compaction_count()
+    assert n1 > n0, "the EOS fixture finishes rows at different steps: the batch should have been compacted"
+    monkeypatch.setenv("GIC_NO_COMPACT", "1")
+    model2, _, _ = gpu_util.product_model(g, dtype)
+    b = model2.generate(image_embeddings=pool.to(DEV), max_length=40, temperature=0.0).cpu()
+    assert CaptionEngine.compaction_count() == n1
+    assert a.shape == b.shape and torch.equal(a, b)
+    if dtype == "fp32":
+        want = oracle.generate(pool[:64], 40, kv_cache=True)
+        L = min(a.shape[1], want.shape[1])
+        eos = int(g.get("eos", oc.EOS_TOKEN_ID))
+        assert torch.equal(a[:64, :L], want[:, :L]) and bool((want[:, L:] == eos).all())

@@ -42,7 +42,7 @@ torch.cuda.synchronize()
 _capi.check(L.gic_trace_install(None, 0))
 rec = buf.cpu()
 rec = rec[rec[:, 2] > 0]
-kinds = {1: "gemm", 2: "attn_decode", 3: "layernorm", 4: "finalize", 5: "attn_prefill"}
+kinds = {1: "gemm", 2: "attn_decode", 3: "layernorm", 4: "finalize", 5: "attn_prefill", 6: "lm_head_rescore"}
 rows = sorted(((int(r[1]), int(r[2]), int(r[0]) & 0xFF, int(r[0]) >> 8) for r in rec if int(r[2]) > 0), key=lambda t: t[0])
 # decode steps are delimited by finalize records; step 0 = prefill + first token
 fins = [i for i, r in enumerate(rows) if r[2] == 4]
