@@ -68,7 +68,10 @@ struct Workspace {
   float* logits = nullptr;         // [rows, V] fp32 (F32 mode)
   float* part_val = nullptr; int* part_idx = nullptr; int n_parts_max = 0;  // [rows][n_parts_max]
   float* part_val2 = nullptr;      // [rows][n_parts_max] runner-up value per slot (bf16x2 engine: exactly re-scored head)
-  int* rescore_stats = nullptr;    // [2] candidates re-scored / rows with more than 8 candidates, summed over the call (diagnostic)
+  // ... and the re-scoring state: ln_f(h) in fp32, the (row, column) candidate list, its counters {pairs, flagged rows}, the rows that did
+  // not fit the list, and the packed (value, ~column) result per row
+  float* rs_a = nullptr; int2* rs_pairs = nullptr; int rs_pair_cap = 0; int* rs_counters = nullptr; int* rs_row_flag = nullptr; int* rs_flag_rows = nullptr;
+  unsigned long long* rs_best = nullptr;
   float* splitk_ws = nullptr; size_t splitk_ws_floats = 0; int* splitk_counters = nullptr;  // split-K partials / per-tile arrival counters
   float2* ln_stats = nullptr; int ln_parts_max = 0;  // [ln_parts_max][m_max] row (sum, sum of squares) partials (folded LayerNorm)
   int64_t* ids = nullptr;          // [rows, max_new]
@@ -91,6 +94,9 @@ struct Workspace {
 
 using namespace gic;
 
+static const int kNumHeadTiles = 5;
+static const int kHeadTiles[kNumHeadTiles] = {32, 64, 128, 192, 256};
+
 struct gic_engine {
   gic_config cfg;
   int d = 0, L = 0, H = 0, V = 0, P_img = 0, P_task = 0, E = 0;
@@ -103,7 +109,8 @@ struct gic_engine {
                          // row statistics and column sums for each of its ~10 tiles per CTA and costs 79 us against 3.8 + 55 us
   bool rescore_head = false;  // BF16X2 greedy: the LM head runs with single bf16 operands (1 MMA per product) and the candidates within the rounding
                               // margin of its maximum are re-scored exactly in fp32 (lm_head_rescore_kernel).  GIC_X2_HEAD_FULL=1: the 3-MMA head
-  float* wte_norm_max = nullptr;  // device scalar: max_n |wte[n]|_2 (the margin's weight-norm bound)
+  float* wte_norm = nullptr;  // [V] |wte[n]|_2: the per-column error bound of the single-MMA head
+  float* slot_norm_max[kNumHeadTiles] = {};  // per LM-head tile width (kHeadTiles): the largest norm inside each (tile, column-parity) slot
   bf16* wte_gather = nullptr;  // BF16: unfolded bf16 embedding table for the next-token gather
   bool tc = false;     // tensor-core modes (BF16 / BF16X2)
   std::vector<void*> allocs;
@@ -326,16 +333,21 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
     w->ln_parts_max = ceil_div(d, 32);
     w->ln_stats = c.take<float2>((size_t)w->ln_parts_max * m);
   }
-  if (e->tc && !e->split) {  // split-K may be used by the decode-size residual GEMMs (few tiles, K up to 4 d)
+  if (e->tc && e->fuse_ln) {  // split-K may be used by the decode-size residual GEMMs (few tiles, K up to 4 d)
     w->splitk_ws_floats = (size_t)4 * w->rows * d;
     w->splitk_ws = c.take<float>(w->splitk_ws_floats);
     w->splitk_counters = c.take<int>(4096);
   }
   w->part_val = c.take<float>((size_t)w->n_parts_max * w->rows);
   w->part_idx = c.take<int>((size_t)w->n_parts_max * w->rows);
-  if (e->rescore_head) {
+  if (e->rescore_head && w->beams == 1) {
     w->part_val2 = c.take<float>((size_t)w->n_parts_max * w->rows);
-    w->rescore_stats = c.take<int>(2);
+    w->rs_a = c.take<float>((size_t)w->rows * d);
+    w->rs_pair_cap = w->rows * 64;
+    w->rs_pairs = c.take<int2>((size_t)w->rs_pair_cap);
+    w->rs_counters = c.take<int>(2);
+    w->rs_row_flag = c.take<int>(w->rows); w->rs_flag_rows = c.take<int>(w->rows);
+    w->rs_best = c.take<unsigned long long>(w->rows);
   }
   w->ids = c.take<int64_t>((size_t)w->rows * (max_new > 0 ? max_new : 1));
   w->finished = c.take<unsigned char>(w->rows);
@@ -504,6 +516,7 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
   const int d = e->d;
   const float* h = h_buf + first_off;
   int n_parts = 0;
+  bool packed = false;  // the token arrives as w.rs_best (exactly re-scored head) instead of argmax partials
   if (e->fuse_ln && e->fuse_lnf) {
     // rows of bf16(h) in w.a at the same (stride, offset) as h in its buffer; statistics indexed by the body row
     const long off = first_off;
@@ -515,7 +528,7 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
     GIC_TRY(linear(e, e->lm_head, a, rows, EPI_NONE, o, e->V, st, w.part_val, w.part_idx, &n_parts, w.n_parts_max, &in));
   } else {
     { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, row_stride, e->lnf.w, e->lnf.b, w.a.out(), rows, d, st)); }
-    if (e->rescore_head && !logits_tap) {
+    if (e->rescore_head && !logits_tap && w.rs_best) {
       // single-MMA head on the hi halves + exact re-scoring of the near-maximal candidates (lmhead.cu)
       GemmBf16Args g;
       int bn = 0, pair = 0;
@@ -528,9 +541,19 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
       g.part_val = w.part_val; g.part_idx = w.part_idx; g.part_val2 = w.part_val2; g.part_ld = w.n_parts_max;
       n_parts = 2 * ceil_div(e->V, bn);
       { ProfScope ps(e, "lm_head", st); GIC_TRY(launch_gemm_bf16(g, st)); }
-      { ProfScope ps(e, "lm_head_rescore", st);
-        GIC_TRY(launch_lm_head_rescore(h, row_stride, e->lnf.w, e->lnf.b, e->wte_f32, e->wte_norm_max, w.part_val, w.part_idx, w.part_val2, n_parts,
-                                       w.n_parts_max, bn, rows, e->V, d, w.rescore_stats, st, w.row_map)); }
+      int ti = -1;
+      for (int i = 0; i < kNumHeadTiles; ++i) if (kHeadTiles[i] == bn) ti = i;
+      GIC_REQUIRE(ti >= 0, "no slot norms for LM-head tile width %d", bn);
+      RescoreArgs ra;
+      ra.h = h; ra.h_row_stride = row_stride; ra.lnw = e->lnf.w; ra.lnb = e->lnf.b;
+      ra.wte = e->wte_f32; ra.wte_norm = e->wte_norm; ra.slot_norm_max = e->slot_norm_max[ti];
+      ra.part_val = w.part_val; ra.part_idx = w.part_idx; ra.part_val2 = w.part_val2; ra.n_parts = n_parts; ra.part_ld = w.n_parts_max; ra.block_n = bn;
+      ra.rows = rows; ra.V = e->V; ra.d = d;
+      ra.a_f32 = w.rs_a; ra.pairs = w.rs_pairs; ra.pair_cap = w.rs_pair_cap; ra.row_budget = 1024;
+      ra.pair_count = w.rs_counters; ra.flag_count = w.rs_counters + 1; ra.row_flag = w.rs_row_flag; ra.flag_rows = w.rs_flag_rows;
+      ra.best = w.rs_best; ra.row_map = w.row_map; ra.step_trace = StepTrace{nullptr, 0, 0};
+      { ProfScope ps(e, "lm_head_rescore", st); GIC_TRY(launch_lm_head_rescore(ra, st)); }
+      packed = true;
       n_parts = 1;
     } else if (!e->tc) {
       float* lg = logits_tap ? logits_tap : w.logits;
@@ -560,6 +583,7 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
   fa.finished = w.finished; fa.first_eos = w.first_eos; fa.ids_out = w.ids; fa.row_map = w.row_map; fa.live_rows = w.live_rows;
   fa.wte_f32 = e->wte_f32; fa.wte_bf16 = e->wte_f32 ? nullptr : e->wte_gather;
   fa.wpe = e->wpe; fa.h_next = w.h_dec;
+  if (packed) { fa.packed_best = w.rs_best; fa.rescore_counters = w.rs_counters; fa.n_parts = 0; }
   fa.hb_next = e->fuse_ln ? w.a.hi : nullptr; fa.hb_next_lo = e->fuse_ln ? w.a.lo : nullptr; fa.stats_next = e->fuse_ln ? w.ln_stats : nullptr;
   return launch_finalize_token(fa, st);
 }
@@ -591,6 +615,7 @@ static Workspace slice_rows(const gic_engine* e, const Workspace& w, int row0, i
   s.part_val += (size_t)w.n_parts_max * row0;
   s.part_idx += (size_t)w.n_parts_max * row0;
   if (s.part_val2) s.part_val2 += (size_t)w.n_parts_max * row0;
+  s.rs_best = nullptr;  // row groups share one candidate list: they take the 3-MMA head instead of the re-scored one
   s.ids += (size_t)row0 * w.max_new;
   s.finished += row0; s.first_eos += row0;
   s.d_step += sub; s.d_pos += sub; s.done_counter += sub; s.fin_counter += sub; s.all_done += sub; s.live_rows += sub;
@@ -769,7 +794,9 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
     e->fuse_ln = e->tc && !(nf && nf[0] == '1');  // GIC_NO_LNFUSE=1: LayerNorm as its own kernel; BF16X2 then also keeps fp32 q | k | v and cache
     e->beam_indirect = e->fuse_ln && gic::attn_decode_indirect_available();
     const char* sk = getenv("GIC_SPLITK");
-    e->use_splitk = sk && sk[0] == '1';
+    // bf16x2: on by default -- fc2's 48 k-blocks of three MMAs each run 22 us on 96 CTAs, a 3-way K split over 144 CTAs with wide tiles
+    // is the better shape there (GIC_SPLITK=0 turns it off); bf16: off unless GIC_SPLITK=1 (measured slower, see use_splitk)
+    e->use_splitk = e->split ? !(sk && sk[0] == '0') : (sk && sk[0] == '1');
     const char* hf = getenv("GIC_LNF_FUSE");
     e->fuse_lnf = e->fuse_ln && !e->split && hf && hf[0] == '1';
     const char* xh = getenv("GIC_X2_HEAD_FULL");
@@ -851,8 +878,12 @@ int gic_engine_load_gpt2(gic_engine* e, const gic_gpt2_weights* w, void* stream)
   if (e->cfg.dtype == GIC_DTYPE_F32) e->wte_f32 = e->lm_head.w_f32;
   else if (e->cfg.dtype == GIC_DTYPE_BF16X2) GIC_TRY(copy_vec(e, &e->wte_f32, w->wte, (size_t)e->V * d, st));
   if (e->rescore_head) {
-    GIC_TRY(dev_alloc(e, (void**)&e->wte_norm_max, sizeof(float)));
-    GIC_TRY(launch_row_norm_max(e->wte_f32, e->V, d, e->wte_norm_max, st));
+    GIC_TRY(dev_alloc(e, (void**)&e->wte_norm, (size_t)e->V * sizeof(float)));
+    GIC_TRY(launch_row_norms(e->wte_f32, e->V, d, e->wte_norm, st));
+    for (int i = 0; i < kNumHeadTiles; ++i) {
+      GIC_TRY(dev_alloc(e, (void**)&e->slot_norm_max[i], (size_t)2 * ceil_div(e->V, kHeadTiles[i]) * sizeof(float)));
+      GIC_TRY(launch_slot_norm_max(e->wte_norm, e->V, kHeadTiles[i], e->slot_norm_max[i], st));
+    }
   }
   GIC_TRY(copy_vec(e, &e->wpe, w->wpe, (size_t)e->cfg.n_positions * d, st));
   GIC_TRY(copy_norm(e, &e->lnf, w->lnf_w, w->lnf_b, d, st));
@@ -959,7 +990,7 @@ static int generate_greedy_on_stream(gic_engine* e, const float* x, int max_new,
   GIC_TRY(launch_init_decode_state(w.finished, w.first_eos, B, max_new, w.d_step, w.d_pos, w.done_counter, P, w.fin_counter, w.all_done, w.ids,
                                    e->cfg.eos_token_id, st));
   if (w.splitk_counters) GIC_CHECK_CUDA(cudaMemsetAsync(w.splitk_counters, 0, 4096 * sizeof(int), st));
-  if (w.rescore_stats) GIC_CHECK_CUDA(cudaMemsetAsync(w.rescore_stats, 0, 2 * sizeof(int), st));
+  if (w.rs_counters) GIC_CHECK_CUDA(cudaMemsetAsync(w.rs_counters, 0, 2 * sizeof(int), st));
   if (e->profiling) GIC_TRY(launch_spin(150000000LL, st));  // ~75 ms: lets the host queue ahead so events time the device only
   { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
   GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));

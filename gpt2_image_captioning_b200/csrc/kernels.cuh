@@ -141,13 +141,28 @@ struct FinalizeArgs {
   float2* stats_next;       // ... and [B] (sum, sum of squares) of that copy
   const int* row_map = nullptr;  // compacted batch: caption row of activation slot b (-1 = padding slot); null = identity
   int* live_rows = nullptr;      // optional device scalar: unfinished rows after this step
+  const unsigned long long* packed_best = nullptr;  // exactly re-scored head: the row's token as a packed (value, ~column) key instead of partials
+  int* rescore_counters = nullptr;  // ... and its two list counters, reset for the next step
 };
 int launch_finalize_token(const FinalizeArgs& a, cudaStream_t st);
-// exact greedy token from the single-MMA bf16 head's per-slot (best, column, runner-up) partials: candidates within the rounding margin of
-// the approximate maximum are re-scored in fp32 against ln_f(h) . wte_f32 (see lmhead.cu); result -> partial 0 of each row
-int launch_lm_head_rescore(const float* h, long h_row_stride, const float* lnw, const float* lnb, const float* wte_f32, const float* wte_norm_max,
-                           float* part_val, int* part_idx, const float* part_val2, int n_parts, int part_ld, int block_n, int rows, int V, int d,
-                           int* stats, cudaStream_t st, const int* row_map = nullptr);
+// exact greedy token from the single-MMA bf16 head's per-slot (best, column, runner-up) partials (lmhead.cu): candidates within the
+// rigorous rounding bound of the approximate maximum are listed as (row, column) pairs and re-scored in fp32 over the whole GPU
+struct RescoreArgs {
+  const float* h; long h_row_stride; const float* lnw; const float* lnb;  // residual rows and ln_f
+  const float* wte; const float* wte_norm; const float* slot_norm_max;     // fp32 table [V,d], its row norms [V], per-slot largest norm for this tiling
+  const float* part_val; const int* part_idx; const float* part_val2; int n_parts, part_ld, block_n;
+  int rows, V, d;
+  float* a_f32;                  // [rows, d] scratch: ln_f(h) in fp32
+  int2* pairs; int pair_cap; int row_budget;
+  int* pair_count; int* flag_count;  // device counters (adjacent ints: rescore_counters[0], [1]); zero before the first step, reset by finalize
+  int* row_flag; int* flag_rows;     // [rows] each; row_flag is cleared by ... the candidates kernel of the next step (see below)
+  unsigned long long* best;      // [rows] packed (value, ~column)
+  const int* row_map;            // compacted batches: padding slots are skipped
+  StepTrace step_trace;
+};
+int launch_lm_head_rescore(const RescoreArgs& r, cudaStream_t st);
+int launch_row_norms(const float* w, int N, int K, float* out, cudaStream_t st);
+int launch_slot_norm_max(const float* norms, int V, int block_n, float* out, cudaStream_t st);
 // finished-row compaction between decode chunks (lmhead.cu): packs the live rows' next-step state to the first m_new slots and writes
 // the new slot -> caption-row map; the KV cache stays where it is
 struct CompactArgs {
@@ -156,7 +171,6 @@ struct CompactArgs {
   float* h; float* h_tmp; bf16* a_hi; bf16* a_hi_tmp; bf16* a_lo; bf16* a_lo_tmp; float2* stats; float2* stats_tmp;
 };
 int launch_compact_rows(const CompactArgs& c, cudaStream_t st);
-int launch_row_norm_max(const float* w, int N, int K, float* out, cudaStream_t st);
 // temperature / top-p sampling of one token per row from fp32 logits [B, V] (src/models.py:400-449); the token goes to slot 0 of the
 // row's (value, index) partials.  step: *d_step unless step_override >= 0 (the Philox counter is (row, step)).
 int launch_sample_top_p(const float* logits, int B, int V, float temperature, float top_p, unsigned long long seed, const int* d_step,

@@ -211,36 +211,40 @@ int launch_sample_top_p(const float* logits, int B, int V, float temperature, fl
 
 // ---------------------------------------------------------------------------------------------------------------
 // Exact greedy token from an approximate LM head (bf16x2 engine).  The head runs ONCE on the tensor cores with single bf16
-// operands (a_hi . wte_hi, 1 MMA per product instead of 3) and its epilogue keeps, per (row, 64..128-column slot), the best
-// value, its column and the runner-up value.  Rounding both operands to bf16 moves a logit by at most
-//   delta = 2^-8 (1 + 2^-10) |a|_2 |wte_n|_2  (+ fp32 accumulation)  <=  DELTA_REL * |a|_2 * max_n |wte_n|_2,
-// so the true argmax is among the columns whose approximate logit is within 2 delta of the approximate maximum.  One block
-// per row recomputes ln_f(h) in fp32 (HF:models/gpt2/modeling_gpt2.py:628), collects those candidates -- the best column of
-// every slot within the margin, plus every column of a slot whose RUNNER-UP is within it -- and re-scores them with fp32
-// dot products against the fp32 embedding table (:705-706, tied head), lowest index on ties (torch.argmax, src/models.py:441).
-// The row's result is written as partial 0; finalize_token_kernel then runs with n_parts = 1.
+// operands (a_hi . wte_hi, 1 MMA per product instead of 3) and its epilogue keeps, per (row, slot of 32..128 columns), the best
+// value, its column and the runner-up value.  Rounding both operands to bf16 moves logit n by at most
+//   err_n <= 2^-8 (1 + 2^-10) sum_k |a_k w_nk| (+ fp32 accumulation)  <=  DELTA_REL |a|_2 |wte_n|_2        (Cauchy-Schwarz),
+// so with i* = the approximate argmax, the true argmax n satisfies  approx_n + err_n >= approx_i* - err_i*.  Per row:
+//   lm_head_candidates_kernel  recomputes a = ln_f(h) in fp32 (HF:models/gpt2/modeling_gpt2.py:628), finds i*, and walks the
+//       slots: a slot whose best value plus the slot's error bound (largest |wte_n| of its columns, precomputed per tiling)
+//       reaches the lower bound contributes its best column -- or all of its columns when its RUNNER-UP reaches it too -- to a
+//       global (row, column) list;
+//   lm_head_rescore_pairs_kernel  re-scores the listed pairs with fp32 dot products a . wte_f32[n] (:705-706, tied head), one warp
+//       per pair over the whole GPU (load-balanced: a row with a flat distribution does not become a straggler), and keeps the
+//       row's best in a packed (value, ~column) key: largest value, then LOWEST index (torch.argmax, src/models.py:441);
+//       rows whose candidates did not fit the list are scanned over all V columns by the whole grid.
+// finalize_token_kernel unpacks the key.  The bound is rigorous, so the token is the argmax of the fp32 logits of ln_f(h).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr float RESCORE_DELTA_REL = 0.00390625f * 1.02f;  // 2^-8 with 2 % slack for the 2^-18 cross term and the fp32 accumulation
 constexpr int RESCORE_THREADS = 128;
-constexpr int RESCORE_MAX_CAND = 256;  // candidate list in shared memory; more than this (pathologically flat rows) -> all slots are rescanned
 
-__global__ void __launch_bounds__(RESCORE_THREADS) lm_head_rescore_kernel(const float* h, long h_row_stride, const float* __restrict__ lnw,
-                                                                          const float* __restrict__ lnb, const float* __restrict__ wte,
-                                                                          const float* __restrict__ wte_norm_max, float* part_val, int* part_idx,
-                                                                          const float* part_val2, int n_parts, int part_ld, int block_n, int V, int d,
-                                                                          int* stats /* [2]: candidates re-scored, rows that rescanned slots */,
-                                                                          const int* row_map, StepTrace step_trace) {
+__device__ __forceinline__ unsigned long long pack_best(float v, int idx) {
+  unsigned int u = __float_as_uint(v);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // order-preserving map of fp32 onto unsigned
+  return ((unsigned long long)u << 32) | (unsigned int)(0x7fffffff - idx);
+}
+
+__global__ void __launch_bounds__(RESCORE_THREADS) lm_head_candidates_kernel(RescoreArgs r) {
   extern __shared__ float rs_a[];  // [d] ln_f(h) in fp32
   __shared__ float red[RESCORE_THREADS / 32];
-  __shared__ int s_cand[RESCORE_MAX_CAND];
-  __shared__ int s_ncand;
   __shared__ float s_bv[RESCORE_THREADS / 32];
   __shared__ int s_bi[RESCORE_THREADS / 32];
+  __shared__ int s_row_n;
   const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
   pdl_launch_dependents();
   pdl_wait();
-  if (row_map && __ldcg(row_map + b) < 0) return;  // padding slot of a compacted batch (its activations are garbage)
-  const int tslot = trace_begin(step_trace, TRACE_RESCORE, 0);
+  if (r.row_map && __ldcg(r.row_map + b) < 0) return;  // padding slot of a compacted batch (its activations are garbage)
+  const int tslot = trace_begin(r.step_trace, TRACE_RESCORE, 0);
   auto block_sum = [&](float v) {
     v = warp_sum(v);
     __syncthreads();
@@ -248,8 +252,9 @@ __global__ void __launch_bounds__(RESCORE_THREADS) lm_head_rescore_kernel(const 
     __syncthreads();
     return (red[0] + red[1]) + (red[2] + red[3]);
   };
-  // ---- ln_f(h) in fp32, two-pass like layernorm_kernel ----
-  const float* hr = h + (size_t)b * h_row_stride;
+  const int d = r.d;
+  // ---- ln_f(h) in fp32, two-pass like layernorm_kernel; kept in global memory for the pair kernel ----
+  const float* hr = r.h + (size_t)b * r.h_row_stride;
   float s = 0.f;
   for (int c = t; c < d; c += RESCORE_THREADS) { const float v = __ldcg(hr + c); rs_a[c] = v; s += v; }
   const float mean = block_sum(s) / (float)d;
@@ -257,97 +262,145 @@ __global__ void __launch_bounds__(RESCORE_THREADS) lm_head_rescore_kernel(const 
   for (int c = t; c < d; c += RESCORE_THREADS) { const float v = rs_a[c] - mean; q += v * v; }
   const float rstd = 1.0f / sqrtf(block_sum(q) / (float)d + 1e-5f);
   float n2 = 0.f;
+  float* ag = r.a_f32 + (size_t)b * d;
   for (int c = t; c < d; c += RESCORE_THREADS) {
-    const float v = (rs_a[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
-    rs_a[c] = v;
+    const float v = (rs_a[c] - mean) * rstd * __ldg(r.lnw + c) + __ldg(r.lnb + c);
+    ag[c] = v;
     n2 += v * v;
   }
-  const float a_norm = sqrtf(block_sum(n2));
-  const float margin = 2.0f * RESCORE_DELTA_REL * a_norm * __ldg(wte_norm_max);
-  // ---- approximate maximum over the row's slots ----
-  const float* pv = part_val + (size_t)b * part_ld;
-  const int* pi = part_idx + (size_t)b * part_ld;
-  const float* pv2 = part_val2 + (size_t)b * part_ld;
+  const float dn = RESCORE_DELTA_REL * sqrtf(block_sum(n2));  // error bound per unit of |wte_n|
+  // ---- approximate argmax over the row's slots ----
+  const float* pv = r.part_val + (size_t)b * r.part_ld;
+  const int* pi = r.part_idx + (size_t)b * r.part_ld;
+  const float* pv2 = r.part_val2 + (size_t)b * r.part_ld;
   float m = -INFINITY;
-  for (int p = t; p < n_parts; p += RESCORE_THREADS) m = fmaxf(m, __ldcg(pv + p));
-  m = warp_max(m);
-  __syncthreads();
-  if (lane == 0) red[warp] = m;
-  if (t == 0) s_ncand = 0;
-  __syncthreads();
-  m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-  const float thr = m - margin;
-  // ---- candidates: the best column of every slot within the margin; a slot whose runner-up is within it contributes all its columns ----
-  for (int p = t; p < n_parts; p += RESCORE_THREADS) {
-    if (__ldcg(pv + p) >= thr) {
-      if (__ldcg(pv2 + p) >= thr) {
-        const int n0 = (p >> 1) * block_n + (p & 1) * 32;
-        for (int c0 = n0; c0 < (p >> 1) * block_n + block_n; c0 += 64)
-          for (int c = c0; c < c0 + 32 && c < V; ++c) {
-            const int k = atomicAdd(&s_ncand, 1);
-            if (k < RESCORE_MAX_CAND) s_cand[k] = c;
-          }
-      } else {
-        const int k = atomicAdd(&s_ncand, 1);
-        if (k < RESCORE_MAX_CAND) s_cand[k] = __ldcg(pi + p);
-      }
+  int mi = 0x7fffffff;
+  for (int p = t; p < r.n_parts; p += RESCORE_THREADS) {
+    const float v = __ldcg(pv + p);
+    const int i = __ldcg(pi + p);
+    if (better(v, i, m, mi)) { m = v; mi = i; }
+  }
+  if (t == 0) { s_row_n = 0; r.row_flag[b] = 0; }
+  block_argmax(m, mi, s_bv, s_bi);
+  if (t == 0) r.best[b] = pack_best(-INFINITY, 0x7fffffff);
+  if (mi < 0 || mi >= r.V) return;  // (a row of NaNs: nothing to re-score; finalize sees the sentinel)
+  const float lb = m - dn * __ldg(r.wte_norm + mi);
+  // ---- candidates ----
+  const int block_n = r.block_n;
+  for (int p = t; p < r.n_parts; p += RESCORE_THREADS) {
+    const float e = dn * __ldg(r.slot_norm_max + p);
+    if (__ldcg(pv + p) + e < lb) continue;
+    const bool rescan = __ldcg(pv2 + p) + e >= lb;
+    const int n0 = (p >> 1) * block_n + (p & 1) * 32, n_end = min((p >> 1) * block_n + block_n, r.V);
+    int k = 1;
+    if (rescan) { k = 0; for (int c0 = n0; c0 < n_end; c0 += 64) k += max(0, min(32, n_end - c0)); }
+    const int mine = atomicAdd(&s_row_n, k);
+    const int base = (mine + k <= r.row_budget) ? atomicAdd(r.pair_count, k) : r.pair_cap;
+    if (base + k > r.pair_cap) {  // no room (pathologically flat row / full list): the whole row is scanned by the pair kernel
+      if (atomicExch(r.row_flag + b, 1) == 0) r.flag_rows[atomicAdd(r.flag_count, 1)] = b;
+      continue;
+    }
+    if (!rescan) r.pairs[base] = make_int2(b, __ldcg(pi + p));
+    else {
+      int o = base;
+      for (int c0 = n0; c0 < n_end; c0 += 64)
+        for (int c = c0; c < c0 + 32 && c < n_end; ++c) r.pairs[o++] = make_int2(b, c);
     }
   }
-  __syncthreads();
-  const int ncand_raw = s_ncand;
-  const bool overflow = ncand_raw > RESCORE_MAX_CAND;  // (block-uniform) pathologically flat row: every column within the margin is re-scored
-  const int ncand = overflow ? V : ncand_raw;
-  // ---- exact fp32 logits of the candidates: one warp per candidate, fixed summation order ----
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int k = warp; k < ncand; k += RESCORE_THREADS / 32) {
-    const int col = overflow ? k : s_cand[k];
-    const float* wr = wte + (size_t)col * d;
-    float acc = 0.f;
-    for (int c = lane * 4; c < d; c += 128) {
-      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + c));
-      acc = fmaf(rs_a[c], wv.x, acc); acc = fmaf(rs_a[c + 1], wv.y, acc); acc = fmaf(rs_a[c + 2], wv.z, acc); acc = fmaf(rs_a[c + 3], wv.w, acc);
-    }
-    acc = warp_sum(acc);
-    if (better(acc, col, bv, bi)) { bv = acc; bi = col; }
-  }
-  if (lane == 0) { s_bv[warp] = bv; s_bi[warp] = bi; }
-  __syncthreads();
-  if (t == 0) {
-    for (int w = 1; w < RESCORE_THREADS / 32; ++w)
-      if (better(s_bv[w], s_bi[w], bv, bi)) { bv = s_bv[w]; bi = s_bi[w]; }
-    part_val[(size_t)b * part_ld] = bv;
-    part_idx[(size_t)b * part_ld] = bi;
-    if (stats) {
-      atomicAdd(stats, ncand);
-      if (ncand > 8) atomicAdd(stats + 1, 1);
-    }
-  }
-  trace_end(step_trace, tslot);
+  trace_end(r.step_trace, tslot);
 }
 
-int launch_lm_head_rescore(const float* h, long h_row_stride, const float* lnw, const float* lnb, const float* wte_f32, const float* wte_norm_max,
-                           float* part_val, int* part_idx, const float* part_val2, int n_parts, int part_ld, int block_n, int rows, int V, int d,
-                           int* stats, cudaStream_t st, const int* row_map) {
-  GIC_REQUIRE(d % 4 == 0 && d <= 4096 && n_parts >= 1 && part_ld >= n_parts, "lm_head_rescore: bad sizes d=%d n_parts=%d part_ld=%d", d, n_parts, part_ld);
-  GIC_CHECK_CUDA(launch_kernel(lm_head_rescore_kernel, dim3(rows), dim3(RESCORE_THREADS), (size_t)d * sizeof(float), st, h, h_row_stride, lnw, lnb, wte_f32,
-                               wte_norm_max, part_val, part_idx, part_val2, n_parts, part_ld, block_n, V, d, stats, row_map, trace_desc()));
+// exact fp32 logit of (row, col): a[row] . wte[col], lanes over k with 128-bit loads, fixed summation order
+__device__ __forceinline__ float rescore_dot(const float* __restrict__ a, const float* __restrict__ w, int d, int lane) {
+  float acc = 0.f;
+  for (int c = lane * 4; c < d; c += 128) {
+    const float4 av = __ldcg(reinterpret_cast<const float4*>(a + c));
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(w + c));
+    acc = fmaf(av.x, wv.x, acc); acc = fmaf(av.y, wv.y, acc); acc = fmaf(av.z, wv.z, acc); acc = fmaf(av.w, wv.w, acc);
+  }
+  return warp_sum(acc);
+}
+
+__global__ void __launch_bounds__(RESCORE_THREADS) lm_head_rescore_pairs_kernel(RescoreArgs r) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * RESCORE_THREADS + threadIdx.x) >> 5, nw = (gridDim.x * RESCORE_THREADS) >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tslot = trace_begin(r.step_trace, TRACE_RESCORE, 1);
+  const int n = min(__ldcg(r.pair_count), r.pair_cap);
+  // two pairs per warp and iteration: their loads overlap
+  for (int i = gw; i < n; i += 2 * nw) {
+    const int2 p0 = __ldcg(r.pairs + i);
+    const bool two = i + nw < n;
+    const int2 p1 = two ? __ldcg(r.pairs + i + nw) : p0;
+    const float v0 = rescore_dot(r.a_f32 + (size_t)p0.x * r.d, r.wte + (size_t)p0.y * r.d, r.d, lane);
+    const float v1 = rescore_dot(r.a_f32 + (size_t)p1.x * r.d, r.wte + (size_t)p1.y * r.d, r.d, lane);
+    if (lane == 0) {
+      atomicMax(r.best + p0.x, pack_best(v0, p0.y));
+      if (two) atomicMax(r.best + p1.x, pack_best(v1, p1.y));
+    }
+  }
+  // rows that did not fit the list: every column, the whole grid
+  const int nf = __ldcg(r.flag_count);
+  for (int f = 0; f < nf; ++f) {
+    const int row = __ldcg(r.flag_rows + f);
+    unsigned long long bk = 0ull;
+    for (int col = gw; col < r.V; col += nw) {
+      const float v = rescore_dot(r.a_f32 + (size_t)row * r.d, r.wte + (size_t)col * r.d, r.d, lane);
+      const unsigned long long k = pack_best(v, col);
+      bk = k > bk ? k : bk;
+    }
+    if (lane == 0 && bk) atomicMax(r.best + row, bk);
+  }
+  trace_end(r.step_trace, tslot);
+}
+
+int launch_lm_head_rescore(const RescoreArgs& r0, cudaStream_t st) {
+  RescoreArgs r = r0;
+  GIC_REQUIRE(r.d % 4 == 0 && r.d <= 4096 && r.n_parts >= 1 && r.part_ld >= r.n_parts && r.rows > 0, "lm_head_rescore: bad sizes d=%d n_parts=%d part_ld=%d", r.d,
+              r.n_parts, r.part_ld);
+  r.step_trace = trace_desc();
+  GIC_CHECK_CUDA(launch_kernel(lm_head_candidates_kernel, dim3(r.rows), dim3(RESCORE_THREADS), (size_t)r.d * sizeof(float), st, r));
+  note_launch();
+  r.step_trace = trace_desc();
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  GIC_CHECK_CUDA(launch_kernel(lm_head_rescore_pairs_kernel, dim3(sms * 4), dim3(RESCORE_THREADS), 0, st, r));
   note_launch();
   return GIC_OK;
 }
 
-// max_n |W[n, :]|_2 of a row-major fp32 matrix (load time; the rescoring margin's weight-norm bound)
-__global__ void __launch_bounds__(128) row_norm_max_kernel(const float* __restrict__ w, int N, int K, float* out) {
+// per-row norms of the fp32 embedding table and, for one LM-head tiling, the largest norm inside each (tile, column-parity) slot
+__global__ void __launch_bounds__(128) row_norm_kernel(const float* __restrict__ w, int N, int K, float* __restrict__ out) {
   const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (n >= N) return;
   float s = 0.f;
   for (int k = lane; k < K; k += 32) { const float v = w[(size_t)n * K + k]; s += v * v; }
   s = warp_sum(s);
-  if (lane == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(s)));  // non-negative floats order like their bit patterns
+  if (lane == 0) out[n] = sqrtf(s);
 }
-int launch_row_norm_max(const float* w, int N, int K, float* out, cudaStream_t st) {
-  GIC_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
-  row_norm_max_kernel<<<ceil_div(N, 4), 128, 0, st>>>(w, N, K, out);
+__global__ void slot_norm_max_kernel(const float* __restrict__ norms, int V, int block_n, float* __restrict__ out, int n_slots) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_slots) return;
+  const int n0 = (p >> 1) * block_n + (p & 1) * 32, n_end = min((p >> 1) * block_n + block_n, V);
+  float m = 0.f;
+  for (int c0 = n0; c0 < n_end; c0 += 64)
+    for (int c = c0; c < c0 + 32 && c < n_end; ++c) m = fmaxf(m, norms[c]);
+  out[p] = m;
+}
+int launch_row_norms(const float* w, int N, int K, float* out, cudaStream_t st) {
+  row_norm_kernel<<<ceil_div(N, 4), 128, 0, st>>>(w, N, K, out);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return GIC_OK;
+}
+int launch_slot_norm_max(const float* norms, int V, int block_n, float* out, cudaStream_t st) {
+  const int n_slots = 2 * ceil_div(V, block_n);
+  slot_norm_max_kernel<<<ceil_div(n_slots, 128), 128, 0, st>>>(norms, V, block_n, out, n_slots);
   GIC_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return GIC_OK;
@@ -367,7 +420,12 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
   const bool dead = orig < 0;  // block-uniform
   float v = -INFINITY;
   int idx = 0x7fffffff;
-  for (int p = threadIdx.x; p < (dead ? 0 : a.n_parts); p += blockDim.x) {
+  if (a.packed_best && !dead && threadIdx.x == 0) {  // exactly re-scored head: the row's (value, ~column) key
+    const unsigned long long k = __ldcg(a.packed_best + b);
+    idx = 0x7fffffff - (int)(unsigned int)(k & 0xffffffffull);
+    v = 0.f;
+  }
+  for (int p = threadIdx.x; p < ((dead || a.packed_best) ? 0 : a.n_parts); p += blockDim.x) {
     const float pv = __ldcg(a.part_val + (size_t)b * a.part_ld + p);
     const int pi = __ldcg(a.part_idx + (size_t)b * a.part_ld + p);
     if (better(pv, pi, v, idx)) { v = pv; idx = pi; }
@@ -456,6 +514,7 @@ __global__ void __launch_bounds__(128) finalize_token_kernel(FinalizeArgs a) {
       *a.done_counter = 0;
       *a.d_pos = pos;
       *a.d_step = step + 1;
+      if (a.rescore_counters) { a.rescore_counters[0] = 0; a.rescore_counters[1] = 0; }  // pair / flagged-row lists of the next step start empty
       if (a.fin_counter) {  // every row has emitted EOS: the reference loop would stop before the next step (src/models.py:390-391)
         const int nf = atomicExch(a.fin_counter, 0);
         if (nf == (int)gridDim.x) *a.all_done = 1;

@@ -72,7 +72,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="c3,c4,c5")
     ap.add_argument("--batch", type=int, default=1024)
-    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--dtypes", default="bf16x2,bf16", help="arithmetic modes to time; every line carries the mode's parity entry (profiles/r2_parity.json)")
     ap.add_argument("--max-length", type=int, default=30)
     ap.add_argument("--in-flight", type=int, default=2, help="batches running concurrently (inflight.py); 1 = one at a time")
     a = ap.parse_args()
@@ -81,12 +81,21 @@ def main():
     torch.cuda.set_device(dev)
     B, N = a.batch, a.max_length
     want = a.configs.split(",")
+    par = bench.parity_table()
+    for dtype in a.dtypes.split(","):
+        run_dtype(a, dev, B, N, want, dtype, par.get(dtype, {}))
+
+
+def run_dtype(a, dev, B, N, want, dtype, par):
+    global IN_FLIGHT
+    a.dtype = dtype
     if "c3" in want:
         model = build(dict(n_embd=1024, n_layer=24, n_head=16), "tfm", 512, 40, a.dtype, dev, beams=5)
         x = bench.synthetic_pool(B, 512).to(dev)
         ms, ids = timed(lambda: model.generate(image_embeddings=x, max_length=N, temperature=0.0))
         print(json.dumps({"config": "c3: GPT-2 medium + 8-layer transformer mapper, prefix_len 40, beam 5 (ancestry-table KV)", "batch": B, "dtype": a.dtype, "in_flight": IN_FLIGHT,
-                          "ms_per_batch": ms, "captions_per_s": B / ms * 1e3, "ids_shape": list(ids.shape)}), flush=True)
+                          "ms_per_batch": ms, "captions_per_s": B / ms * 1e3, "ids_shape": list(ids.shape),
+                          "parity": {k: par.get(k) for k in ("c3_beam5_32_rows_vs_hf", "c3_medium_tfm_full32")}}), flush=True)
         del model
         torch.cuda.empty_cache()
     if "c4" in want:
@@ -94,7 +103,7 @@ def main():
         x = bench.synthetic_pool(B, 1024).to(dev)
         ms, ids = timed(lambda: model.generate(image_embeddings=x, max_length=N, temperature=0.0))
         print(json.dumps({"config": "c4: GPT-2 large + MLP mapper, 1024-d embeddings, greedy", "batch": B, "dtype": a.dtype, "in_flight": IN_FLIGHT, "ms_per_batch": ms,
-                          "captions_per_s": B / ms * 1e3, "ids_shape": list(ids.shape)}), flush=True)
+                          "captions_per_s": B / ms * 1e3, "ids_shape": list(ids.shape), "parity": {"c4_large_mlp_full16": par.get("c4_large_mlp_full16")}}), flush=True)
         del model
         torch.cuda.empty_cache()
     if "c5" in want:
@@ -117,7 +126,10 @@ def main():
         print(json.dumps({"config": "c5: RAT, top-5 over 118 287 images -> caption rows of 591 753 -> mean-add, GPT-2 small greedy", "batch": B,
                           "dtype": a.dtype, "in_flight": IN_FLIGHT, "ms_per_batch": ms, "captions_per_s": B / ms * 1e3, "retrieve_and_aggregate_ms": ms_r,
                           "top5_over_591753_rows_ms": ms_s, "top5_scan_TFLOPs": 2.0 * B * n_cap * 512 / ms_s * 1e-9,
-                          "ids_shape": list(ids.shape)}), flush=True)
+                          "ids_shape": list(ids.shape), "parity": {"c5_rat_256_rows_vs_fp32_engine": par.get("c5_rat_256_rows_vs_fp32_engine"),
+                                                                   "retrieval": bench.parity_table().get("retrieval")}}), flush=True)
+        del model, store
+        torch.cuda.empty_cache()
 
 
 if __name__ == "__main__":
