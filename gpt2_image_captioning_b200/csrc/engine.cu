@@ -794,9 +794,10 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
     e->fuse_ln = e->tc && !(nf && nf[0] == '1');  // GIC_NO_LNFUSE=1: LayerNorm as its own kernel; BF16X2 then also keeps fp32 q | k | v and cache
     e->beam_indirect = e->fuse_ln && gic::attn_decode_indirect_available();
     const char* sk = getenv("GIC_SPLITK");
-    // bf16x2: on by default -- fc2's 48 k-blocks of three MMAs each run 22 us on 96 CTAs, a 3-way K split over 144 CTAs with wide tiles
-    // is the better shape there (GIC_SPLITK=0 turns it off); bf16: off unless GIC_SPLITK=1 (measured slower, see use_splitk)
-    e->use_splitk = e->split ? !(sk && sk[0] == '0') : (sk && sk[0] == '1');
+    // off unless GIC_SPLITK=1 in both tensor-core modes: measured again in round 2 for bf16x2, whose fc2 main loop is 2.5x longer
+    // (profiles/r2f_splitk.txt): 29.2 us with the 3-way K split against 22.6 us unsplit -- the parked-partials reduction costs more than
+    // the shorter main loop saves
+    e->use_splitk = sk && sk[0] == '1';
     const char* hf = getenv("GIC_LNF_FUSE");
     e->fuse_lnf = e->fuse_ln && !e->split && hf && hf[0] == '1';
     const char* xh = getenv("GIC_X2_HEAD_FULL");
