@@ -3,6 +3,8 @@
 // finished |= (tok == eos); tok[finished] = eos -> append -> wte(tok) as the next input (+ wpe of its position,
 // HF:models/gpt2/modeling_gpt2.py:579-585).  Everything stays on the device: no per-step host sync
 // (the reference does `is_finished.all()` on the host every step, src/models.py:390).
+#include <atomic>
+
 #include "kernels.cuh"
 
 namespace gic {
@@ -198,10 +200,10 @@ int launch_sample_top_p(const float* logits, int B, int V, float temperature, fl
   GIC_REQUIRE(top_p > 0.f, "sample_top_p: top_p must be > 0");
   const size_t smem = (size_t)V * sizeof(float);
   GIC_REQUIRE(smem <= 200 * 1024, "sample_top_p: a row of %d probabilities does not fit in shared memory", V);
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<bool> configured{false};  // (engine contexts may be driven from several host threads)
+  if (!configured.load(std::memory_order_acquire)) {
     GIC_CHECK_CUDA(cudaFuncSetAttribute(sample_top_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+    configured.store(true, std::memory_order_release);
   }
   sample_top_p_kernel<<<B, SAMPLE_THREADS, smem, st>>>(logits, V, 1.0f / temperature, top_p, seed, d_step, step_override, part_val, part_idx, part_ld);
   GIC_CHECK_CUDA(cudaGetLastError());

@@ -16,6 +16,41 @@ def _f32(t: torch.Tensor, device) -> torch.Tensor:
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+def _check_supported(gcfg, mapping_network) -> None:
+    """The kernels implement exactly the arithmetic of the reference's models (HF GPT-2 defaults, HF:models/gpt2/configuration_gpt2.py;
+    nn.TransformerEncoderLayer as src/models.py:129-139 builds it).  Anything else would produce wrong tokens silently, so it is refused."""
+    bad = []
+    if getattr(gcfg, "activation_function", "gelu_new") != "gelu_new":
+        bad.append(f"activation_function={gcfg.activation_function!r} (kernels: gelu_new)")
+    if abs(float(getattr(gcfg, "layer_norm_epsilon", 1e-5)) - 1e-5) > 1e-12:
+        bad.append(f"layer_norm_epsilon={gcfg.layer_norm_epsilon} (kernels: 1e-5)")
+    if not getattr(gcfg, "scale_attn_weights", True):
+        bad.append("scale_attn_weights=False (kernels scale by 1/sqrt(head_dim))")
+    if getattr(gcfg, "scale_attn_by_inverse_layer_idx", False):
+        bad.append("scale_attn_by_inverse_layer_idx=True")
+    if getattr(gcfg, "reorder_and_upcast_attn", False):
+        bad.append("reorder_and_upcast_attn=True")
+    if getattr(gcfg, "add_cross_attention", False):
+        bad.append("add_cross_attention=True")
+    layers = getattr(getattr(mapping_network, "transformer", None), "layers", None)
+    if layers is not None:
+        for i, lyr in enumerate(layers):
+            if not getattr(lyr, "norm_first", False):
+                bad.append(f"mapper layer {i}: norm_first=False (kernels: pre-LN, src/models.py:135)")
+            act = getattr(lyr, "activation", None)
+            if act is not torch.nn.functional.relu and getattr(act, "__name__", "") != "relu" and not isinstance(act, torch.nn.ReLU):
+                bad.append(f"mapper layer {i}: activation {act!r} (kernels: relu)")
+            for nm in ("norm1", "norm2"):
+                if abs(float(getattr(lyr, nm).eps) - 1e-5) > 1e-12:
+                    bad.append(f"mapper layer {i}: {nm}.eps={getattr(lyr, nm).eps} (kernels: 1e-5)")
+            if not getattr(lyr.self_attn, "batch_first", True):
+                bad.append(f"mapper layer {i}: batch_first=False")
+        if getattr(mapping_network.transformer, "norm", None) is not None:
+            bad.append("mapper: final encoder norm (the reference has none)")
+    if bad:
+        raise NotImplementedError("the B200 engine does not implement this model variant: " + "; ".join(bad))
+
+
 class CaptionEngine:
     def __init__(self, gpt, mapping_network, eos_token_id: int, task_prefix_embeds: torch.Tensor | None = None,
                  dtype: str = "bf16", device: torch.device | str | None = None):
@@ -31,6 +66,7 @@ class CaptionEngine:
         self._handle = C.c_void_p()
         self._ws: torch.Tensor | None = None
         gcfg = gpt.config
+        _check_supported(gcfg, mapping_network)
         sd = {k: v for k, v in gpt.state_dict().items()}
         msd = {k: v for k, v in mapping_network.state_dict().items()}
         is_tfm = "prefix_const" in msd

@@ -9,7 +9,13 @@ identical.  Rows of different batches never interact, so this i
 `map_batches(fn, batches, in_flight)` runs `fn(batch)` for every batch, batch i on worker i % in_flight.  Each worker has a
 CUDA stream that first waits for the caller's current stream and that the caller's stream waits for at the end, so the call
 behaves like the sequential loop for whoever consumes the results (and can be bracketed by CUDA events on the caller's stream).
-Inside a worker `current_slot()` names its engine slot; `_EngineMixin._get_engine()` (models.py) keeps one engine per slot.
+Inside a worker `current_slot()` names its engine slot; `_EngineMixin._get_engine()` (models.py) keeps one engine CONTEXT per slot
+(slot 0 owns the packed weights, the others are contexts cloned from it: own stream, workspace, KV cache and CUDA graphs).
+
+Stream-ordering contract of `fn`'s results: a CUDA tensor returned by `fn` was allocated and written on the slot's stream.  The
+caller's stream waits for every slot stream before `map_batches` returns, and the results are handed to the caching allocator's
+bookkeeping with `record_stream(caller)`, so consuming or freeing them on the caller's stream afterwards is safe.  (Host tensors --
+what `generate_batches` and `evaluation.run` return -- need none of this.)
 """
 from __future__ import annotations
 
@@ -75,6 +81,10 @@ def map_batches(fn: Callable, batches: Sequence, in_flight: int = 2) -> list:
     if cuda:
         for s in streams:
             caller.wait_stream(s)
+        for r in out:  # results allocated on a slot stream are about to be used (and freed) on the caller's
+            for t in (r if isinstance(r, (tuple, list)) else (r,)):
+                if torch.is_tensor(t) and t.is_cuda:
+                    t.record_stream(caller)
     if errors:
         raise errors[0]
     return out

@@ -366,3 +366,60 @@ def test_max_length_up_to_the_position_table():
     assert out.shape[0] == 3 and out.shape[1] <= 13
     with pytest.raises(Exception):
         model.generate(image_embeddings=x, max_length=14, temperature=0.0)
+
+
+_SHARD_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+rank, world = int(sys.argv[1]), int(sys.argv[2])
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str({port}), RANK=str(rank), WORLD_SIZE=str(world))
+torch.cuda.set_device(rank)
+dist.init_process_group("gloo", rank=rank, world_size=world)  # the only communication of the path is the host gather of token ids
+from gpt2_image_captioning_b200 import ImageCaptioningModel, MLPMappingNetwork, generate_for_embeddings
+from oracle import captioner as oc
+from oracle.ref_harness import StubTokenizer
+spec = oc.ModelSpec(gpt="tiny", embed_dim=64, prefix_length=4)
+gpt, mapper_ref = oc.build_modules(spec)
+mapper = MLPMappingNetwork(prefix_length=4, embed_dim=64, gpt_dim=128)
+mapper.load_state_dict(mapper_ref.state_dict())
+model = ImageCaptioningModel(mapper, tokenizer=StubTokenizer(), gpt=gpt, engine_dtype={dtype!r}).to(f"cuda:{{rank}}")
+x = oc.synthetic_embeddings(1003, 64, 5)
+ids = generate_for_embeddings(model, x, batch_size=128, max_length=12, device=f"cuda:{{rank}}", in_flight=2)
+if rank == 0:
+    assert ids.shape == (1003, 12) and ids.device.type == "cpu"
+    dist.destroy_process_group()
+    alone = generate_for_embeddings(model, x, batch_size=128, max_length=12, device="cuda:0", in_flight=1)
+    assert torch.equal(ids, alone), "sharded + gathered ids differ from the 1-GPU ids"
+    if {dtype!r} == "fp32":
+        want = oc.CaptionOracle(spec, gpt.cpu(), mapper_ref).generate(x[500:540], 12, kv_cache=True)
+        assert torch.equal(ids[500:540, : want.shape[1]], want)
+    print("SHARDED_GPU_OK")
+else:
+    assert ids is None
+    dist.destroy_process_group()
+'''
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16x2"])
+def test_sharded_job_on_several_gpus(tmp_path, dtype):
+    """north_star: "images shard independently across the GPUs of one box (no NCCL on the hot path; only a final host gather of
+    captions)".  One process per GPU (up to 4), contiguous shards of 1003 rows, ragged batches, two batches in flight per GPU, ids
+    gathered over gloo on rank 0: equal to the 1-GPU result (and to the oracle in fp32).  Skips on a single-GPU box."""
+    import socket
+    import subprocess
+    import sys
+    n = min(4, torch.cuda.device_count())
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "shard_worker.py"
+    script.write_text(_SHARD_WORKER.format(root=root, port=port, dtype=dtype))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(n)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(n)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "SHARDED_GPU_OK" in outs[0]

@@ -35,7 +35,7 @@ def classify(name: str, grid: str, counters: dict) -> str:
         i = counters["gemm"] % 4 if counters["in_layers"] else -1
         counters["gemm"] += 1
         return ("gemm_qkv", "gemm_proj", "gemm_fc", "gemm_fc2")[i] if i >= 0 else "lm_head"
-    for key in ("attn_decode", "attn_seq", "layernorm", "finalize", "kv_reorder"):
+    for key in ("attn_decode", "attn_seq", "layernorm", "finalize", "kv_reorder", "lm_head_candidates", "lm_head_rescore_pairs"):
         if s.startswith(key):
             return key
     return s
@@ -133,7 +133,7 @@ def step_metrics(tag: str) -> None:
     for rec in recs:
         groups.setdefault(rec["class"], []).append(rec)
     tot = sum(r["dur_us"] for r in recs if isinstance(r["dur_us"], float))
-    out = [f"# {tag}: ncu --set full --clock-control none over one decode step (B=1024, GPT-2 small, bf16); means per kernel class.",
+    out = [f"# {tag}: ncu --set full --clock-control none over the last layer + head of one decode step (B=1024, GPT-2 small, {os.environ.get('DTYPE', 'bf16x2')}); means per kernel class.",
            "# dur = gpu__time_duration (cold-cache, serialised under the profiler: compare shares); dram = dram__bytes_read+write per launch;",
            "# l2_to_sm = l1tex__m_xbar2l1tex_read_bytes; pct columns are % of peak sustained over the kernel's elapsed time.",
            f"{'class':12s} {'n':>3s} {'dur_us':>8s} {'share':>6s} {'dram_MB':>9s} {'l2_to_sm_MB':>11s} {'dramGB/s':>8s} {'l2%':>6s} {'tensor%':>7s} {'sm%':>6s} {'regs':>5s} {'grid':>6s}"]
@@ -154,7 +154,15 @@ def step_metrics(tag: str) -> None:
     dst = os.path.join(ROOT, "profiles", f"{tag}_step_metrics.txt")
     open(dst, "w").write("\n".join(out) + "\n")
     print("wrote", dst)
-    json.dump({k: v for k, v in traffic.items()}, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
+    # bench.py's roofline.traffic: dram bytes per launch per class; "gemm_body" = mean over the four body GEMMs of a layer
+    body = [traffic[k] for k in ("gemm_qkv", "gemm_proj", "gemm_fc", "gemm_fc2") if k in traffic]
+    if body:
+        traffic["gemm_body"] = sum(body) / len(body)
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    old = json.load(open(tpath)) if os.path.isfile(tpath) else {}
+    dt = os.environ.get("DTYPE", "bf16x2")
+    old.update({f"{k}_{dt}": v for k, v in traffic.items()})
+    json.dump(old, open(tpath, "w"), indent=1, sort_keys=True)
     print("\n".join(out))
 
 
