@@ -795,6 +795,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
             o[i].w = epi_act<EPI>(o[i].w + b4.w, SPLIT);
             if (EPI == EPI_RESIDUAL) { o[i].x += res[i].x; o[i].y += res[i].y; o[i].z += res[i].z; o[i].w += res[i].w; }
           }
+          if (tr) trc[5] = clock64() - t_start + (long long)(o[7].w * 0.f);  // math done (residual / bias operands have arrived)
           // rows of this warp's band that exist: all 32 unless this is the ragged last row tile (warp-uniform count)
           const int rows_here = min(32, p.M - wrow0);
           if (EPI == EPI_ARGMAX) {
@@ -865,6 +866,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
               }
             }
           }
+          if (tr) trc[6] = clock64() - t_start;  // stores issued
         } else if (RAGGED) {
           // ---- generic path: ragged right edge (col0 + 32 > N) or unaligned leading dimensions ----
           const bool full4 = col + 3 < p.N;

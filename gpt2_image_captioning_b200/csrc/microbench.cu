@@ -289,6 +289,50 @@ int main(int argc, char** argv) {
     return 0;
   }
 
+  // ---- mode 7: CTA-0 clock64 timeline of the bf16x2 decode GEMMs in their engine configuration (tile / pair as the engine picks) ----
+  if (argc > 2 && atoi(argv[2]) == 7) {
+    long long* tr = (long long*)dmalloc(640 * 8);
+    bf16* a_lo = (bf16*)dmalloc((size_t)B * 4 * d * 2);
+    bf16* o_lo = (bf16*)dmalloc((size_t)B * 4 * d * 2);
+    bf16* wl = (bf16*)dmalloc((size_t)4 * d * d * 2);
+    float2* stats = (float2*)dmalloc((size_t)64 * B * 8);
+    float* colsum = (float*)dmalloc((size_t)V * 4);
+    struct Shape { const char* name; bf16* W; int N, K, epi; bool res; };
+    Shape shapes[] = {{"qkv", w_qkv[0], 3 * d, d, EPI_NONE, false}, {"proj", w_proj[0], d, d, EPI_RESIDUAL, true},
+                      {"fc", w_fc[0], 4 * d, d, EPI_GELU, false}, {"fc2", w_fc2[0], d, 4 * d, EPI_RESIDUAL, true}};
+    for (const Shape& sh : shapes) {
+      int bn = 0, pair = 0;
+      gemm_bf16_pick(B, sh.N, sh.K, 1, 1, &bn, &pair);
+      GemmBf16Args g;
+      OK(make_tma_2d_bf16(&g.a_hi, a, B, sh.K, sh.K, 128));
+      OK(make_tma_2d_bf16(&g.a_lo, a_lo, B, sh.K, sh.K, 128));
+      OK(make_tma_2d_bf16(&g.w_hi, sh.W, sh.N, sh.K, sh.K, pair ? bn / 2 : bn));
+      OK(make_tma_2d_bf16(&g.w_lo, wl, sh.N, sh.K, sh.K, pair ? bn / 2 : bn));
+      g.M = B; g.N = sh.N; g.K = sh.K; g.block_n = bn; g.split = 1; g.epilogue = sh.epi; g.bias = bias; g.ld_out = sh.N; g.pair = pair; g.w_static = 1;
+      if (sh.res) { g.out.f32 = h; g.out.hi = o; g.out.lo = o_lo; g.stats_out = stats; g.ln_stats_ld = B; }
+      else {
+        g.ln_stats = stats; g.ln_parts = d / 32; g.ln_stats_ld = B; g.ln_colsum = colsum;
+        if (sh.epi == EPI_NONE) { g.out.hi = qkv; g.out_f16 = 1; } else { g.out.hi = o; g.out.lo = o_lo; }
+      }
+      for (int i = 0; i < 3; ++i) OK(launch_gemm_bf16(g, st));
+      float us = time_loop(st, 50, [&](int) { OK(launch_gemm_bf16(g, st)); });
+      CK(cudaMemsetAsync(tr, 0, 640 * 8, st));
+      g.trace = tr;
+      OK(launch_gemm_bf16(g, st));
+      long long h_tr[640];
+      CK(cudaMemcpyAsync(h_tr, tr, sizeof(h_tr), cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+      const int nkb = sh.K / 64;
+      printf("x2 timeline %s (N=%d K=%d block_n=%d%s, %.2f us back to back): prologue done %lld | first TMA issued %lld | first MMA issued %lld | last MMA committed %lld | "
+             "epilogue: accumulator seen %lld, done %lld cycles\n", sh.name, sh.N, sh.K, bn, pair ? " pair" : "", us, h_tr[600], h_tr[2], h_tr[256 + 1],
+             h_tr[256 + (nkb - 1 < 59 ? nkb - 1 : 59) * 4 + 2], h_tr[512 + 1], h_tr[512 + 2]);
+      printf("   per k-block MMA issue times:");
+      for (int kb = 0; kb < nkb && kb < 16; ++kb) printf(" %lld", h_tr[256 + kb * 4 + 1]);
+      printf("\n   epilogue warp 0 chunk 0: begin %lld tmem_loaded %lld staged %lld bias_arrived %lld math_done %lld stores_issued %lld chunk_done(stats) %lld\n", h_tr[540], h_tr[541],
+             h_tr[542], h_tr[543], h_tr[545], h_tr[546], h_tr[544]);
+    }
+    return 0;
+  }
+
   // ---- layernorm ----
   for (int rows : {32, 256, B, 4 * B}) {
     float* hh = (float*)dmalloc((size_t)rows * d * 4);

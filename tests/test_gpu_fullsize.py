@@ -369,7 +369,8 @@ def test_max_length_up_to_the_position_table():
 
 
 _SHARD_WORKER = r'''
-import os, sys
+import faulthandler, os, sys
+faulthandler.enable()
 sys.path.insert(0, {root!r})
 import torch, torch.distributed as dist
 rank, world = int(sys.argv[1]), int(sys.argv[2])
@@ -398,6 +399,9 @@ if rank == 0:
 else:
     assert ids is None
     dist.destroy_process_group()
+    print("SHARD_RANK_DONE", rank)
+model.invalidate_engine()
+torch.cuda.synchronize()
 '''
 
 
@@ -421,5 +425,5 @@ def test_sharded_job_on_several_gpus(tmp_path, dtype):
     script.write_text(_SHARD_WORKER.format(root=root, port=port, dtype=dtype))
     procs = [subprocess.Popen([sys.executable, str(script), str(r), str(n)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(n)]
     outs = [p.communicate(timeout=600)[0] for p in procs]
-    assert all(p.returncode == 0 for p in procs), outs
+    assert all(p.returncode == 0 for p in procs), ([p.returncode for p in procs], outs)
     assert "SHARDED_GPU_OK" in outs[0]
