@@ -1230,7 +1230,7 @@ static int launch_one_pair(const GemmKernelParams& kp, cudaStream_t st) {
   attr[na].id = cudaLaunchAttributeClusterDimension;
   attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
   ++na;
-  if (pdl_enabled()) {
+  if (pdl_enabled() && !g_gemm_no_pdl) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;

@@ -297,12 +297,15 @@ int main(int argc, char** argv) {
     bf16* wl = (bf16*)dmalloc((size_t)4 * d * d * 2);
     float2* stats = (float2*)dmalloc((size_t)64 * B * 8);
     float* colsum = (float*)dmalloc((size_t)V * 4);
-    struct Shape { const char* name; bf16* W; int N, K, epi; bool res; };
-    Shape shapes[] = {{"qkv", w_qkv[0], 3 * d, d, EPI_NONE, false}, {"proj", w_proj[0], d, d, EPI_RESIDUAL, true},
-                      {"fc", w_fc[0], 4 * d, d, EPI_GELU, false}, {"fc2", w_fc2[0], d, 4 * d, EPI_RESIDUAL, true}};
+    struct Shape { const char* name; bf16* W; int N, K, epi; bool res; int sk; };
+    float* skws = (float*)dmalloc((size_t)4 * B * d * 4);
+    int* skcnt = (int*)dmalloc(4096 * 4);
+    Shape shapes[] = {{"qkv", w_qkv[0], 3 * d, d, EPI_NONE, false, 1}, {"proj", w_proj[0], d, d, EPI_RESIDUAL, true, 1},
+                      {"fc", w_fc[0], 4 * d, d, EPI_GELU, false, 1}, {"fc2", w_fc2[0], d, 4 * d, EPI_RESIDUAL, true, 1},
+                      {"fc2 split-K 3", w_fc2[0], d, 4 * d, EPI_RESIDUAL, true, 3}, {"proj split-K 2", w_proj[0], d, d, EPI_RESIDUAL, true, 2}};
     for (const Shape& sh : shapes) {
       int bn = 0, pair = 0;
-      gemm_bf16_pick(B, sh.N, sh.K, 1, 1, &bn, &pair);
+      gemm_bf16_pick(B, sh.N, sh.K, 1, sh.sk, &bn, sh.sk > 1 ? nullptr : &pair);
       GemmBf16Args g;
       OK(make_tma_2d_bf16(&g.a_hi, a, B, sh.K, sh.K, 128));
       OK(make_tma_2d_bf16(&g.a_lo, a_lo, B, sh.K, sh.K, 128));
@@ -314,6 +317,7 @@ int main(int argc, char** argv) {
         g.ln_stats = stats; g.ln_parts = d / 32; g.ln_stats_ld = B; g.ln_colsum = colsum;
         if (sh.epi == EPI_NONE) { g.out.hi = qkv; g.out_f16 = 1; } else { g.out.hi = o; g.out.lo = o_lo; }
       }
+      if (sh.sk > 1) { g.split_k = sh.sk; g.splitk_ws = skws; g.splitk_counters = skcnt; }
       for (int i = 0; i < 3; ++i) OK(launch_gemm_bf16(g, st));
       float us = time_loop(st, 50, [&](int) { OK(launch_gemm_bf16(g, st)); });
       CK(cudaMemsetAsync(tr, 0, 640 * 8, st));

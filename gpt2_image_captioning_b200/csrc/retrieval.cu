@@ -381,10 +381,14 @@ int launch_topk_ip_tc(const float* q, const float* db, const bf16* db_hi, const 
   for (long base = 0; base < N; base += TOPK_CHUNK) {
     const int rows = (int)((N - base) < TOPK_CHUNK ? (N - base) : TOPK_CHUNK);
     const auto c0 = now();
-    GIC_TRY(make_tma_2d_bf16(&g.w_hi, db_hi + (size_t)base * D, rows, D, D, 64));
-    GIC_TRY(make_tma_2d_bf16(&g.w_lo, db_lo + (size_t)base * D, rows, D, D, 64));
+    // tile shape from the GEMM cost model (round 2: the bf16x2 kernels have wide tiles and CTA pairs; 64-column tiles ran this scan
+    // at 166 TFLOP/s); a ragged last chunk takes single CTAs (pairs need whole 32-column groups and aligned rows)
+    int bn = 64, pair = 0;
+    gemm_bf16_pick(B, rows, D, 1, 1, &bn, (rows % 32 == 0) ? &pair : nullptr);
+    GIC_TRY(make_tma_2d_bf16(&g.w_hi, db_hi + (size_t)base * D, rows, D, D, pair ? bn / 2 : bn));
+    GIC_TRY(make_tma_2d_bf16(&g.w_lo, db_lo + (size_t)base * D, rows, D, D, pair ? bn / 2 : bn));
     const auto c1 = now();
-    g.M = B; g.N = rows; g.K = D; g.block_n = 64; g.split = 1; g.epilogue = EPI_NONE; g.bias = nullptr;
+    g.M = B; g.N = rows; g.K = D; g.block_n = bn; g.pair = pair; g.split = 1; g.epilogue = EPI_NONE; g.bias = nullptr;
     g.out = ActOut(); g.out.f32 = chunk_scores; g.ld_out = rows;
     GIC_TRY(launch_gemm_bf16(g, st));
     const auto c2 = now();
