@@ -222,6 +222,9 @@ struct alignas(64) GemmKernelParams {
   bf16* out_hi; bf16* out_lo; int ld_bf16;
   float* part_val; int* part_idx; int part_ld;  // [M][part_ld]: slot (tile * 2 + column-parity warp) of each row
   float* part_val2;  // EPI_ARGMAX2: the slot's second-best value (candidate generation for the exactly re-scored LM head)
+  // EPI_TOPK (retrieval scan, no score matrix): every epilogue thread keeps the GEMM_TOPK_KEEP best (score, column) of the columns it
+  // sees for ITS row + the largest score it dropped; written at the end as stream (unit index / m_units) * 2 + column-parity warp of the row
+  float* topk_v; int* topk_i; float* topk_u; int topk_streams;
   // folded LayerNorm on the A operand (see launch_gemm_bf16): out = rstd_r * (acc - mean_r * colsum_n) + bias_n
   const float2* ln_stats; int ln_parts; long ln_stats_ld; int ln_row_mul, ln_row_off; const float* ln_colsum;
   // split-K (see launch_gemm_bf16): `split_k` CTAs share one output tile, each over K / split_k; fp32 partials go to splitk_ws
@@ -233,6 +236,8 @@ struct alignas(64) GemmKernelParams {
   long long* trace;  // null; microbenchmark only: clock64 timeline of CTA 0's producer / MMA / epilogue warps
 };
 
+constexpr int GEMM_TOPK_KEEP = 8;
+static_assert(GEMM_TOPK_KEEP == GEMM_TOPK_KEEP_PUBLIC, "kernels.cuh publishes the survivor count of the fused top-k epilogue");
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;   // one 128-byte swizzle atom per row
 constexpr int GEMM_THREADS = 320;
@@ -478,12 +483,61 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
       if (PAIR) ptx::mbar_arrive_cluster(tmem_empty_bar + 8 * a, 0);
       else ptx::mbar_arrive(tmem_empty_bar + 8 * a);
     };
+    // EPI_TOPK: the launch keeps the row tile of a CTA fixed (grid units a multiple of m_units), so this thread's row never changes
+    float tk_v[GEMM_TOPK_KEEP], tk_u = -INFINITY;
+    int tk_i[GEMM_TOPK_KEEP];
+    if (EPI == EPI_TOPK) {
+#pragma unroll
+      for (int j = 0; j < GEMM_TOPK_KEEP; ++j) { tk_v[j] = -INFINITY; tk_i[j] = -1; }
+    }
     for (int work = work0; work < total_work; work += work_stride, ++local) {
       const int tile = work % total_tiles, ks = work / total_tiles;
       const uint32_t acc = local & 1, use = local >> 1;
       const int n_tile = tile / m_units;
       const int m0 = ((tile % m_units) * m_per_unit + (int)rank) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
       const int wrow0 = m0 + q * 32;  // first row of this warp's 32-row band
+      if (EPI == EPI_TOPK) {
+        // ---- retrieval scan: scores straight from the TMEM registers (lane = row) into the thread's running top-KEEP; columns arrive
+        // in ascending order within a thread, so on equal scores the lower column stays (the exact path's tie rule) ----
+        ptx::mbar_wait(tmem_full_bar + 8 * acc, use & 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_row = tmem_base + acc * Tile::ACC_COLS + ((uint32_t)(q * 32) << 16);
+        if (sub * 32 >= BLOCK_N) {
+          ptx::tc_fence_before();
+          if (lane == 0) release_acc(acc);
+        }
+#pragma unroll 1
+        for (int c0 = sub * 32; c0 < BLOCK_N; c0 += 64) {
+          const int col0 = n0 + c0;
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_row + (uint32_t)c0, r);
+          ptx::tmem_ld_wait();
+          if (c0 + 64 >= BLOCK_N) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) release_acc(acc);
+          }
+          if (col0 >= p.N) continue;  // warp-uniform
+          const int ncol = min(32, p.N - col0);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float x = __uint_as_float(r[c]);
+            if (c < ncol) {
+              if (x > tk_v[GEMM_TOPK_KEEP - 1]) {
+                tk_u = fmaxf(tk_u, tk_v[GEMM_TOPK_KEEP - 1]);
+                float pv = x;
+                int pi = col0 + c;
+#pragma unroll
+                for (int j = 0; j < GEMM_TOPK_KEEP; ++j)
+                  if (pv > tk_v[j]) { const float tv = tk_v[j]; const int ti = tk_i[j]; tk_v[j] = pv; tk_i[j] = pi; pv = tv; pi = ti; }
+              } else {
+                tk_u = fmaxf(tk_u, x);
+              }
+            }
+          }
+        }
+        continue;
+      }
       if ((EPI == EPI_ARGMAX || EPI == EPI_ARGMAX2) && OUT == OUT_NONE) {
         // ---- LM head on the product path: argmax straight from the TMEM registers (lane = row), nothing is staged or stored.
         // (the staging tile would add ~20 % to the shared-memory traffic that bounds this kernel's main loop) ----
@@ -972,6 +1026,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
       }
       if (tracing && e == 0 && lane == 0 && local < 8) p.trace[512 + local * 4 + 2] = clock64() - t_start;
     }
+    if (EPI == EPI_TOPK && work0 < total_work) {
+      const int row = ((work0 % m_units) * m_per_unit + (int)rank) * GEMM_BLOCK_M + q * 32 + lane;
+      if (row < p.M && sub * 32 < BLOCK_N) {
+        const int stream = (work0 / m_units) * 2 + sub;
+        const size_t so = ((size_t)row * p.topk_streams + stream) * GEMM_TOPK_KEEP;
+#pragma unroll
+        for (int j = 0; j < GEMM_TOPK_KEEP; ++j) { p.topk_v[so + j] = tk_v[j]; p.topk_i[so + j] = tk_i[j]; }
+        p.topk_u[(size_t)row * p.topk_streams + stream] = tk_u;
+      }
+    }
   }
 
   ptx::tc_fence_before();
@@ -1116,7 +1180,8 @@ static int gemm_num_sms() {
 // and the LM head; the narrow tiles (32 / 64) keep the full list above for the mappers and the test hooks
 #define GIC_GEMM_VARIANTS_SPLIT_WIDE(X) \
   X(EPI_NONE, OUT_F16, true, false) X(EPI_GELU, OUT_BF16X2, true, false) X(EPI_RESIDUAL, OUT_F32_BF16X2_STATS, false, false) \
-  X(EPI_ARGMAX, OUT_NONE, false, false) X(EPI_NONE, OUT_F32, false, false) X(EPI_NONE, OUT_F32, false, true) X(EPI_ARGMAX, OUT_F32, false, true)
+  X(EPI_ARGMAX, OUT_NONE, false, false) X(EPI_NONE, OUT_F32, false, false) X(EPI_NONE, OUT_F32, false, true) X(EPI_ARGMAX, OUT_F32, false, true) \
+  X(EPI_TOPK, OUT_NONE, false, false)
 
 // CTA-pair instantiations (aligned shapes, bf16 operands): the fused decode / prefill GEMMs, the LM head, and the plain fp32-output
 // GEMM of the kernel test hook
@@ -1124,7 +1189,8 @@ static int gemm_num_sms() {
   X(EPI_NONE, OUT_BF16, true) X(EPI_GELU, OUT_BF16, true) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_NONE, OUT_F32, false) \
   X(EPI_ARGMAX2, OUT_NONE, false)
 #define GIC_GEMM_VARIANTS_PAIR_SPLIT(X) \
-  X(EPI_NONE, OUT_F16, true) X(EPI_GELU, OUT_BF16X2, true) X(EPI_RESIDUAL, OUT_F32_BF16X2_STATS, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_NONE, OUT_F32, false)
+  X(EPI_NONE, OUT_F16, true) X(EPI_GELU, OUT_BF16X2, true) X(EPI_RESIDUAL, OUT_F32_BF16X2_STATS, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_NONE, OUT_F32, false) \
+  X(EPI_TOPK, OUT_NONE, false)
 
 template <int BLOCK_N>
 static int configure_pair() {
@@ -1192,6 +1258,10 @@ static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
 
   const int sms = cta_limit() > 0 && cta_limit() < gemm_num_sms() ? cta_limit() : gemm_num_sms();
   dim3 grid((unsigned)(tiles < sms ? tiles : sms));  // persistent: one CTA per SM (of this chain's share, see cta_limit)
+  if (EPI == EPI_TOPK) {  // row-tile-stationary CTAs: the grid is a multiple of the number of row tiles (see launch_gemm_topk_streams)
+    const int m_units = ceil_div(kp.M, GEMM_BLOCK_M);
+    grid.x = (unsigned)(kp.topk_streams / 2 * m_units);
+  }
   if (g_gemm_no_pdl) {
     kern<<<grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st>>>(kp);
     GIC_CHECK_CUDA(cudaGetLastError());
@@ -1219,7 +1289,8 @@ static int launch_one_pair(const GemmKernelParams& kp, cudaStream_t st) {
     max_pairs = n;
   }
   const long units = (long)(ceil_div(kp.M, GEMM_BLOCK_M) / 2) * ceil_div(kp.N, BLOCK_N);
-  const long pairs = units < max_pairs ? units : max_pairs;
+  long pairs = units < max_pairs ? units : max_pairs;
+  if (EPI == EPI_TOPK) pairs = (long)(kp.topk_streams / 2) * (ceil_div(kp.M, GEMM_BLOCK_M) / 2);  // row-tile-stationary pairs
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * pairs));
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -1287,6 +1358,19 @@ static int launch_cfg(const GemmKernelParams& kp, int epi, int out, bool fold, c
   return GIC_ERR_UNSUPPORTED;
 }
 
+// Streams of the fused top-k epilogue: CTAs (or CTA pairs) are row-tile-stationary -- the grid holds `g` units per row tile, each walking
+// every g-th column tile -- and each unit's two column-parity epilogue warps keep one candidate stream per row: 2 g streams per row.
+int gemm_topk_streams(int M, int N, int block_n, int pair) {
+  const int m_units = pair ? ceil_div(M, GEMM_BLOCK_M) / 2 : ceil_div(M, GEMM_BLOCK_M);
+  const int n_tiles = ceil_div(N, block_n);
+  int units = pair ? gemm_num_sms() / 2 : gemm_num_sms();
+  if (cta_limit() > 0 && cta_limit() < gemm_num_sms()) units = pair ? cta_limit() / 2 : cta_limit();
+  int g = units / (m_units < 1 ? 1 : m_units);
+  if (g > n_tiles) g = n_tiles;
+  if (g < 1) g = 1;
+  return 2 * g;
+}
+
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   struct NoPdlScope { bool prev; explicit NoPdlScope(bool v) : prev(g_gemm_no_pdl) { g_gemm_no_pdl = v; } ~NoPdlScope() { g_gemm_no_pdl = prev; } } no_pdl_scope(a.no_pdl != 0);
   GIC_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm_bf16: empty problem");
@@ -1297,6 +1381,7 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   kp.mma_repeat = a.mma_repeat < 1 ? 1 : a.mma_repeat;
   kp.out_f32 = a.out.f32; kp.ld_f32 = a.ld_out; kp.out_hi = a.out.hi; kp.out_lo = a.out.lo; kp.ld_bf16 = a.ld_out;
   kp.part_val = a.part_val; kp.part_idx = a.part_idx; kp.part_ld = a.part_ld; kp.part_val2 = a.part_val2; kp.trace = a.trace;
+  kp.topk_v = a.topk_v; kp.topk_i = a.topk_i; kp.topk_u = a.topk_u; kp.topk_streams = a.topk_streams;
   kp.ln_stats = a.ln_stats; kp.ln_parts = a.ln_parts; kp.ln_stats_ld = a.ln_stats_ld; kp.ln_row_mul = a.ln_row_mul; kp.ln_row_off = a.ln_row_off;
   kp.ln_colsum = a.ln_colsum; kp.stats_out = a.stats_out;
   kp.split_k = a.split_k < 1 ? 1 : a.split_k; kp.splitk_ws = a.splitk_ws; kp.splitk_counters = a.splitk_counters;
@@ -1304,6 +1389,13 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   kp.step_trace = trace_desc();
   GIC_REQUIRE(!a.ln_stats || (a.ln_colsum && a.ln_parts > 0), "gemm_bf16: folded LayerNorm needs the column sums and at least one statistics part");
   int epi = a.epilogue;
+  if (a.topk_v) {
+    GIC_REQUIRE(a.epilogue == EPI_NONE && a.topk_i && a.topk_u && !a.part_val && !a.out.f32 && !a.out.hi && !a.ln_stats && kp.split_k == 1,
+                "gemm_bf16: the fused top-k epilogue takes raw scores and no other output");
+    GIC_REQUIRE(a.topk_streams >= 2 && a.topk_streams == gemm_topk_streams(a.M, a.N, a.block_n, a.pair), "gemm_bf16: top-k stream count %d does not match the launch shape",
+                a.topk_streams);
+    epi = EPI_TOPK;
+  }
   if (a.part_val) {
     GIC_REQUIRE(a.epilogue == EPI_NONE && a.part_idx, "gemm_bf16: the fused argmax takes no activation and needs both partial buffers");
     GIC_REQUIRE(a.part_ld >= 2 * ceil_div(a.N, a.block_n), "gemm_bf16: argmax partial rows too short (%d slots for %d)", a.part_ld, 2 * ceil_div(a.N, a.block_n));
@@ -1327,7 +1419,7 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   } else if (a.out.hi) {
     out = a.out.lo ? OUT_BF16X2 : OUT_BF16;
   } else {
-    GIC_REQUIRE(epi == EPI_ARGMAX || epi == EPI_ARGMAX2, "gemm_bf16: no output buffer");
+    GIC_REQUIRE(epi == EPI_ARGMAX || epi == EPI_ARGMAX2 || epi == EPI_TOPK, "gemm_bf16: no output buffer");
   }
   if (kp.split_k > 1) {
     GIC_REQUIRE(epi != EPI_ARGMAX && epi != EPI_ARGMAX2 && a.splitk_ws && a.splitk_counters, "gemm_bf16: split-K needs its workspace / counters and a storing epilogue");

@@ -5,7 +5,8 @@
 namespace gic {
 
 enum Epilogue { EPI_NONE = 0, EPI_TANH = 1, EPI_GELU = 2, EPI_RELU = 3, EPI_RESIDUAL = 4, EPI_ARGMAX = 5 /* internal: set by part_val */,
-                EPI_ARGMAX2 = 6 /* internal: set by part_val2 (best + runner-up value per slot) */ };
+                EPI_ARGMAX2 = 6 /* internal: set by part_val2 (best + runner-up value per slot) */,
+                EPI_TOPK = 7 /* internal: set by topk_v (per-row running top-8 + drop bound, no score matrix) */ };
 
 // Where a producer kernel writes an activation: fp32 and/or bf16 (hi) and/or the bf16 remainder (lo = bf16(v - hi),
 // the second half of a BF16X2 GEMM operand).  Any pointer may be null.
@@ -49,6 +50,9 @@ struct GemmBf16Args {
   int* part_idx = nullptr;         // ... and its lowest column index (cols >= N masked)
   int part_ld = 0;                 // slots per row (>= 2 * n_tiles)
   float* part_val2 = nullptr;      // optional [M][part_ld]: second-best value of each slot (lm_head_rescore_kernel's candidate test)
+  // fused top-k scan (retrieval): per row and stream the GEMM_TOPK_KEEP (8) best (score, column) + the largest dropped score; stream count from
+  // gemm_topk_streams(M, N, block_n, pair).  topk_v / topk_i [M][streams][8], topk_u [M][streams]
+  float* topk_v = nullptr; int* topk_i = nullptr; float* topk_u = nullptr; int topk_streams = 0;
   // LayerNorm folded into the GEMM (A holds the RAW rows x, W was packed as gamma_k * W[n,k], bias as b_n + sum_k beta_k W[n,k]):
   //   out[r,n] = rstd_r * (acc[r,n] - mean_r * ln_colsum[n]) + bias[n],   mean / rstd from sum_parts ln_stats[part][r * mul + off]
   const float2* ln_stats = nullptr;  // [ln_parts][ln_stats_ld] (sum x, sum x^2) partials written by the producer of A
@@ -65,6 +69,8 @@ struct GemmBf16Args {
   long long* trace = nullptr;      // microbenchmark only: device buffer of >= 640 int64 for CTA 0's clock64 timeline
 };
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st);
+int gemm_topk_streams(int M, int N, int block_n, int pair);
+constexpr int GEMM_TOPK_KEEP_PUBLIC = 8;  // == GEMM_TOPK_KEEP (gemm_tcgen05.cu)
 int gemm_bf16_pick_block_n(int M, int N, int split);
 // tile width for an M x N x K problem cut into split_k K slices (split: bf16x2 operands)
 // pair (may be null): out, 1 = run as CTA pairs (cta_group::2); the W tensor map's box is then block_n / 2 rows and GemmBf16Args::pair is set

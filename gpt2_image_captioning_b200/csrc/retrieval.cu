@@ -142,9 +142,11 @@ int launch_topk_ip(const float* q, const float* db, int B, int N, int D, int k, 
 // Tensor-core top-k with the exact path's results.  The fp32 scan above runs at ~27 TFLOP/s on the CUDA cores (23 ms for
 // 1024 queries over the 591 753-row caption matrix, profiles/r1ak_configs.jsonl).  Here the scan is a bf16x2 tcgen05 GEMM
 // (operands split hi + lo, three MMAs per product: error <= ~2.3e-5 |q||d|), which only has to find CANDIDATES:
-//   1. per chunk: approximate scores -> every scan thread (256 per query) keeps its four best and the largest score it DROPPED;
-//      at the end the 32 best of the 1024 survivors become the candidates and U = the largest score dropped anywhere
-//      (the sorted-insertion merge above costs ~1 ms per 32 768-row chunk at k = 16 and more at 32: too slow for this path);
+//   1. ONE GEMM launch over the whole database whose epilogue never writes a score (EPI_TOPK, gemm_tcgen05.cu): CTAs are
+//      row-tile-stationary, every epilogue thread owns one query row and keeps, over all the column tiles it walks, its 8 best
+//      (score, row id) and the largest score it DROPPED; a query ends with 2 x (CTAs per row tile) such streams.  The 32 best of the
+//      survivors become the candidates and U = the largest score dropped anywhere.  (Round 1 materialised [B, 32 768] fp32 score
+//      chunks and re-read them with a scan kernel: 4.8 GB of traffic for configs[4], 3.7 ms; fused: the GEMM's own time.)
 //   2. every candidate is re-scored exactly: one thread per candidate, fp32 FMA chain over the dims in ascending order --
 //      the summation order of sgemm_nt_kernel, so scores AND ranks are bit-identical to the exact path;
 //   3. certificate: U bounds every non-candidate's approximate score, so its exact score is at most U + eps,
@@ -154,17 +156,17 @@ int launch_topk_ip(const float* q, const float* db, int B, int N, int D, int k, 
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int TOPK_TC_CAND = 32;
 constexpr int TOPK_TC_MAXK = 16;
-constexpr int TOPK_TC_THREADS = 256;  // scan threads per query ...
-constexpr int TOPK_TC_KEEP = 4;       // ... each keeps this many of its best approximate scores
+constexpr int TOPK_TC_THREADS = 256;   // select kernel threads per query
+constexpr int TOPK_TC_KEEP = GEMM_TOPK_KEEP_PUBLIC;  // survivors per (query, stream): the fused epilogue's running list
+constexpr int TOPK_TC_MAX_STREAMS = 2 * 160;  // 2 per CTA of a row tile, at most one row tile and every SM
 
 size_t topk_tc_workspace_bytes(int B, int N, int D, int k) {
-  (void)k;
-  const size_t chunk = (size_t)(N < TOPK_CHUNK ? N : TOPK_CHUNK);
-  return align_up((size_t)B * chunk * sizeof(float), 256) + 2 * align_up((size_t)B * D * sizeof(bf16), 256) +
-         align_up((size_t)B * TOPK_TC_CAND * sizeof(float), 256) + align_up((size_t)B * TOPK_TC_CAND * sizeof(int64_t), 256) +
-         align_up(((size_t)B + 1) * sizeof(int), 256) +  // flags [B] + the number of flagged queries
-         align_up((size_t)B * TOPK_TC_THREADS * TOPK_TC_KEEP * sizeof(float), 256) + align_up((size_t)B * TOPK_TC_THREADS * TOPK_TC_KEEP * sizeof(int), 256) +
-         align_up((size_t)B * TOPK_TC_THREADS * sizeof(float), 256) + align_up((size_t)B * sizeof(float), 256) + 256;  // scan state + bounds
+  (void)k; (void)N;
+  const size_t surv = (size_t)B * TOPK_TC_MAX_STREAMS * TOPK_TC_KEEP;
+  return 2 * align_up((size_t)B * D * sizeof(bf16), 256) + align_up((size_t)B * TOPK_TC_CAND * sizeof(float), 256) +
+         align_up((size_t)B * TOPK_TC_CAND * sizeof(int64_t), 256) + align_up(((size_t)B + 1) * sizeof(int), 256) +  // flags [B] + the number of flagged queries
+         align_up(surv * sizeof(float), 256) + align_up(surv * sizeof(int), 256) + align_up((size_t)B * TOPK_TC_MAX_STREAMS * sizeof(float), 256) +
+         align_up((size_t)B * sizeof(float), 256) + 512;  // scan state + bounds
 }
 
 // exact fp32 inner product in the summation order of the exact path (ascending k, one FMA chain from 0)
@@ -180,82 +182,55 @@ __device__ __forceinline__ float dot_exact(const float* __restrict__ q_s, const 
   return acc;
 }
 
-// scan one chunk of approximate scores: thread t of query b looks at columns t, t + 256, ... and updates its TOPK_TC_KEEP best +
-// drop bound.  (A query is flagged when one thread's columns hold more than TOPK_TC_KEEP of the rows that matter: with 256 threads
-// and 4 kept that is ~C(k,5) / 256^4 < 1e-6 per query for k <= 16.)
-__global__ void __launch_bounds__(TOPK_TC_THREADS) topk_tc_scan_kernel(const float* __restrict__ chunk_scores, int chunk_rows, int chunk_base, int first,
-                                                                       float* __restrict__ st_v, int* __restrict__ st_i, float* __restrict__ st_u) {
-  const int b = blockIdx.x, t = threadIdx.x;
-  const size_t so = ((size_t)b * TOPK_TC_THREADS + t) * TOPK_TC_KEEP;
-  float v[TOPK_TC_KEEP], u = -INFINITY;
-  int ix[TOPK_TC_KEEP];
-#pragma unroll
-  for (int j = 0; j < TOPK_TC_KEEP; ++j) { v[j] = -INFINITY; ix[j] = -1; }
-  if (!first) {
-#pragma unroll
-    for (int j = 0; j < TOPK_TC_KEEP; ++j) { v[j] = st_v[so + j]; ix[j] = st_i[so + j]; }
-    u = st_u[(size_t)b * TOPK_TC_THREADS + t];
-  }
-  const float* row = chunk_scores + (size_t)b * chunk_rows;
-  for (int c = t; c < chunk_rows; c += TOPK_TC_THREADS) {
-    const float x = row[c];
-    if (x > v[TOPK_TC_KEEP - 1]) {  // (columns arrive in ascending index order, so on equal scores the earlier index stays)
-      u = fmaxf(u, v[TOPK_TC_KEEP - 1]);
-      float pv = x; int pi = chunk_base + c;
-#pragma unroll
-      for (int j = 0; j < TOPK_TC_KEEP; ++j)
-        if (pv > v[j]) { const float tv = v[j]; const int ti = ix[j]; v[j] = pv; ix[j] = pi; pv = tv; pi = ti; }
-    } else {
-      u = fmaxf(u, x);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < TOPK_TC_KEEP; ++j) { st_v[so + j] = v[j]; st_i[so + j] = ix[j]; }
-  st_u[(size_t)b * TOPK_TC_THREADS + t] = u;
-}
-
-// the TOPK_TC_CAND best of a query's 256 x TOPK_TC_KEEP survivors -> candidate list; bound[b] = the largest approximate score that is
-// NOT a candidate
+// the TOPK_TC_CAND best of a query's `streams` x TOPK_TC_KEEP survivors -> candidate list; bound[b] = the largest approximate score that is
+// NOT a candidate (dropped by a stream, or a survivor that did not make the list).  A query would be wrong only if one stream held more than
+// TOPK_TC_KEEP of the rows that matter and dropped one -- which the certificate below catches (the dropped score raises U).
 __global__ void __launch_bounds__(TOPK_TC_THREADS) topk_tc_select_kernel(const float* __restrict__ st_v, const int* __restrict__ st_i,
-                                                                         const float* __restrict__ st_u, float* __restrict__ cand_score,
+                                                                         const float* __restrict__ st_u, int streams, float* __restrict__ cand_score,
                                                                          int64_t* __restrict__ cand_idx, float* __restrict__ bound) {
-  constexpr int KEEP = TOPK_TC_KEEP;
-  __shared__ float sv[KEEP * TOPK_TC_THREADS];
-  __shared__ int si[KEEP * TOPK_TC_THREADS];
+  extern __shared__ unsigned char sel_raw[];
+  const int S = streams * TOPK_TC_KEEP;
+  float* sv = reinterpret_cast<float*>(sel_raw);  // [S]
+  int* si = reinterpret_cast<int*>(sv + S);        // [S]
   __shared__ float rv[8];
   __shared__ int rs[8];
   const int b = blockIdx.x, t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const size_t so = ((size_t)b * TOPK_TC_THREADS + t) * KEEP;
-#pragma unroll
-  for (int j = 0; j < KEEP; ++j) { sv[KEEP * t + j] = st_v[so + j]; si[KEEP * t + j] = st_i[so + j]; }
-  float u = st_u[(size_t)b * TOPK_TC_THREADS + t];
+  for (int i = t; i < S; i += TOPK_TC_THREADS) { sv[i] = st_v[(size_t)b * S + i]; si[i] = st_i[(size_t)b * S + i]; }
+  float u = -INFINITY;
+  for (int i = t; i < streams; i += TOPK_TC_THREADS) u = fmaxf(u, st_u[(size_t)b * streams + i]);
   __syncthreads();
   for (int out = 0; out < TOPK_TC_CAND; ++out) {
-    // block argmax over the survivors still in the pool (ties: lower slot; any consistent rule will do for candidates)
-    float bv = sv[KEEP * t]; int bs = KEEP * t;
-#pragma unroll
-    for (int j = 1; j < KEEP; ++j)
-      if (sv[KEEP * t + j] > bv) { bv = sv[KEEP * t + j]; bs = KEEP * t + j; }
+    // block argmax over the survivors still in the pool (ties: the lower row id, so that the candidates do not depend on the stream layout)
+    float bv = -INFINITY; int bs = -1, bid = 0x7fffffff;
+    for (int i = t; i < S; i += TOPK_TC_THREADS) {
+      const float v = sv[i]; const int id = si[i];
+      if (id >= 0 && (v > bv || (v == bv && id < bid))) { bv = v; bs = i; bid = id; }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
       const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-      if (ov > bv || (ov == bv && os < bs)) { bv = ov; bs = os; }
+      const int oid = __shfl_xor_sync(0xffffffffu, bid, o);
+      if (os >= 0 && (bs < 0 || ov > bv || (ov == bv && oid < bid))) { bv = ov; bs = os; bid = oid; }
     }
     if (lane == 0) { rv[warp] = bv; rs[warp] = bs; }
     __syncthreads();
     if (t == 0) {
-      for (int w = 1; w < TOPK_TC_THREADS / 32; ++w)
-        if (rv[w] > bv || (rv[w] == bv && rs[w] < bs)) { bv = rv[w]; bs = rs[w]; }
-      const bool valid = si[bs] >= 0;
-      cand_score[(size_t)b * TOPK_TC_CAND + out] = valid ? bv : -INFINITY;
-      cand_idx[(size_t)b * TOPK_TC_CAND + out] = valid ? (int64_t)si[bs] : -1;
-      sv[bs] = -INFINITY; si[bs] = -1;
+      int best = -1; float best_v = -INFINITY; int best_id = 0x7fffffff;
+      for (int w = 0; w < TOPK_TC_THREADS / 32; ++w) {
+        const int sidx = rs[w];
+        if (sidx < 0) continue;
+        const float v = rv[w]; const int id = si[sidx];
+        if (best < 0 || v > best_v || (v == best_v && id < best_id)) { best = sidx; best_v = v; best_id = id; }
+      }
+      cand_score[(size_t)b * TOPK_TC_CAND + out] = best >= 0 ? best_v : -INFINITY;
+      cand_idx[(size_t)b * TOPK_TC_CAND + out] = best >= 0 ? (int64_t)best_id : -1;
+      if (best >= 0) { sv[best] = -INFINITY; si[best] = -1; }
     }
     __syncthreads();
   }
-#pragma unroll
-  for (int j = 0; j < KEEP; ++j) u = fmaxf(u, sv[KEEP * t + j]);  // survivors that did not make the list count as dropped
+  for (int i = t; i < S; i += TOPK_TC_THREADS)
+    if (si[i] >= 0) u = fmaxf(u, sv[i]);  // survivors that did not make the list count as dropped
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) u = fmaxf(u, __shfl_xor_sync(0xffffffffu, u, o));
   if (lane == 0) rv[warp] = u;
@@ -353,53 +328,37 @@ int launch_topk_ip_tc(const float* q, const float* db, const bf16* db_hi, const 
   GIC_REQUIRE(ws_bytes >= topk_tc_workspace_bytes(B, N, D, k), "topk_ip_tc: workspace too small");
   GIC_TRY(tma_init());
   GIC_TRY(gemm_bf16_configure());
-  const size_t chunk = (size_t)(N < TOPK_CHUNK ? N : TOPK_CHUNK);
   unsigned char* w8 = reinterpret_cast<unsigned char*>(align_up((size_t)ws, 256));
-  float* chunk_scores = reinterpret_cast<float*>(w8); w8 += align_up((size_t)B * chunk * sizeof(float), 256);
   bf16* q_hi = reinterpret_cast<bf16*>(w8); w8 += align_up((size_t)B * D * sizeof(bf16), 256);
   bf16* q_lo = reinterpret_cast<bf16*>(w8); w8 += align_up((size_t)B * D * sizeof(bf16), 256);
   float* cand_score = reinterpret_cast<float*>(w8); w8 += align_up((size_t)B * TOPK_TC_CAND * sizeof(float), 256);
   int64_t* cand_idx = reinterpret_cast<int64_t*>(w8); w8 += align_up((size_t)B * TOPK_TC_CAND * sizeof(int64_t), 256);
   int* flags = reinterpret_cast<int*>(w8); w8 += align_up(((size_t)B + 1) * sizeof(int), 256);
-  float* st_v = reinterpret_cast<float*>(w8); w8 += align_up((size_t)B * TOPK_TC_THREADS * TOPK_TC_KEEP * sizeof(float), 256);
-  int* st_i = reinterpret_cast<int*>(w8); w8 += align_up((size_t)B * TOPK_TC_THREADS * TOPK_TC_KEEP * sizeof(int), 256);
-  float* st_u = reinterpret_cast<float*>(w8); w8 += align_up((size_t)B * TOPK_TC_THREADS * sizeof(float), 256);
+  const size_t surv_max = (size_t)B * TOPK_TC_MAX_STREAMS * TOPK_TC_KEEP;
+  float* st_v = reinterpret_cast<float*>(w8); w8 += align_up(surv_max * sizeof(float), 256);
+  int* st_i = reinterpret_cast<int*>(w8); w8 += align_up(surv_max * sizeof(int), 256);
+  float* st_u = reinterpret_cast<float*>(w8); w8 += align_up((size_t)B * TOPK_TC_MAX_STREAMS * sizeof(float), 256);
   float* bound = reinterpret_cast<float*>(w8);
 
-  static const bool trace_host = getenv("GIC_TRACE_HOST") != nullptr;
-  auto now = [] { return std::chrono::steady_clock::now(); };
-  auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
-  const auto t0 = now();
   ActOut qo; qo.hi = q_hi; qo.lo = q_lo;
   GIC_TRY(launch_convert(q, qo, (size_t)B * D, st));
-  const auto t1 = now();
-  double t_enc = 0, t_gemm = 0, t_scan = 0;
+  // one bf16x2 GEMM over the whole database, scores consumed in the epilogue
   GemmBf16Args g;
-  g.no_pdl = 1;  // plain stream order: these launches alternate with ordinary <<<>>> launches on the caller's stream
+  g.no_pdl = 1;  // plain stream order: its neighbours are ordinary <<<>>> launches on the caller's stream
+  int bn = 128, pair = 0;
+  gemm_bf16_pick(B, N, D, 1, 1, &bn, &pair);
+  if (!pair) bn = 128;  // (single CTAs: the fused epilogue exists for the 128-column bf16x2 tile)
   GIC_TRY(make_tma_2d_bf16(&g.a_hi, q_hi, B, D, D, 128));
   GIC_TRY(make_tma_2d_bf16(&g.a_lo, q_lo, B, D, D, 128));
-  for (long base = 0; base < N; base += TOPK_CHUNK) {
-    const int rows = (int)((N - base) < TOPK_CHUNK ? (N - base) : TOPK_CHUNK);
-    const auto c0 = now();
-    // tile shape from the GEMM cost model (round 2: the bf16x2 kernels have wide tiles and CTA pairs; 64-column tiles ran this scan
-    // at 166 TFLOP/s); a ragged last chunk takes single CTAs (pairs need whole 32-column groups and aligned rows)
-    int bn = 64, pair = 0;
-    gemm_bf16_pick(B, rows, D, 1, 1, &bn, (rows % 32 == 0) ? &pair : nullptr);
-    GIC_TRY(make_tma_2d_bf16(&g.w_hi, db_hi + (size_t)base * D, rows, D, D, pair ? bn / 2 : bn));
-    GIC_TRY(make_tma_2d_bf16(&g.w_lo, db_lo + (size_t)base * D, rows, D, D, pair ? bn / 2 : bn));
-    const auto c1 = now();
-    g.M = B; g.N = rows; g.K = D; g.block_n = bn; g.pair = pair; g.split = 1; g.epilogue = EPI_NONE; g.bias = nullptr;
-    g.out = ActOut(); g.out.f32 = chunk_scores; g.ld_out = rows;
-    GIC_TRY(launch_gemm_bf16(g, st));
-    const auto c2 = now();
-    topk_tc_scan_kernel<<<B, TOPK_TC_THREADS, 0, st>>>(chunk_scores, rows, (int)base, base == 0 ? 1 : 0, st_v, st_i, st_u);
-    GIC_CHECK_CUDA(cudaGetLastError());
-    note_launch();
-    const auto c3 = now();
-    t_enc += us(c0, c1); t_gemm += us(c1, c2); t_scan += us(c2, c3);
-  }
-  const auto t2 = now();
-  topk_tc_select_kernel<<<B, TOPK_TC_THREADS, 0, st>>>(st_v, st_i, st_u, cand_score, cand_idx, bound);
+  GIC_TRY(make_tma_2d_bf16(&g.w_hi, db_hi, N, D, D, pair ? bn / 2 : bn));
+  GIC_TRY(make_tma_2d_bf16(&g.w_lo, db_lo, N, D, D, pair ? bn / 2 : bn));
+  const int streams = gemm_topk_streams(B, N, bn, pair);
+  GIC_REQUIRE(streams <= TOPK_TC_MAX_STREAMS, "topk_ip_tc: %d candidate streams exceed the workspace layout", streams);
+  g.M = B; g.N = N; g.K = D; g.block_n = bn; g.pair = pair; g.split = 1; g.epilogue = EPI_NONE; g.bias = nullptr;
+  g.topk_v = st_v; g.topk_i = st_i; g.topk_u = st_u; g.topk_streams = streams;
+  GIC_TRY(launch_gemm_bf16(g, st));
+  const size_t sel_smem = (size_t)streams * TOPK_TC_KEEP * (sizeof(float) + sizeof(int));
+  topk_tc_select_kernel<<<B, TOPK_TC_THREADS, sel_smem, st>>>(st_v, st_i, st_u, streams, cand_score, cand_idx, bound);
   GIC_CHECK_CUDA(cudaGetLastError());
   note_launch();
   GIC_CHECK_CUDA(cudaMemsetAsync(flags + B, 0, sizeof(int), st));
@@ -412,9 +371,6 @@ int launch_topk_ip_tc(const float* q, const float* db, const bf16* db_hi, const 
   topk_exact_row_kernel<TOPK_TC_MAXK><<<B, fthreads, fsmem, st>>>(q, db, (long)N, D, k, flags, scores, idx);
   GIC_CHECK_CUDA(cudaGetLastError());
   note_launch();
-  if (trace_host)
-    fprintf(stderr, "topk_ip_tc host us: convert %.0f | chunks %.0f (encode %.0f gemm-launch %.0f scan-launch %.0f) | tail %.0f\n", us(t0, t1), us(t1, t2), t_enc,
-            t_gemm, t_scan, us(t2, now()));
   return GIC_OK;
 }
 
