@@ -796,7 +796,9 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
     const char* sk = getenv("GIC_SPLITK");
     // off unless GIC_SPLITK=1 in both tensor-core modes: measured again in round 2 for bf16x2, whose fc2 main loop is 2.5x longer
     // (profiles/r2f_splitk.txt): 29.2 us with the 3-way K split against 22.6 us unsplit -- the parked-partials reduction costs more than
-    // the shorter main loop saves
+    // the shorter main loop saves.  The cooperative reduction (every slice finishes a share of the tile; CTA pairs allowed) brings the
+    // split to 23.5 us -- still not below the unsplit pair kernel: 144 CTAs x 64 KB of partials make ~9 MB of L2 writes + reads per launch
+    // (profiles/r2n_splitk_coop_microbench.txt)
     e->use_splitk = sk && sk[0] == '1';
     const char* hf = getenv("GIC_LNF_FUSE");
     e->fuse_lnf = e->fuse_ln && !e->split && hf && hf[0] == '1';

@@ -230,6 +230,7 @@ struct alignas(64) GemmKernelParams {
   // split-K (see launch_gemm_bf16): `split_k` CTAs share one output tile, each over K / split_k; fp32 partials go to splitk_ws
   // [split_k][M][N] and the CTA that arrives last at splitk_counters[tile] sums them in split order and runs the epilogue
   int split_k; float* splitk_ws; int* splitk_counters;
+  int splitk_coop;  // every work item has its own CTA: the K slices of a tile finish it together (see the epilogue)
   int w_static;  // W may be fetched before griddepcontrol.wait (see the kernel)
   StepTrace step_trace;  // in-situ timeline (common.cuh); null buffer = off
   float2* stats_out;  // [ceil(N / 32)][ln_stats_ld] (sum, sum of squares) of the values written, per row and 32-column chunk
@@ -312,7 +313,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   const int m_units = PAIR ? (m_tiles + 1) / 2 : m_tiles, m_per_unit = PAIR ? 2 : 1;
   const int total_tiles = m_units * n_tiles;
   const int nk = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
-  const int total_work = total_tiles * p.split_k;  // work item w: tile = w % total_tiles, K slice = w / total_tiles
+  // work item w: tile = w / split_k, K slice = w % split_k -- the slices of a tile are consecutive CTAs (launched, and so resident,
+  // together: the cooperative reduction below waits for them)
+  const int total_work = total_tiles * p.split_k;
   const int work0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, work_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   pdl_launch_dependents();  // let the next kernel's CTAs be scheduled behind this grid (see common.cuh)
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
@@ -352,21 +355,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
   // (w_static: the caller vouches that W was not written by the kernel launched just before this one)
   uint32_t pre = 0;
   constexpr bool PAIR_PRELOAD = GIC_PAIR_PRELOAD != 0;
-  if ((!PAIR || PAIR_PRELOAD) && warp == 0 && p.w_static && p.split_k == 1 && work0 < total_work) {
-    pre = (uint32_t)(nk < STAGES ? nk : STAGES);
+  if ((!PAIR || PAIR_PRELOAD) && warp == 0 && p.w_static && work0 < total_work) {
+    const int ks0 = work0 % p.split_k;
+    const int kb0 = (int)((long)ks0 * nk / p.split_k), nk0 = (int)((long)(ks0 + 1) * nk / p.split_k) - kb0;  // this CTA's first K slice
+    pre = (uint32_t)(nk0 < STAGES ? nk0 : STAGES);
     if (ptx::elect_one()) {
-      const int n0 = ((work0 % total_tiles) / m_units) * BLOCK_N;
+      const int n0 = (((work0 / p.split_k) % total_tiles) / m_units) * BLOCK_N;
       for (uint32_t ps = 0; ps < pre; ++ps) {
         const uint32_t fb = full_bar + 8 * ps;
         const uint32_t st = smem_base + ps * Tile::STAGE_BYTES;
+        const int kc = (kb0 + (int)ps) * GEMM_BLOCK_K;
         if (PAIR) {  // (both CTAs' barriers exist: the cluster barrier above)
           if (rank == 0) ptx::mbar_expect_tx(fb, 2 * Tile::STAGE_BYTES);
-          ptx::tma_load_2d_pair(st + Tile::A_BYTES, &p.w_hi, fb, (int)ps * GEMM_BLOCK_K, n0 + (int)rank * (BLOCK_N / 2));
-          if (SPLIT) ptx::tma_load_2d_pair(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, fb, (int)ps * GEMM_BLOCK_K, n0 + (int)rank * (BLOCK_N / 2));
+          ptx::tma_load_2d_pair(st + Tile::A_BYTES, &p.w_hi, fb, kc, n0 + (int)rank * (BLOCK_N / 2));
+          if (SPLIT) ptx::tma_load_2d_pair(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, fb, kc, n0 + (int)rank * (BLOCK_N / 2));
         } else {
           ptx::mbar_expect_tx(fb, Tile::STAGE_BYTES);
-          ptx::tma_load_2d(st + Tile::A_BYTES, &p.w_hi, fb, (int)ps * GEMM_BLOCK_K, n0);
-          if (SPLIT) ptx::tma_load_2d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, fb, (int)ps * GEMM_BLOCK_K, n0);
+          ptx::tma_load_2d(st + Tile::A_BYTES, &p.w_hi, fb, kc, n0);
+          if (SPLIT) ptx::tma_load_2d(st + 2 * Tile::A_BYTES + Tile::W_BYTES, &p.w_lo, fb, kc, n0);
         }
       }
     }
@@ -379,7 +385,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     // ===== TMA producer: streams k-blocks of successive tiles through the ring without pausing at tile boundaries =====
     uint32_t s = 0, ph = 0, it = 0;
     for (int work = work0; work < total_work; work += work_stride) {
-      const int tile = work % total_tiles, ks = work / total_tiles;
+      const int tile = work / p.split_k, ks = work % p.split_k;
       const int m0 = ((tile % m_units) * m_per_unit + (int)rank) * GEMM_BLOCK_M, n0 = (tile / m_units) * BLOCK_N;
       const int kb_end = (int)((long)(ks + 1) * nk / p.split_k);
       for (int kb = (int)((long)ks * nk / p.split_k); kb < kb_end; ++kb, ++it) {
@@ -423,7 +429,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
     constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * GEMM_BLOCK_M : GEMM_BLOCK_M, BLOCK_N);
     uint32_t s = 0, ph = 0, it = 0, local = 0;
     for (int work = (PAIR && rank != 0) ? total_work : work0; work < total_work; work += work_stride, ++local) {  // (pair: the leader only)
-      const int ks = work / total_tiles;
+      const int ks = work % p.split_k;
       const int kb_begin = (int)((long)ks * nk / p.split_k), kb_end = (int)((long)(ks + 1) * nk / p.split_k);
       const uint32_t acc = local & 1, use = local >> 1;
       ptx::mbar_wait(tmem_empty_bar + 8 * acc, (use & 1) ^ 1);  // epilogue has drained this accumulator (passes at first use)
@@ -491,7 +497,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
       for (int j = 0; j < GEMM_TOPK_KEEP; ++j) { tk_v[j] = -INFINITY; tk_i[j] = -1; }
     }
     for (int work = work0; work < total_work; work += work_stride, ++local) {
-      const int tile = work % total_tiles, ks = work / total_tiles;
+      const int tile = work / p.split_k, ks = work % p.split_k;
       const uint32_t acc = local & 1, use = local >> 1;
       const int n_tile = tile / m_units;
       const int m0 = ((tile % m_units) * m_per_unit + (int)rank) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
@@ -694,7 +700,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
       // operands of a chunk that do not depend on the accumulator (residual in the coalesced layout, bias, column sums) are
       // requested one chunk ahead: the first chunk's before the accumulator wait, chunk c+1's while chunk c is processed
       float4 res_n[8], b4_n = make_float4(0.f, 0.f, 0.f, 0.f), cs4_n = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto prefetch = [&](int c0) {
+      auto prefetch = [&](int wrow, int c0) {  // wrow: first row of the 32-row band
         const int col0 = n0 + c0, col = col0 + cchunk * 4;
         b4_n = make_float4(0.f, 0.f, 0.f, 0.f);
         cs4_n = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -703,7 +709,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           if (EPI == EPI_RESIDUAL) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int row = min(wrow0 + crow0 + 4 * i, p.M - 1);  // clamped: rows >= M are never stored
+              const int row = min(wrow + crow0 + 4 * i, p.M - 1);  // clamped: rows >= M are never stored
               res_n[i] = __ldcg(reinterpret_cast<const float4*>(p.out_f32 + (size_t)row * p.ld_f32 + col));
             }
           }
@@ -713,7 +719,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           if (EPI == EPI_RESIDUAL) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const int row = wrow0 + crow0 + 4 * i;
+              const int row = wrow + crow0 + 4 * i;
               res_n[i] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (row < p.M) {
                 const float* src = p.out_f32 + (size_t)row * p.ld_f32 + col;
@@ -738,14 +744,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           }
         }
       };
-      // split-K: phase 0 parks this CTA's raw fp32 partial tile in the workspace; the CTA that arrives last at the tile's
-      // counter runs phase 1 = the normal epilogue on the sum of all partials (added in split order: deterministic)
+      // split-K: phase 0 parks this CTA's raw fp32 partial tile in the workspace; phase 1 = the normal epilogue on the sum of all
+      // partials (added in split order: deterministic).  Cooperative form (p.splitk_coop: every work item has its own resident CTA):
+      // the split_k CTAs of a tile wait for each other at the tile's counter and then EACH finishes its share of the tile's
+      // 32 x 32 units (unit u = 4 * column chunk + row quarter belongs to slice u % split_k and to that CTA's warp (u / split_k) % 8),
+      // so reduction, epilogue math and stores of a tile are spread over split_k SMs.  Otherwise the CTA that arrives last does all of it.
       const bool split = EPI == EPI_RESIDUAL && p.split_k > 1;  // (the K split is offered for the residual GEMMs only)
+      const bool coop = split && p.splitk_coop != 0;
+      int* const sk_counter = split ? p.splitk_counters + (PAIR ? tile * 2 + (int)rank : tile) : nullptr;
       const uint32_t tmem_acc = tmem_base + acc * Tile::ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
       for (int phase = 0; phase < (split ? 2 : 1); ++phase) {
       const bool to_ws = split && phase == 0, from_ws = split && phase == 1;
-      if (!to_ws && sub * 32 < BLOCK_N) prefetch(sub * 32);
+      const bool by_unit = from_ws && coop;  // this phase walks the units this CTA owns instead of the warp's TMEM chunks
+      if (!to_ws && !by_unit && sub * 32 < BLOCK_N) prefetch(wrow0, sub * 32);
       if (phase == 0) {
         ptx::mbar_wait(tmem_full_bar + 8 * acc, use & 1);
         ptx::tc_fence_after();
@@ -756,7 +768,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         }
       }
 #pragma unroll 1
-      for (int c0 = sub * 32; c0 < BLOCK_N; c0 += 64) {
+      for (int itc = 0;; ++itc) {
+        int c0, wrow;  // this iteration's 32-column chunk of the tile and the first row of its 32-row band
+        if (by_unit) {
+          const int u = ks + p.split_k * (e + GEMM_EPI_WARPS * itc);
+          if (u >= 4 * (BLOCK_N / 32)) break;
+          c0 = (u >> 2) * 32;
+          wrow = m0 + (u & 3) * 32;
+          prefetch(wrow, c0);
+        } else {
+          c0 = sub * 32 + 64 * itc;
+          if (c0 >= BLOCK_N) break;
+          wrow = wrow0;
+        }
         const int col0 = n0 + c0, col = col0 + cchunk * 4;
         const bool tr = tracing && e == 0 && lane == 0 && local == 0 && c0 < 128;
         long long* trc = p.trace + 540 + (c0 >> 6) * 8;
@@ -769,7 +793,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           for (int i = 0; i < 8; ++i) res[i] = res_n[i];
         }
         const float4 b4 = b4_n, cs4 = cs4_n;
-        if (!to_ws && c0 + 64 < BLOCK_N) prefetch(c0 + 64);
+        if (!to_ws && !by_unit && c0 + 64 < BLOCK_N) prefetch(wrow0, c0 + 64);
         if (!from_ws) {
           uint32_t r[32];
           ptx::tmem_ld_32x32(tmem_acc + (uint32_t)c0, r);
@@ -794,7 +818,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         if (fast) {
           // ---- specialised path: OUT / EPI / FOLD are compile-time, so this is a few instructions per element ----
           if (tr) trc[3] = clock64() - t_start + (long long)(b4.x * 0.f);
-          const size_t rowoff = (size_t)(wrow0 + crow0);
+          const size_t rowoff = (size_t)(wrow + crow0);
           constexpr bool W_F32 = OUT == OUT_F32 || OUT == OUT_F32_BF16_STATS || OUT == OUT_F32_BF16X2_STATS;
           constexpr bool W_HI = OUT == OUT_BF16 || OUT == OUT_BF16X2 || OUT == OUT_F32_BF16_STATS || OUT == OUT_F16 || OUT == OUT_F32_BF16X2_STATS;
           constexpr bool W_LO = OUT == OUT_BF16X2 || OUT == OUT_F32_BF16X2_STATS;
@@ -815,8 +839,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           }
           if (split) {
             // (split-K runs on whole, aligned tiles only -- launch_gemm_bf16 checks -- so every chunk takes this path)
-            const int rows_ok = min(32, p.M - wrow0);
-            float* wsp = p.splitk_ws + ((size_t)(wrow0 + crow0)) * p.N + col;
+            const int rows_ok = min(32, p.M - wrow);
+            float* wsp = p.splitk_ws + ((size_t)(wrow + crow0)) * p.N + col;
             const size_t ws_row4 = (size_t)4 * p.N, ws_split = (size_t)p.M * p.N;
             if (to_ws) {
 #pragma unroll
@@ -851,7 +875,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           }
           if (tr) trc[5] = clock64() - t_start + (long long)(o[7].w * 0.f);  // math done (residual / bias operands have arrived)
           // rows of this warp's band that exist: all 32 unless this is the ragged last row tile (warp-uniform count)
-          const int rows_here = min(32, p.M - wrow0);
+          const int rows_here = min(32, p.M - wrow);
           if (EPI == EPI_ARGMAX) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -926,7 +950,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           const bool full4 = col + 3 < p.N;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int lr = crow0 + 4 * i, row = wrow0 + lr;
+            const int lr = crow0 + 4 * i, row = wrow + lr;
             float4 o = stage[lr * 8 + (cchunk ^ (lr & 7))];
             if (fold) {
               o.x = rstd[i] * (o.x - mean[i] * cs4.x);
@@ -982,7 +1006,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
               rsum[i] += __shfl_xor_sync(0xffffffffu, rsum[i], o);
               rsq[i] += __shfl_xor_sync(0xffffffffu, rsq[i], o);
             }
-            const int row = wrow0 + crow0 + 4 * i;
+            const int row = wrow + crow0 + 4 * i;
             if (cchunk == 0 && row < p.M) p.stats_out[(size_t)(col0 >> 5) * p.ln_stats_ld + row] = make_float2(rsum[i], rsq[i]);
             rsum[i] = 0.f;
             rsq[i] = 0.f;
@@ -991,19 +1015,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
         if (tr) trc[4] = clock64() - t_start;
       }
       if (to_ws) {
-        // publish the partial, count arrivals at this tile; only the last CTA goes on to phase 1
+        // publish the partial and count arrivals at this tile
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps
-        if (e == 0 && lane == 0) {
-          const int old = atomicAdd(p.splitk_counters + tile, 1);
-          *s_flag = (old == p.split_k - 1) ? 1 : 0;
-          if (old == p.split_k - 1) p.splitk_counters[tile] = 0;  // self-cleaning: ready for the next launch
+        if (coop) {
+          // cooperative: wait until every K slice of the tile has been parked (low half of the counter = arrivals); all of them go on
+          if (e == 0 && lane == 0) {
+            atomicAdd(sk_counter, 1);
+            int seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(sk_counter) : "memory");
+            } while ((seen & 0xffff) < p.split_k);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          __threadfence();
+        } else {
+          // only the CTA that arrives last goes on to phase 1
+          if (e == 0 && lane == 0) {
+            const int old = atomicAdd(sk_counter, 1);
+            *s_flag = (old == p.split_k - 1) ? 1 : 0;
+            if (old == p.split_k - 1) *sk_counter = 0;  // self-cleaning: ready for the next launch
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          const int last = *s_flag;
+          asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read the flag before a later tile may overwrite it
+          if (!last) break;
+          __threadfence();
         }
+      } else if (by_unit) {
+        // departures in the high half; the last CTA to leave has seen every partner finish reading and re-arms the counter for the next launch
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const int last = *s_flag;
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read the flag before a later tile may overwrite it
-        if (!last) break;
-        __threadfence();
+        if (e == 0 && lane == 0) {
+          const int old = atomicAdd(sk_counter, 0x10000);
+          if ((old >> 16) == p.split_k - 1) *sk_counter = 0;
+        }
       }
       }  // phase
       // per-(tile, column-parity) argmax partials of each row
@@ -1248,6 +1293,12 @@ int gemm_bf16_configure() {
   return GIC_OK;
 }
 
+// GIC_SPLITK_COOP=0: every K split falls back to the last-arriver reduction (measurement / tests)
+static bool splitk_coop_disabled() {
+  static const bool off = [] { const char* v = getenv("GIC_SPLITK_COOP"); return v && v[0] == '0'; }();
+  return off;
+}
+
 static thread_local bool g_gemm_no_pdl = false;  // set by launch_gemm_bf16 from GemmBf16Args::no_pdl for the launch it issues
 
 template <int BLOCK_N, bool SPLIT, int EPI, int OUT, bool FOLD, bool RAGGED>
@@ -1262,11 +1313,13 @@ static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
     const int m_units = ceil_div(kp.M, GEMM_BLOCK_M);
     grid.x = (unsigned)(kp.topk_streams / 2 * m_units);
   }
+  GemmKernelParams kq = kp;
+  kq.splitk_coop = (kp.split_k > 1 && tiles <= sms && !splitk_coop_disabled()) ? 1 : 0;  // one resident CTA per work item
   if (g_gemm_no_pdl) {
-    kern<<<grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st>>>(kp);
+    kern<<<grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st>>>(kq);
     GIC_CHECK_CUDA(cudaGetLastError());
   } else {
-    GIC_CHECK_CUDA(launch_kernel(kern, grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st, kp));
+    GIC_CHECK_CUDA(launch_kernel(kern, grid, dim3(GEMM_THREADS), (size_t)Tile::SMEM_BYTES, st, kq));
   }
   note_launch();
   return GIC_OK;
@@ -1288,8 +1341,10 @@ static int launch_one_pair(const GemmKernelParams& kp, cudaStream_t st) {
     if (cudaOccupancyMaxActiveClusters(&n, kern, &q) != cudaSuccess || n <= 0) { cudaGetLastError(); n = gemm_num_sms() / 2; }
     max_pairs = n;
   }
-  const long units = (long)(ceil_div(kp.M, GEMM_BLOCK_M) / 2) * ceil_div(kp.N, BLOCK_N);
+  const long units = (long)(ceil_div(kp.M, GEMM_BLOCK_M) / 2) * ceil_div(kp.N, BLOCK_N) * kp.split_k;
   long pairs = units < max_pairs ? units : max_pairs;
+  GemmKernelParams kq = kp;
+  kq.splitk_coop = (kp.split_k > 1 && units <= max_pairs && !splitk_coop_disabled()) ? 1 : 0;  // one resident pair per work item
   if (EPI == EPI_TOPK) pairs = (long)(kp.topk_streams / 2) * (ceil_div(kp.M, GEMM_BLOCK_M) / 2);  // row-tile-stationary pairs
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * pairs));
@@ -1308,7 +1363,7 @@ static int launch_one_pair(const GemmKernelParams& kp, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  GIC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, kp));
+  GIC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, kq));
   note_launch();
   return GIC_OK;
 }
@@ -1427,7 +1482,6 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
     GIC_REQUIRE(ceil_div(a.K, GEMM_BLOCK_K) >= kp.split_k, "gemm_bf16: more K slices than k-blocks");
   }
   if (a.pair) {
-    GIC_REQUIRE(kp.split_k == 1, "gemm_bf16: CTA pairs take no K split");
     GIC_REQUIRE(ceil_div(a.M, GEMM_BLOCK_M) % 2 == 0, "gemm_bf16: CTA pairs need an even number of 128-row tiles (M = %d)", a.M);
     GIC_REQUIRE(out == OUT_NONE || (a.N % 32 == 0 && a.ld_out % 4 == 0), "gemm_bf16: CTA pairs need N %% 32 == 0 and aligned outputs");
     switch (a.block_n) {

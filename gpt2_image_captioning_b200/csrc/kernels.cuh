@@ -59,13 +59,15 @@ struct GemmBf16Args {
   int ln_parts = 0; long ln_stats_ld = 0; int ln_row_mul = 1, ln_row_off = 0;
   const float* ln_colsum = nullptr;  // [N] sum_k of the packed (bf16) gamma-folded weights
   float2* stats_out = nullptr;       // [ceil(N / 32)][ln_stats_ld]: per-row (sum, sum of squares) of the values this GEMM writes, per 32-column chunk
-  // split-K for short-and-wide problems (few output tiles, long K): split_k CTAs per tile, deterministic last-CTA reduction
   int w_static = 0;  // the weights were written long before this launch (engine weights): their first tiles may be fetched before
                      // griddepcontrol.wait, i.e. while the previous kernel is still finishing
   int no_pdl = 0;  // launch in plain stream order (no programmatic dependent launch): for callers outside the engine's launch chain, whose
                    // neighbours are ordinary <<<>>> launches (the retrieval scan)
   int pair = 0;  // CTA pairs: 256 x block_n tiles by two CTAs (cta_group::2); w_hi's box holds block_n / 2 rows
-  int split_k = 1; float* splitk_ws = nullptr;  /* [split_k][M][N] fp32 */  int* splitk_counters = nullptr;  /* [tiles], zero on entry and exit */
+  // split-K for short-and-wide problems (few output tiles, long K): split_k consecutive CTAs (or CTA pairs) per tile park fp32 partials in
+  // splitk_ws; summed in slice order (deterministic).  When every work item has its own resident CTA the slices of a tile wait for each
+  // other and each finishes its share of the tile (cooperative reduction), otherwise the CTA that arrives last does
+  int split_k = 1; float* splitk_ws = nullptr;  /* [split_k][M][N] fp32 */  int* splitk_counters = nullptr;  /* [2 * tiles], zero on entry and exit */
   long long* trace = nullptr;      // microbenchmark only: device buffer of >= 640 int64 for CTA 0's clock64 timeline
 };
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st);

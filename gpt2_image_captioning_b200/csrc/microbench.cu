@@ -52,6 +52,18 @@ __global__ void chase_kernel(const int* __restrict__ next, int start, int n, lon
   out[1] = p;
 }
 
+__device__ __forceinline__ float hash_unit(size_t i, unsigned seed) {  // (-1, 1)
+  unsigned long long x = (unsigned long long)i * 0x9E3779B97F4A7C15ull + seed * 0xD1B54A32D192ED03ull;
+  x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+  return (float)((int)(x & 0xffffff) - 0x800000) * (1.0f / 0x800000);
+}
+__global__ void fill_bf16(bf16* p, size_t n, unsigned seed, float scale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = __float2bfloat16_rn(scale * hash_unit(i, seed));
+}
+__global__ void fill_f32(float* p, size_t n, unsigned seed, float scale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = scale * hash_unit(i, seed);
+}
+
 template <typename F>
 static float time_loop(cudaStream_t st, int iters, F f) {
   cudaEvent_t a, b;
@@ -334,6 +346,78 @@ int main(int argc, char** argv) {
       printf("\n   epilogue warp 0 chunk 0: begin %lld tmem_loaded %lld staged %lld bias_arrived %lld math_done %lld stores_issued %lld chunk_done(stats) %lld\n", h_tr[540], h_tr[541],
              h_tr[542], h_tr[543], h_tr[545], h_tr[546], h_tr[544]);
     }
+    return 0;
+  }
+
+  // ---- mode 8: K split of the residual GEMMs (proj, fc2) with the cooperative reduction: every (operand mode, pair, tile width, split)
+  // timed back to back over rotating weight sets, and its h / hi / lo / statistics checked against the unsplit 64-wide launch ----
+  if (argc > 2 && atoi(argv[2]) == 8) {
+    bf16* a_lo = (bf16*)dmalloc((size_t)B * 4 * d * 2);
+    bf16* o_lo = (bf16*)dmalloc((size_t)B * 4 * d * 2);
+    bf16* wl = (bf16*)dmalloc((size_t)4 * d * d * 2);
+    float2* stats = (float2*)dmalloc((size_t)64 * B * 8);
+    float* skws = (float*)dmalloc((size_t)4 * B * d * 4);
+    int* skcnt = (int*)dmalloc(4096 * 4);
+    float* h0 = (float*)dmalloc((size_t)B * d * 4);
+    fill_bf16<<<512, 256, 0, st>>>(a, (size_t)B * 4 * d, 1u, 1.0f);
+    fill_bf16<<<512, 256, 0, st>>>(a_lo, (size_t)B * 4 * d, 2u, 1.0f / 256);
+    fill_bf16<<<512, 256, 0, st>>>(w_proj[0], (size_t)d * d, 3u, 0.05f);
+    fill_bf16<<<512, 256, 0, st>>>(w_fc2[0], (size_t)4 * d * d, 4u, 0.05f);
+    fill_bf16<<<512, 256, 0, st>>>(wl, (size_t)4 * d * d, 5u, 0.05f / 256);
+    fill_f32<<<512, 256, 0, st>>>(h0, (size_t)B * d, 6u, 1.0f);
+    fill_f32<<<512, 256, 0, st>>>(bias, (size_t)4 * d, 7u, 0.1f);
+    CK(cudaStreamSynchronize(st));
+    std::vector<float> ref_h((size_t)B * d), got_h((size_t)B * d);
+    std::vector<float2> ref_st((size_t)(d / 32) * B), got_st((size_t)(d / 32) * B);
+    std::vector<uint16_t> ref_hi((size_t)B * d), got_hi((size_t)B * d), ref_lo((size_t)B * d), got_lo((size_t)B * d);
+    struct Shape { const char* name; bf16* W; int K; };
+    Shape shapes[] = {{"proj", w_proj[0], d}, {"fc2", w_fc2[0], 4 * d}};
+    for (int x2 = 1; x2 >= 0; --x2)
+      for (const Shape& sh : shapes) {
+        bool have_ref = false;
+        for (int pair = 0; pair < 2; ++pair)
+          for (int bn : {64, 128, 192, 256})
+            for (int sk = 1; sk <= 4; ++sk) {
+              if (!pair && x2 && bn > 128) continue;
+              if (pair && ((B + 127) / 128) % 2) continue;
+              if (sk > 1 && bn < 128) continue;
+              const long work = (long)((B + 127) / 128) * ((d + bn - 1) / bn) * sk;
+              if (sk > 1 && work > 148) continue;
+              GemmBf16Args g;
+              OK(make_tma_2d_bf16(&g.a_hi, a, B, sh.K, sh.K, 128));
+              OK(make_tma_2d_bf16(&g.a_lo, a_lo, B, sh.K, sh.K, 128));
+              OK(make_tma_2d_bf16(&g.w_hi, sh.W, d, sh.K, sh.K, pair ? bn / 2 : bn));
+              OK(make_tma_2d_bf16(&g.w_lo, wl, d, sh.K, sh.K, pair ? bn / 2 : bn));
+              g.M = B; g.N = d; g.K = sh.K; g.block_n = bn; g.split = x2; g.epilogue = EPI_RESIDUAL; g.bias = bias; g.ld_out = d; g.pair = pair; g.w_static = 1;
+              g.out.f32 = h; g.out.hi = o; g.out.lo = x2 ? o_lo : nullptr; g.stats_out = stats; g.ln_stats_ld = B;
+              if (sk > 1) { g.split_k = sk; g.splitk_ws = skws; g.splitk_counters = skcnt; }
+              CK(cudaMemcpyAsync(h, h0, (size_t)B * d * 4, cudaMemcpyDeviceToDevice, st));
+              OK(launch_gemm_bf16(g, st));
+              std::vector<float>& dst_h = have_ref ? got_h : ref_h;
+              std::vector<float2>& dst_st = have_ref ? got_st : ref_st;
+              std::vector<uint16_t>& dst_hi = have_ref ? got_hi : ref_hi; std::vector<uint16_t>& dst_lo = have_ref ? got_lo : ref_lo;
+              CK(cudaMemcpyAsync(dst_h.data(), h, (size_t)B * d * 4, cudaMemcpyDeviceToHost, st));
+              CK(cudaMemcpyAsync(dst_st.data(), stats, (size_t)(d / 32) * B * 8, cudaMemcpyDeviceToHost, st));
+              CK(cudaMemcpyAsync(dst_hi.data(), o, (size_t)B * d * 2, cudaMemcpyDeviceToHost, st));
+              if (x2) CK(cudaMemcpyAsync(dst_lo.data(), o_lo, (size_t)B * d * 2, cudaMemcpyDeviceToHost, st));
+              CK(cudaStreamSynchronize(st));
+              double err_h = 0, err_st = 0, mag = 0; long bad_hi = 0;
+              if (have_ref) {
+                for (size_t i = 0; i < ref_h.size(); ++i) { err_h = fmax(err_h, fabs((double)got_h[i] - ref_h[i])); mag = fmax(mag, fabs((double)ref_h[i])); }
+                for (size_t i = 0; i < ref_st.size(); ++i) err_st = fmax(err_st, fabs((double)got_st[i].x - ref_st[i].x) / (1.0 + fabs((double)ref_st[i].x)));
+                for (size_t i = 0; i < ref_hi.size(); ++i) bad_hi += (got_hi[i] != ref_hi[i]);
+              }
+              have_ref = true;
+              float us = time_loop(st, 120, [&](int) { OK(launch_gemm_bf16(g, st)); });
+              int cnt_bad = 0;
+              std::vector<int> hc(4096);
+              CK(cudaMemcpy(hc.data(), skcnt, 4096 * 4, cudaMemcpyDeviceToHost));
+              for (int v : hc) cnt_bad += (v != 0);
+              printf("splitk %s %-4s%s block_n=%3d split_k=%d (%3ld CTAs): %7.2f us   max|dh| %.2e of %.1f  stats rel %.1e  hi differs %ld  counters nonzero %d\n", x2 ? "x2  " : "bf16", sh.name,
+                     pair ? " pair" : "     ", bn, sk, work, us, err_h, mag, err_st, bad_hi, cnt_bad);
+              fflush(stdout);
+            }
+      }
     return 0;
   }
 
