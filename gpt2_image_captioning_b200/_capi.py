@@ -96,6 +96,8 @@ SIGNATURES = {
     "gic_test_gemm": (C.c_int, [C.c_int, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gic_test_layernorm": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_void_p]),
     "gic_test_attn_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "gic_test_attn_decode_beam": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_void_p]),
     "gic_test_attn_prefill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "gic_test_sample_top_p": (C.c_int, [_fp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_ulonglong, C.c_int, _fp, C.c_void_p]),
     "gic_trace_install": (C.c_int, [C.c_void_p, C.c_uint]),

@@ -638,6 +638,239 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
   trace_end(step_trace, tslot);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Beam-search decode attention with the image prefix read ONCE per image.  The `beams` hypotheses of an image share the
+// first n_prefix cached positions (the prefill row of the image, see INDIRECT above): at config 3 (prefix 40, 5 beams, <= 30 generated
+// tokens) those are 58-100 % of the keys every hypothesis walks, so one warp takes an (image, head) item and runs the beams as the ROWS of
+// the m16n8k16 tile: a prefix chunk (16 keys, contiguous) is scored against all beams at once, a generated chunk (16 positions of ONE
+// hypothesis, each from the cache row its ancestry table names) only counts for that hypothesis' row (the other rows are masked).
+// Per-row online softmax (FlashAttention-2 register reuse: the S accumulators become the A operand of P.V, split hi + lo).
+// Chunks land in a per-warp cp.async ring with the 16-byte columns XOR-swizzled by the key index, so ldmatrix (K) / ldmatrix.trans (V) read
+// true fragments without bank conflicts.  The new token of each hypothesis goes into the free slot of its last chunk and is appended to
+// its own cache row.  HF semantics unchanged: softmax over [prefix | own generated history | new token] (HF:models/gpt2/modeling_gpt2.py:
+// 144-226 with DynamicCache.reorder_cache replaced by the ancestry table).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int BEAM_ATTN_WARPS = 8, BEAM_ATTN_STAGES = 4;
+constexpr int BEAM_ATTN_SMEM = BEAM_ATTN_WARPS * BEAM_ATTN_STAGES * MMA_STAGE_BYTES + 128;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+template <bool F16>
+__global__ void __launch_bounds__(BEAM_ATTN_WARPS * 32, 1) attn_decode_beam_kernel(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, bf16* out_lo,
+                                                                                   const int* d_pos, int images, int nb, int H, int t_max, const int* anc,
+                                                                                   int anc_ld, int n_prefix, StepTrace step_trace) {
+  constexpr int STAGES = BEAM_ATTN_STAGES;
+  extern __shared__ uint8_t dec_smem_raw[];
+  const uint32_t smem_base = (dec_smem_u32(dec_smem_raw) + 127u) & ~127u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ring = smem_base + warp * (STAGES * MMA_STAGE_BYTES);
+  pdl_launch_dependents();
+  // zero the ring: slots no copy has filled are multiplied by P = 0 and must not hold NaN / Inf
+  for (int i = lane; i < STAGES * MMA_STAGE_BYTES / 16; i += 32)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(ring + i * 16), "r"(0u) : "memory");
+  __syncwarp();
+  pdl_wait();
+  const int tslot = trace_begin(step_trace, TRACE_ATTN_DECODE, 1);
+  const int pos = __ldcg(d_pos);       // positions already cached == position of the new token
+  const int ngen = pos - n_prefix;     // cached generated positions of every hypothesis
+  const int d = H * HD;
+  const int n_items = images * H;
+  const int wstride = gridDim.x * BEAM_ATTN_WARPS;
+  const int w0 = blockIdx.x * BEAM_ATTN_WARPS + warp;
+  const int nchp = (n_prefix + MMA_CHUNK - 1) / MMA_CHUNK;  // prefix chunks (shared by the beams)
+  const int nchg = ngen / MMA_CHUNK + 1;                    // chunks of one hypothesis' generated keys + its new token
+  const int nch = nchp + nb * nchg;
+  const int my_items = w0 < n_items ? (n_items - 1 - w0) / wstride + 1 : 0;
+  const int total_chunks = my_items * nch;
+  const int g = lane >> 2, t = lane & 3;
+  // this lane's copy pieces of a chunk: keys (lane >> 3) + 4 i, 16-byte column lane & 7 -> swizzled column (lane & 7) ^ (key & 7)
+  const int pj = lane >> 3, pc = lane & 7;
+
+  // producer cursor: item, chunk of the item, stage.  Cache rows of the generated keys this lane copies in the NEXT chunk to be issued
+  // are looked up one issue ahead (an L2 round trip that would otherwise sit in front of every generated chunk)
+  int p_item = w0, p_c = 0, p_s = 0;
+  int src_next[4];
+  auto lookup = [&](int item, int c) {
+    if (c < nchp) return;
+    const int img = item / H, gc = c - nchp, b = gc / nchg, k0 = (gc - b * nchg) * MMA_CHUNK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int gk = k0 + pj + 4 * i;
+      src_next[i] = gk < ngen ? __ldcg(anc + (size_t)(img * nb + b) * anc_ld + gk) : -1;
+    }
+  };
+  auto issue_next = [&]() {
+    const int img = p_item / H, h = p_item - img * H;
+    const uint32_t dst = ring + p_s * MMA_STAGE_BYTES;
+    if (p_c < nchp) {
+      const int k0 = p_c * MMA_CHUNK, nkeys = min(MMA_CHUNK, n_prefix - k0);
+      const size_t base = (((size_t)img * nb) * H + h) * t_max;  // the image's prefill row
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = pj + 4 * i;
+        if (j < nkeys) {
+          const size_t off = (base + k0 + j) * HD + pc * 8;
+          const uint32_t o = (uint32_t)(j * (HD * 2) + ((pc ^ (j & 7)) << 4));
+          cp_async16(dst + o, kcache + off);
+          cp_async16(dst + MMA_CHUNK * HD * 2 + o, vcache + off);
+        }
+      }
+    } else {
+      const int gc = p_c - nchp, b = gc / nchg, k0 = (gc - b * nchg) * MMA_CHUNK;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = pj + 4 * i;
+        if (src_next[i] >= 0) {  // (k0 + j < ngen)
+          const size_t off = ((((size_t)src_next[i]) * H + h) * t_max + n_prefix + k0 + j) * HD + pc * 8;
+          const uint32_t o = (uint32_t)(j * (HD * 2) + ((pc ^ (j & 7)) << 4));
+          cp_async16(dst + o, kcache + off);
+          cp_async16(dst + MMA_CHUNK * HD * 2 + o, vcache + off);
+        }
+      }
+    }
+    if (++p_c == nch) { p_c = 0; p_item += wstride; }
+    if (++p_s == STAGES) p_s = 0;
+    if (p_item < n_items) lookup(p_item, p_c);
+  };
+  int issued = 0;
+  if (my_items > 0) lookup(w0, 0);
+  for (; issued < STAGES - 1; ++issued) {
+    if (issued < total_chunks) issue_next();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
+  // q of the item's hypotheses as A fragments (row g = beam g; rows >= nb zero), requested one item ahead
+  uint32_t qa_n[8];
+  auto load_q = [&](int item) {
+    const int img = item / H, h = item - img * H;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) qa_n[j] = 0u;
+    if (g < nb) {
+      const uint32_t* q32 = reinterpret_cast<const uint32_t*>(qkv + (size_t)(img * nb + g) * 3 * d + h * HD);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        qa_n[2 * ks] = __ldcg(q32 + 8 * ks + t);          // dims 16 ks + 2 t, + 1
+        qa_n[2 * ks + 1] = __ldcg(q32 + 8 * ks + 4 + t);  // dims 16 ks + 8 + 2 t, + 1
+      }
+    }
+  };
+  if (my_items > 0) load_q(w0);
+  const int r8 = lane & 7, mlo = (lane >> 3) & 1, mhi = lane >> 4;
+  const uint32_t k_row_off = (uint32_t)((8 * mhi + r8) * (HD * 2));
+  const uint32_t v_row_off = (uint32_t)(MMA_CHUNK * HD * 2 + (8 * mlo + r8) * (HD * 2));
+  int c_s = 0;
+  for (int ii = 0; ii < my_items; ++ii) {
+    const int item = w0 + ii * wstride;
+    const int img = item / H, h = item - img * H;
+    uint32_t qa[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qa[i] = scale_eighth<F16>(qa_n[i]);
+    if (ii + 1 < my_items) load_q(item + wstride);
+    // the hypotheses' new k / v rows: 16 pieces of 16 bytes per beam (8 of k, 8 of v), piece lane + 32 i
+    uint4 newkv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int pi = lane + 32 * i, b = pi >> 4;
+      if (b < nb) newkv[i] = __ldcg(reinterpret_cast<const uint4*>(qkv + (size_t)(img * nb + b) * 3 * d + d + ((pi >> 3) & 1) * d + h * HD) + (pi & 7));
+    }
+    float m = -INFINITY, l = 0.f;  // row g: running maximum (uniform over the quad) and this lane's share of the running sum
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] = 0.f; o[j][1] = 0.f; o[j][2] = 0.f; o[j][3] = 0.f; }
+    for (int c = 0; c < nch; ++c) {
+      if (issued < total_chunks) issue_next();
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      ++issued;
+      const uint32_t st = ring + c_s * MMA_STAGE_BYTES;
+      // which rows this chunk counts for, how many key slots it fills
+      int beam = -1, nkeys;
+      if (c < nchp) {
+        nkeys = min(MMA_CHUNK, n_prefix - c * MMA_CHUNK);
+      } else {
+        const int gc = c - nchp;
+        beam = gc / nchg;
+        const int gch = gc - beam * nchg, cached = min(MMA_CHUNK, ngen - gch * MMA_CHUNK);
+        nkeys = cached;
+        if (gch == nchg - 1) {  // the hypothesis' new token: slot `cached` (< 16) of its last chunk, and its own cache row
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int pi = lane + 32 * i;
+            if ((pi >> 4) == beam) {
+              const int kv = (pi >> 3) & 1, cc = pi & 7;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + kv * (MMA_CHUNK * HD * 2) + cached * (HD * 2) + ((cc ^ (cached & 7)) << 4)),
+                           "r"(newkv[i].x), "r"(newkv[i].y), "r"(newkv[i].z), "r"(newkv[i].w) : "memory");
+              const size_t coff = ((((size_t)(img * nb + beam)) * H + h) * t_max + pos) * HD + cc * 8;
+              *reinterpret_cast<uint4*>((kv ? vcache : kcache) + coff) = newkv[i];  // append (HF:cache_utils.py:102-121)
+            }
+          }
+          nkeys = cached + 1;
+        }
+      }
+      asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+      __syncwarp();  // every lane's pieces of this chunk (and the new token's row) are visible
+      // ---- S = Q . K^T: rows = beams, 16 key slots ----
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b00, b01, b10, b11;
+        ldsm_x4(st + k_row_off + 16 * ((2 * ks + mlo) ^ r8), b00, b01, b10, b11);
+        mma_16816_top<F16>(s0[0], s0[1], s0[2], s0[3], qa[2 * ks], qa[2 * ks + 1], b00, b01);
+        mma_16816_top<F16>(s1[0], s1[1], s1[2], s1[3], qa[2 * ks], qa[2 * ks + 1], b10, b11);
+      }
+      const bool row_on = g < nb && (beam < 0 || beam == g);
+      const float x0 = (row_on && 2 * t < nkeys) ? s0[0] : -INFINITY, x1 = (row_on && 2 * t + 1 < nkeys) ? s0[1] : -INFINITY;
+      const float x2 = (row_on && 8 + 2 * t < nkeys) ? s1[0] : -INFINITY, x3 = (row_on && 9 + 2 * t < nkeys) ? s1[1] : -INFINITY;
+      float cm = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 1));
+      cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 2));
+      const float mn = fmaxf(m, cm);
+      const float mref = (mn == -INFINITY) ? 0.f : mn * LOG2E;  // rows this chunk (and all before it) do not count for: everything stays 0
+      const float scale = exp2f(m * LOG2E - mref);              // 0 while m = -inf
+      m = mn;
+      const float p0 = exp2f(fmaf(x0, LOG2E, -mref)), p1 = exp2f(fmaf(x1, LOG2E, -mref)), p2 = exp2f(fmaf(x2, LOG2E, -mref)), p3 = exp2f(fmaf(x3, LOG2E, -mref));
+      l = l * scale + ((p0 + p1) + (p2 + p3));
+      const float p0h = round_op<F16>(p0), p1h = round_op<F16>(p1), p2h = round_op<F16>(p2), p3h = round_op<F16>(p3);
+      const uint32_t a0h = pack_op2<F16>(p0h, p1h), a2h = pack_op2<F16>(p2h, p3h);
+      const uint32_t a0l = pack_op2<F16>(p0 - p0h, p1 - p1h), a2l = pack_op2<F16>(p2 - p2h, p3 - p3h);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o[j][0] *= scale; o[j][1] *= scale; }
+      // ---- O += P . V ----
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        uint32_t v00, v01, v10, v11;
+        ldsm_x4_trans(st + v_row_off + 16 * ((2 * jj + mhi) ^ r8), v00, v01, v10, v11);
+        mma_16816_top<F16>(o[2 * jj][0], o[2 * jj][1], o[2 * jj][2], o[2 * jj][3], a0h, a2h, v00, v01);
+        mma_16816_top<F16>(o[2 * jj + 1][0], o[2 * jj + 1][1], o[2 * jj + 1][2], o[2 * jj + 1][3], a0h, a2h, v10, v11);
+        mma_16816_top<F16>(o[2 * jj][0], o[2 * jj][1], o[2 * jj][2], o[2 * jj][3], a0l, a2l, v00, v01);
+        mma_16816_top<F16>(o[2 * jj + 1][0], o[2 * jj + 1][1], o[2 * jj + 1][2], o[2 * jj + 1][3], a0l, a2l, v10, v11);
+      }
+      __syncwarp();  // every lane is done reading this stage before the next iteration's copies may overwrite it
+      if (++c_s == STAGES) c_s = 0;
+    }
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    if (g < nb) {
+      const float inv = 1.0f / l;
+      bf16* orow = out + (size_t)(img * nb + g) * d + h * HD + 2 * t;
+      bf16* lrow = F16 ? out_lo + (size_t)(img * nb + g) * d + h * HD + 2 * t : nullptr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y0 = o[j][0] * inv, y1 = o[j][1] * inv;
+        const uint32_t yh = pack_bf16x2(y0, y1);
+        *reinterpret_cast<uint32_t*>(orow + 8 * j) = yh;
+        if (F16) {
+          const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yh));
+          *reinterpret_cast<uint32_t*>(lrow + 8 * j) = pack_bf16x2(y0 - yf.x, y1 - yf.y);
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  trace_end(step_trace, tslot);
+}
+
 static int g_dec_sms = 0;
 constexpr int DEC_PRODUCT_VARIANT = 12;  // mma.sync kernel, 12 warps x 4 stages (profiles/r1aa_microbench.txt)
 static int g_dec_variant = DEC_PRODUCT_VARIANT;  // microbenchmark / test knob (attn_decode_set_variant); < 0 = back to the product shape
@@ -658,6 +891,8 @@ int attn_decode_configure() {
   GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<12, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<12, 4>::SMEM_BYTES));
   GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<12, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<12, 4>::SMEM_BYTES));
   GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<12, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<12, 4>::SMEM_BYTES));
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_beam_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BEAM_ATTN_SMEM));
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_beam_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BEAM_ATTN_SMEM));
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
@@ -695,12 +930,34 @@ static int launch_attn_decode_bulk(const bf16* qkv, bf16* kcache, bf16* vcache, 
   return GIC_ERR_UNSUPPORTED;
 }
 
-// beam search without cache reordering (see attn_decode_mma_kernel INDIRECT)
+// GIC_BEAM_SHARED_PREFIX=0: every hypothesis walks its whole context on its own (attn_decode_mma_kernel INDIRECT; measurement / tests)
+static int g_beam_shared_override = -1;  // test knob (attn_decode_set_beam_shared): 0 / 1 force the kernel, < 0 = the environment's choice
+void attn_decode_set_beam_shared(int v) { g_beam_shared_override = v; }
+static bool beam_shared_prefix_enabled() {
+  if (g_beam_shared_override >= 0) return g_beam_shared_override != 0;
+  const char* v = getenv("GIC_BEAM_SHARED_PREFIX");  // (read per launch: the tests switch it inside one process)
+  return !(v && v[0] == '0');
+}
+
+// beam search without cache reordering (see attn_decode_mma_kernel INDIRECT and attn_decode_beam_kernel)
 int launch_attn_decode_indirect(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos, int rows, int H, int t_max, const int* anc,
                                 int anc_ld, int n_prefix, int beams, cudaStream_t st, bf16* out_lo) {
   GIC_TRY(attn_decode_configure());
   GIC_REQUIRE(anc != nullptr && beams >= 1 && n_prefix >= 0, "attn_decode_indirect: bad ancestry arguments");
   const int sms = cta_limit() > 0 && cta_limit() < g_dec_sms ? cta_limit() : g_dec_sms;
+  if (beam_shared_prefix_enabled() && beams >= 2 && beams <= 8 && rows % beams == 0) {
+    // the beams of an image as the rows of one MMA tile: the shared prefix is read once per image (attn_decode_beam_kernel)
+    const int images = rows / beams;
+    const int bgrid = min(sms, ceil_div(images * H, BEAM_ATTN_WARPS));
+    if (out_lo)
+      GIC_CHECK_CUDA(launch_kernel(attn_decode_beam_kernel<true>, dim3(bgrid), dim3(BEAM_ATTN_WARPS * 32), (size_t)BEAM_ATTN_SMEM, st, qkv, kcache, vcache, out, out_lo,
+                                   d_pos, images, beams, H, t_max, anc, anc_ld, n_prefix, trace_desc()));
+    else
+      GIC_CHECK_CUDA(launch_kernel(attn_decode_beam_kernel<false>, dim3(bgrid), dim3(BEAM_ATTN_WARPS * 32), (size_t)BEAM_ATTN_SMEM, st, qkv, kcache, vcache, out,
+                                   (bf16*)nullptr, d_pos, images, beams, H, t_max, anc, anc_ld, n_prefix, trace_desc()));
+    note_launch();
+    return GIC_OK;
+  }
   const int grid = min(sms, ceil_div(rows * H, 12));
   if (out_lo)  // fp16 q / k / v / cache, hi + lo output (bf16x2 engine)
     GIC_CHECK_CUDA(launch_kernel(attn_decode_mma_kernel<12, 4, true, true>, dim3(grid), dim3(12 * 32), (size_t)DecMmaCfg<12, 4>::SMEM_BYTES, st, qkv, kcache,

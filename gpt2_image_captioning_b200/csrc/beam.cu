@@ -187,6 +187,72 @@ static int launch_beam_rowtopk(const float* logits, int B, int rows_per_image, i
   return GIC_OK;
 }
 
+// ---- the same step without a logits matrix: the LM-head GEMM's EPI_BEAM epilogue (gemm_tcgen05.cu) leaves, per row and stream, the stream's
+// GEMM_BEAM_KEEP best (logit, column) pairs and its running (maximum, sum of exp(logit - maximum)).  One warp per live row combines the
+// streams' log-sum-exp partials in stream order, turns the kept logits into (logit - lse) + running score exactly as beam_rowtopk_kernel
+// does, and selects the row's K best (value desc, flat index asc).  A row's top K by value lies inside the union of its streams' top 16 by
+// logit (K <= 16; value is a non-decreasing function of the logit). ----
+__global__ void __launch_bounds__(32) beam_streams_kernel(const float* __restrict__ tk_v, const int* __restrict__ tk_i, const float* __restrict__ bm,
+                                                          const float* __restrict__ bs, int streams, int rows_per_image, int n_live,
+                                                          const float* __restrict__ run_score, int beams, int V, int K, float* __restrict__ lse,
+                                                          float* __restrict__ row_val, int* __restrict__ row_idx) {
+  extern __shared__ unsigned char sm_raw[];
+  const int n = streams * GEMM_BEAM_KEEP;
+  float* cv = reinterpret_cast<float*>(sm_raw);             // [n]
+  int* ci = reinterpret_cast<int*>(sm_raw + (size_t)n * 4);  // [n]
+  const int b = blockIdx.x / n_live, j = blockIdx.x % n_live, lane = threadIdx.x;
+  const size_t r = (size_t)b * rows_per_image + j;
+  // log-sum-exp: every lane runs the same short loop (streams <= a few dozen): no reduction order to worry about
+  float M = -INFINITY;
+  for (int s = 0; s < streams; ++s) M = fmaxf(M, bm[r * streams + s]);
+  float S = 0.f;
+  for (int s = 0; s < streams; ++s) {
+    const float m = bm[r * streams + s];
+    if (m != -INFINITY) S += bs[r * streams + s] * expf(m - M);
+  }
+  const float l = M + logf(S), base = run_score[(size_t)b * beams + j];
+  if (lane == 0) lse[r] = l;
+  for (int s = lane; s < n; s += 32) {
+    const int c = tk_i[r * n + s];
+    cv[s] = c >= 0 ? (tk_v[r * n + s] - l) + base : -INFINITY;  // log_softmax first, then + running score (HF :3252-3256,3283)
+    ci[s] = c >= 0 ? j * V + c : 0x7fffffff;
+  }
+  __syncwarp();
+  for (int out = 0; out < K; ++out) {
+    float bv = -INFINITY; int bi = 0x7fffffff, bslot = -1;
+    for (int s = lane; s < n; s += 32)
+      if (bcand_better(cv[s], ci[s], bv, bi)) { bv = cv[s]; bi = ci[s]; bslot = s; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o), os = __shfl_xor_sync(0xffffffffu, bslot, o);
+      if (bcand_better(ov, oi, bv, bi)) { bv = ov; bi = oi; bslot = os; }
+    }
+    if (lane == 0) {
+      row_val[r * K + out] = bv;
+      row_idx[r * K + out] = bi;
+      if (bslot >= 0) { cv[bslot] = -INFINITY; ci[bslot] = 0x7fffffff; }
+    }
+    __syncwarp();
+  }
+}
+
+int launch_beam_topk_streams(const float* tk_v, const int* tk_i, const float* bm, const float* bs, int streams, int B, int rows_per_image, int n_live,
+                             const float* run_score, int beams, int V, int K, float* lse, float* row_val, int* row_idx, float* cand_score, int* cand_idx,
+                             cudaStream_t st) {
+  GIC_REQUIRE(K == 2 * beams && beams >= 2 && beams <= 8 && n_live >= 1 && n_live <= beams && K <= GEMM_BEAM_KEEP && streams >= 1,
+              "beam_topk_streams: beams %d / K %d / live %d / streams %d out of range", beams, K, n_live, streams);
+  const size_t smem = (size_t)streams * GEMM_BEAM_KEEP * 8;
+  GIC_REQUIRE(smem <= 48 * 1024, "beam_topk_streams: %d streams do not fit the merge kernel's shared memory", streams);
+  beam_streams_kernel<<<B * n_live, 32, smem, st>>>(tk_v, tk_i, bm, bs, streams, rows_per_image, n_live, run_score, beams, V, K, lse, row_val, row_idx);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  beam_merge_kernel<<<B, 32, 0, st>>>(row_val, row_idx, rows_per_image, n_live, K, cand_score, cand_idx);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return GIC_OK;
+}
+
 int launch_beam_topk(const float* logits, int B, int rows_per_image, int n_live, const float* run_score, int beams, int V, int K,
                      float* lse, float* row_val, int* row_idx, float* cand_score, int* cand_idx, cudaStream_t st) {
   GIC_REQUIRE(K == 2 * beams && beams >= 2 && beams <= 8 && n_live >= 1 && n_live <= beams, "beam_topk: beams %d / K %d / live %d out of range", beams, K, n_live);

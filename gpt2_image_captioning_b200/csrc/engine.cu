@@ -101,6 +101,7 @@ struct gic_engine {
   gic_config cfg;
   int d = 0, L = 0, H = 0, V = 0, P_img = 0, P_task = 0, E = 0;
   bool split = false;  // BF16X2
+  bool beam_fused_head = false;  // beam search: log-sum-exp + top-2K candidates from the LM-head epilogue (no [rows, V] logits); GIC_BEAM_LOGITS=1: off
   bool beam_indirect = false;  // BF16 beam search: no KV reorder, decode attention reads through an ancestry table (GIC_BEAM_REORDER=1: gather)
   bool fuse_ln = false;  // BF16 / BF16X2: ln_1 / ln_2 folded into the GEMM that follows them (no LayerNorm launches inside the GPT-2 blocks)
   bool use_splitk = false;  // GIC_SPLITK=1 turns the K split of the decode-size residual GEMMs on.  Off by default: measured round 1
@@ -278,6 +279,12 @@ static void carve_act(const gic_engine* e, Carver& c, Act* a, size_t n) {
 // the KV cache (and q | k | v) hold 2-byte elements: bf16 in the BF16 engine, IEEE half in the fused BF16X2 engine
 static bool kv16(const gic_engine* e) { return e->cfg.dtype == GIC_DTYPE_BF16 || (e->split && e->fuse_ln); }
 
+// tile shape of the beam-search LM head (EPI_BEAM): CTA pairs on 256-wide tiles when the row tiles pair up, else single CTAs
+static void beam_head_shape(const gic_engine* e, int M, int* bn, int* pair) {
+  *pair = (ceil_div(M, 128) % 2 == 0 && cta_limit() == 0) ? 1 : 0;
+  *bn = (*pair || !e->split) ? 256 : 128;
+}
+
 static void carve(const gic_engine* e, void* base, int B, int max_new, int beams, Workspace* w) {
   const int d = e->d;
   w->B = B; w->beams = beams < 1 ? 1 : beams; w->rows = B * w->beams; w->max_new = max_new;
@@ -310,7 +317,8 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
     w->n_parts_max = LMHEAD_F32_PARTS;
   } else {
     w->n_parts_max = 2 * ceil_div(e->V, 32);
-    if (w->beams > 1) w->logits = c.take<float>((size_t)w->rows * e->V);  // beam search needs full rows for log-softmax + top-2K
+    // beam search: log-softmax + top-2K come out of the LM-head epilogue (EPI_BEAM streams, below); full fp32 rows only with GIC_BEAM_LOGITS=1
+    if (w->beams > 1 && !e->beam_fused_head) w->logits = c.take<float>((size_t)w->rows * e->V);
   }
   if (w->beams > 1) {
     BeamState& bs = w->beam;
@@ -328,6 +336,17 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
     bs.beam_idx = c.take<int>(w->rows); bs.next_tok = c.take<int>(w->rows);
     bs.cand_score = c.take<float>((size_t)2 * w->rows); bs.cand_idx = c.take<int>((size_t)2 * w->rows);
     bs.lse = c.take<float>(w->rows); bs.row_val = c.take<float>((size_t)2 * w->beams * w->rows); bs.row_idx = c.take<int>((size_t)2 * w->beams * w->rows);
+    if (e->beam_fused_head) {
+      // (row, stream) slots of the two launch shapes: B rows after the prefill, B * beams rows per decode step
+      int bn = 0, pair = 0;
+      beam_head_shape(e, B, &bn, &pair);
+      const size_t s0 = (size_t)B * gemm_topk_streams(B, e->V, bn, pair);
+      beam_head_shape(e, w->rows, &bn, &pair);
+      const size_t s1 = (size_t)w->rows * gemm_topk_streams(w->rows, e->V, bn, pair);
+      bs.tk_slots = s0 > s1 ? s0 : s1;
+      bs.tk_v = c.take<float>(bs.tk_slots * GEMM_BEAM_KEEP); bs.tk_i = c.take<int>(bs.tk_slots * GEMM_BEAM_KEEP);
+      bs.tk_m = c.take<float>(bs.tk_slots); bs.tk_s = c.take<float>(bs.tk_slots);
+    }
   }
   if (e->fuse_ln) {
     w->ln_parts_max = ceil_div(d, 32);
@@ -793,6 +812,8 @@ int gic_engine_create(const gic_config* cfg, gic_engine** out) {
     const char* nf = getenv("GIC_NO_LNFUSE");
     e->fuse_ln = e->tc && !(nf && nf[0] == '1');  // GIC_NO_LNFUSE=1: LayerNorm as its own kernel; BF16X2 then also keeps fp32 q | k | v and cache
     e->beam_indirect = e->fuse_ln && gic::attn_decode_indirect_available();
+    const char* bl = getenv("GIC_BEAM_LOGITS");
+    e->beam_fused_head = e->tc && !(bl && bl[0] == '1');
     const char* sk = getenv("GIC_SPLITK");
     // off unless GIC_SPLITK=1 in both tensor-core modes: measured again in round 2 for bf16x2, whose fc2 main loop is 2.5x longer
     // (profiles/r2f_splitk.txt): 29.2 us with the 3-way K split against 22.6 us unsplit -- the parked-partials reduction costs more than
@@ -1151,6 +1172,31 @@ static int lm_head_logits(const gic_engine* e, const Workspace& w, const float* 
   return linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st);
 }
 
+// ln_f -> LM head whose epilogue keeps, per row and stream, the 16 best logits and the log-sum-exp partials (EPI_BEAM): what HF's
+// log_softmax + topk(2 * beams) (HF:generation/utils.py:3252-3256,2981-2987) need, without the [rows, V] fp32 matrix (1 GB per step at config 3)
+static int lm_head_beam(const gic_engine* e, const Workspace& w, const float* h_buf, long first_off, long row_stride, int rows, int* streams_out, cudaStream_t st) {
+  { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h_buf + first_off, row_stride, e->lnf.w, e->lnf.b, w.a.out(), rows, e->d, st)); }
+  ProfScope ps(e, "lm_head", st);
+  const Linear& lin = e->lm_head;
+  GemmBf16Args g;
+  int bn = 0, pair = 0;
+  beam_head_shape(e, rows, &bn, &pair);
+  const int bi = box_rows_index(pair ? bn / 2 : bn);
+  GIC_REQUIRE(bi >= 0, "no W tensor map for box height %d", pair ? bn / 2 : bn);
+  GIC_TRY(make_tma_2d_bf16(&g.a_hi, w.a.hi, rows, lin.K, lin.K, 128));
+  g.w_hi = lin.tm_hi[bi];
+  if (e->split) {
+    GIC_TRY(make_tma_2d_bf16(&g.a_lo, w.a.lo, rows, lin.K, lin.K, 128));
+    g.w_lo = lin.tm_lo[bi];
+  }
+  const int streams = gemm_topk_streams(rows, lin.N, bn, pair);
+  GIC_REQUIRE((size_t)rows * streams <= w.beam.tk_slots, "beam LM head: %d rows x %d streams exceed the workspace", rows, streams);
+  g.M = rows; g.N = lin.N; g.K = lin.K; g.block_n = bn; g.pair = pair; g.split = e->split ? 1 : 0; g.epilogue = EPI_NONE; g.w_static = 1;
+  g.topk_v = w.beam.tk_v; g.topk_i = w.beam.tk_i; g.beam_m = w.beam.tk_m; g.beam_s = w.beam.tk_s; g.topk_streams = streams;
+  *streams_out = streams;
+  return launch_gemm_bf16(g, st);
+}
+
 int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int num_beams, float length_penalty, int64_t* ids_out,
                       float* scores_out, int32_t* gen_len_out, void* workspace, size_t workspace_bytes, void* stream) {
   GIC_TRY(check_ready(e));
@@ -1169,12 +1215,18 @@ int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int
   // prefill once per image; its K/V land in cache row b*beams and the first reorder fans them out to every beam
   if (e->fuse_ln) GIC_TRY(launch_row_stats(w.h, d, w.a.hi, w.ln_stats, B * P, d, st, w.a.lo));
   GIC_TRY(gpt_layers(e, w, w.h, B * P, true, st));
-  GIC_TRY(lm_head_logits(e, w, w.h, (long)(P - 1) * d, (long)P * d, B, B * P, st));
+  int streams = 0;
+  if (e->beam_fused_head) GIC_TRY(lm_head_beam(e, w, w.h, (long)(P - 1) * d, (long)P * d, B, &streams, st));
+  else GIC_TRY(lm_head_logits(e, w, w.h, (long)(P - 1) * d, (long)P * d, B, B * P, st));
   for (int t = 0; t < max_new; ++t) {
     const int live = t == 0 ? 1 : nb;  // only beam 0 is live at the first step (running scores 0, -1e9, ...)
     { ProfScope ps(e, "beam_topk", st);
-      GIC_TRY(launch_beam_topk(w.logits, B, live, live, w.beam.run_score, nb, e->V, K, w.beam.lse, w.beam.row_val, w.beam.row_idx, w.beam.cand_score,
-                               w.beam.cand_idx, st)); }
+      if (e->beam_fused_head)
+        GIC_TRY(launch_beam_topk_streams(w.beam.tk_v, w.beam.tk_i, w.beam.tk_m, w.beam.tk_s, streams, B, live, live, w.beam.run_score, nb, e->V, K, w.beam.lse,
+                                         w.beam.row_val, w.beam.row_idx, w.beam.cand_score, w.beam.cand_idx, st));
+      else
+        GIC_TRY(launch_beam_topk(w.logits, B, live, live, w.beam.run_score, nb, e->V, K, w.beam.lse, w.beam.row_val, w.beam.row_idx, w.beam.cand_score,
+                                 w.beam.cand_idx, st)); }
     const float denom = (float)pow((double)(t + 1), (double)length_penalty);
     { ProfScope ps(e, "beam_update", st); GIC_TRY(launch_beam_update(w.beam, t, denom, st)); }
     if (t + 1 == max_new) break;
@@ -1196,7 +1248,8 @@ int gic_generate_beam(gic_engine* e, const float* x, int batch, int max_new, int
     GIC_TRY(launch_set_int(w.d_pos, P + t, st));
     if (e->fuse_ln) GIC_TRY(launch_row_stats(w.h_dec, d, w.a.hi, w.ln_stats, rows, d, st, w.a.lo));
     GIC_TRY(gpt_layers(e, w, w.h_dec, rows, false, st));
-    GIC_TRY(lm_head_logits(e, w, w.h_dec, 0, d, rows, rows, st));
+    if (e->beam_fused_head) GIC_TRY(lm_head_beam(e, w, w.h_dec, 0, d, rows, &streams, st));
+    else GIC_TRY(lm_head_logits(e, w, w.h_dec, 0, d, rows, rows, st));
   }
   GIC_TRY(launch_beam_finalize(w.beam, max_new & 1, ids_out, scores_out, gen_len_out, st));
   return join_stream(e, user);
@@ -1423,6 +1476,32 @@ int gic_test_attn_decode(const void* qkv, void* kcache, void* vcache, void* out,
     gic::attn_decode_set_variant(variant);
     r = launch_attn_decode<bf16>((const bf16*)qkv, (bf16*)kcache, (bf16*)vcache, o, d_pos, rows, H, t_max, st);
     gic::attn_decode_set_variant(-1);
+    ce = cudaStreamSynchronize(st);
+  }
+  cudaFree(d_pos);
+  if (r != GIC_OK) return r;
+  GIC_CHECK_CUDA(ce);
+  return GIC_OK;
+}
+
+// Kernel-level hook of the beam-search decode attention (ancestry table instead of a reordered cache; see the header)
+int gic_test_attn_decode_beam(const void* qkv, void* kcache, void* vcache, void* out, void* out_lo, const int32_t* anc, int anc_ld, int pos, int rows, int H,
+                              int t_max, int n_prefix, int beams, int f16, int shared, void* stream) {
+  GIC_REQUIRE(qkv && kcache && vcache && out && anc, "null argument");
+  GIC_REQUIRE((f16 != 0) == (out_lo != nullptr), "the fp16 flavour writes hi + lo outputs, the bf16 one a single output");
+  GIC_REQUIRE(pos >= n_prefix && pos < t_max && rows > 0 && H > 0 && beams >= 1 && rows % beams == 0 && anc_ld >= pos - n_prefix,
+              "bad shape: pos %d n_prefix %d t_max %d rows %d H %d beams %d anc_ld %d", pos, n_prefix, t_max, rows, H, beams, anc_ld);
+  cudaStream_t st = (cudaStream_t)stream;
+  GIC_TRY(gic_device_check());
+  GIC_TRY(gic::attn_decode_configure());
+  int* d_pos = nullptr;
+  GIC_CHECK_CUDA(cudaMalloc((void**)&d_pos, sizeof(int)));
+  cudaError_t ce = cudaMemcpyAsync(d_pos, &pos, sizeof(int), cudaMemcpyHostToDevice, st);
+  int r = GIC_OK;
+  if (ce == cudaSuccess) {
+    gic::attn_decode_set_beam_shared(shared ? 1 : 0);
+    r = launch_attn_decode_indirect((const bf16*)qkv, (bf16*)kcache, (bf16*)vcache, (bf16*)out, d_pos, rows, H, t_max, anc, anc_ld, n_prefix, beams, st, (bf16*)out_lo);
+    gic::attn_decode_set_beam_shared(-1);
     ce = cudaStreamSynchronize(st);
   }
   cudaFree(d_pos);

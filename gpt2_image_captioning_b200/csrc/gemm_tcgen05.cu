@@ -225,6 +225,7 @@ struct alignas(64) GemmKernelParams {
   // EPI_TOPK (retrieval scan, no score matrix): every epilogue thread keeps the GEMM_TOPK_KEEP best (score, column) of the columns it
   // sees for ITS row + the largest score it dropped; written at the end as stream (unit index / m_units) * 2 + column-parity warp of the row
   float* topk_v; int* topk_i; float* topk_u; int topk_streams;
+  float* beam_m; float* beam_s;  // EPI_BEAM: per (row, stream) running maximum and sum of exp(score - maximum); KEEP = GEMM_BEAM_KEEP, no topk_u
   // folded LayerNorm on the A operand (see launch_gemm_bf16): out = rstd_r * (acc - mean_r * colsum_n) + bias_n
   const float2* ln_stats; int ln_parts; long ln_stats_ld; int ln_row_mul, ln_row_off; const float* ln_colsum;
   // split-K (see launch_gemm_bf16): `split_k` CTAs share one output tile, each over K / split_k; fp32 partials go to splitk_ws
@@ -489,12 +490,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
       if (PAIR) ptx::mbar_arrive_cluster(tmem_empty_bar + 8 * a, 0);
       else ptx::mbar_arrive(tmem_empty_bar + 8 * a);
     };
-    // EPI_TOPK: the launch keeps the row tile of a CTA fixed (grid units a multiple of m_units), so this thread's row never changes
-    float tk_v[GEMM_TOPK_KEEP], tk_u = -INFINITY;
-    int tk_i[GEMM_TOPK_KEEP];
-    if (EPI == EPI_TOPK) {
+    // EPI_TOPK / EPI_BEAM: the launch keeps the row tile of a CTA fixed (grid units a multiple of m_units), so this thread's row never changes
+    constexpr bool STREAMS = EPI == EPI_TOPK || EPI == EPI_BEAM;
+    constexpr int KEEP = EPI == EPI_BEAM ? GEMM_BEAM_KEEP : GEMM_TOPK_KEEP;
+    float tk_v[KEEP], tk_u = -INFINITY;
+    int tk_i[KEEP];
+    float lse_m = -INFINITY, lse_s = 0.f;  // EPI_BEAM: online log-sum-exp of the columns this thread saw (base 2 inside, natural on output)
+    if (STREAMS) {
 #pragma unroll
-      for (int j = 0; j < GEMM_TOPK_KEEP; ++j) { tk_v[j] = -INFINITY; tk_i[j] = -1; }
+      for (int j = 0; j < KEEP; ++j) { tk_v[j] = -INFINITY; tk_i[j] = -1; }
     }
     for (int work = work0; work < total_work; work += work_stride, ++local) {
       const int tile = work / p.split_k, ks = work % p.split_k;
@@ -502,8 +506,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
       const int n_tile = tile / m_units;
       const int m0 = ((tile % m_units) * m_per_unit + (int)rank) * GEMM_BLOCK_M, n0 = n_tile * BLOCK_N;
       const int wrow0 = m0 + q * 32;  // first row of this warp's 32-row band
-      if (EPI == EPI_TOPK) {
-        // ---- retrieval scan: scores straight from the TMEM registers (lane = row) into the thread's running top-KEEP; columns arrive
+      if (STREAMS) {
+        // ---- retrieval scan / beam-search LM head: scores straight from the TMEM registers (lane = row) into the thread's running top-KEEP; columns arrive
         // in ascending order within a thread, so on equal scores the lower column stays (the exact path's tie rule) ----
         ptx::mbar_wait(tmem_full_bar + 8 * acc, use & 1);
         ptx::tc_fence_after();
@@ -525,16 +529,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
           }
           if (col0 >= p.N) continue;  // warp-uniform
           const int ncol = min(32, p.N - col0);
+          if (EPI == EPI_BEAM) {
+            // online log-sum-exp over the chunk: one rescale per chunk, then 32 independent exp2
+            float cm = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) cm = fmaxf(cm, c < ncol ? __uint_as_float(r[c]) : -INFINITY);
+            const float nm = fmaxf(lse_m, cm);  // finite: the chunk holds at least one column
+            const float nml = nm * 1.4426950408889634f;
+            float add = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) add += c < ncol ? exp2f(fmaf(__uint_as_float(r[c]), 1.4426950408889634f, -nml)) : 0.f;
+            lse_s = lse_s * exp2f(lse_m * 1.4426950408889634f - nml) + add;  // exp2(-inf) = 0 at the first chunk
+            lse_m = nm;
+          }
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
             const float x = __uint_as_float(r[c]);
             if (c < ncol) {
-              if (x > tk_v[GEMM_TOPK_KEEP - 1]) {
-                tk_u = fmaxf(tk_u, tk_v[GEMM_TOPK_KEEP - 1]);
+              if (x > tk_v[KEEP - 1]) {
+                tk_u = fmaxf(tk_u, tk_v[KEEP - 1]);
                 float pv = x;
                 int pi = col0 + c;
 #pragma unroll
-                for (int j = 0; j < GEMM_TOPK_KEEP; ++j)
+                for (int j = 0; j < KEEP; ++j)
                   if (pv > tk_v[j]) { const float tv = tk_v[j]; const int ti = tk_i[j]; tk_v[j] = pv; tk_i[j] = pi; pv = tv; pi = ti; }
               } else {
                 tk_u = fmaxf(tk_u, x);
@@ -1071,14 +1088,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_bf16_tcgen05_kernel(cons
       }
       if (tracing && e == 0 && lane == 0 && local < 8) p.trace[512 + local * 4 + 2] = clock64() - t_start;
     }
-    if (EPI == EPI_TOPK && work0 < total_work) {
+    if (STREAMS && work0 < total_work) {
       const int row = ((work0 % m_units) * m_per_unit + (int)rank) * GEMM_BLOCK_M + q * 32 + lane;
       if (row < p.M && sub * 32 < BLOCK_N) {
         const int stream = (work0 / m_units) * 2 + sub;
-        const size_t so = ((size_t)row * p.topk_streams + stream) * GEMM_TOPK_KEEP;
+        const size_t so = ((size_t)row * p.topk_streams + stream) * KEEP;
 #pragma unroll
-        for (int j = 0; j < GEMM_TOPK_KEEP; ++j) { p.topk_v[so + j] = tk_v[j]; p.topk_i[so + j] = tk_i[j]; }
-        p.topk_u[(size_t)row * p.topk_streams + stream] = tk_u;
+        for (int j = 0; j < KEEP; ++j) { p.topk_v[so + j] = tk_v[j]; p.topk_i[so + j] = tk_i[j]; }
+        if (EPI == EPI_BEAM) {
+          p.beam_m[(size_t)row * p.topk_streams + stream] = lse_m;
+          p.beam_s[(size_t)row * p.topk_streams + stream] = lse_s;
+        } else {
+          p.topk_u[(size_t)row * p.topk_streams + stream] = tk_u;
+        }
       }
     }
   }
@@ -1217,7 +1239,8 @@ static int gemm_num_sms() {
 #define GIC_GEMM_VARIANTS_BF16(X) \
   X(EPI_NONE, OUT_BF16, false, false) X(EPI_NONE, OUT_BF16, true, false) X(EPI_TANH, OUT_BF16, false, false) X(EPI_GELU, OUT_BF16, false, false) \
   X(EPI_GELU, OUT_BF16, true, false) X(EPI_RELU, OUT_BF16, false, false) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false, false) \
-  X(EPI_ARGMAX, OUT_NONE, true, false) X(EPI_ARGMAX, OUT_F32, true, true) X(EPI_NONE, OUT_F32, true, true) X(EPI_ARGMAX2, OUT_NONE, false, false)
+  X(EPI_ARGMAX, OUT_NONE, true, false) X(EPI_ARGMAX, OUT_F32, true, true) X(EPI_NONE, OUT_F32, true, true) X(EPI_ARGMAX2, OUT_NONE, false, false) \
+  X(EPI_BEAM, OUT_NONE, false, false)
 #define GIC_GEMM_VARIANTS_SPLIT(X) \
   X(EPI_NONE, OUT_BF16X2, false, false) X(EPI_TANH, OUT_BF16X2, false, false) X(EPI_GELU, OUT_BF16X2, false, false) X(EPI_RELU, OUT_BF16X2, false, false) \
   X(EPI_NONE, OUT_F16, true, false) X(EPI_GELU, OUT_BF16X2, true, false) X(EPI_RESIDUAL, OUT_F32_BF16X2_STATS, false, false)
@@ -1226,16 +1249,16 @@ static int gemm_num_sms() {
 #define GIC_GEMM_VARIANTS_SPLIT_WIDE(X) \
   X(EPI_NONE, OUT_F16, true, false) X(EPI_GELU, OUT_BF16X2, true, false) X(EPI_RESIDUAL, OUT_F32_BF16X2_STATS, false, false) \
   X(EPI_ARGMAX, OUT_NONE, false, false) X(EPI_NONE, OUT_F32, false, false) X(EPI_NONE, OUT_F32, false, true) X(EPI_ARGMAX, OUT_F32, false, true) \
-  X(EPI_TOPK, OUT_NONE, false, false)
+  X(EPI_TOPK, OUT_NONE, false, false) X(EPI_BEAM, OUT_NONE, false, false)
 
 // CTA-pair instantiations (aligned shapes, bf16 operands): the fused decode / prefill GEMMs, the LM head, and the plain fp32-output
 // GEMM of the kernel test hook
 #define GIC_GEMM_VARIANTS_PAIR(X) \
   X(EPI_NONE, OUT_BF16, true) X(EPI_GELU, OUT_BF16, true) X(EPI_RESIDUAL, OUT_F32_BF16_STATS, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_NONE, OUT_F32, false) \
-  X(EPI_ARGMAX2, OUT_NONE, false)
+  X(EPI_ARGMAX2, OUT_NONE, false) X(EPI_BEAM, OUT_NONE, false)
 #define GIC_GEMM_VARIANTS_PAIR_SPLIT(X) \
   X(EPI_NONE, OUT_F16, true) X(EPI_GELU, OUT_BF16X2, true) X(EPI_RESIDUAL, OUT_F32_BF16X2_STATS, false) X(EPI_ARGMAX, OUT_NONE, false) X(EPI_NONE, OUT_F32, false) \
-  X(EPI_TOPK, OUT_NONE, false)
+  X(EPI_TOPK, OUT_NONE, false) X(EPI_BEAM, OUT_NONE, false)
 
 template <int BLOCK_N>
 static int configure_pair() {
@@ -1309,7 +1332,7 @@ static int launch_one(const GemmKernelParams& kp, cudaStream_t st) {
 
   const int sms = cta_limit() > 0 && cta_limit() < gemm_num_sms() ? cta_limit() : gemm_num_sms();
   dim3 grid((unsigned)(tiles < sms ? tiles : sms));  // persistent: one CTA per SM (of this chain's share, see cta_limit)
-  if (EPI == EPI_TOPK) {  // row-tile-stationary CTAs: the grid is a multiple of the number of row tiles (see launch_gemm_topk_streams)
+  if (EPI == EPI_TOPK || EPI == EPI_BEAM) {  // row-tile-stationary CTAs: the grid is a multiple of the number of row tiles (see launch_gemm_topk_streams)
     const int m_units = ceil_div(kp.M, GEMM_BLOCK_M);
     grid.x = (unsigned)(kp.topk_streams / 2 * m_units);
   }
@@ -1345,7 +1368,7 @@ static int launch_one_pair(const GemmKernelParams& kp, cudaStream_t st) {
   long pairs = units < max_pairs ? units : max_pairs;
   GemmKernelParams kq = kp;
   kq.splitk_coop = (kp.split_k > 1 && units <= max_pairs && !splitk_coop_disabled()) ? 1 : 0;  // one resident pair per work item
-  if (EPI == EPI_TOPK) pairs = (long)(kp.topk_streams / 2) * (ceil_div(kp.M, GEMM_BLOCK_M) / 2);  // row-tile-stationary pairs
+  if (EPI == EPI_TOPK || EPI == EPI_BEAM) pairs = (long)(kp.topk_streams / 2) * (ceil_div(kp.M, GEMM_BLOCK_M) / 2);  // row-tile-stationary pairs
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(2 * pairs));
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -1436,7 +1459,7 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   kp.mma_repeat = a.mma_repeat < 1 ? 1 : a.mma_repeat;
   kp.out_f32 = a.out.f32; kp.ld_f32 = a.ld_out; kp.out_hi = a.out.hi; kp.out_lo = a.out.lo; kp.ld_bf16 = a.ld_out;
   kp.part_val = a.part_val; kp.part_idx = a.part_idx; kp.part_ld = a.part_ld; kp.part_val2 = a.part_val2; kp.trace = a.trace;
-  kp.topk_v = a.topk_v; kp.topk_i = a.topk_i; kp.topk_u = a.topk_u; kp.topk_streams = a.topk_streams;
+  kp.topk_v = a.topk_v; kp.topk_i = a.topk_i; kp.topk_u = a.topk_u; kp.topk_streams = a.topk_streams; kp.beam_m = a.beam_m; kp.beam_s = a.beam_s;
   kp.ln_stats = a.ln_stats; kp.ln_parts = a.ln_parts; kp.ln_stats_ld = a.ln_stats_ld; kp.ln_row_mul = a.ln_row_mul; kp.ln_row_off = a.ln_row_off;
   kp.ln_colsum = a.ln_colsum; kp.stats_out = a.stats_out;
   kp.split_k = a.split_k < 1 ? 1 : a.split_k; kp.splitk_ws = a.splitk_ws; kp.splitk_counters = a.splitk_counters;
@@ -1445,11 +1468,12 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   GIC_REQUIRE(!a.ln_stats || (a.ln_colsum && a.ln_parts > 0), "gemm_bf16: folded LayerNorm needs the column sums and at least one statistics part");
   int epi = a.epilogue;
   if (a.topk_v) {
-    GIC_REQUIRE(a.epilogue == EPI_NONE && a.topk_i && a.topk_u && !a.part_val && !a.out.f32 && !a.out.hi && !a.ln_stats && kp.split_k == 1,
+    GIC_REQUIRE(a.epilogue == EPI_NONE && a.topk_i && (a.topk_u || a.beam_m) && (a.beam_m != nullptr) == (a.beam_s != nullptr) && !a.part_val && !a.out.f32 && !a.out.hi &&
+                    !a.ln_stats && kp.split_k == 1,
                 "gemm_bf16: the fused top-k epilogue takes raw scores and no other output");
     GIC_REQUIRE(a.topk_streams >= 2 && a.topk_streams == gemm_topk_streams(a.M, a.N, a.block_n, a.pair), "gemm_bf16: top-k stream count %d does not match the launch shape",
                 a.topk_streams);
-    epi = EPI_TOPK;
+    epi = a.beam_m ? EPI_BEAM : EPI_TOPK;
   }
   if (a.part_val) {
     GIC_REQUIRE(a.epilogue == EPI_NONE && a.part_idx, "gemm_bf16: the fused argmax takes no activation and needs both partial buffers");
@@ -1474,7 +1498,7 @@ int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st) {
   } else if (a.out.hi) {
     out = a.out.lo ? OUT_BF16X2 : OUT_BF16;
   } else {
-    GIC_REQUIRE(epi == EPI_ARGMAX || epi == EPI_ARGMAX2 || epi == EPI_TOPK, "gemm_bf16: no output buffer");
+    GIC_REQUIRE(epi == EPI_ARGMAX || epi == EPI_ARGMAX2 || epi == EPI_TOPK || epi == EPI_BEAM, "gemm_bf16: no output buffer");
   }
   if (kp.split_k > 1) {
     GIC_REQUIRE(epi != EPI_ARGMAX && epi != EPI_ARGMAX2 && a.splitk_ws && a.splitk_counters, "gemm_bf16: split-K needs its workspace / counters and a storing epilogue");

@@ -6,7 +6,8 @@ namespace gic {
 
 enum Epilogue { EPI_NONE = 0, EPI_TANH = 1, EPI_GELU = 2, EPI_RELU = 3, EPI_RESIDUAL = 4, EPI_ARGMAX = 5 /* internal: set by part_val */,
                 EPI_ARGMAX2 = 6 /* internal: set by part_val2 (best + runner-up value per slot) */,
-                EPI_TOPK = 7 /* internal: set by topk_v (per-row running top-8 + drop bound, no score matrix) */ };
+                EPI_TOPK = 7 /* internal: set by topk_v (per-row running top-8 + drop bound, no score matrix) */,
+                EPI_BEAM = 8 /* internal: set by topk_v + beam_m (per-row running top-16 + online log-sum-exp: the beam-search LM head) */ };
 
 // Where a producer kernel writes an activation: fp32 and/or bf16 (hi) and/or the bf16 remainder (lo = bf16(v - hi),
 // the second half of a BF16X2 GEMM operand).  Any pointer may be null.
@@ -53,6 +54,10 @@ struct GemmBf16Args {
   // fused top-k scan (retrieval): per row and stream the GEMM_TOPK_KEEP (8) best (score, column) + the largest dropped score; stream count from
   // gemm_topk_streams(M, N, block_n, pair).  topk_v / topk_i [M][streams][8], topk_u [M][streams]
   float* topk_v = nullptr; int* topk_i = nullptr; float* topk_u = nullptr; int topk_streams = 0;
+  // beam-search LM head (HF:generation/utils.py:3252-3256 log_softmax, :2981-2987 top 2 * beams): with beam_m / beam_s set the streams keep
+  // GEMM_BEAM_KEEP (16) candidates each (topk_v / topk_i [M][streams][16], no drop bound) and every stream's running maximum and
+  // sum of exp(logit - maximum) over the columns it saw ([M][streams] each): log-sum-exp and top-2K without a logits matrix
+  float* beam_m = nullptr; float* beam_s = nullptr;
   // LayerNorm folded into the GEMM (A holds the RAW rows x, W was packed as gamma_k * W[n,k], bias as b_n + sum_k beta_k W[n,k]):
   //   out[r,n] = rstd_r * (acc[r,n] - mean_r * ln_colsum[n]) + bias[n],   mean / rstd from sum_parts ln_stats[part][r * mul + off]
   const float2* ln_stats = nullptr;  // [ln_parts][ln_stats_ld] (sum x, sum x^2) partials written by the producer of A
@@ -73,6 +78,7 @@ struct GemmBf16Args {
 int launch_gemm_bf16(const GemmBf16Args& a, cudaStream_t st);
 int gemm_topk_streams(int M, int N, int block_n, int pair);
 constexpr int GEMM_TOPK_KEEP_PUBLIC = 8;  // == GEMM_TOPK_KEEP (gemm_tcgen05.cu)
+constexpr int GEMM_BEAM_KEEP = 16;        // candidates per stream of the beam-search LM head (>= 2 * beams for beams <= 8)
 int gemm_bf16_pick_block_n(int M, int N, int split);
 // tile width for an M x N x K problem cut into split_k K slices (split: bf16x2 operands)
 // pair (may be null): out, 1 = run as CTA pairs (cta_group::2); the W tensor map's box is then block_n / 2 rows and GemmBf16Args::pair is set
@@ -114,6 +120,7 @@ int launch_attn_decode(const T* qkv, T* kcache, T* vcache, ActOut out, const int
 // (out_lo non-null: the fp16-cache / hi + lo output flavour of the bf16x2 engine)
 int launch_attn_decode_indirect(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, const int* d_pos, int rows, int H, int t_max, const int* anc,
                                 int anc_ld, int n_prefix, int beams, cudaStream_t st, bf16* out_lo = nullptr);
+void attn_decode_set_beam_shared(int v);  // test knob: 1 = attn_decode_beam_kernel (prefix shared by an image's beams), 0 = one walk per hypothesis, < 0 = default
 // bf16x2 engine: q | k | v and the KV cache are IEEE half (2-byte elements, typed bf16* for the shared plumbing), the output a bf16 hi + lo pair
 int launch_attn_decode_f16(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out_hi, bf16* out_lo, const int* d_pos, int rows, int H, int t_max,
                            cudaStream_t st, const int* row_map = nullptr);
@@ -199,11 +206,17 @@ struct BeamState {
   float* cand_score; int* cand_idx;       // [B, 2 * beams]
   int* anc[2];                            // [B * beams, max_new] ancestry tables (double-buffered): cache row of every generated position
   float* lse; float* row_val; int* row_idx;  // [B * beams], [B * beams, 2 * beams]: per-row log-sum-exp and top-2*beams continuations
+  // fused LM head (EPI_BEAM): per row and stream the kept candidates and the log-sum-exp partials; null = logits are materialised instead
+  float* tk_v = nullptr; int* tk_i = nullptr; float* tk_m = nullptr; float* tk_s = nullptr; size_t tk_slots = 0;  // tk_slots: (row, stream) pairs allocated
 };
 int launch_beam_init(const BeamState& s, cudaStream_t st);
 int launch_beam_topk(const float* logits, int B, int rows_per_image, int n_live, const float* run_score, int beams, int V, int K,
                      float* lse /* [B * rows_per_image] */, float* row_val, int* row_idx /* [B * rows_per_image, K] */, float* cand_score,
                      int* cand_idx, cudaStream_t st);
+// the same from the EPI_BEAM streams of the LM-head GEMM (tk_v / tk_i [rows, streams, GEMM_BEAM_KEEP], bm / bs [rows, streams]): no logits matrix
+int launch_beam_topk_streams(const float* tk_v, const int* tk_i, const float* bm, const float* bs, int streams, int B, int rows_per_image, int n_live,
+                             const float* run_score, int beams, int V, int K, float* lse, float* row_val, int* row_idx, float* cand_score, int* cand_idx,
+                             cudaStream_t st);
 int launch_beam_update(const BeamState& s, int step, float len_denom, cudaStream_t st);
 // anc_new[r][g] = g == t - 1 ? beam_idx[r] : anc_old[beam_idx[r]][g] for g < t (t = tokens generated so far)
 int launch_beam_ancestry(const int* anc_old, int* anc_new, const int* beam_idx, int rows, int ld, int t, cudaStream_t st);

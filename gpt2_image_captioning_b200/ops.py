@@ -158,6 +158,18 @@ def test_attn_decode(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tens
     _capi.check(L.gic_test_attn_decode(qkv.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), out.data_ptr(), pos, rows, H, t_max, variant, _stream()))
 
 
+@torch.library.custom_op("gic::test_attn_decode_beam", mutates_args=("kcache", "vcache", "out", "out_lo"))
+def test_attn_decode_beam(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, out: torch.Tensor, out_lo: torch.Tensor, anc: torch.Tensor, pos: int,
+                          n_prefix: int, beams: int, f16: bool, shared: bool) -> None:
+    """Beam-search decode attention through an ancestry table.  qkv [rows, 3*H*64], kcache / vcache [rows, H, t_max, 64], out (and, f16, out_lo)
+    [rows, H*64], all 2-byte elements (bf16, or IEEE half viewed as bf16 when f16); anc int32 [rows, anc_ld]; out_lo is ignored unless f16."""
+    _need_cuda(qkv, kcache, vcache, out, anc)
+    L = _capi.lib()
+    rows, H, t_max = kcache.shape[0], kcache.shape[1], kcache.shape[2]
+    _capi.check(L.gic_test_attn_decode_beam(qkv.data_ptr(), kcache.data_ptr(), vcache.data_ptr(), out.data_ptr(), out_lo.data_ptr() if f16 else None, anc.data_ptr(),
+                                            anc.shape[1], pos, rows, H, t_max, n_prefix, beams, int(f16), int(shared), _stream()))
+
+
 @torch.library.custom_op("gic::test_attn_prefill", mutates_args=("kcache", "vcache", "out"))
 def test_attn_prefill(qkv: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, out: torch.Tensor, S: int) -> None:
     """qkv [rows*S, 3*H*64] bf16; kcache / vcache [rows, H, t_max, 64] bf16; out [rows*S, H*64] bf16."""

@@ -231,6 +231,13 @@ GIC_API int gic_test_ln_mlp(float* h, const float* gamma, const float* beta, con
 /* one decode-attention launch on caller data: qkv [rows, 3*H*64] bf16, K / V caches [rows][H][t_max][64] bf16 with `pos` cached tokens;
  * appends the new K / V at `pos`, writes out [rows, H*64] bf16 (HF:models/gpt2/modeling_gpt2.py:185-220 for one query).  variant < 0: product kernel */
 GIC_API int gic_test_attn_decode(const void* qkv, void* kcache, void* vcache, void* out, int pos, int rows, int H, int t_max, int variant, void* stream);
+/* one beam-search decode-attention launch on caller data (no cache reorder: HF DynamicCache.reorder_cache, HF:cache_utils.py:81-85, replaced by an
+ * ancestry table): rows = images * beams hypotheses; row r reads positions [0, n_prefix) from the prefill row of its image ((r / beams) * beams),
+ * position n_prefix + g from cache row anc[r * anc_ld + g] (g < pos - n_prefix), plus its own new token, which is appended to row r at `pos`.
+ * f16 != 0: q / k / v / cache are IEEE half and out_lo receives the remainder of the bf16 output (bf16x2 engine).  shared: 1 = the image's
+ * beams share one read of the prefix (attn_decode_beam_kernel), 0 = one walk per hypothesis. */
+GIC_API int gic_test_attn_decode_beam(const void* qkv, void* kcache, void* vcache, void* out, void* out_lo, const int32_t* anc, int anc_ld, int pos, int rows, int H,
+                                      int t_max, int n_prefix, int beams, int f16, int shared, void* stream);
 /* measurement hook (bench.py `roofline`): `launches` back-to-back product decode-attention launches, ASYNCHRONOUS on `stream` (the caller
  * brackets them with CUDA events); launch i works on cache plane i % planes (kcache / vcache + plane * rows*H*t_max*64 elements), the way
  * the 12 layers of a decode step do, so consecutive launches do not find each other's lines in L2.  d_pos: dev int, tokens already cached. */

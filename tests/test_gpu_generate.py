@@ -165,12 +165,15 @@ def test_beam_search_matches_hf_generation(name, dtype, emb_total):
 @pytest.mark.parametrize("name,beams,rows", [("tiny_mlp_beam5", 5, 8), ("tiny_mlp_beam5", 3, 37), ("c3_medium_tfm_beam5", 5, 6), ("tiny_mlp_eos", 4, 40)])
 def test_bf16_beam_search_ancestry_table_equals_cache_reorder(monkeypatch, name, beams, rows):
     """bf16 beam search reads the KV cache through an ancestry table (no reorder); GIC_BEAM_REORDER=1 runs HF's
-    reorder_cache gather instead (HF:cache_utils.py:81-85).  Attention sees the same keys in the same slots either way, so the
-    hypotheses must be identical -- also with EOS-terminated hypotheses and a transformer mapper with P = 40."""
+    reorder_cache gather instead (HF:cache_utils.py:81-85).  With one walk per hypothesis (GIC_BEAM_SHARED_PREFIX=0) attention sees the
+    same keys in the same slots either way, so the hypotheses must be identical -- also with EOS-terminated hypotheses and a transformer
+    mapper with P = 40.  The product kernel (the image's beams share one read of the prefix) sums in a different order: same hypotheses up
+    to bf16 near-ties (its exactness is pinned against HF in fp32 / bf16x2 by test_beam_search_matches_hf_generation and the kernel test)."""
     g = gu.load(name)
     outs = []
-    for mode in ("0", "1"):
-        monkeypatch.setenv("GIC_BEAM_REORDER", mode)
+    for reorder, shared in (("0", "0"), ("1", "0"), ("0", "1")):
+        monkeypatch.setenv("GIC_BEAM_REORDER", reorder)
+        monkeypatch.setenv("GIC_BEAM_SHARED_PREFIX", shared)
         model, _, x0 = gpu_util.product_model(g, "bf16")
         xx = oc.synthetic_embeddings(rows, int(x0.shape[1]), seed=21)
         model.num_beams = beams
@@ -180,6 +183,9 @@ def test_bf16_beam_search_ancestry_table_equals_cache_reorder(monkeypatch, name,
         outs.append(ws_bytes)
     assert torch.equal(outs[0], outs[2]), (outs[0], outs[2])
     assert outs[1] < outs[3]  # no second cache
+    n = min(outs[0].shape[1], outs[4].shape[1])
+    same = (outs[0][:, :n] == outs[4][:, :n]).all(dim=1).float().mean().item()
+    assert same >= 0.7, f"shared-prefix attention changed {1 - same:.0%} of the bf16 hypotheses"
 
 
 def test_kv_reorder_gathers_rows():

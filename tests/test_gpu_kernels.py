@@ -213,6 +213,57 @@ def test_attn_decode_kernel(variant, rows, H, pos, t_max):
     assert same(kd.cpu(), kc2) and same(vd.cpu(), vc2)
 
 
+@pytest.mark.parametrize("shared", [True, False])
+@pytest.mark.parametrize("f16", [False, True])
+@pytest.mark.parametrize("images,beams,H,n_prefix,pos,t_max", [(3, 5, 16, 40, 40, 72), (7, 5, 16, 40, 41, 72), (20, 5, 16, 40, 56, 72), (9, 4, 12, 10, 39, 40),
+                                                               (5, 8, 12, 17, 34, 48), (33, 2, 20, 0, 16, 40), (40, 5, 16, 40, 69, 70), (11, 3, 12, 16, 48, 64)])
+def test_attn_decode_beam_kernel(images, beams, H, n_prefix, pos, t_max, f16, shared):
+    """Beam-search decode attention without a cache reorder: hypothesis r attends to the image's prefix (prefill row of the image), to generated
+    position g in the cache row its ancestry table names, and to its own new token -- fp64 softmax(q K^T / 8) V on the same 16-bit inputs.  Both
+    kernels (prefix shared by the image's beams / one walk per hypothesis), both element types; the new K / V must land in row r at `pos` and the
+    rest of the cache must stay untouched (unwritten slots hold NaN and must never be read)."""
+    ops, _ = _ops()
+    rows, d, ngen = images * beams, H * 64, pos - n_prefix
+    et = torch.float16 if f16 else torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(rows * 1000 + pos + beams)
+    qkv = (torch.randn(rows, 3 * d, generator=g) * 1.5).to(et)
+    kc = torch.randn(rows, H, t_max, 64, generator=g).to(et)
+    vc = torch.randn(rows, H, t_max, 64, generator=g).to(et)
+    kc[:, :, pos:] = float("nan")
+    vc[:, :, pos:] = float("nan")
+    # generated position g of hypothesis r lives in the row of some hypothesis of the same image
+    anc = (torch.arange(rows).view(rows, 1) // beams) * beams + torch.randint(0, beams, (rows, max(ngen, 1)), generator=g)
+    anc = anc.int().contiguous()
+    as16 = lambda x: x.view(torch.bfloat16) if f16 else x  # the C ABI moves 2-byte elements
+    out = torch.zeros(rows, d, dtype=torch.bfloat16, device=DEV)
+    out_lo = torch.zeros(rows, d, dtype=torch.bfloat16, device=DEV)
+    kd, vd = as16(kc).to(DEV), as16(vc).to(DEV)
+    ops.test_attn_decode_beam(as16(qkv).to(DEV), kd, vd, out, out_lo, anc.to(DEV), pos, n_prefix, beams, f16, shared)
+    torch.cuda.synchronize()
+    q = qkv[:, :d].double().view(rows, H, 1, 64)
+    kn = qkv[:, d:2 * d].view(rows, H, 1, 64)
+    vn = qkv[:, 2 * d:].view(rows, H, 1, 64)
+    img_row = (torch.arange(rows) // beams) * beams
+    parts_k, parts_v = [kc[img_row][:, :, :n_prefix]], [vc[img_row][:, :, :n_prefix]]
+    for gi in range(ngen):
+        src = anc[:, gi].long()
+        parts_k.append(kc[src][:, :, n_prefix + gi:n_prefix + gi + 1])
+        parts_v.append(vc[src][:, :, n_prefix + gi:n_prefix + gi + 1])
+    K = torch.cat(parts_k + [kn], dim=2).double()
+    V = torch.cat(parts_v + [vn], dim=2).double()
+    p = torch.softmax((q @ K.transpose(2, 3)) / 8.0, dim=-1)
+    ref = (p @ V).view(rows, d)
+    got = out.cpu().double() + (out_lo.cpu().double() if f16 else 0.0)
+    err = (got - ref).abs().max().item()
+    tol = (2.0 ** -11 if f16 else 2.0 ** -8) * max(1.0, ref.abs().max().item())
+    assert err <= tol, f"max abs err {err} (tol {tol})"
+    kc2, vc2 = kc.clone(), vc.clone()
+    kc2[:, :, pos] = kn[:, :, 0]
+    vc2[:, :, pos] = vn[:, :, 0]
+    same = lambda a, b: torch.equal(a.view(torch.int16), b.view(torch.int16))  # bit-exact, NaN slots included
+    assert same(kd.cpu(), as16(kc2)) and same(vd.cpu(), as16(vc2))
+
+
 @pytest.mark.parametrize("rows,H,S,t_max", [(3, 12, 1, 8), (37, 12, 10, 40), (9, 16, 16, 20), (11, 16, 17, 72), (6, 12, 40, 70), (5, 20, 64, 64), (2, 12, 70, 80)])
 def test_attn_prefill_kernel(rows, H, S, t_max):
     """causal attention over the S prefix tokens of every (row, head) in fp64 on the same bf16 inputs; K / V of the S tokens
