@@ -650,14 +650,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) attn_decode_mma_kernel(const bf
 // its own cache row.  HF semantics unchanged: softmax over [prefix | own generated history | new token] (HF:models/gpt2/modeling_gpt2.py:
 // 144-226 with DynamicCache.reorder_cache replaced by the ancestry table).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int BEAM_ATTN_WARPS = 8, BEAM_ATTN_STAGES = 4;
-constexpr int BEAM_ATTN_SMEM = BEAM_ATTN_WARPS * BEAM_ATTN_STAGES * MMA_STAGE_BYTES + 128;
+template <int WARPS, int STAGES> struct BeamAttnCfg { static constexpr int SMEM_BYTES = WARPS * STAGES * MMA_STAGE_BYTES + 128; };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
-template <bool F16>
+template <bool F16, int BEAM_ATTN_WARPS, int BEAM_ATTN_STAGES>
 __global__ void __launch_bounds__(BEAM_ATTN_WARPS * 32, 1) attn_decode_beam_kernel(const bf16* qkv, bf16* kcache, bf16* vcache, bf16* out, bf16* out_lo,
                                                                                    const int* d_pos, int images, int nb, int H, int t_max, const int* anc,
                                                                                    int anc_ld, int n_prefix, StepTrace step_trace) {
@@ -685,57 +684,60 @@ __global__ void __launch_bounds__(BEAM_ATTN_WARPS * 32, 1) attn_decode_beam_kern
   const int my_items = w0 < n_items ? (n_items - 1 - w0) / wstride + 1 : 0;
   const int total_chunks = my_items * nch;
   const int g = lane >> 2, t = lane & 3;
-  // this lane's copy pieces of a chunk: keys (lane >> 3) + 4 i, 16-byte column lane & 7 -> swizzled column (lane & 7) ^ (key & 7)
+  // this lane's copy pieces of a chunk: keys (lane >> 3) + 4 i, 16-byte column lane & 7 -> swizzled column (lane & 7) ^ (key & 7).
+  // (every offset below is a 32-bit element index: the launcher checks that a cache plane has fewer than 2^31 elements)
   const int pj = lane >> 3, pc = lane & 7;
-
-  // producer cursor: item, chunk of the item, stage.  Cache rows of the generated keys this lane copies in the NEXT chunk to be issued
-  // are looked up one issue ahead (an L2 round trip that would otherwise sit in front of every generated chunk)
-  int p_item = w0, p_c = 0, p_s = 0;
-  int src_next[4];
-  auto lookup = [&](int item, int c) {
-    if (c < nchp) return;
-    const int img = item / H, gc = c - nchp, b = gc / nchg, k0 = (gc - b * nchg) * MMA_CHUNK;
+  const uint32_t hstride = (uint32_t)t_max * HD;  // elements between two (row, head) planes
+  uint32_t sw_off[4];                             // swizzled byte offset of piece i inside the K (or V) half of a stage
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int gk = k0 + pj + 4 * i;
-      src_next[i] = gk < ngen ? __ldcg(anc + (size_t)(img * nb + b) * anc_ld + gk) : -1;
-    }
+  for (int i = 0; i < 4; ++i) sw_off[i] = (uint32_t)((pj + 4 * i) * (HD * 2) + ((pc ^ ((pj + 4 * i) & 7)) << 4));
+
+  // producer cursor (no divisions on the per-chunk path): item -> (image, head), chunk -> prefix chunk p_c < nchp or (beam p_b, chunk p_g)
+  int p_item = w0, p_img = w0 / H, p_h = w0 - (w0 / H) * H, p_c = 0, p_b = 0, p_g = 0, p_s = 0;
+  // cache rows of the generated keys this lane copies in the NEXT chunk to be issued, looked up one issue ahead (an L2 round trip
+  // that would otherwise sit in front of every generated chunk)
+  int src_next[4];
+  auto lookup = [&]() {
+    if (p_c < nchp) return;
+    const int* arow = anc + (size_t)(p_img * nb + p_b) * anc_ld + p_g * MMA_CHUNK + pj;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) src_next[i] = p_g * MMA_CHUNK + pj + 4 * i < ngen ? __ldcg(arow + 4 * i) : -1;
   };
   auto issue_next = [&]() {
-    const int img = p_item / H, h = p_item - img * H;
     const uint32_t dst = ring + p_s * MMA_STAGE_BYTES;
     if (p_c < nchp) {
       const int k0 = p_c * MMA_CHUNK, nkeys = min(MMA_CHUNK, n_prefix - k0);
-      const size_t base = (((size_t)img * nb) * H + h) * t_max;  // the image's prefill row
+      const uint32_t base = ((uint32_t)(p_img * nb) * H + p_h) * hstride + (uint32_t)(k0 + pj) * HD + pc * 8;  // the image's prefill row
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = pj + 4 * i;
-        if (j < nkeys) {
-          const size_t off = (base + k0 + j) * HD + pc * 8;
-          const uint32_t o = (uint32_t)(j * (HD * 2) + ((pc ^ (j & 7)) << 4));
-          cp_async16(dst + o, kcache + off);
-          cp_async16(dst + MMA_CHUNK * HD * 2 + o, vcache + off);
+      for (int i = 0; i < 4; ++i)
+        if (pj + 4 * i < nkeys) {
+          cp_async16(dst + sw_off[i], kcache + base + i * (4 * HD));
+          cp_async16(dst + MMA_CHUNK * HD * 2 + sw_off[i], vcache + base + i * (4 * HD));
         }
-      }
     } else {
-      const int gc = p_c - nchp, b = gc / nchg, k0 = (gc - b * nchg) * MMA_CHUNK;
+      const uint32_t rel = (uint32_t)p_h * hstride + (uint32_t)(n_prefix + p_g * MMA_CHUNK + pj) * HD + pc * 8;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int j = pj + 4 * i;
-        if (src_next[i] >= 0) {  // (k0 + j < ngen)
-          const size_t off = ((((size_t)src_next[i]) * H + h) * t_max + n_prefix + k0 + j) * HD + pc * 8;
-          const uint32_t o = (uint32_t)(j * (HD * 2) + ((pc ^ (j & 7)) << 4));
-          cp_async16(dst + o, kcache + off);
-          cp_async16(dst + MMA_CHUNK * HD * 2 + o, vcache + off);
+      for (int i = 0; i < 4; ++i)
+        if (src_next[i] >= 0) {
+          const uint32_t off = (uint32_t)src_next[i] * (H * hstride) + rel + i * (4 * HD);
+          cp_async16(dst + sw_off[i], kcache + off);
+          cp_async16(dst + MMA_CHUNK * HD * 2 + sw_off[i], vcache + off);
         }
-      }
     }
-    if (++p_c == nch) { p_c = 0; p_item += wstride; }
+    // advance
     if (++p_s == STAGES) p_s = 0;
-    if (p_item < n_items) lookup(p_item, p_c);
+    if (++p_c > nchp && ++p_g == nchg) { p_g = 0; ++p_b; }
+    if (p_c == nchp) { p_b = 0; p_g = 0; }
+    if (p_c == nch) {
+      p_c = 0; p_b = 0; p_g = 0;
+      p_item += wstride;
+      p_img = p_item / H;
+      p_h = p_item - p_img * H;
+    }
+    if (p_item < n_items) lookup();
   };
   int issued = 0;
-  if (my_items > 0) lookup(w0, 0);
+  if (my_items > 0) lookup();
   for (; issued < STAGES - 1; ++issued) {
     if (issued < total_chunks) issue_next();
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -743,8 +745,7 @@ __global__ void __launch_bounds__(BEAM_ATTN_WARPS * 32, 1) attn_decode_beam_kern
 
   // q of the item's hypotheses as A fragments (row g = beam g; rows >= nb zero), requested one item ahead
   uint32_t qa_n[8];
-  auto load_q = [&](int item) {
-    const int img = item / H, h = item - img * H;
+  auto load_q = [&](int img, int h) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) qa_n[j] = 0u;
     if (g < nb) {
@@ -756,18 +757,23 @@ __global__ void __launch_bounds__(BEAM_ATTN_WARPS * 32, 1) attn_decode_beam_kern
       }
     }
   };
-  if (my_items > 0) load_q(w0);
+  int c_img = w0 / H, c_h = w0 - (w0 / H) * H;
+  if (my_items > 0) load_q(c_img, c_h);
   const int r8 = lane & 7, mlo = (lane >> 3) & 1, mhi = lane >> 4;
   const uint32_t k_row_off = (uint32_t)((8 * mhi + r8) * (HD * 2));
   const uint32_t v_row_off = (uint32_t)(MMA_CHUNK * HD * 2 + (8 * mlo + r8) * (HD * 2));
   int c_s = 0;
   for (int ii = 0; ii < my_items; ++ii) {
-    const int item = w0 + ii * wstride;
-    const int img = item / H, h = item - img * H;
+    const int img = c_img, h = c_h;
     uint32_t qa[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) qa[i] = scale_eighth<F16>(qa_n[i]);
-    if (ii + 1 < my_items) load_q(item + wstride);
+    if (ii + 1 < my_items) {
+      const int nitem = w0 + (ii + 1) * wstride;
+      c_img = nitem / H;
+      c_h = nitem - c_img * H;
+      load_q(c_img, c_h);
+    }
     // the hypotheses' new k / v rows: 16 pieces of 16 bytes per beam (8 of k, 8 of v), piece lane + 32 i
     uint4 newkv[4];
 #pragma unroll
@@ -779,19 +785,19 @@ __global__ void __launch_bounds__(BEAM_ATTN_WARPS * 32, 1) attn_decode_beam_kern
     float o[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { o[j][0] = 0.f; o[j][1] = 0.f; o[j][2] = 0.f; o[j][3] = 0.f; }
+    int beam = -1, gch = 0;  // consumer cursor: prefix chunks (beam < 0), then chunk gch of hypothesis `beam`
     for (int c = 0; c < nch; ++c) {
       if (issued < total_chunks) issue_next();
       asm volatile("cp.async.commit_group;" ::: "memory");
       ++issued;
       const uint32_t st = ring + c_s * MMA_STAGE_BYTES;
+      if (c == nchp) { beam = 0; gch = 0; }
       // which rows this chunk counts for, how many key slots it fills
-      int beam = -1, nkeys;
-      if (c < nchp) {
+      int nkeys;
+      if (beam < 0) {
         nkeys = min(MMA_CHUNK, n_prefix - c * MMA_CHUNK);
       } else {
-        const int gc = c - nchp;
-        beam = gc / nchg;
-        const int gch = gc - beam * nchg, cached = min(MMA_CHUNK, ngen - gch * MMA_CHUNK);
+        const int cached = min(MMA_CHUNK, ngen - gch * MMA_CHUNK);
         nkeys = cached;
         if (gch == nchg - 1) {  // the hypothesis' new token: slot `cached` (< 16) of its last chunk, and its own cache row
 #pragma unroll
@@ -801,7 +807,7 @@ __global__ void __launch_bounds__(BEAM_ATTN_WARPS * 32, 1) attn_decode_beam_kern
               const int kv = (pi >> 3) & 1, cc = pi & 7;
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st + kv * (MMA_CHUNK * HD * 2) + cached * (HD * 2) + ((cc ^ (cached & 7)) << 4)),
                            "r"(newkv[i].x), "r"(newkv[i].y), "r"(newkv[i].z), "r"(newkv[i].w) : "memory");
-              const size_t coff = ((((size_t)(img * nb + beam)) * H + h) * t_max + pos) * HD + cc * 8;
+              const uint32_t coff = ((uint32_t)(img * nb + beam) * H + h) * hstride + (uint32_t)pos * HD + cc * 8;
               *reinterpret_cast<uint4*>((kv ? vcache : kcache) + coff) = newkv[i];  // append (HF:cache_utils.py:102-121)
             }
           }
@@ -848,6 +854,7 @@ __global__ void __launch_bounds__(BEAM_ATTN_WARPS * 32, 1) attn_decode_beam_kern
       }
       __syncwarp();  // every lane is done reading this stage before the next iteration's copies may overwrite it
       if (++c_s == STAGES) c_s = 0;
+      if (beam >= 0 && ++gch == nchg) { gch = 0; ++beam; }
     }
     l += __shfl_xor_sync(0xffffffffu, l, 1);
     l += __shfl_xor_sync(0xffffffffu, l, 2);
@@ -871,6 +878,7 @@ __global__ void __launch_bounds__(BEAM_ATTN_WARPS * 32, 1) attn_decode_beam_kern
   trace_end(step_trace, tslot);
 }
 
+#define GIC_BEAM_ATTN_VARIANTS(X) X(8, 4) X(12, 4) X(16, 3)
 static int g_dec_sms = 0;
 constexpr int DEC_PRODUCT_VARIANT = 12;  // mma.sync kernel, 12 warps x 4 stages (profiles/r1aa_microbench.txt)
 static int g_dec_variant = DEC_PRODUCT_VARIANT;  // microbenchmark / test knob (attn_decode_set_variant); < 0 = back to the product shape
@@ -891,8 +899,11 @@ int attn_decode_configure() {
   GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<12, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<12, 4>::SMEM_BYTES));
   GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<12, 4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<12, 4>::SMEM_BYTES));
   GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_mma_kernel<12, 4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecMmaCfg<12, 4>::SMEM_BYTES));
-  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_beam_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BEAM_ATTN_SMEM));
-  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_beam_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BEAM_ATTN_SMEM));
+#define X(W, S)                                                                                                                                           \
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_beam_kernel<false, W, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, BeamAttnCfg<W, S>::SMEM_BYTES)); \
+  GIC_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_beam_kernel<true, W, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, BeamAttnCfg<W, S>::SMEM_BYTES));
+  GIC_BEAM_ATTN_VARIANTS(X)
+#undef X
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
@@ -931,6 +942,7 @@ static int launch_attn_decode_bulk(const bf16* qkv, bf16* kcache, bf16* vcache, 
 }
 
 // GIC_BEAM_SHARED_PREFIX=0: every hypothesis walks its whole context on its own (attn_decode_mma_kernel INDIRECT; measurement / tests)
+constexpr int BEAM_ATTN_DEFAULT_WARPS = 12;  // c3 decode step, bf16: 140 / 124.5 / 124.3 us per launch with 8 / 12 / 16 warps (issue bound; 16 spills) -- profiles/r2u_beam_attn_warps.txt
 static int g_beam_shared_override = -1;  // test knob (attn_decode_set_beam_shared): 0 / 1 force the kernel, < 0 = the environment's choice
 void attn_decode_set_beam_shared(int v) { g_beam_shared_override = v; }
 static bool beam_shared_prefix_enabled() {
@@ -945,18 +957,27 @@ int launch_attn_decode_indirect(const bf16* qkv, bf16* kcache, bf16* vcache, bf1
   GIC_TRY(attn_decode_configure());
   GIC_REQUIRE(anc != nullptr && beams >= 1 && n_prefix >= 0, "attn_decode_indirect: bad ancestry arguments");
   const int sms = cta_limit() > 0 && cta_limit() < g_dec_sms ? cta_limit() : g_dec_sms;
-  if (beam_shared_prefix_enabled() && beams >= 2 && beams <= 8 && rows % beams == 0) {
+  if (beam_shared_prefix_enabled() && beams >= 2 && beams <= 8 && rows % beams == 0 && (size_t)rows * H * t_max * HD < ((size_t)1 << 31)) {
     // the beams of an image as the rows of one MMA tile: the shared prefix is read once per image (attn_decode_beam_kernel)
     const int images = rows / beams;
-    const int bgrid = min(sms, ceil_div(images * H, BEAM_ATTN_WARPS));
-    if (out_lo)
-      GIC_CHECK_CUDA(launch_kernel(attn_decode_beam_kernel<true>, dim3(bgrid), dim3(BEAM_ATTN_WARPS * 32), (size_t)BEAM_ATTN_SMEM, st, qkv, kcache, vcache, out, out_lo,
-                                   d_pos, images, beams, H, t_max, anc, anc_ld, n_prefix, trace_desc()));
-    else
-      GIC_CHECK_CUDA(launch_kernel(attn_decode_beam_kernel<false>, dim3(bgrid), dim3(BEAM_ATTN_WARPS * 32), (size_t)BEAM_ATTN_SMEM, st, qkv, kcache, vcache, out,
-                                   (bf16*)nullptr, d_pos, images, beams, H, t_max, anc, anc_ld, n_prefix, trace_desc()));
-    note_launch();
-    return GIC_OK;
+    const char* wv = getenv("GIC_BEAM_ATTN_WARPS");  // measurement knob: 8 | 12 | 16 warps per CTA
+    const int want = wv ? atoi(wv) : BEAM_ATTN_DEFAULT_WARPS;
+#define X(W, S)                                                                                                                                                \
+    if (want == W) {                                                                                                                                             \
+      const int bgrid = min(sms, ceil_div(images * H, W));                                                                                                       \
+      if (out_lo)                                                                                                                                                \
+        GIC_CHECK_CUDA(launch_kernel(attn_decode_beam_kernel<true, W, S>, dim3(bgrid), dim3(W * 32), (size_t)BeamAttnCfg<W, S>::SMEM_BYTES, st, qkv, kcache, vcache, out, \
+                                     out_lo, d_pos, images, beams, H, t_max, anc, anc_ld, n_prefix, trace_desc()));                                            \
+      else                                                                                                                                                       \
+        GIC_CHECK_CUDA(launch_kernel(attn_decode_beam_kernel<false, W, S>, dim3(bgrid), dim3(W * 32), (size_t)BeamAttnCfg<W, S>::SMEM_BYTES, st, qkv, kcache, vcache, out, \
+                                     (bf16*)nullptr, d_pos, images, beams, H, t_max, anc, anc_ld, n_prefix, trace_desc()));                                    \
+      note_launch();                                                                                                                                             \
+      return GIC_OK;                                                                                                                                             \
+    }
+    GIC_BEAM_ATTN_VARIANTS(X)
+#undef X
+    set_error("attn_decode_indirect: GIC_BEAM_ATTN_WARPS=%d is not one of 8, 12, 16", want);
+    return GIC_ERR_UNSUPPORTED;
   }
   const int grid = min(sms, ceil_div(rows * H, 12));
   if (out_lo)  // fp16 q / k / v / cache, hi + lo output (bf16x2 engine)

@@ -7,12 +7,13 @@ from tools.bench_configs import build
 dev = torch.device("cuda:0")
 cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+DT = sys.argv[3] if len(sys.argv) > 3 else "bf16"
 if cfg == "c3":
-    model = build(dict(n_embd=1024, n_layer=24, n_head=16), "tfm", 512, 40, "bf16", dev, beams=5); E = 512
+    model = build(dict(n_embd=1024, n_layer=24, n_head=16), "tfm", 512, 40, DT, dev, beams=5); E = 512
 elif cfg == "c4":
-    model = build(dict(n_embd=1280, n_layer=36, n_head=20), "mlp", 1024, 10, "bf16", dev); E = 1024
+    model = build(dict(n_embd=1280, n_layer=36, n_head=20), "mlp", 1024, 10, DT, dev); E = 1024
 else:
-    model = build(bench.MODEL, "mlp", 512, 10, "bf16", dev); E = 512
+    model = build(bench.MODEL, "mlp", 512, 10, DT, dev); E = 512
 x = bench.synthetic_pool(B, E).to(dev)
 model.generate(image_embeddings=x, max_length=30, temperature=0.0)
 eng = model._get_engine()
