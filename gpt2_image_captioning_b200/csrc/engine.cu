@@ -77,6 +77,7 @@ struct Workspace {
   int64_t* ids = nullptr;          // [rows, max_new]
   unsigned char* finished = nullptr; int* first_eos = nullptr;
   int *d_step = nullptr, *d_pos = nullptr, *done_counter = nullptr;
+  SampleParams* sample_params = nullptr;  // temperature / top_p / seed of the running gic_generate_sample call (read by the captured sampling launches)
   int *fin_counter = nullptr, *all_done = nullptr;  // [sub-batch] rows finished in the current step / every row has emitted EOS
   int* live_rows = nullptr;        // [sub-batch] unfinished rows after the last step (the host sizes the compacted batch from it)
   // finished-row compaction (greedy): slot -> caption row map of the compacted batch (null while the batch is whole), scratch for the move
@@ -131,6 +132,7 @@ struct gic_engine {
   struct GraphEntry { int M; cudaGraphExec_t exec; int nodes; };  // one chunk of decode steps over M activation slots
   std::vector<GraphEntry> graphs;  // M = the whole batch, plus one entry per compacted size used so far
   void* graph_ws = nullptr; int graph_B = 0, graph_max_new = 0;
+  const float* graph_logits = nullptr;  // logits tap baked into the captured launches (sampling; null = the greedy graphs)
   bool use_graph = true;
   int graph_steps = 1;  // decode steps held by each graph
   unsigned int graph_trace_gen = 0;        // trace_generation() the graph was captured under
@@ -147,7 +149,7 @@ struct gic_engine {
   cudaStream_t sub_stream[MAX_SUB] = {};  // [0] unused (= stream)
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_SUB] = {};
   // temperature / top-p sampling (gic_generate_sample): set for the duration of one call
-  struct SampleCfg { bool on = false; float temperature = 1.f, top_p = 1.f; unsigned long long seed = 0; float* logits = nullptr; } sample;
+  struct SampleCfg { bool on = false; float temperature = 1.f, top_p = 1.f; unsigned long long seed = 0; float* logits = nullptr; int ld = 0; } sample;
   int sub_batches = 1;  // GIC_SUBBATCH=n: decode as n row groups (whole 128-row GEMM tiles) on n streams, each kernel limited to 1/n of the SMs
   // per-kernel-class CUDA-event profiling (bench.py roofline leg); generate runs eagerly while enabled
   bool profiling = false;
@@ -377,6 +379,7 @@ static void carve(const gic_engine* e, void* base, int B, int max_new, int beams
   w->fin_counter = c.take<int>(gic_engine::MAX_SUB);
   w->all_done = c.take<int>(gic_engine::MAX_SUB);
   w->live_rows = c.take<int>(gic_engine::MAX_SUB);
+  w->sample_params = c.take<SampleParams>(1);
   if (w->beams == 1) {
     w->row_map_buf = c.take<int>(w->rows); w->src_slot = c.take<int>(w->rows);
     w->h_tmp = c.take<float>((size_t)w->rows * d);
@@ -536,6 +539,9 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
   const float* h = h_buf + first_off;
   int n_parts = 0;
   bool packed = false;  // the token arrives as w.rs_best (exactly re-scored head) instead of argmax partials
+  // row stride of the logits tap: V for the per-step tap of the tests; the sampling scratch of the tensor-core engines is padded to a
+  // multiple of 32 floats so that the GEMM epilogue stores whole aligned 16-byte vectors and the sampler's bulk copies start aligned
+  const int ld_tap = (e->sample.on && e->tc) ? e->sample.ld : e->V;
   if (e->fuse_ln && e->fuse_lnf) {
     // rows of bf16(h) in w.a at the same (stride, offset) as h in its buffer; statistics indexed by the body row
     const long off = first_off;
@@ -544,7 +550,7 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
     in.row_mul = (int)(row_stride / d); in.row_off = (int)(off / d); in.a_row_stride = row_stride;
     ActOut o; o.f32 = logits_tap;  // null on the product path: logits never reach HBM
     ProfScope ps(e, "lm_head", st);
-    GIC_TRY(linear(e, e->lm_head, a, rows, EPI_NONE, o, e->V, st, w.part_val, w.part_idx, &n_parts, w.n_parts_max, &in));
+    GIC_TRY(linear(e, e->lm_head, a, rows, EPI_NONE, o, ld_tap, st, w.part_val, w.part_idx, &n_parts, w.n_parts_max, &in));
   } else {
     { ProfScope ps(e, "layernorm", st); GIC_TRY(launch_layernorm(h, row_stride, e->lnf.w, e->lnf.b, w.a.out(), rows, d, st)); }
     if (e->rescore_head && !logits_tap && w.rs_best) {
@@ -583,7 +589,7 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
     } else {
       ActOut o; o.f32 = logits_tap;  // null on the product path: logits never reach HBM
       ProfScope ps(e, "lm_head", st);
-      GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, e->V, st, w.part_val, w.part_idx, &n_parts, w.n_parts_max));
+      GIC_TRY(linear(e, e->lm_head, w.a, rows, EPI_NONE, o, ld_tap, st, w.part_val, w.part_idx, &n_parts, w.n_parts_max));
     }
   }
   if (e->sample.on) {
@@ -591,7 +597,7 @@ static int lm_head_and_token(const gic_engine* e, const Workspace& w, const floa
     GIC_REQUIRE(logits_tap != nullptr, "sampling needs the logits tap");
     ProfScope pss(e, "sample", st);
     GIC_TRY(launch_sample_top_p(logits_tap, rows, e->V, e->sample.temperature, e->sample.top_p, e->sample.seed, w.d_step, -1, w.part_val, w.part_idx,
-                                w.n_parts_max, st));
+                                w.n_parts_max, st, w.sample_params, ld_tap));
     n_parts = 1;
   }
   ProfScope psf(e, "finalize", st);
@@ -1015,6 +1021,7 @@ static int generate_greedy_on_stream(gic_engine* e, const float* x, int max_new,
                                    e->cfg.eos_token_id, st));
   if (w.splitk_counters) GIC_CHECK_CUDA(cudaMemsetAsync(w.splitk_counters, 0, 4096 * sizeof(int), st));
   if (w.rs_counters) GIC_CHECK_CUDA(cudaMemsetAsync(w.rs_counters, 0, 2 * sizeof(int), st));
+  if (e->sample.on) GIC_TRY(launch_set_sample_params(w.sample_params, e->sample.temperature, e->sample.top_p, e->sample.seed, st));
   if (e->profiling) GIC_TRY(launch_spin(150000000LL, st));  // ~75 ms: lets the host queue ahead so events time the device only
   { ProfScope ps(e, "mapper", st); GIC_TRY(mapper_forward(e, w, x, st)); }
   GIC_TRY(launch_embed_prefix(w.prefix, e->P_img, e->task_prefix, e->P_task, e->wpe, w.h, nullptr, B, d, st));
@@ -1032,7 +1039,9 @@ static int generate_greedy_on_stream(gic_engine* e, const float* x, int max_new,
   // benchmark runs every chunk at full size. ----
   const int steps = max_new - 1;
   constexpr int DECODE_CHUNK = 4;
-  const bool graph_ok = e->use_graph && !e->profiling && logits_out == nullptr && steps >= 2;
+  // (sampling taps every step's logits into the SAME scratch rows and reads its parameters from device memory: capturable; the
+  // per-step logits tap of the tests is not)
+  const bool graph_ok = e->use_graph && !e->profiling && (logits_out == nullptr || e->sample.on) && steps >= 2;
   static const bool per_step = [] { const char* v = getenv("GIC_GRAPH_PER_STEP"); return v && v[0] == '1'; }();
   const char* ne = getenv("GIC_NO_EARLY_EXIT");  // (read per call: a test flips it inside one process)
   const bool no_early = ne && ne[0] == '1';
@@ -1049,10 +1058,12 @@ static int generate_greedy_on_stream(gic_engine* e, const float* x, int max_new,
   // the steps that do not fill a whole chunk go first, as ordinary launches (the host is far ahead of the device after prefill)
   const int lead = graph_ok ? steps % chunk : 0;
   for (; s_next <= lead; ++s_next) GIC_TRY(eager_step(s_next));
-  if (!(e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new && e->graph_steps == chunk && e->graph_trace_gen == gic::trace_generation())) {
+  if (!(e->graph_ws == workspace && e->graph_B == B && e->graph_max_new == max_new && e->graph_steps == chunk && e->graph_trace_gen == gic::trace_generation() &&
+        e->graph_logits == logits_out)) {
     for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
     e->graphs.clear();
     e->graph_ws = workspace; e->graph_B = B; e->graph_max_new = max_new; e->graph_steps = chunk; e->graph_trace_gen = gic::trace_generation();
+    e->graph_logits = logits_out;
   }
   // the chunk graph over the current batch view (captured on first use, one per batch size)
   auto chunk_graph = [&](const gic_engine::GraphEntry** out) -> int {
@@ -1061,7 +1072,7 @@ static int generate_greedy_on_stream(gic_engine* e, const float* x, int max_new,
     const unsigned long long before = tl_launches;
     GIC_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     int r = GIC_OK;
-    for (int s = 0; s < chunk && r == GIC_OK; ++s) r = decode_step_all(e, wc, nullptr, st);
+    for (int s = 0; s < chunk && r == GIC_OK; ++s) r = decode_step_all(e, wc, e->sample.on ? logits_out : nullptr, st);
     cudaError_t ce = cudaStreamEndCapture(st, &graph);
     gic_engine::GraphEntry ge;
     ge.M = wc.rows; ge.exec = nullptr;
@@ -1144,13 +1155,15 @@ int gic_generate_greedy(gic_engine* e, const float* x, int batch, int max_new, i
 }
 
 // the `temperature > 0` branch of ImageCaptioningModel.generate (src/models.py:400-449): the greedy driver with every step's
-// logits tapped into logits_scratch and the token drawn by sample_top_p_kernel (eager launches: the tap disables the graph)
+// logits tapped into logits_scratch and the token drawn by sample_top_p_kernel; the decode steps replay the same chunked CUDA graphs as
+// the greedy path (temperature / top_p / seed are read from the workspace, so one capture serves every call)
 int gic_generate_sample(gic_engine* e, const float* x, int batch, int max_new, float temperature, float top_p, unsigned long long seed,
                         int64_t* ids_out, int32_t* gen_len_out, float* logits_scratch, void* workspace, size_t workspace_bytes, void* stream) {
   GIC_TRY(check_ready(e));
   GIC_REQUIRE(logits_scratch != nullptr, "null argument");
   GIC_REQUIRE(temperature > 0.f && top_p > 0.f, "sampling needs temperature > 0 and top_p > 0 (temperature %g, top_p %g)", temperature, top_p);
   e->sample.on = true; e->sample.temperature = temperature; e->sample.top_p = top_p; e->sample.seed = seed; e->sample.logits = logits_scratch;
+  e->sample.ld = (e->V + 31) / 32 * 32;
   const int r = gic_generate_greedy(e, x, batch, max_new, ids_out, gen_len_out, logits_scratch, workspace, workspace_bytes, stream);
   e->sample.on = false;
   return r;

@@ -188,8 +188,13 @@ struct CompactArgs {
 int launch_compact_rows(const CompactArgs& c, cudaStream_t st);
 // temperature / top-p sampling of one token per row from fp32 logits [B, V] (src/models.py:400-449); the token goes to slot 0 of the
 // row's (value, index) partials.  step: *d_step unless step_override >= 0 (the Philox counter is (row, step)).
+// dev_params (optional): the kernel reads temperature / top_p / seed from device memory instead of its arguments, so that a CUDA graph
+// holding the launch can be replayed by calls with other values (launch_set_sample_params writes them, outside the graph).
+struct SampleParams { float inv_temperature, top_p; unsigned long long seed; };
+int launch_set_sample_params(SampleParams* dst, float temperature, float top_p, unsigned long long seed, cudaStream_t st);
 int launch_sample_top_p(const float* logits, int B, int V, float temperature, float top_p, unsigned long long seed, const int* d_step,
-                        int step_override, float* part_val, int* part_idx, int part_ld, cudaStream_t st);
+                        int step_override, float* part_val, int* part_idx, int part_ld, cudaStream_t st, const SampleParams* dev_params = nullptr,
+                        long ld = 0 /* row stride of `logits` in floats; 0 = V */);
 int launch_init_decode_state(unsigned char* finished, int* first_eos, int B, int max_new, int* d_step, int* d_pos, int* done_counter,
                              int P, int* fin_counter, int* all_done, int64_t* ids, int eos, cudaStream_t st);
 int launch_gen_len(const int* first_eos, int B, int max_new, int* gen_len_out, cudaStream_t st);

@@ -71,22 +71,27 @@ int launch_argmax_partials(const float* logits, int B, int V, float* part_val, i
 
 // ---------------------------------------------------------------------------------------------------------------
 // Temperature / nucleus (top-p) sampling: the `temperature > 0` branch of ImageCaptioningModel.generate
-// (src/models.py:400-449).  One block per row keeps the row's V unnormalised probabilities exp((z_i - max) / T) in shared
-// memory (50 257 x 4 B = 196 KB).  The reference sorts the row, takes the cumulative softmax and keeps every token up to and
-// including the first whose cumulative probability exceeds top_p (:413-432); the same set is {p_i >= tau} for
-// tau = the largest probability value whose tail mass sum_{p_i >= tau} p_i / S still exceeds top_p, found by bisection over the
-// float bit patterns (31 block-wide sums from shared memory, no sort).  The token is then drawn from the kept mass in index
-// order with one Philox4x32-10 uniform per (seed, row, step).  Parity with torch.multinomial is distributional only.
-// The token is handed to finalize_token_kernel as a single (value, index) "partial", so the EOS rules are shared with greedy.
+// (src/models.py:400-449).  One block per row; the row's V logits arrive in shared memory (50 257 x 4 B = 196 KB) as eight
+// cp.async.bulk chunks (the running maximum is taken chunk by chunk while the later ones are in flight) and are replaced in place by
+// the unnormalised probabilities p_i = exp((z_i - max) / T).  The reference sorts the row, takes the cumulative softmax and keeps
+// every token up to and including the first whose cumulative probability exceeds top_p (:413-432), then draws from the renormalised
+// kept set.  That kept set is {i : sum of p_j over p_j > p_i  <=  top_p S}, so drawing from it is REJECTION SAMPLING on the full
+// distribution: draw a token by inverse CDF in index order (one Philox4x32-10 uniform per (seed, row, step, attempt)), accept it if
+// the mass strictly above its probability is <= top_p S (one block-wide sum), else draw again.  The acceptance probability is the
+// nucleus mass >= top_p, so 1 / top_p attempts on average (two sweeps of shared memory each) instead of a sort or a 31-pass
+// bisection.  After SAMPLE_ATTEMPTS rejections (tiny top_p on a flat row) the exact threshold is found by bisection over the float
+// bit patterns and the token drawn from the kept mass directly -- the same distribution, so the mixture is exact.
+// Parity with torch.multinomial is distributional only.  The token is handed to finalize_token_kernel as a single (value, index)
+// "partial", so the EOS rules are shared with greedy.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
   const unsigned long long p = (unsigned long long)a * b;
   *hi = (uint32_t)(p >> 32);
   return (uint32_t)p;
 }
-__device__ __forceinline__ float philox_uniform(unsigned long long seed, uint32_t c0, uint32_t c1) {
+__device__ __forceinline__ float philox_uniform(unsigned long long seed, uint32_t c0, uint32_t c1, uint32_t c2 = 0u) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  uint32_t x0 = c0, x1 = c1, x2 = 0u, x3 = 0u;
+  uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = 0u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     uint32_t h0, h1;
@@ -99,6 +104,9 @@ __device__ __forceinline__ float philox_uniform(unsigned long long seed, uint32_
 }
 
 constexpr int SAMPLE_THREADS = 512;
+constexpr int SAMPLE_CHUNKS = 8;    // bulk copies per row
+constexpr int SAMPLE_ATTEMPTS = 4;  // rejection rounds before the exact bisection
+constexpr int SAMPLE_PAD = 8;       // floats of slack in front of / behind the row in shared memory (16-byte alignment of the bulk part)
 
 __device__ __forceinline__ float sample_block_sum(float v, float* red) {
   v = warp_sum(v);
@@ -111,33 +119,136 @@ __device__ __forceinline__ float sample_block_sum(float v, float* red) {
   return t;
 }
 
-__global__ void __launch_bounds__(SAMPLE_THREADS) sample_top_p_kernel(const float* __restrict__ logits, int V, float inv_temperature, float top_p,
+__global__ void __launch_bounds__(SAMPLE_THREADS) sample_top_p_kernel(const float* __restrict__ logits, int V, long ld, float inv_temperature, float top_p,
                                                                       unsigned long long seed, const int* __restrict__ d_step, int step_override,
-                                                                      float* __restrict__ part_val, int* __restrict__ part_idx, int part_ld) {
-  extern __shared__ float prob[];  // [V]
+                                                                      float* __restrict__ part_val, int* __restrict__ part_idx, int part_ld,
+                                                                      const SampleParams* __restrict__ dev_params) {
+  extern __shared__ __align__(16) float sample_smem[];  // [SAMPLE_PAD + V + SAMPLE_PAD]
   __shared__ float red[SAMPLE_THREADS / 32];
   __shared__ float s_scan[SAMPLE_THREADS];
+  __shared__ float s_wtot[SAMPLE_THREADS / 32];
   __shared__ int s_tok;
-  const int b = blockIdx.x, t = threadIdx.x;
-  const float* z = logits + (size_t)b * V;
+  __shared__ float s_ptok;
+  __shared__ __align__(8) unsigned long long s_bar[SAMPLE_CHUNKS];
+  if (dev_params) {  // graph replays: the call's temperature / top_p / seed live in device memory, not in the captured arguments
+    inv_temperature = __ldcg(&dev_params->inv_temperature);
+    top_p = __ldcg(&dev_params->top_p);
+    seed = __ldcg(&dev_params->seed);
+  }
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const float* z = logits + (size_t)b * ld;
+  // the row in three parts: `head` floats up to the first 16-byte boundary of the global address, `body` floats in whole 16-byte
+  // units (bulk copies), `tail` floats after them; prob[i] sits where the body lands 16-byte aligned in shared memory too
+  const int head = min(V, (int)(((16u - (unsigned)((uintptr_t)z & 15u)) & 15u) >> 2));
+  const int body = ((V - head) >> 2) << 2;
+  float* prob = sample_smem + SAMPLE_PAD - head;
+  const int per = ((((body + SAMPLE_CHUNKS - 1) / SAMPLE_CHUNKS) + 3) >> 2) << 2;  // floats per chunk (multiple of 4)
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(s_bar);
+  if (t == 0) {
+    for (int c = 0; c < SAMPLE_CHUNKS; ++c) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * c) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int c = 0; c < SAMPLE_CHUNKS; ++c) {
+      const int c0 = min(body, c * per), c1 = min(body, c0 + per);
+      const uint32_t bytes = (uint32_t)(c1 - c0) * 4u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + 8 * c), "r"(bytes) : "memory");
+      if (bytes)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         (uint32_t)__cvta_generic_to_shared(prob + head + c0)),
+                     "l"(z + head + c0), "r"(bytes), "r"(bar0 + 8 * c)
+                     : "memory");
+    }
+  }
+  // the unaligned ends (at most 3 + 3 floats) through ordinary loads
   float m = -INFINITY;
-  for (int i = t; i < V; i += SAMPLE_THREADS) m = fmaxf(m, z[i]);
+  if (t < head) { const float v = z[t]; prob[t] = v; m = v; }
+  if (head + body + t < V) { const float v = z[head + body + t]; prob[head + body + t] = v; m = fmaxf(m, v); }
+  __syncthreads();  // barriers initialised before anyone polls them
+  for (int c = 0; c < SAMPLE_CHUNKS; ++c) {
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar0 + 8 * c), "r"(0u) : "memory");
+    const int c0 = head + min(body, c * per), c1 = head + min(body, c * per + per);
+    for (int i = c0 + t; i < c1; i += SAMPLE_THREADS) m = fmaxf(m, prob[i]);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((t & 31) == 0) red[t >> 5] = m;
+  if (lane == 0) red[warp] = m;
   __syncthreads();
   for (int w = 0; w < SAMPLE_THREADS / 32; ++w) m = fmaxf(m, red[w]);
-  float s = 0.f;
-  for (int i = t; i < V; i += SAMPLE_THREADS) {
-    const float p = expf((z[i] - m) * inv_temperature);  // softmax(z / T) up to the common factor
+  // p_i in place; thread t owns the contiguous slice [t * seg, (t + 1) * seg) (bank = (3 t + j) mod 32: conflict-free) -- the
+  // inverse CDF below walks the row in index order
+  const int seg = (V + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
+  const int i0 = min(V, t * seg), i1 = min(V, i0 + seg);
+  float part = 0.f;
+  for (int i = i0; i < i1; ++i) {
+    const float p = expf((prob[i] - m) * inv_temperature);  // softmax(z / T) up to the common factor
     prob[i] = p;
-    s += p;
+    part += p;
   }
-  const float S = sample_block_sum(s, red);
-  // tau: bit pattern of the smallest kept probability.  Invariant: tail(lo) > top_p * S >= tail(hi)   (tail(t) = sum of p >= t)
-  uint32_t lo = 0u, hi = __float_as_uint(1.0f) + 1u;
-  if (top_p < 1.0f) {
-    const float want = top_p * S;
+  // inclusive scan of the 512 slice sums (fixed order: deterministic)
+  float incl = part;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_wtot[warp] = incl;
+  __syncthreads();  // (also: every p_i is in place)
+  float woff = 0.f, total = 0.f;
+#pragma unroll
+  for (int w = 0; w < SAMPLE_THREADS / 32; ++w) {
+    if (w < warp) woff += s_wtot[w];
+    total += s_wtot[w];
+  }
+  s_scan[t] = woff + incl;
+  const float before = woff + incl - part;
+  const int step = step_override >= 0 ? step_override : __ldcg(d_step);
+  const float want = top_p * total;
+  // token at inverse-CDF position `target` of the mass selected by `keep` (bit pattern threshold; 0 = the whole row)
+  auto draw = [&](float target, float my_before, float my_after, float my_part, uint32_t keep) {
+    if (t == 0) s_tok = -1;
+    __syncthreads();
+    if (my_part > 0.f && target >= my_before && target < my_after) {
+      float run = my_before;
+      int tok = -1;
+      float ptok = 0.f;
+      for (int i = i0; i < i1; ++i) {
+        const float p = prob[i];
+        if (p > 0.f && __float_as_uint(p) >= keep) {
+          tok = i;  // the last kept token of the slice catches rounding at its upper edge
+          ptok = p;
+          run += p;
+          if (target < run) break;
+        }
+      }
+      s_tok = tok;
+      s_ptok = ptok;
+    }
+    __syncthreads();
+    if (s_tok < 0) {  // target landed on / beyond the total through rounding: the last kept token of the row
+      if (t == 0) {
+        for (int i = V - 1; i >= 0; --i)
+          if (prob[i] > 0.f && __float_as_uint(prob[i]) >= keep) { s_tok = i; s_ptok = prob[i]; break; }
+      }
+      __syncthreads();
+    }
+  };
+  bool accepted = false;
+  for (int attempt = 0; attempt < SAMPLE_ATTEMPTS && !accepted; ++attempt) {
+    const float target = philox_uniform(seed, (uint32_t)b, (uint32_t)step, (uint32_t)attempt) * total;
+    draw(target, before, s_scan[t], part, 0u);
+    if (top_p >= 1.0f) { accepted = true; break; }
+    const float ptok = s_ptok;
+    float above = 0.f;
+    for (int i = t; i < V; i += SAMPLE_THREADS) {
+      const float p = prob[i];
+      above += p > ptok ? p : 0.f;
+    }
+    accepted = sample_block_sum(above, red) <= want;  // (block-uniform: every thread holds the same sum)
+  }
+  if (!accepted) {
+    // exact path.  tau: bit pattern of the smallest kept probability.  Invariant: tail(lo) > top_p * S >= tail(hi)   (tail(x) = sum of p >= x)
+    uint32_t lo = 0u, hi = __float_as_uint(1.0f) + 1u;
     while (hi - lo > 1u) {
       const uint32_t mid = lo + ((hi - lo) >> 1);
       float a = 0.f;
@@ -145,67 +256,60 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_top_p_kernel(const floa
         const float p = prob[i];
         a += (__float_as_uint(p) >= mid) ? p : 0.f;
       }
-      const float tail = sample_block_sum(a, red);
-      if (tail > want) lo = mid; else hi = mid;  // (block-uniform: every thread holds the same sum)
+      if (sample_block_sum(a, red) > want) lo = mid; else hi = mid;
     }
-  }
-  // draw from the kept mass in index order: thread t owns the contiguous slice [t * seg, (t + 1) * seg)
-  const int seg = (V + SAMPLE_THREADS - 1) / SAMPLE_THREADS;
-  const int i0 = t * seg, i1 = min(V, i0 + seg);
-  float part = 0.f;
-  for (int i = i0; i < i1; ++i) {
-    const float p = prob[i];
-    part += (__float_as_uint(p) >= lo) ? p : 0.f;
-  }
-  s_scan[t] = part;
-  if (t == 0) s_tok = -1;
-  __syncthreads();
-  if (t == 0) {  // serial inclusive scan of 512 partials
-    float run = 0.f;
-    for (int j = 0; j < SAMPLE_THREADS; ++j) { run += s_scan[j]; s_scan[j] = run; }
-  }
-  __syncthreads();
-  const float total = s_scan[SAMPLE_THREADS - 1];
-  const int step = step_override >= 0 ? step_override : __ldcg(d_step);
-  const float target = philox_uniform(seed, (uint32_t)b, (uint32_t)step) * total;
-  const float before = t == 0 ? 0.f : s_scan[t - 1];
-  if (part > 0.f && target >= before && target < s_scan[t]) {
-    float run = before;
-    int tok = -1;
+    float kpart = 0.f;
     for (int i = i0; i < i1; ++i) {
       const float p = prob[i];
-      if (__float_as_uint(p) >= lo) {
-        tok = i;  // the last kept token of the slice catches rounding at its upper edge
-        run += p;
-        if (target < run) break;
-      }
+      kpart += (__float_as_uint(p) >= lo) ? p : 0.f;
     }
-    s_tok = tok;
+    __syncthreads();
+    s_scan[t] = kpart;
+    __syncthreads();
+    if (t == 0) {  // serial inclusive scan of 512 partials (rare path)
+      float run = 0.f;
+      for (int j = 0; j < SAMPLE_THREADS; ++j) { run += s_scan[j]; s_scan[j] = run; }
+    }
+    __syncthreads();
+    const float ktotal = s_scan[SAMPLE_THREADS - 1];
+    const float target = philox_uniform(seed, (uint32_t)b, (uint32_t)step, (uint32_t)SAMPLE_ATTEMPTS) * ktotal;
+    draw(target, t == 0 ? 0.f : s_scan[t - 1], s_scan[t], kpart, lo);
   }
-  __syncthreads();
   if (t == 0) {
-    int tok = s_tok;
-    if (tok < 0) {  // target landed on / beyond the total through rounding: the last kept token of the row
-      for (int i = V - 1; i >= 0; --i)
-        if (__float_as_uint(prob[i]) >= lo) { tok = i; break; }
-    }
     part_val[(size_t)b * part_ld] = 1.0f;
-    part_idx[(size_t)b * part_ld] = tok;
+    part_idx[(size_t)b * part_ld] = s_tok;
   }
 }
 
+__global__ void set_sample_params_kernel(SampleParams* dst, float inv_temperature, float top_p, unsigned long long seed) {
+  dst->inv_temperature = inv_temperature;
+  dst->top_p = top_p;
+  dst->seed = seed;
+}
+
+int launch_set_sample_params(SampleParams* dst, float temperature, float top_p, unsigned long long seed, cudaStream_t st) {
+  GIC_REQUIRE(dst != nullptr && temperature > 0.f && top_p > 0.f, "set_sample_params: bad argument");
+  set_sample_params_kernel<<<1, 1, 0, st>>>(dst, 1.0f / temperature, top_p, seed);
+  GIC_CHECK_CUDA(cudaGetLastError());
+  note_launch();
+  return GIC_OK;
+}
+
 int launch_sample_top_p(const float* logits, int B, int V, float temperature, float top_p, unsigned long long seed, const int* d_step,
-                        int step_override, float* part_val, int* part_idx, int part_ld, cudaStream_t st) {
+                        int step_override, float* part_val, int* part_idx, int part_ld, cudaStream_t st, const SampleParams* dev_params, long ld) {
   GIC_REQUIRE(temperature > 0.f, "sample_top_p: temperature must be > 0 (0 is the greedy path)");
   GIC_REQUIRE(top_p > 0.f, "sample_top_p: top_p must be > 0");
-  const size_t smem = (size_t)V * sizeof(float);
+  const size_t smem = ((size_t)V + 2 * SAMPLE_PAD) * sizeof(float);
   GIC_REQUIRE(smem <= 200 * 1024, "sample_top_p: a row of %d probabilities does not fit in shared memory", V);
+  if (ld <= 0) ld = V;
+  GIC_REQUIRE(ld >= V, "sample_top_p: leading dimension %ld < V = %d", ld, V);
   static std::atomic<bool> configured{false};  // (engine contexts may be driven from several host threads)
   if (!configured.load(std::memory_order_acquire)) {
     GIC_CHECK_CUDA(cudaFuncSetAttribute(sample_top_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured.store(true, std::memory_order_release);
   }
-  sample_top_p_kernel<<<B, SAMPLE_THREADS, smem, st>>>(logits, V, 1.0f / temperature, top_p, seed, d_step, step_override, part_val, part_idx, part_ld);
+  sample_top_p_kernel<<<B, SAMPLE_THREADS, smem, st>>>(logits, V, ld, 1.0f / temperature, top_p, seed, d_step, step_override, part_val, part_idx, part_ld,
+                                                       dev_params);
   GIC_CHECK_CUDA(cudaGetLastError());
   note_launch();
   return GIC_OK;

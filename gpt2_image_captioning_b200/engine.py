@@ -243,7 +243,11 @@ class CaptionEngine:
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         if B > 0 and max_new_tokens > 0:
-            scratch = torch.empty(B, self.vocab, dtype=torch.float32, device=self.device)
+            # one step's logits; kept with the engine: the captured decode graphs hold its address
+            scratch = getattr(self, "_sample_scratch", None)
+            ld = (self.vocab + 31) // 32 * 32  # rows padded for aligned vector stores / bulk copies (include/gic_b200.h)
+            if scratch is None or scratch.numel() < B * ld:
+                self._sample_scratch = scratch = torch.empty(B * ld, dtype=torch.float32, device=self.device)
             ops.generate_sample(self.handle, x, max_new_tokens, float(temperature), float(top_p), int(seed), ids, gen_len, scratch,
                                 self.workspace(B, max_new_tokens))
         return ids, gen_len

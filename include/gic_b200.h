@@ -146,7 +146,10 @@ GIC_API int gic_generate_greedy(gic_engine* e, const float* image_embeddings /* 
 /* replaces the sampling branch of ImageCaptioningModel.generate (src/models.py:400-449, temperature > 0): logits / temperature,
  * nucleus filter (keep the sorted tokens up to and including the first whose cumulative probability exceeds top_p; top_p >= 1 keeps
  * all), one multinomial draw per row and step from a Philox4x32-10 stream keyed by (seed, row, step).  Same outputs and EOS rules as
- * gic_generate_greedy; logits_scratch: dev fp32 [B, V].  Parity with torch.multinomial is distributional. */
+ * gic_generate_greedy; logits_scratch: dev fp32 [B, V rounded up to a multiple of 32] (one step's logits, 16-byte aligned; the tensor-core
+ * engines pad the rows so that the LM-head epilogue and the sampler move whole aligned vectors).  The decode steps replay the same CUDA
+ * graphs as the greedy call (temperature / top_p / seed are read from the workspace), keyed by the scratch address: pass the same buffer
+ * on every call.  Parity with torch.multinomial is distributional. */
 GIC_API int gic_generate_sample(gic_engine* e, const float* image_embeddings /* dev [B,E] */, int batch, int max_new_tokens, float temperature,
                                 float top_p, unsigned long long seed, int64_t* ids_out, int32_t* gen_len_out, float* logits_scratch,
                                 void* workspace, size_t workspace_bytes, void* stream);

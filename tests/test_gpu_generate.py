@@ -339,6 +339,26 @@ def test_sampling_path_behaviour(dtype):
     assert torch.equal(greedy, cold)
 
 
+@pytest.mark.parametrize("dtype", ["bf16x2", "bf16"])
+def test_sampling_replays_the_decode_graphs(monkeypatch, dtype):
+    """The sampling path runs its decode steps from the same chunked CUDA graphs as the greedy one; temperature / top_p / seed are
+    read from device memory, so a graph captured by one call serves the next with other values: tokens equal the eager
+    (GIC_NO_GRAPH=1) launches for every (seed, temperature, top_p), call after call on one engine."""
+    g = gu.load("tiny_mlp_eos")
+    model, _, x = gpu_util.product_model(g, dtype)
+    xx = x[:24].to(DEV)
+    eng = model._get_engine()
+    calls = [(11, 1.0, 0.9), (12, 1.0, 0.9), (11, 1.0, 0.9), (11, 0.7, 0.5), (13, 1.3, 1.0)]
+    graph = [eng.generate_sample(xx, 14, temperature=t, top_p=p, seed=s)[0].cpu() for s, t, p in calls]
+    monkeypatch.setenv("GIC_NO_GRAPH", "1")
+    model2, _, _ = gpu_util.product_model(g, dtype)
+    eng2 = model2._get_engine()
+    eager = [eng2.generate_sample(xx, 14, temperature=t, top_p=p, seed=s)[0].cpu() for s, t, p in calls]
+    for a, b in zip(graph, eager):
+        assert torch.equal(a, b)
+    assert torch.equal(graph[0], graph[2]) and not torch.equal(graph[0], graph[1]) and not torch.equal(graph[0], graph[3])
+
+
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
 def test_early_exit_once_every_row_has_finished(monkeypatch, dtype):
     """The reference loop stops before a step once every row has emitted EOS (src/models.py:390-391).  The engine runs the decode

@@ -5,7 +5,7 @@ import torch
 import bench
 from tools.bench_configs import build
 dev = torch.device("cuda:0")
-cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"
+cfg = sys.argv[1] if len(sys.argv) > 1 else "c3"  # c3 | c4 | c5 | c2 (the headline model) ; a 4th argument "sample" profiles temperature 1.0 / top_p 0.9
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 DT = sys.argv[3] if len(sys.argv) > 3 else "bf16"
 if cfg == "c3":
@@ -15,10 +15,11 @@ elif cfg == "c4":
 else:
     model = build(bench.MODEL, "mlp", 512, 10, DT, dev); E = 512
 x = bench.synthetic_pool(B, E).to(dev)
-model.generate(image_embeddings=x, max_length=30, temperature=0.0)
+kw = dict(temperature=1.0, top_p=0.9) if (len(sys.argv) > 4 and sys.argv[4] == "sample") else dict(temperature=0.0)
+model.generate(image_embeddings=x, max_length=30, **kw)
 eng = model._get_engine()
 eng.profile(True)
-model.generate(image_embeddings=x, max_length=30, temperature=0.0)
+model.generate(image_embeddings=x, max_length=30, **kw)
 torch.cuda.synchronize()
 prof = eng.profile_read()
 eng.profile(False)
