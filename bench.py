@@ -10,7 +10,7 @@ A "step" = one pass of the hot path over one batch: mapper -> prefill -> 29 KV-c
 `e2e` times the public `model.generate(image_embeddings=<pinned host tensor>)` call, H2D + D2H inside the timed region.
 
 The headline is quoted in the arithmetic mode that MEETS north_star's caption tolerance (>= 99 % of greedy captions identical to
-the fp32 reference): `bf16x2` -- bf16 hi + lo tensor-core operands, fp16 KV cache, exactly re-scored LM head; 99.46 % on the 5 000
+the fp32 reference): `bf16x2` -- bf16 hi + lo tensor-core operands, fp16 KV cache, exactly re-scored LM head; 99.40 % on the 5 000
 rows of configs[1] (profiles/r2_parity.json).  `modes` carries the same measurement for plain `bf16` (faster, 79 % of captions --
 below the contract) and `fp32` (CUDA cores, token-exact), each with its parity entry, so every throughput number has its parity
 next to it.
