@@ -7,7 +7,7 @@ and `tests/test_oracle.py::test_full_fixtures_extend_the_reference_ones` checks 
 reference-made fixture on the rows they share.  Beam search (not in the reference) comes from HF GenerationMixin on the
 same weights, as in make_golden.py.
 
-    python tests/golden/make_golden_full.py [c2 c3 c4 c5]
+    python tests/golden/make_golden_full.py [c2 c3 c4 c5 c3x c4x]     (c3x / c4x: 256-row greedy sets of configs 3 / 4)
 
 Every greedy fixture also stores, per row, the smallest top-1 - top-2 logit gap the fp32 oracle saw over the caption
 (`min_gap`, `min_gap_step`): a row whose CUDA tokens differ is audited against it (a gap below ~1e-5 is a legitimate fp32
@@ -114,6 +114,28 @@ def case_c4():
     ids, gap, gstep = greedy_with_gaps(o, x, 30, chunk=16)
     save("c4_large_mlp_full16", spec, o, ids=ids, min_gap=gap, min_gap_step=gstep, batch=np.array(16), n_rows=np.array(16),
          batch_lens=batch_lens(ids, 16, 30), max_length=np.array(30), emb_seed=np.array(1), emb_total=np.array(16),
+         eos=np.array(oc.EOS_TOKEN_ID), eos_row_scale=np.array(1.0), source=np.array("oracle kv_cache=True"))
+
+
+def case_c3x():
+    """configs[2] greedy on 256 rows (the 32-row file stays: it shares rows with the reference-made fixture and carries the beam set)."""
+    spec = oc.ModelSpec(gpt="medium", mapper="transformer", embed_dim=512, prefix_length=40, hidden_length=10, mapper_layers=8)
+    o = oc.CaptionOracle(spec)
+    x = oc.synthetic_embeddings(256, 512, 1)
+    ids, gap, gstep = greedy_with_gaps(o, x, 30, chunk=64)
+    save("c3_medium_tfm_full256", spec, o, ids=ids, min_gap=gap, min_gap_step=gstep, batch=np.array(256), n_rows=np.array(256),
+         batch_lens=batch_lens(ids, 256, 30), max_length=np.array(30), emb_seed=np.array(1), emb_total=np.array(256),
+         eos=np.array(oc.EOS_TOKEN_ID), eos_row_scale=np.array(1.0), source=np.array("oracle kv_cache=True"))
+
+
+def case_c4x():
+    """configs[3] on 256 rows: enough rows for a caption-match RATE of the 36-layer model (one flip in 16 rows is 6 %)."""
+    spec = oc.ModelSpec(gpt="large", embed_dim=1024, prefix_length=10)
+    o = oc.CaptionOracle(spec)
+    x = oc.synthetic_embeddings(256, 1024, 1)
+    ids, gap, gstep = greedy_with_gaps(o, x, 30, chunk=64)
+    save("c4_large_mlp_full256", spec, o, ids=ids, min_gap=gap, min_gap_step=gstep, batch=np.array(256), n_rows=np.array(256),
+         batch_lens=batch_lens(ids, 256, 30), max_length=np.array(30), emb_seed=np.array(1), emb_total=np.array(256),
          eos=np.array(oc.EOS_TOKEN_ID), eos_row_scale=np.array(1.0), source=np.array("oracle kv_cache=True"))
 
 

@@ -71,10 +71,12 @@ def test_c2_all_5000_rows_through_the_job_api(dtype, min_match):
         assert np.median(gaps) < 0.02, f"bf16x2 mismatches at large reference margins: {audits[:5]}"
 
 
-@pytest.mark.parametrize("name,rows", [("c3_medium_tfm_full32", 32), ("c4_large_mlp_full16", 16)])
+@pytest.mark.parametrize("name,rows", [("c3_medium_tfm_full32", 32), ("c4_large_mlp_full16", 16), ("c3_medium_tfm_full256", 256),
+                                       ("c4_large_mlp_full256", 256)])
 @pytest.mark.parametrize("dtype,min_match", MODES)
 def test_c3_c4_greedy_full_fixture(name, rows, dtype, min_match):
-    """configs[2] greedy (GPT-2 medium + 8-layer transformer mapper, P = 40, 32 rows) and configs[3] (GPT-2 large, E = 1024, 16 rows)."""
+    """configs[2] greedy (GPT-2 medium + 8-layer transformer mapper, P = 40) and configs[3] (GPT-2 large, E = 1024): the 32- / 16-row
+    files share rows with the reference-made fixtures; the 256-row files give the caption-match RATE of the deeper models."""
     g = gu.load(name)
     model, _, x = gpu_util.product_model(g, dtype)
     ids = model.generate(image_embeddings=x.to(DEV), max_length=30, temperature=0.0).cpu().numpy()
@@ -84,11 +86,21 @@ def test_c3_c4_greedy_full_fixture(name, rows, dtype, min_match):
     audits = _audit_rows(g, ids, ref)
     _report(test="c3_c4_full", case=name, dtype=dtype, rows=rows, caption_match=float(row_ok.mean()), audits=audits[:8])
     if dtype == "bf16":
-        assert row_ok.mean() >= 0.4, f"{name}/bf16: {row_ok.mean():.3f}"  # (16 - 32 rows: the 5 000-row test carries the statistic)
+        assert row_ok.mean() >= 0.4, f"{name}/bf16: {row_ok.mean():.3f}"  # (the 5 000-row test carries the statistic)
         return
-    for a in audits:  # fp32 / bf16x2 on a few dozen rows: exact, or a near-tie of the reference
-        assert a["ref_min_gap"] < (1e-4 if dtype == "fp32" else 2e-3), f"{name}/{dtype}: mismatch is not a near-tie: {a}"
-    assert len(audits) <= 1
+    if rows < 64:
+        for a in audits:  # fp32 / bf16x2 on a few dozen rows: exact, or a near-tie of the reference
+            assert a["ref_min_gap"] < (1e-4 if dtype == "fp32" else 2e-3), f"{name}/{dtype}: mismatch is not a near-tie: {a}"
+        assert len(audits) <= 1
+        return
+    if dtype == "fp32":
+        for a in audits:
+            assert a["ref_min_gap"] < 1e-4, f"{name}/fp32: mismatch that is not a near-tie of the reference: {a}"
+        assert row_ok.mean() >= 0.995, f"{name}/fp32: {row_ok.mean():.4f}"
+    else:  # bf16x2: flips sit at the reference's small margins (these deeper models: median per-caption minimum gap 5e-3)
+        gaps = np.array([a["ref_min_gap"] for a in audits] or [0.0])
+        assert np.median(gaps) < 0.02, f"{name}/bf16x2 mismatches at large reference margins: {audits[:5]}"
+        assert row_ok.mean() >= 0.97, f"{name}/bf16x2: {row_ok.mean():.4f}"
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16x2", "bf16"])
@@ -172,7 +184,7 @@ def test_c5_rat_captions_in_the_timed_dtypes(c5_store, dtype):
     mapper = MLPMappingNetwork(prefix_length=10, embed_dim=512, gpt_dim=768)
     mapper.load_state_dict(mapper_ref.state_dict())
     rat = RetrievalAugmentedTransformer(512, 4, "mean", mapper, tokenizer=StubTokenizer(), gpt=gpt, engine_dtype=dtype).to(DEV)
-    x = q[:256].to(DEV)
+    x = q.to(DEV)  # all 1024 queries
     got = rat.generate(store, 5, 5, x, max_length=30, temperature=0.0)
     aug = store.retrieve_and_aggregate(x, top_i=5, top_k=5)
     plain = rat._generate_on_engine(aug, 30, 0.0, 0.9)
@@ -180,7 +192,7 @@ def test_c5_rat_captions_in_the_timed_dtypes(c5_store, dtype):
     rat.engine_dtype = "fp32"
     ref = rat._generate_on_engine(aug, 30, 0.0, 0.9)
     match = float((got == ref).all(dim=1).float().mean())
-    _report(test="c5_rat_tokens", dtype=dtype, rows=256, caption_match_vs_fp32_engine=match)
+    _report(test="c5_rat_tokens", dtype=dtype, rows=int(x.shape[0]), caption_match_vs_fp32_engine=match)
     assert match >= (0.98 if dtype == "bf16x2" else 0.6), match
 
 

@@ -165,7 +165,8 @@ def test_oracle_equals_live_reference_on_fresh_inputs():
 
 
 @pytest.mark.parametrize("full,ref_made,rows", [("c2_small_mlp_full5000", "c2_small_mlp_first1024", 1024), ("c3_medium_tfm_full32", "c3_medium_tfm", 8),
-                                                ("c4_large_mlp_full16", "c4_large_mlp", 4), ("c3_medium_tfm_beam5_full32", "c3_medium_tfm_beam5", 4)])
+                                                ("c4_large_mlp_full16", "c4_large_mlp", 4), ("c3_medium_tfm_beam5_full32", "c3_medium_tfm_beam5", 4),
+                                                ("c3_medium_tfm_full256", "c3_medium_tfm", 8), ("c4_large_mlp_full256", "c4_large_mlp", 4)])
 def test_full_fixtures_extend_the_reference_ones(full, ref_made, rows):
     """The full-size fixtures (tests/golden/make_golden_full.py: oracle, KV-cached; beam through HF) agree token for token with the
     fixtures the UNMODIFIED reference produced on every row they share -- same pinned weights (fingerprint), same embeddings."""

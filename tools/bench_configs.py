@@ -95,7 +95,7 @@ def run_dtype(a, dev, B, N, want, dtype, par):
         ms, ids = timed(lambda: model.generate(image_embeddings=x, max_length=N, temperature=0.0))
         print(json.dumps({"config": "c3: GPT-2 medium + 8-layer transformer mapper, prefix_len 40, beam 5 (ancestry-table KV)", "batch": B, "dtype": a.dtype, "in_flight": IN_FLIGHT,
                           "ms_per_batch": ms, "captions_per_s": B / ms * 1e3, "ids_shape": list(ids.shape),
-                          "parity": {k: par.get(k) for k in ("c3_beam5_32_rows_vs_hf", "c3_medium_tfm_full32")}}), flush=True)
+                          "parity": {k: par.get(k) for k in ("c3_beam5_32_rows_vs_hf", "c3_medium_tfm_full32", "c3_medium_tfm_full256")}}), flush=True)
         del model
         torch.cuda.empty_cache()
     if "c4" in want:
@@ -103,7 +103,7 @@ def run_dtype(a, dev, B, N, want, dtype, par):
         x = bench.synthetic_pool(B, 1024).to(dev)
         ms, ids = timed(lambda: model.generate(image_embeddings=x, max_length=N, temperature=0.0))
         print(json.dumps({"config": "c4: GPT-2 large + MLP mapper, 1024-d embeddings, greedy", "batch": B, "dtype": a.dtype, "in_flight": IN_FLIGHT, "ms_per_batch": ms,
-                          "captions_per_s": B / ms * 1e3, "ids_shape": list(ids.shape), "parity": {"c4_large_mlp_full16": par.get("c4_large_mlp_full16")}}), flush=True)
+                          "captions_per_s": B / ms * 1e3, "ids_shape": list(ids.shape), "parity": {k: par.get(k) for k in ("c4_large_mlp_full16", "c4_large_mlp_full256")}}), flush=True)
         del model
         torch.cuda.empty_cache()
     if "c5" in want:
@@ -126,7 +126,7 @@ def run_dtype(a, dev, B, N, want, dtype, par):
         print(json.dumps({"config": "c5: RAT, top-5 over 118 287 images -> caption rows of 591 753 -> mean-add, GPT-2 small greedy", "batch": B,
                           "dtype": a.dtype, "in_flight": IN_FLIGHT, "ms_per_batch": ms, "captions_per_s": B / ms * 1e3, "retrieve_and_aggregate_ms": ms_r,
                           "top5_over_591753_rows_ms": ms_s, "top5_scan_TFLOPs": 2.0 * B * n_cap * 512 / ms_s * 1e-9,
-                          "ids_shape": list(ids.shape), "parity": {"c5_rat_256_rows_vs_fp32_engine": par.get("c5_rat_256_rows_vs_fp32_engine"),
+                          "ids_shape": list(ids.shape), "parity": {"c5_rat_rows_vs_fp32_engine": par.get("c5_rat_rows_vs_fp32_engine"),
                                                                    "retrieval": bench.parity_table().get("retrieval")}}), flush=True)
         del model, store
         torch.cuda.empty_cache()

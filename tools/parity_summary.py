@@ -29,7 +29,7 @@ for line in open(src):
     elif t == "c3_beam5_full":
         m["c3_beam5_32_rows_vs_hf"] = {"hypotheses_identical": r["rows_identical"], "rows": r["rows"], "tokens_identical": r["token_match"]}
     elif t == "c5_rat_tokens":
-        m["c5_rat_256_rows_vs_fp32_engine"] = {"captions_identical": r["caption_match_vs_fp32_engine"]}
+        m["c5_rat_rows_vs_fp32_engine"] = {"rows": r.get("rows", 256), "captions_identical": r["caption_match_vs_fp32_engine"]}
     elif t == "step0_logits" and r.get("case") == "c1_small_mlp_b64":
         m["c1_step0_logits_max_rel_err"] = r["max_rel_err"]
 for r in (json.loads(l) for l in open(src)):
