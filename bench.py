@@ -99,6 +99,58 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+class Watchdog:
+    """A bench run must end with ONE JSON line even when a phase hangs (a rank stuck in a collective, a broken interconnect on the
+    box): every phase has a time budget, the line assembled so far is handed over after every phase, and when a budget runs out rank 0
+    prints that line with the key "incomplete" naming the phase, and every rank leaves with os._exit.  Before the headline numbers
+    exist there is nothing to print: the run then ends with exit code 3 and a message on stderr instead of hanging."""
+
+    def __init__(self):
+        self.rank, self.emit, self.line = 0, None, None
+        self.name, self.budget, self.deadline, self.finished = "start-up", 0.0, None, False
+        self.lock = threading.Lock()
+
+    def start(self, rank: int, emit, name: str, budget_s: float) -> None:
+        self.rank, self.emit = rank, emit
+        self.phase(name, budget_s)
+        threading.Thread(target=self._run, daemon=True, name="bench-watchdog").start()
+
+    def phase(self, name: str, budget_s: float) -> None:
+        with self.lock:
+            self.name, self.budget, self.deadline = name, float(budget_s), time.monotonic() + float(budget_s)
+
+    def have(self, line: dict) -> None:
+        with self.lock:
+            self.line = dict(line)
+
+    def done(self) -> None:
+        with self.lock:
+            self.finished = True
+
+    def _run(self) -> None:
+        while True:
+            time.sleep(1.0)
+            with self.lock:
+                if self.finished:
+                    return
+                late = self.deadline is not None and time.monotonic() > self.deadline
+                line, name, budget = self.line, self.name, self.budget
+            if not late:
+                continue
+            msg = f"phase '{name}' did not finish within its {budget:.0f} s budget"
+            try:
+                sys.stderr.write(f"[bench watchdog, rank {self.rank}] {msg}\n")
+                sys.stderr.flush()
+                if line is not None and self.rank == 0 and self.emit is not None:
+                    line["incomplete"] = msg + "; the keys that phase would have added are missing"
+                    self.emit(line)
+            finally:
+                os._exit(0 if line is not None else 3)
+
+
+WATCHDOG = Watchdog()
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 def build_product_model(dtype: str, device, dims: dict | None = None, embed_dim: int = E, prefix: int = P, init_on_device: bool = False):
     """Random-init weights of the named architecture (seed 0: GPT-2 first, then the mapper -- SURVEY.md 8(d)).  init_on_device draws the
@@ -308,66 +360,12 @@ def run_product(args, rank: int, world: int, local_rank: int) -> dict | None:
     model = head.pop("_model")
     eng = model._get_engine()
     value, ms_total_per_step = head["value"], head["ms_per_step"]
-
-    # the other arithmetic modes, each next to its parity entry
-    modes = {}
-    if not args.no_modes:
-        for dt, st in (("bf16", K), ("bf16x2", K), ("fp32", max(1, min(2, K)))):
-            if dt == args.dtype:
-                m = {k: v for k, v in head.items() if k in ("value", "ms_per_step", "e2e", "in_flight_1", "weight_bytes", "engine_contexts")}
-            else:
-                m = measure(dt, st)
-                m.pop("_model").invalidate_engine()
-                torch.cuda.empty_cache()
-            modes[dt] = m
-
-    # the literal jobs of configs[1] and configs[3], host to host, sharded over the ranks (strong scaling), with the gather
-    job = None if args.no_job else run_jobs(args, model, dev, rank, world)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return None
-
     pk = peaks()
     par = parity_table()
-    for dt, m in modes.items():
-        m["parity"] = par.get(dt)
-    eng = model._get_engine()  # (the jobs dropped the engine to make room for the GPT-2 large one)
-    # ---- per-class CUDA-event timing of the same step (eager launches: every sample carries an isolated launch's ramp) ------
-    eng.profile(True)
-    eng.generate_greedy(dev_batches[0], N)
-    prof = eng.profile_read()
-    eng.profile(False)
-    ctx_mean = P + (1 + (N - 1)) / 2.0  # context incl. the new token, mean over decode steps t = 1 .. N-1
-    step_total_ms = sum(v["total_ms"] for v in prof.values())
-    classes = {name: {"launches": v["launches"], "avg_us": v["total_ms"] / max(1, v["launches"]) * 1e3, "share": v["total_ms"] / step_total_ms}
-               for name, v in prof.items()}
-    prefill_ms = sum(v["total_ms"] for n, v in prof.items() if n in ("prefill_gemm", "attn_prefill", "mapper"))
-
-    # ---- roofline: the kernel family with the largest share of the decode step, timed inside the timed region's CUDA graph ----
-    tl = in_graph_timeline(eng, dev_batches[0], N, B, args.dtype, pk) if args.dtype != "fp32" else None
-    roof = roof_attn = None
-    if tl:
-        shares = tl["share_of_step"]
-        dom = max(("gemm_body", "lm_head", "attn_decode"), key=lambda k: shares[k])
-        roof = dict(tl[dom], share_of_decode_step=shares[dom])
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu --set full capture
-        if os.path.isfile(tpath):
-            roof["traffic"] = json.load(open(tpath)).get(dom + "_" + args.dtype, json.load(open(tpath)).get(dom))
-        roof_attn = dict(tl["attn_decode"], share_of_decode_step=shares["attn_decode"])
-    # whole decode step against max(t_HBM, t_tensor)  
-    byt, flo = algorithmic_decode_step(B, ctx_mean, args.dtype)
-    step_ms_eff = (ms_total_per_step - prefill_ms) / max(1, N - 1)
-    step_roof = {"alg_bytes": byt, "alg_flops": flo, "t_hbm_us": byt / (pk["hbm_gbs"] * 1e9) * 1e6,
-                 "t_tensor_us": flo / (pk["tf_sustained"] * 1e12) * 1e6, "measured_us": step_ms_eff * 1e3,
-                 "single_chain_us": tl["decode_step_span_us"] if tl else None,
-                 "achieved_GBps": byt / (step_ms_eff * 1e-3) / 1e9, "achieved_TFLOPs": flo / (step_ms_eff * 1e-3) / 1e12,
-                 "note": f"measured_us = (batch time - prefill) / {N - 1} with {F} batches in flight: throughput-effective; single_chain_us = one chain's step inside the graph"}
-    bound = max(step_roof["t_hbm_us"], step_roof["t_tensor_us"])
-    step_roof["frac_of_max_bound"] = bound / step_roof["measured_us"]
-    step_roof["frac_of_max_bound_single_chain"] = bound / tl["decode_step_span_us"] if tl else None
-
+    # The line is assembled as the phases finish, and handed to the watchdog after every phase: should a later phase hang (a rank stuck
+    # in a collective, a box with a broken interconnect), the watchdog prints what has been measured so far with the key "incomplete"
+    # instead of leaving the driver without a line.  The headline (value, e2e, clocks) comes first, then rank 0's own measurements (no
+    # collectives: roofline, in-graph timeline, sampling), then the phases every rank takes part in (the other modes, the sharded jobs).
     line = {
         "metric": "captions/sec (GPT-2 greedy, 30 tokens/caption)", "value": value, "unit": "captions/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms_total_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
@@ -382,17 +380,82 @@ def run_product(args, rank: int, world: int, local_rank: int) -> dict | None:
         "parity": par.get(args.dtype),
         "clocks": head.get("clocks"), "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "in_flight_1": head["in_flight_1"],
         "weight_bytes": head["weight_bytes"], "engine_contexts": head["engine_contexts"],
-        "roofline": roof, "roofline_attention": roof_attn, "frac_of_max_bound": step_roof["frac_of_max_bound"], "decode_step_roofline": step_roof,
-        "in_graph": None if not tl else {k: tl[k] for k in ("decode_step_span_us", "launch_gap_us_per_step", "share_of_step", "gap_share_of_step",
-                                                            "per_gemm_avg_us", "gemm_body", "lm_head", "attn_decode", "method")},
-        "kernel_classes_eager_events": classes, "modes": modes, "job": job,
     }
-    if not args.no_sampling:
-        line["sampling"] = sampling_throughput(model, dev_batches[0], N)
+    WATCHDOG.have(line)
+
+    if rank == 0:
+        WATCHDOG.phase("roofline (eager kernel classes + in-graph timeline)", 150)
+        # ---- per-class CUDA-event timing of the same step (eager launches: every sample carries an isolated launch's ramp) ------
+        eng.profile(True)
+        eng.generate_greedy(dev_batches[0], N)
+        prof = eng.profile_read()
+        eng.profile(False)
+        ctx_mean = P + (1 + (N - 1)) / 2.0  # context incl. the new token, mean over decode steps t = 1 .. N-1
+        step_total_ms = sum(v["total_ms"] for v in prof.values())
+        classes = {name: {"launches": v["launches"], "avg_us": v["total_ms"] / max(1, v["launches"]) * 1e3, "share": v["total_ms"] / step_total_ms}
+                   for name, v in prof.items()}
+        prefill_ms = sum(v["total_ms"] for n, v in prof.items() if n in ("prefill_gemm", "attn_prefill", "mapper"))
+
+        # ---- roofline: the kernel family with the largest share of the decode step, timed inside the timed region's CUDA graph ----
+        tl = in_graph_timeline(eng, dev_batches[0], N, B, args.dtype, pk) if args.dtype != "fp32" else None
+        roof = roof_attn = None
+        if tl:
+            shares = tl["share_of_step"]
+            dom = max(("gemm_body", "lm_head", "attn_decode"), key=lambda k: shares[k])
+            roof = dict(tl[dom], share_of_decode_step=shares[dom])
+            tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+            if os.path.isfile(tpath):
+                roof["traffic"] = json.load(open(tpath)).get(dom + "_" + args.dtype, json.load(open(tpath)).get(dom))
+            roof_attn = dict(tl["attn_decode"], share_of_decode_step=shares["attn_decode"])
+        # whole decode step against max(t_HBM, t_tensor)  
+        byt, flo = algorithmic_decode_step(B, ctx_mean, args.dtype)
+        step_ms_eff = (ms_total_per_step - prefill_ms) / max(1, N - 1)
+        step_roof = {"alg_bytes": byt, "alg_flops": flo, "t_hbm_us": byt / (pk["hbm_gbs"] * 1e9) * 1e6,
+                     "t_tensor_us": flo / (pk["tf_sustained"] * 1e12) * 1e6, "measured_us": step_ms_eff * 1e3,
+                     "single_chain_us": tl["decode_step_span_us"] if tl else None,
+                     "achieved_GBps": byt / (step_ms_eff * 1e-3) / 1e9, "achieved_TFLOPs": flo / (step_ms_eff * 1e-3) / 1e12,
+                     "note": f"measured_us = (batch time - prefill) / {N - 1} with {F} batches in flight: throughput-effective; single_chain_us = one chain's step inside the graph"}
+        bound = max(step_roof["t_hbm_us"], step_roof["t_tensor_us"])
+        step_roof["frac_of_max_bound"] = bound / step_roof["measured_us"]
+        step_roof["frac_of_max_bound_single_chain"] = bound / tl["decode_step_span_us"] if tl else None
+        line.update({
+            "roofline": roof, "roofline_attention": roof_attn, "frac_of_max_bound": step_roof["frac_of_max_bound"], "decode_step_roofline": step_roof,
+            "in_graph": None if not tl else {k: tl[k] for k in ("decode_step_span_us", "launch_gap_us_per_step", "share_of_step", "gap_share_of_step",
+                                                                "per_gemm_avg_us", "gemm_body", "lm_head", "attn_decode", "method")},
+            "kernel_classes_eager_events": classes})
+        WATCHDOG.have(line)
+        if not args.no_sampling:
+            WATCHDOG.phase("sampling", 90)
+            line["sampling"] = sampling_throughput(model, dev_batches[0], N)
+            WATCHDOG.have(line)
+
+    # the other arithmetic modes, each next to its parity entry; every rank takes part (barriers, max over ranks)
+    if not args.no_modes:
+        WATCHDOG.phase("modes (bf16 / fp32 beside the headline)", 200)
+        modes = {}
+        for dt, st in (("bf16", K), ("bf16x2", K), ("fp32", max(1, min(2, K)))):
+            if dt == args.dtype:
+                m = {k: v for k, v in head.items() if k in ("value", "ms_per_step", "e2e", "in_flight_1", "weight_bytes", "engine_contexts")}
+            else:
+                m = measure(dt, st)
+                m.pop("_model").invalidate_engine()
+                torch.cuda.empty_cache()
+            m["parity"] = par.get(dt)
+            modes[dt] = m
+        line["modes"] = modes
+        WATCHDOG.have(line)
+
+    # the literal jobs of configs[1] and configs[3], host to host, sharded over the ranks (strong scaling), with the gather
+    if not args.no_job:
+        WATCHDOG.phase("jobs (c2 5 000 rows, c4 118 287 rows, host to host)", 300)
+        line["job"] = run_jobs(args, model, dev, rank, world)
+        WATCHDOG.have(line)
+
+    if rank != 0:
+        return None
     if world == 1 and not args.no_cpu_baseline:
+        WATCHDOG.phase("cpu baseline", 240)
         line["cpu_baseline"] = cpu_baseline_sample(rows=args.cpu_rows, max_length=N)
-    if world > 1:
-        dist.destroy_process_group()
     return line
 
 
@@ -424,7 +487,14 @@ def run_jobs(args, model, dev, rank: int, world: int) -> dict:
     from gpt2_image_captioning_b200.sharding import shard_range
     N = args.max_length
     out = {}
-    host_group = dist.new_group(backend="gloo") if world > 1 else None  # the ids are gathered host to host, not over NCCL
+    if world > 1:
+        # the ids are gathered host to host, not over NCCL.  One node by contract: gloo over the loopback interface (the container
+        # hostname may not resolve to a routable address), and a finite timeout so that a broken gather raises instead of hanging
+        import datetime
+        os.environ.setdefault("GLOO_SOCKET_IFNAME", "lo")
+        host_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=180))
+    else:
+        host_group = None
 
     def one(name, mdl, emb, batch, runs=1):
         lo, hi = shard_range(emb.shape[0], (rank + 1) % world, world)
@@ -458,7 +528,7 @@ def run_jobs(args, model, dev, rank: int, world: int) -> dict:
                      "ids_shape": list(ids.shape), "batch": batch, "cross_rank_rows_checked": int(sum(p.shape[0] for _, p in probes)),
                      "gathered_ids_equal_independent_generation": ok, "dtype": mdl.engine_dtype}
 
-    one("c2_5000_rows_gpt2_small", model, synthetic_pool(POOL_ROWS, E).pin_memory(), args.batch, runs=3)
+    one("c2_5000_rows_gpt2_small", model, synthetic_pool(POOL_ROWS, E).pin_memory(), args.batch, runs=2 if world == 1 else 1)
     if not args.no_c4_job:
         model.invalidate_engine()
         torch.cuda.empty_cache()
@@ -631,7 +701,29 @@ def main():
                    "127.0.0.1", "--master-port", "29577", os.path.abspath(__file__)] + sys.argv[1:]
             os.dup2(json_fd, 1)  # the ranks inherit the real stdout; rank 0 prints the line
             sys.exit(subprocess.call(cmd))
+        emitted = []
+        emit_lock = threading.Lock()
+
+        def emit(ln: dict) -> None:  # exactly one line, whoever gets there first (the run or its watchdog)
+            with emit_lock:
+                if not emitted:
+                    emitted.append(True)
+                    os.write(json_fd, (json.dumps(ln) + "\n").encode())
+
+        WATCHDOG.start(rank, emit, "start-up + headline (process group, weights, CUDA graphs, timed steps)", 420)
         line = run_product(args, rank, world, local_rank)
+        if line is not None:
+            sys.stdout.flush()
+            emit(line)
+        # the line is out: tearing the process group down must not be able to hang the run
+        WATCHDOG.have({"done": True})
+        WATCHDOG.phase("process-group shutdown", 30)
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+        WATCHDOG.done()
+        return
     if line is not None:
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())

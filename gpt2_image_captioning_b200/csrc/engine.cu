@@ -749,8 +749,8 @@ static int create_context_resources(gic_engine* e) {
             cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaHostAlloc((void**)&e->h_done, 4 * sizeof(int), cudaHostAllocDefault) == cudaSuccess &&
-       cudaEventCreateWithFlags(&e->ev_done[0], cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess &&
-       cudaEventCreateWithFlags(&e->ev_done[1], cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
+       cudaEventCreateWithFlags(&e->ev_done[0], cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&e->ev_done[1], cudaEventDisableTiming) == cudaSuccess;
   for (int i = 1; i < gic_engine::MAX_SUB && ok; ++i)
     ok = cudaStreamCreateWithFlags(&e->sub_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
