@@ -305,3 +305,40 @@ def test_generate_batches_in_flight_equals_sequential():
     a = generate_batches(fake_generate, x, 6, 5, in_flight=1)
     b = generate_batches(fake_generate, x, 6, 5, in_flight=3)
     assert a.shape == (23, 6) and torch.equal(a, b)
+
+
+def test_rejection_rule_of_the_sampler_is_the_reference_nucleus():
+    """sample_top_p_kernel (csrc/lmhead.cu) draws from the FULL softmax and accepts a token iff the probability mass strictly above
+    its own probability is <= top_p * S.  That accepted set must be exactly the set the reference keeps (sort, cumulative softmax,
+    keep everything up to and including the first token whose cumulative probability exceeds top_p, src/models.py:413-432) -- then
+    rejection sampling IS sampling from the reference's renormalised nucleus.  Checked on random rows, peaked rows and rows with ties."""
+    import numpy as np
+    import torch
+
+    rng = np.random.default_rng(0)
+    rows = [rng.normal(size=500) * s for s in (0.5, 2.0, 6.0)]
+    tied = rng.normal(size=500) * 2.0
+    tied[100:140] = tied[100]  # a plateau of equal logits that straddles some thresholds
+    rows.append(tied)
+    for z_np in rows:
+        for top_p in (0.05, 0.5, 0.9, 0.999):
+            for temperature in (0.7, 1.0):
+                z = torch.from_numpy(z_np / temperature).float().unsqueeze(0)
+                sl, si = torch.sort(z, descending=True)
+                cp = torch.cumsum(torch.softmax(sl, dim=-1), dim=-1)
+                rem = cp > top_p
+                rem[:, 1:] = rem[:, :-1].clone()
+                rem[:, 0] = False
+                kept_ref = ~rem.scatter(1, si, rem)[0].numpy()
+                p = np.exp((z[0].double().numpy() - z[0].double().numpy().max()))
+                S = p.sum()
+                above = np.array([p[p > pi].sum() for pi in p])
+                kept_rule = above <= top_p * S
+                # ties: the reference's sort order decides which of several EQUAL probabilities fall behind the cut, the rule keeps or
+                # drops a plateau as a whole; away from a plateau at the cut the two sets are identical
+                differ = kept_ref != kept_rule
+                if differ.any():
+                    cut = p[differ]
+                    assert np.allclose(cut, cut[0]) and (np.isclose(p, cut[0]).sum() > 1), (top_p, temperature, int(differ.sum()))
+                    assert kept_rule[differ].all()  # the plateau is kept whole: a superset of the reference's set by equal-probability tokens only
+                assert kept_rule[np.argmax(p)]
