@@ -3,7 +3,7 @@
 A decode step of one 1024-row batch is a chain of ~60 short kernels (6-17 us each, one persistent CTA per SM); the tail of
 every kernel, the ~1 us hand-over to its successor and the HBM-bound attention leave SMs / the tensor pipe idle.  A second
 batch on its own stream (own engine handle = own workspace, KV cache and CUDA graph; own host thread because the decode driver
-polls the early-exit flag) fills those holes: measured 41.2k -> 45.4k captions/s on one B200 (tools/two_in_flight.py), token ids
+polls the early-exit flag) fills those holes: measured 41.2k -> 45.4k captions/s on one B200 (tools/experiments/two_in_flight.py), token ids
 identical.  Rows of different batches never interact, so this is the same job in a different order.
 
 `map_batches(fn, batches, in_flight)` runs `fn(batch)` for every batch, batch i on worker i % in_flight.  Each worker has a

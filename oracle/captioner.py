@@ -187,7 +187,8 @@ def gpt2_forward(w: dict, inputs_embeds: torch.Tensor, kv: list | None = None, l
     rnd=round_bf16 this is a CPU emulation of that mode (fp32 accumulation, residual stream and logits), used to
     separate "bf16 rounding" from "kernel bug" in the parity tests.  `rnd_w` / `rnd_kv` (default: same as
     `rnd`) give the weight matrices and the q/k/v (KV-cache) stores their own rounding, so that mixed
-    schemes (fp16 activations with split weights, fp32 KV ...) can be screened on the CPU; `rnd_head` = (activation,
+    schemes (fp16 activations with split weights, fp32 KV ...) can be screened on the CPU (`rnd_kv` may also be a
+    (q, k, v) tuple of roundings); `rnd_head` = (activation,
     weight) roundings of the LM head alone (default: those of the body).
     Returns fp32 logits [B, T, V] (or [B, 1, V] if last_only)."""
     B, T, d = inputs_embeds.shape
@@ -200,8 +201,11 @@ def gpt2_forward(w: dict, inputs_embeds: torch.Tensor, kv: list | None = None, l
     h = inputs_embeds + w["wpe"][pos]  # HF :579-585 -- prefix tokens also get wpe
     for li, lw in enumerate(w["layers"]):
         a = rnd(layer_norm(h, lw["ln1_w"], lw["ln1_b"]))
-        qkv = rkv(a @ rw(lw["attn_w"]) + lw["attn_b"])  # Conv1D = addmm(bias, x, W[in,out])
-        q, k, v = qkv.split(d, dim=-1)
+        qkv = a @ rw(lw["attn_w"]) + lw["attn_b"]  # Conv1D = addmm(bias, x, W[in,out])
+        if isinstance(rkv, tuple):  # (q, k, v) roundings screened one at a time
+            q, k, v = (r(t) for r, t in zip(rkv, qkv.split(d, dim=-1)))
+        else:
+            q, k, v = rkv(qkv).split(d, dim=-1)
         q = q.view(B, T, H, hd).transpose(1, 2)
         k = k.view(B, T, H, hd).transpose(1, 2)
         v = v.view(B, T, H, hd).transpose(1, 2)

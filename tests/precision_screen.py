@@ -76,6 +76,11 @@ SCHEMES = {
     "hx_fp16_Ax2": (r_split(r_fp16, r_fp16), r_fp16, r_fp16, 2, 1.5, "exact_head"),
     "hx_bf16x2_kv16": (r_split(r_bf16, r_bf16), r_split(r_bf16, r_bf16), r_fp16, 3, 2.0, "exact_head"),
     "hx_bf16x2_kvbf16": (r_split(r_bf16, r_bf16), r_split(r_bf16, r_bf16), r_bf16, 3, 2.0, "exact_head"),
+    # which of q / k / v pays for the fp16 stores of the split mode (everything else hi + lo, exact head)
+    "hx_bf16x2_q16": (r_split(r_bf16, r_bf16), r_split(r_bf16, r_bf16), (r_fp16, r_id, r_id), 3, 2.0, "exact_head"),
+    "hx_bf16x2_k16": (r_split(r_bf16, r_bf16), r_split(r_bf16, r_bf16), (r_id, r_fp16, r_id), 3, 2.0, "exact_head"),
+    "hx_bf16x2_v16": (r_split(r_bf16, r_bf16), r_split(r_bf16, r_bf16), (r_id, r_id, r_fp16), 3, 2.0, "exact_head"),
+    "hx_bf16x2_kv16_q32": (r_split(r_bf16, r_bf16), r_split(r_bf16, r_bf16), (r_id, r_fp16, r_fp16), 3, 2.0, "exact_head"),
     "head_only_fp16": (r_id, r_id, r_id, 0, 0, "head_fp16"),
     "head_only_bf16": (r_id, r_id, r_id, 0, 0, "head_bf16"),
     "Aonly_fp16": (r_fp16, r_id, r_id, 0, 0),
@@ -129,10 +134,15 @@ def main():
     ap.add_argument("--tokens", type=int, default=30)
     ap.add_argument("--schemes", default=",".join(SCHEMES))
     ap.add_argument("--out", default="")
+    ap.add_argument("--spec", default="c2", choices=["c2", "c4"], help="c2: GPT-2 small, 512-d embeddings (configs[1]); c4: GPT-2 large, 1024-d (configs[3])")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    o = oc.CaptionOracle(oc.ModelSpec())
-    x = oc.synthetic_embeddings(5000)[: a.rows]
+    if a.spec == "c4":  # the rows of tests/golden/c4_large_mlp_full256.npz
+        o = oc.CaptionOracle(oc.ModelSpec(gpt="large", embed_dim=1024, prefix_length=10))
+        x = oc.synthetic_embeddings(256, 1024, 1)[: a.rows]
+    else:
+        o = oc.CaptionOracle(oc.ModelSpec())
+        x = oc.synthetic_embeddings(5000)[: a.rows]
     t0 = time.time()
     ref = generate(o, x, a.tokens, r_id, r_id, r_id)
     print(f"fp32 reference: {time.time() - t0:.1f}s", flush=True)
@@ -143,7 +153,7 @@ def main():
         ids = generate(o, x, a.tokens, ra, rw, rkv, head)
         same = (ids == ref).all(dim=1)
         first = torch.where((ids != ref).any(dim=1), (ids != ref).float().argmax(dim=1), torch.full((ids.shape[0],), -1))
-        rec = {"scheme": name, "rows": a.rows, "tokens": a.tokens, "captions_identical": int(same.sum()),
+        rec = {"scheme": name, "spec": a.spec, "rows": int(x.shape[0]), "tokens": a.tokens, "captions_identical": int(same.sum()),
                "match": round(float(same.float().mean()), 4), "mmas_per_product": mmas, "operand_bytes_rel": rel_bytes,
                "median_first_flip_step": int(first[first >= 0].median()) if (first >= 0).any() else None,
                "seconds": round(time.time() - t0, 1)}

@@ -1,6 +1,6 @@
 """Timing probe for the tensor-core retrieval path (CUDA events, each repetition printed)."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from gpt2_image_captioning_b200.database import _GpuFlatIndex
 dev = 'cuda:0'
