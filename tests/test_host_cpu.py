@@ -342,3 +342,52 @@ def test_rejection_rule_of_the_sampler_is_the_reference_nucleus():
                     assert np.allclose(cut, cut[0]) and (np.isclose(p, cut[0]).sum() > 1), (top_p, temperature, int(differ.sum()))
                     assert kept_rule[differ].all()  # the plateau is kept whole: a superset of the reference's set by equal-probability tokens only
                 assert kept_rule[np.argmax(p)]
+
+
+def test_host_logic_properties():
+    """Property-based checks (hypothesis) of the host logic every job goes through: the rank shards tile the rows in order and are
+    balanced; generate_batches reassembles any split into the rows' own results whatever the batch size or the number of batches in
+    flight, right-padded with EOS; the dedupe of the eval loop keeps the first position of every image id."""
+    from hypothesis import given, settings, strategies as st
+    from gpt2_image_captioning_b200 import shard_range
+    from gpt2_image_captioning_b200.evaluation import first_seen
+    from gpt2_image_captioning_b200.sharding import generate_batches
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 200000), st.integers(1, 16))
+    def shards(n, world):
+        spans = [shard_range(n, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 70), st.integers(1, 33), st.integers(1, 3), st.integers(1, 9))
+    def batches(n, batch, in_flight, max_length):
+        x = torch.arange(n, dtype=torch.float32).unsqueeze(1)
+
+        def fake_generate(e):  # row r -> r's own tokens, trimmed to a length that depends on the batch (as L_gen does)
+            L = 1 + int(e[:, 0].max().item()) % max_length
+            return (e[:, :1].long() % 1000).expand(-1, L).contiguous()
+
+        out = generate_batches(fake_generate, x, max_length, batch, eos_token_id=50256, in_flight=in_flight)
+        assert out.shape == (n, max_length)
+        for s in range(0, n, batch):
+            L = 1 + (min(n, s + batch) - 1) % max_length
+            rows = out[s:s + batch]
+            assert bool((rows[:, :L] == (torch.arange(s, min(n, s + batch)) % 1000).unsqueeze(1)).all())
+            assert bool((rows[:, L:] == 50256).all())
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.lists(st.lists(st.integers(0, 30), max_size=12), max_size=8))
+    def dedupe(id_batches):
+        seen: set = set()
+        kept = []
+        for ids in id_batches:
+            kept.extend(ids[p] for p in first_seen(ids, seen))
+        flat = [i for ids in id_batches for i in ids]
+        assert kept == list(dict.fromkeys(flat))
+
+    shards()
+    batches()
+    dedupe()
