@@ -113,9 +113,12 @@ def generate(o, x, n_tokens, ra, rw, rkv, head=None, chunk=256):
     outs = []
     for s in range(0, x.shape[0], chunk):
         xb = x[s:s + chunk]
-        # mapper: activations rounded by `ra` (input and tanh output), weights already rounded
-        h = ra(torch.tanh(ra(xb) @ mw["model.0.weight"].t() + mw["model.0.bias"]))
-        cur = (h @ mw["model.2.weight"].t() + mw["model.2.bias"]).view(xb.shape[0], o.spec.prefix_length, -1)
+        if o.spec.mapper == "mlp":
+            # mapper: activations rounded by `ra` (input and tanh output), weights already rounded
+            h = ra(torch.tanh(ra(xb) @ mw["model.0.weight"].t() + mw["model.0.bias"]))
+            cur = (h @ mw["model.2.weight"].t() + mw["model.2.bias"]).view(xb.shape[0], o.spec.prefix_length, -1)
+        else:
+            cur = o.prefix(xb)  # transformer mapper (configs[2]): kept exact here -- the screen is about the 24 GPT-2 layers behind it
         kv = [None] * w["n_layer"]
         toks = []
         step_in = cur
@@ -134,12 +137,16 @@ def main():
     ap.add_argument("--tokens", type=int, default=30)
     ap.add_argument("--schemes", default=",".join(SCHEMES))
     ap.add_argument("--out", default="")
-    ap.add_argument("--spec", default="c2", choices=["c2", "c4"], help="c2: GPT-2 small, 512-d embeddings (configs[1]); c4: GPT-2 large, 1024-d (configs[3])")
+    ap.add_argument("--spec", default="c2", choices=["c2", "c3", "c4"],
+                    help="c2: GPT-2 small, 512-d embeddings (configs[1]); c3: GPT-2 medium + transformer mapper, prefix 40 (configs[2]); c4: GPT-2 large, 1024-d (configs[3])")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
     if a.spec == "c4":  # the rows of tests/golden/c4_large_mlp_full256.npz
         o = oc.CaptionOracle(oc.ModelSpec(gpt="large", embed_dim=1024, prefix_length=10))
         x = oc.synthetic_embeddings(256, 1024, 1)[: a.rows]
+    elif a.spec == "c3":  # the rows of tests/golden/c3_medium_tfm_full256.npz
+        o = oc.CaptionOracle(oc.ModelSpec(gpt="medium", mapper="transformer", embed_dim=512, prefix_length=40, hidden_length=10, mapper_layers=8))
+        x = oc.synthetic_embeddings(256, 512, 1)[: a.rows]
     else:
         o = oc.CaptionOracle(oc.ModelSpec())
         x = oc.synthetic_embeddings(5000)[: a.rows]
