@@ -1,4 +1,5 @@
-"""CPU emulation of the engine roundings on configs[4] (RAT): the configs[1] model on the 1024 retrieval-augmented embeddings of the full-size\nretrieval fixture -> profiles/r2ag_precision_screen_c5.jsonl.   python tools/experiments/c5_precision_emulation.py"""
+"""CPU emulation of the engine roundings on configs[4] (RAT): the configs[1] model on the 1024 retrieval-augmented embeddings of the full-size
+retrieval fixture -> profiles/r2ag_precision_screen_c5.jsonl.   python tools/experiments/c5_precision_emulation.py"""
 import sys, os, json, time, numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, ROOT); os.chdir(ROOT)
 import precision_screen as ps, golden_util as gu
