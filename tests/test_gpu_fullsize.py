@@ -71,12 +71,11 @@ def test_c2_all_5000_rows_through_the_job_api(dtype, min_match):
         assert np.median(gaps) < 0.02, f"bf16x2 mismatches at large reference margins: {audits[:5]}"
 
 
-@pytest.mark.parametrize("name,rows", [("c3_medium_tfm_full32", 32), ("c4_large_mlp_full16", 16), ("c3_medium_tfm_full256", 256),
-                                       ("c4_large_mlp_full256", 256)])
+@pytest.mark.parametrize("name,rows", [("c3_medium_tfm_full32", 32), ("c4_large_mlp_full16", 16)])
 @pytest.mark.parametrize("dtype,min_match", MODES)
 def test_c3_c4_greedy_full_fixture(name, rows, dtype, min_match):
-    """configs[2] greedy (GPT-2 medium + 8-layer transformer mapper, P = 40) and configs[3] (GPT-2 large, E = 1024): the 32- / 16-row
-    files share rows with the reference-made fixtures; the 256-row files give the caption-match RATE of the deeper models."""
+    """configs[2] greedy (GPT-2 medium + 8-layer transformer mapper, P = 40, 32 rows) and configs[3] (GPT-2 large, E = 1024, 16 rows); the
+    256-row sets of the same configs are in tests/test_zz_gpu_rates.py."""
     g = gu.load(name)
     model, _, x = gpu_util.product_model(g, dtype)
     ids = model.generate(image_embeddings=x.to(DEV), max_length=30, temperature=0.0).cpu().numpy()
@@ -85,13 +84,6 @@ def test_c3_c4_greedy_full_fixture(name, rows, dtype, min_match):
     row_ok = (ids == ref).all(axis=1)
     audits = _audit_rows(g, ids, ref)
     _report(test="c3_c4_full", case=name, dtype=dtype, rows=rows, caption_match=float(row_ok.mean()), audits=audits[:8])
-    if rows >= 64:
-        # the 256-row sets report the caption-match RATE of the deeper models (profiles/r2_parity.json via tools/parity_summary.py); the
-        # floors only catch a broken engine: these models' margins are smaller than config 2's (median per-caption minimum top-2 gap
-        # 5e-3 against 7e-3), so a few more near-tie flips than on the 5 000-row set are expected
-        floor = {"fp32": 0.98, "bf16x2": 0.90, "bf16": 0.30}[dtype]
-        assert row_ok.mean() >= floor, f"{name}/{dtype}: {row_ok.mean():.4f} of {rows} captions match (floor {floor})"
-        return
     if dtype == "bf16":
         assert row_ok.mean() >= 0.4, f"{name}/bf16: {row_ok.mean():.3f}"  # (16 - 32 rows: the 5 000-row test carries the statistic)
         return
